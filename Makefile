@@ -1,0 +1,28 @@
+# Builds the product library in-tree: locarna_b200/liblocarna_b200.so (sm_100a only).
+NVCC      ?= nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unused-function -ccbin /usr/bin/g++
+SRC       := locarna_b200/csrc
+OBJ       := build/obj
+LIB       := locarna_b200/liblocarna_b200.so
+
+OBJS := $(OBJ)/kernels.o $(OBJ)/runtime.o $(OBJ)/host_model.o
+
+all: $(LIB)
+
+$(OBJ):
+	mkdir -p $(OBJ)
+
+$(OBJ)/%.o: $(SRC)/%.cu $(wildcard $(SRC)/*.h) include/locarna_b200.h | $(OBJ)
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@
+
+# host-only code: plain x86-64 code generation (no -march, no fast-math) so that the 80-bit envelope
+# arithmetic is evaluated exactly like the reference's
+$(OBJ)/%.o: $(SRC)/%.cc $(wildcard $(SRC)/*.h) | $(OBJ)
+	/usr/bin/g++ -std=c++17 -O3 -fPIC -Wall -c $< -o $@
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -cudart static -lpthread
+
+clean:
+	rm -rf build $(LIB)

@@ -1,0 +1,135 @@
+/* locarna_b200 -- C ABI of the B200-native pairwise sequence-structure alignment path.
+ *
+ * This is the drop-in boundary for the hot path of LocARNA 2.0.1 (paths below are relative to the
+ * reference tree, /root/reference):
+ *
+ *   lb200_seq_add_pp / lb200_seq_add   replace  RnaData(file, min_prob, ...)       src/LocARNA/rna_data.cc:45-68, :984-1103
+ *                                      and      BasePairs(rna_data, min_prob)      src/LocARNA/basepairs.cc:68-77, :155-205
+ *   lb200_pair_add (band == NULL)      replaces TraceController(seqA, seqB, ..)    src/LocARNA/trace_controller.cc:406-539
+ *                                      and      restrict_trace_by_probabilities    src/LocARNA/main_helper.icc:408-426
+ *   lb200_run                          replaces ArcMatches(...)                    src/LocARNA/arc_matches.cc:130-188
+ *                                               Scoring(...)/Scoring::arcmatch     src/LocARNA/scoring.cc:28-52, :441-554
+ *                                               Aligner::align()                   src/LocARNA/aligner.cc:924-962
+ *                                               Aligner::trace()                   src/LocARNA/aligner.cc:1345-1363
+ *   lb200_pair_score                   replaces the infty_score_t returned by Aligner::align()   src/LocARNA/aligner.hh:120
+ *   lb200_pair_alignment               replaces Aligner::get_alignment()           src/LocARNA/aligner.hh:105, alignment.hh:217-249
+ *   lb200_params                       carries what AlignerParams / ScoringParams / the locarna CLI pass down
+ *                                               src/LocARNA/aligner_params.hh:49-116, scoring.hh:59-166, src/locarna.cc:83-272
+ *
+ * All functions return LB200_OK (0) or a negative error code; lb200_last_error() gives the message.
+ * Nothing throws across this boundary. There is no CPU fallback: without a CUDA device
+ * lb200_ctx_create fails.
+ *
+ * Threading: a context is not thread-safe; use one context per host thread / GPU.
+ */
+#ifndef LOCARNA_B200_H
+#define LOCARNA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LB200_OK 0
+#define LB200_ERR_ARG (-1)
+#define LB200_ERR_CUDA (-2)
+#define LB200_ERR_UNSUPPORTED (-3)
+#define LB200_ERR_IO (-4)
+#define LB200_ERR_STATE (-5)
+
+/* score value used for "-inf" (InftyInt::neg_infty, src/LocARNA/infty_int.cc:7-23; printed "-inf") */
+#define LB200_SCORE_NEG_INF INT64_MIN
+
+/* lb200_run flags */
+#define LB200_RUN_SCORE_ONLY 0 /* D fill + top level score (what mlocarna's guide tree stage consumes, mlocarna:3516-3527) */
+#define LB200_RUN_TRACE 1      /* additionally trace back the alignment */
+#define LB200_RUN_KEEP_D 2     /* keep the D table for lb200_pair_arcmatches (parity tests) */
+
+typedef struct lb200_ctx lb200_ctx;
+
+typedef struct lb200_params {
+    /* heuristics (src/locarna.cc:183-200) */
+    double min_prob;              /* --min-prob / -p            0.001 */
+    int max_diff_am;              /* --max-diff-am / -D         -1 = off */
+    int max_diff_at_am;           /* --max-diff-at-am           -1 = off */
+    int max_diff;                 /* --max-diff / -d            -1 = off */
+    double min_trace_probability; /* --min-trace-probability    1e-4, 0 = off */
+    /* scoring (src/locarna.cc:99-148) */
+    int struct_weight;            /* --struct-weight / -s       200 */
+    int indel;                    /* --indel / -i               -150 */
+    int indel_opening;            /* --indel-opening            -750 */
+    int tau;                      /* --tau / -t                 50 */
+    int exclusion;                /* --exclusion / -E           0 */
+    int match, mismatch;          /* --match 50, --mismatch 0 (without ribosum, or symbols outside ACGU) */
+    int use_ribosum;              /* --use-ribosum              1 (built-in RIBOSUM85_60) */
+    int unpaired_penalty;         /* --unpaired-penalty         0 */
+    int temperature_alipf;        /* --temperature-alipf        300 (envelope partition function) */
+    /* locality / constraints (src/locarna.cc:150-181, :251-256) */
+    int no_lonely_pairs;          /* --noLP */
+    int struct_local;             /* --struct-local */
+    int sequ_local;               /* --sequ-local */
+    char free_endgaps[8];         /* --free-endgaps "----": left1 right1 left2 right2 */
+    int pf_double;                /* 1: envelope in double precision (locarna_p default) instead of long double */
+} lb200_params;
+
+typedef struct lb200_pair_info {
+    int lenA, lenB;
+    int n_arcsA, n_arcsB;
+    int64_t n_arcmatches;
+    int64_t n_tasks;
+    int64_t cells;                /* DP cell updates: sum over D-fill tasks of |box ∩ band| + top level band area */
+    int64_t n_edges;              /* alignment edges after lb200_run(LB200_RUN_TRACE) */
+} lb200_pair_info;
+
+void lb200_default_params(lb200_params *p);
+
+/* device >= 0: CUDA device ordinal. LB200_DEVICE_NONE creates a host-only context that can read inputs,
+ * derive bands and arc matches (lb200_prepare) and be inspected, but whose lb200_run fails: there is no CPU fallback. */
+#define LB200_DEVICE_NONE (-1)
+int lb200_ctx_create(int device, lb200_ctx **ctx);
+void lb200_ctx_destroy(lb200_ctx *ctx);
+const char *lb200_last_error(const lb200_ctx *ctx);
+
+/* Parameters must be set before sequences are added (min_prob filters the base pairs). */
+int lb200_set_params(lb200_ctx *ctx, const lb200_params *p);
+
+/* Add one RNA from a PP 2.0 file; returns the sequence id (>= 0) or an error code. */
+int lb200_seq_add_pp(lb200_ctx *ctx, const char *path);
+/* Add one RNA from memory: sequence (ACGU..., T is read as U) and base pairs (1-based i<j, probability). */
+int lb200_seq_add(lb200_ctx *ctx, const char *name, const char *seq, const int *pair_i, const int *pair_j, const double *pair_p,
+                  int n_pairs);
+int lb200_seq_length(const lb200_ctx *ctx, int seq);
+
+/* Add one alignment problem (A = seqA, B = seqB). min_col/max_col (lenA+1 entries each) give the band
+ * [min_col(i), max_col(i)] per row; pass NULL for both to have it derived like the reference does
+ * (--max-diff, then the probability envelope). Returns the pair id (>= 0). */
+int lb200_pair_add(lb200_ctx *ctx, int seqA, int seqB, const int *min_col, const int *max_col);
+int lb200_num_pairs(const lb200_ctx *ctx);
+int lb200_clear_pairs(lb200_ctx *ctx);
+
+/* Host-side preparation of all pairs added so far (bands, arc matches, tasks); implied by lb200_run. */
+int lb200_prepare(lb200_ctx *ctx);
+/* Align all pairs added so far on the GPU. */
+int lb200_run(lb200_ctx *ctx, int flags);
+/* device time of the last lb200_run's kernels (CUDA events on the launching stream), milliseconds */
+double lb200_last_kernel_ms(const lb200_ctx *ctx);
+/* number of kernel launches of the last lb200_run */
+int64_t lb200_last_launches(const lb200_ctx *ctx);
+
+int lb200_pair_score(const lb200_ctx *ctx, int pair, int64_t *score);
+int lb200_get_scores(const lb200_ctx *ctx, int64_t *scores, int n);
+int lb200_pair_get_info(const lb200_ctx *ctx, int pair, lb200_pair_info *info);
+int lb200_pair_band(const lb200_ctx *ctx, int pair, int *min_col, int *max_col);
+/* Arc matches in the reference's index order (arc_matches.cc:161-183) with Scoring::arcmatch and, after
+ * lb200_run(.. | LB200_RUN_KEEP_D), the D entries (LB200_SCORE_NEG_INF for -inf). Arrays hold n_arcmatches items;
+ * any may be NULL. */
+int lb200_pair_arcmatches(const lb200_ctx *ctx, int pair, int *al, int *ar, int *bl, int *br, int *score, int64_t *D);
+/* Alignment edges in order (position or -1 for a gap), and per-position structure strings
+ * (lenA+1 / lenB+1 bytes incl. NUL) as in Alignment (alignment.cc:81-118). edges arrays hold n_edges items. */
+int lb200_pair_alignment(const lb200_ctx *ctx, int pair, int *edges_a, int *edges_b, char *str_a, char *str_b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,215 @@
+"""ctypes binding of the C ABI in include/locarna_b200.h (the product's only entry point).
+
+This module deliberately contains no algorithmic code: everything is done by
+``liblocarna_b200.so`` (host C++ + sm_100a CUDA kernels). If the library is missing or no CUDA
+device is present the calls fail loudly; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblocarna_b200.so")
+
+OK = 0
+DEVICE_NONE = -1
+RUN_SCORE_ONLY, RUN_TRACE, RUN_KEEP_D = 0, 1, 2
+SCORE_NEG_INF = -(2 ** 63)
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("min_prob", C.c_double), ("max_diff_am", C.c_int), ("max_diff_at_am", C.c_int), ("max_diff", C.c_int),
+        ("min_trace_probability", C.c_double),
+        ("struct_weight", C.c_int), ("indel", C.c_int), ("indel_opening", C.c_int), ("tau", C.c_int), ("exclusion", C.c_int),
+        ("match", C.c_int), ("mismatch", C.c_int), ("use_ribosum", C.c_int), ("unpaired_penalty", C.c_int),
+        ("temperature_alipf", C.c_int),
+        ("no_lonely_pairs", C.c_int), ("struct_local", C.c_int), ("sequ_local", C.c_int),
+        ("free_endgaps", C.c_char * 8), ("pf_double", C.c_int),
+    ]
+
+
+class PairInfo(C.Structure):
+    _fields_ = [("lenA", C.c_int), ("lenB", C.c_int), ("n_arcsA", C.c_int), ("n_arcsB", C.c_int),
+                ("n_arcmatches", C.c_int64), ("n_tasks", C.c_int64), ("cells", C.c_int64), ("n_edges", C.c_int64)]
+
+
+EXPORTS = [
+    "lb200_default_params", "lb200_ctx_create", "lb200_ctx_destroy", "lb200_last_error", "lb200_set_params",
+    "lb200_seq_add_pp", "lb200_seq_add", "lb200_seq_length", "lb200_pair_add", "lb200_num_pairs", "lb200_clear_pairs",
+    "lb200_prepare", "lb200_run", "lb200_last_kernel_ms", "lb200_last_launches", "lb200_pair_score", "lb200_get_scores",
+    "lb200_pair_get_info", "lb200_pair_band", "lb200_pair_arcmatches", "lb200_pair_alignment",
+]
+
+_lib = None
+
+
+def load():
+    """Load liblocarna_b200.so; raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("liblocarna_b200.so is missing (%s); build it with `make` - there is no fallback path" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, ip, dp, i64p = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_int64)
+    lib.lb200_default_params.argtypes = [C.POINTER(Params)]
+    lib.lb200_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.lb200_ctx_destroy.argtypes = [vp]
+    lib.lb200_last_error.argtypes = [vp]
+    lib.lb200_last_error.restype = C.c_char_p
+    lib.lb200_set_params.argtypes = [vp, C.POINTER(Params)]
+    lib.lb200_seq_add_pp.argtypes = [vp, C.c_char_p]
+    lib.lb200_seq_add.argtypes = [vp, C.c_char_p, C.c_char_p, ip, ip, dp, C.c_int]
+    lib.lb200_seq_length.argtypes = [vp, C.c_int]
+    lib.lb200_pair_add.argtypes = [vp, C.c_int, C.c_int, ip, ip]
+    lib.lb200_num_pairs.argtypes = [vp]
+    lib.lb200_clear_pairs.argtypes = [vp]
+    lib.lb200_prepare.argtypes = [vp]
+    lib.lb200_run.argtypes = [vp, C.c_int]
+    lib.lb200_last_kernel_ms.argtypes = [vp]
+    lib.lb200_last_kernel_ms.restype = C.c_double
+    lib.lb200_last_launches.argtypes = [vp]
+    lib.lb200_last_launches.restype = C.c_int64
+    lib.lb200_pair_score.argtypes = [vp, C.c_int, i64p]
+    lib.lb200_get_scores.argtypes = [vp, i64p, C.c_int]
+    lib.lb200_pair_get_info.argtypes = [vp, C.c_int, C.POINTER(PairInfo)]
+    lib.lb200_pair_band.argtypes = [vp, C.c_int, ip, ip]
+    lib.lb200_pair_arcmatches.argtypes = [vp, C.c_int, ip, ip, ip, ip, ip, i64p]
+    lib.lb200_pair_alignment.argtypes = [vp, C.c_int, ip, ip, C.c_char_p, C.c_char_p]
+    _lib = lib
+    return lib
+
+
+# reference CLI flag name -> lb200_params field
+FLAG_FIELDS = {
+    "min-prob": "min_prob", "max-diff-am": "max_diff_am", "max-diff-at-am": "max_diff_at_am", "max-diff": "max_diff",
+    "min-trace-probability": "min_trace_probability", "noLP": "no_lonely_pairs", "struct-local": "struct_local",
+    "sequ-local": "sequ_local", "struct-weight": "struct_weight", "indel": "indel", "indel-opening": "indel_opening",
+    "tau": "tau", "exclusion": "exclusion", "match": "match", "mismatch": "mismatch",
+    "temperature-alipf": "temperature_alipf", "unpaired-penalty": "unpaired_penalty", "pf-double": "pf_double",
+}
+
+
+def make_params(flags: dict | None = None) -> Params:
+    p = Params()
+    load().lb200_default_params(C.byref(p))
+    for k, v in (flags or {}).items():
+        if k == "free-endgaps":
+            p.free_endgaps = v.encode()
+        elif k == "no-ribosum":
+            p.use_ribosum = 0 if v else 1
+        else:
+            setattr(p, FLAG_FIELDS[k], int(v) if isinstance(v, bool) else v)
+    return p
+
+
+class Error(RuntimeError):
+    pass
+
+
+class Context:
+    """One GPU context: sequences are uploaded once, pairs are batched, `run` aligns them all."""
+
+    def __init__(self, device: int = 0, flags: dict | None = None):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.lb200_ctx_create(device, C.byref(h))
+        if rc != OK:
+            raise Error("lb200_ctx_create failed with code %d (no CUDA device? there is no CPU fallback)" % rc)
+        self.h = h
+        if flags is not None:
+            self.set_params(flags)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lb200_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc < 0:
+            raise Error("locarna_b200 error %d: %s" % (rc, self.lib.lb200_last_error(self.h).decode()))
+        return rc
+
+    def set_params(self, flags: dict):
+        p = make_params(flags)
+        self._chk(self.lib.lb200_set_params(self.h, C.byref(p)))
+
+    def add_pp(self, path: str) -> int:
+        return self._chk(self.lib.lb200_seq_add_pp(self.h, path.encode()))
+
+    def add_seq(self, name: str, seq: str, pairs) -> int:
+        n = len(pairs)
+        ai = (C.c_int * max(n, 1))(*[p[0] for p in pairs])
+        aj = (C.c_int * max(n, 1))(*[p[1] for p in pairs])
+        ap = (C.c_double * max(n, 1))(*[p[2] for p in pairs])
+        return self._chk(self.lib.lb200_seq_add(self.h, name.encode(), seq.encode(), ai, aj, ap, n))
+
+    def add_pair(self, a: int, b: int, band=None) -> int:
+        if band is None:
+            return self._chk(self.lib.lb200_pair_add(self.h, a, b, None, None))
+        lo, hi = band
+        return self._chk(self.lib.lb200_pair_add(self.h, a, b, (C.c_int * len(lo))(*lo), (C.c_int * len(hi))(*hi)))
+
+    def clear_pairs(self):
+        self._chk(self.lib.lb200_clear_pairs(self.h))
+
+    def prepare(self):
+        self._chk(self.lib.lb200_prepare(self.h))
+
+    def run(self, flags: int = RUN_SCORE_ONLY):
+        self._chk(self.lib.lb200_run(self.h, flags))
+
+    @property
+    def kernel_ms(self) -> float:
+        return self.lib.lb200_last_kernel_ms(self.h)
+
+    @property
+    def launches(self) -> int:
+        return self.lib.lb200_last_launches(self.h)
+
+    def num_pairs(self) -> int:
+        return self._chk(self.lib.lb200_num_pairs(self.h))
+
+    def scores(self):
+        n = self.num_pairs()
+        out = (C.c_int64 * max(n, 1))()
+        self._chk(self.lib.lb200_get_scores(self.h, out, n))
+        return [None if out[k] == SCORE_NEG_INF else out[k] for k in range(n)]
+
+    def info(self, pair: int) -> PairInfo:
+        inf = PairInfo()
+        self._chk(self.lib.lb200_pair_get_info(self.h, pair, C.byref(inf)))
+        return inf
+
+    def band(self, pair: int):
+        n = self.info(pair).lenA + 1
+        lo, hi = (C.c_int * n)(), (C.c_int * n)()
+        self._chk(self.lib.lb200_pair_band(self.h, pair, lo, hi))
+        return list(lo), list(hi)
+
+    def arcmatches(self, pair: int, with_D: bool = False):
+        K = self.info(pair).n_arcmatches
+        arrs = [(C.c_int * max(K, 1))() for _ in range(5)]
+        D = (C.c_int64 * max(K, 1))() if with_D else None
+        self._chk(self.lib.lb200_pair_arcmatches(self.h, pair, *arrs, D))
+        am = [tuple(a[k] for a in arrs[:4]) for k in range(K)]
+        score = [arrs[4][k] for k in range(K)]
+        if with_D:
+            return am, score, [None if D[k] == SCORE_NEG_INF else D[k] for k in range(K)]
+        return am, score
+
+    def alignment(self, pair: int):
+        inf = self.info(pair)
+        n = inf.n_edges
+        ea, eb = (C.c_int * max(n, 1))(), (C.c_int * max(n, 1))()
+        sa, sb = C.create_string_buffer(inf.lenA + 2), C.create_string_buffer(inf.lenB + 2)
+        self._chk(self.lib.lb200_pair_alignment(self.h, pair, ea, eb, sa, sb))
+        return [(ea[k], eb[k]) for k in range(n)], sa.value.decode(), sb.value.decode()

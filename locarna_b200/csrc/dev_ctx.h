@@ -1,0 +1,28 @@
+// Kernel argument block: raw device pointers into the batch arrays (see dev_types.h).
+#ifndef LB200_DEV_CTX_H
+#define LB200_DEV_CTX_H
+#include "dev_types.h"
+
+#define LB_MAX_NC 16      // diagonal pairs per lane: one warp covers up to 64*16 = 1024 band diagonals
+
+struct DevCtx {
+    DevParams params;
+    const DevPair *pairs;
+    const uint8_t *codes;
+    const int *band_lo, *band_hi;
+    const int *sptr;
+    const DevEntry *ent;     // S-order
+    int *dval;               // D(arcA,arcB) in S-order
+    const DevArcMatch *am;   // L-order
+    const DevTask *tasks;
+    DevTopResult *top;
+    int *scratch;            // per-CTA M box spill area (L2 resident)
+    int scratch_words;
+    int smem_words;          // dynamic shared memory per CTA in words
+    int max_rows;            // rowinfo capacity (words)
+    int max_cols_padded;     // colinfo capacity (bytes, multiple of 4)
+    int arcbuf_words;        // RING * 32 * NCmax
+    int *error_flag;
+};
+
+#endif

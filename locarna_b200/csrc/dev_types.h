@@ -1,0 +1,69 @@
+// Device-side data layout shared by the host runtime (ctx.cu) and the kernels (kernels.cu).
+// All per-pair arrays live in a few large HBM allocations; DevPair holds the offsets.
+#ifndef LB200_DEV_TYPES_H
+#define LB200_DEV_TYPES_H
+#include <stdint.h>
+
+// -inf encoding for 32-bit scores. The reference uses 64-bit scores with -inf = LONG_MIN/5*2 and
+// only normalises on store (infty_int.hh:39-60, :374-388); only finiteness and finite values are
+// observable.  Here: finite values satisfy |v| < 2^27, every "-inf-like" value stays below
+// LB_NEG_LIMIT, and the sum of two of them does not overflow int32 (see DESIGN.md "-inf in 32 bits").
+#define LB_NEG (-0x20000000)        // -2^29
+#define LB_NEG_LIMIT (-0x10000000)  // anything below is -inf
+
+#define LB_MAXLEN 4095              // positions are packed into 12 bits
+#define LB_CODE_N 17                // symbol code of 'N' (codes: A C G U = 0..3, other capitals 4 + c - 'A', rest 30)
+
+// scoring parameters that the kernels need (single sequences: position independent gap cost)
+struct DevParams {
+    int gap;          // gapA(i) = gapB(j) = indel - unpaired_penalty     (scoring.cc:272-311, :64-74)
+    int gap_open;     // gap + indel_opening
+    int open;         // indel_opening
+    int exclusion;
+    int no_lonely_pairs, struct_local, sequ_local;
+    int fe_left1, fe_right1, fe_left2, fe_right2;  // free_endgaps.hh:42-70
+    int sigma4[16];   // base match score for A C G U (codes 0..3), unpaired penalty applied (scoring.cc:141-198)
+    int match_ext, mismatch_ext, n_ext;            // symbols outside ACGU: identical / different / either is 'N' (scoring.cc:186-191)
+};
+
+// one sequence-structure alignment problem
+struct DevPair {
+    int lenA, lenB;
+    int codesA, codesB;   // offsets into codes[] (1-based position p at codes[off + p])
+    int band;             // offset into band_lo[] / band_hi[] (entries 0..lenA)
+    int sptr;             // offset into sptr[] (entries 0..lenA+lenB+1): S-order start per anti-diagonal ar+br
+    int K;                // number of arc matches
+    int pad;
+    long long am_base;    // offset of this pair's arc matches in the L-order and S-order arrays
+};
+
+// S-order entry: one valid arc match, sorted by (ar+br, ar, al desc, bl desc)
+//   x = (al-1) | (bl-1) << 12         source cell of the recurrence M(al-1, bl-1) + D
+//   y = ar | br << 12                 target cell
+struct DevEntry { uint32_t x, y; };
+
+// L-order record: arc matches grouped by common left ends (al desc, bl desc, ar asc, br asc)
+struct DevArcMatch {
+    uint32_t ends_a;   // al | ar << 12
+    uint32_t ends_b;   // bl | br << 12
+    int score;         // Scoring::arcmatch(am) (scoring.cc:441-485)
+    int spos;          // position in S-order (relative to am_base)
+    int inner;         // L-order index of the inner arc match (al+1,ar-1,bl+1,br-1) or -1
+};
+
+// one D-fill task: all arc matches with common left ends (arc_matches.cc:313-355, aligner.cc:660-732)
+struct DevTask {
+    int pair;
+    short al, bl;      // origin of the M box (no-lonely-pairs mode: inner left ends)
+    short R, C;        // last row / column of the box (max right end - 1)
+    int run_start;     // L-order range of the arc matches whose D entries this task defines
+    int run_count;
+};
+
+struct DevTopResult {
+    int score;         // LB_NEG.. if -inf
+    int max_i, max_j;
+    int pad;
+};
+
+#endif

@@ -1,0 +1,439 @@
+// Host-side problem model (see host_model.h). Each function names the reference code whose observable
+// behaviour it reproduces (paths relative to /root/reference/src/LocARNA).
+#include "host_model.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <unordered_map>
+
+#include "ribosum85_60_tables.h"
+
+namespace lb200 {
+
+static inline long round2score(double d) { return (long)((d < 0) ? (d - 0.5) : (d + 0.5)); }  // scoring.hh:384-387
+
+// symbol codes: A C G U -> 0..3, other capital letters -> 4 + (c - 'A'), anything else -> 30
+static inline uint8_t symbol_code(char c) {
+    switch (c) {
+        case 'A': return 0;
+        case 'C': return 1;
+        case 'G': return 2;
+        case 'U': return 3;
+        default: return (c >= 'A' && c <= 'Z') ? (uint8_t)(4 + (c - 'A')) : (uint8_t)30;
+    }
+}
+static const uint8_t CODE_N = LB_CODE_N;
+static_assert(LB_CODE_N == 4 + ('N' - 'A'), "symbol code of N");
+
+// ---------------------------------------------------------------------------------- input
+// Line discipline of the reference reader: lines that are empty or start with white space are
+// comments, trailing blanks are dropped (aux.cc:122-145).
+static bool next_line(std::istream &in, std::string &line) {
+    while (std::getline(in, line)) {
+        if (line.empty() || isspace((unsigned char)line[0])) continue;
+        size_t e = line.find_last_not_of(" \t\r");
+        line.erase(e + 1);
+        return true;
+    }
+    return false;
+}
+
+static bool begins(const std::string &s, const char *p) { return s.compare(0, strlen(p), p) == 0; }
+
+// rna_data.cc:984-1103 (PP 2.0), multiple_alignment.cc:279-401 (sequence block), aux.cc:65-70
+bool read_pp(const std::string &path, double p_bpcut, Sequence &out, std::string &err) {
+    std::ifstream in(path.c_str());
+    if (!in) { err = "cannot open " + path; return false; }
+    std::string line;
+    std::getline(in, line);
+    if (!begins(line, "#PP 2")) { err = path + ": not in PP 2.0 format"; return false; }
+    std::string name, seq;
+    bool named = false;
+    while (next_line(in, line)) {
+        if (line[0] == '#') {
+            if (begins(line, "#END")) break;
+            if (begins(line, "#A")) { err = path + ": anchor constraints are not supported by the B200 path"; return false; }
+            continue;
+        }
+        std::istringstream ls(line);
+        std::string n, s;
+        ls >> n >> s;
+        if (!named) { name = n; named = true; }
+        else if (n != name) { err = path + ": alignments (several rows) are not supported by the B200 path yet"; return false; }
+        seq += s;
+    }
+    if (!next_line(in, line) || line != "#SECTION BASEPAIRS") { err = path + ": Expected base pair section header."; return false; }
+    std::vector<int> pi, pj;
+    std::vector<double> pp;
+    double cut = p_bpcut;
+    // #BPCUT may raise the cutoff at any point of the section; it applies to the lines after it (rna_data.cc:1047-1078)
+    std::vector<double> cut_at;
+    while (next_line(in, line)) {
+        if (line[0] == '#') {
+            if (begins(line, "#END")) break;
+            if (begins(line, "#BPCUT")) {
+                std::istringstream ls(line);
+                std::string d; double p;
+                ls >> d >> p;
+                if (ls.fail()) { err = "Cannot parse line \"" + line + "\" in base pairs section."; return false; }
+                cut = std::max(p, cut);
+            }
+            continue;
+        }
+        std::istringstream ls(line);
+        long i, j; double p;
+        ls >> i >> j >> p;
+        if (ls.fail()) { err = "Cannot parse line \"" + line + "\" in base pairs section."; return false; }
+        if (!(1 <= i && i < j && j <= (long)seq.size())) { err = "Invalid indices in PP input line \"" + line + "\"."; return false; }
+        if (p <= cut) continue;
+        pi.push_back((int)i); pj.push_back((int)j); pp.push_back(p);
+    }
+    // the pairs were already filtered line by line; pass a cutoff that keeps them all
+    return make_sequence(name, seq, pi.data(), pj.data(), pp.data(), (int)pi.size(), -1.0, out, err);
+}
+
+bool make_sequence(const std::string &name, const std::string &seq, const int *pi, const int *pj, const double *pp, int npairs,
+                   double p_bpcut, Sequence &out, std::string &err) {
+    out = Sequence();
+    out.name = name;
+    out.seq = seq;
+    for (auto &c : out.seq) { c = (char)toupper((unsigned char)c); if (c == 'T') c = 'U'; }
+    out.len = (int)out.seq.size();
+    if (out.len > LB_MAXLEN) { err = "sequence longer than 4095 positions"; return false; }
+    out.codes.assign(out.len + 1, 0);
+    for (int i = 1; i <= out.len; i++) out.codes[i] = symbol_code(out.seq[i - 1]);
+    out.cutoff = p_bpcut;
+    std::map<std::pair<int, int>, double> uniq;  // a repeated pair overwrites the earlier value (sparse matrix assignment)
+    for (int k = 0; k < npairs; k++) {
+        if (!(1 <= pi[k] && pi[k] < pj[k] && pj[k] <= out.len)) { err = "invalid base pair indices"; return false; }
+        if (pp[k] <= p_bpcut) continue;
+        uniq[std::make_pair(pi[k], pj[k])] = pp[k];
+    }
+    for (auto &kv : uniq) { out.pp_i.push_back(kv.first.first); out.pp_j.push_back(kv.first.second); out.pp_p.push_back(kv.second); }
+    return true;
+}
+
+// basepairs.cc:155-205: arcs (i,j), j >= i+3, p >= min_prob, indexed in loop order i = len-3..1, j = i+3..len;
+// rna_data.cc:713-732: paired upstream/downstream mass, summed over ascending partner position
+void finish_sequence(Sequence &s, double min_prob) {
+    const int n = s.len;
+    std::vector<int> order;
+    for (size_t k = 0; k < s.pp_i.size(); k++)
+        if (s.pp_j[k] >= s.pp_i[k] + 3 && s.pp_p[k] >= min_prob) order.push_back((int)k);
+    std::sort(order.begin(), order.end(), [&](int x, int y) {
+        if (s.pp_i[x] != s.pp_i[y]) return s.pp_i[x] > s.pp_i[y];
+        return s.pp_j[x] < s.pp_j[y];
+    });
+    s.arcs.clear(); s.arc_prob.clear();
+    s.lptr.assign(n + 2, 0); s.lcount.assign(n + 2, 0);
+    for (int k : order) {
+        int l = s.pp_i[k];
+        if (s.lcount[l] == 0) s.lptr[l] = (int)s.arcs.size();
+        s.lcount[l]++;
+        s.arcs.push_back(Arc{s.pp_i[k], s.pp_j[k]});
+        s.arc_prob.push_back(s.pp_p[k]);
+    }
+    // pp_* is sorted by (i, j) ascending (std::map order)
+    s.p_up.assign(n + 1, 0.0); s.p_down.assign(n + 1, 0.0);
+    for (size_t k = 0; k < s.pp_i.size(); k++) s.p_up[s.pp_i[k]] += s.pp_p[k];  // fixed i: j ascending
+    {
+        std::vector<int> idx(s.pp_i.size());
+        for (size_t k = 0; k < idx.size(); k++) idx[k] = (int)k;
+        std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) {
+            if (s.pp_j[x] != s.pp_j[y]) return s.pp_j[x] < s.pp_j[y];
+            return s.pp_i[x] < s.pp_i[y];
+        });
+        for (int k : idx) s.p_down[s.pp_j[k]] += s.pp_p[k];  // fixed right end: left partner ascending
+    }
+}
+
+// scoring.cc:201-265 (probToWeight with p_exp = 1/(2 len), aux.hh:216-220)
+std::vector<int> arc_weights(const Sequence &s, const Params &p) {
+    std::vector<int> w(s.arcs.size());
+    const double pe = 1.0 / (2.0 * s.len);
+    for (size_t k = 0; k < w.size(); k++) w[k] = (int)round2score(round(p.struct_weight * (1 - log(s.arc_prob[k]) / log(pe))));
+    return w;
+}
+
+// scoring.cc:141-198 (sigma_ for single sequences), :64-74 (unpaired penalty), :369-485 (arc match sequence term)
+void make_score_tables(const Params &p, ScoreTables &t) {
+    memset(&t, 0, sizeof t);
+    for (int a = 0; a < 4; a++)
+        for (int b = 0; b < 4; b++) {
+            long s = p.use_ribosum ? RIBOSUM85_60_SIGMA4[a * 4 + b] : (a == b ? p.match : p.mismatch);
+            t.dev.sigma4[a * 4 + b] = (int)s - 2 * p.unpaired_penalty;
+        }
+    t.match_ext = p.match - 2 * p.unpaired_penalty;
+    t.mismatch_ext = p.mismatch - 2 * p.unpaired_penalty;
+    t.n_ext = -2 * p.unpaired_penalty;
+    for (int x = 0; x < 16; x++)
+        for (int y = 0; y < 16; y++) t.am_seq[x * 16 + y] = (int)(((long)p.tau * RIBOSUM85_60_AM16[x * 16 + y]) / 100);
+    DevParams &d = t.dev;
+    d.gap = p.indel - p.unpaired_penalty;
+    d.open = p.indel_opening;
+    d.gap_open = d.gap + d.open;
+    d.exclusion = p.exclusion;
+    d.no_lonely_pairs = p.no_lonely_pairs; d.struct_local = p.struct_local; d.sequ_local = p.sequ_local;
+    d.fe_left1 = p.fe_left1; d.fe_right1 = p.fe_right1; d.fe_left2 = p.fe_left2; d.fe_right2 = p.fe_right2;
+    d.match_ext = t.match_ext; d.mismatch_ext = t.mismatch_ext; d.n_ext = t.n_ext;
+}
+
+int base_match_score(const ScoreTables &t, uint8_t a, uint8_t b) {
+    if (a < 4 && b < 4) return t.dev.sigma4[a * 4 + b];
+    if (a == CODE_N || b == CODE_N) return t.n_ext;
+    return a == b ? t.match_ext : t.mismatch_ext;
+}
+
+int arcmatch_score(const ScoreTables &t, const Params &p, const Sequence &A, const Sequence &B, int a, int b, const std::vector<int> &wA,
+                   const std::vector<int> &wB) {
+    const Arc &x = A.arcs[a], &y = B.arcs[b];
+    long seqc = 0;
+    if (p.tau != 0) {
+        const uint8_t c1 = A.codes[x.left], c2 = A.codes[x.right], c3 = B.codes[y.left], c4 = B.codes[y.right];
+        if (p.use_ribosum) {
+            if (c1 < 4 && c2 < 4 && c3 < 4 && c4 < 4) return t.am_seq[(c1 * 4 + c2) * 16 + c3 * 4 + c4] + wA[a] + wB[b];
+            seqc = 0;
+        } else seqc = (long)base_match_score(t, c1, c3) + base_match_score(t, c2, c4);
+    }
+    return (int)(((long)p.tau * seqc) / 100) + wA[a] + wB[b];
+}
+
+// ---------------------------------------------------------------------------------- band
+// trace_controller.cc:406-424 and constrain_wo_ref :360-390 (unsigned 64-bit arithmetic as in the reference)
+Band make_band(int lenA, int lenB, int max_diff) {
+    Band b;
+    b.lenA = lenA; b.lenB = lenB;
+    b.lo.assign(lenA + 1, 0); b.hi.assign(lenA + 1, lenB);
+    if (max_diff == -1 || lenA == 0 || lenB == 0) return b;
+    const uint64_t A = lenA, B = lenB, d = (uint64_t)max_diff;
+    for (uint64_t i = 0; i <= A; i++) {
+        uint64_t x = i * B * (A + B), y = 2 * d * A * B, z = A * (A + B);
+        if (A > B) y = std::max(y, (A + B) * A / 2);
+        else if (B > A) y = std::max(y, (A + B) * B / 2);
+        b.lo[i] = x > y ? (int)((x - y + z - 1) / z) : 0;
+        b.hi[i] = (int)std::min((x + y) / z, B);
+    }
+    return b;
+}
+
+namespace {
+
+// STRAL-like position score of the sequence-only partition function (stral_score.cc:29-60);
+// sim = ribosum base match scores (main_helper.icc:291-293) or match/mismatch (:300-306)
+struct EnvScore {
+    const Sequence *A, *B;
+    bool rev = false;
+    double sw, match, mismatch;
+    bool ribo;
+    double up(const Sequence &s, int i) const { return rev ? s.p_down[s.len + 1 - i] : s.p_up[i]; }
+    double down(const Sequence &s, int i) const { return rev ? s.p_up[s.len + 1 - i] : s.p_down[i]; }
+    uint8_t code(const Sequence &s, int i) const { return s.codes[rev ? s.len + 1 - i : i]; }
+    double sigma(int i, int j) const {
+        double seq_score = 0;
+        const uint8_t a = code(*A, i), b = code(*B, j);
+        if (a < 4 && b < 4) { seq_score += ribo ? RIBOSUM85_60_BM[a * 4 + b] : (a == b ? match : mismatch); seq_score /= 1; }
+        double res = sw * (sqrt(down(*A, i) * down(*B, j)) + sqrt(up(*A, i) * up(*B, j))) + seq_score;
+        return res;
+    }
+};
+
+template <class T> struct Grid {
+    size_t cols = 0;
+    std::vector<T> v;
+    void reset(size_t r, size_t c) { cols = c; v.assign(r * c, T(0)); }
+    T &operator()(size_t i, size_t j) { return v[i * cols + j]; }
+};
+
+// edge_probs.icc:76-162, evaluated in the same order and with the same operand types
+template <class T>
+void gotoh_pf(Grid<T> &zM, Grid<T> &zA, Grid<T> &zB, const std::vector<int> &lo, const std::vector<int> &hi, size_t lenA, size_t lenB,
+              const EnvScore &sc, double open, double ext, double temp, bool free_left1, bool free_left2, bool local) {
+    const double g_open = exp(open / temp);
+    const double g_ext = exp(ext / temp);
+    zM.reset(lenA + 1, lenB + 1); zA.reset(lenA + 1, lenB + 1); zB.reset(lenA + 1, lenB + 1);
+    auto valid = [&](size_t i, size_t j) { return (size_t)lo[i] <= j && j <= (size_t)hi[i]; };
+    if (valid(0, 0)) zM(0, 0) = local ? 0 : 1;
+    if (lenA > 0 && valid(1, 0)) zA(1, 0) = g_open * g_ext;
+    if (lenB > 0 && valid(0, 1)) zB(0, 1) = g_open * g_ext;
+    for (size_t i = 2; i <= lenA; i++) {
+        if (lo[i] > 0) break;
+        zA(i, 0) = zA(i - 1, 0) * g_ext;
+    }
+    for (size_t j = std::max((size_t)lo[0], (size_t)2); j <= std::min((size_t)hi[0], lenB); j++) zB(0, j) = zB(0, j - 1) * g_ext;
+    if (free_left2) for (size_t i = 1; i <= lenA; i++) zA(i, 0) += 1;
+    if (free_left1) for (size_t j = 1; j <= lenB; j++) zB(0, j) += 1;
+    for (size_t i = 1; i <= lenA; i++) {
+        for (size_t j = std::max((size_t)lo[i], (size_t)1); j <= std::min((size_t)hi[i], lenB); j++) {
+            double match_score_ij = sc.sigma((int)i, (int)j);
+            double match_ij = exp(match_score_ij / temp);
+            zM(i, j) = zM(i - 1, j - 1) * match_ij + zA(i - 1, j - 1) * match_ij + zB(i - 1, j - 1) * match_ij + (local ? match_ij : 0);
+            zA(i, j) = zA(i - 1, j) * g_ext + zM(i - 1, j) * g_open * g_ext + zB(i - 1, j) * g_open * g_ext;
+            zB(i, j) = zB(i, j - 1) * g_ext + zM(i, j - 1) * g_open * g_ext + zA(i, j - 1) * g_open * g_ext;
+        }
+    }
+}
+
+// edge_probs.icc:7-60 + :212-268 (trace probabilities), trace_controller.cc:565-597 (threshold + monotone closure)
+template <class T>
+void envelope_impl(Band &band, const Sequence &A, const Sequence &B, const Params &p) {
+    const size_t lenA = A.len, lenB = B.len;
+    EnvScore sc;
+    sc.A = &A; sc.B = &B; sc.sw = p.struct_weight / 100.0; sc.match = p.match; sc.mismatch = p.mismatch; sc.ribo = p.use_ribosum;
+    const double open = p.indel_opening / 100.0, ext = p.indel / 100.0, temp = p.temperature_alipf / 100.0;
+    const bool local = p.sequ_local;
+    Grid<T> zM, zA, zB, zMr, zAr, zBr;
+    gotoh_pf<T>(zM, zA, zB, band.lo, band.hi, lenA, lenB, sc, open, ext, temp, p.fe_left1, p.fe_left2, local);
+    // reversed problem: reversed sequences, up/down swapped, band mirrored, free end gaps swapped
+    std::vector<int> rlo(lenA + 1), rhi(lenA + 1);
+    for (size_t i = 0; i <= lenA; i++) { rhi[lenA - i] = (int)lenB - band.lo[i]; rlo[lenA - i] = (int)lenB - band.hi[i]; }
+    sc.rev = true;
+    gotoh_pf<T>(zMr, zAr, zBr, rlo, rhi, lenA, lenB, sc, open, ext, temp, p.fe_right1, p.fe_right2, local);
+    T z;
+    if (local) {
+        z = 1;
+        for (size_t i = 0; i <= lenA; i++)
+            for (size_t j = 0; j <= lenB; j++) z += zM(i, j);
+    } else {
+        z = zM(lenA, lenB) + zA(lenA, lenB) + zB(lenA, lenB);
+        if (p.fe_left2) for (size_t i = 0; i <= lenA; i++) z += zA(i, lenB);
+        if (p.fe_left1) for (size_t j = 0; j <= lenB; j++) z += zB(lenA, j);
+    }
+    const double locality_add = local ? 1 : 0;
+    const double g_open = exp(open / temp);
+    for (size_t i = 0; i <= lenA; i++) {
+        int new_min = band.hi[i], new_max = band.lo[i];
+        for (size_t j = (size_t)std::max(band.lo[i], 0); j <= std::min((size_t)band.hi[i], lenB); j++) {
+            const size_t ri = lenA - i, rj = lenB - j;
+            T z_ij = zM(i, j) * (zMr(ri, rj) + zAr(ri, rj) + zBr(ri, rj) + locality_add) +
+                     zA(i, j) * (zMr(ri, rj) + zAr(ri, rj) / g_open + zBr(ri, rj)) +
+                     zB(i, j) * (zMr(ri, rj) + zAr(ri, rj) + zBr(ri, rj) / g_open);
+            const double pr = (double)(z_ij / z);
+            if (pr >= p.min_trace_probability) { new_min = std::min(new_min, (int)j); new_max = std::max(new_max, (int)j); }
+        }
+        band.lo[i] = std::max(band.lo[i], new_min);
+        band.hi[i] = std::min(band.hi[i], new_max);
+    }
+    int run = 0;
+    for (size_t i = 0; i <= lenA; i++) { band.hi[i] = std::max(band.hi[i], run); run = band.hi[i]; }
+    run = band.hi[lenA];
+    for (size_t i = lenA + 1; i-- > 0;) { band.lo[i] = std::min(band.lo[i], run); run = band.lo[i]; }
+}
+
+}  // namespace
+
+void restrict_band_by_envelope(Band &band, const Sequence &A, const Sequence &B, const Params &p) {
+    if (!(p.min_trace_probability > 0.0)) return;  // main_helper.icc:416
+    if (p.pf_double) envelope_impl<double>(band, A, B, p);
+    else envelope_impl<long double>(band, A, B, p);  // locarna.cc:384-391: extended precision is forced
+}
+
+// ---------------------------------------------------------------------------------- arc matches, tasks
+// arc_matches.cc:19-48 (validity), :130-188 (enumeration), :50-74 (inner arc matches), :313-355 (max right ends);
+// aligner.cc:660-732 (task = left end pair)
+void build_pair_problem(const Sequence &A, const Sequence &B, const Band &band, const Params &p, const ScoreTables &t, PairProblem &out) {
+    out = PairProblem();
+    const int n = A.len, m = B.len;
+    const std::vector<int> &lo = band.lo, &hi = band.hi;
+    auto valid = [&](int i, int j) { return lo[i] <= j && j <= hi[i]; };
+    auto valid_match = [&](int i, int j) { return i >= 1 && j >= 1 && valid(i, j) && valid(i - 1, j - 1); };
+    const long mdam = p.max_diff_am != -1 ? p.max_diff_am : std::max(n, m);
+    const long mdat = p.max_diff_at_am != -1 ? p.max_diff_at_am : std::max(n, m);
+    const std::vector<int> wA = arc_weights(A, p), wB = arc_weights(B, p);
+
+    struct Run { int start, count; };
+    std::unordered_map<int, Run> runs;  // key al * 4096 + bl
+    std::vector<int> run_keys;
+    for (int al = n; al >= 1; al--) {
+        if (A.lcount[al] == 0) continue;
+        for (int bl = std::min(hi[al], m); bl >= std::max(lo[al], 1); bl--) {
+            if (B.lcount[bl] == 0 || !valid_match(al, bl)) continue;
+            if (std::abs(al - bl) > mdat) continue;
+            const int start = (int)out.am.size();
+            for (int a = A.lptr[al]; a < A.lptr[al] + A.lcount[al]; a++) {
+                const int ar = A.arcs[a].right;
+                for (int b = B.lptr[bl]; b < B.lptr[bl] + B.lcount[bl]; b++) {
+                    const int br = B.arcs[b].right;
+                    if (!valid_match(ar, br)) continue;
+                    if (std::labs((long)(ar - al) - (long)(br - bl)) > mdam) continue;
+                    if (std::abs(ar - br) > mdat) continue;
+                    DevArcMatch x;
+                    x.ends_a = (uint32_t)al | ((uint32_t)ar << 12);
+                    x.ends_b = (uint32_t)bl | ((uint32_t)br << 12);
+                    x.score = arcmatch_score(t, p, A, B, a, b, wA, wB);
+                    x.spos = -1; x.inner = -1;
+                    out.am.push_back(x); out.am_a.push_back(a); out.am_b.push_back(b);
+                }
+            }
+            const int cnt = (int)out.am.size() - start;
+            if (cnt > 0) { runs[al * 4096 + bl] = Run{start, cnt}; run_keys.push_back(al * 4096 + bl); }
+        }
+    }
+    const int K = (int)out.am.size();
+    // inner arc match: (al+1, ar-1, bl+1, br-1)
+    for (int k = 0; k < K; k++) {
+        const int al = out.am[k].ends_a & 0xfff, ar = out.am[k].ends_a >> 12, bl = out.am[k].ends_b & 0xfff, br = out.am[k].ends_b >> 12;
+        auto it = runs.find((al + 1) * 4096 + bl + 1);
+        if (it == runs.end()) continue;
+        for (int x = it->second.start; x < it->second.start + it->second.count; x++)
+            if ((int)(out.am[x].ends_a >> 12) == ar - 1 && (int)(out.am[x].ends_b >> 12) == br - 1) { out.am[k].inner = x; break; }
+    }
+    // S-order: stable sort of the L-order by (ar+br, ar); within equal keys the L-order (al desc, bl desc) is what
+    // common_right_end_list uses (arc_matches.hh:188-220)
+    std::vector<int> perm(K);
+    for (int k = 0; k < K; k++) perm[k] = k;
+    std::stable_sort(perm.begin(), perm.end(), [&](int x, int y) {
+        const int ax = out.am[x].ends_a >> 12, ay = out.am[y].ends_a >> 12;
+        const int sx = ax + (int)(out.am[x].ends_b >> 12), sy = ay + (int)(out.am[y].ends_b >> 12);
+        if (sx != sy) return sx < sy;
+        return ax < ay;
+    });
+    out.ent.resize(K);
+    out.sptr.assign(n + m + 3, 0);
+    for (int s = 0; s < K; s++) {
+        DevArcMatch &x = out.am[perm[s]];
+        x.spos = s;
+        const int al = x.ends_a & 0xfff, ar = x.ends_a >> 12, bl = x.ends_b & 0xfff, br = x.ends_b >> 12;
+        out.ent[s].x = (uint32_t)(al - 1) | ((uint32_t)(bl - 1) << 12);
+        out.ent[s].y = (uint32_t)ar | ((uint32_t)br << 12);
+        out.sptr[ar + br + 1]++;
+    }
+    for (int s = 0; s + 1 < (int)out.sptr.size(); s++) out.sptr[s + 1] += out.sptr[s];
+    // tasks
+    const bool nolp = p.no_lonely_pairs;
+    for (int key : run_keys) {
+        const Run r = runs[key];
+        const int al = key / 4096, bl = key % 4096;
+        int max_ar = 0, max_br = 0;
+        for (int x = r.start; x < r.start + r.count; x++) {
+            if (nolp && out.am[x].inner < 0) continue;
+            max_ar = std::max(max_ar, (int)(out.am[x].ends_a >> 12));
+            max_br = std::max(max_br, (int)(out.am[x].ends_b >> 12));
+        }
+        if (max_ar == 0) continue;
+        DevTask tk;
+        tk.pair = 0;
+        tk.al = (short)(nolp ? al + 1 : al); tk.bl = (short)(nolp ? bl + 1 : bl);
+        tk.R = (short)(nolp ? max_ar - 2 : max_ar - 1); tk.C = (short)(nolp ? max_br - 2 : max_br - 1);
+        tk.run_start = r.start; tk.run_count = r.count;
+        out.tasks.push_back(tk);
+        for (int i = tk.al + 1; i <= tk.R; i++) {
+            const int jl = std::max((int)tk.bl + 1, lo[i]), jh = std::min((int)tk.C, hi[i]);
+            if (jh >= jl) out.cells += jh - jl + 1;
+        }
+    }
+    // bound on the diagonals (j - i) touched by any box: band cells, plus row 0 of the top level box, which is
+    // initialised from column 0 even where the band starts further right (aligner.cc:345-357)
+    int dmin = 0, dmax = 0;
+    for (int i = 0; i <= n; i++) {
+        dmin = std::min(dmin, lo[i] - i); dmax = std::max(dmax, hi[i] - i);
+        if (i >= 1) { const int jl = std::max(1, lo[i]), jh = std::min(m, hi[i]); if (jh >= jl) out.cells += jh - jl + 1; }
+    }
+    out.wd_bound = dmax - dmin + 1;
+    out.max_box_words = (n + 1) * (out.wd_bound | 1);
+}
+
+}  // namespace lb200

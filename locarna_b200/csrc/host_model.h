@@ -1,0 +1,86 @@
+// Host-side problem model of the B200 aligner: what the reference keeps in RnaData / BasePairs /
+// TraceController / Scoring, reduced to flat arrays that can be uploaded once per sequence / pair.
+// (Reference files cited per function in host_model.cc.)
+#ifndef LB200_HOST_MODEL_H
+#define LB200_HOST_MODEL_H
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "dev_types.h"
+
+namespace lb200 {
+
+struct Params {  // mirrors the `locarna` CLI options that reach the path (locarna.cc:83-272)
+    double min_prob = 0.001;
+    int max_diff_am = -1, max_diff_at_am = -1, max_diff = -1;
+    double min_trace_probability = 1e-4;
+    bool no_lonely_pairs = false, struct_local = false, sequ_local = false;
+    bool fe_left1 = false, fe_right1 = false, fe_left2 = false, fe_right2 = false;
+    int struct_weight = 200, indel = -150, indel_opening = -750, tau = 50, exclusion = 0;
+    int match = 50, mismatch = 0, unpaired_penalty = 0, temperature_alipf = 300;
+    bool use_ribosum = true;
+    bool pf_double = false;  // envelope in double (locarna_p default) instead of long double (locarna)
+};
+
+struct Arc { int left, right; };
+
+// One RNA: sequence + sparse base pair probabilities, already filtered like RnaData/BasePairs do.
+struct Sequence {
+    std::string name, seq;             // seq[0] is position 1
+    int len = 0;
+    std::vector<uint8_t> codes;        // 1-based symbol codes (A C G U = 0..3, other capitals 4 + c - 'A', rest 30)
+    // all pairs kept by the PP reader (p > cutoff), for the envelope's paired-up/down sums
+    std::vector<int> pp_i, pp_j;
+    std::vector<double> pp_p;
+    double cutoff = 0;
+    // arcs with p >= min_prob in the reference's index order (left descending, right ascending)
+    std::vector<Arc> arcs;
+    std::vector<double> arc_prob;
+    std::vector<int> lptr;             // arcs with left end l are arcs[lptr[l] .. lptr[l]+lcount[l])
+    std::vector<int> lcount;
+    std::vector<double> p_up, p_down;  // rna_data.cc:713-732
+};
+
+struct Band {
+    int lenA = 0, lenB = 0;
+    std::vector<int> lo, hi;  // min_col / max_col, entries 0..lenA
+};
+
+struct ScoreTables {
+    int match_ext, mismatch_ext, n_ext;  // base match score for symbols outside ACGU
+    int am_seq[256];           // (tau * ribosum arc match score) / 100 per (pair type A, pair type B), ACGU only
+    DevParams dev;
+};
+
+// PP 2.0 reader
+bool read_pp(const std::string &path, double p_bpcut, Sequence &out, std::string &err);
+// sequence + explicit pair list (i, j, p): same filtering as the PP reader with #BPCUT = cutoff
+bool make_sequence(const std::string &name, const std::string &seq, const int *pi, const int *pj, const double *pp, int npairs,
+                   double p_bpcut, Sequence &out, std::string &err);
+void finish_sequence(Sequence &s, double min_prob);
+
+std::vector<int> arc_weights(const Sequence &s, const Params &p);
+void make_score_tables(const Params &p, ScoreTables &t);
+int base_match_score(const ScoreTables &t, uint8_t a, uint8_t b);
+int arcmatch_score(const ScoreTables &t, const Params &p, const Sequence &A, const Sequence &B, int a, int b, const std::vector<int> &wA,
+                   const std::vector<int> &wB);
+
+Band make_band(int lenA, int lenB, int max_diff);
+// probability envelope (PFGotoh in 80-bit or 64-bit floating point on the host)
+void restrict_band_by_envelope(Band &band, const Sequence &A, const Sequence &B, const Params &p);
+
+// Per-pair problem in device layout, built on the host (L-order / S-order, see dev_types.h)
+struct PairProblem {
+    std::vector<DevArcMatch> am;      // L-order
+    std::vector<int> am_a, am_b;      // arc indices per L-order arc match
+    std::vector<DevEntry> ent;        // S-order
+    std::vector<int> sptr;            // lenA+lenB+2
+    std::vector<DevTask> tasks;       // pair field left 0
+    int wd_bound = 1;                 // upper bound on the number of band diagonals of any box
+    int max_box_words = 0;
+    uint64_t cells = 0;               // DP cell updates of all D-fill tasks + top level (reference count)
+};
+void build_pair_problem(const Sequence &A, const Sequence &B, const Band &band, const Params &p, const ScoreTables &t, PairProblem &out);
+
+}  // namespace lb200
+#endif

@@ -1,0 +1,496 @@
+// Context, device memory management, scheduling and the C ABI (include/locarna_b200.h).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/locarna_b200.h"
+#include "dev_ctx.h"
+#include "host_model.h"
+
+namespace lb200 {
+void launch_dfill(const DevCtx &c, int ncmax, int grid, int smem_bytes, int task_begin, int task_end, int *cursor, cudaStream_t st);
+void launch_toplevel(const DevCtx &c, int ncmax, int grid, int smem_bytes, int pair_begin, int pair_end, int *cursor, cudaStream_t st);
+cudaError_t configure_kernels(int ncmax, int smem_bytes, int *dfill_ctas_per_sm);
+}  // namespace lb200
+
+using namespace lb200;
+
+cudaError_t lb200_fill_i32(int *p, size_t n, int v, cudaStream_t st);
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PairRec {
+    int seqA, seqB;
+    Band band;
+    PairProblem prob;
+    bool built = false;
+    // results
+    int64_t score = 0; bool neg_inf = true; int max_i = 0, max_j = 0;
+    std::vector<int> dvals;  // S-order, when LB200_RUN_KEEP_D
+    std::vector<int> edges_a, edges_b; std::string str_a, str_b;
+};
+
+}  // namespace
+
+struct lb200_ctx {
+    int device = 0;
+    cudaDeviceProp prop;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    Params params;
+    ScoreTables tables;
+    bool params_locked = false;
+    std::vector<Sequence> seqs;
+    std::vector<PairRec> pairs;
+    double last_kernel_ms = 0;
+    int64_t last_launches = 0;
+    int smem_bytes = 24 * 1024;
+    int host_threads = 0;
+    DevBuf d_pairs, d_codes, d_band_lo, d_band_hi, d_sptr, d_ent, d_dval, d_am, d_tasks, d_top, d_scratch, d_cursor, d_flag;
+    ~lb200_ctx() {
+        DevBuf *all[] = {&d_pairs, &d_codes, &d_band_lo, &d_band_hi, &d_sptr, &d_ent, &d_dval, &d_am, &d_tasks, &d_top, &d_scratch, &d_cursor, &d_flag};
+        for (auto *b : all) b->release();
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+static int fail(lb200_ctx *c, int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+#define CUDA_TRY(c, call)                                                                                   \
+    do {                                                                                                    \
+        cudaError_t e__ = (call);                                                                           \
+        if (e__ != cudaSuccess) return fail(c, LB200_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+static Params to_params(const lb200_params &p) {
+    Params q;
+    q.min_prob = p.min_prob; q.max_diff_am = p.max_diff_am; q.max_diff_at_am = p.max_diff_at_am; q.max_diff = p.max_diff;
+    q.min_trace_probability = p.min_trace_probability;
+    q.no_lonely_pairs = p.no_lonely_pairs != 0; q.struct_local = p.struct_local != 0; q.sequ_local = p.sequ_local != 0;
+    const size_t fl = strnlen(p.free_endgaps, sizeof p.free_endgaps);
+    if (fl >= 4) {  // free_endgaps.hh:27-32: fewer than 4 characters means no free end gaps
+        q.fe_left1 = p.free_endgaps[0] == '+'; q.fe_right1 = p.free_endgaps[1] == '+';
+        q.fe_left2 = p.free_endgaps[2] == '+'; q.fe_right2 = p.free_endgaps[3] == '+';
+    }
+    q.struct_weight = p.struct_weight; q.indel = p.indel; q.indel_opening = p.indel_opening; q.tau = p.tau; q.exclusion = p.exclusion;
+    q.match = p.match; q.mismatch = p.mismatch; q.unpaired_penalty = p.unpaired_penalty; q.temperature_alipf = p.temperature_alipf;
+    q.use_ribosum = p.use_ribosum != 0; q.pf_double = p.pf_double != 0;
+    return q;
+}
+
+extern "C" {
+
+void lb200_default_params(lb200_params *p) {
+    memset(p, 0, sizeof *p);
+    p->min_prob = 0.001; p->max_diff_am = -1; p->max_diff_at_am = -1; p->max_diff = -1; p->min_trace_probability = 1e-4;
+    p->struct_weight = 200; p->indel = -150; p->indel_opening = -750; p->tau = 50; p->exclusion = 0;
+    p->match = 50; p->mismatch = 0; p->use_ribosum = 1; p->unpaired_penalty = 0; p->temperature_alipf = 300;
+    strcpy(p->free_endgaps, "----");
+}
+
+int lb200_ctx_create(int device, lb200_ctx **out) {
+    if (!out) return LB200_ERR_ARG;
+    *out = nullptr;
+    if (device == LB200_DEVICE_NONE) {  // host-only context: lb200_prepare + inspection, lb200_run refuses
+        lb200_ctx *c = new lb200_ctx();
+        c->device = LB200_DEVICE_NONE;
+        lb200_params dp;
+        lb200_default_params(&dp);
+        c->params = to_params(dp);
+        make_score_tables(c->params, c->tables);
+        if (const char *s = getenv("LB200_HOST_THREADS")) c->host_threads = atoi(s);
+        *out = c;
+        return LB200_OK;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        fprintf(stderr, "locarna_b200: no CUDA device available (%s); this library has no CPU fallback\n",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return LB200_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) return LB200_ERR_ARG;
+    lb200_ctx *c = new lb200_ctx();
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&c->prop, device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess ||
+        cudaEventCreate(&c->ev1) != cudaSuccess) {
+        fprintf(stderr, "locarna_b200: cannot initialise device %d: %s\n", device, cudaGetErrorString(cudaGetLastError()));
+        delete c;
+        return LB200_ERR_CUDA;
+    }
+    lb200_params dp;
+    lb200_default_params(&dp);
+    c->params = to_params(dp);
+    make_score_tables(c->params, c->tables);
+    if (const char *s = getenv("LB200_SMEM_KB")) c->smem_bytes = std::max(8, atoi(s)) * 1024;
+    if (const char *s = getenv("LB200_HOST_THREADS")) c->host_threads = atoi(s);
+    *out = c;
+    return LB200_OK;
+}
+
+void lb200_ctx_destroy(lb200_ctx *c) { delete c; }
+const char *lb200_last_error(const lb200_ctx *c) { return c ? c->err.c_str() : "null context"; }
+
+int lb200_set_params(lb200_ctx *c, const lb200_params *p) {
+    if (!c || !p) return LB200_ERR_ARG;
+    if (!c->seqs.empty()) return fail(c, LB200_ERR_STATE, "parameters must be set before sequences are added");
+    if (p->struct_local) return fail(c, LB200_ERR_UNSUPPORTED, "--struct-local is not implemented on the B200 path yet");
+    c->params = to_params(*p);
+    make_score_tables(c->params, c->tables);
+    return LB200_OK;
+}
+
+int lb200_seq_add_pp(lb200_ctx *c, const char *path) {
+    if (!c || !path) return LB200_ERR_ARG;
+    Sequence s;
+    std::string err;
+    if (!read_pp(path, c->params.min_prob, s, err)) return fail(c, LB200_ERR_IO, "%s", err.c_str());
+    finish_sequence(s, c->params.min_prob);
+    c->seqs.push_back(std::move(s));
+    return (int)c->seqs.size() - 1;
+}
+
+int lb200_seq_add(lb200_ctx *c, const char *name, const char *seq, const int *pi, const int *pj, const double *pp, int n) {
+    if (!c || !seq || n < 0 || (n > 0 && (!pi || !pj || !pp))) return LB200_ERR_ARG;
+    Sequence s;
+    std::string err;
+    if (!make_sequence(name ? name : "seq", seq, pi, pj, pp, n, c->params.min_prob, s, err)) return fail(c, LB200_ERR_ARG, "%s", err.c_str());
+    finish_sequence(s, c->params.min_prob);
+    c->seqs.push_back(std::move(s));
+    return (int)c->seqs.size() - 1;
+}
+
+int lb200_seq_length(const lb200_ctx *c, int seq) {
+    if (!c || seq < 0 || seq >= (int)c->seqs.size()) return LB200_ERR_ARG;
+    return c->seqs[seq].len;
+}
+
+int lb200_pair_add(lb200_ctx *c, int seqA, int seqB, const int *min_col, const int *max_col) {
+    if (!c || seqA < 0 || seqB < 0 || seqA >= (int)c->seqs.size() || seqB >= (int)c->seqs.size()) return LB200_ERR_ARG;
+    if ((min_col == nullptr) != (max_col == nullptr)) return LB200_ERR_ARG;
+    PairRec r;
+    r.seqA = seqA; r.seqB = seqB;
+    const int n = c->seqs[seqA].len, m = c->seqs[seqB].len;
+    if (n < 1 || m < 1) return fail(c, LB200_ERR_UNSUPPORTED, "empty sequences are not supported");
+    if (min_col) {
+        r.band.lenA = n; r.band.lenB = m;
+        r.band.lo.assign(min_col, min_col + n + 1); r.band.hi.assign(max_col, max_col + n + 1);
+        for (int i = 0; i <= n; i++)
+            if (r.band.lo[i] < 0 || r.band.hi[i] > m) return fail(c, LB200_ERR_ARG, "band out of range in row %d", i);
+    }
+    c->pairs.push_back(std::move(r));
+    return (int)c->pairs.size() - 1;
+}
+
+int lb200_num_pairs(const lb200_ctx *c) { return c ? (int)c->pairs.size() : LB200_ERR_ARG; }
+int lb200_clear_pairs(lb200_ctx *c) {
+    if (!c) return LB200_ERR_ARG;
+    c->pairs.clear();
+    return LB200_OK;
+}
+
+}  // extern "C"
+
+static void parallel_for(int n, int threads, const std::function<void(int)> &fn) {
+    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    threads = std::max(1, std::min(threads, n));
+    if (threads == 1) { for (int i = 0; i < n; i++) fn(i); return; }
+    std::atomic<int> next(0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++)
+        pool.emplace_back([&]() { for (int i = next++; i < n; i = next++) fn(i); });
+    for (auto &t : pool) t.join();
+}
+
+template <class T>
+static cudaError_t upload(DevBuf &b, const std::vector<T> &v, cudaStream_t st) {
+    cudaError_t e = b.ensure(std::max<size_t>(v.size() * sizeof(T), 16));
+    if (e != cudaSuccess) return e;
+    if (v.empty()) return cudaSuccess;
+    return cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+}
+
+extern "C" {
+
+int lb200_prepare(lb200_ctx *c) {
+    if (!c) return LB200_ERR_ARG;
+    const int P = (int)c->pairs.size();
+    // ---- host: bands (unless supplied) and per-pair problems
+    parallel_for(P, c->host_threads, [&](int k) {
+        PairRec &r = c->pairs[k];
+        if (r.built) return;
+        const Sequence &A = c->seqs[r.seqA], &B = c->seqs[r.seqB];
+        if (r.band.lo.empty()) {
+            r.band = make_band(A.len, B.len, c->params.max_diff);
+            restrict_band_by_envelope(r.band, A, B, c->params);
+        }
+        build_pair_problem(A, B, r.band, c->params, c->tables, r.prob);
+        r.built = true;
+    });
+    return LB200_OK;
+}
+
+int lb200_run(lb200_ctx *c, int flags) {
+    if (!c) return LB200_ERR_ARG;
+    if (c->device == LB200_DEVICE_NONE) return fail(c, LB200_ERR_CUDA, "host-only context: lb200_run needs a CUDA device (no CPU fallback)");
+    if (flags & LB200_RUN_TRACE) return fail(c, LB200_ERR_UNSUPPORTED, "device traceback is not implemented yet");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const int P = (int)c->pairs.size();
+    c->last_kernel_ms = 0; c->last_launches = 0;
+    if (P == 0) return LB200_OK;
+    { const int rc = lb200_prepare(c); if (rc != LB200_OK) return rc; }
+
+    // ---- flatten into batch arrays
+    std::vector<DevPair> h_pairs(P);
+    std::vector<uint8_t> h_codes;
+    std::vector<int> seq_off(c->seqs.size(), -1);
+    std::vector<int> h_lo, h_hi, h_sptr;
+    std::vector<DevEntry> h_ent;
+    std::vector<DevArcMatch> h_am;
+    std::vector<DevTask> h_tasks;
+    size_t total_am = 0, total_tasks = 0;
+    int wd_bound = 1, max_rows = 1, max_cols = 1;
+    for (auto &r : c->pairs) { total_am += r.prob.am.size(); total_tasks += r.prob.tasks.size(); }
+    h_ent.reserve(total_am); h_am.reserve(total_am); h_tasks.reserve(total_tasks);
+    for (int k = 0; k < P; k++) {
+        PairRec &r = c->pairs[k];
+        for (int s : {r.seqA, r.seqB}) {
+            if (seq_off[s] < 0) {
+                seq_off[s] = (int)h_codes.size();
+                h_codes.insert(h_codes.end(), c->seqs[s].codes.begin(), c->seqs[s].codes.end());
+            }
+        }
+        DevPair &d = h_pairs[k];
+        d.lenA = c->seqs[r.seqA].len; d.lenB = c->seqs[r.seqB].len;
+        d.codesA = seq_off[r.seqA]; d.codesB = seq_off[r.seqB];
+        d.band = (int)h_lo.size();
+        h_lo.insert(h_lo.end(), r.band.lo.begin(), r.band.lo.end());
+        h_hi.insert(h_hi.end(), r.band.hi.begin(), r.band.hi.end());
+        d.sptr = (int)h_sptr.size();
+        h_sptr.insert(h_sptr.end(), r.prob.sptr.begin(), r.prob.sptr.end());
+        d.K = (int)r.prob.am.size(); d.pad = 0;
+        d.am_base = (long long)h_am.size();
+        h_am.insert(h_am.end(), r.prob.am.begin(), r.prob.am.end());
+        h_ent.insert(h_ent.end(), r.prob.ent.begin(), r.prob.ent.end());
+        for (DevTask t : r.prob.tasks) { t.pair = k; h_tasks.push_back(t); }
+        wd_bound = std::max(wd_bound, r.prob.wd_bound);
+        max_rows = std::max(max_rows, d.lenA + 1); max_cols = std::max(max_cols, d.lenB + 1);
+    }
+    // ---- schedule: groups of two levels (al+bl)>>1, descending; larger boxes first inside a group
+    auto group_of = [](const DevTask &t) { return ((int)t.al + (int)t.bl) >> 1; };
+    auto size_of = [](const DevTask &t) { return ((int)t.R - t.al + 1) * ((int)t.C - t.bl + 1); };
+    std::sort(h_tasks.begin(), h_tasks.end(), [&](const DevTask &x, const DevTask &y) {
+        const int gx = group_of(x), gy = group_of(y);
+        if (gx != gy) return gx > gy;
+        return size_of(x) > size_of(y);
+    });
+    std::vector<int> group_start;
+    for (size_t t = 0; t < h_tasks.size(); t++)
+        if (t == 0 || group_of(h_tasks[t]) != group_of(h_tasks[t - 1])) group_start.push_back((int)t);
+    group_start.push_back((int)h_tasks.size());
+    const int n_groups = (int)group_start.size() - 1;
+
+    // ---- kernel configuration
+    const int nslots_bound = (wd_bound + 1) / 2;
+    const int ncmax = (nslots_bound + 31) / 32;
+    if (ncmax > LB_MAX_NC) return fail(c, LB200_ERR_UNSUPPORTED, "band of %d diagonals is wider than the supported %d", wd_bound, 64 * LB_MAX_NC);
+    const int nc_inst = ncmax <= 1 ? 1 : ncmax <= 2 ? 2 : ncmax <= 4 ? 4 : ncmax <= 8 ? 8 : 16;
+    DevCtx dc;
+    memset(&dc, 0, sizeof dc);
+    dc.params = c->tables.dev;
+    dc.max_rows = max_rows;
+    dc.max_cols_padded = (max_cols + 3) & ~3;
+    dc.arcbuf_words = 8 * 32 * nc_inst;
+    const int fixed_words = 16 + dc.max_rows + dc.max_cols_padded / 4 + dc.arcbuf_words;
+    int smem_bytes = std::max(c->smem_bytes, (fixed_words + 64) * 4);
+    if (smem_bytes > (int)c->prop.sharedMemPerBlockOptin) return fail(c, LB200_ERR_UNSUPPORTED, "problem needs %d bytes of shared memory per warp", smem_bytes);
+    dc.smem_words = smem_bytes / 4;
+    int ctas_per_sm = 1;
+    CUDA_TRY(c, configure_kernels(nc_inst, smem_bytes, &ctas_per_sm));
+    const int grid_cap = std::max(1, ctas_per_sm) * c->prop.multiProcessorCount;
+    int max_box_words = 0;
+    for (auto &r : c->pairs) max_box_words = std::max(max_box_words, r.prob.max_box_words);
+    dc.scratch_words = max_box_words;
+
+    // ---- upload
+    cudaStream_t st = c->stream;
+    CUDA_TRY(c, upload(c->d_pairs, h_pairs, st));
+    CUDA_TRY(c, upload(c->d_codes, h_codes, st));
+    CUDA_TRY(c, upload(c->d_band_lo, h_lo, st));
+    CUDA_TRY(c, upload(c->d_band_hi, h_hi, st));
+    CUDA_TRY(c, upload(c->d_sptr, h_sptr, st));
+    CUDA_TRY(c, upload(c->d_ent, h_ent, st));
+    CUDA_TRY(c, upload(c->d_am, h_am, st));
+    CUDA_TRY(c, upload(c->d_tasks, h_tasks, st));
+    CUDA_TRY(c, c->d_dval.ensure(std::max<size_t>(total_am * 4, 16)));
+    CUDA_TRY(c, c->d_top.ensure((size_t)P * sizeof(DevTopResult)));
+    CUDA_TRY(c, c->d_scratch.ensure((size_t)grid_cap * dc.scratch_words * 4 + 16));
+    CUDA_TRY(c, c->d_cursor.ensure((size_t)(n_groups + 2) * 4));
+    CUDA_TRY(c, c->d_flag.ensure(16));
+    dc.pairs = (const DevPair *)c->d_pairs.p; dc.codes = (const uint8_t *)c->d_codes.p;
+    dc.band_lo = (const int *)c->d_band_lo.p; dc.band_hi = (const int *)c->d_band_hi.p; dc.sptr = (const int *)c->d_sptr.p;
+    dc.ent = (const DevEntry *)c->d_ent.p; dc.dval = (int *)c->d_dval.p; dc.am = (const DevArcMatch *)c->d_am.p;
+    dc.tasks = (const DevTask *)c->d_tasks.p; dc.top = (DevTopResult *)c->d_top.p; dc.scratch = (int *)c->d_scratch.p;
+    dc.error_flag = (int *)c->d_flag.p;
+
+    // ---- run: D entries start as -inf (aligner.cc:122-123)
+    CUDA_TRY(c, cudaEventRecord(c->ev0, st));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_cursor.p, 0, (size_t)(n_groups + 2) * 4, st));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_flag.p, 0, 16, st));
+    CUDA_TRY(c, lb200_fill_i32((int *)c->d_dval.p, total_am, LB_NEG, st));
+    int64_t launches = 1;
+    for (int g = 0; g < n_groups; g++) {
+        const int b = group_start[g], e = group_start[g + 1];
+        const int grid = std::min(grid_cap, e - b);
+        launch_dfill(dc, nc_inst, grid, smem_bytes, b, e, (int *)c->d_cursor.p + g, st);
+        launches++;
+    }
+    launch_toplevel(dc, nc_inst, std::min(grid_cap, P), smem_bytes, 0, P, (int *)c->d_cursor.p + n_groups, st);
+    launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaEventRecord(c->ev1, st));
+
+    // ---- results
+    std::vector<DevTopResult> h_top(P);
+    int h_flag[4] = {0, 0, 0, 0};
+    CUDA_TRY(c, cudaMemcpyAsync(h_top.data(), c->d_top.p, (size_t)P * sizeof(DevTopResult), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaMemcpyAsync(h_flag, c->d_flag.p, 16, cudaMemcpyDeviceToHost, st));
+    std::vector<int> h_dval;
+    if (flags & LB200_RUN_KEEP_D) {
+        h_dval.resize(total_am);
+        if (total_am) CUDA_TRY(c, cudaMemcpyAsync(h_dval.data(), c->d_dval.p, total_am * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    float ms = 0;
+    CUDA_TRY(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->last_kernel_ms = ms; c->last_launches = launches;
+    if (h_flag[0] != 0) return fail(c, LB200_ERR_UNSUPPORTED, "kernel reported error %d (1: band too wide, 2: box exceeds scratch)", h_flag[0]);
+    for (int k = 0; k < P; k++) {
+        PairRec &r = c->pairs[k];
+        r.neg_inf = h_top[k].score < LB_NEG_LIMIT;
+        r.score = r.neg_inf ? 0 : h_top[k].score;
+        r.max_i = h_top[k].max_i; r.max_j = h_top[k].max_j;
+        if (flags & LB200_RUN_KEEP_D) r.dvals.assign(h_dval.begin() + h_pairs[k].am_base, h_dval.begin() + h_pairs[k].am_base + h_pairs[k].K);
+    }
+    return LB200_OK;
+}
+
+double lb200_last_kernel_ms(const lb200_ctx *c) { return c ? c->last_kernel_ms : 0; }
+int64_t lb200_last_launches(const lb200_ctx *c) { return c ? c->last_launches : 0; }
+
+int lb200_pair_score(const lb200_ctx *c, int pair, int64_t *score) {
+    if (!c || !score || pair < 0 || pair >= (int)c->pairs.size()) return LB200_ERR_ARG;
+    const PairRec &r = c->pairs[pair];
+    *score = r.neg_inf ? LB200_SCORE_NEG_INF : r.score;
+    return LB200_OK;
+}
+
+int lb200_get_scores(const lb200_ctx *c, int64_t *scores, int n) {
+    if (!c || !scores || n != (int)c->pairs.size()) return LB200_ERR_ARG;
+    for (int k = 0; k < n; k++) scores[k] = c->pairs[k].neg_inf ? LB200_SCORE_NEG_INF : c->pairs[k].score;
+    return LB200_OK;
+}
+
+int lb200_pair_get_info(const lb200_ctx *c, int pair, lb200_pair_info *info) {
+    if (!c || !info || pair < 0 || pair >= (int)c->pairs.size()) return LB200_ERR_ARG;
+    const PairRec &r = c->pairs[pair];
+    memset(info, 0, sizeof *info);
+    info->lenA = c->seqs[r.seqA].len; info->lenB = c->seqs[r.seqB].len;
+    info->n_arcsA = (int)c->seqs[r.seqA].arcs.size(); info->n_arcsB = (int)c->seqs[r.seqB].arcs.size();
+    info->n_arcmatches = (int64_t)r.prob.am.size(); info->n_tasks = (int64_t)r.prob.tasks.size(); info->cells = (int64_t)r.prob.cells;
+    info->n_edges = (int64_t)r.edges_a.size();
+    return LB200_OK;
+}
+
+int lb200_pair_band(const lb200_ctx *c, int pair, int *min_col, int *max_col) {
+    if (!c || !min_col || !max_col || pair < 0 || pair >= (int)c->pairs.size()) return LB200_ERR_ARG;
+    const PairRec &r = c->pairs[pair];
+    if (r.band.lo.empty()) return LB200_ERR_STATE;
+    std::copy(r.band.lo.begin(), r.band.lo.end(), min_col);
+    std::copy(r.band.hi.begin(), r.band.hi.end(), max_col);
+    return LB200_OK;
+}
+
+int lb200_pair_arcmatches(const lb200_ctx *c, int pair, int *al, int *ar, int *bl, int *br, int *score, int64_t *D) {
+    if (!c || pair < 0 || pair >= (int)c->pairs.size()) return LB200_ERR_ARG;
+    const PairRec &r = c->pairs[pair];
+    if (!r.built) return LB200_ERR_STATE;
+    const size_t K = r.prob.am.size();
+    if (D && r.dvals.size() != K) return LB200_ERR_STATE;
+    // reference index order = (arc A index, arc B index) ascending (arc_matches.cc:161-183)
+    std::vector<int> order(K);
+    for (size_t k = 0; k < K; k++) order[k] = (int)k;
+    std::sort(order.begin(), order.end(), [&](int x, int y) {
+        if (r.prob.am_a[x] != r.prob.am_a[y]) return r.prob.am_a[x] < r.prob.am_a[y];
+        return r.prob.am_b[x] < r.prob.am_b[y];
+    });
+    for (size_t k = 0; k < K; k++) {
+        const DevArcMatch &x = r.prob.am[order[k]];
+        if (al) al[k] = x.ends_a & 0xfff;
+        if (ar) ar[k] = x.ends_a >> 12;
+        if (bl) bl[k] = x.ends_b & 0xfff;
+        if (br) br[k] = x.ends_b >> 12;
+        if (score) score[k] = x.score;
+        if (D) { const int d = r.dvals[x.spos]; D[k] = d < LB_NEG_LIMIT ? LB200_SCORE_NEG_INF : d; }
+    }
+    return LB200_OK;
+}
+
+int lb200_pair_alignment(const lb200_ctx *c, int pair, int *ea, int *eb, char *sa, char *sb) {
+    if (!c || pair < 0 || pair >= (int)c->pairs.size()) return LB200_ERR_ARG;
+    const PairRec &r = c->pairs[pair];
+    if (r.str_a.empty()) return LB200_ERR_STATE;
+    if (ea) std::copy(r.edges_a.begin(), r.edges_a.end(), ea);
+    if (eb) std::copy(r.edges_b.begin(), r.edges_b.end(), eb);
+    if (sa) strcpy(sa, r.str_a.c_str());
+    if (sb) strcpy(sb, r.str_b.c_str());
+    return LB200_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+__global__ void fill_i32_kernel(int *p, size_t n, int v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+cudaError_t lb200_fill_i32(int *p, size_t n, int v, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+    fill_i32_kernel<<<grid, 256, 0, st>>>(p, n, v);
+    return cudaGetLastError();
+}

@@ -1,0 +1,77 @@
+"""GPU parity: D table and score of the CUDA path (through the C ABI) against the oracle port, bit-exact."""
+import os
+
+import pytest
+
+from locarna_b200 import capi
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FLAGSETS = [
+    {},
+    {"noLP": True, "max-diff-am": 30},
+    {"sequ-local": True},
+    {"free-endgaps": "++++"},
+    {"free-endgaps": "+-+-"},
+    {"free-endgaps": "-+-+", "noLP": True},
+    {"min-trace-probability": 0, "max-diff": 20},
+    {"min-trace-probability": 0},
+    {"max-diff-at-am": 25, "min-prob": 0.01},
+    {"no-ribosum": True, "indel-opening": 0, "tau": 100},
+    {"unpaired-penalty": 10, "struct-weight": 150, "noLP": True},
+]
+
+
+def gpu_align(pairs, flags, run_flags=capi.RUN_KEEP_D):
+    ctx = capi.Context(device=0, flags=flags)
+    ids = {}
+    for a, b in pairs:
+        for f in (a, b):
+            if f not in ids:
+                ids[f] = ctx.add_pp(f)
+        ctx.add_pair(ids[a], ids[b])
+    ctx.run(run_flags)
+    return ctx
+
+
+def check_pairs(pairs, flags):
+    ctx = gpu_align(pairs, flags)
+    scores = ctx.scores()
+    for k, (a, b) in enumerate(pairs):
+        ref = O.port_align(a, b, flags, do_trace=False)
+        am, score, D = ctx.arcmatches(k, with_D=True)
+        assert am == [x[:4] for x in ref["am"]]
+        assert score == ref["am_score"]
+        bad = [i for i in range(len(D)) if D[i] != ref["D"][i]]
+        assert not bad, "D mismatch at %d of %d arc matches, first %s: gpu %s ref %s" % (
+            len(bad), len(D), am[bad[0]], D[bad[0]], ref["D"][bad[0]])
+        assert scores[k] == ref["score"], (flags, a, b)
+        assert ctx.info(k).cells == ref["cells"]
+    ctx.close()
+
+
+@pytest.mark.parametrize("flags", FLAGSETS)
+def test_d_table_and_score(synth_dir, flags):
+    pairs = [tuple(synth_dir["cfg2"][:2]), tuple(synth_dir["cfg3"][:2]), tuple(synth_dir["cfg3"][2:4]),
+             tuple(synth_dir["short"][:2]), tuple(synth_dir["short"][2:4]), tuple(synth_dir["short"][4:6]),
+             (synth_dir["short"][0], synth_dir["cfg3"][5])]
+    check_pairs(pairs, flags)
+
+
+def test_spill_path_small_smem(synth_dir, monkeypatch):
+    """Boxes that do not fit the per-warp shared memory live in the L2 scratch: force that path."""
+    monkeypatch.setenv("LB200_SMEM_KB", "8")
+    check_pairs([tuple(synth_dir["cfg2"][:2]), tuple(synth_dir["cfg3"][:2])], {"noLP": True, "max-diff-am": 30})
+
+
+def test_batch_order_independent(synth_dir):
+    """Scores do not depend on batch composition / order."""
+    fam = synth_dir["cfg3"]
+    pairs = [(fam[i], fam[j]) for i in range(4) for j in range(i)]
+    flags = {"noLP": True, "max-diff-am": 30}
+    c1 = gpu_align(pairs, flags, capi.RUN_SCORE_ONLY)
+    c2 = gpu_align(list(reversed(pairs)), flags, capi.RUN_SCORE_ONLY)
+    assert c1.scores() == list(reversed(c2.scores()))
+    for k, (a, b) in enumerate(pairs):
+        assert c1.scores()[k] == O.port_align(a, b, flags, do_trace=False)["score"]
