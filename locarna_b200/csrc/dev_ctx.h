@@ -18,9 +18,9 @@ struct DevCtx {
     DevTopResult *top;
     int *scratch;            // per-CTA M box spill area (L2 resident)
     int scratch_words;
-    int smem_words;          // dynamic shared memory per CTA in words
-    int max_rows;            // rowinfo capacity (words)
-    int max_cols_padded;     // colinfo capacity (bytes, multiple of 4)
+    int max_rows;            // largest lenA + 1 of the batch (rowrange holds max_rows + 2 words)
+    int rowcode_bytes;       // >= max_rows + 2, multiple of 4
+    int colcode_bytes;       // >= largest lenB + 2, multiple of 4
     int arcbuf_words;        // RING * 32 * NCmax
     int *error_flag;
 };

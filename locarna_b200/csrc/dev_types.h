@@ -12,7 +12,8 @@
 #define LB_NEG_LIMIT (-0x10000000)  // anything below is -inf
 
 #define LB_MAXLEN 4095              // positions are packed into 12 bits
-#define LB_CODE_N 17                // symbol code of 'N' (codes: A C G U = 0..3, other capitals 4 + c - 'A', rest 30)
+#define LB_CODE_N 4                 // symbol codes: A C G U = 0..3, N = 4, up to three further symbols 5..7 (per process)
+#define LB_NCODES 8
 
 // scoring parameters that the kernels need (single sequences: position independent gap cost)
 struct DevParams {
@@ -22,8 +23,7 @@ struct DevParams {
     int exclusion;
     int no_lonely_pairs, struct_local, sequ_local;
     int fe_left1, fe_right1, fe_left2, fe_right2;  // free_endgaps.hh:42-70
-    int sigma4[16];   // base match score for A C G U (codes 0..3), unpaired penalty applied (scoring.cc:141-198)
-    int match_ext, mismatch_ext, n_ext;            // symbols outside ACGU: identical / different / either is 'N' (scoring.cc:186-191)
+    int sigma8[64];   // base match score by symbol codes (8x8), unpaired penalty applied (scoring.cc:141-198)
 };
 
 // one sequence-structure alignment problem

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <mutex>
 #include <sstream>
 #include <unordered_map>
 
@@ -16,18 +17,27 @@ namespace lb200 {
 
 static inline long round2score(double d) { return (long)((d < 0) ? (d - 0.5) : (d + 0.5)); }  // scoring.hh:384-387
 
-// symbol codes: A C G U -> 0..3, other capital letters -> 4 + (c - 'A'), anything else -> 30
-static inline uint8_t symbol_code(char c) {
+// symbol codes: A C G U -> 0..3, N -> 4; any other symbol gets one of the codes 5..7, assigned per process in
+// order of first appearance (the base match score of such symbols only depends on identity, scoring.cc:186-191)
+static std::mutex g_symbol_mutex;
+static char g_other_symbols[3] = {0, 0, 0};
+static int symbol_code(char c) {
     switch (c) {
         case 'A': return 0;
         case 'C': return 1;
         case 'G': return 2;
         case 'U': return 3;
-        default: return (c >= 'A' && c <= 'Z') ? (uint8_t)(4 + (c - 'A')) : (uint8_t)30;
+        case 'N': return LB_CODE_N;
+        default: break;
     }
+    std::lock_guard<std::mutex> lock(g_symbol_mutex);
+    for (int k = 0; k < 3; k++) {
+        if (g_other_symbols[k] == c) return 5 + k;
+        if (g_other_symbols[k] == 0) { g_other_symbols[k] = c; return 5 + k; }
+    }
+    return -1;
 }
 static const uint8_t CODE_N = LB_CODE_N;
-static_assert(LB_CODE_N == 4 + ('N' - 'A'), "symbol code of N");
 
 // ---------------------------------------------------------------------------------- input
 // Line discipline of the reference reader: lines that are empty or start with white space are
@@ -105,7 +115,11 @@ bool make_sequence(const std::string &name, const std::string &seq, const int *p
     out.len = (int)out.seq.size();
     if (out.len > LB_MAXLEN) { err = "sequence longer than 4095 positions"; return false; }
     out.codes.assign(out.len + 1, 0);
-    for (int i = 1; i <= out.len; i++) out.codes[i] = symbol_code(out.seq[i - 1]);
+    for (int i = 1; i <= out.len; i++) {
+        const int code = symbol_code(out.seq[i - 1]);
+        if (code < 0) { err = "more than three distinct sequence symbols besides A C G U N are not supported"; return false; }
+        out.codes[i] = (uint8_t)code;
+    }
     out.cutoff = p_bpcut;
     std::map<std::pair<int, int>, double> uniq;  // a repeated pair overwrites the earlier value (sparse matrix assignment)
     for (int k = 0; k < npairs; k++) {
@@ -162,14 +176,14 @@ std::vector<int> arc_weights(const Sequence &s, const Params &p) {
 // scoring.cc:141-198 (sigma_ for single sequences), :64-74 (unpaired penalty), :369-485 (arc match sequence term)
 void make_score_tables(const Params &p, ScoreTables &t) {
     memset(&t, 0, sizeof t);
-    for (int a = 0; a < 4; a++)
-        for (int b = 0; b < 4; b++) {
-            long s = p.use_ribosum ? RIBOSUM85_60_SIGMA4[a * 4 + b] : (a == b ? p.match : p.mismatch);
-            t.dev.sigma4[a * 4 + b] = (int)s - 2 * p.unpaired_penalty;
+    for (int a = 0; a < LB_NCODES; a++)
+        for (int b = 0; b < LB_NCODES; b++) {
+            long s;
+            if (a < 4 && b < 4) s = p.use_ribosum ? RIBOSUM85_60_SIGMA4[a * 4 + b] : (a == b ? p.match : p.mismatch);
+            else if (a == CODE_N || b == CODE_N) s = 0;
+            else s = (a == b) ? p.match : p.mismatch;
+            t.dev.sigma8[a * LB_NCODES + b] = (int)s - 2 * p.unpaired_penalty;
         }
-    t.match_ext = p.match - 2 * p.unpaired_penalty;
-    t.mismatch_ext = p.mismatch - 2 * p.unpaired_penalty;
-    t.n_ext = -2 * p.unpaired_penalty;
     for (int x = 0; x < 16; x++)
         for (int y = 0; y < 16; y++) t.am_seq[x * 16 + y] = (int)(((long)p.tau * RIBOSUM85_60_AM16[x * 16 + y]) / 100);
     DevParams &d = t.dev;
@@ -179,14 +193,9 @@ void make_score_tables(const Params &p, ScoreTables &t) {
     d.exclusion = p.exclusion;
     d.no_lonely_pairs = p.no_lonely_pairs; d.struct_local = p.struct_local; d.sequ_local = p.sequ_local;
     d.fe_left1 = p.fe_left1; d.fe_right1 = p.fe_right1; d.fe_left2 = p.fe_left2; d.fe_right2 = p.fe_right2;
-    d.match_ext = t.match_ext; d.mismatch_ext = t.mismatch_ext; d.n_ext = t.n_ext;
 }
 
-int base_match_score(const ScoreTables &t, uint8_t a, uint8_t b) {
-    if (a < 4 && b < 4) return t.dev.sigma4[a * 4 + b];
-    if (a == CODE_N || b == CODE_N) return t.n_ext;
-    return a == b ? t.match_ext : t.mismatch_ext;
-}
+int base_match_score(const ScoreTables &t, uint8_t a, uint8_t b) { return t.dev.sigma8[a * LB_NCODES + b]; }
 
 int arcmatch_score(const ScoreTables &t, const Params &p, const Sequence &A, const Sequence &B, int a, int b, const std::vector<int> &wA,
                    const std::vector<int> &wB) {

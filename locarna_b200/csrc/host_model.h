@@ -28,7 +28,7 @@ struct Arc { int left, right; };
 struct Sequence {
     std::string name, seq;             // seq[0] is position 1
     int len = 0;
-    std::vector<uint8_t> codes;        // 1-based symbol codes (A C G U = 0..3, other capitals 4 + c - 'A', rest 30)
+    std::vector<uint8_t> codes;        // 1-based symbol codes (A C G U = 0..3, N = 4, other symbols 5..7)
     // all pairs kept by the PP reader (p > cutoff), for the envelope's paired-up/down sums
     std::vector<int> pp_i, pp_j;
     std::vector<double> pp_p;
@@ -47,7 +47,6 @@ struct Band {
 };
 
 struct ScoreTables {
-    int match_ext, mismatch_ext, n_ext;  // base match score for symbols outside ACGU
     int am_seq[256];           // (tau * ribosum arc match score) / 100 per (pair type A, pair type B), ACGU only
     DevParams dev;
 };

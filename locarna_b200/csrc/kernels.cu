@@ -12,12 +12,13 @@
 // adjacent diagonals v = j'-i' (only diagonals of the parity of u are active in a step), so every
 // lane has work in every step of a diagonal band, M/E/F of the three neighbours stay in registers and
 // only the two cells at a lane boundary travel by warp shuffle. The recurrence uses the DPX
-// instructions (VIADDMNMX / VIMNMX3). The box itself is written once per cell (shared memory when it
-// fits, an L2-resident scratch otherwise) because arc-match terms read M(al'-1, bl'-1) at arbitrary
-// earlier cells. Arc-match terms are not pulled per cell: the valid arc matches of a pair are kept
-// sorted by the anti-diagonal of their right ends (S-order), the warp streams the entries four
-// anti-diagonals ahead with coalesced loads and folds M(src)+D into a small ring of per-diagonal
-// accumulators with shared-memory atomicMax.
+// instructions (VIADDMNMX / VIMNMX3). The box itself is written once per cell into an L2-resident
+// per-warp scratch (arc-match terms read M(al'-1, bl'-1) at arbitrary earlier cells); shared memory
+// holds only the per-row band/sequence info and the arc-term accumulators, which keeps 32 warps per SM
+// resident - the sweep is a dependent chain, so throughput comes from warps in flight.
+// Arc-match terms are not pulled per cell: the valid arc matches of a pair are kept sorted by the
+// anti-diagonal of their right ends (S-order); the warp streams them in chunks of 32 with coalesced,
+// prefetched loads and folds M(src)+D into a ring of per-diagonal accumulators with shared-memory atomicMax.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "dev_types.h"
@@ -32,7 +33,6 @@ __device__ __forceinline__ int max3(int a, int b, int c) { return __vimax3_s32(a
 struct BoxInit {
     int col_base, col_step;  // M(al+i', bl) = col_base + i'*col_step   (deleting a prefix of A)
     int row_base, row_step;  // M(al, bl+j') = row_base + j'*row_step   (inserting a prefix of B)
-    int clamp0;              // sequence-local top level: M = max(M, 0)  (aligner.cc:866-868)
 };
 
 struct BoxGeom {
@@ -42,15 +42,14 @@ struct BoxGeom {
 };
 
 constexpr int RING = 8;      // arc-term accumulators for 8 consecutive anti-diagonals
-constexpr int LOOKAHEAD = 4; // entries of anti-diagonal u+4 are folded in step u; their sources are final:
-                             // an arc spans >= 3 positions, so src = (al'-1, bl'-1) lies >= 8 anti-diagonals back
 
-// per-warp shared memory carve-up
+// per-warp shared memory
 struct WarpSmem {
-    uint32_t *rowinfo;  // Rn+1 words: jl | jh<<12 | codeA<<24
-    uint8_t *colinfo;   // Cn+1 bytes: codeB
-    int *arcbuf;        // RING * 32*NC
-    int *box;           // smem box (or nullptr when the box lives in scratch)
+    const int *sig;      // 8x8 base match scores by symbol code
+    uint32_t *rowrange;  // [ip+1], ip = -1..Rn+1: first valid diagonal (c index) | number of further valid diagonals << 16
+    uint8_t *rowcode;    // [ip+1]: 8 * symbol code of A[al+ip]
+    uint8_t *colcode;    // [jp],  jp = 0..Cn+1: symbol code of B[bl+jp]
+    int *arcbuf;         // RING * 32*NC accumulators
 };
 
 __device__ __forceinline__ int warp_min(int v) {
@@ -64,178 +63,264 @@ __device__ __forceinline__ int warp_max(int v) {
     return v;
 }
 
+constexpr uint32_t ROW_INVALID = 0x0000ffffu;  // first valid diagonal 65535, width 0: never matches
+
 // Stage the per-row band/sequence info of a box into shared memory and derive its geometry.
-__device__ void setup_box(const DevCtx &c, const DevPair &pr, int al, int bl, int R, int C, BoxGeom &g, uint32_t *rowinfo,
-                          uint8_t *colinfo) {
+// Row ip covers local columns [jl, jh]: row 0 and column 0 are the initialised borders
+// (aligner.cc:307-357): column 0 belongs to row ip as long as min_col(al+ip) <= bl.
+__device__ void setup_box(const DevCtx &c, const DevPair &pr, int al, int bl, int R, int C, BoxGeom &g, const WarpSmem &ws) {
     const int lane = threadIdx.x & 31;
     g.al = al; g.bl = bl; g.Rn = R - al; g.Cn = C - bl;
     int vmin = 1 << 20, vmax = -(1 << 20), umax = 0;
     const int *lo = c.band_lo + pr.band, *hi = c.band_hi + pr.band;
     const uint8_t *ca = c.codes + pr.codesA, *cb = c.codes + pr.codesB;
     for (int ip = lane; ip <= g.Rn; ip += 32) {
-        int i = al + ip;
-        int l = lo[i], h = hi[i];
+        const int i = al + ip;
+        const int l = lo[i], h = hi[i];
         int jl = (ip == 0 || l <= bl) ? 0 : (l - bl);
         int jh = min(g.Cn, h - bl);
-        if (jh < jl) { jl = 1; jh = 0; }
+        if (jh < jl) { jl = 0xffff; jh = 0xffff; }
         else { vmin = min(vmin, jl - ip); vmax = max(vmax, jh - ip); umax = max(umax, ip + jh); }
-        uint32_t code = (i >= 1) ? ca[i] : 0;
-        rowinfo[ip] = (uint32_t)jl | ((uint32_t)jh << 12) | (code << 24);
+        ws.rowrange[ip + 1] = (uint32_t)jl | ((uint32_t)jh << 16);
+        ws.rowcode[ip + 1] = (uint8_t)(((i >= 1) ? ca[i] : 0) * 8);
     }
-    for (int jp = lane; jp <= g.Cn; jp += 32) colinfo[jp] = (bl + jp >= 1) ? cb[bl + jp] : 0;
+    for (int jp = lane; jp <= g.Cn; jp += 32) ws.colcode[jp] = (bl + jp >= 1) ? cb[bl + jp] : 0;
+    if (lane == 0) {
+        ws.rowrange[0] = ROW_INVALID; ws.rowrange[g.Rn + 2] = ROW_INVALID;
+        ws.rowcode[0] = 0; ws.rowcode[g.Rn + 2] = 0; ws.colcode[g.Cn + 1] = 0;
+    }
     g.vmin = warp_min(vmin);
     vmax = warp_max(vmax);
     g.umax = warp_max(umax);
-    int wd = vmax - g.vmin + 1;
+    const int wd = vmax - g.vmin + 1;
     g.nslots = (wd + 1) >> 1;
     g.strideD = wd | 1;
     __syncwarp();
+    // convert column ranges to diagonal ranges relative to vmin
+    for (int ip = lane; ip <= g.Rn; ip += 32) {
+        const uint32_t r = ws.rowrange[ip + 1];
+        const int jl = r & 0xffff, jh = r >> 16;
+        ws.rowrange[ip + 1] = (jl == 0xffff) ? ROW_INVALID : ((uint32_t)(jl - ip - g.vmin) | ((uint32_t)(jh - jl) << 16));
+    }
+    __syncwarp();
+}
+
+// One anti-diagonal step of the cell recurrence for the NC diagonal pairs of this lane.
+// PAR = parity of (u - vmin): the active diagonal of pair g is c = 2g + PAR.
+//   PAR == 0: up neighbour (i-1,j) is the odd diagonal of the same pair, left neighbour (i,j-1) the odd diagonal
+//             of the previous pair (previous lane for k == 0);
+//   PAR == 1: left neighbour is the even diagonal of the same pair, up neighbour the even diagonal of the next pair.
+// GB (generic borders): row 0 / column 0 get explicit values; otherwise they fall out of the recurrence, which is
+//   exact for the all-global box init with indel_opening <= 0: M(al, bl+j') = open + j'*gap is what F yields on a
+//   row whose only finite predecessor is the origin (and E likewise for column 0).
+// CLAMP: sequence-local top level, M = max(M, 0) (aligner.cc:866-868).
+template <int NC, int PAR, bool GB, bool CLAMP>
+__device__ __forceinline__ void dp_step(const BoxGeom &g, const BoxInit &init, const WarpSmem &ws, int *box, const DevParams &P, int u,
+                                        int lane, int (&mE)[NC], int (&eE)[NC], int (&fE)[NC], int (&mO)[NC], int (&eO)[NC],
+                                        int (&fO)[NC]) {
+    constexpr int NW = 32 * NC;
+    int xm, xo;
+    if (PAR == 0) {
+        xm = __shfl_up_sync(0xffffffffu, mO[NC - 1], 1);
+        xo = __shfl_up_sync(0xffffffffu, fO[NC - 1], 1);
+        if (lane == 0) { xm = LB_NEG; xo = LB_NEG; }
+    } else {
+        xm = __shfl_down_sync(0xffffffffu, mE[0], 1);
+        xo = __shfl_down_sync(0xffffffffu, eE[0], 1);
+        if (lane == 31) { xm = LB_NEG; xo = LB_NEG; }
+    }
+    // warp-uniform per step: row / column of diagonal pair 0
+    const int U2 = (u - g.vmin - PAR) >> 1;  // ip = U2 - gidx
+    const int J2 = (u + g.vmin + PAR) >> 1;  // jp = J2 + gidx
+    const int ring = (u & (RING - 1)) * NW;
+    const int boxbase = U2 * g.strideD + PAR;
+    const int gap = P.gap, gap_open = P.gap_open;
+    int nm[NC], ne[NC], nf[NC];
+#pragma unroll
+    for (int k = 0; k < NC; k++) {
+        const int gidx = lane * NC + k;
+        int m_up, e_up, m_left, f_left, m_diag;
+        if (PAR == 0) {
+            m_up = mO[k]; e_up = eO[k]; m_diag = mE[k];
+            if (k == 0) { m_left = xm; f_left = xo; } else { m_left = mO[k > 0 ? k - 1 : 0]; f_left = fO[k > 0 ? k - 1 : 0]; }
+        } else {
+            m_left = mE[k]; f_left = fE[k]; m_diag = mO[k];
+            if (k == NC - 1) { m_up = xm; e_up = xo; } else { m_up = mE[k < NC - 1 ? k + 1 : k]; e_up = eE[k < NC - 1 ? k + 1 : k]; }
+        }
+        const int ip = U2 - gidx, jp = J2 + gidx;
+        const uint32_t ridx = min((uint32_t)(ip + 1), (uint32_t)(g.Rn + 2));  // rows outside 0..Rn hit an invalid sentinel
+        const uint32_t cidx = min((uint32_t)jp, (uint32_t)(g.Cn + 1));
+        const uint32_t rr = ws.rowrange[ridx];
+        const int sg = ws.sig[ws.rowcode[ridx] + ws.colcode[cidx]];
+        const bool ok = (uint32_t)(2 * gidx + PAR - (int)(rr & 0xffff)) <= (rr >> 16);
+        int e = addmax(e_up, gap, m_up + gap_open);
+        int f = addmax(f_left, gap, m_left + gap_open);
+        const int arc = ws.arcbuf[ring + gidx];
+        ws.arcbuf[ring + gidx] = LB_NEG;
+        int m = max3(addmax(m_diag, sg, e), f, arc);
+        if (CLAMP) m = max(m, 0);
+        if (GB) {
+            if (ip == 0) { m = (jp == 0) ? 0 : init.row_base + jp * init.row_step; e = LB_NEG; f = LB_NEG; }
+            else if (jp == 0) { m = init.col_base + ip * init.col_step; e = LB_NEG; f = LB_NEG; }
+        }
+        if (ok) box[boxbase + gidx * (2 - g.strideD)] = m;
+        nm[k] = ok ? m : LB_NEG; ne[k] = ok ? e : LB_NEG; nf[k] = ok ? f : LB_NEG;
+    }
+#pragma unroll
+    for (int k = 0; k < NC; k++) {
+        if (PAR == 0) { mE[k] = nm[k]; eE[k] = ne[k]; fE[k] = nf[k]; }
+        else { mO[k] = nm[k]; eO[k] = ne[k]; fO[k] = nf[k]; }
+    }
+}
+
+// The arc-match entry stream of one box: entries of the pair in S-order restricted to the anti-diagonals of the
+// box, consumed in chunks of 32 with the global loads (entry, D) prefetched one chunk ahead and the M(source)
+// load of a chunk left in flight across the next cell step.
+struct EntryStream {
+    const DevEntry *ent;
+    const int *dval;
+    int pos, end;        // next entry / end of the stream (relative to the pair's S-order)
+    DevEntry pre_en;     // prefetched ent[pos + lane]
+    int pre_dv;          // prefetched dval[pos + lane]
+    int pend_m, pend_d, pend_slot;  // chunk in flight: M(source) (load pending), D, accumulator slot (-1: none)
+};
+
+__device__ __forceinline__ void stream_prefetch(EntryStream &es, int lane) {
+    const int e = es.pos + lane;
+    if (e < es.end) { es.pre_en = es.ent[e]; es.pre_dv = es.dval[e]; }
+}
+
+__device__ __forceinline__ void stream_finish(EntryStream &es, const WarpSmem &ws) {
+    if (es.pend_slot >= 0) atomicMax(&ws.arcbuf[es.pend_slot], es.pend_m + es.pend_d);
+    es.pend_slot = -1;
+}
+
+// issue one chunk [pos, pos+count): filter, compute the accumulator slot, start the M(source) load
+template <int NC>
+__device__ __forceinline__ void stream_issue(EntryStream &es, const BoxGeom &g, const int *box, int count, int lane) {
+    constexpr int NW = 32 * NC;
+    es.pend_slot = -1;
+    if (lane < count) {
+        const DevEntry en = es.pre_en;
+        const int p = (int)(en.x & 0xfff) - g.al, q = (int)(en.x >> 12) - g.bl;
+        const int ar = (int)(en.y & 0xfff) - g.al, br = (int)(en.y >> 12) - g.bl;
+        // inside the box: left ends right of the origin (al' > al, bl' > bl, aligner.cc:214-215), right ends within
+        if ((p | q | (g.Rn - ar) | (g.Cn - br)) >= 0) {
+            es.pend_m = box[p * g.strideD + (q - p - g.vmin)];
+            es.pend_d = es.pre_dv;
+            es.pend_slot = ((ar + br) & (RING - 1)) * NW + ((br - ar - g.vmin) >> 1);
+        }
+    }
+    es.pos += count;
+    stream_prefetch(es, lane);
 }
 
 // Fill one M box. NC = diagonal pairs per lane (the warp covers 64*NC diagonals).
-template <int NC>
-__device__ void fill_box(const DevCtx &c, const DevPair &pr, const BoxGeom &g, const BoxInit &init, const WarpSmem &ws,
-                         int *box, const int *sig) {
+template <int NC, bool GB, bool CLAMP>
+__device__ void fill_box(const DevCtx &c, const DevPair &pr, const BoxGeom &g, const BoxInit &init, const WarpSmem &ws, int *box) {
     const int lane = threadIdx.x & 31;
     constexpr int NW = 32 * NC;
-    const int gap = c.params.gap, gap_open = c.params.gap_open;
-    const DevEntry *ent = c.ent + pr.am_base;
-    const int *dval = c.dval + pr.am_base;
-    const int *sptr = c.sptr + pr.sptr;
+    const DevParams &P = c.params;
 
     for (int k = lane; k < RING * NW; k += 32) ws.arcbuf[k] = LB_NEG;
-    __syncwarp();
+
+    // S-order offset of the first entry whose right ends lie on local anti-diagonal >= t
+    const int *sptr = c.sptr + pr.sptr;
+    const int s_base = g.al + g.bl, s_last = pr.lenA + pr.lenB + 1;
+    auto sp = [&](int t) { return __ldg(sptr + min(s_base + min(t, g.umax + 1), s_last)); };
+
+    EntryStream es;
+    es.ent = c.ent + pr.am_base; es.dval = c.dval + pr.am_base;
+    // right ends of arc matches inside the box lie on local anti-diagonals >= 8 (both arcs span >= 3 positions)
+    es.pos = sp(8); es.end = sp(g.umax + 1);
+    es.pend_slot = -1; es.pend_m = 0; es.pend_d = 0;
+    stream_prefetch(es, lane);
 
     // register state per diagonal pair: the cell last computed on the even / odd diagonal of the pair
     int mE[NC], eE[NC], fE[NC], mO[NC], eO[NC], fO[NC];
 #pragma unroll
     for (int k = 0; k < NC; k++) { mE[k] = eE[k] = fE[k] = mO[k] = eO[k] = fO[k] = LB_NEG; }
 
-    // u runs over anti-diagonals; the parity of (u - vmin) selects which diagonal of each pair is active.
-    // par0 = parity of u=0: diagonals c = 2g + par
-    const int s_base = g.al + g.bl;
-    for (int u = 0; u <= g.umax; u++) {
-        const int par = (u - g.vmin) & 1;
-        // ---- neighbour exchange across lane boundaries
-        int xm, xo;  // par==0: left neighbour's (m,f) from lane-1; par==1: up neighbour's (m,e) from lane+1
-        if (par == 0) {
-            xm = __shfl_up_sync(0xffffffffu, mO[NC - 1], 1);
-            xo = __shfl_up_sync(0xffffffffu, fO[NC - 1], 1);
-            if (lane == 0) { xm = LB_NEG; xo = LB_NEG; }
-        } else {
-            xm = __shfl_down_sync(0xffffffffu, mE[0], 1);
-            xo = __shfl_down_sync(0xffffffffu, eE[0], 1);
-            if (lane == 31) { xm = LB_NEG; xo = LB_NEG; }
-        }
-        const int ring = (u & (RING - 1)) * NW;
-        int nm[NC], ne[NC], nf[NC];
+    // seed the origin M(al, bl) = 0 (aligner.cc:289): diagonal v = 0, i.e. c = -vmin
+    const int par0 = (0 - g.vmin) & 1;
+    {
+        const int c0 = -g.vmin;
 #pragma unroll
         for (int k = 0; k < NC; k++) {
-            const int gidx = lane * NC + k;
-            const int cc = 2 * gidx + par;
-            const int v = g.vmin + cc;
-            const int ip = (u - v) >> 1, jp = (u + v) >> 1;
-            int m_up, e_up, m_left, f_left, m_diag;
-            if (par == 0) {
-                m_up = mO[k]; e_up = eO[k]; m_diag = mE[k];
-                if (k == 0) { m_left = xm; f_left = xo; } else { m_left = mO[k > 0 ? k - 1 : 0]; f_left = fO[k > 0 ? k - 1 : 0]; }
-            } else {
-                m_left = mE[k]; f_left = fE[k]; m_diag = mO[k];
-                if (k == NC - 1) { m_up = xm; e_up = xo; } else { m_up = mE[k < NC - 1 ? k + 1 : k]; e_up = eE[k < NC - 1 ? k + 1 : k]; }
-            }
-            const bool inr = (ip >= 0) & (ip <= g.Rn) & (jp >= 0) & (jp <= g.Cn);
-            const uint32_t ri = ws.rowinfo[inr ? ip : 0];
-            const int jl = ri & 0xfff, jh = (ri >> 12) & 0xfff;
-            const bool ok = inr & (jp >= jl) & (jp <= jh);
-            const uint32_t a = ri >> 24, b = ws.colinfo[inr ? jp : 0];
-            int sg;
-            if ((a | b) < 4) sg = sig[a * 4 + b];
-            else sg = (a == LB_CODE_N || b == LB_CODE_N) ? c.params.n_ext : (a == b ? c.params.match_ext : c.params.mismatch_ext);
-            int e = addmax(e_up, gap, m_up + gap_open);
-            int f = addmax(f_left, gap, m_left + gap_open);
-            int arc = LB_NEG;
-            if (gidx < g.nslots) { arc = ws.arcbuf[ring + gidx]; ws.arcbuf[ring + gidx] = LB_NEG; }
-            int m = max3(addmax(m_diag, sg, e), f, arc);
-            if (init.clamp0) m = max(m, 0);
-            if (ip == 0) { m = (jp == 0) ? 0 : init.row_base + jp * init.row_step; e = LB_NEG; f = LB_NEG; }
-            else if (jp == 0) { m = init.col_base + ip * init.col_step; e = LB_NEG; f = LB_NEG; }
-            if (!ok) { m = LB_NEG; e = LB_NEG; f = LB_NEG; }
-            else box[ip * g.strideD + cc] = m;
-            nm[k] = m; ne[k] = e; nf[k] = f;
+            if (2 * (lane * NC + k) + par0 == c0) { if (par0 == 0) mE[k] = 0; else mO[k] = 0; box[c0] = 0; }
         }
-#pragma unroll
-        for (int k = 0; k < NC; k++) {
-            if (par == 0) { mE[k] = nm[k]; eE[k] = ne[k]; fE[k] = nf[k]; }
-            else { mO[k] = nm[k]; eO[k] = ne[k]; fO[k] = nf[k]; }
-        }
-        __syncwarp();
-        // ---- fold the arc-match terms whose right ends lie on anti-diagonal u + LOOKAHEAD
-        {
-            const int ut = u + LOOKAHEAD;
-            const int s = s_base + ut;
-            if (ut <= g.umax && s <= pr.lenA + pr.lenB) {
-                const int e0 = sptr[s], e1 = sptr[s + 1];
-                const int tring = (ut & (RING - 1)) * NW;
-                for (int e = e0 + lane; e < e1; e += 32) {
-                    const DevEntry en = ent[e];
-                    const int p = (en.x & 0xfff) - g.al, q = ((en.x >> 12) & 0xfff) - g.bl;
-                    const int ar = (en.y & 0xfff) - g.al, br = ((en.y >> 12) & 0xfff) - g.bl;
-                    if (p >= 0 && q >= 0 && ar <= g.Rn && br <= g.Cn) {
-                        const int val = box[p * g.strideD + (q - p - g.vmin)] + dval[e];
-                        const int ct = br - ar - g.vmin;
-                        atomicMax(&ws.arcbuf[tring + (ct >> 1)], val);
-                    }
-                }
-            }
-        }
-        __syncwarp();
     }
+    int need_end = sp(3), allow_end = sp(9);  // for step u = 1
+    __syncwarp();
+
+    for (int u = 1; u <= g.umax; u++) {
+        // (1) land the chunk that was in flight across the previous step
+        stream_finish(es, ws);
+        const int next_need = sp(u + 3), next_allow = sp(u + 9);
+        __syncwarp();
+        // (2) cells of anti-diagonal u
+        if (((u + par0) & 1) == 0) dp_step<NC, 0, GB, CLAMP>(g, init, ws, box, P, u, lane, mE, eE, fE, mO, eO, fO);
+        else dp_step<NC, 1, GB, CLAMP>(g, init, ws, box, P, u, lane, mE, eE, fE, mO, eO, fO);
+        __syncwarp();
+        // (3) stream arc-match entries: everything with right ends on anti-diagonal <= u+1 must be issued now (it lands
+        //     before step u+1); entries up to anti-diagonal u+7 may be issued (their sources M(al'-1,bl'-1) lie >= 8
+        //     anti-diagonals back, i.e. are final after step u-1). Prefer full chunks.
+        int quota = 1;
+        while (es.pos < need_end || (quota > 0 && allow_end - es.pos >= 32)) {
+            stream_finish(es, ws);
+            stream_issue<NC>(es, g, box, min(32, allow_end - es.pos), lane);
+            quota--;
+        }
+        need_end = next_need; allow_end = next_allow;
+    }
+    stream_finish(es, ws);
+    __syncwarp();
 }
 
 __device__ __forceinline__ int box_get(const int *box, const BoxGeom &g, int ip, int jp) { return box[ip * g.strideD + (jp - ip - g.vmin)]; }
 
 // Dispatch on the number of diagonal pairs per lane (NCMAX bounds the instantiated variants and thereby
 // the register footprint of the kernel). Returns false if the band is wider than supported.
-template <int NCMAX>
-__device__ bool run_box(const DevCtx &c, const DevPair &pr, const BoxGeom &g, const BoxInit &init, const WarpSmem &ws, int *box,
-                        const int *sig) {
+template <int NCMAX, bool GB, bool CLAMP>
+__device__ bool run_box(const DevCtx &c, const DevPair &pr, const BoxGeom &g, const BoxInit &init, const WarpSmem &ws, int *box) {
     const int nc = (g.nslots + 31) >> 5;
-    if (nc <= 1) fill_box<1>(c, pr, g, init, ws, box, sig);
-    else if (NCMAX >= 2 && nc <= 2) fill_box<(NCMAX >= 2 ? 2 : 1)>(c, pr, g, init, ws, box, sig);
-    else if (NCMAX >= 3 && nc <= 3) fill_box<(NCMAX >= 3 ? 3 : 1)>(c, pr, g, init, ws, box, sig);
-    else if (NCMAX >= 4 && nc <= 4) fill_box<(NCMAX >= 4 ? 4 : 1)>(c, pr, g, init, ws, box, sig);
-    else if (NCMAX >= 8 && nc <= 8) fill_box<(NCMAX >= 8 ? 8 : 1)>(c, pr, g, init, ws, box, sig);
-    else if (NCMAX >= 16 && nc <= 16) fill_box<(NCMAX >= 16 ? 16 : 1)>(c, pr, g, init, ws, box, sig);
+    if (nc <= 1) fill_box<1, GB, CLAMP>(c, pr, g, init, ws, box);
+    else if (NCMAX >= 2 && nc <= 2) fill_box<(NCMAX >= 2 ? 2 : 1), GB, CLAMP>(c, pr, g, init, ws, box);
+    else if (NCMAX >= 3 && nc <= 3) fill_box<(NCMAX >= 3 ? 3 : 1), GB, CLAMP>(c, pr, g, init, ws, box);
+    else if (NCMAX >= 4 && nc <= 4) fill_box<(NCMAX >= 4 ? 4 : 1), GB, CLAMP>(c, pr, g, init, ws, box);
+    else if (NCMAX >= 8 && nc <= 8) fill_box<(NCMAX >= 8 ? 8 : 1), GB, CLAMP>(c, pr, g, init, ws, box);
+    else if (NCMAX >= 16 && nc <= 16) fill_box<(NCMAX >= 16 ? 16 : 1), GB, CLAMP>(c, pr, g, init, ws, box);
     else return false;
     return true;
 }
 
-// shared memory layout of a one-warp CTA: [sigma4 16][rowinfo maxrows][colinfo maxcols (bytes, padded)][arcbuf RING*32*LB_MAX_NC ... sized by host][box ...]
-__device__ __forceinline__ void carve(const DevCtx &c, int *smem, int *&sig, WarpSmem &ws, int &box_words) {
-    sig = smem;
-    ws.rowinfo = (uint32_t *)(smem + 16);
-    ws.colinfo = (uint8_t *)(ws.rowinfo + c.max_rows);
-    ws.arcbuf = (int *)(ws.colinfo + c.max_cols_padded);
-    ws.box = ws.arcbuf + c.arcbuf_words;
-    box_words = c.smem_words - (int)(ws.box - smem);
+// shared memory layout of a one-warp CTA: [sig 64][rowrange max_rows+2][rowcode max_rows+2 (bytes, padded)][colcode max_cols+1 (bytes, padded)][arcbuf]
+__device__ __forceinline__ void carve(const DevCtx &c, int *smem, WarpSmem &ws) {
+    int *sig = smem;
+    ws.sig = sig;
+    ws.rowrange = (uint32_t *)(smem + 64);
+    ws.rowcode = (uint8_t *)(ws.rowrange + c.max_rows + 2);
+    ws.colcode = ws.rowcode + c.rowcode_bytes;
+    ws.arcbuf = (int *)(ws.colcode + c.colcode_bytes);
+    const int lane = threadIdx.x & 31;
+    sig[lane] = c.params.sigma8[lane]; sig[lane + 32] = c.params.sigma8[lane + 32];
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
 // D-fill kernel: persistent one-warp CTAs pull the tasks of one scheduling level from an atomic cursor.
 // Tasks of a level are mutually independent: a task reads D only for arc matches strictly inside its
 // box, whose left ends have a larger al+bl (aligner.cc:675-728; levels = al+bl descending, two at a time).
-template <int NCMAX>
+template <int NCMAX, bool GB>
 __global__ void __launch_bounds__(32) dfill_kernel(DevCtx c, int task_begin, int task_end, int *cursor) {
     extern __shared__ int smem[];
     const int lane = threadIdx.x;
-    int *sig; WarpSmem ws; int box_words;
-    carve(c, smem, sig, ws, box_words);
-    if (lane < 16) sig[lane] = c.params.sigma4[lane];
-    __syncwarp();
-    int *scratch = c.scratch + (size_t)blockIdx.x * c.scratch_words;
+    WarpSmem ws;
+    carve(c, smem, ws);
+    int *box = c.scratch + (size_t)blockIdx.x * c.scratch_words;
     const bool nolp = c.params.no_lonely_pairs != 0;
     BoxInit init;
-    init.col_base = c.params.open; init.col_step = c.params.gap; init.row_base = c.params.open; init.row_step = c.params.gap; init.clamp0 = 0;
+    init.col_base = c.params.open; init.col_step = c.params.gap; init.row_base = c.params.open; init.row_step = c.params.gap;
 
     for (;;) {
         int t = 0;
@@ -245,11 +330,9 @@ __global__ void __launch_bounds__(32) dfill_kernel(DevCtx c, int task_begin, int
         const DevTask task = c.tasks[t];
         const DevPair pr = c.pairs[task.pair];
         BoxGeom g;
-        setup_box(c, pr, task.al, task.bl, task.R, task.C, g, ws.rowinfo, ws.colinfo);
-        const int need = (g.Rn + 1) * g.strideD;
-        int *box = (need <= box_words) ? ws.box : scratch;
-        if (need > c.scratch_words && need > box_words) { if (lane == 0) atomicExch(c.error_flag, 2); continue; }
-        if (!run_box<NCMAX>(c, pr, g, init, ws, box, sig)) { if (lane == 0) atomicExch(c.error_flag, 1); continue; }
+        setup_box(c, pr, task.al, task.bl, task.R, task.C, g, ws);
+        if ((g.Rn + 1) * g.strideD > c.scratch_words) { if (lane == 0) atomicExch(c.error_flag, 2); continue; }
+        if (!run_box<NCMAX, GB, false>(c, pr, g, init, ws, box)) { if (lane == 0) atomicExch(c.error_flag, 1); continue; }
         // ---- D entries of all arc matches with these left ends (aligner.cc:574-657)
         const DevArcMatch *am = c.am + pr.am_base;
         int *dval = c.dval + pr.am_base;
@@ -274,22 +357,19 @@ __global__ void __launch_bounds__(32) dfill_kernel(DevCtx c, int task_begin, int
 
 // ------------------------------------------------------------------------------------------------
 // Top level (aligner.cc:736-880): one box over the whole band with al = bl = 0, then the score.
-template <int NCMAX>
+template <int NCMAX, bool CLAMP>
 __global__ void __launch_bounds__(32) toplevel_kernel(DevCtx c, int pair_begin, int pair_end, int *cursor) {
     extern __shared__ int smem[];
     const int lane = threadIdx.x;
-    int *sig; WarpSmem ws; int box_words;
-    carve(c, smem, sig, ws, box_words);
-    if (lane < 16) sig[lane] = c.params.sigma4[lane];
-    __syncwarp();
-    int *scratch = c.scratch + (size_t)blockIdx.x * c.scratch_words;
+    WarpSmem ws;
+    carve(c, smem, ws);
+    int *box = c.scratch + (size_t)blockIdx.x * c.scratch_words;
     const DevParams &P = c.params;
     BoxInit init;
     // init_state(E_NO_NO, 0, lenA+1, 0, lenB+1, !allow_left_2, false, !allow_left_1, false) resp. all-local
     const bool globalA = !(P.sequ_local || P.fe_left2), globalB = !(P.sequ_local || P.fe_left1);
     init.col_base = globalA ? P.open : 0; init.col_step = globalA ? P.gap : 0;
     init.row_base = globalB ? P.open : 0; init.row_step = globalB ? P.gap : 0;
-    init.clamp0 = P.sequ_local;
     for (;;) {
         int t = 0;
         if (lane == 0) t = pair_begin + atomicAdd(cursor, 1);
@@ -297,16 +377,14 @@ __global__ void __launch_bounds__(32) toplevel_kernel(DevCtx c, int pair_begin, 
         if (t >= pair_end) break;
         const DevPair pr = c.pairs[t];
         BoxGeom g;
-        setup_box(c, pr, 0, 0, pr.lenA, pr.lenB, g, ws.rowinfo, ws.colinfo);
-        const int need = (g.Rn + 1) * g.strideD;
-        int *box = (need <= box_words) ? ws.box : scratch;
-        if (need > c.scratch_words && need > box_words) { if (lane == 0) atomicExch(c.error_flag, 2); continue; }
-        if (!run_box<NCMAX>(c, pr, g, init, ws, box, sig)) { if (lane == 0) atomicExch(c.error_flag, 1); continue; }
+        setup_box(c, pr, 0, 0, pr.lenA, pr.lenB, g, ws);
+        if ((g.Rn + 1) * g.strideD > c.scratch_words) { if (lane == 0) atomicExch(c.error_flag, 2); continue; }
+        if (!run_box<NCMAX, true, CLAMP>(c, pr, g, init, ws, box)) { if (lane == 0) atomicExch(c.error_flag, 1); continue; }
         const int n = pr.lenA, m = pr.lenB;
+        const int *lo = c.band_lo + pr.band, *hi = c.band_hi + pr.band;
+        // band cell of the top level box, normalised -inf
         auto cell = [&](int i, int j) -> int {
-            const uint32_t ri = ws.rowinfo[i];
-            const int jl = ri & 0xfff, jh = (ri >> 12) & 0xfff;
-            if (j < jl || j > jh) return LB_NEG;
+            if (j < ((i == 0) ? 0 : lo[i]) || j > min(m, hi[i])) return LB_NEG;
             const int v = box_get(box, g, i, j);
             return v < LB_NEG_LIMIT ? LB_NEG : v;
         };
@@ -320,21 +398,17 @@ __global__ void __launch_bounds__(32) toplevel_kernel(DevCtx c, int pair_begin, 
             // first strict maximum in row-major order, initial best 0 at (0,0) (aligner.cc:829-876)
             best = 0; bkey = -1;
             for (int i = 1; i <= n; i++) {
-                const uint32_t ri = ws.rowinfo[i];
-                const int jl = max(1, (int)(ri & 0xfff)), jh = (ri >> 12) & 0xfff;
+                const int jl = max(1, lo[i]), jh = min(m, hi[i]);
                 for (int j = jl + lane; j <= jh; j += 32) consider(cell(i, j), i, j, (long long)i * (m + 1) + j);
             }
         } else if (P.fe_right1 || P.fe_right2) {
             // aligner.cc:775-816: last column scanned by rows first, then the last row by columns; strict >
             if (P.fe_right2) {
-                for (int i = 1 + lane; i <= n; i += 32) {
-                    const int jh = (ws.rowinfo[i] >> 12) & 0xfff;
-                    if (jh >= m) consider(cell(i, m), i, m, (long long)i);
-                }
+                for (int i = 1 + lane; i <= n; i += 32)
+                    if (hi[i] >= m) consider(cell(i, m), i, m, (long long)i);
             }
             if (P.fe_right1) {
-                const uint32_t ri = ws.rowinfo[n];
-                const int jl = max(1, (int)(ri & 0xfff)), jh = (ri >> 12) & 0xfff;
+                const int jl = max(1, lo[n]), jh = min(m, hi[n]);
                 for (int j = jl + lane; j <= jh; j += 32) consider(cell(n, j), n, j, (long long)n + 1 + j);
             }
         } else {
@@ -368,24 +442,31 @@ __global__ void __launch_bounds__(32) toplevel_kernel(DevCtx c, int pair_begin, 
         else { CALL(16); }                                        \
     } while (0)
 
-void launch_dfill(const DevCtx &c, int ncmax, int grid, int smem_bytes, int task_begin, int task_end, int *cursor, cudaStream_t st) {
-#define CALL(N) dfill_kernel<N><<<grid, 32, smem_bytes, st>>>(c, task_begin, task_end, cursor)
+void launch_dfill(const DevCtx &c, int ncmax, bool generic_borders, int grid, int smem_bytes, int task_begin, int task_end, int *cursor,
+                  cudaStream_t st) {
+#define CALL(N)                                                                                      \
+    if (generic_borders) dfill_kernel<N, true><<<grid, 32, smem_bytes, st>>>(c, task_begin, task_end, cursor); \
+    else dfill_kernel<N, false><<<grid, 32, smem_bytes, st>>>(c, task_begin, task_end, cursor)
     LB_DISPATCH(ncmax, CALL);
 #undef CALL
 }
 void launch_toplevel(const DevCtx &c, int ncmax, int grid, int smem_bytes, int pair_begin, int pair_end, int *cursor, cudaStream_t st) {
-#define CALL(N) toplevel_kernel<N><<<grid, 32, smem_bytes, st>>>(c, pair_begin, pair_end, cursor)
+    const bool clamp = c.params.sequ_local != 0;
+#define CALL(N)                                                                                      \
+    if (clamp) toplevel_kernel<N, true><<<grid, 32, smem_bytes, st>>>(c, pair_begin, pair_end, cursor); \
+    else toplevel_kernel<N, false><<<grid, 32, smem_bytes, st>>>(c, pair_begin, pair_end, cursor)
     LB_DISPATCH(ncmax, CALL);
 #undef CALL
 }
 cudaError_t configure_kernels(int ncmax, int smem_bytes, int *dfill_ctas_per_sm) {
     cudaError_t e = cudaSuccess;
+#define SET(K) if (e == cudaSuccess) e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)
 #define CALL(N)                                                                                                         \
-    e = cudaFuncSetAttribute(dfill_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);                 \
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(toplevel_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); \
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(dfill_ctas_per_sm, dfill_kernel<N>, 32, smem_bytes)
+    SET((dfill_kernel<N, true>)); SET((dfill_kernel<N, false>)); SET((toplevel_kernel<N, true>)); SET((toplevel_kernel<N, false>)); \
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(dfill_ctas_per_sm, dfill_kernel<N, false>, 32, smem_bytes)
     LB_DISPATCH(ncmax, CALL);
 #undef CALL
+#undef SET
     return e;
 }
 

@@ -17,7 +17,8 @@
 #include "host_model.h"
 
 namespace lb200 {
-void launch_dfill(const DevCtx &c, int ncmax, int grid, int smem_bytes, int task_begin, int task_end, int *cursor, cudaStream_t st);
+void launch_dfill(const DevCtx &c, int ncmax, bool generic_borders, int grid, int smem_bytes, int task_begin, int task_end, int *cursor,
+                  cudaStream_t st);
 void launch_toplevel(const DevCtx &c, int ncmax, int grid, int smem_bytes, int pair_begin, int pair_end, int *cursor, cudaStream_t st);
 cudaError_t configure_kernels(int ncmax, int smem_bytes, int *dfill_ctas_per_sm);
 }  // namespace lb200
@@ -69,7 +70,6 @@ struct lb200_ctx {
     std::vector<PairRec> pairs;
     double last_kernel_ms = 0;
     int64_t last_launches = 0;
-    int smem_bytes = 24 * 1024;
     int host_threads = 0;
     DevBuf d_pairs, d_codes, d_band_lo, d_band_hi, d_sptr, d_ent, d_dval, d_am, d_tasks, d_top, d_scratch, d_cursor, d_flag;
     ~lb200_ctx() {
@@ -157,7 +157,6 @@ int lb200_ctx_create(int device, lb200_ctx **out) {
     lb200_default_params(&dp);
     c->params = to_params(dp);
     make_score_tables(c->params, c->tables);
-    if (const char *s = getenv("LB200_SMEM_KB")) c->smem_bytes = std::max(8, atoi(s)) * 1024;
     if (const char *s = getenv("LB200_HOST_THREADS")) c->host_threads = atoi(s);
     *out = c;
     return LB200_OK;
@@ -334,12 +333,11 @@ int lb200_run(lb200_ctx *c, int flags) {
     memset(&dc, 0, sizeof dc);
     dc.params = c->tables.dev;
     dc.max_rows = max_rows;
-    dc.max_cols_padded = (max_cols + 3) & ~3;
+    dc.rowcode_bytes = (max_rows + 2 + 3) & ~3;
+    dc.colcode_bytes = (max_cols + 1 + 3) & ~3;
     dc.arcbuf_words = 8 * 32 * nc_inst;
-    const int fixed_words = 16 + dc.max_rows + dc.max_cols_padded / 4 + dc.arcbuf_words;
-    int smem_bytes = std::max(c->smem_bytes, (fixed_words + 64) * 4);
+    const int smem_bytes = (64 + dc.max_rows + 2 + dc.arcbuf_words) * 4 + dc.rowcode_bytes + dc.colcode_bytes;
     if (smem_bytes > (int)c->prop.sharedMemPerBlockOptin) return fail(c, LB200_ERR_UNSUPPORTED, "problem needs %d bytes of shared memory per warp", smem_bytes);
-    dc.smem_words = smem_bytes / 4;
     int ctas_per_sm = 1;
     CUDA_TRY(c, configure_kernels(nc_inst, smem_bytes, &ctas_per_sm));
     const int grid_cap = std::max(1, ctas_per_sm) * c->prop.multiProcessorCount;
@@ -377,7 +375,7 @@ int lb200_run(lb200_ctx *c, int flags) {
     for (int g = 0; g < n_groups; g++) {
         const int b = group_start[g], e = group_start[g + 1];
         const int grid = std::min(grid_cap, e - b);
-        launch_dfill(dc, nc_inst, grid, smem_bytes, b, e, (int *)c->d_cursor.p + g, st);
+        launch_dfill(dc, nc_inst, c->params.indel_opening > 0, grid, smem_bytes, b, e, (int *)c->d_cursor.p + g, st);
         launches++;
     }
     launch_toplevel(dc, nc_inst, std::min(grid_cap, P), smem_bytes, 0, P, (int *)c->d_cursor.p + n_groups, st);

@@ -20,6 +20,7 @@ FLAGSETS = [
     {"max-diff-at-am": 25, "min-prob": 0.01},
     {"no-ribosum": True, "indel-opening": 0, "tau": 100},
     {"unpaired-penalty": 10, "struct-weight": 150, "noLP": True},
+    {"indel-opening": 40, "indel": -120},  # positive opening: explicit border initialisation in the D-fill kernel
 ]
 
 
@@ -57,12 +58,6 @@ def test_d_table_and_score(synth_dir, flags):
              tuple(synth_dir["short"][:2]), tuple(synth_dir["short"][2:4]), tuple(synth_dir["short"][4:6]),
              (synth_dir["short"][0], synth_dir["cfg3"][5])]
     check_pairs(pairs, flags)
-
-
-def test_spill_path_small_smem(synth_dir, monkeypatch):
-    """Boxes that do not fit the per-warp shared memory live in the L2 scratch: force that path."""
-    monkeypatch.setenv("LB200_SMEM_KB", "8")
-    check_pairs([tuple(synth_dir["cfg2"][:2]), tuple(synth_dir["cfg3"][:2])], {"noLP": True, "max-diff-am": 30})
 
 
 def test_batch_order_independent(synth_dir):

@@ -16,7 +16,7 @@ pairs = [(a, b) for a in range(n_seq) for b in range(a)]
 for a, b in pairs:
     ctx.add_pair(ids[a], ids[b])
 t = time.time(); ctx.prepare(); print("prepare %.2fs for %d pairs" % (time.time() - t, len(pairs)))
-for it in range(3):
+for it in range(int(os.environ.get("ITERS", "3"))):
     t = time.time(); ctx.run(); w = time.time() - t
     cells = sum(ctx.info(k).cells for k in range(len(pairs)))
     print("run wall %.3fs kernel %.1f ms launches %d cells %.3g GCUPS %.1f pairs/s %.1f" % (w, ctx.kernel_ms, ctx.launches, cells, cells / ctx.kernel_ms / 1e6, len(pairs) / (ctx.kernel_ms / 1e3)))
