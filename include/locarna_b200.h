@@ -79,6 +79,7 @@ typedef struct lb200_pair_info {
     int64_t n_arcmatches;
     int64_t n_tasks;
     int64_t cells;                /* DP cell updates: sum over D-fill tasks of |box ∩ band| + top level band area */
+    int64_t terms;                /* arc-match entries streamed by the D-fill tasks and the top level (each costs an add and a max) */
     int64_t n_edges;              /* alignment edges after lb200_run(LB200_RUN_TRACE) */
 } lb200_pair_info;
 
@@ -110,10 +111,18 @@ int lb200_clear_pairs(lb200_ctx *ctx);
 
 /* Host-side preparation of all pairs added so far (bands, arc matches, tasks); implied by lb200_run. */
 int lb200_prepare(lb200_ctx *ctx);
+/* Build the batch of all pairs added so far and copy it to the GPU (HBM resident until pairs change); implied by lb200_run. */
+int lb200_upload(lb200_ctx *ctx);
 /* Align all pairs added so far on the GPU. */
 int lb200_run(lb200_ctx *ctx, int flags);
 /* device time of the last lb200_run's kernels (CUDA events on the launching stream), milliseconds */
 double lb200_last_kernel_ms(const lb200_ctx *ctx);
+/* host->device bytes of the last lb200_upload (0 if lb200_run found the batch resident) and device->host bytes of the last lb200_run */
+int64_t lb200_last_h2d_bytes(const lb200_ctx *ctx);
+int64_t lb200_last_d2h_bytes(const lb200_ctx *ctx);
+/* device time and launch count of the D-fill kernel (the dominant kernel) within the last lb200_run */
+double lb200_last_dfill_ms(const lb200_ctx *ctx);
+int64_t lb200_last_dfill_launches(const lb200_ctx *ctx);
 /* number of kernel launches of the last lb200_run */
 int64_t lb200_last_launches(const lb200_ctx *ctx);
 

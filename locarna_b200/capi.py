@@ -32,13 +32,13 @@ class Params(C.Structure):
 
 class PairInfo(C.Structure):
     _fields_ = [("lenA", C.c_int), ("lenB", C.c_int), ("n_arcsA", C.c_int), ("n_arcsB", C.c_int),
-                ("n_arcmatches", C.c_int64), ("n_tasks", C.c_int64), ("cells", C.c_int64), ("n_edges", C.c_int64)]
+                ("n_arcmatches", C.c_int64), ("n_tasks", C.c_int64), ("cells", C.c_int64), ("terms", C.c_int64), ("n_edges", C.c_int64)]
 
 
 EXPORTS = [
     "lb200_default_params", "lb200_ctx_create", "lb200_ctx_destroy", "lb200_last_error", "lb200_set_params",
     "lb200_seq_add_pp", "lb200_seq_add", "lb200_seq_length", "lb200_pair_add", "lb200_num_pairs", "lb200_clear_pairs",
-    "lb200_prepare", "lb200_run", "lb200_last_kernel_ms", "lb200_last_launches", "lb200_pair_score", "lb200_get_scores",
+    "lb200_prepare", "lb200_upload", "lb200_run", "lb200_last_kernel_ms", "lb200_last_h2d_bytes", "lb200_last_d2h_bytes", "lb200_last_dfill_ms", "lb200_last_dfill_launches", "lb200_last_launches", "lb200_pair_score", "lb200_get_scores",
     "lb200_pair_get_info", "lb200_pair_band", "lb200_pair_arcmatches", "lb200_pair_alignment",
 ]
 
@@ -67,6 +67,15 @@ def load():
     lib.lb200_num_pairs.argtypes = [vp]
     lib.lb200_clear_pairs.argtypes = [vp]
     lib.lb200_prepare.argtypes = [vp]
+    lib.lb200_upload.argtypes = [vp]
+    lib.lb200_last_dfill_ms.argtypes = [vp]
+    lib.lb200_last_dfill_ms.restype = C.c_double
+    lib.lb200_last_dfill_launches.argtypes = [vp]
+    lib.lb200_last_dfill_launches.restype = C.c_int64
+    lib.lb200_last_h2d_bytes.argtypes = [vp]
+    lib.lb200_last_h2d_bytes.restype = C.c_int64
+    lib.lb200_last_d2h_bytes.argtypes = [vp]
+    lib.lb200_last_d2h_bytes.restype = C.c_int64
     lib.lb200_run.argtypes = [vp, C.c_int]
     lib.lb200_last_kernel_ms.argtypes = [vp]
     lib.lb200_last_kernel_ms.restype = C.c_double
@@ -164,12 +173,31 @@ class Context:
     def prepare(self):
         self._chk(self.lib.lb200_prepare(self.h))
 
+    def upload(self):
+        self._chk(self.lib.lb200_upload(self.h))
+
+    @property
+    def h2d_bytes(self) -> int:
+        return self.lib.lb200_last_h2d_bytes(self.h)
+
+    @property
+    def d2h_bytes(self) -> int:
+        return self.lib.lb200_last_d2h_bytes(self.h)
+
     def run(self, flags: int = RUN_SCORE_ONLY):
         self._chk(self.lib.lb200_run(self.h, flags))
 
     @property
     def kernel_ms(self) -> float:
         return self.lib.lb200_last_kernel_ms(self.h)
+
+    @property
+    def dfill_ms(self) -> float:
+        return self.lib.lb200_last_dfill_ms(self.h)
+
+    @property
+    def dfill_launches(self) -> int:
+        return self.lib.lb200_last_dfill_launches(self.h)
 
     @property
     def launches(self) -> int:

@@ -429,9 +429,14 @@ void build_pair_problem(const Sequence &A, const Sequence &B, const Band &band, 
         tk.R = (short)(nolp ? max_ar - 2 : max_ar - 1); tk.C = (short)(nolp ? max_br - 2 : max_br - 1);
         tk.run_start = r.start; tk.run_count = r.count;
         out.tasks.push_back(tk);
+        int umax = 0;
         for (int i = tk.al + 1; i <= tk.R; i++) {
             const int jl = std::max((int)tk.bl + 1, lo[i]), jh = std::min((int)tk.C, hi[i]);
-            if (jh >= jl) out.cells += jh - jl + 1;
+            if (jh >= jl) { out.cells += jh - jl + 1; umax = (i - tk.al) + (jh - tk.bl); }
+        }
+        {   // entries streamed: right ends on local anti-diagonals 8..umax
+            const int s0 = std::min(tk.al + tk.bl + 8, n + m + 1), s1 = std::min(tk.al + tk.bl + umax + 1, n + m + 1);
+            if (s1 > s0) out.terms += (uint64_t)(out.sptr[s1] - out.sptr[s0]);
         }
     }
     // bound on the diagonals (j - i) touched by any box: band cells, plus row 0 of the top level box, which is
@@ -441,8 +446,9 @@ void build_pair_problem(const Sequence &A, const Sequence &B, const Band &band, 
         dmin = std::min(dmin, lo[i] - i); dmax = std::max(dmax, hi[i] - i);
         if (i >= 1) { const int jl = std::max(1, lo[i]), jh = std::min(m, hi[i]); if (jh >= jl) out.cells += jh - jl + 1; }
     }
+    out.terms += (uint64_t)out.sptr[n + m + 1] - out.sptr[std::min(8, n + m + 1)];  // top level box
     out.wd_bound = dmax - dmin + 1;
-    out.max_box_words = (n + 1) * (out.wd_bound | 1);
+    out.max_box_words = (n + m + 1) * ((out.wd_bound + 1) / 2);  // anti-diagonal major box: (umax + 1) * diagonal pairs
 }
 
 }  // namespace lb200

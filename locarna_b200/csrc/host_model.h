@@ -78,6 +78,7 @@ struct PairProblem {
     int wd_bound = 1;                 // upper bound on the number of band diagonals of any box
     int max_box_words = 0;
     uint64_t cells = 0;               // DP cell updates of all D-fill tasks + top level (reference count)
+    uint64_t terms = 0;               // arc-match entries streamed by all boxes (S-order range of the box anti-diagonals)
 };
 void build_pair_problem(const Sequence &A, const Sequence &B, const Band &band, const Params &p, const ScoreTables &t, PairProblem &out);
 

@@ -37,8 +37,10 @@ struct BoxInit {
 
 struct BoxGeom {
     int al, bl, Rn, Cn;      // origin and local extent (rows 0..Rn, cols 0..Cn; row/col 0 are borders)
-    int vmin, strideD, umax;
-    int nslots;              // number of diagonal pairs
+    int vmin, umax;
+    int nslots;              // number of diagonal pairs = row stride of the box, which is stored anti-diagonal major:
+                             // M(i',j') lives at box[(i'+j') * nslots + ((j'-i'-vmin) >> 1)], so the cells of one step
+                             // are contiguous (coalesced stores)
 };
 
 constexpr int RING = 8;      // arc-term accumulators for 8 consecutive anti-diagonals
@@ -94,7 +96,6 @@ __device__ void setup_box(const DevCtx &c, const DevPair &pr, int al, int bl, in
     g.umax = warp_max(umax);
     const int wd = vmax - g.vmin + 1;
     g.nslots = (wd + 1) >> 1;
-    g.strideD = wd | 1;
     __syncwarp();
     // convert column ranges to diagonal ranges relative to vmin
     for (int ip = lane; ip <= g.Rn; ip += 32) {
@@ -133,7 +134,7 @@ __device__ __forceinline__ void dp_step(const BoxGeom &g, const BoxInit &init, c
     const int U2 = (u - g.vmin - PAR) >> 1;  // ip = U2 - gidx
     const int J2 = (u + g.vmin + PAR) >> 1;  // jp = J2 + gidx
     const int ring = (u & (RING - 1)) * NW;
-    const int boxbase = U2 * g.strideD + PAR;
+    int *boxrow = box + u * g.nslots;
     const int gap = P.gap, gap_open = P.gap_open;
     int nm[NC], ne[NC], nf[NC];
 #pragma unroll
@@ -163,7 +164,7 @@ __device__ __forceinline__ void dp_step(const BoxGeom &g, const BoxInit &init, c
             if (ip == 0) { m = (jp == 0) ? 0 : init.row_base + jp * init.row_step; e = LB_NEG; f = LB_NEG; }
             else if (jp == 0) { m = init.col_base + ip * init.col_step; e = LB_NEG; f = LB_NEG; }
         }
-        if (ok) box[boxbase + gidx * (2 - g.strideD)] = m;
+        if (ok) boxrow[gidx] = m;
         nm[k] = ok ? m : LB_NEG; ne[k] = ok ? e : LB_NEG; nf[k] = ok ? f : LB_NEG;
     }
 #pragma unroll
@@ -206,7 +207,7 @@ __device__ __forceinline__ void stream_issue(EntryStream &es, const BoxGeom &g, 
         const int ar = (int)(en.y & 0xfff) - g.al, br = (int)(en.y >> 12) - g.bl;
         // inside the box: left ends right of the origin (al' > al, bl' > bl, aligner.cc:214-215), right ends within
         if ((p | q | (g.Rn - ar) | (g.Cn - br)) >= 0) {
-            es.pend_m = box[p * g.strideD + (q - p - g.vmin)];
+            es.pend_m = box[(p + q) * g.nslots + ((q - p - g.vmin) >> 1)];
             es.pend_d = es.pre_dv;
             es.pend_slot = ((ar + br) & (RING - 1)) * NW + ((br - ar - g.vmin) >> 1);
         }
@@ -247,7 +248,7 @@ __device__ void fill_box(const DevCtx &c, const DevPair &pr, const BoxGeom &g, c
         const int c0 = -g.vmin;
 #pragma unroll
         for (int k = 0; k < NC; k++) {
-            if (2 * (lane * NC + k) + par0 == c0) { if (par0 == 0) mE[k] = 0; else mO[k] = 0; box[c0] = 0; }
+            if (2 * (lane * NC + k) + par0 == c0) { if (par0 == 0) mE[k] = 0; else mO[k] = 0; box[c0 >> 1] = 0; }
         }
     }
     int need_end = sp(3), allow_end = sp(9);  // for step u = 1
@@ -265,7 +266,7 @@ __device__ void fill_box(const DevCtx &c, const DevPair &pr, const BoxGeom &g, c
         // (3) stream arc-match entries: everything with right ends on anti-diagonal <= u+1 must be issued now (it lands
         //     before step u+1); entries up to anti-diagonal u+7 may be issued (their sources M(al'-1,bl'-1) lie >= 8
         //     anti-diagonals back, i.e. are final after step u-1). Prefer full chunks.
-        int quota = 1;
+        int quota = 2;
         while (es.pos < need_end || (quota > 0 && allow_end - es.pos >= 32)) {
             stream_finish(es, ws);
             stream_issue<NC>(es, g, box, min(32, allow_end - es.pos), lane);
@@ -277,7 +278,9 @@ __device__ void fill_box(const DevCtx &c, const DevPair &pr, const BoxGeom &g, c
     __syncwarp();
 }
 
-__device__ __forceinline__ int box_get(const int *box, const BoxGeom &g, int ip, int jp) { return box[ip * g.strideD + (jp - ip - g.vmin)]; }
+__device__ __forceinline__ int box_get(const int *box, const BoxGeom &g, int ip, int jp) {
+    return box[(ip + jp) * g.nslots + ((jp - ip - g.vmin) >> 1)];
+}
 
 // Dispatch on the number of diagonal pairs per lane (NCMAX bounds the instantiated variants and thereby
 // the register footprint of the kernel). Returns false if the band is wider than supported.
@@ -331,7 +334,7 @@ __global__ void __launch_bounds__(32) dfill_kernel(DevCtx c, int task_begin, int
         const DevPair pr = c.pairs[task.pair];
         BoxGeom g;
         setup_box(c, pr, task.al, task.bl, task.R, task.C, g, ws);
-        if ((g.Rn + 1) * g.strideD > c.scratch_words) { if (lane == 0) atomicExch(c.error_flag, 2); continue; }
+        if ((g.umax + 1) * g.nslots > c.scratch_words) { if (lane == 0) atomicExch(c.error_flag, 2); continue; }
         if (!run_box<NCMAX, GB, false>(c, pr, g, init, ws, box)) { if (lane == 0) atomicExch(c.error_flag, 1); continue; }
         // ---- D entries of all arc matches with these left ends (aligner.cc:574-657)
         const DevArcMatch *am = c.am + pr.am_base;
@@ -378,7 +381,7 @@ __global__ void __launch_bounds__(32) toplevel_kernel(DevCtx c, int pair_begin, 
         const DevPair pr = c.pairs[t];
         BoxGeom g;
         setup_box(c, pr, 0, 0, pr.lenA, pr.lenB, g, ws);
-        if ((g.Rn + 1) * g.strideD > c.scratch_words) { if (lane == 0) atomicExch(c.error_flag, 2); continue; }
+        if ((g.umax + 1) * g.nslots > c.scratch_words) { if (lane == 0) atomicExch(c.error_flag, 2); continue; }
         if (!run_box<NCMAX, true, CLAMP>(c, pr, g, init, ws, box)) { if (lane == 0) atomicExch(c.error_flag, 1); continue; }
         const int n = pr.lenA, m = pr.lenB;
         const int *lo = c.band_lo + pr.band, *hi = c.band_hi + pr.band;

@@ -61,7 +61,7 @@ struct lb200_ctx {
     int device = 0;
     cudaDeviceProp prop;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
     std::string err;
     Params params;
     ScoreTables tables;
@@ -70,6 +70,19 @@ struct lb200_ctx {
     std::vector<PairRec> pairs;
     double last_kernel_ms = 0;
     int64_t last_launches = 0;
+    int64_t last_h2d_bytes = 0, last_d2h_bytes = 0;
+    double last_dfill_ms = 0;
+    int64_t last_dfill_launches = 0;
+    // batch resident in HBM (lb200_upload)
+    struct Resident {
+        bool valid = false;
+        DevCtx dc;
+        int nc_inst = 1, smem_bytes = 0, grid_cap = 1, n_groups = 0;
+        std::vector<int> group_start;
+        size_t total_am = 0;
+        std::vector<long long> am_base;
+        std::vector<int> K;
+    } res;
     int host_threads = 0;
     DevBuf d_pairs, d_codes, d_band_lo, d_band_hi, d_sptr, d_ent, d_dval, d_am, d_tasks, d_top, d_scratch, d_cursor, d_flag;
     ~lb200_ctx() {
@@ -77,6 +90,7 @@ struct lb200_ctx {
         for (auto *b : all) b->release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (ev_mid) cudaEventDestroy(ev_mid);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -148,7 +162,7 @@ int lb200_ctx_create(int device, lb200_ctx **out) {
     c->device = device;
     if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&c->prop, device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess ||
-        cudaEventCreate(&c->ev1) != cudaSuccess) {
+        cudaEventCreate(&c->ev1) != cudaSuccess || cudaEventCreate(&c->ev_mid) != cudaSuccess) {
         fprintf(stderr, "locarna_b200: cannot initialise device %d: %s\n", device, cudaGetErrorString(cudaGetLastError()));
         delete c;
         return LB200_ERR_CUDA;
@@ -213,6 +227,7 @@ int lb200_pair_add(lb200_ctx *c, int seqA, int seqB, const int *min_col, const i
             if (r.band.lo[i] < 0 || r.band.hi[i] > m) return fail(c, LB200_ERR_ARG, "band out of range in row %d", i);
     }
     c->pairs.push_back(std::move(r));
+    c->res.valid = false;
     return (int)c->pairs.size() - 1;
 }
 
@@ -220,6 +235,7 @@ int lb200_num_pairs(const lb200_ctx *c) { return c ? (int)c->pairs.size() : LB20
 int lb200_clear_pairs(lb200_ctx *c) {
     if (!c) return LB200_ERR_ARG;
     c->pairs.clear();
+    c->res.valid = false;
     return LB200_OK;
 }
 
@@ -264,13 +280,13 @@ int lb200_prepare(lb200_ctx *c) {
     return LB200_OK;
 }
 
-int lb200_run(lb200_ctx *c, int flags) {
+int lb200_upload(lb200_ctx *c) {
     if (!c) return LB200_ERR_ARG;
-    if (c->device == LB200_DEVICE_NONE) return fail(c, LB200_ERR_CUDA, "host-only context: lb200_run needs a CUDA device (no CPU fallback)");
-    if (flags & LB200_RUN_TRACE) return fail(c, LB200_ERR_UNSUPPORTED, "device traceback is not implemented yet");
+    if (c->device == LB200_DEVICE_NONE) return fail(c, LB200_ERR_CUDA, "host-only context: lb200_upload needs a CUDA device (no CPU fallback)");
     CUDA_TRY(c, cudaSetDevice(c->device));
     const int P = (int)c->pairs.size();
-    c->last_kernel_ms = 0; c->last_launches = 0;
+    c->res.valid = false;
+    c->last_h2d_bytes = 0;
     if (P == 0) return LB200_OK;
     { const int rc = lb200_prepare(c); if (rc != LB200_OK) return rc; }
 
@@ -365,6 +381,33 @@ int lb200_run(lb200_ctx *c, int flags) {
     dc.ent = (const DevEntry *)c->d_ent.p; dc.dval = (int *)c->d_dval.p; dc.am = (const DevArcMatch *)c->d_am.p;
     dc.tasks = (const DevTask *)c->d_tasks.p; dc.top = (DevTopResult *)c->d_top.p; dc.scratch = (int *)c->d_scratch.p;
     dc.error_flag = (int *)c->d_flag.p;
+    CUDA_TRY(c, cudaStreamSynchronize(st));  // the host staging vectors go out of scope
+    c->last_h2d_bytes = (int64_t)(h_pairs.size() * sizeof(DevPair) + h_codes.size() + (h_lo.size() + h_hi.size() + h_sptr.size()) * 4 +
+                                  h_ent.size() * sizeof(DevEntry) + h_am.size() * sizeof(DevArcMatch) + h_tasks.size() * sizeof(DevTask));
+    lb200_ctx::Resident &R = c->res;
+    R.dc = dc; R.nc_inst = nc_inst; R.smem_bytes = smem_bytes; R.grid_cap = grid_cap; R.n_groups = n_groups;
+    R.group_start = group_start; R.total_am = total_am;
+    R.am_base.resize(P); R.K.resize(P);
+    for (int k = 0; k < P; k++) { R.am_base[k] = h_pairs[k].am_base; R.K[k] = h_pairs[k].K; }
+    R.valid = true;
+    return LB200_OK;
+}
+
+int lb200_run(lb200_ctx *c, int flags) {
+    if (!c) return LB200_ERR_ARG;
+    if (c->device == LB200_DEVICE_NONE) return fail(c, LB200_ERR_CUDA, "host-only context: lb200_run needs a CUDA device (no CPU fallback)");
+    if (flags & LB200_RUN_TRACE) return fail(c, LB200_ERR_UNSUPPORTED, "device traceback is not implemented yet");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const int P = (int)c->pairs.size();
+    c->last_kernel_ms = 0; c->last_launches = 0; c->last_d2h_bytes = 0;
+    if (P == 0) return LB200_OK;
+    if (!c->res.valid) { const int rc = lb200_upload(c); if (rc != LB200_OK) return rc; } else c->last_h2d_bytes = 0;
+    const lb200_ctx::Resident &R = c->res;
+    const DevCtx &dc = R.dc;
+    const int nc_inst = R.nc_inst, smem_bytes = R.smem_bytes, grid_cap = R.grid_cap, n_groups = R.n_groups;
+    const std::vector<int> &group_start = R.group_start;
+    const size_t total_am = R.total_am;
+    cudaStream_t st = c->stream;
 
     // ---- run: D entries start as -inf (aligner.cc:122-123)
     CUDA_TRY(c, cudaEventRecord(c->ev0, st));
@@ -378,6 +421,7 @@ int lb200_run(lb200_ctx *c, int flags) {
         launch_dfill(dc, nc_inst, c->params.indel_opening > 0, grid, smem_bytes, b, e, (int *)c->d_cursor.p + g, st);
         launches++;
     }
+    CUDA_TRY(c, cudaEventRecord(c->ev_mid, st));
     launch_toplevel(dc, nc_inst, std::min(grid_cap, P), smem_bytes, 0, P, (int *)c->d_cursor.p + n_groups, st);
     launches++;
     CUDA_TRY(c, cudaGetLastError());
@@ -396,19 +440,26 @@ int lb200_run(lb200_ctx *c, int flags) {
     CUDA_TRY(c, cudaStreamSynchronize(st));
     float ms = 0;
     CUDA_TRY(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    c->last_kernel_ms = ms; c->last_launches = launches;
+    float ms_dfill = 0;
+    CUDA_TRY(c, cudaEventElapsedTime(&ms_dfill, c->ev0, c->ev_mid));
+    c->last_kernel_ms = ms; c->last_launches = launches; c->last_dfill_ms = ms_dfill; c->last_dfill_launches = n_groups;
+    c->last_d2h_bytes = (int64_t)((size_t)P * sizeof(DevTopResult) + 16 + h_dval.size() * 4);
     if (h_flag[0] != 0) return fail(c, LB200_ERR_UNSUPPORTED, "kernel reported error %d (1: band too wide, 2: box exceeds scratch)", h_flag[0]);
     for (int k = 0; k < P; k++) {
         PairRec &r = c->pairs[k];
         r.neg_inf = h_top[k].score < LB_NEG_LIMIT;
         r.score = r.neg_inf ? 0 : h_top[k].score;
         r.max_i = h_top[k].max_i; r.max_j = h_top[k].max_j;
-        if (flags & LB200_RUN_KEEP_D) r.dvals.assign(h_dval.begin() + h_pairs[k].am_base, h_dval.begin() + h_pairs[k].am_base + h_pairs[k].K);
+        if (flags & LB200_RUN_KEEP_D) r.dvals.assign(h_dval.begin() + R.am_base[k], h_dval.begin() + R.am_base[k] + R.K[k]);
     }
     return LB200_OK;
 }
 
 double lb200_last_kernel_ms(const lb200_ctx *c) { return c ? c->last_kernel_ms : 0; }
+double lb200_last_dfill_ms(const lb200_ctx *c) { return c ? c->last_dfill_ms : 0; }
+int64_t lb200_last_dfill_launches(const lb200_ctx *c) { return c ? c->last_dfill_launches : 0; }
+int64_t lb200_last_h2d_bytes(const lb200_ctx *c) { return c ? c->last_h2d_bytes : 0; }
+int64_t lb200_last_d2h_bytes(const lb200_ctx *c) { return c ? c->last_d2h_bytes : 0; }
 int64_t lb200_last_launches(const lb200_ctx *c) { return c ? c->last_launches : 0; }
 
 int lb200_pair_score(const lb200_ctx *c, int pair, int64_t *score) {
@@ -430,7 +481,7 @@ int lb200_pair_get_info(const lb200_ctx *c, int pair, lb200_pair_info *info) {
     memset(info, 0, sizeof *info);
     info->lenA = c->seqs[r.seqA].len; info->lenB = c->seqs[r.seqB].len;
     info->n_arcsA = (int)c->seqs[r.seqA].arcs.size(); info->n_arcsB = (int)c->seqs[r.seqB].arcs.size();
-    info->n_arcmatches = (int64_t)r.prob.am.size(); info->n_tasks = (int64_t)r.prob.tasks.size(); info->cells = (int64_t)r.prob.cells;
+    info->n_arcmatches = (int64_t)r.prob.am.size(); info->n_tasks = (int64_t)r.prob.tasks.size(); info->cells = (int64_t)r.prob.cells; info->terms = (int64_t)r.prob.terms;
     info->n_edges = (int64_t)r.edges_a.size();
     return LB200_OK;
 }
