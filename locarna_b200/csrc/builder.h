@@ -1,0 +1,39 @@
+// Device builder interface (builder.cu): arc matches, S-order, tasks of a batch of pairs.
+#ifndef LB200_BUILDER_H
+#define LB200_BUILDER_H
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include "dev_types.h"
+
+namespace lb200 {
+
+struct BuildCtx {
+    // inputs
+    DevPair *pairs;
+    const uint8_t *codes;
+    const int *band_lo, *band_hi, *cell_rev;   // cell_rev[al] = number of band cells in rows > al
+    const int *arc_left, *arc_right, *arc_weight, *lptr, *lcount;
+    const int *am_seq;                          // 256: (tau * ribosum arc-match score) / 100
+    int sigma8[64];
+    int tau, use_ribosum, no_lonely_pairs, max_diff_am, max_diff_at_am;
+    // outputs / work arrays
+    int *cell_start;                            // total_cells + 1: counts, then exclusive offsets (global L-order index)
+    DevArcMatch *am;
+    DevEntry *ent;
+    int *sptr;
+    unsigned long long *skeys, *skeys_sorted;
+    unsigned *svals, *svals_sorted;
+    DevTask *tasks_unsorted, *tasks;
+    unsigned *tkeys, *tkeys_sorted, *tvals, *tvals_sorted;
+    unsigned *n_tasks;
+    int *qstart;                                // 4098 entries
+    DevPairStats *stats;
+};
+
+cudaError_t builder_count(const BuildCtx &b, int n_pairs, long long total_cells, void *tmp, size_t tmp_bytes, size_t *tmp_need, cudaStream_t st);
+size_t builder_sort_tmp_bytes(long long total_am, int n_pairs);
+cudaError_t builder_fill(const BuildCtx &b, int n_pairs, long long total_am, long long sptr_total, void *tmp, size_t tmp_bytes, cudaStream_t st);
+cudaError_t builder_sort_tasks(const BuildCtx &b, unsigned n_tasks, void *tmp, size_t tmp_bytes, cudaStream_t st);
+
+}  // namespace lb200
+#endif

@@ -15,6 +15,8 @@ struct DevCtx {
     int *dval;               // D(arcA,arcB) in S-order
     const DevArcMatch *am;   // L-order
     const DevTask *tasks;
+    const int *qstart;       // task range of level group q = 4095 - ((al+bl)>>1): tasks[qstart[q] .. qstart[q+1])
+    int *cursor;             // per level group work cursor (4097 entries) + 1 for the top level
     DevTopResult *top;
     int *scratch;            // per-CTA M box spill area (L2 resident)
     int scratch_words;

@@ -30,11 +30,22 @@ struct DevParams {
 struct DevPair {
     int lenA, lenB;
     int codesA, codesB;   // offsets into codes[] (1-based position p at codes[off + p])
-    int band;             // offset into band_lo[] / band_hi[] (entries 0..lenA)
-    int sptr;             // offset into sptr[] (entries 0..lenA+lenB+1): S-order start per anti-diagonal ar+br
-    int K;                // number of arc matches
-    int pad;
-    long long am_base;    // offset of this pair's arc matches in the L-order and S-order arrays
+    int band;             // offset into band_lo[] / band_hi[] / cell_rev[] (entries 0..lenA)
+    int sptr;             // offset into sptr[] (entries 0..lenA+lenB+2): S-order start per anti-diagonal ar+br
+    int arcsA, arcsB;     // offsets into arc_left[] / arc_right[] / arc_weight[] (arcs in BasePairs index order)
+    int lptrA, lptrB;     // offsets into lptr[] / lcount[] (entries 0..len+1): arcs with a given left end
+    int n_cells;          // band cells (al, bl) with al >= 1, bl >= 1
+    int K;                // number of arc matches                                       (filled by the device builder)
+    long long cell_base;  // offset of this pair's cells in the cell arrays (cells ranked al desc, bl desc)
+    long long am_base;    // offset of this pair's arc matches in the L-order / S-order arrays  (device builder)
+};
+
+// per-pair counters produced by the device builder
+struct DevPairStats {
+    long long n_tasks;
+    long long cells;      // DP cell updates: sum over D-fill tasks of |box and band| + top level band area
+    long long terms;      // arc-match entries streamed by all boxes
+    long long pad;
 };
 
 // S-order entry: one valid arc match, sorted by (ar+br, ar, al desc, bl desc)

@@ -315,9 +315,12 @@ __device__ __forceinline__ void carve(const DevCtx &c, int *smem, WarpSmem &ws) 
 // Tasks of a level are mutually independent: a task reads D only for arc matches strictly inside its
 // box, whose left ends have a larger al+bl (aligner.cc:675-728; levels = al+bl descending, two at a time).
 template <int NCMAX, bool GB>
-__global__ void __launch_bounds__(32) dfill_kernel(DevCtx c, int task_begin, int task_end, int *cursor) {
+__global__ void __launch_bounds__(32) dfill_kernel(DevCtx c, int q) {
     extern __shared__ int smem[];
     const int lane = threadIdx.x;
+    const int task_begin = c.qstart[q], task_end = c.qstart[q + 1];
+    if ((int)blockIdx.x >= task_end - task_begin) return;
+    int *cursor = c.cursor + q;
     WarpSmem ws;
     carve(c, smem, ws);
     int *box = c.scratch + (size_t)blockIdx.x * c.scratch_words;
@@ -445,11 +448,10 @@ __global__ void __launch_bounds__(32) toplevel_kernel(DevCtx c, int pair_begin, 
         else { CALL(16); }                                        \
     } while (0)
 
-void launch_dfill(const DevCtx &c, int ncmax, bool generic_borders, int grid, int smem_bytes, int task_begin, int task_end, int *cursor,
-                  cudaStream_t st) {
+void launch_dfill(const DevCtx &c, int ncmax, bool generic_borders, int grid, int smem_bytes, int q, cudaStream_t st) {
 #define CALL(N)                                                                                      \
-    if (generic_borders) dfill_kernel<N, true><<<grid, 32, smem_bytes, st>>>(c, task_begin, task_end, cursor); \
-    else dfill_kernel<N, false><<<grid, 32, smem_bytes, st>>>(c, task_begin, task_end, cursor)
+    if (generic_borders) dfill_kernel<N, true><<<grid, 32, smem_bytes, st>>>(c, q); \
+    else dfill_kernel<N, false><<<grid, 32, smem_bytes, st>>>(c, q)
     LB_DISPATCH(ncmax, CALL);
 #undef CALL
 }

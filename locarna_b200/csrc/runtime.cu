@@ -13,12 +13,12 @@
 #include <vector>
 
 #include "../../include/locarna_b200.h"
+#include "builder.h"
 #include "dev_ctx.h"
 #include "host_model.h"
 
 namespace lb200 {
-void launch_dfill(const DevCtx &c, int ncmax, bool generic_borders, int grid, int smem_bytes, int task_begin, int task_end, int *cursor,
-                  cudaStream_t st);
+void launch_dfill(const DevCtx &c, int ncmax, bool generic_borders, int grid, int smem_bytes, int q, cudaStream_t st);
 void launch_toplevel(const DevCtx &c, int ncmax, int grid, int smem_bytes, int pair_begin, int pair_end, int *cursor, cudaStream_t st);
 cudaError_t configure_kernels(int ncmax, int smem_bytes, int *dfill_ctas_per_sm);
 }  // namespace lb200
@@ -48,10 +48,13 @@ struct PairRec {
     int seqA, seqB;
     Band band;
     PairProblem prob;
-    bool built = false;
+    bool built = false;      // host mirror of the arc-match tables (host-only contexts / inspection without a GPU)
+    bool banded = false;     // band available
+    // device builder results
+    long long am_base = 0; int K = 0;
+    DevPairStats stats = {0, 0, 0, 0};
     // results
     int64_t score = 0; bool neg_inf = true; int max_i = 0, max_j = 0;
-    std::vector<int> dvals;  // S-order, when LB200_RUN_KEEP_D
     std::vector<int> edges_a, edges_b; std::string str_a, str_b;
 };
 
@@ -77,16 +80,19 @@ struct lb200_ctx {
     struct Resident {
         bool valid = false;
         DevCtx dc;
-        int nc_inst = 1, smem_bytes = 0, grid_cap = 1, n_groups = 0;
-        std::vector<int> group_start;
+        int nc_inst = 1, smem_bytes = 0, grid_cap = 1, q_lo = 0, q_hi = 0;
         size_t total_am = 0;
-        std::vector<long long> am_base;
-        std::vector<int> K;
     } res;
     int host_threads = 0;
+    size_t seqs_uploaded = 0;  // sequences whose arrays are on the device
+    std::vector<int> seq_codes_off, seq_arcs_off, seq_lptr_off;
+    DevBuf d_arc_left, d_arc_right, d_arc_weight, d_lptr, d_lcount, d_am_seq, d_cell_rev, d_cell_start, d_skeys, d_skeys2, d_svals, d_svals2,
+        d_tasks_unsorted, d_tkeys, d_tkeys2, d_tvals, d_tvals2, d_ntasks, d_qstart, d_stats, d_tmp;
     DevBuf d_pairs, d_codes, d_band_lo, d_band_hi, d_sptr, d_ent, d_dval, d_am, d_tasks, d_top, d_scratch, d_cursor, d_flag;
     ~lb200_ctx() {
-        DevBuf *all[] = {&d_pairs, &d_codes, &d_band_lo, &d_band_hi, &d_sptr, &d_ent, &d_dval, &d_am, &d_tasks, &d_top, &d_scratch, &d_cursor, &d_flag};
+        DevBuf *all[] = {&d_pairs, &d_codes, &d_band_lo, &d_band_hi, &d_sptr, &d_ent, &d_dval, &d_am, &d_tasks, &d_top, &d_scratch, &d_cursor, &d_flag,
+                         &d_arc_left, &d_arc_right, &d_arc_weight, &d_lptr, &d_lcount, &d_am_seq, &d_cell_rev, &d_cell_start, &d_skeys, &d_skeys2,
+                         &d_svals, &d_svals2, &d_tasks_unsorted, &d_tkeys, &d_tkeys2, &d_tvals, &d_tvals2, &d_ntasks, &d_qstart, &d_stats, &d_tmp};
         for (auto *b : all) b->release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -262,21 +268,66 @@ static cudaError_t upload(DevBuf &b, const std::vector<T> &v, cudaStream_t st) {
 
 extern "C" {
 
-int lb200_prepare(lb200_ctx *c) {
-    if (!c) return LB200_ERR_ARG;
+// bands of all pairs that do not have one yet (host, all cores)
+static void derive_bands(lb200_ctx *c) {
     const int P = (int)c->pairs.size();
-    // ---- host: bands (unless supplied) and per-pair problems
     parallel_for(P, c->host_threads, [&](int k) {
         PairRec &r = c->pairs[k];
-        if (r.built) return;
+        if (r.banded) return;
         const Sequence &A = c->seqs[r.seqA], &B = c->seqs[r.seqB];
         if (r.band.lo.empty()) {
             r.band = make_band(A.len, B.len, c->params.max_diff);
             restrict_band_by_envelope(r.band, A, B, c->params);
         }
-        build_pair_problem(A, B, r.band, c->params, c->tables, r.prob);
+        r.banded = true;
+    });
+}
+
+int lb200_prepare(lb200_ctx *c) {
+    if (!c) return LB200_ERR_ARG;
+    derive_bands(c);
+    if (c->device != LB200_DEVICE_NONE) return LB200_OK;
+    // host-only context: mirror of the device builder, for inspection without a GPU
+    const int P = (int)c->pairs.size();
+    parallel_for(P, c->host_threads, [&](int k) {
+        PairRec &r = c->pairs[k];
+        if (r.built) return;
+        build_pair_problem(c->seqs[r.seqA], c->seqs[r.seqB], r.band, c->params, c->tables, r.prob);
+        r.K = (int)r.prob.am.size();
+        r.stats.n_tasks = (long long)r.prob.tasks.size(); r.stats.cells = (long long)r.prob.cells; r.stats.terms = (long long)r.prob.terms;
         r.built = true;
     });
+    return LB200_OK;
+}
+
+// sequences -> device arrays (codes, arcs in index order, arc weights, left-end index)
+static int upload_sequences(lb200_ctx *c) {
+    if (c->seqs_uploaded == c->seqs.size()) return LB200_OK;
+    std::vector<uint8_t> codes;
+    std::vector<int> al, ar, aw, lptr, lcount;
+    c->seq_codes_off.clear(); c->seq_arcs_off.clear(); c->seq_lptr_off.clear();
+    for (const Sequence &s : c->seqs) {
+        c->seq_codes_off.push_back((int)codes.size());
+        codes.insert(codes.end(), s.codes.begin(), s.codes.end());
+        c->seq_arcs_off.push_back((int)al.size());
+        const std::vector<int> w = arc_weights(s, c->params);
+        for (size_t k = 0; k < s.arcs.size(); k++) { al.push_back(s.arcs[k].left); ar.push_back(s.arcs[k].right); aw.push_back(w[k]); }
+        c->seq_lptr_off.push_back((int)lptr.size());
+        lptr.insert(lptr.end(), s.lptr.begin(), s.lptr.end());
+        lcount.insert(lcount.end(), s.lcount.begin(), s.lcount.end());
+    }
+    cudaStream_t st = c->stream;
+    std::vector<int> amseq(c->tables.am_seq, c->tables.am_seq + 256);
+    CUDA_TRY(c, upload(c->d_codes, codes, st));
+    CUDA_TRY(c, upload(c->d_arc_left, al, st));
+    CUDA_TRY(c, upload(c->d_arc_right, ar, st));
+    CUDA_TRY(c, upload(c->d_arc_weight, aw, st));
+    CUDA_TRY(c, upload(c->d_lptr, lptr, st));
+    CUDA_TRY(c, upload(c->d_lcount, lcount, st));
+    CUDA_TRY(c, upload(c->d_am_seq, amseq, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    c->last_h2d_bytes += (int64_t)(codes.size() + (al.size() * 3 + lptr.size() * 2 + 256) * 4);
+    c->seqs_uploaded = c->seqs.size();
     return LB200_OK;
 }
 
@@ -288,57 +339,44 @@ int lb200_upload(lb200_ctx *c) {
     c->res.valid = false;
     c->last_h2d_bytes = 0;
     if (P == 0) return LB200_OK;
-    { const int rc = lb200_prepare(c); if (rc != LB200_OK) return rc; }
+    derive_bands(c);
+    { const int rc = upload_sequences(c); if (rc != LB200_OK) return rc; }
+    cudaStream_t st = c->stream;
 
-    // ---- flatten into batch arrays
+    // ---- per-pair inputs: band, cell ranks, offsets
     std::vector<DevPair> h_pairs(P);
-    std::vector<uint8_t> h_codes;
-    std::vector<int> seq_off(c->seqs.size(), -1);
-    std::vector<int> h_lo, h_hi, h_sptr;
-    std::vector<DevEntry> h_ent;
-    std::vector<DevArcMatch> h_am;
-    std::vector<DevTask> h_tasks;
-    size_t total_am = 0, total_tasks = 0;
-    int wd_bound = 1, max_rows = 1, max_cols = 1;
-    for (auto &r : c->pairs) { total_am += r.prob.am.size(); total_tasks += r.prob.tasks.size(); }
-    h_ent.reserve(total_am); h_am.reserve(total_am); h_tasks.reserve(total_tasks);
+    std::vector<int> h_lo, h_hi, h_rev;
+    long long total_cells = 0, sptr_total = 0;
+    int wd_bound = 1, max_rows = 1, max_cols = 1, max_box_words = 1;
     for (int k = 0; k < P; k++) {
         PairRec &r = c->pairs[k];
-        for (int s : {r.seqA, r.seqB}) {
-            if (seq_off[s] < 0) {
-                seq_off[s] = (int)h_codes.size();
-                h_codes.insert(h_codes.end(), c->seqs[s].codes.begin(), c->seqs[s].codes.end());
-            }
-        }
         DevPair &d = h_pairs[k];
-        d.lenA = c->seqs[r.seqA].len; d.lenB = c->seqs[r.seqB].len;
-        d.codesA = seq_off[r.seqA]; d.codesB = seq_off[r.seqB];
+        memset(&d, 0, sizeof d);
+        const int n = c->seqs[r.seqA].len, m = c->seqs[r.seqB].len;
+        d.lenA = n; d.lenB = m;
+        d.codesA = c->seq_codes_off[r.seqA]; d.codesB = c->seq_codes_off[r.seqB];
+        d.arcsA = c->seq_arcs_off[r.seqA]; d.arcsB = c->seq_arcs_off[r.seqB];
+        d.lptrA = c->seq_lptr_off[r.seqA]; d.lptrB = c->seq_lptr_off[r.seqB];
         d.band = (int)h_lo.size();
         h_lo.insert(h_lo.end(), r.band.lo.begin(), r.band.lo.end());
         h_hi.insert(h_hi.end(), r.band.hi.begin(), r.band.hi.end());
-        d.sptr = (int)h_sptr.size();
-        h_sptr.insert(h_sptr.end(), r.prob.sptr.begin(), r.prob.sptr.end());
-        d.K = (int)r.prob.am.size(); d.pad = 0;
-        d.am_base = (long long)h_am.size();
-        h_am.insert(h_am.end(), r.prob.am.begin(), r.prob.am.end());
-        h_ent.insert(h_ent.end(), r.prob.ent.begin(), r.prob.ent.end());
-        for (DevTask t : r.prob.tasks) { t.pair = k; h_tasks.push_back(t); }
-        wd_bound = std::max(wd_bound, r.prob.wd_bound);
-        max_rows = std::max(max_rows, d.lenA + 1); max_cols = std::max(max_cols, d.lenB + 1);
+        // cells (al, bl), al >= 1, bl >= 1, ranked al descending / bl descending; diagonal bound of any box
+        h_rev.resize(h_lo.size());
+        int cells = 0, dmin = 0, dmax = 0;
+        for (int i = n; i >= 0; i--) {
+            h_rev[d.band + i] = cells;
+            if (i >= 1) cells += std::max(0, std::min(r.band.hi[i], m) - std::max(r.band.lo[i], 1) + 1);
+            dmin = std::min(dmin, r.band.lo[i] - i); dmax = std::max(dmax, r.band.hi[i] - i);
+        }
+        d.n_cells = cells;
+        d.cell_base = total_cells; total_cells += cells;
+        d.sptr = (int)sptr_total; sptr_total += n + m + 3;
+        const int wd = dmax - dmin + 1;
+        wd_bound = std::max(wd_bound, wd);
+        max_box_words = std::max(max_box_words, (n + m + 1) * ((wd + 1) / 2));  // anti-diagonal major box
+        max_rows = std::max(max_rows, n + 1); max_cols = std::max(max_cols, m + 1);
     }
-    // ---- schedule: groups of two levels (al+bl)>>1, descending; larger boxes first inside a group
-    auto group_of = [](const DevTask &t) { return ((int)t.al + (int)t.bl) >> 1; };
-    auto size_of = [](const DevTask &t) { return ((int)t.R - t.al + 1) * ((int)t.C - t.bl + 1); };
-    std::sort(h_tasks.begin(), h_tasks.end(), [&](const DevTask &x, const DevTask &y) {
-        const int gx = group_of(x), gy = group_of(y);
-        if (gx != gy) return gx > gy;
-        return size_of(x) > size_of(y);
-    });
-    std::vector<int> group_start;
-    for (size_t t = 0; t < h_tasks.size(); t++)
-        if (t == 0 || group_of(h_tasks[t]) != group_of(h_tasks[t - 1])) group_start.push_back((int)t);
-    group_start.push_back((int)h_tasks.size());
-    const int n_groups = (int)group_start.size() - 1;
+    if (total_cells >= (1LL << 31) - 2) return fail(c, LB200_ERR_UNSUPPORTED, "batch too large (%lld band cells); split it", total_cells);
 
     // ---- kernel configuration
     const int nslots_bound = (wd_bound + 1) / 2;
@@ -357,38 +395,87 @@ int lb200_upload(lb200_ctx *c) {
     int ctas_per_sm = 1;
     CUDA_TRY(c, configure_kernels(nc_inst, smem_bytes, &ctas_per_sm));
     const int grid_cap = std::max(1, ctas_per_sm) * c->prop.multiProcessorCount;
-    int max_box_words = 0;
-    for (auto &r : c->pairs) max_box_words = std::max(max_box_words, r.prob.max_box_words);
     dc.scratch_words = max_box_words;
 
-    // ---- upload
-    cudaStream_t st = c->stream;
+    // ---- device builder
     CUDA_TRY(c, upload(c->d_pairs, h_pairs, st));
-    CUDA_TRY(c, upload(c->d_codes, h_codes, st));
     CUDA_TRY(c, upload(c->d_band_lo, h_lo, st));
     CUDA_TRY(c, upload(c->d_band_hi, h_hi, st));
-    CUDA_TRY(c, upload(c->d_sptr, h_sptr, st));
-    CUDA_TRY(c, upload(c->d_ent, h_ent, st));
-    CUDA_TRY(c, upload(c->d_am, h_am, st));
-    CUDA_TRY(c, upload(c->d_tasks, h_tasks, st));
-    CUDA_TRY(c, c->d_dval.ensure(std::max<size_t>(total_am * 4, 16)));
+    CUDA_TRY(c, upload(c->d_cell_rev, h_rev, st));
+    CUDA_TRY(c, c->d_cell_start.ensure((size_t)(total_cells + 1) * 4));
+    CUDA_TRY(c, c->d_sptr.ensure((size_t)sptr_total * 4));
+    CUDA_TRY(c, c->d_stats.ensure((size_t)P * sizeof(DevPairStats)));
+    CUDA_TRY(c, c->d_ntasks.ensure(16));
+    CUDA_TRY(c, c->d_qstart.ensure(4098 * 4));
+    BuildCtx b;
+    memset(&b, 0, sizeof b);
+    b.pairs = (DevPair *)c->d_pairs.p; b.codes = (const uint8_t *)c->d_codes.p;
+    b.band_lo = (const int *)c->d_band_lo.p; b.band_hi = (const int *)c->d_band_hi.p; b.cell_rev = (const int *)c->d_cell_rev.p;
+    b.arc_left = (const int *)c->d_arc_left.p; b.arc_right = (const int *)c->d_arc_right.p; b.arc_weight = (const int *)c->d_arc_weight.p;
+    b.lptr = (const int *)c->d_lptr.p; b.lcount = (const int *)c->d_lcount.p; b.am_seq = (const int *)c->d_am_seq.p;
+    memcpy(b.sigma8, c->tables.dev.sigma8, sizeof b.sigma8);
+    b.tau = c->params.tau; b.use_ribosum = c->params.use_ribosum; b.no_lonely_pairs = c->params.no_lonely_pairs;
+    b.max_diff_am = c->params.max_diff_am; b.max_diff_at_am = c->params.max_diff_at_am;
+    b.cell_start = (int *)c->d_cell_start.p; b.sptr = (int *)c->d_sptr.p; b.stats = (DevPairStats *)c->d_stats.p;
+    b.n_tasks = (unsigned *)c->d_ntasks.p; b.qstart = (int *)c->d_qstart.p;
+    size_t tmp_need = 0;
+    CUDA_TRY(c, builder_count(b, P, total_cells, nullptr, 0, &tmp_need, st));
+    CUDA_TRY(c, c->d_tmp.ensure(tmp_need));
+    CUDA_TRY(c, builder_count(b, P, total_cells, c->d_tmp.p, c->d_tmp.cap, &tmp_need, st));
+    int total_am_i = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&total_am_i, (int *)c->d_cell_start.p + total_cells, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    const size_t total_am = (size_t)total_am_i;
+    const size_t task_cap = std::min<size_t>(total_am, (size_t)total_cells) + 1;
+    CUDA_TRY(c, c->d_am.ensure(std::max<size_t>(total_am, 1) * sizeof(DevArcMatch)));
+    CUDA_TRY(c, c->d_ent.ensure(std::max<size_t>(total_am, 1) * sizeof(DevEntry)));
+    CUDA_TRY(c, c->d_dval.ensure(std::max<size_t>(total_am, 1) * 4));
+    CUDA_TRY(c, c->d_skeys.ensure(std::max<size_t>(total_am, 1) * 8));
+    CUDA_TRY(c, c->d_skeys2.ensure(std::max<size_t>(total_am, 1) * 8));
+    CUDA_TRY(c, c->d_svals.ensure(std::max<size_t>(total_am, 1) * 4));
+    CUDA_TRY(c, c->d_svals2.ensure(std::max<size_t>(total_am, 1) * 4));
+    CUDA_TRY(c, c->d_tasks_unsorted.ensure(task_cap * sizeof(DevTask)));
+    CUDA_TRY(c, c->d_tasks.ensure(task_cap * sizeof(DevTask)));
+    CUDA_TRY(c, c->d_tkeys.ensure(task_cap * 4));
+    CUDA_TRY(c, c->d_tkeys2.ensure(task_cap * 4));
+    CUDA_TRY(c, c->d_tvals.ensure(task_cap * 4));
+    CUDA_TRY(c, c->d_tvals2.ensure(task_cap * 4));
+    CUDA_TRY(c, c->d_tmp.ensure(builder_sort_tmp_bytes((long long)std::max<size_t>(total_am, 1), P)));
+    b.am = (DevArcMatch *)c->d_am.p; b.ent = (DevEntry *)c->d_ent.p;
+    b.skeys = (unsigned long long *)c->d_skeys.p; b.skeys_sorted = (unsigned long long *)c->d_skeys2.p;
+    b.svals = (unsigned *)c->d_svals.p; b.svals_sorted = (unsigned *)c->d_svals2.p;
+    b.tasks_unsorted = (DevTask *)c->d_tasks_unsorted.p; b.tasks = (DevTask *)c->d_tasks.p;
+    b.tkeys = (unsigned *)c->d_tkeys.p; b.tkeys_sorted = (unsigned *)c->d_tkeys2.p;
+    b.tvals = (unsigned *)c->d_tvals.p; b.tvals_sorted = (unsigned *)c->d_tvals2.p;
+    CUDA_TRY(c, builder_fill(b, P, (long long)total_am, sptr_total, c->d_tmp.p, c->d_tmp.cap, st));
+    unsigned n_tasks = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&n_tasks, c->d_ntasks.p, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    CUDA_TRY(c, builder_sort_tasks(b, n_tasks, c->d_tmp.p, c->d_tmp.cap, st));
+    std::vector<DevPairStats> h_stats(P);
+    CUDA_TRY(c, cudaMemcpyAsync(h_stats.data(), c->d_stats.p, (size_t)P * sizeof(DevPairStats), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaMemcpyAsync(h_pairs.data(), c->d_pairs.p, (size_t)P * sizeof(DevPair), cudaMemcpyDeviceToHost, st));
+
     CUDA_TRY(c, c->d_top.ensure((size_t)P * sizeof(DevTopResult)));
     CUDA_TRY(c, c->d_scratch.ensure((size_t)grid_cap * dc.scratch_words * 4 + 16));
-    CUDA_TRY(c, c->d_cursor.ensure((size_t)(n_groups + 2) * 4));
+    CUDA_TRY(c, c->d_cursor.ensure(4100 * 4));
     CUDA_TRY(c, c->d_flag.ensure(16));
     dc.pairs = (const DevPair *)c->d_pairs.p; dc.codes = (const uint8_t *)c->d_codes.p;
     dc.band_lo = (const int *)c->d_band_lo.p; dc.band_hi = (const int *)c->d_band_hi.p; dc.sptr = (const int *)c->d_sptr.p;
     dc.ent = (const DevEntry *)c->d_ent.p; dc.dval = (int *)c->d_dval.p; dc.am = (const DevArcMatch *)c->d_am.p;
     dc.tasks = (const DevTask *)c->d_tasks.p; dc.top = (DevTopResult *)c->d_top.p; dc.scratch = (int *)c->d_scratch.p;
+    dc.qstart = (const int *)c->d_qstart.p; dc.cursor = (int *)c->d_cursor.p;
     dc.error_flag = (int *)c->d_flag.p;
-    CUDA_TRY(c, cudaStreamSynchronize(st));  // the host staging vectors go out of scope
-    c->last_h2d_bytes = (int64_t)(h_pairs.size() * sizeof(DevPair) + h_codes.size() + (h_lo.size() + h_hi.size() + h_sptr.size()) * 4 +
-                                  h_ent.size() * sizeof(DevEntry) + h_am.size() * sizeof(DevArcMatch) + h_tasks.size() * sizeof(DevTask));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    for (int k = 0; k < P; k++) {
+        PairRec &r = c->pairs[k];
+        r.am_base = h_pairs[k].am_base; r.K = h_pairs[k].K; r.stats = h_stats[k];
+    }
+    c->last_h2d_bytes += (int64_t)(h_pairs.size() * sizeof(DevPair) + (h_lo.size() + h_hi.size() + h_rev.size()) * 4);
     lb200_ctx::Resident &R = c->res;
-    R.dc = dc; R.nc_inst = nc_inst; R.smem_bytes = smem_bytes; R.grid_cap = grid_cap; R.n_groups = n_groups;
-    R.group_start = group_start; R.total_am = total_am;
-    R.am_base.resize(P); R.K.resize(P);
-    for (int k = 0; k < P; k++) { R.am_base[k] = h_pairs[k].am_base; R.K[k] = h_pairs[k].K; }
+    R.dc = dc; R.nc_inst = nc_inst; R.smem_bytes = smem_bytes; R.grid_cap = grid_cap; R.total_am = total_am;
+    R.q_lo = 4095 - ((max_rows + max_cols) >> 1); R.q_hi = 4095;
+    if (R.q_lo < 0) R.q_lo = 0;
     R.valid = true;
     return LB200_OK;
 }
@@ -404,25 +491,20 @@ int lb200_run(lb200_ctx *c, int flags) {
     if (!c->res.valid) { const int rc = lb200_upload(c); if (rc != LB200_OK) return rc; } else c->last_h2d_bytes = 0;
     const lb200_ctx::Resident &R = c->res;
     const DevCtx &dc = R.dc;
-    const int nc_inst = R.nc_inst, smem_bytes = R.smem_bytes, grid_cap = R.grid_cap, n_groups = R.n_groups;
-    const std::vector<int> &group_start = R.group_start;
-    const size_t total_am = R.total_am;
     cudaStream_t st = c->stream;
 
     // ---- run: D entries start as -inf (aligner.cc:122-123)
     CUDA_TRY(c, cudaEventRecord(c->ev0, st));
-    CUDA_TRY(c, cudaMemsetAsync(c->d_cursor.p, 0, (size_t)(n_groups + 2) * 4, st));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_cursor.p, 0, 4100 * 4, st));
     CUDA_TRY(c, cudaMemsetAsync(c->d_flag.p, 0, 16, st));
-    CUDA_TRY(c, lb200_fill_i32((int *)c->d_dval.p, total_am, LB_NEG, st));
+    CUDA_TRY(c, lb200_fill_i32((int *)c->d_dval.p, R.total_am, LB_NEG, st));
     int64_t launches = 1;
-    for (int g = 0; g < n_groups; g++) {
-        const int b = group_start[g], e = group_start[g + 1];
-        const int grid = std::min(grid_cap, e - b);
-        launch_dfill(dc, nc_inst, c->params.indel_opening > 0, grid, smem_bytes, b, e, (int *)c->d_cursor.p + g, st);
+    for (int q = R.q_lo; q <= R.q_hi; q++) {
+        launch_dfill(dc, R.nc_inst, c->params.indel_opening > 0, R.grid_cap, R.smem_bytes, q, st);
         launches++;
     }
     CUDA_TRY(c, cudaEventRecord(c->ev_mid, st));
-    launch_toplevel(dc, nc_inst, std::min(grid_cap, P), smem_bytes, 0, P, (int *)c->d_cursor.p + n_groups, st);
+    launch_toplevel(dc, R.nc_inst, std::min(R.grid_cap, P), R.smem_bytes, 0, P, (int *)c->d_cursor.p + 4098, st);
     launches++;
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaEventRecord(c->ev1, st));
@@ -432,26 +514,20 @@ int lb200_run(lb200_ctx *c, int flags) {
     int h_flag[4] = {0, 0, 0, 0};
     CUDA_TRY(c, cudaMemcpyAsync(h_top.data(), c->d_top.p, (size_t)P * sizeof(DevTopResult), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(c, cudaMemcpyAsync(h_flag, c->d_flag.p, 16, cudaMemcpyDeviceToHost, st));
-    std::vector<int> h_dval;
-    if (flags & LB200_RUN_KEEP_D) {
-        h_dval.resize(total_am);
-        if (total_am) CUDA_TRY(c, cudaMemcpyAsync(h_dval.data(), c->d_dval.p, total_am * 4, cudaMemcpyDeviceToHost, st));
-    }
     CUDA_TRY(c, cudaStreamSynchronize(st));
-    float ms = 0;
+    float ms = 0, ms_dfill = 0;
     CUDA_TRY(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    float ms_dfill = 0;
     CUDA_TRY(c, cudaEventElapsedTime(&ms_dfill, c->ev0, c->ev_mid));
-    c->last_kernel_ms = ms; c->last_launches = launches; c->last_dfill_ms = ms_dfill; c->last_dfill_launches = n_groups;
-    c->last_d2h_bytes = (int64_t)((size_t)P * sizeof(DevTopResult) + 16 + h_dval.size() * 4);
+    c->last_kernel_ms = ms; c->last_launches = launches; c->last_dfill_ms = ms_dfill; c->last_dfill_launches = R.q_hi - R.q_lo + 1;
+    c->last_d2h_bytes = (int64_t)((size_t)P * sizeof(DevTopResult) + 16);
     if (h_flag[0] != 0) return fail(c, LB200_ERR_UNSUPPORTED, "kernel reported error %d (1: band too wide, 2: box exceeds scratch)", h_flag[0]);
     for (int k = 0; k < P; k++) {
         PairRec &r = c->pairs[k];
         r.neg_inf = h_top[k].score < LB_NEG_LIMIT;
         r.score = r.neg_inf ? 0 : h_top[k].score;
         r.max_i = h_top[k].max_i; r.max_j = h_top[k].max_j;
-        if (flags & LB200_RUN_KEEP_D) r.dvals.assign(h_dval.begin() + R.am_base[k], h_dval.begin() + R.am_base[k] + R.K[k]);
     }
+    (void)flags;
     return LB200_OK;
 }
 
@@ -481,7 +557,7 @@ int lb200_pair_get_info(const lb200_ctx *c, int pair, lb200_pair_info *info) {
     memset(info, 0, sizeof *info);
     info->lenA = c->seqs[r.seqA].len; info->lenB = c->seqs[r.seqB].len;
     info->n_arcsA = (int)c->seqs[r.seqA].arcs.size(); info->n_arcsB = (int)c->seqs[r.seqB].arcs.size();
-    info->n_arcmatches = (int64_t)r.prob.am.size(); info->n_tasks = (int64_t)r.prob.tasks.size(); info->cells = (int64_t)r.prob.cells; info->terms = (int64_t)r.prob.terms;
+    info->n_arcmatches = r.K; info->n_tasks = r.stats.n_tasks; info->cells = r.stats.cells; info->terms = r.stats.terms;
     info->n_edges = (int64_t)r.edges_a.size();
     return LB200_OK;
 }
@@ -495,27 +571,45 @@ int lb200_pair_band(const lb200_ctx *c, int pair, int *min_col, int *max_col) {
     return LB200_OK;
 }
 
-int lb200_pair_arcmatches(const lb200_ctx *c, int pair, int *al, int *ar, int *bl, int *br, int *score, int64_t *D) {
+int lb200_pair_arcmatches(const lb200_ctx *cc, int pair, int *al, int *ar, int *bl, int *br, int *score, int64_t *D) {
+    lb200_ctx *c = const_cast<lb200_ctx *>(cc);
     if (!c || pair < 0 || pair >= (int)c->pairs.size()) return LB200_ERR_ARG;
     const PairRec &r = c->pairs[pair];
-    if (!r.built) return LB200_ERR_STATE;
-    const size_t K = r.prob.am.size();
-    if (D && r.dvals.size() != K) return LB200_ERR_STATE;
-    // reference index order = (arc A index, arc B index) ascending (arc_matches.cc:161-183)
+    std::vector<DevArcMatch> am;
+    std::vector<int> dvals;
+    if (c->device == LB200_DEVICE_NONE) {
+        if (!r.built) return LB200_ERR_STATE;
+        if (D) return fail(c, LB200_ERR_STATE, "no D table on a host-only context");
+        am = r.prob.am;
+    } else {
+        if (!c->res.valid) return fail(c, LB200_ERR_STATE, "no resident batch: call lb200_upload / lb200_run first");
+        am.resize(r.K); dvals.resize(r.K);
+        if (r.K) {
+            CUDA_TRY(c, cudaMemcpy(am.data(), (const DevArcMatch *)c->d_am.p + r.am_base, (size_t)r.K * sizeof(DevArcMatch), cudaMemcpyDeviceToHost));
+            CUDA_TRY(c, cudaMemcpy(dvals.data(), (const int *)c->d_dval.p + r.am_base, (size_t)r.K * 4, cudaMemcpyDeviceToHost));
+        }
+    }
+    const size_t K = am.size();
+    // reference index order = (arc A index, arc B index) ascending (arc_matches.cc:161-183); arcs are indexed by
+    // left end descending, right end ascending (basepairs.cc:162-163)
     std::vector<int> order(K);
     for (size_t k = 0; k < K; k++) order[k] = (int)k;
     std::sort(order.begin(), order.end(), [&](int x, int y) {
-        if (r.prob.am_a[x] != r.prob.am_a[y]) return r.prob.am_a[x] < r.prob.am_a[y];
-        return r.prob.am_b[x] < r.prob.am_b[y];
+        const int xal = am[x].ends_a & 0xfff, yal = am[y].ends_a & 0xfff, xar = am[x].ends_a >> 12, yar = am[y].ends_a >> 12;
+        if (xal != yal) return xal > yal;
+        if (xar != yar) return xar < yar;
+        const int xbl = am[x].ends_b & 0xfff, ybl = am[y].ends_b & 0xfff, xbr = am[x].ends_b >> 12, ybr = am[y].ends_b >> 12;
+        if (xbl != ybl) return xbl > ybl;
+        return xbr < ybr;
     });
     for (size_t k = 0; k < K; k++) {
-        const DevArcMatch &x = r.prob.am[order[k]];
+        const DevArcMatch &x = am[order[k]];
         if (al) al[k] = x.ends_a & 0xfff;
         if (ar) ar[k] = x.ends_a >> 12;
         if (bl) bl[k] = x.ends_b & 0xfff;
         if (br) br[k] = x.ends_b >> 12;
         if (score) score[k] = x.score;
-        if (D) { const int d = r.dvals[x.spos]; D[k] = d < LB_NEG_LIMIT ? LB200_SCORE_NEG_INF : d; }
+        if (D) { const int d = dvals[x.spos]; D[k] = d < LB_NEG_LIMIT ? LB200_SCORE_NEG_INF : d; }
     }
     return LB200_OK;
 }
