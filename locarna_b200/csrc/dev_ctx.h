@@ -24,6 +24,12 @@ struct DevCtx {
     int rowcode_bytes;       // >= max_rows + 2, multiple of 4
     int colcode_bytes;       // >= largest lenB + 2, multiple of 4
     int arcbuf_words;        // RING * 32 * NCmax
+    // traceback
+    const unsigned *lpos;    // S-order position -> L-order index (relative to the pair)
+    int *trace_edges;        // per pair n+m+3 slots (same offsets as sptr): edge at slot i+j = i << 2 | kind
+    char *trace_str;         // per pair: structure string of A (n+1 bytes) then of B (m+1 bytes), at the sptr offset
+    TraceJob *trace_stack;   // per pair trace_stack_cap pending boxes
+    int trace_stack_cap;
     int *error_flag;
 };
 

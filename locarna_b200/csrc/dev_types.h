@@ -71,6 +71,9 @@ struct DevTask {
     int run_count;
 };
 
+// a box whose optimal path still has to be traced (traceback kernel)
+struct TraceJob { short al, bl, R, C; };
+
 struct DevTopResult {
     int score;         // LB_NEG.. if -inf
     int max_i, max_j;

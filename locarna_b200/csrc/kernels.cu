@@ -438,6 +438,167 @@ __global__ void __launch_bounds__(32) toplevel_kernel(DevCtx c, int pair_begin, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Traceback (aligner.cc:967-1358). One warp per pair works off a stack of boxes: the top level box first, then the
+// box of every arc match found on the optimal path (the reference re-runs align_in_arcmatch for each of them,
+// aligner.cc:1012/:1056). Inside a box the warp walks back from the last cell following trace_noex's case order
+// (base match, deletion run, insertion run, arc matches in common_right_end_list order; first equality wins).
+// Every alignment edge is written to slot i+j of the pair's edge array - i+j strictly increases along an alignment,
+// so the order in which boxes are processed does not matter and the host only compacts the array.
+#define LB_EDGE_MATCH 1
+#define LB_EDGE_DEL 2   // (i, gap)
+#define LB_EDGE_INS 3   // (gap, j)
+
+template <int NCMAX, bool GBD, bool CLAMP>
+__global__ void __launch_bounds__(32) trace_kernel(DevCtx c, int pair_begin, int pair_end, int *cursor) {
+    extern __shared__ int smem[];
+    const int lane = threadIdx.x;
+    WarpSmem ws;
+    carve(c, smem, ws);
+    int *box = c.scratch + (size_t)blockIdx.x * c.scratch_words;
+    const DevParams &P = c.params;
+    const bool nolp = P.no_lonely_pairs != 0;
+    BoxInit top_init, in_init;
+    const bool globalA = !(P.sequ_local || P.fe_left2), globalB = !(P.sequ_local || P.fe_left1);
+    top_init.col_base = globalA ? P.open : 0; top_init.col_step = globalA ? P.gap : 0;
+    top_init.row_base = globalB ? P.open : 0; top_init.row_step = globalB ? P.gap : 0;
+    in_init.col_base = P.open; in_init.col_step = P.gap; in_init.row_base = P.open; in_init.row_step = P.gap;
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = pair_begin + atomicAdd(cursor, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= pair_end) break;
+        const DevPair pr = c.pairs[t];
+        const int n = pr.lenA, m = pr.lenB;
+        const int *lo = c.band_lo + pr.band, *hi = c.band_hi + pr.band;
+        const uint8_t *ca = c.codes + pr.codesA, *cb = c.codes + pr.codesB;
+        const DevEntry *ent = c.ent + pr.am_base;
+        const int *dval = c.dval + pr.am_base;
+        const DevArcMatch *am = c.am + pr.am_base;
+        const unsigned *lpos = c.lpos + pr.am_base;
+        const int *sptr = c.sptr + pr.sptr;
+        int *edges = c.trace_edges + pr.sptr;                // n + m + 3 slots
+        char *strA = c.trace_str + pr.sptr, *strB = strA + n + 1;  // n + 1 and m + 1 bytes (sptr offsets are a superset)
+        TraceJob *stack = c.trace_stack + (size_t)t * c.trace_stack_cap;
+        for (int k = lane; k < n + m + 3; k += 32) edges[k] = 0;
+        for (int k = lane; k <= n; k += 32) strA[k] = '.';
+        for (int k = lane; k <= m; k += 32) strB[k] = '.';
+        __syncwarp();
+        auto valid = [&](int i, int j) { return i >= 0 && j >= 0 && lo[i] <= j && j <= hi[i]; };
+        auto emit = [&](int i, int j, int kind) { if (lane == 0) edges[i + j] = (i << 2) | kind; };
+        int sp = 0;
+        const DevTopResult top = c.top[t];
+        bool tl = true;
+        TraceJob job;
+        job.al = 0; job.bl = 0; job.R = (short)n; job.C = (short)m;
+        bool have = true;
+        while (have) {
+            BoxGeom g;
+            setup_box(c, pr, job.al, job.bl, job.R, job.C, g, ws);
+            bool ok;
+            if ((g.umax + 1) * g.nslots > c.scratch_words) ok = false;
+            else if (tl) ok = run_box<NCMAX, true, CLAMP>(c, pr, g, top_init, ws, box);
+            else ok = run_box<NCMAX, GBD, false>(c, pr, g, in_init, ws, box);
+            if (!ok) { if (lane == 0) atomicExch(c.error_flag, 3); break; }
+            const int al = job.al, bl = job.bl;
+            int i = tl ? top.max_i : job.R, j = tl ? top.max_j : job.C;
+            // ---- walk (trace_in_arcmatch / trace_noex, state E_NO_NO)
+            for (;;) {
+                const int mij = box_get(box, g, i - al, j - bl);
+                if (tl && P.sequ_local && mij == 0) break;                                   // aligner.cc:1251-1255
+                if (i <= al) {                                                               // :1257-1271
+                    if (!(tl && (P.sequ_local || P.fe_left1))) for (int k = bl + 1 + lane; k <= j; k += 32) edges[al + k] = (al << 2) | LB_EDGE_INS;
+                    break;
+                }
+                if (j <= bl) {                                                               // :1273-1287
+                    if (!(tl && (P.sequ_local || P.fe_left2))) for (int k = al + 1 + lane; k <= i; k += 32) edges[k + bl] = (k << 2) | LB_EDGE_DEL;
+                    break;
+                }
+                const bool vdiag = valid(i - 1, j - 1);
+                if (vdiag && mij == box_get(box, g, i - 1 - al, j - 1 - bl) + P.sigma8[ca[i] * LB_NCODES + cb[j]]) {   // :1099-1105
+                    emit(i, j, LB_EDGE_MATCH);
+                    i--; j--;
+                    continue;
+                }
+                bool moved = false;
+                if (P.open == 0) {                                                           // :1107-1124 linear gap cost
+                    if (valid(i - 1, j) && mij == box_get(box, g, i - 1 - al, j - bl) + P.gap) { emit(i, j, LB_EDGE_DEL); i--; moved = true; }
+                    else if (valid(i, j - 1) && mij == box_get(box, g, i - al, j - 1 - bl) + P.gap) { emit(i, j, LB_EDGE_INS); j--; moved = true; }
+                } else {                                                                     // :1125-1172 affine: gap runs
+                    int cost = P.open;
+                    for (int k = 1; i >= al + k; k++) {
+                        if (!valid(i - k, j)) break;
+                        cost += P.gap;
+                        if (mij == box_get(box, g, i - k - al, j - bl) + cost) {
+                            for (int l = lane; l < k; l += 32) edges[(i - l) + j] = ((i - l) << 2) | LB_EDGE_DEL;
+                            i -= k; moved = true;
+                            break;
+                        }
+                    }
+                    if (!moved) {
+                        cost = P.open;
+                        for (int k = 1; j >= bl + k; k++) {
+                            if (!valid(i, j - k)) break;
+                            cost += P.gap;
+                            if (mij == box_get(box, g, i - al, j - k - bl) + cost) {
+                                for (int l = lane; l < k; l += 32) edges[i + (j - l)] = (i << 2) | LB_EDGE_INS;
+                                j -= k; moved = true;
+                                break;
+                            }
+                        }
+                    }
+                }
+                if (moved) continue;
+                if (!vdiag) break;                                                           // :1176-1178
+                // arc matches with right ends (i, j), in common_right_end_list order (:1186-1228)
+                const int e0 = sptr[i + j], e1 = sptr[i + j + 1];
+                int found = -1;
+                for (int base = e0; base < e1 && found < 0; base += 32) {
+                    const int e = base + lane;
+                    bool hit = false;
+                    if (e < e1) {
+                        const DevEntry en = ent[e];
+                        const int p = (int)(en.x & 0xfff), q = (int)(en.x >> 12);
+                        if ((int)(en.y & 0xfff) == i && p >= al && q >= bl) hit = (mij == box_get(box, g, p - al, q - bl) + dval[e]);
+                    }
+                    const unsigned b = __ballot_sync(0xffffffffu, hit);
+                    if (b) found = base + __ffs(b) - 1;
+                }
+                if (found < 0) { if (lane == 0) atomicExch(c.error_flag, 4); break; }
+                const DevEntry en = ent[found];
+                const int xl = (int)(en.x & 0xfff) + 1, yl = (int)(en.x >> 12) + 1;  // left ends of the arc match
+                if (lane == 0) { strA[xl] = '('; strA[i] = ')'; strB[yl] = '('; strB[j] = ')'; }
+                emit(xl, yl, LB_EDGE_MATCH);
+                emit(i, j, LB_EDGE_MATCH);
+                if (!nolp) {                                                                 // trace_arcmatch :967-1028
+                    if (lane == 0) { TraceJob nj; nj.al = (short)xl; nj.bl = (short)yl; nj.R = (short)(i - 1); nj.C = (short)(j - 1); stack[sp] = nj; }
+                    sp++;
+                } else {                                                                     // trace_arcmatch_noLP :1030-1079
+                    int cur = (int)lpos[found];
+                    for (;;) {
+                        const DevArcMatch x = am[cur];
+                        const DevArcMatch in = am[x.inner];
+                        const int ial = in.ends_a & 0xfff, iar = in.ends_a >> 12, ibl = in.ends_b & 0xfff, ibr = in.ends_b >> 12;
+                        if (lane == 0) { strA[ial] = '('; strA[iar] = ')'; strB[ibl] = '('; strB[ibr] = ')'; }
+                        emit(ial, ibl, LB_EDGE_MATCH);
+                        emit(iar, ibr, LB_EDGE_MATCH);
+                        if (dval[x.spos] == dval[in.spos] + x.score) { cur = x.inner; continue; }
+                        if (lane == 0) { TraceJob nj; nj.al = (short)ial; nj.bl = (short)ibl; nj.R = (short)(iar - 1); nj.C = (short)(ibr - 1); stack[sp] = nj; }
+                        sp++;
+                        break;
+                    }
+                }
+                i = xl - 1; j = yl - 1;
+            }
+            __syncwarp();
+            tl = false;
+            have = sp > 0;
+            if (have) { sp--; job = stack[sp]; }
+        }
+        __syncwarp();
+    }
+}
+
 // host-side launchers; ncmax selects the instantiation (1, 2, 4, 8 or 16 diagonal pairs per lane)
 #define LB_DISPATCH(ncmax, CALL)                                  \
     do {                                                          \
@@ -463,11 +624,22 @@ void launch_toplevel(const DevCtx &c, int ncmax, int grid, int smem_bytes, int p
     LB_DISPATCH(ncmax, CALL);
 #undef CALL
 }
+void launch_trace(const DevCtx &c, int ncmax, bool generic_borders, int grid, int smem_bytes, int pair_begin, int pair_end, int *cursor, cudaStream_t st) {
+    const bool clamp = c.params.sequ_local != 0;
+#define CALL(N)                                                                                                  \
+    if (clamp) { if (generic_borders) trace_kernel<N, true, true><<<grid, 32, smem_bytes, st>>>(c, pair_begin, pair_end, cursor); \
+                 else trace_kernel<N, false, true><<<grid, 32, smem_bytes, st>>>(c, pair_begin, pair_end, cursor); }              \
+    else { if (generic_borders) trace_kernel<N, true, false><<<grid, 32, smem_bytes, st>>>(c, pair_begin, pair_end, cursor);      \
+           else trace_kernel<N, false, false><<<grid, 32, smem_bytes, st>>>(c, pair_begin, pair_end, cursor); }
+    LB_DISPATCH(ncmax, CALL);
+#undef CALL
+}
 cudaError_t configure_kernels(int ncmax, int smem_bytes, int *dfill_ctas_per_sm) {
     cudaError_t e = cudaSuccess;
 #define SET(K) if (e == cudaSuccess) e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)
 #define CALL(N)                                                                                                         \
     SET((dfill_kernel<N, true>)); SET((dfill_kernel<N, false>)); SET((toplevel_kernel<N, true>)); SET((toplevel_kernel<N, false>)); \
+    SET((trace_kernel<N, true, true>)); SET((trace_kernel<N, false, true>)); SET((trace_kernel<N, true, false>)); SET((trace_kernel<N, false, false>)); \
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(dfill_ctas_per_sm, dfill_kernel<N, false>, 32, smem_bytes)
     LB_DISPATCH(ncmax, CALL);
 #undef CALL

@@ -20,6 +20,7 @@
 namespace lb200 {
 void launch_dfill(const DevCtx &c, int ncmax, bool generic_borders, int grid, int smem_bytes, int q, cudaStream_t st);
 void launch_toplevel(const DevCtx &c, int ncmax, int grid, int smem_bytes, int pair_begin, int pair_end, int *cursor, cudaStream_t st);
+void launch_trace(const DevCtx &c, int ncmax, bool generic_borders, int grid, int smem_bytes, int pair_begin, int pair_end, int *cursor, cudaStream_t st);
 cudaError_t configure_kernels(int ncmax, int smem_bytes, int *dfill_ctas_per_sm);
 }  // namespace lb200
 
@@ -55,7 +56,7 @@ struct PairRec {
     DevPairStats stats = {0, 0, 0, 0};
     // results
     int64_t score = 0; bool neg_inf = true; int max_i = 0, max_j = 0;
-    std::vector<int> edges_a, edges_b; std::string str_a, str_b;
+    std::vector<int> edges_a, edges_b; std::string str_a, str_b; bool traced = false;
 };
 
 }  // namespace
@@ -82,17 +83,20 @@ struct lb200_ctx {
         DevCtx dc;
         int nc_inst = 1, smem_bytes = 0, grid_cap = 1, q_lo = 0, q_hi = 0;
         size_t total_am = 0;
+        long long sptr_total = 0;
+        int stack_cap = 0;
+        std::vector<int> sptr_off;
     } res;
     int host_threads = 0;
     size_t seqs_uploaded = 0;  // sequences whose arrays are on the device
     std::vector<int> seq_codes_off, seq_arcs_off, seq_lptr_off;
     DevBuf d_arc_left, d_arc_right, d_arc_weight, d_lptr, d_lcount, d_am_seq, d_cell_rev, d_cell_start, d_skeys, d_skeys2, d_svals, d_svals2,
-        d_tasks_unsorted, d_tkeys, d_tkeys2, d_tvals, d_tvals2, d_ntasks, d_qstart, d_stats, d_tmp;
+        d_tasks_unsorted, d_tkeys, d_tkeys2, d_tvals, d_tvals2, d_ntasks, d_qstart, d_stats, d_tmp, d_tr_edges, d_tr_str, d_tr_stack;
     DevBuf d_pairs, d_codes, d_band_lo, d_band_hi, d_sptr, d_ent, d_dval, d_am, d_tasks, d_top, d_scratch, d_cursor, d_flag;
     ~lb200_ctx() {
         DevBuf *all[] = {&d_pairs, &d_codes, &d_band_lo, &d_band_hi, &d_sptr, &d_ent, &d_dval, &d_am, &d_tasks, &d_top, &d_scratch, &d_cursor, &d_flag,
                          &d_arc_left, &d_arc_right, &d_arc_weight, &d_lptr, &d_lcount, &d_am_seq, &d_cell_rev, &d_cell_start, &d_skeys, &d_skeys2,
-                         &d_svals, &d_svals2, &d_tasks_unsorted, &d_tkeys, &d_tkeys2, &d_tvals, &d_tvals2, &d_ntasks, &d_qstart, &d_stats, &d_tmp};
+                         &d_svals, &d_svals2, &d_tasks_unsorted, &d_tkeys, &d_tkeys2, &d_tvals, &d_tvals2, &d_ntasks, &d_qstart, &d_stats, &d_tmp, &d_tr_edges, &d_tr_str, &d_tr_stack};
         for (auto *b : all) b->release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -474,6 +478,10 @@ int lb200_upload(lb200_ctx *c) {
     c->last_h2d_bytes += (int64_t)(h_pairs.size() * sizeof(DevPair) + (h_lo.size() + h_hi.size() + h_rev.size()) * 4);
     lb200_ctx::Resident &R = c->res;
     R.dc = dc; R.nc_inst = nc_inst; R.smem_bytes = smem_bytes; R.grid_cap = grid_cap; R.total_am = total_am;
+    R.sptr_total = sptr_total; R.stack_cap = std::min(max_rows, max_cols) / 2 + 8;
+    R.sptr_off.resize(P);
+    for (int k = 0; k < P; k++) R.sptr_off[k] = h_pairs[k].sptr;
+    R.dc.lpos = (const unsigned *)c->d_svals2.p;
     R.q_lo = 4095 - ((max_rows + max_cols) >> 1); R.q_hi = 4095;
     if (R.q_lo < 0) R.q_lo = 0;
     R.valid = true;
@@ -483,15 +491,22 @@ int lb200_upload(lb200_ctx *c) {
 int lb200_run(lb200_ctx *c, int flags) {
     if (!c) return LB200_ERR_ARG;
     if (c->device == LB200_DEVICE_NONE) return fail(c, LB200_ERR_CUDA, "host-only context: lb200_run needs a CUDA device (no CPU fallback)");
-    if (flags & LB200_RUN_TRACE) return fail(c, LB200_ERR_UNSUPPORTED, "device traceback is not implemented yet");
     CUDA_TRY(c, cudaSetDevice(c->device));
     const int P = (int)c->pairs.size();
     c->last_kernel_ms = 0; c->last_launches = 0; c->last_d2h_bytes = 0;
     if (P == 0) return LB200_OK;
     if (!c->res.valid) { const int rc = lb200_upload(c); if (rc != LB200_OK) return rc; } else c->last_h2d_bytes = 0;
-    const lb200_ctx::Resident &R = c->res;
-    const DevCtx &dc = R.dc;
+    lb200_ctx::Resident &R = c->res;
     cudaStream_t st = c->stream;
+    const bool do_trace = (flags & LB200_RUN_TRACE) != 0;
+    if (do_trace) {
+        CUDA_TRY(c, c->d_tr_edges.ensure((size_t)R.sptr_total * 4));
+        CUDA_TRY(c, c->d_tr_str.ensure((size_t)R.sptr_total));
+        CUDA_TRY(c, c->d_tr_stack.ensure((size_t)P * R.stack_cap * sizeof(TraceJob)));
+        R.dc.trace_edges = (int *)c->d_tr_edges.p; R.dc.trace_str = (char *)c->d_tr_str.p;
+        R.dc.trace_stack = (TraceJob *)c->d_tr_stack.p; R.dc.trace_stack_cap = R.stack_cap;
+    }
+    const DevCtx &dc = R.dc;
 
     // ---- run: D entries start as -inf (aligner.cc:122-123)
     CUDA_TRY(c, cudaEventRecord(c->ev0, st));
@@ -506,6 +521,10 @@ int lb200_run(lb200_ctx *c, int flags) {
     CUDA_TRY(c, cudaEventRecord(c->ev_mid, st));
     launch_toplevel(dc, R.nc_inst, std::min(R.grid_cap, P), R.smem_bytes, 0, P, (int *)c->d_cursor.p + 4098, st);
     launches++;
+    if (do_trace) {
+        launch_trace(dc, R.nc_inst, c->params.indel_opening > 0, std::min(R.grid_cap, P), R.smem_bytes, 0, P, (int *)c->d_cursor.p + 4099, st);
+        launches++;
+    }
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaEventRecord(c->ev1, st));
 
@@ -514,20 +533,42 @@ int lb200_run(lb200_ctx *c, int flags) {
     int h_flag[4] = {0, 0, 0, 0};
     CUDA_TRY(c, cudaMemcpyAsync(h_top.data(), c->d_top.p, (size_t)P * sizeof(DevTopResult), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(c, cudaMemcpyAsync(h_flag, c->d_flag.p, 16, cudaMemcpyDeviceToHost, st));
+    std::vector<int> h_edges;
+    std::vector<char> h_str;
+    if (do_trace) {
+        h_edges.resize(R.sptr_total); h_str.resize(R.sptr_total);
+        CUDA_TRY(c, cudaMemcpyAsync(h_edges.data(), c->d_tr_edges.p, (size_t)R.sptr_total * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaMemcpyAsync(h_str.data(), c->d_tr_str.p, (size_t)R.sptr_total, cudaMemcpyDeviceToHost, st));
+    }
     CUDA_TRY(c, cudaStreamSynchronize(st));
     float ms = 0, ms_dfill = 0;
     CUDA_TRY(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     CUDA_TRY(c, cudaEventElapsedTime(&ms_dfill, c->ev0, c->ev_mid));
     c->last_kernel_ms = ms; c->last_launches = launches; c->last_dfill_ms = ms_dfill; c->last_dfill_launches = R.q_hi - R.q_lo + 1;
-    c->last_d2h_bytes = (int64_t)((size_t)P * sizeof(DevTopResult) + 16);
-    if (h_flag[0] != 0) return fail(c, LB200_ERR_UNSUPPORTED, "kernel reported error %d (1: band too wide, 2: box exceeds scratch)", h_flag[0]);
+    c->last_d2h_bytes = (int64_t)((size_t)P * sizeof(DevTopResult) + 16 + h_edges.size() * 4 + h_str.size());
+    if (h_flag[0] != 0)
+        return fail(c, LB200_ERR_UNSUPPORTED, "kernel reported error %d (1: band too wide, 2: box exceeds scratch, 3: trace box failed, 4: traceback dead end)", h_flag[0]);
     for (int k = 0; k < P; k++) {
         PairRec &r = c->pairs[k];
         r.neg_inf = h_top[k].score < LB_NEG_LIMIT;
         r.score = r.neg_inf ? 0 : h_top[k].score;
         r.max_i = h_top[k].max_i; r.max_j = h_top[k].max_j;
+        r.edges_a.clear(); r.edges_b.clear(); r.str_a.clear(); r.str_b.clear();
+        if (do_trace) {
+            // compact the edge slots (slot index = i + j increases along the alignment)
+            const int n = c->seqs[r.seqA].len, m = c->seqs[r.seqB].len, off = R.sptr_off[k];
+            for (int idx = 0; idx <= n + m; idx++) {
+                const int v = h_edges[off + idx];
+                if (v == 0) continue;
+                const int i = v >> 2, j = idx - i, kind = v & 3;
+                r.edges_a.push_back(kind == 3 ? -1 : i);
+                r.edges_b.push_back(kind == 2 ? -1 : j);
+            }
+            r.str_a.assign(h_str.begin() + off + 1, h_str.begin() + off + n + 1);
+            r.str_b.assign(h_str.begin() + off + n + 2, h_str.begin() + off + n + 2 + m);
+            r.traced = true;
+        }
     }
-    (void)flags;
     return LB200_OK;
 }
 
@@ -617,7 +658,7 @@ int lb200_pair_arcmatches(const lb200_ctx *cc, int pair, int *al, int *ar, int *
 int lb200_pair_alignment(const lb200_ctx *c, int pair, int *ea, int *eb, char *sa, char *sb) {
     if (!c || pair < 0 || pair >= (int)c->pairs.size()) return LB200_ERR_ARG;
     const PairRec &r = c->pairs[pair];
-    if (r.str_a.empty()) return LB200_ERR_STATE;
+    if (!r.traced) return LB200_ERR_STATE;
     if (ea) std::copy(r.edges_a.begin(), r.edges_a.end(), ea);
     if (eb) std::copy(r.edges_b.begin(), r.edges_b.end(), eb);
     if (sa) strcpy(sa, r.str_a.c_str());
