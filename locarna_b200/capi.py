@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblocarna_b200.so")
+LIB_PATH = os.environ.get("LB200_LIB", os.path.join(_HERE, "liblocarna_b200.so"))
 
 OK = 0
 DEVICE_NONE = -1
