@@ -8,7 +8,9 @@ LIB       := locarna_b200/liblocarna_b200.so
 
 OBJS := $(OBJ)/kernels.o $(OBJ)/builder.o $(OBJ)/runtime.o $(OBJ)/host_model.o
 
-all: $(LIB)
+CLI       := locarna_b200/bin/locarna_b200
+
+all: $(LIB) $(CLI)
 
 $(OBJ):
 	mkdir -p $(OBJ)
@@ -24,5 +26,10 @@ $(OBJ)/%.o: $(SRC)/%.cc $(wildcard $(SRC)/*.h) | $(OBJ)
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -cudart static -lpthread
 
+# `locarna`-compatible command line front end (host C++ over the C ABI)
+$(CLI): $(SRC)/cli/locarna_main.cc include/locarna_b200.hh include/locarna_b200.h $(LIB)
+	mkdir -p locarna_b200/bin
+	/usr/bin/g++ -std=c++17 -O2 -Wall -Iinclude $< -o $@ -Llocarna_b200 -llocarna_b200 -Wl,-rpath,'$$ORIGIN/..'
+
 clean:
-	rm -rf build $(LIB)
+	rm -rf build $(LIB) locarna_b200/bin

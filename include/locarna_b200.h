@@ -101,6 +101,8 @@ int lb200_seq_add_pp(lb200_ctx *ctx, const char *path);
 int lb200_seq_add(lb200_ctx *ctx, const char *name, const char *seq, const int *pair_i, const int *pair_j, const double *pair_p,
                   int n_pairs);
 int lb200_seq_length(const lb200_ctx *ctx, int seq);
+/* name (at most name_cap-1 characters) and normalised sequence (length+1 bytes incl. NUL) of a sequence; either may be NULL */
+int lb200_seq_get(const lb200_ctx *ctx, int seq, char *name, int name_cap, char *sequence);
 
 /* Add one alignment problem (A = seqA, B = seqB). min_col/max_col (lenA+1 entries each) give the band
  * [min_col(i), max_col(i)] per row; pass NULL for both to have it derived like the reference does

@@ -1,0 +1,246 @@
+// locarna_b200.hh -- C++ mirror of the reference's operator API for the pairwise alignment path, header-only over
+// the C ABI (locarna_b200.h). Same class names, method names, argument meaning and error behaviour as LocARNA 2.0.1:
+//
+//   RnaData            src/LocARNA/rna_data.hh:60           (PP 2.0 input only)
+//   ScoringParams      src/LocARNA/scoring.hh:59-166        (named arguments -> plain members with the same names)
+//   AlignerParams      src/LocARNA/aligner_params.hh:49-116 (named arguments -> chained setters with the same names)
+//   Aligner            src/LocARNA/aligner.hh:67-189        construct, align(), trace(), get_alignment() (aligner.hh:56)
+//   Alignment          src/LocARNA/alignment.hh:84-281
+//   MultipleAlignment  src/LocARNA/multiple_alignment.hh    (from an Alignment; CLUSTAL writer)
+//   infty_score_t      src/LocARNA/infty_int.hh             (finite value or -inf; prints "-inf")
+//   failure            src/LocARNA/aux.hh:160-209
+//
+// A maintainer switching a translation unit over writes `namespace LocARNA = LocARNA_B200;`.
+#ifndef LOCARNA_B200_HH
+#define LOCARNA_B200_HH
+
+#include <algorithm>
+#include <cstring>
+#include <exception>
+#include <memory>
+#include <ostream>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "locarna_b200.h"
+
+namespace LocARNA_B200 {
+
+class failure : public std::exception {
+    std::string msg_;
+public:
+    explicit failure(const std::string &msg) : msg_(msg) {}
+    const char *what() const noexcept override { return msg_.c_str(); }
+};
+
+class infty_score_t {
+    long val_ = 0;
+    bool neg_inf_ = false;
+public:
+    infty_score_t() {}
+    explicit infty_score_t(long v) : val_(v) {}
+    static infty_score_t neg_infty_value() { infty_score_t s; s.neg_inf_ = true; return s; }
+    bool is_neg_infty() const { return neg_inf_; }
+    bool is_finite() const { return !neg_inf_; }
+    long finite_value() const { return val_; }
+};
+inline std::ostream &operator<<(std::ostream &out, const infty_score_t &s) {  // infty_int.cc:33-43
+    if (s.is_neg_infty()) return out << "-inf";
+    return out << s.finite_value();
+}
+
+// one GPU context shared by the objects of a program (the reference has no such object: state lives in the classes)
+class Context {
+    lb200_ctx *ctx_ = nullptr;
+public:
+    explicit Context(int device = 0) {
+        if (lb200_ctx_create(device, &ctx_) != LB200_OK) throw failure("locarna_b200: cannot create a CUDA context (no CPU fallback)");
+    }
+    ~Context() { lb200_ctx_destroy(ctx_); }
+    Context(const Context &) = delete;
+    Context &operator=(const Context &) = delete;
+    lb200_ctx *get() const { return ctx_; }
+    void check(int rc) const { if (rc < 0) throw failure(lb200_last_error(ctx_)); }
+};
+
+struct ScoringParams {  // scoring.hh:59-166 (defaults of the locarna CLI)
+    int match = 50, mismatch = 0, indel = -150, indel_opening = -750, unpaired_penalty = 0;
+    int struct_weight = 200, tau_factor = 50, exclusion = 0, temperature_alipf = 300;
+    bool use_ribosum = true, stacking = false, new_stacking = false, mea_scoring = false;
+};
+
+class RnaData {  // PP 2.0 input (rna_data.cc:984-1103); p_bpcut as in RnaData(file, p_bpcut, ...)
+    std::string file_;
+    double p_bpcut_;
+public:
+    RnaData(const std::string &file, double p_bpcut) : file_(file), p_bpcut_(p_bpcut) {}
+    const std::string &filename() const { return file_; }
+    double arc_cutoff_prob() const { return p_bpcut_; }
+};
+
+class Alignment {  // alignment.hh:84-281
+    friend class Aligner;
+    std::string nameA_, nameB_, seqA_, seqB_;
+    std::vector<std::pair<int, int>> edges_;  // position or -1 (gap), in order
+    std::string strA_, strB_;                 // per position, '.', '(' or ')'
+public:
+    typedef std::vector<std::pair<int, int>> edges_t;
+    // alignment_edges(only_local) (alignment.cc:120-167): locality gaps are reported as -3
+    edges_t alignment_edges(bool only_local) const {
+        edges_t res;
+        int lastA = 1, lastB = 1;
+        for (const auto &e : edges_) {
+            if (e.first > 0) for (; lastA < e.first; lastA++) if (!only_local) res.emplace_back(lastA, -3);
+            if (e.second > 0) for (; lastB < e.second; lastB++) if (!only_local) res.emplace_back(-3, lastB);
+            if (e.first > 0) lastA++;
+            if (e.second > 0) lastB++;
+            res.push_back(e);
+        }
+        if (!only_local) {
+            for (; lastA <= (int)seqA_.size(); lastA++) res.emplace_back(lastA, -3);
+            for (; lastB <= (int)seqB_.size(); lastB++) res.emplace_back(-3, lastB);
+        }
+        return res;
+    }
+    std::string dot_bracket_structureA(bool only_local) const { return project(strA_, true, only_local); }
+    std::string dot_bracket_structureB(bool only_local) const { return project(strB_, false, only_local); }
+    std::string rowA(bool only_local) const { return project(seqA_, true, only_local); }
+    std::string rowB(bool only_local) const { return project(seqB_, false, only_local); }
+    const std::string &nameA() const { return nameA_; }
+    const std::string &nameB() const { return nameB_; }
+    bool empty() const { return edges_.empty(); }
+private:
+    std::string project(const std::string &s, bool first, bool only_local) const {  // alignment.cc:215-230, aux.cc:23-39
+        std::string out;
+        for (const auto &e : alignment_edges(only_local)) {
+            const int p = first ? e.first : e.second;
+            out += p > 0 ? s[p - 1] : '-';
+        }
+        return out;
+    }
+};
+
+class MultipleAlignment {  // rows of a pairwise Alignment + CLUSTAL writer (multiple_alignment.cc:153-249, :1007-1086)
+public:
+    struct SeqEntry { std::string name, seq; SeqEntry(const std::string &n, const std::string &s) : name(n), seq(s) {} };
+    enum class FormatType { CLUSTAL };
+    MultipleAlignment(const Alignment &a, bool only_local = false) {
+        const bool clash = a.nameA() == a.nameB();
+        rows_.emplace_back(clash ? "A." + a.nameA() : a.nameA(), a.rowA(only_local));
+        rows_.emplace_back(clash ? "B." + a.nameB() : a.nameB(), a.rowB(only_local));
+    }
+    void prepend(const SeqEntry &e) { rows_.insert(rows_.begin(), e); }
+    void append(const SeqEntry &e) { rows_.push_back(e); }
+    size_t length() const { return rows_.empty() ? 0 : rows_[0].seq.size(); }
+    std::ostream &write(std::ostream &out, size_t width, FormatType = FormatType::CLUSTAL) const {
+        size_t namewidth = 18;
+        for (const auto &r : rows_) namewidth = std::max(namewidth, r.name.size());
+        size_t start = 0;
+        do {
+            const size_t end = std::min(length(), start + width);
+            for (const auto &r : rows_) {
+                std::string name = r.name;
+                name.resize(namewidth, ' ');
+                out << name << " " << r.seq.substr(start, end - start) << std::endl;
+            }
+            start = end;
+        } while (start < length() && out << std::endl);
+        return out;
+    }
+private:
+    std::vector<SeqEntry> rows_;
+};
+
+class AlignerParams {  // aligner_params.hh:51-115: same argument names, chained setters instead of named-argument objects
+    friend class Aligner;
+    const RnaData *rnaA_ = nullptr, *rnaB_ = nullptr;
+    ScoringParams scoring_;
+    bool no_lonely_pairs_ = false, struct_local_ = false, sequ_local_ = false, stacking_ = false;
+    std::string free_endgaps_ = "----";
+    int max_diff_am_ = -1, max_diff_at_am_ = -1, max_diff_ = -1;
+    double min_prob_ = 0.001, min_trace_probability_ = 1e-4;
+    std::vector<int> min_col_, max_col_;
+public:
+    AlignerParams &seqA(const RnaData *r) { rnaA_ = r; return *this; }
+    AlignerParams &seqB(const RnaData *r) { rnaB_ = r; return *this; }
+    AlignerParams &scoring(const ScoringParams &s) { scoring_ = s; return *this; }
+    AlignerParams &no_lonely_pairs(bool b) { no_lonely_pairs_ = b; return *this; }
+    AlignerParams &struct_local(bool b) { struct_local_ = b; return *this; }
+    AlignerParams &sequ_local(bool b) { sequ_local_ = b; return *this; }
+    AlignerParams &free_endgaps(const std::string &d) { free_endgaps_ = d; return *this; }
+    AlignerParams &max_diff_am(int d) { max_diff_am_ = d; return *this; }
+    AlignerParams &max_diff_at_am(int d) { max_diff_at_am_ = d; return *this; }
+    AlignerParams &stacking(bool b) { stacking_ = b; return *this; }
+    // the reference passes a TraceController; here either its rows (min_col/max_col) or the two numbers it is built from
+    AlignerParams &trace_controller(const std::vector<int> &min_col, const std::vector<int> &max_col) { min_col_ = min_col; max_col_ = max_col; return *this; }
+    AlignerParams &max_diff(int d) { max_diff_ = d; return *this; }
+    AlignerParams &min_trace_probability(double p) { min_trace_probability_ = p; return *this; }
+    AlignerParams &min_prob(double p) { min_prob_ = p; return *this; }
+};
+
+class Aligner {  // aligner.hh:67-189
+    std::shared_ptr<Context> ctx_;
+    int pair_ = -1;
+    bool traced_ = false;
+    Alignment alignment_;
+public:
+    explicit Aligner(const AlignerParams &ap, int device = 0) : ctx_(std::make_shared<Context>(device)) {
+        if (!ap.rnaA_ || !ap.rnaB_) throw failure("AlignerParams: seqA and seqB are mandatory");
+        if (ap.stacking_ || ap.scoring_.stacking || ap.scoring_.new_stacking) throw failure("locarna_b200: stacking is not supported");
+        if (ap.scoring_.mea_scoring) throw failure("locarna_b200: MEA scoring is not supported");
+        lb200_params p;
+        lb200_default_params(&p);
+        const ScoringParams &s = ap.scoring_;
+        p.min_prob = ap.min_prob_; p.max_diff_am = ap.max_diff_am_; p.max_diff_at_am = ap.max_diff_at_am_; p.max_diff = ap.max_diff_;
+        p.min_trace_probability = ap.min_trace_probability_;
+        p.struct_weight = s.struct_weight; p.indel = s.indel; p.indel_opening = s.indel_opening; p.tau = s.tau_factor;
+        p.exclusion = s.exclusion; p.match = s.match; p.mismatch = s.mismatch; p.use_ribosum = s.use_ribosum;
+        p.unpaired_penalty = s.unpaired_penalty; p.temperature_alipf = s.temperature_alipf;
+        p.no_lonely_pairs = ap.no_lonely_pairs_; p.struct_local = ap.struct_local_; p.sequ_local = ap.sequ_local_;
+        strncpy(p.free_endgaps, ap.free_endgaps_.c_str(), sizeof(p.free_endgaps) - 1);
+        ctx_->check(lb200_set_params(ctx_->get(), &p));
+        const int a = lb200_seq_add_pp(ctx_->get(), ap.rnaA_->filename().c_str());
+        ctx_->check(a);
+        const int b = lb200_seq_add_pp(ctx_->get(), ap.rnaB_->filename().c_str());
+        ctx_->check(b);
+        pair_ = lb200_pair_add(ctx_->get(), a, b, ap.min_col_.empty() ? nullptr : ap.min_col_.data(), ap.max_col_.empty() ? nullptr : ap.max_col_.data());
+        ctx_->check(pair_);
+        char name[256], *seq;
+        const int la = lb200_seq_length(ctx_->get(), a), lb = lb200_seq_length(ctx_->get(), b);
+        seq = new char[std::max(la, lb) + 1];
+        lb200_seq_get(ctx_->get(), a, name, sizeof name, seq); alignment_.nameA_ = name; alignment_.seqA_ = seq;
+        lb200_seq_get(ctx_->get(), b, name, sizeof name, seq); alignment_.nameB_ = name; alignment_.seqB_ = seq;
+        delete[] seq;
+    }
+    //! compute the alignment score (aligner.cc:924-962)
+    infty_score_t align() {
+        ctx_->check(lb200_run(ctx_->get(), LB200_RUN_TRACE));
+        traced_ = true;
+        int64_t sc = 0;
+        ctx_->check(lb200_pair_score(ctx_->get(), pair_, &sc));
+        return sc == LB200_SCORE_NEG_INF ? infty_score_t::neg_infty_value() : infty_score_t((long)sc);
+    }
+    //! trace back (aligner.cc:1345-1363); the device already traced during align()
+    void trace() {
+        if (!traced_) align();
+        lb200_pair_info inf;
+        ctx_->check(lb200_pair_get_info(ctx_->get(), pair_, &inf));
+        std::vector<int> ea(inf.n_edges + 1), eb(inf.n_edges + 1);
+        std::string sa(inf.lenA + 1, '\0'), sb(inf.lenB + 1, '\0');
+        ctx_->check(lb200_pair_alignment(ctx_->get(), pair_, ea.data(), eb.data(), &sa[0], &sb[0]));
+        alignment_.edges_.clear();
+        for (int64_t k = 0; k < inf.n_edges; k++) alignment_.edges_.emplace_back(ea[k], eb[k]);
+        alignment_.strA_ = sa.substr(0, inf.lenA); alignment_.strB_ = sb.substr(0, inf.lenB);
+    }
+    const Alignment &get_alignment() const { return alignment_; }
+    void band(std::vector<int> &min_col, std::vector<int> &max_col) const {
+        lb200_pair_info inf;
+        ctx_->check(lb200_pair_get_info(ctx_->get(), pair_, &inf));
+        min_col.resize(inf.lenA + 1); max_col.resize(inf.lenA + 1);
+        ctx_->check(lb200_pair_band(ctx_->get(), pair_, min_col.data(), max_col.data()));
+    }
+};
+
+}  // namespace LocARNA_B200
+#endif

@@ -37,7 +37,7 @@ class PairInfo(C.Structure):
 
 EXPORTS = [
     "lb200_default_params", "lb200_ctx_create", "lb200_ctx_destroy", "lb200_last_error", "lb200_set_params",
-    "lb200_seq_add_pp", "lb200_seq_add", "lb200_seq_length", "lb200_pair_add", "lb200_num_pairs", "lb200_clear_pairs",
+    "lb200_seq_add_pp", "lb200_seq_add", "lb200_seq_length", "lb200_seq_get", "lb200_pair_add", "lb200_num_pairs", "lb200_clear_pairs",
     "lb200_prepare", "lb200_upload", "lb200_run", "lb200_last_kernel_ms", "lb200_last_h2d_bytes", "lb200_last_d2h_bytes", "lb200_last_dfill_ms", "lb200_last_dfill_launches", "lb200_last_launches", "lb200_pair_score", "lb200_get_scores",
     "lb200_pair_get_info", "lb200_pair_band", "lb200_pair_arcmatches", "lb200_pair_alignment",
 ]
@@ -63,6 +63,7 @@ def load():
     lib.lb200_seq_add_pp.argtypes = [vp, C.c_char_p]
     lib.lb200_seq_add.argtypes = [vp, C.c_char_p, C.c_char_p, ip, ip, dp, C.c_int]
     lib.lb200_seq_length.argtypes = [vp, C.c_int]
+    lib.lb200_seq_get.argtypes = [vp, C.c_int, C.c_char_p, C.c_int, C.c_char_p]
     lib.lb200_pair_add.argtypes = [vp, C.c_int, C.c_int, ip, ip]
     lib.lb200_num_pairs.argtypes = [vp]
     lib.lb200_clear_pairs.argtypes = [vp]

@@ -1,0 +1,161 @@
+// locarna_b200 -- command line front end with the flag surface of the reference's `locarna` (src/locarna.cc:83-272)
+// for the modes the B200 path implements. Output follows src/locarna.cc:766-948: "Score: N", the alignment in
+// CLUSTAL-like blocks of --width columns, and optionally --clustal <file> with the header mlocarna parses
+// ("CLUSTAL W --- LocARNA 2.0.1 --- Score: N", main_helper.icc:556-566, mlocarna:3516-3527).
+// Options of modes that are not implemented are recognised and rejected with an error (exit code 255 like the
+// reference's `return -1`), never ignored.
+#include <getopt.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "locarna_b200.hh"
+
+using namespace LocARNA_B200;
+
+namespace {
+struct Opt { const char *name; int has_arg; int id; };
+enum {
+    O_INDEL = 1000, O_INDEL_OPENING, O_RIBOSUM_FILE, O_USE_RIBOSUM, O_MATCH, O_MISMATCH, O_UNPAIRED_PENALTY, O_STRUCT_WEIGHT, O_EXP_PROB,
+    O_TAU, O_EXCLUSION, O_STACKING, O_NEW_STACKING, O_STRUCT_LOCAL, O_SEQU_LOCAL, O_FREE_ENDGAPS, O_NORMALIZED, O_PENALIZED, O_WIDTH,
+    O_CLUSTAL, O_STOCKHOLM, O_PP, O_LOCAL_OUTPUT, O_LOCAL_FILE_OUTPUT, O_POS_OUTPUT, O_WRITE_STRUCTURE, O_MIN_PROB, O_MAX_BPS_LENGTH_RATIO,
+    O_MAX_DIFF_AM, O_MAX_DIFF, O_MAX_DIFF_AT_AM, O_MIN_TRACE_PROB, O_NOLP, O_MAXBPSPAN, O_TEMPERATURE_ALIPF, O_CONSENSUS_STRUCTURE,
+    O_UNSUPPORTED, O_DEVICE, O_VERSION, O_QUIET, O_VERBOSE, O_HELP
+};
+bool parse_bool(const char *s) {
+    const std::string v = s ? s : "";  // options.cc:867-880
+    if (v == "t" || v == "true" || v == "on" || v == "1") return true;
+    if (v == "f" || v == "false" || v == "off" || v == "0") return false;
+    std::cerr << "ERROR: cannot parse boolean value \"" << v << "\"" << std::endl;
+    exit(255);
+}
+}  // namespace
+
+int main(int argc, char **argv) {
+    static const struct option longopts[] = {
+        {"indel", required_argument, 0, O_INDEL}, {"indel-opening", required_argument, 0, O_INDEL_OPENING},
+        {"ribosum-file", required_argument, 0, O_RIBOSUM_FILE}, {"use-ribosum", required_argument, 0, O_USE_RIBOSUM},
+        {"match", required_argument, 0, O_MATCH}, {"mismatch", required_argument, 0, O_MISMATCH},
+        {"unpaired-penalty", required_argument, 0, O_UNPAIRED_PENALTY}, {"struct-weight", required_argument, 0, O_STRUCT_WEIGHT},
+        {"exp-prob", required_argument, 0, O_EXP_PROB}, {"tau", required_argument, 0, O_TAU}, {"exclusion", required_argument, 0, O_EXCLUSION},
+        {"stacking", no_argument, 0, O_STACKING}, {"new-stacking", no_argument, 0, O_NEW_STACKING},
+        {"struct-local", required_argument, 0, O_STRUCT_LOCAL}, {"sequ-local", required_argument, 0, O_SEQU_LOCAL},
+        {"free-endgaps", required_argument, 0, O_FREE_ENDGAPS}, {"normalized", required_argument, 0, O_NORMALIZED},
+        {"penalized", required_argument, 0, O_PENALIZED}, {"width", required_argument, 0, O_WIDTH}, {"clustal", required_argument, 0, O_CLUSTAL},
+        {"stockholm", required_argument, 0, O_STOCKHOLM}, {"pp", required_argument, 0, O_PP}, {"local-output", no_argument, 0, O_LOCAL_OUTPUT},
+        {"local-file-output", no_argument, 0, O_LOCAL_FILE_OUTPUT}, {"pos-output", no_argument, 0, O_POS_OUTPUT},
+        {"write-structure", no_argument, 0, O_WRITE_STRUCTURE}, {"min-prob", required_argument, 0, O_MIN_PROB},
+        {"max-bps-length-ratio", required_argument, 0, O_MAX_BPS_LENGTH_RATIO}, {"max-diff-am", required_argument, 0, O_MAX_DIFF_AM},
+        {"max-diff", required_argument, 0, O_MAX_DIFF}, {"max-diff-at-am", required_argument, 0, O_MAX_DIFF_AT_AM},
+        {"min-trace-probability", required_argument, 0, O_MIN_TRACE_PROB}, {"noLP", no_argument, 0, O_NOLP},
+        {"maxBPspan", required_argument, 0, O_MAXBPSPAN}, {"temperature-alipf", required_argument, 0, O_TEMPERATURE_ALIPF},
+        {"consensus-structure", required_argument, 0, O_CONSENSUS_STRUCTURE},
+        // recognised, not implemented on the B200 path
+        {"max-diff-aln", required_argument, 0, O_UNSUPPORTED}, {"max-diff-pw-aln", required_argument, 0, O_UNSUPPORTED},
+        {"max-diff-relax", no_argument, 0, O_UNSUPPORTED}, {"kbest", required_argument, 0, O_UNSUPPORTED}, {"better", required_argument, 0, O_UNSUPPORTED},
+        {"mea-alignment", no_argument, 0, O_UNSUPPORTED}, {"match-prob-method", required_argument, 0, O_UNSUPPORTED},
+        {"read-match-probs", required_argument, 0, O_UNSUPPORTED}, {"write-match-probs", required_argument, 0, O_UNSUPPORTED},
+        {"read-arcmatch-scores", required_argument, 0, O_UNSUPPORTED}, {"read-arcmatch-probs", required_argument, 0, O_UNSUPPORTED},
+        {"write-arcmatch-scores", required_argument, 0, O_UNSUPPORTED}, {"write-trace-probs", required_argument, 0, O_UNSUPPORTED},
+        {"alifold-consensus-dp", no_argument, 0, O_UNSUPPORTED}, {"ribofit", required_argument, 0, O_UNSUPPORTED},
+        {"relaxed-anchors", no_argument, 0, O_UNSUPPORTED}, {"score-components", no_argument, 0, O_UNSUPPORTED},
+        {"extended-pf", no_argument, 0, O_UNSUPPORTED}, {"quad-pf", no_argument, 0, O_UNSUPPORTED},
+        {"device", required_argument, 0, O_DEVICE}, {"version", no_argument, 0, O_VERSION}, {"quiet", no_argument, 0, O_QUIET},
+        {"verbose", no_argument, 0, O_VERBOSE}, {"help", no_argument, 0, O_HELP}, {"stopwatch", no_argument, 0, O_VERBOSE},
+        {0, 0, 0, 0}};
+    ScoringParams sp;
+    AlignerParams ap;
+    int width = 120, device = 0;
+    double min_prob = 0.001;
+    bool quiet = false, local_output = false, local_file_output = false, write_structure = false, pos_output = false;
+    std::string clustal;
+    int c, idx = 0;
+    while ((c = getopt_long(argc, argv, "i:m:M:s:e:t:E:w:Lp:D:d:P:qvVh", longopts, &idx)) != -1) {
+        switch (c) {
+            case 'i': case O_INDEL: sp.indel = atoi(optarg); break;
+            case O_INDEL_OPENING: sp.indel_opening = atoi(optarg); break;
+            case O_RIBOSUM_FILE:
+                if (std::string(optarg) != "RIBOSUM85_60") { std::cerr << "ERROR: only the built-in RIBOSUM85_60 is supported by locarna_b200." << std::endl; return 255; }
+                break;
+            case O_USE_RIBOSUM: sp.use_ribosum = parse_bool(optarg); break;
+            case 'm': case O_MATCH: sp.match = atoi(optarg); break;
+            case 'M': case O_MISMATCH: sp.mismatch = atoi(optarg); break;
+            case O_UNPAIRED_PENALTY: sp.unpaired_penalty = atoi(optarg); break;
+            case 's': case O_STRUCT_WEIGHT: sp.struct_weight = atoi(optarg); break;
+            case 't': case O_TAU: sp.tau_factor = atoi(optarg); break;
+            case 'E': case O_EXCLUSION: sp.exclusion = atoi(optarg); break;
+            case O_STRUCT_LOCAL: ap.struct_local(parse_bool(optarg)); break;
+            case O_SEQU_LOCAL: ap.sequ_local(parse_bool(optarg)); break;
+            case O_FREE_ENDGAPS: ap.free_endgaps(optarg); break;
+            case 'w': case O_WIDTH: width = atoi(optarg); break;
+            case O_CLUSTAL: clustal = optarg; break;
+            case 'L': case O_LOCAL_OUTPUT: local_output = true; break;
+            case O_LOCAL_FILE_OUTPUT: local_file_output = true; break;
+            case 'P': case O_POS_OUTPUT: pos_output = true; break;
+            case O_WRITE_STRUCTURE: write_structure = true; break;
+            case 'p': case O_MIN_PROB: min_prob = atof(optarg); break;
+            case 'D': case O_MAX_DIFF_AM: ap.max_diff_am(atoi(optarg)); break;
+            case 'd': case O_MAX_DIFF: ap.max_diff(atoi(optarg)); break;
+            case O_MAX_DIFF_AT_AM: ap.max_diff_at_am(atoi(optarg)); break;
+            case O_MIN_TRACE_PROB: ap.min_trace_probability(atof(optarg)); break;
+            case O_NOLP: ap.no_lonely_pairs(true); break;
+            case O_TEMPERATURE_ALIPF: sp.temperature_alipf = atoi(optarg); break;
+            case O_CONSENSUS_STRUCTURE:
+                if (std::string(optarg) != "none") { std::cerr << "ERROR: --consensus-structure " << optarg << " needs ViennaRNA; only \"none\" is supported." << std::endl; return 255; }
+                break;
+            case O_MAX_BPS_LENGTH_RATIO: if (atof(optarg) != 0.0) { std::cerr << "ERROR: --max-bps-length-ratio is not supported by locarna_b200." << std::endl; return 255; } break;
+            case O_MAXBPSPAN: if (atoi(optarg) != -1) { std::cerr << "ERROR: --maxBPspan is not supported by locarna_b200." << std::endl; return 255; } break;
+            case 'e': case O_EXP_PROB: case O_STACKING: case O_NEW_STACKING: case O_NORMALIZED: case O_PENALIZED: case O_STOCKHOLM: case O_PP:
+            case O_UNSUPPORTED:
+                std::cerr << "ERROR: option --" << (idx >= 0 && longopts[idx].name ? longopts[idx].name : "?")
+                          << " selects a mode that locarna_b200 does not implement." << std::endl;
+                return 255;
+            case O_DEVICE: device = atoi(optarg); break;
+            case 'q': case O_QUIET: quiet = true; break;
+            case 'v': case O_VERBOSE: break;
+            case 'V': case O_VERSION: std::cout << "locarna_b200 (LocARNA 2.0.1 pairwise path, B200)" << std::endl; return 0;
+            case 'h': case O_HELP: std::cout << "usage: locarna_b200 [options as locarna] <fileA.pp> <fileB.pp>" << std::endl; return 0;
+            default: return 255;
+        }
+    }
+    if (argc - optind != 2) { std::cerr << "ERROR: expected two input files (PP 2.0)." << std::endl; return 255; }
+    try {
+        RnaData rnaA(argv[optind], min_prob), rnaB(argv[optind + 1], min_prob);
+        ap.seqA(&rnaA).seqB(&rnaB).scoring(sp).min_prob(min_prob);
+        Aligner aligner(ap, device);
+        const infty_score_t score = aligner.align();
+        if (!quiet) std::cout << "Score: " << score << std::endl << std::endl;     // locarna.cc:769-771
+        aligner.trace();
+        const Alignment &alignment = aligner.get_alignment();
+        int rc = 0;
+        if (!clustal.empty()) {                                                     // main_helper.icc:556-584
+            std::ofstream out(clustal.c_str());
+            if (out.good()) {
+                MultipleAlignment ma(alignment, local_file_output);
+                out << "CLUSTAL W --- LocARNA 2.0.1 --- Score: " << score << std::endl << std::endl;
+                if (write_structure) {
+                    ma.prepend(MultipleAlignment::SeqEntry("", alignment.dot_bracket_structureA(local_file_output)));
+                    ma.append(MultipleAlignment::SeqEntry("", alignment.dot_bracket_structureB(local_file_output)));
+                }
+                ma.write(out, width);
+            } else { std::cerr << "ERROR: Cannot write to " << clustal << "." << std::endl; rc = 255; }
+        }
+        if ((!pos_output && !quiet) || local_output) {                              // locarna.cc:891-935
+            MultipleAlignment ma(alignment, local_output);
+            if (write_structure) {
+                ma.prepend(MultipleAlignment::SeqEntry("", alignment.dot_bracket_structureA(local_output)));
+                ma.append(MultipleAlignment::SeqEntry("", alignment.dot_bracket_structureB(local_output)));
+            }
+            ma.write(std::cout, width);
+        }
+        if (!quiet) std::cout << std::endl;
+        return rc;
+    } catch (failure &f) {
+        std::cerr << "ERROR: " << f.what() << std::endl;
+        return 255;
+    }
+}

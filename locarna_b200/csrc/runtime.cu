@@ -223,6 +223,13 @@ int lb200_seq_length(const lb200_ctx *c, int seq) {
     return c->seqs[seq].len;
 }
 
+int lb200_seq_get(const lb200_ctx *c, int seq, char *name, int name_cap, char *sequence) {
+    if (!c || seq < 0 || seq >= (int)c->seqs.size()) return LB200_ERR_ARG;
+    if (name && name_cap > 0) { strncpy(name, c->seqs[seq].name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+    if (sequence) strcpy(sequence, c->seqs[seq].seq.c_str());
+    return LB200_OK;
+}
+
 int lb200_pair_add(lb200_ctx *c, int seqA, int seqB, const int *min_col, const int *max_col) {
     if (!c || seqA < 0 || seqB < 0 || seqA >= (int)c->seqs.size() || seqB >= (int)c->seqs.size()) return LB200_ERR_ARG;
     if ((min_col == nullptr) != (max_col == nullptr)) return LB200_ERR_ARG;

@@ -85,6 +85,18 @@ def main():
         res = O.ref_batch([(paths[a], paths[b]) for a, b in pl], flags, dump="aln", timing=False)
         out["archaea"] = {"flags": flags, "names": [n for n, _ in names], "pairs": [list(p) for p in pl],
                           "scores": [r["score"] for r in res], "rowA": [r["rowA"] for r in res], "rowB": [r["rowB"] for r in res]}
+    # stdout and --clustal file of the reference's own `locarna` binary (oracle/_ref/locarna) for the CLI parity test
+    import subprocess
+    cli = []
+    for args in ([], ["--noLP", "--max-diff-am", "30"], ["--sequ-local", "true"], ["--free-endgaps", "++++", "--width", "40"],
+                 ["--write-structure"], ["-L", "--sequ-local", "true"], ["-q"]):
+        for a, b in [(0, 1), (2, 3), (4, 5)]:
+            clu = os.path.join(GOLD, "tmp.aln")
+            r = subprocess.run([O.REF_LOCARNA, seqs[a][2], seqs[b][2], "--clustal", clu] + args, capture_output=True, text=True)
+            cli.append({"args": args, "A": os.path.basename(seqs[a][2]), "B": os.path.basename(seqs[b][2]), "rc": r.returncode,
+                        "stdout": r.stdout, "clustal": open(clu).read()})
+            os.unlink(clu)
+    out["cli"] = cli
     with open(os.path.join(GOLD, "reference_outputs.json"), "w") as f:
         json.dump(out, f, indent=0)
     print("wrote", len(out["cases"]), "cases")
