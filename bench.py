@@ -78,8 +78,8 @@ def read_pp(path):
 
 
 def all_vs_all(n):
-    # mlocarna pair order: for a in 0..n-1, for b in 0..a-1, A = sequence a (mlocarna:3577-3604)
-    return [(a, b) for a in range(n) for b in range(a)]
+    from locarna_b200 import allpairs
+    return allpairs.all_vs_all(n)  # mlocarna pair order (mlocarna:3577-3604)
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -309,10 +309,9 @@ def main():
     for s in range(W, n_steps):
         sc, a, b = e2e_step(s)
         h2d += a; d2h += b
-    if dist is not None:  # the one collective of the path: score slices to rank 0
-        t = torch.tensor([x if x is not None else -(2 ** 62) for x in sc], dtype=torch.int64, device="cuda")
-        gathered = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
-        dist.gather(t, gathered, dst=0)
+    if dist is not None:  # the one collective of the path: score slices of the last step to rank 0 (NCCL gather)
+        from locarna_b200 import allpairs
+        gathered = allpairs.gather_scores(dist, list(range(rank * B, rank * B + len(sc))), sc, world * B, device="cuda")
     barrier()
     e2e_elapsed = time.time() - t0
     e2e_ctx.close()

@@ -1,0 +1,74 @@
+"""All-vs-all stage of mlocarna on top of the C ABI: pair order, sharding over ranks, score matrix / score-list formats.
+
+Reference: src/Utils/mlocarna:3547-3643 (compute_all_pairwise_alignments: pair (a, b) for a in 0..n-1, b in 0..a-1, A = the
+later sequence), :2321-2344 (--compute-pairwise-scores k/N partial score lists), lib/perl/MLocarna/SparseMatrix.pm:264-276
+(score list lines "<a> <b> <score>"), lib/perl/MLocarna.pm:2034-2052 (result.matrix, "%6d", diagonal 0).
+The pairwise alignments are independent, so ranks take disjoint subsets (no data-path collective); the only exchange is the
+gather of the score slices to rank 0.
+"""
+from __future__ import annotations
+
+
+def all_vs_all(n: int):
+    """Pair list in mlocarna's order."""
+    return [(a, b) for a in range(n) for b in range(a)]
+
+
+def pair_cost(n_arcs_a: int, n_arcs_b: int, len_a: int, len_b: int) -> float:
+    """Cheap proxy of the D-fill work of a pair: candidate arc matches x band length."""
+    return float(n_arcs_a) * float(n_arcs_b) * (len_a + len_b)
+
+
+def shard_pairs(pairs, costs, world: int):
+    """Longest-processing-time-first assignment of pairs to ranks. Returns a list (per rank) of pair indices, each
+    sorted by descending cost. Deterministic (ties by pair index)."""
+    order = sorted(range(len(pairs)), key=lambda k: (-costs[k], k))
+    load = [0.0] * world
+    shards = [[] for _ in range(world)]
+    for k in order:
+        r = min(range(world), key=lambda x: (load[x], x))
+        shards[r].append(k)
+        load[r] += costs[k]
+    return shards
+
+
+def assemble_matrix(n: int, pairs, scores, neg_inf_value: int = -100000000):
+    """Symmetric score matrix with zero diagonal (mlocarna:2353-2373); '-inf' maps to -1e8 (mlocarna:3523)."""
+    m = [[0] * n for _ in range(n)]
+    for (a, b), s in zip(pairs, scores):
+        v = neg_inf_value if s is None else int(s)
+        m[a][b] = v
+        m[b][a] = v
+    return m
+
+
+def format_matrix(m) -> str:
+    return "".join(" ".join("%6d" % v for v in row) + "\n" for row in m)
+
+
+def format_score_list(pairs, scores) -> str:
+    """scores/scores-<k> format consumed by `mlocarna --score-lists`."""
+    return "".join("%d %d %s\n" % (a, b, "-inf" if s is None else str(int(s))) for (a, b), s in zip(pairs, scores))
+
+
+def gather_scores(dist, local_idx, local_scores, n_pairs: int, device=None):
+    """Gather per-rank (pair index, score) slices on rank 0 with one collective. `dist` is torch.distributed (NCCL on the
+    GPU box, gloo in the CPU tests). Returns the full score list on rank 0, None elsewhere."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    cap = (n_pairs + world - 1) // world + 1
+    NEG = -(2 ** 62)
+    buf = torch.full((cap, 2), -1, dtype=torch.int64, device=device)
+    for k, (i, s) in enumerate(zip(local_idx, local_scores)):
+        buf[k, 0] = i
+        buf[k, 1] = NEG if s is None else int(s)
+    out = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+    dist.gather(buf, out, dst=0)
+    if rank != 0:
+        return None
+    scores = [None] * n_pairs
+    for t in out:
+        for i, s in t.tolist():
+            if i >= 0:
+                scores[i] = None if s == NEG else s
+    return scores
