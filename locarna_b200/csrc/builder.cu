@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(128) task_kernel(BuildCtx b) {
             int umax = 0;
             for (int i = tk.al + 1; i <= tk.R; i++) {
                 const int jl = max((int)tk.bl + 1, v.lo[i]), jh = min((int)tk.C, v.hi[i]);
-                if (jh >= jl) { cells += jh - jl + 1; umax = (i - tk.al) + (jh - tk.bl); }
+                if (jh >= jl) { cells += (unsigned long long)(jh - jl + 1) * (b.struct_local ? 4 : 1); umax = (i - tk.al) + (jh - tk.bl); }  // 4 align_noex states
             }
             const int t0 = min(tk.al + tk.bl + 8, s_last), t1 = min(tk.al + tk.bl + umax + 1, s_last);
             if (t1 > t0) terms += sp[t1] - sp[t0];

@@ -15,7 +15,7 @@ struct BuildCtx {
     const int *arc_left, *arc_right, *arc_weight, *lptr, *lcount;
     const int *am_seq;                          // 256: (tau * ribosum arc-match score) / 100
     int sigma8[64];
-    int tau, use_ribosum, no_lonely_pairs, max_diff_am, max_diff_at_am;
+    int tau, use_ribosum, no_lonely_pairs, struct_local, max_diff_am, max_diff_at_am;
     // outputs / work arrays
     int *cell_start;                            // total_cells + 1: counts, then exclusive offsets (global L-order index)
     DevArcMatch *am;

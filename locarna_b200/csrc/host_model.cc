@@ -432,7 +432,7 @@ void build_pair_problem(const Sequence &A, const Sequence &B, const Band &band, 
         int umax = 0;
         for (int i = tk.al + 1; i <= tk.R; i++) {
             const int jl = std::max((int)tk.bl + 1, lo[i]), jh = std::min((int)tk.C, hi[i]);
-            if (jh >= jl) { out.cells += jh - jl + 1; umax = (i - tk.al) + (jh - tk.bl); }
+            if (jh >= jl) { out.cells += (uint64_t)(jh - jl + 1) * (p.struct_local ? 4 : 1); umax = (i - tk.al) + (jh - tk.bl); }
         }
         {   // entries streamed: right ends on local anti-diagonals 8..umax
             const int s0 = std::min(tk.al + tk.bl + 8, n + m + 1), s1 = std::min(tk.al + tk.bl + umax + 1, n + m + 1);

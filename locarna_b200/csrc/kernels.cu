@@ -278,6 +278,204 @@ __device__ void fill_box(const DevCtx &c, const DevPair &pr, const BoxGeom &g, c
     __syncwarp();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Structure-local boxes (aligner.cc:398-418 init, :443-564 fill): eight matrices per box.
+//   closed states 0..3 = E_NO_NO, E_X_NO, E_NO_X, E_X_X run the align_noex recurrence with their own E/F and their own
+//   arc-match sources M_k(al'-1, bl'-1); open states E_OP_NO, E_NO_OP, E_OP_X, E_X_OP (here 0..3 of the o-arrays) are running
+//   maxima along a column / row. All cross terms are cell-local or read the up / left neighbour, so one anti-diagonal sweep
+//   computes the eight matrices together, per cell in the reference's matrix order
+//   NO_NO, OP_NO, NO_OP, NO_X, OP_X, X_NO, X_OP, X_X.
+// Boxes: box_k = boxes + k * box_words, k = 0..3 closed states, 4..7 = OP_NO, NO_OP, OP_X, X_OP (only if STORE_OPEN, for the
+// traceback). Four accumulator rings (one per closed state) in ws.arcbuf.
+struct SlBorder { int col[8], col_step[8], row[8], row_step[8]; };
+
+__device__ __forceinline__ void sl_borders(const DevParams &P, SlBorder &b) {
+    // init_state(state, globalA, exclA, globalB, exclB): aligner.cc:398-417
+    const bool gA[8] = {true, true, true, true, false, true, false, true};     // NO_NO X_NO NO_X X_X OP_NO NO_OP OP_X X_OP
+    const bool xA[8] = {false, true, false, true, false, false, false, true};
+    const bool gB[8] = {true, true, true, true, true, false, true, false};
+    const bool xB[8] = {false, false, true, true, false, false, true, false};
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        b.col[k] = xA[k] ? P.exclusion : (gA[k] ? P.open : 0); b.col_step[k] = (!xA[k] && gA[k]) ? P.gap : 0;
+        b.row[k] = xB[k] ? P.exclusion : (gB[k] ? P.open : 0); b.row_step[k] = (!xB[k] && gB[k]) ? P.gap : 0;
+    }
+}
+
+template <int NC, int PAR, bool STORE_OPEN>
+__device__ __forceinline__ void dp_step_sl(const BoxGeom &g, const SlBorder &bd, const WarpSmem &ws, int *boxes, int box_words,
+                                           const DevParams &P, int u, int lane, int (&mE)[4][NC], int (&eE)[4][NC], int (&fE)[4][NC],
+                                           int (&mO)[4][NC], int (&eO)[4][NC], int (&fO)[4][NC], int (&oE)[4][NC], int (&oO)[4][NC]) {
+    constexpr int NW = 32 * NC;
+    // open-state order in the o-arrays: 0 OP_NO (up), 1 NO_OP (left), 2 OP_X (up), 3 X_OP (left)
+    int xm[4], xo[4], xop[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (PAR == 0) {
+            xm[k] = __shfl_up_sync(0xffffffffu, mO[k][NC - 1], 1);
+            xo[k] = __shfl_up_sync(0xffffffffu, fO[k][NC - 1], 1);
+            xop[k] = __shfl_up_sync(0xffffffffu, oO[k][NC - 1], 1);
+            if (lane == 0) { xm[k] = LB_NEG; xo[k] = LB_NEG; xop[k] = LB_NEG; }
+        } else {
+            xm[k] = __shfl_down_sync(0xffffffffu, mE[k][0], 1);
+            xo[k] = __shfl_down_sync(0xffffffffu, eE[k][0], 1);
+            xop[k] = __shfl_down_sync(0xffffffffu, oE[k][0], 1);
+            if (lane == 31) { xm[k] = LB_NEG; xo[k] = LB_NEG; xop[k] = LB_NEG; }
+        }
+    }
+    const int U2 = (u - g.vmin - PAR) >> 1, J2 = (u + g.vmin + PAR) >> 1;
+    const int ring = (u & (RING - 1)) * NW;
+    const int ex = P.exclusion;
+    int nm[4][NC], ne[4][NC], nf[4][NC], no[4][NC];
+#pragma unroll
+    for (int k = 0; k < NC; k++) {
+        const int gidx = lane * NC + k;
+        const int ip = U2 - gidx, jp = J2 + gidx;
+        const uint32_t ridx = min((uint32_t)(ip + 1), (uint32_t)(g.Rn + 2));
+        const uint32_t cidx = min((uint32_t)jp, (uint32_t)(g.Cn + 1));
+        const uint32_t rr = ws.rowrange[ridx];
+        const int sg = ws.sig[ws.rowcode[ridx] + ws.colcode[cidx]];
+        const bool ok = (uint32_t)(2 * gidx + PAR - (int)(rr & 0xffff)) <= (rr >> 16);
+        const bool brow = ip == 0, bcol = (jp == 0) & (ip != 0);
+        int cm[4];  // closed states of this cell before the cross terms (align_noex)
+#pragma unroll
+        for (int st = 0; st < 4; st++) {
+            int m_up, e_up, m_left, f_left, m_diag;
+            if (PAR == 0) {
+                m_up = mO[st][k]; e_up = eO[st][k]; m_diag = mE[st][k];
+                if (k == 0) { m_left = xm[st]; f_left = xo[st]; } else { m_left = mO[st][k > 0 ? k - 1 : 0]; f_left = fO[st][k > 0 ? k - 1 : 0]; }
+            } else {
+                m_left = mE[st][k]; f_left = fE[st][k]; m_diag = mO[st][k];
+                if (k == NC - 1) { m_up = xm[st]; e_up = xo[st]; } else { m_up = mE[st][k < NC - 1 ? k + 1 : k]; e_up = eE[st][k < NC - 1 ? k + 1 : k]; }
+            }
+            int e = addmax(e_up, P.gap, m_up + P.gap_open);
+            int f = addmax(f_left, P.gap, m_left + P.gap_open);
+            int *acc = ws.arcbuf + st * (RING * NW) + ring + gidx;
+            const int arc = *acc;
+            *acc = LB_NEG;
+            cm[st] = max3(addmax(m_diag, sg, e), f, arc);
+            ne[st][k] = e; nf[st][k] = f;
+        }
+        // neighbours of the open states
+        int o_up0, o_up2, o_left1, o_left3;
+        if (PAR == 0) {
+            o_up0 = oO[0][k]; o_up2 = oO[2][k];
+            if (k == 0) { o_left1 = xop[1]; o_left3 = xop[3]; } else { o_left1 = oO[1][k > 0 ? k - 1 : 0]; o_left3 = oO[3][k > 0 ? k - 1 : 0]; }
+        } else {
+            o_left1 = oE[1][k]; o_left3 = oE[3][k];
+            if (k == NC - 1) { o_up0 = xop[0]; o_up2 = xop[2]; } else { o_up0 = oE[0][k < NC - 1 ? k + 1 : k]; o_up2 = oE[2][k < NC - 1 ? k + 1 : k]; }
+        }
+        // matrix order of the reference: NO_NO, OP_NO, NO_OP, NO_X, OP_X, X_NO, X_OP, X_X (aligner.cc:443-563)
+        int m0 = cm[0];
+        int op_no = max(o_up0, m0);
+        int no_op = max(o_left1, m0);
+        int m2 = max(cm[2], no_op + ex);       // E_NO_X
+        int op_x = max(o_up2, m2);
+        int m1 = max(cm[1], op_no + ex);       // E_X_NO
+        int x_op = max(o_left3, m1);
+        int m3 = max3(cm[3], op_x + ex, x_op + ex);  // E_X_X
+        int mm[4] = {m0, m1, m2, m3};
+        int oo[4] = {op_no, no_op, op_x, x_op};
+        if (brow | bcol) {  // explicit borders (init_state); the origin is 0 in every state
+            const int t = brow ? jp : ip;
+#pragma unroll
+            for (int st = 0; st < 4; st++) {
+                mm[st] = (brow && jp == 0) ? 0 : (brow ? bd.row[st] + t * bd.row_step[st] : bd.col[st] + t * bd.col_step[st]);
+                oo[st] = (brow && jp == 0) ? 0 : (brow ? bd.row[4 + st] + t * bd.row_step[4 + st] : bd.col[4 + st] + t * bd.col_step[4 + st]);
+                ne[st][k] = LB_NEG; nf[st][k] = LB_NEG;
+            }
+        }
+#pragma unroll
+        for (int st = 0; st < 4; st++) {
+            if (ok) {
+                boxes[st * box_words + u * g.nslots + gidx] = mm[st];
+                if (STORE_OPEN) boxes[(4 + st) * box_words + u * g.nslots + gidx] = oo[st];
+            }
+            nm[st][k] = ok ? mm[st] : LB_NEG; no[st][k] = ok ? oo[st] : LB_NEG;
+            if (!ok) { ne[st][k] = LB_NEG; nf[st][k] = LB_NEG; }
+        }
+    }
+#pragma unroll
+    for (int st = 0; st < 4; st++)
+#pragma unroll
+        for (int k = 0; k < NC; k++) {
+            if (PAR == 0) { mE[st][k] = nm[st][k]; eE[st][k] = ne[st][k]; fE[st][k] = nf[st][k]; oE[st][k] = no[st][k]; }
+            else { mO[st][k] = nm[st][k]; eO[st][k] = ne[st][k]; fO[st][k] = nf[st][k]; oO[st][k] = no[st][k]; }
+        }
+}
+
+// Fill the eight matrices of one structure-local box. The arc-match entries are folded synchronously per step (this path
+// serves single long pairs, not the batched all-vs-all workload).
+template <int NC, bool STORE_OPEN>
+__device__ void fill_box_sl(const DevCtx &c, const DevPair &pr, const BoxGeom &g, const WarpSmem &ws, int *boxes, int box_words) {
+    const int lane = threadIdx.x & 31;
+    constexpr int NW = 32 * NC;
+    const DevParams &P = c.params;
+    SlBorder bd;
+    sl_borders(P, bd);
+    for (int k = lane; k < 4 * RING * NW; k += 32) ws.arcbuf[k] = LB_NEG;
+    const int *sptr = c.sptr + pr.sptr;
+    const int s_base = g.al + g.bl, s_last = pr.lenA + pr.lenB + 1;
+    auto sp = [&](int t) { return __ldg(sptr + min(s_base + min(t, g.umax + 1), s_last)); };
+    const DevEntry *ent = c.ent + pr.am_base;
+    const int *dval = c.dval + pr.am_base;
+    int mE[4][NC], eE[4][NC], fE[4][NC], mO[4][NC], eO[4][NC], fO[4][NC], oE[4][NC], oO[4][NC];
+#pragma unroll
+    for (int st = 0; st < 4; st++)
+#pragma unroll
+        for (int k = 0; k < NC; k++) { mE[st][k] = eE[st][k] = fE[st][k] = mO[st][k] = eO[st][k] = fO[st][k] = oE[st][k] = oO[st][k] = LB_NEG; }
+    const int par0 = (0 - g.vmin) & 1;
+    {
+        const int c0 = -g.vmin;
+#pragma unroll
+        for (int k = 0; k < NC; k++) {
+            if (2 * (lane * NC + k) + par0 == c0) {
+#pragma unroll
+                for (int st = 0; st < 4; st++) {
+                    if (par0 == 0) { mE[st][k] = 0; oE[st][k] = 0; } else { mO[st][k] = 0; oO[st][k] = 0; }
+                    boxes[st * box_words + (c0 >> 1)] = 0;
+                    if (STORE_OPEN) boxes[(4 + st) * box_words + (c0 >> 1)] = 0;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    for (int u = 1; u <= g.umax; u++) {
+        // arc-match terms of anti-diagonal u: sources lie >= 8 anti-diagonals back
+        {
+            const int e0 = sp(u), e1 = sp(u + 1);
+            const int tring = (u & (RING - 1)) * NW;
+            for (int e = e0 + lane; e < e1; e += 32) {
+                const DevEntry en = ent[e];
+                const int p = (int)(en.x & 0xfff) - g.al, q = (int)(en.x >> 12) - g.bl;
+                const int ar = (int)(en.y & 0xfff) - g.al, br = (int)(en.y >> 12) - g.bl;
+                if ((p | q | (g.Rn - ar) | (g.Cn - br)) >= 0) {
+                    const int d = dval[e];
+                    const int src = (p + q) * g.nslots + ((q - p - g.vmin) >> 1);
+                    const int slot = tring + ((br - ar - g.vmin) >> 1);
+#pragma unroll
+                    for (int st = 0; st < 4; st++) atomicMax(&ws.arcbuf[st * (RING * NW) + slot], boxes[st * box_words + src] + d);
+                }
+            }
+        }
+        __syncwarp();
+        if (((u + par0) & 1) == 0) dp_step_sl<NC, 0, STORE_OPEN>(g, bd, ws, boxes, box_words, P, u, lane, mE, eE, fE, mO, eO, fO, oE, oO);
+        else dp_step_sl<NC, 1, STORE_OPEN>(g, bd, ws, boxes, box_words, P, u, lane, mE, eE, fE, mO, eO, fO, oE, oO);
+        __syncwarp();
+    }
+}
+
+template <bool STORE_OPEN>
+__device__ bool run_box_sl(const DevCtx &c, const DevPair &pr, const BoxGeom &g, const WarpSmem &ws, int *boxes, int box_words) {
+    const int nc = (g.nslots + 31) >> 5;
+    if (nc <= 1) fill_box_sl<1, STORE_OPEN>(c, pr, g, ws, boxes, box_words);
+    else if (nc <= 2) fill_box_sl<2, STORE_OPEN>(c, pr, g, ws, boxes, box_words);
+    else if (nc <= 3) fill_box_sl<3, STORE_OPEN>(c, pr, g, ws, boxes, box_words);
+    else if (nc <= 4) fill_box_sl<4, STORE_OPEN>(c, pr, g, ws, boxes, box_words);
+    else return false;
+    return true;
+}
+
 __device__ __forceinline__ int box_get(const int *box, const BoxGeom &g, int ip, int jp) {
     return box[(ip + jp) * g.nslots + ((jp - ip - g.vmin) >> 1)];
 }
@@ -348,6 +546,52 @@ __global__ void __launch_bounds__(32) dfill_kernel(DevCtx c, int q) {
             if (nolp && x.inner < 0) continue;
             const int ar = (x.ends_a >> 12) & 0xfff, br = (x.ends_b >> 12) & 0xfff;
             const int mv = box_get(box, g, ar - sh - g.al, br - sh - g.bl);
+            int d;
+            if (nolp) {
+                const DevArcMatch in = am[x.inner];
+                const int a = (mv < LB_NEG_LIMIT) ? LB_NEG : mv + in.score;
+                const int y = max(a, dval[in.spos]);
+                d = (y < LB_NEG_LIMIT) ? LB_NEG : y + x.score;
+            } else d = (mv < LB_NEG_LIMIT) ? LB_NEG : mv + x.score;
+            dval[x.spos] = d;
+        }
+        __syncwarp();
+    }
+}
+
+// D-fill for --struct-local: D = max over the four closed states (aligner.cc:586-595, :632-640)
+__global__ void __launch_bounds__(32) dfill_sl_kernel(DevCtx c, int q) {
+    extern __shared__ int smem[];
+    const int lane = threadIdx.x;
+    const int task_begin = c.qstart[q], task_end = c.qstart[q + 1];
+    if ((int)blockIdx.x >= task_end - task_begin) return;
+    int *cursor = c.cursor + q;
+    WarpSmem ws;
+    carve(c, smem, ws);
+    const int box_words = c.scratch_words / 8;
+    int *boxes = c.scratch + (size_t)blockIdx.x * c.scratch_words;
+    const bool nolp = c.params.no_lonely_pairs != 0;
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = task_begin + atomicAdd(cursor, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= task_end) break;
+        const DevTask task = c.tasks[t];
+        const DevPair pr = c.pairs[task.pair];
+        BoxGeom g;
+        setup_box(c, pr, task.al, task.bl, task.R, task.C, g, ws);
+        if ((g.umax + 1) * g.nslots > box_words) { if (lane == 0) atomicExch(c.error_flag, 2); continue; }
+        if (!run_box_sl<false>(c, pr, g, ws, boxes, box_words)) { if (lane == 0) atomicExch(c.error_flag, 1); continue; }
+        const DevArcMatch *am = c.am + pr.am_base;
+        int *dval = c.dval + pr.am_base;
+        const int sh = nolp ? 2 : 1;
+        for (int k = task.run_start + lane; k < task.run_start + task.run_count; k += 32) {
+            const DevArcMatch x = am[k];
+            if (nolp && x.inner < 0) continue;
+            const int ar = (x.ends_a >> 12) & 0xfff, br = (x.ends_b >> 12) & 0xfff;
+            int mv = LB_NEG;
+#pragma unroll
+            for (int st = 0; st < 4; st++) mv = max(mv, box_get(boxes + st * box_words, g, ar - sh - g.al, br - sh - g.bl));
             int d;
             if (nolp) {
                 const DevArcMatch in = am[x.inner];
@@ -615,6 +859,12 @@ void launch_dfill(const DevCtx &c, int ncmax, bool generic_borders, int grid, in
     else dfill_kernel<N, false><<<grid, 32, smem_bytes, st>>>(c, q)
     LB_DISPATCH(ncmax, CALL);
 #undef CALL
+}
+void launch_dfill_sl(const DevCtx &c, int grid, int smem_bytes, int q, cudaStream_t st) { dfill_sl_kernel<<<grid, 32, smem_bytes, st>>>(c, q); }
+cudaError_t configure_sl(int smem_bytes, int *ctas_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(dfill_sl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, dfill_sl_kernel, 32, smem_bytes);
+    return e;
 }
 void launch_toplevel(const DevCtx &c, int ncmax, int grid, int smem_bytes, int pair_begin, int pair_end, int *cursor, cudaStream_t st) {
     const bool clamp = c.params.sequ_local != 0;

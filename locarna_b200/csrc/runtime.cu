@@ -22,6 +22,8 @@ void launch_dfill(const DevCtx &c, int ncmax, bool generic_borders, int grid, in
 void launch_toplevel(const DevCtx &c, int ncmax, int grid, int smem_bytes, int pair_begin, int pair_end, int *cursor, cudaStream_t st);
 void launch_trace(const DevCtx &c, int ncmax, bool generic_borders, int grid, int smem_bytes, int pair_begin, int pair_end, int *cursor, cudaStream_t st);
 cudaError_t configure_kernels(int ncmax, int smem_bytes, int *dfill_ctas_per_sm);
+void launch_dfill_sl(const DevCtx &c, int grid, int smem_bytes, int q, cudaStream_t st);
+cudaError_t configure_sl(int smem_bytes, int *ctas_per_sm);
 }  // namespace lb200
 
 using namespace lb200;
@@ -192,7 +194,6 @@ const char *lb200_last_error(const lb200_ctx *c) { return c ? c->err.c_str() : "
 int lb200_set_params(lb200_ctx *c, const lb200_params *p) {
     if (!c || !p) return LB200_ERR_ARG;
     if (!c->seqs.empty()) return fail(c, LB200_ERR_STATE, "parameters must be set before sequences are added");
-    if (p->struct_local) return fail(c, LB200_ERR_UNSUPPORTED, "--struct-local is not implemented on the B200 path yet");
     c->params = to_params(*p);
     make_score_tables(c->params, c->tables);
     return LB200_OK;
@@ -400,13 +401,16 @@ int lb200_upload(lb200_ctx *c) {
     dc.max_rows = max_rows;
     dc.rowcode_bytes = (max_rows + 2 + 3) & ~3;
     dc.colcode_bytes = (max_cols + 1 + 3) & ~3;
-    dc.arcbuf_words = 8 * 32 * nc_inst;
+    const bool sl = c->params.struct_local;
+    if (sl && ncmax > 4) return fail(c, LB200_ERR_UNSUPPORTED, "--struct-local supports bands of up to 256 diagonals (this batch: %d)", wd_bound);
+    dc.arcbuf_words = 8 * 32 * nc_inst * (sl ? 4 : 1);  // structure local: one accumulator ring per closed state
     const int smem_bytes = (64 + dc.max_rows + 2 + dc.arcbuf_words) * 4 + dc.rowcode_bytes + dc.colcode_bytes;
     if (smem_bytes > (int)c->prop.sharedMemPerBlockOptin) return fail(c, LB200_ERR_UNSUPPORTED, "problem needs %d bytes of shared memory per warp", smem_bytes);
     int ctas_per_sm = 1;
     CUDA_TRY(c, configure_kernels(nc_inst, smem_bytes, &ctas_per_sm));
+    if (sl) CUDA_TRY(c, configure_sl(smem_bytes, &ctas_per_sm));
     const int grid_cap = std::max(1, ctas_per_sm) * c->prop.multiProcessorCount;
-    dc.scratch_words = max_box_words;
+    dc.scratch_words = max_box_words * (sl ? 8 : 1);  // structure local: eight matrices per box
 
     // ---- device builder
     CUDA_TRY(c, upload(c->d_pairs, h_pairs, st));
@@ -425,7 +429,7 @@ int lb200_upload(lb200_ctx *c) {
     b.arc_left = (const int *)c->d_arc_left.p; b.arc_right = (const int *)c->d_arc_right.p; b.arc_weight = (const int *)c->d_arc_weight.p;
     b.lptr = (const int *)c->d_lptr.p; b.lcount = (const int *)c->d_lcount.p; b.am_seq = (const int *)c->d_am_seq.p;
     memcpy(b.sigma8, c->tables.dev.sigma8, sizeof b.sigma8);
-    b.tau = c->params.tau; b.use_ribosum = c->params.use_ribosum; b.no_lonely_pairs = c->params.no_lonely_pairs;
+    b.tau = c->params.tau; b.use_ribosum = c->params.use_ribosum; b.no_lonely_pairs = c->params.no_lonely_pairs; b.struct_local = c->params.struct_local;
     b.max_diff_am = c->params.max_diff_am; b.max_diff_at_am = c->params.max_diff_at_am;
     b.cell_start = (int *)c->d_cell_start.p; b.sptr = (int *)c->d_sptr.p; b.stats = (DevPairStats *)c->d_stats.p;
     b.n_tasks = (unsigned *)c->d_ntasks.p; b.qstart = (int *)c->d_qstart.p;
@@ -506,6 +510,7 @@ int lb200_run(lb200_ctx *c, int flags) {
     lb200_ctx::Resident &R = c->res;
     cudaStream_t st = c->stream;
     const bool do_trace = (flags & LB200_RUN_TRACE) != 0;
+    if (do_trace && c->params.struct_local) return fail(c, LB200_ERR_UNSUPPORTED, "traceback of --struct-local alignments is not implemented on the B200 path yet");
     if (do_trace) {
         CUDA_TRY(c, c->d_tr_edges.ensure((size_t)R.sptr_total * 4));
         CUDA_TRY(c, c->d_tr_str.ensure((size_t)R.sptr_total));
@@ -522,7 +527,8 @@ int lb200_run(lb200_ctx *c, int flags) {
     CUDA_TRY(c, lb200_fill_i32((int *)c->d_dval.p, R.total_am, LB_NEG, st));
     int64_t launches = 1;
     for (int q = R.q_lo; q <= R.q_hi; q++) {
-        launch_dfill(dc, R.nc_inst, c->params.indel_opening > 0, R.grid_cap, R.smem_bytes, q, st);
+        if (c->params.struct_local) launch_dfill_sl(dc, R.grid_cap, R.smem_bytes, q, st);
+        else launch_dfill(dc, R.nc_inst, c->params.indel_opening > 0, R.grid_cap, R.smem_bytes, q, st);
         launches++;
     }
     CUDA_TRY(c, cudaEventRecord(c->ev_mid, st));

@@ -21,6 +21,9 @@ FLAGSETS = [
     {"no-ribosum": True, "indel-opening": 0, "tau": 100},
     {"unpaired-penalty": 10, "struct-weight": 150, "noLP": True},
     {"indel-opening": 40, "indel": -120},  # positive opening: explicit border initialisation in the D-fill kernel
+    {"struct-local": True},
+    {"struct-local": True, "exclusion": -100, "noLP": True},
+    {"struct-local": True, "sequ-local": True, "exclusion": -250},
 ]
 
 
