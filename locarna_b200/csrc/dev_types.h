@@ -72,7 +72,7 @@ struct DevTask {
 };
 
 // a box whose optimal path still has to be traced (traceback kernel)
-struct TraceJob { short al, bl, R, C; };
+struct TraceJob { short al, bl, R, C; int am; };  // am: L-order index of the arc match the box belongs to (struct-local)
 
 struct DevTopResult {
     int score;         // LB_NEG.. if -inf

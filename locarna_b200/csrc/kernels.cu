@@ -734,7 +734,7 @@ __global__ void __launch_bounds__(32) trace_kernel(DevCtx c, int pair_begin, int
         const DevTopResult top = c.top[t];
         bool tl = true;
         TraceJob job;
-        job.al = 0; job.bl = 0; job.R = (short)n; job.C = (short)m;
+        job.al = 0; job.bl = 0; job.R = (short)n; job.C = (short)m; job.am = -1;
         bool have = true;
         while (have) {
             BoxGeom g;
@@ -815,7 +815,7 @@ __global__ void __launch_bounds__(32) trace_kernel(DevCtx c, int pair_begin, int
                 emit(xl, yl, LB_EDGE_MATCH);
                 emit(i, j, LB_EDGE_MATCH);
                 if (!nolp) {                                                                 // trace_arcmatch :967-1028
-                    if (lane == 0) { TraceJob nj; nj.al = (short)xl; nj.bl = (short)yl; nj.R = (short)(i - 1); nj.C = (short)(j - 1); stack[sp] = nj; }
+                    if (lane == 0) { TraceJob nj; nj.al = (short)xl; nj.bl = (short)yl; nj.R = (short)(i - 1); nj.C = (short)(j - 1); nj.am = -1; stack[sp] = nj; }
                     sp++;
                 } else {                                                                     // trace_arcmatch_noLP :1030-1079
                     int cur = (int)lpos[found];
@@ -827,7 +827,182 @@ __global__ void __launch_bounds__(32) trace_kernel(DevCtx c, int pair_begin, int
                         emit(ial, ibl, LB_EDGE_MATCH);
                         emit(iar, ibr, LB_EDGE_MATCH);
                         if (dval[x.spos] == dval[in.spos] + x.score) { cur = x.inner; continue; }
-                        if (lane == 0) { TraceJob nj; nj.al = (short)ial; nj.bl = (short)ibl; nj.R = (short)(iar - 1); nj.C = (short)(ibr - 1); stack[sp] = nj; }
+                        if (lane == 0) { TraceJob nj; nj.al = (short)ial; nj.bl = (short)ibl; nj.R = (short)(iar - 1); nj.C = (short)(ibr - 1); nj.am = -1; stack[sp] = nj; }
+                        sp++;
+                        break;
+                    }
+                }
+                i = xl - 1; j = yl - 1;
+            }
+            __syncwarp();
+            tl = false;
+            have = sp > 0;
+            if (have) { sp--; job = stack[sp]; }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Traceback for --struct-local (aligner.cc:1019-1026, :1065-1076, :1289-1342): the top level box has the single state
+// E_NO_NO; every arc-match box is refilled with all eight matrices and walked with the reference's state machine.
+template <bool CLAMP>
+__global__ void __launch_bounds__(32) trace_sl_kernel(DevCtx c, int pair_begin, int pair_end, int *cursor) {
+    extern __shared__ int smem[];
+    const int lane = threadIdx.x;
+    WarpSmem ws;
+    carve(c, smem, ws);
+    const int box_words = c.scratch_words / 8;
+    int *boxes = c.scratch + (size_t)blockIdx.x * c.scratch_words;
+    const DevParams &P = c.params;
+    const bool nolp = P.no_lonely_pairs != 0;
+    const int ex = P.exclusion;
+    BoxInit top_init;
+    const bool globalA = !(P.sequ_local || P.fe_left2), globalB = !(P.sequ_local || P.fe_left1);
+    top_init.col_base = globalA ? P.open : 0; top_init.col_step = globalA ? P.gap : 0;
+    top_init.row_base = globalB ? P.open : 0; top_init.row_step = globalB ? P.gap : 0;
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = pair_begin + atomicAdd(cursor, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= pair_end) break;
+        const DevPair pr = c.pairs[t];
+        const int n = pr.lenA, m = pr.lenB;
+        const int *lo = c.band_lo + pr.band, *hi = c.band_hi + pr.band;
+        const uint8_t *ca = c.codes + pr.codesA, *cb = c.codes + pr.codesB;
+        const DevEntry *ent = c.ent + pr.am_base;
+        const int *dval = c.dval + pr.am_base;
+        const DevArcMatch *am = c.am + pr.am_base;
+        const unsigned *lpos = c.lpos + pr.am_base;
+        const int *sptr = c.sptr + pr.sptr;
+        int *edges = c.trace_edges + pr.sptr;
+        char *strA = c.trace_str + pr.sptr, *strB = strA + n + 1;
+        TraceJob *stack = c.trace_stack + (size_t)t * c.trace_stack_cap;
+        for (int k = lane; k < n + m + 3; k += 32) edges[k] = 0;
+        for (int k = lane; k <= n; k += 32) strA[k] = '.';
+        for (int k = lane; k <= m; k += 32) strB[k] = '.';
+        __syncwarp();
+        auto valid = [&](int i, int j) { return i >= 0 && j >= 0 && lo[i] <= j && j <= hi[i]; };
+        auto emit = [&](int i, int j, int kind) { if (lane == 0) edges[i + j] = (i << 2) | kind; };
+        int sp = 0;
+        const DevTopResult top = c.top[t];
+        bool tl = true;
+        TraceJob job;
+        job.al = 0; job.bl = 0; job.R = (short)n; job.C = (short)m; job.am = -1;
+        bool have = true;
+        while (have) {
+            BoxGeom g;
+            setup_box(c, pr, job.al, job.bl, job.R, job.C, g, ws);
+            bool ok = (g.umax + 1) * g.nslots <= box_words;
+            if (ok) ok = tl ? run_box<4, true, CLAMP>(c, pr, g, top_init, ws, boxes) : run_box_sl<true>(c, pr, g, ws, boxes, box_words);
+            if (!ok) { if (lane == 0) atomicExch(c.error_flag, 3); break; }
+            const int al = job.al, bl = job.bl;
+            auto B = [&](int st, int i, int j) { return box_get(boxes + st * box_words, g, i - al, j - bl); };
+            // M_st(i, j) or -inf if the cell is outside the band (such cells hold -inf in the reference, aligner.cc:322-367)
+            auto Bv = [&](int st, int i, int j) { return valid(i, j) ? B(st, i, j) : LB_NEG; };
+            int i = tl ? top.max_i : job.R, j = tl ? top.max_j : job.C;
+            int st = 0;
+            if (!tl) {
+                // state in which the arc match closes: first closed state that explains D (aligner.cc:1019-1025, :1065-1075)
+                const DevArcMatch x = am[job.am];
+                const int add = nolp ? x.score + am[x.inner].score : x.score;
+                st = -1;
+                for (int k = 0; k < 4; k++) if (dval[x.spos] == B(k, i, j) + add) { st = k; break; }
+                if (st < 0) { tl = false; have = sp > 0; if (have) { sp--; job = stack[sp]; } continue; }
+            }
+            for (;;) {
+                const int mij = B(st, i, j);
+                if (tl && P.sequ_local && mij == 0) break;
+                if (i <= al) {
+                    if (st == 0 || st == 4 || st == 1)
+                        if (!(tl && (P.sequ_local || P.fe_left1))) for (int k = bl + 1 + lane; k <= j; k += 32) edges[al + k] = (al << 2) | LB_EDGE_INS;
+                    break;
+                }
+                if (j <= bl) {
+                    if (st == 0 || st == 5 || st == 2)
+                        if (!(tl && (P.sequ_local || P.fe_left2))) for (int k = al + 1 + lane; k <= i; k += 32) edges[k + bl] = (k << 2) | LB_EDGE_DEL;
+                    break;
+                }
+                // ---- open states and exclusion transitions (aligner.cc:1289-1342)
+                bool noex = false, dead = false;
+                switch (st) {
+                    case 0: noex = true; break;
+                    case 4: if (mij == Bv(4, i - 1, j)) i--; else if (mij == B(0, i, j)) st = 0; else dead = true; break;
+                    case 5: if (mij == Bv(5, i, j - 1)) j--; else if (mij == B(0, i, j)) st = 0; else dead = true; break;
+                    case 2: if (mij == B(5, i, j) + ex) st = 5; else noex = true; break;
+                    case 6: if (mij == Bv(6, i - 1, j)) i--; else if (mij == B(2, i, j)) st = 2; else dead = true; break;
+                    case 1: if (mij == B(4, i, j) + ex) st = 4; else noex = true; break;
+                    case 7: if (mij == Bv(7, i, j - 1)) j--; else if (mij == B(1, i, j)) st = 1; else dead = true; break;
+                    default: if (mij == B(6, i, j) + ex) st = 6; else if (mij == B(7, i, j) + ex) st = 7; else noex = true; break;
+                }
+                if (dead) break;
+                if (!noex) continue;
+                // ---- trace_noex in closed state st (aligner.cc:1082-1229)
+                const bool vdiag = valid(i - 1, j - 1);
+                if (vdiag && mij == B(st, i - 1, j - 1) + P.sigma8[ca[i] * LB_NCODES + cb[j]]) { emit(i, j, LB_EDGE_MATCH); i--; j--; continue; }
+                bool moved = false;
+                if (P.open == 0) {
+                    if (valid(i - 1, j) && mij == B(st, i - 1, j) + P.gap) { emit(i, j, LB_EDGE_DEL); i--; moved = true; }
+                    else if (valid(i, j - 1) && mij == B(st, i, j - 1) + P.gap) { emit(i, j, LB_EDGE_INS); j--; moved = true; }
+                } else {
+                    int cost = P.open;
+                    for (int k = 1; i >= al + k; k++) {
+                        if (!valid(i - k, j)) break;
+                        cost += P.gap;
+                        if (mij == B(st, i - k, j) + cost) {
+                            for (int l = lane; l < k; l += 32) edges[(i - l) + j] = ((i - l) << 2) | LB_EDGE_DEL;
+                            i -= k; moved = true;
+                            break;
+                        }
+                    }
+                    if (!moved) {
+                        cost = P.open;
+                        for (int k = 1; j >= bl + k; k++) {
+                            if (!valid(i, j - k)) break;
+                            cost += P.gap;
+                            if (mij == B(st, i, j - k) + cost) {
+                                for (int l = lane; l < k; l += 32) edges[i + (j - l)] = (i << 2) | LB_EDGE_INS;
+                                j -= k; moved = true;
+                                break;
+                            }
+                        }
+                    }
+                }
+                if (moved) continue;
+                if (!vdiag) break;
+                const int e0 = sptr[i + j], e1 = sptr[i + j + 1];
+                int found = -1;
+                for (int base = e0; base < e1 && found < 0; base += 32) {
+                    const int e = base + lane;
+                    bool hit = false;
+                    if (e < e1) {
+                        const DevEntry en = ent[e];
+                        const int p = (int)(en.x & 0xfff), q = (int)(en.x >> 12);
+                        if ((int)(en.y & 0xfff) == i && p >= al && q >= bl) hit = (mij == B(st, p, q) + dval[e]);
+                    }
+                    const unsigned bm = __ballot_sync(0xffffffffu, hit);
+                    if (bm) found = base + __ffs(bm) - 1;
+                }
+                if (found < 0) { if (lane == 0) atomicExch(c.error_flag, 4); break; }
+                const DevEntry en = ent[found];
+                const int xl = (int)(en.x & 0xfff) + 1, yl = (int)(en.x >> 12) + 1;
+                if (lane == 0) { strA[xl] = '('; strA[i] = ')'; strB[yl] = '('; strB[j] = ')'; }
+                emit(xl, yl, LB_EDGE_MATCH);
+                emit(i, j, LB_EDGE_MATCH);
+                int cur = (int)lpos[found];
+                if (!nolp) {
+                    if (lane == 0) { TraceJob nj; nj.al = (short)xl; nj.bl = (short)yl; nj.R = (short)(i - 1); nj.C = (short)(j - 1); nj.am = cur; stack[sp] = nj; }
+                    sp++;
+                } else {
+                    for (;;) {
+                        const DevArcMatch x = am[cur];
+                        const DevArcMatch in = am[x.inner];
+                        const int ial = in.ends_a & 0xfff, iar = in.ends_a >> 12, ibl = in.ends_b & 0xfff, ibr = in.ends_b >> 12;
+                        if (lane == 0) { strA[ial] = '('; strA[iar] = ')'; strB[ibl] = '('; strB[ibr] = ')'; }
+                        emit(ial, ibl, LB_EDGE_MATCH);
+                        emit(iar, ibr, LB_EDGE_MATCH);
+                        if (dval[x.spos] == dval[in.spos] + x.score) { cur = x.inner; continue; }
+                        if (lane == 0) { TraceJob nj; nj.al = (short)ial; nj.bl = (short)ibl; nj.R = (short)(iar - 1); nj.C = (short)(ibr - 1); nj.am = cur; stack[sp] = nj; }
                         sp++;
                         break;
                     }
@@ -861,8 +1036,14 @@ void launch_dfill(const DevCtx &c, int ncmax, bool generic_borders, int grid, in
 #undef CALL
 }
 void launch_dfill_sl(const DevCtx &c, int grid, int smem_bytes, int q, cudaStream_t st) { dfill_sl_kernel<<<grid, 32, smem_bytes, st>>>(c, q); }
+void launch_trace_sl(const DevCtx &c, int grid, int smem_bytes, int pair_begin, int pair_end, int *cursor, cudaStream_t st) {
+    if (c.params.sequ_local) trace_sl_kernel<true><<<grid, 32, smem_bytes, st>>>(c, pair_begin, pair_end, cursor);
+    else trace_sl_kernel<false><<<grid, 32, smem_bytes, st>>>(c, pair_begin, pair_end, cursor);
+}
 cudaError_t configure_sl(int smem_bytes, int *ctas_per_sm) {
     cudaError_t e = cudaFuncSetAttribute(dfill_sl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(trace_sl_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(trace_sl_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, dfill_sl_kernel, 32, smem_bytes);
     return e;
 }

@@ -24,6 +24,7 @@ void launch_trace(const DevCtx &c, int ncmax, bool generic_borders, int grid, in
 cudaError_t configure_kernels(int ncmax, int smem_bytes, int *dfill_ctas_per_sm);
 void launch_dfill_sl(const DevCtx &c, int grid, int smem_bytes, int q, cudaStream_t st);
 cudaError_t configure_sl(int smem_bytes, int *ctas_per_sm);
+void launch_trace_sl(const DevCtx &c, int grid, int smem_bytes, int pair_begin, int pair_end, int *cursor, cudaStream_t st);
 }  // namespace lb200
 
 using namespace lb200;
@@ -510,7 +511,6 @@ int lb200_run(lb200_ctx *c, int flags) {
     lb200_ctx::Resident &R = c->res;
     cudaStream_t st = c->stream;
     const bool do_trace = (flags & LB200_RUN_TRACE) != 0;
-    if (do_trace && c->params.struct_local) return fail(c, LB200_ERR_UNSUPPORTED, "traceback of --struct-local alignments is not implemented on the B200 path yet");
     if (do_trace) {
         CUDA_TRY(c, c->d_tr_edges.ensure((size_t)R.sptr_total * 4));
         CUDA_TRY(c, c->d_tr_str.ensure((size_t)R.sptr_total));
@@ -535,7 +535,8 @@ int lb200_run(lb200_ctx *c, int flags) {
     launch_toplevel(dc, R.nc_inst, std::min(R.grid_cap, P), R.smem_bytes, 0, P, (int *)c->d_cursor.p + 4098, st);
     launches++;
     if (do_trace) {
-        launch_trace(dc, R.nc_inst, c->params.indel_opening > 0, std::min(R.grid_cap, P), R.smem_bytes, 0, P, (int *)c->d_cursor.p + 4099, st);
+        if (c->params.struct_local) launch_trace_sl(dc, std::min(R.grid_cap, P), R.smem_bytes, 0, P, (int *)c->d_cursor.p + 4099, st);
+        else launch_trace(dc, R.nc_inst, c->params.indel_opening > 0, std::min(R.grid_cap, P), R.smem_bytes, 0, P, (int *)c->d_cursor.p + 4099, st);
         launches++;
     }
     CUDA_TRY(c, cudaGetLastError());

@@ -18,6 +18,10 @@ FLAGSETS = [
     {"no-ribosum": True, "indel-opening": 0, "tau": 100},
     {"indel-opening": 40, "indel": -120},
     {"struct-weight": 400, "tau": 0},
+    {"struct-local": True},
+    {"struct-local": True, "exclusion": -100, "noLP": True},
+    {"struct-local": True, "sequ-local": True, "exclusion": -250},
+    {"struct-local": True, "exclusion": -1000, "free-endgaps": "++++"},
 ]
 
 
