@@ -128,6 +128,10 @@ int64_t lb200_last_dfill_launches(const lb200_ctx *ctx);
 /* number of kernel launches of the last lb200_run */
 int64_t lb200_last_launches(const lb200_ctx *ctx);
 
+/* Band derivation of the last lb200_prepare / lb200_upload: pairs whose probability envelope was decided on the GPU (FP64
+ * screening) and pairs that were (re)computed on the host in long double because a cell was too close to the threshold. */
+int lb200_envelope_stats(const lb200_ctx *ctx, int64_t *device_pairs, int64_t *host_pairs);
+
 int lb200_pair_score(const lb200_ctx *ctx, int pair, int64_t *score);
 int lb200_get_scores(const lb200_ctx *ctx, int64_t *scores, int n);
 int lb200_pair_get_info(const lb200_ctx *ctx, int pair, lb200_pair_info *info);

@@ -38,7 +38,7 @@ class PairInfo(C.Structure):
 EXPORTS = [
     "lb200_default_params", "lb200_ctx_create", "lb200_ctx_destroy", "lb200_last_error", "lb200_set_params",
     "lb200_seq_add_pp", "lb200_seq_add", "lb200_seq_length", "lb200_seq_get", "lb200_pair_add", "lb200_num_pairs", "lb200_clear_pairs",
-    "lb200_prepare", "lb200_upload", "lb200_run", "lb200_last_kernel_ms", "lb200_last_h2d_bytes", "lb200_last_d2h_bytes", "lb200_last_dfill_ms", "lb200_last_dfill_launches", "lb200_last_launches", "lb200_pair_score", "lb200_get_scores",
+    "lb200_prepare", "lb200_upload", "lb200_run", "lb200_last_kernel_ms", "lb200_last_h2d_bytes", "lb200_last_d2h_bytes", "lb200_last_dfill_ms", "lb200_last_dfill_launches", "lb200_last_launches", "lb200_envelope_stats", "lb200_pair_score", "lb200_get_scores",
     "lb200_pair_get_info", "lb200_pair_band", "lb200_pair_arcmatches", "lb200_pair_alignment",
 ]
 
@@ -82,6 +82,7 @@ def load():
     lib.lb200_last_kernel_ms.restype = C.c_double
     lib.lb200_last_launches.argtypes = [vp]
     lib.lb200_last_launches.restype = C.c_int64
+    lib.lb200_envelope_stats.argtypes = [vp, i64p, i64p]
     lib.lb200_pair_score.argtypes = [vp, C.c_int, i64p]
     lib.lb200_get_scores.argtypes = [vp, i64p, C.c_int]
     lib.lb200_pair_get_info.argtypes = [vp, C.c_int, C.POINTER(PairInfo)]
@@ -203,6 +204,12 @@ class Context:
     @property
     def launches(self) -> int:
         return self.lib.lb200_last_launches(self.h)
+
+    def envelope_stats(self):
+        """(pairs whose band was decided on the GPU, pairs recomputed on the host) of the last prepare/upload."""
+        a, b = C.c_int64(), C.c_int64()
+        self._chk(self.lib.lb200_envelope_stats(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def num_pairs(self) -> int:
         return self._chk(self.lib.lb200_num_pairs(self.h))

@@ -1,0 +1,143 @@
+// Probability envelope of the band on the device.
+//
+// Reference: PFGotoh / PFTraceProbs (src/LocARNA/edge_probs.icc:7-268), StralScore::sigma (stral_score.cc:29-60),
+// TraceController::restrict_by_trace_probabilities (trace_controller.cc:565-597), call site main_helper.icc:371-426.
+// `locarna` evaluates this sequence-only partition function in 80-bit long double (locarna.cc:384-391); the GPU has no
+// such type. The kernel evaluates the same recursions, in the same operation order, in FP64 and *screens*: rows get
+// their new [min_col, max_col] from the FP64 probabilities, and a pair is flagged "uncertain" when any cell lies within a
+// relative margin of 1e-9 of the threshold (FP64 error of these all-positive sums is < 1e-12) or when the partition
+// function leaves the FP64 range. Flagged pairs are recomputed on the host in long double (host_model.cc), so the bands
+// are always exactly the reference's; nothing is approximated silently.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "envelope.h"
+
+namespace lb200 {
+
+struct EnvSeq {
+    const uint8_t *code; const double *up, *down; int len; bool rev;
+    __device__ int c(int i) const { return code[rev ? len + 1 - i : i]; }
+    __device__ double u(int i) const { return rev ? down[len + 1 - i] : up[i]; }   // reversed: up/down swap (stral_score.cc:82-98)
+    __device__ double d(int i) const { return rev ? up[len + 1 - i] : down[i]; }
+};
+
+// one pass of pf_gotoh (edge_probs.icc:76-162) over the band [lo, hi] by anti-diagonals; matrices are (n+1) x (m+1) row major
+__device__ void gotoh_pass(double *zM, double *zA, double *zB, const int *lo, const int *hi, bool band_rev, int n, int m, const EnvSeq &A,
+                           const EnvSeq &B, const EnvCtx &e, bool free_left1, bool free_left2) {
+    const int W = m + 1;
+    const double g_open = exp(e.open / e.temp), g_ext = exp(e.ext / e.temp);
+    auto LO = [&](int i) { return band_rev ? m - hi[n - i] : lo[i]; };   // trace_controller.cc:319-338
+    auto HI = [&](int i) { return band_rev ? m - lo[n - i] : hi[i]; };
+    auto valid = [&](int i, int j) { return LO(i) <= j && j <= HI(i); };
+    for (int k = threadIdx.x; k < (n + 1) * W; k += blockDim.x) { zM[k] = 0; zA[k] = 0; zB[k] = 0; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (valid(0, 0)) zM[0] = e.local ? 0 : 1;
+        if (n > 0 && valid(1, 0)) zA[1 * W] = g_open * g_ext;
+        if (m > 0 && valid(0, 1)) zB[1] = g_open * g_ext;
+        for (int i = 2; i <= n; i++) { if (LO(i) > 0) break; zA[i * W] = zA[(i - 1) * W] * g_ext; }
+        for (int j = max(LO(0), 2); j <= min(HI(0), m); j++) zB[j] = zB[j - 1] * g_ext;
+        if (free_left2) for (int i = 1; i <= n; i++) zA[i * W] += 1;
+        if (free_left1) for (int j = 1; j <= m; j++) zB[j] += 1;
+    }
+    __syncthreads();
+    for (int d = 2; d <= n + m; d++) {
+        for (int i = max(1, d - m) + threadIdx.x; i <= min(n, d - 1); i += blockDim.x) {
+            const int j = d - i;
+            if (j >= max(LO(i), 1) && j <= min(HI(i), m)) {
+                // StralScore::sigma
+                double seq_score = 0;
+                const int a = A.c(i), b = B.c(j);
+                if (a < 4 && b < 4) seq_score = e.bm[a * 4 + b];
+                const double s = e.sw * (sqrt(A.d(i) * B.d(j)) + sqrt(A.u(i) * B.u(j))) + seq_score;
+                const double mt = exp(s / e.temp);
+                const int p = i * W + j, pd = p - W - 1, pu = p - W, pl = p - 1;
+                zM[p] = zM[pd] * mt + zA[pd] * mt + zB[pd] * mt + (e.local ? mt : 0);
+                zA[p] = zA[pu] * g_ext + zM[pu] * g_open * g_ext + zB[pu] * g_open * g_ext;
+                zB[p] = zB[pl] * g_ext + zM[pl] * g_open * g_ext + zA[pl] * g_open * g_ext;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) envelope_kernel(EnvCtx e, int n_pairs, int *cursor) {
+    __shared__ int s_pair;
+    __shared__ double s_red[256];
+    __shared__ int s_flag;
+    double *base = e.scratch + (size_t)blockIdx.x * e.scratch_doubles;
+    for (;;) {
+        if (threadIdx.x == 0) s_pair = atomicAdd(cursor, 1);
+        __syncthreads();
+        const int pk = s_pair;
+        __syncthreads();
+        if (pk >= n_pairs) break;
+        const EnvPair pr = e.pairs[pk];
+        const int n = pr.lenA, m = pr.lenB, W = m + 1;
+        const size_t sz = (size_t)(n + 1) * W;
+        double *zM = base, *zA = base + sz, *zB = base + 2 * sz, *zMr = base + 3 * sz, *zAr = base + 4 * sz, *zBr = base + 5 * sz;
+        int *lo = e.band_lo + pr.band, *hi = e.band_hi + pr.band;
+        EnvSeq A, B;
+        A.code = e.codes + pr.codesA; A.up = e.p_up + pr.probA; A.down = e.p_down + pr.probA; A.len = n; A.rev = false;
+        B.code = e.codes + pr.codesB; B.up = e.p_up + pr.probB; B.down = e.p_down + pr.probB; B.len = m; B.rev = false;
+        gotoh_pass(zM, zA, zB, lo, hi, false, n, m, A, B, e, e.fe_left1, e.fe_left2);
+        A.rev = true; B.rev = true;
+        gotoh_pass(zMr, zAr, zBr, lo, hi, true, n, m, A, B, e, e.fe_right1, e.fe_right2);   // FreeEndgaps::reverse (free_endgaps.hh:74-79)
+        // partition function z (edge_probs.icc:34-59)
+        double z;
+        if (e.local) {
+            double acc = 0;  // the reference sums row major starting from 1; the order only matters below the screening margin
+            for (size_t k = threadIdx.x; k < sz; k += blockDim.x) acc += zM[k];
+            s_red[threadIdx.x] = acc;
+            __syncthreads();
+            for (int o = 128; o; o >>= 1) { if ((int)threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o]; __syncthreads(); }
+            z = 1 + s_red[0];
+        } else {
+            z = zM[sz - 1] + zA[sz - 1] + zB[sz - 1];
+            if (e.fe_left2) for (int i = 0; i <= n; i++) z += zA[i * W + m];
+            if (e.fe_left1) for (int j = 0; j <= m; j++) z += zB[n * W + j];
+        }
+        if (threadIdx.x == 0) s_flag = (!isfinite(z) || z <= 0) ? 1 : 0;
+        __syncthreads();
+        // trace probabilities and the new row ranges (edge_probs.icc:243-264, trace_controller.cc:567-583)
+        const double locality_add = e.local ? 1 : 0, g_open = exp(e.open / e.temp);
+        const double thr = e.min_prob, margin = 1e-9 * e.min_prob;
+        int *nlo = e.out_lo + pr.band, *nhi = e.out_hi + pr.band;
+        for (int i = threadIdx.x; i <= n; i += blockDim.x) {
+            int new_min = hi[i], new_max = lo[i];
+            bool unsure = false;
+            for (int j = max(lo[i], 0); j <= min(hi[i], m); j++) {
+                const size_t p = (size_t)i * W + j, r = (size_t)(n - i) * W + (m - j);
+                const double zij = zM[p] * (zMr[r] + zAr[r] + zBr[r] + locality_add) + zA[p] * (zMr[r] + zAr[r] / g_open + zBr[r]) +
+                                   zB[p] * (zMr[r] + zAr[r] + zBr[r] / g_open);
+                const double prob = zij / z;
+                if (!(fabs(prob - thr) > margin)) unsure = true;  // also catches NaN
+                if (prob >= thr) { new_min = min(new_min, j); new_max = max(new_max, j); }
+            }
+            nlo[i] = max(lo[i], new_min);
+            nhi[i] = min(hi[i], new_max);
+            if (unsure) s_flag = 1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            // monotone closure (trace_controller.cc:585-596)
+            int run = 0;
+            for (int i = 0; i <= n; i++) { nhi[i] = max(nhi[i], run); run = nhi[i]; }
+            run = nhi[n];
+            for (int i = n; i >= 0; i--) { nlo[i] = min(nlo[i], run); run = nlo[i]; }
+            e.out_flag[pk] = s_flag;
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_envelope(const EnvCtx &e, int n_pairs, int grid, int *cursor, cudaStream_t st) {
+    cudaError_t err = cudaMemsetAsync(cursor, 0, sizeof(int), st);
+    if (err != cudaSuccess) return err;
+    envelope_kernel<<<grid, 256, 0, st>>>(e, n_pairs, cursor);
+    return cudaGetLastError();
+}
+
+}  // namespace lb200

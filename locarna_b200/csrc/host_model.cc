@@ -334,6 +334,12 @@ void envelope_impl(Band &band, const Sequence &A, const Sequence &B, const Param
 
 }  // namespace
 
+void envelope_score_params(const Params &p, double bm[16], double *sw, double *open, double *ext, double *temp) {
+    for (int a = 0; a < 4; a++)
+        for (int b = 0; b < 4; b++) bm[a * 4 + b] = p.use_ribosum ? RIBOSUM85_60_BM[a * 4 + b] : (a == b ? (double)p.match : (double)p.mismatch);
+    *sw = p.struct_weight / 100.0; *open = p.indel_opening / 100.0; *ext = p.indel / 100.0; *temp = p.temperature_alipf / 100.0;
+}
+
 void restrict_band_by_envelope(Band &band, const Sequence &A, const Sequence &B, const Params &p) {
     if (!(p.min_trace_probability > 0.0)) return;  // main_helper.icc:416
     if (p.pf_double) envelope_impl<double>(band, A, B, p);

@@ -67,6 +67,8 @@ int arcmatch_score(const ScoreTables &t, const Params &p, const Sequence &A, con
 Band make_band(int lenA, int lenB, int max_diff);
 // probability envelope (PFGotoh in 80-bit or 64-bit floating point on the host)
 void restrict_band_by_envelope(Band &band, const Sequence &A, const Sequence &B, const Params &p);
+// score parameters of the envelope partition function as the reference passes them (main_helper.icc:389-400)
+void envelope_score_params(const Params &p, double bm[16], double *sw, double *open, double *ext, double *temp);
 
 // Per-pair problem in device layout, built on the host (L-order / S-order, see dev_types.h)
 struct PairProblem {

@@ -14,6 +14,7 @@
 
 #include "../../include/locarna_b200.h"
 #include "builder.h"
+#include "envelope.h"
 #include "dev_ctx.h"
 #include "host_model.h"
 
@@ -94,12 +95,17 @@ struct lb200_ctx {
     size_t seqs_uploaded = 0;  // sequences whose arrays are on the device
     std::vector<int> seq_codes_off, seq_arcs_off, seq_lptr_off;
     DevBuf d_arc_left, d_arc_right, d_arc_weight, d_lptr, d_lcount, d_am_seq, d_cell_rev, d_cell_start, d_skeys, d_skeys2, d_svals, d_svals2,
-        d_tasks_unsorted, d_tkeys, d_tkeys2, d_tvals, d_tvals2, d_ntasks, d_qstart, d_stats, d_tmp, d_tr_edges, d_tr_str, d_tr_stack;
+        d_tasks_unsorted, d_tkeys, d_tkeys2, d_tvals, d_tvals2, d_ntasks, d_qstart, d_stats, d_tmp, d_tr_edges, d_tr_str, d_tr_stack,
+        d_pup, d_pdown, d_env_pairs, d_env_lo, d_env_hi, d_env_olo, d_env_ohi, d_env_flag, d_env_scratch;
+    std::vector<int> seq_prob_off;
+    int64_t env_device_pairs = 0, env_host_pairs = 0;  // statistics of the last band derivation
+    int env_mode = 1;  // 1: device screening + host re-check, 0: host only (LB200_ENVELOPE=host)
     DevBuf d_pairs, d_codes, d_band_lo, d_band_hi, d_sptr, d_ent, d_dval, d_am, d_tasks, d_top, d_scratch, d_cursor, d_flag;
     ~lb200_ctx() {
         DevBuf *all[] = {&d_pairs, &d_codes, &d_band_lo, &d_band_hi, &d_sptr, &d_ent, &d_dval, &d_am, &d_tasks, &d_top, &d_scratch, &d_cursor, &d_flag,
                          &d_arc_left, &d_arc_right, &d_arc_weight, &d_lptr, &d_lcount, &d_am_seq, &d_cell_rev, &d_cell_start, &d_skeys, &d_skeys2,
-                         &d_svals, &d_svals2, &d_tasks_unsorted, &d_tkeys, &d_tkeys2, &d_tvals, &d_tvals2, &d_ntasks, &d_qstart, &d_stats, &d_tmp, &d_tr_edges, &d_tr_str, &d_tr_stack};
+                         &d_svals, &d_svals2, &d_tasks_unsorted, &d_tkeys, &d_tkeys2, &d_tvals, &d_tvals2, &d_ntasks, &d_qstart, &d_stats, &d_tmp, &d_tr_edges, &d_tr_str, &d_tr_stack,
+                         &d_pup, &d_pdown, &d_env_pairs, &d_env_lo, &d_env_hi, &d_env_olo, &d_env_ohi, &d_env_flag, &d_env_scratch};
         for (auto *b : all) b->release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -185,6 +191,7 @@ int lb200_ctx_create(int device, lb200_ctx **out) {
     c->params = to_params(dp);
     make_score_tables(c->params, c->tables);
     if (const char *s = getenv("LB200_HOST_THREADS")) c->host_threads = atoi(s);
+    if (const char *s = getenv("LB200_ENVELOPE")) c->env_mode = strcmp(s, "host") == 0 ? 0 : 1;
     *out = c;
     return LB200_OK;
 }
@@ -281,24 +288,126 @@ static cudaError_t upload(DevBuf &b, const std::vector<T> &v, cudaStream_t st) {
 
 extern "C" {
 
-// bands of all pairs that do not have one yet (host, all cores)
-static void derive_bands(lb200_ctx *c) {
+// sequences -> device arrays (codes, arcs in index order, arc weights, left-end index)
+static int upload_sequences(lb200_ctx *c) {
+    if (c->seqs_uploaded == c->seqs.size()) return LB200_OK;
+    std::vector<uint8_t> codes;
+    std::vector<int> al, ar, aw, lptr, lcount;
+    std::vector<double> pup, pdown;
+    c->seq_codes_off.clear(); c->seq_arcs_off.clear(); c->seq_lptr_off.clear(); c->seq_prob_off.clear();
+    for (const Sequence &s : c->seqs) {
+        c->seq_codes_off.push_back((int)codes.size());
+        codes.insert(codes.end(), s.codes.begin(), s.codes.end());
+        c->seq_arcs_off.push_back((int)al.size());
+        const std::vector<int> w = arc_weights(s, c->params);
+        for (size_t k = 0; k < s.arcs.size(); k++) { al.push_back(s.arcs[k].left); ar.push_back(s.arcs[k].right); aw.push_back(w[k]); }
+        c->seq_lptr_off.push_back((int)lptr.size());
+        lptr.insert(lptr.end(), s.lptr.begin(), s.lptr.end());
+        lcount.insert(lcount.end(), s.lcount.begin(), s.lcount.end());
+        c->seq_prob_off.push_back((int)pup.size());
+        pup.insert(pup.end(), s.p_up.begin(), s.p_up.end());
+        pdown.insert(pdown.end(), s.p_down.begin(), s.p_down.end());
+    }
+    cudaStream_t st = c->stream;
+    std::vector<int> amseq(c->tables.am_seq, c->tables.am_seq + 256);
+    CUDA_TRY(c, upload(c->d_codes, codes, st));
+    CUDA_TRY(c, upload(c->d_arc_left, al, st));
+    CUDA_TRY(c, upload(c->d_arc_right, ar, st));
+    CUDA_TRY(c, upload(c->d_arc_weight, aw, st));
+    CUDA_TRY(c, upload(c->d_lptr, lptr, st));
+    CUDA_TRY(c, upload(c->d_lcount, lcount, st));
+    CUDA_TRY(c, upload(c->d_am_seq, amseq, st));
+    CUDA_TRY(c, upload(c->d_pup, pup, st));
+    CUDA_TRY(c, upload(c->d_pdown, pdown, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    c->last_h2d_bytes += (int64_t)(codes.size() + (al.size() * 3 + lptr.size() * 2 + 256) * 4);
+    c->seqs_uploaded = c->seqs.size();
+    return LB200_OK;
+}
+
+// Bands of all pairs that do not have one yet. Device contexts screen the probability envelope on the GPU in FP64
+// (envelope.cu) and recompute only the flagged pairs on the host in long double; host-only contexts (and
+// LB200_ENVELOPE=host) compute everything on the host. Either way the bands equal the reference's.
+static int derive_bands(lb200_ctx *c) {
     const int P = (int)c->pairs.size();
-    parallel_for(P, c->host_threads, [&](int k) {
+    std::vector<int> todo;
+    for (int k = 0; k < P; k++) {
         PairRec &r = c->pairs[k];
-        if (r.banded) return;
-        const Sequence &A = c->seqs[r.seqA], &B = c->seqs[r.seqB];
-        if (r.band.lo.empty()) {
+        if (r.banded) continue;
+        if (!r.band.lo.empty()) { r.banded = true; continue; }
+        todo.push_back(k);
+    }
+    c->env_device_pairs = 0; c->env_host_pairs = 0;
+    if (todo.empty()) return LB200_OK;
+    const bool envelope = c->params.min_trace_probability > 0.0;
+    std::vector<char> on_host(todo.size(), 1);
+    if (envelope && c->device != LB200_DEVICE_NONE && c->env_mode == 1) {
+        { const int rc = upload_sequences(c); if (rc != LB200_OK) return rc; }
+        cudaStream_t st = c->stream;
+        std::vector<EnvPair> ep(todo.size());
+        std::vector<int> lo, hi;
+        size_t max_cells = 1;
+        for (size_t t = 0; t < todo.size(); t++) {
+            PairRec &r = c->pairs[todo[t]];
+            const Sequence &A = c->seqs[r.seqA], &B = c->seqs[r.seqB];
             r.band = make_band(A.len, B.len, c->params.max_diff);
-            restrict_band_by_envelope(r.band, A, B, c->params);
+            EnvPair &e = ep[t];
+            e.lenA = A.len; e.lenB = B.len; e.codesA = c->seq_codes_off[r.seqA]; e.codesB = c->seq_codes_off[r.seqB];
+            e.probA = c->seq_prob_off[r.seqA]; e.probB = c->seq_prob_off[r.seqB]; e.band = (int)lo.size(); e.pad = 0;
+            lo.insert(lo.end(), r.band.lo.begin(), r.band.lo.end());
+            hi.insert(hi.end(), r.band.hi.begin(), r.band.hi.end());
+            max_cells = std::max(max_cells, (size_t)(A.len + 1) * (B.len + 1));
         }
+        const int grid = (int)std::min<size_t>(todo.size(), (size_t)c->prop.multiProcessorCount * 4);
+        EnvCtx e;
+        memset(&e, 0, sizeof e);
+        CUDA_TRY(c, upload(c->d_env_pairs, ep, st));
+        CUDA_TRY(c, upload(c->d_env_lo, lo, st));
+        CUDA_TRY(c, upload(c->d_env_hi, hi, st));
+        CUDA_TRY(c, c->d_env_olo.ensure(lo.size() * 4));
+        CUDA_TRY(c, c->d_env_ohi.ensure(lo.size() * 4));
+        CUDA_TRY(c, c->d_env_flag.ensure(todo.size() * 4 + 16));
+        CUDA_TRY(c, c->d_env_scratch.ensure((size_t)grid * 6 * max_cells * sizeof(double)));
+        CUDA_TRY(c, c->d_cursor.ensure(4100 * 4));
+        e.pairs = (const EnvPair *)c->d_env_pairs.p; e.codes = (const uint8_t *)c->d_codes.p;
+        e.p_up = (const double *)c->d_pup.p; e.p_down = (const double *)c->d_pdown.p;
+        e.band_lo = (int *)c->d_env_lo.p; e.band_hi = (int *)c->d_env_hi.p; e.out_lo = (int *)c->d_env_olo.p; e.out_hi = (int *)c->d_env_ohi.p;
+        e.out_flag = (int *)c->d_env_flag.p; e.scratch = (double *)c->d_env_scratch.p; e.scratch_doubles = 6 * max_cells;
+        envelope_score_params(c->params, e.bm, &e.sw, &e.open, &e.ext, &e.temp);
+        e.min_prob = c->params.min_trace_probability; e.local = c->params.sequ_local;
+        e.fe_left1 = c->params.fe_left1; e.fe_right1 = c->params.fe_right1; e.fe_left2 = c->params.fe_left2; e.fe_right2 = c->params.fe_right2;
+        CUDA_TRY(c, launch_envelope(e, (int)todo.size(), grid, (int *)c->d_cursor.p, st));
+        std::vector<int> olo(lo.size()), ohi(lo.size()), flag(todo.size());
+        CUDA_TRY(c, cudaMemcpyAsync(olo.data(), c->d_env_olo.p, lo.size() * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaMemcpyAsync(ohi.data(), c->d_env_ohi.p, lo.size() * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaMemcpyAsync(flag.data(), c->d_env_flag.p, todo.size() * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));
+        for (size_t t = 0; t < todo.size(); t++) {
+            if (flag[t] != 0) continue;  // uncertain: exact host computation below
+            PairRec &r = c->pairs[todo[t]];
+            std::copy(olo.begin() + ep[t].band, olo.begin() + ep[t].band + ep[t].lenA + 1, r.band.lo.begin());
+            std::copy(ohi.begin() + ep[t].band, ohi.begin() + ep[t].band + ep[t].lenA + 1, r.band.hi.begin());
+            r.banded = true;
+            on_host[t] = 0;
+            c->env_device_pairs++;
+        }
+    }
+    parallel_for((int)todo.size(), c->host_threads, [&](int t) {
+        if (!on_host[t]) return;
+        PairRec &r = c->pairs[todo[t]];
+        const Sequence &A = c->seqs[r.seqA], &B = c->seqs[r.seqB];
+        r.band = make_band(A.len, B.len, c->params.max_diff);
+        restrict_band_by_envelope(r.band, A, B, c->params);
         r.banded = true;
     });
+    for (size_t t = 0; t < todo.size(); t++) c->env_host_pairs += on_host[t] ? 1 : 0;
+    return LB200_OK;
 }
 
 int lb200_prepare(lb200_ctx *c) {
     if (!c) return LB200_ERR_ARG;
-    derive_bands(c);
+    if (c->device != LB200_DEVICE_NONE) CUDA_TRY(c, cudaSetDevice(c->device));
+    { const int rc = derive_bands(c); if (rc != LB200_OK) return rc; }
     if (c->device != LB200_DEVICE_NONE) return LB200_OK;
     // host-only context: mirror of the device builder, for inspection without a GPU
     const int P = (int)c->pairs.size();
@@ -313,37 +422,6 @@ int lb200_prepare(lb200_ctx *c) {
     return LB200_OK;
 }
 
-// sequences -> device arrays (codes, arcs in index order, arc weights, left-end index)
-static int upload_sequences(lb200_ctx *c) {
-    if (c->seqs_uploaded == c->seqs.size()) return LB200_OK;
-    std::vector<uint8_t> codes;
-    std::vector<int> al, ar, aw, lptr, lcount;
-    c->seq_codes_off.clear(); c->seq_arcs_off.clear(); c->seq_lptr_off.clear();
-    for (const Sequence &s : c->seqs) {
-        c->seq_codes_off.push_back((int)codes.size());
-        codes.insert(codes.end(), s.codes.begin(), s.codes.end());
-        c->seq_arcs_off.push_back((int)al.size());
-        const std::vector<int> w = arc_weights(s, c->params);
-        for (size_t k = 0; k < s.arcs.size(); k++) { al.push_back(s.arcs[k].left); ar.push_back(s.arcs[k].right); aw.push_back(w[k]); }
-        c->seq_lptr_off.push_back((int)lptr.size());
-        lptr.insert(lptr.end(), s.lptr.begin(), s.lptr.end());
-        lcount.insert(lcount.end(), s.lcount.begin(), s.lcount.end());
-    }
-    cudaStream_t st = c->stream;
-    std::vector<int> amseq(c->tables.am_seq, c->tables.am_seq + 256);
-    CUDA_TRY(c, upload(c->d_codes, codes, st));
-    CUDA_TRY(c, upload(c->d_arc_left, al, st));
-    CUDA_TRY(c, upload(c->d_arc_right, ar, st));
-    CUDA_TRY(c, upload(c->d_arc_weight, aw, st));
-    CUDA_TRY(c, upload(c->d_lptr, lptr, st));
-    CUDA_TRY(c, upload(c->d_lcount, lcount, st));
-    CUDA_TRY(c, upload(c->d_am_seq, amseq, st));
-    CUDA_TRY(c, cudaStreamSynchronize(st));
-    c->last_h2d_bytes += (int64_t)(codes.size() + (al.size() * 3 + lptr.size() * 2 + 256) * 4);
-    c->seqs_uploaded = c->seqs.size();
-    return LB200_OK;
-}
-
 int lb200_upload(lb200_ctx *c) {
     if (!c) return LB200_ERR_ARG;
     if (c->device == LB200_DEVICE_NONE) return fail(c, LB200_ERR_CUDA, "host-only context: lb200_upload needs a CUDA device (no CPU fallback)");
@@ -352,7 +430,7 @@ int lb200_upload(lb200_ctx *c) {
     c->res.valid = false;
     c->last_h2d_bytes = 0;
     if (P == 0) return LB200_OK;
-    derive_bands(c);
+    { const int rc = derive_bands(c); if (rc != LB200_OK) return rc; }
     { const int rc = upload_sequences(c); if (rc != LB200_OK) return rc; }
     cudaStream_t st = c->stream;
 
@@ -592,6 +670,12 @@ int64_t lb200_last_dfill_launches(const lb200_ctx *c) { return c ? c->last_dfill
 int64_t lb200_last_h2d_bytes(const lb200_ctx *c) { return c ? c->last_h2d_bytes : 0; }
 int64_t lb200_last_d2h_bytes(const lb200_ctx *c) { return c ? c->last_d2h_bytes : 0; }
 int64_t lb200_last_launches(const lb200_ctx *c) { return c ? c->last_launches : 0; }
+int lb200_envelope_stats(const lb200_ctx *c, int64_t *device_pairs, int64_t *host_pairs) {
+    if (!c) return LB200_ERR_ARG;
+    if (device_pairs) *device_pairs = c->env_device_pairs;
+    if (host_pairs) *host_pairs = c->env_host_pairs;
+    return LB200_OK;
+}
 
 int lb200_pair_score(const lb200_ctx *c, int pair, int64_t *score) {
     if (!c || !score || pair < 0 || pair >= (int)c->pairs.size()) return LB200_ERR_ARG;
