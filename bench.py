@@ -274,30 +274,25 @@ def main():
             inf = ctxs[s].info(k)
             cells += inf.cells; terms += inf.terms; am += inf.n_arcmatches; arcs += inf.n_arcsA + inf.n_arcsB; rows += inf.lenA + 1
     my_scores = [ctxs[s].scores() for s in range(n_steps)]
-    # bands of the e2e batches are inputs of the e2e call: derive them now, outside the timed region
-    t0 = time.time()
-    e2e_bands = []
-    for sp in e2e_steps:
-        c = new_ctx(sp)
-        c.prepare()
-        e2e_bands.append([c.band(k) for k in range(len(sp))])
-        c.close()
-    band_s = time.time() - t0
     for c in ctxs:
         c.close()
 
     # ---- e2e leg: host buffers -> scores on the host, everything timed.
     # The job's sequences (512 RNAs: sequence + base pairs) are uploaded once per job before the steps, as a caller
-    # of the all-vs-all stage would do; every step passes its pair list and bands as host buffers through the C ABI
-    # (lb200_clear_pairs, lb200_pair_add, lb200_run = device build + D fill + top level + D2H of the scores).
+    # of the all-vs-all stage would do; every step passes its pair list as host buffers through the C ABI
+    # (lb200_clear_pairs, lb200_pair_add with no band, lb200_run = band derivation (GPU envelope screening + exact host
+    # re-check of uncertain pairs) + device build + D fill + top level + D2H of the scores).
+    env_stats = [0, 0]
     e2e_ctx = capi.Context(local_rank, FLAGS)
     e2e_ids = [e2e_ctx.add_seq(*seqs[s]) for s in range(len(seqs))]
 
     def e2e_step(s):
         e2e_ctx.clear_pairs()
         for k, (a, b) in enumerate(e2e_steps[s]):
-            e2e_ctx.add_pair(e2e_ids[a], e2e_ids[b], e2e_bands[s][k])
+            e2e_ctx.add_pair(e2e_ids[a], e2e_ids[b], None)
         e2e_ctx.run()
+        dev, host = e2e_ctx.envelope_stats()
+        env_stats[0] += dev; env_stats[1] += host
         return e2e_ctx.scores(), e2e_ctx.h2d_bytes, e2e_ctx.d2h_bytes
 
     for s in range(W):
@@ -375,7 +370,7 @@ def main():
             "config": {"workload": "cfg5 mlocarna guide-tree stage, all-vs-all %d x %d nt (%d pairs), step = %d-pair slice per GPU, score only" % (args.seqs, args.len, len(pairs), B),
                        "flags": "--noLP --max-diff-am 30 --struct-weight 200 --min-prob 0.001", "pairs_per_step": B,
                        "l2": "inputs larger than L2: one step batch holds %.0f MB of arc-match / task tables in HBM (L2: 126 MB)" % (resident_bytes / 1e6),
-                       "bands": "probability envelope (80-bit PFGotoh) precomputed on the host: %.1f s for %d pairs on %d cores; input of the e2e call" % (band_s, n_steps * B, cores),
+                       "bands": "derived inside every run (value: before the timed region, e2e: inside it): GPU FP64 envelope screening decided %d pairs, %d re-checked on the host in long double" % (env_stats[0], env_stats[1]),
                        "resident_prep_s": prep_s},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K},

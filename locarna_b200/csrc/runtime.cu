@@ -85,6 +85,7 @@ struct lb200_ctx {
     struct Resident {
         bool valid = false;
         DevCtx dc;
+        int p0 = 0, p1 = 0;  // pair range of the resident chunk
         int nc_inst = 1, smem_bytes = 0, grid_cap = 1, q_lo = 0, q_hi = 0;
         size_t total_am = 0;
         long long sptr_total = 0;
@@ -422,15 +423,11 @@ int lb200_prepare(lb200_ctx *c) {
     return LB200_OK;
 }
 
-int lb200_upload(lb200_ctx *c) {
-    if (!c) return LB200_ERR_ARG;
-    if (c->device == LB200_DEVICE_NONE) return fail(c, LB200_ERR_CUDA, "host-only context: lb200_upload needs a CUDA device (no CPU fallback)");
-    CUDA_TRY(c, cudaSetDevice(c->device));
-    const int P = (int)c->pairs.size();
+// Build the arc-match tables of the pairs [p0, p1) on the device and make them resident.
+static int upload_chunk(lb200_ctx *c, int p0, int p1) {
+    const int P = p1 - p0;
     c->res.valid = false;
-    c->last_h2d_bytes = 0;
-    if (P == 0) return LB200_OK;
-    { const int rc = derive_bands(c); if (rc != LB200_OK) return rc; }
+    if (P <= 0) return LB200_OK;
     { const int rc = upload_sequences(c); if (rc != LB200_OK) return rc; }
     cudaStream_t st = c->stream;
 
@@ -440,7 +437,7 @@ int lb200_upload(lb200_ctx *c) {
     long long total_cells = 0, sptr_total = 0;
     int wd_bound = 1, max_rows = 1, max_cols = 1, max_box_words = 1;
     for (int k = 0; k < P; k++) {
-        PairRec &r = c->pairs[k];
+        PairRec &r = c->pairs[p0 + k];
         DevPair &d = h_pairs[k];
         memset(&d, 0, sizeof d);
         const int n = c->seqs[r.seqA].len, m = c->seqs[r.seqB].len;
@@ -562,7 +559,7 @@ int lb200_upload(lb200_ctx *c) {
     dc.error_flag = (int *)c->d_flag.p;
     CUDA_TRY(c, cudaStreamSynchronize(st));
     for (int k = 0; k < P; k++) {
-        PairRec &r = c->pairs[k];
+        PairRec &r = c->pairs[p0 + k];
         r.am_base = h_pairs[k].am_base; r.K = h_pairs[k].K; r.stats = h_stats[k];
     }
     c->last_h2d_bytes += (int64_t)(h_pairs.size() * sizeof(DevPair) + (h_lo.size() + h_hi.size() + h_rev.size()) * 4);
@@ -574,18 +571,69 @@ int lb200_upload(lb200_ctx *c) {
     R.dc.lpos = (const unsigned *)c->d_svals2.p;
     R.q_lo = 4095 - ((max_rows + max_cols) >> 1); R.q_hi = 4095;
     if (R.q_lo < 0) R.q_lo = 0;
+    R.p0 = p0; R.p1 = p1;
     R.valid = true;
     return LB200_OK;
 }
+
+// Chunks of the pair list that are built and aligned together: bounded by a pair count (LB200_CHUNK_PAIRS, default
+// 4096) and by the number of band cells (32-bit cell offsets on the device).
+static std::vector<int> chunk_plan(lb200_ctx *c) {
+    std::vector<int> cuts(1, 0);
+    const int P = (int)c->pairs.size();
+    int max_pairs = 4096;
+    if (const char *s = getenv("LB200_CHUNK_PAIRS")) max_pairs = std::max(1, atoi(s));
+    long long cells = 0;
+    int count = 0;
+    for (int k = 0; k < P; k++) {
+        const PairRec &r = c->pairs[k];
+        long long pc = 0;
+        for (size_t i = 1; i < r.band.lo.size(); i++) pc += std::max(0, r.band.hi[i] - std::max(r.band.lo[i], 1) + 1);
+        if (count > 0 && (count >= max_pairs || cells + pc > 1500000000LL)) { cuts.push_back(k); cells = 0; count = 0; }
+        cells += pc; count++;
+    }
+    cuts.push_back(P);
+    return cuts;
+}
+
+int lb200_upload(lb200_ctx *c) {
+    if (!c) return LB200_ERR_ARG;
+    if (c->device == LB200_DEVICE_NONE) return fail(c, LB200_ERR_CUDA, "host-only context: lb200_upload needs a CUDA device (no CPU fallback)");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    c->res.valid = false;
+    c->last_h2d_bytes = 0;
+    if (c->pairs.empty()) return LB200_OK;
+    { const int rc = derive_bands(c); if (rc != LB200_OK) return rc; }
+    const std::vector<int> cuts = chunk_plan(c);
+    if (cuts.size() > 2) return LB200_OK;  // several chunks: lb200_run streams them, nothing stays resident
+    return upload_chunk(c, 0, (int)c->pairs.size());
+}
+
+static int run_chunk(lb200_ctx *c, int flags);
 
 int lb200_run(lb200_ctx *c, int flags) {
     if (!c) return LB200_ERR_ARG;
     if (c->device == LB200_DEVICE_NONE) return fail(c, LB200_ERR_CUDA, "host-only context: lb200_run needs a CUDA device (no CPU fallback)");
     CUDA_TRY(c, cudaSetDevice(c->device));
     const int P = (int)c->pairs.size();
-    c->last_kernel_ms = 0; c->last_launches = 0; c->last_d2h_bytes = 0;
+    c->last_kernel_ms = 0; c->last_launches = 0; c->last_d2h_bytes = 0; c->last_dfill_ms = 0; c->last_dfill_launches = 0;
     if (P == 0) return LB200_OK;
-    if (!c->res.valid) { const int rc = lb200_upload(c); if (rc != LB200_OK) return rc; } else c->last_h2d_bytes = 0;
+    if (c->res.valid && c->res.p0 == 0 && c->res.p1 == P) { c->last_h2d_bytes = 0; return run_chunk(c, flags); }
+    c->last_h2d_bytes = 0;
+    { const int rc = derive_bands(c); if (rc != LB200_OK) return rc; }
+    const std::vector<int> cuts = chunk_plan(c);
+    for (size_t k = 0; k + 1 < cuts.size(); k++) {
+        int rc = upload_chunk(c, cuts[k], cuts[k + 1]);
+        if (rc == LB200_OK) rc = run_chunk(c, flags);
+        if (rc != LB200_OK) return rc;
+    }
+    return LB200_OK;
+}
+
+// D fill, top level and (optionally) traceback of the resident chunk
+static int run_chunk(lb200_ctx *c, int flags) {
+    const int P = c->res.p1 - c->res.p0;
+    const int p0 = c->res.p0;
     lb200_ctx::Resident &R = c->res;
     cudaStream_t st = c->stream;
     const bool do_trace = (flags & LB200_RUN_TRACE) != 0;
@@ -636,12 +684,12 @@ int lb200_run(lb200_ctx *c, int flags) {
     float ms = 0, ms_dfill = 0;
     CUDA_TRY(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     CUDA_TRY(c, cudaEventElapsedTime(&ms_dfill, c->ev0, c->ev_mid));
-    c->last_kernel_ms = ms; c->last_launches = launches; c->last_dfill_ms = ms_dfill; c->last_dfill_launches = R.q_hi - R.q_lo + 1;
-    c->last_d2h_bytes = (int64_t)((size_t)P * sizeof(DevTopResult) + 16 + h_edges.size() * 4 + h_str.size());
+    c->last_kernel_ms += ms; c->last_launches += launches; c->last_dfill_ms += ms_dfill; c->last_dfill_launches += R.q_hi - R.q_lo + 1;
+    c->last_d2h_bytes += (int64_t)((size_t)P * sizeof(DevTopResult) + 16 + h_edges.size() * 4 + h_str.size());
     if (h_flag[0] != 0)
         return fail(c, LB200_ERR_UNSUPPORTED, "kernel reported error %d (1: band too wide, 2: box exceeds scratch, 3: trace box failed, 4: traceback dead end)", h_flag[0]);
     for (int k = 0; k < P; k++) {
-        PairRec &r = c->pairs[k];
+        PairRec &r = c->pairs[p0 + k];
         r.neg_inf = h_top[k].score < LB_NEG_LIMIT;
         r.score = r.neg_inf ? 0 : h_top[k].score;
         r.max_i = h_top[k].max_i; r.max_j = h_top[k].max_j;
@@ -721,7 +769,8 @@ int lb200_pair_arcmatches(const lb200_ctx *cc, int pair, int *al, int *ar, int *
         if (D) return fail(c, LB200_ERR_STATE, "no D table on a host-only context");
         am = r.prob.am;
     } else {
-        if (!c->res.valid) return fail(c, LB200_ERR_STATE, "no resident batch: call lb200_upload / lb200_run first");
+        if (!c->res.valid || pair < c->res.p0 || pair >= c->res.p1)
+            return fail(c, LB200_ERR_STATE, "the arc-match tables of this pair are not resident (call lb200_upload / lb200_run; large batches are streamed in chunks)");
         am.resize(r.K); dvals.resize(r.K);
         if (r.K) {
             CUDA_TRY(c, cudaMemcpy(am.data(), (const DevArcMatch *)c->d_am.p + r.am_base, (size_t)r.K * sizeof(DevArcMatch), cudaMemcpyDeviceToHost));

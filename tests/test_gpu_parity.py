@@ -73,3 +73,17 @@ def test_batch_order_independent(synth_dir):
     assert c1.scores() == list(reversed(c2.scores()))
     for k, (a, b) in enumerate(pairs):
         assert c1.scores()[k] == O.port_align(a, b, flags, do_trace=False)["score"]
+
+
+def test_chunked_batches_equal_single_batch(synth_dir, monkeypatch):
+    """Large batches are streamed in chunks (LB200_CHUNK_PAIRS): same scores and alignments as one batch."""
+    fam = synth_dir["cfg3"]
+    pairs = [(fam[i], fam[j]) for i in range(6) for j in range(i)]
+    flags = {"noLP": True, "max-diff-am": 30}
+    c1 = gpu_align(pairs, flags, capi.RUN_TRACE)
+    monkeypatch.setenv("LB200_CHUNK_PAIRS", "4")
+    c2 = gpu_align(pairs, flags, capi.RUN_TRACE)
+    assert c1.scores() == c2.scores()
+    for k in range(len(pairs)):
+        assert c1.alignment(k) == c2.alignment(k)
+        assert c1.info(k).cells == c2.info(k).cells
