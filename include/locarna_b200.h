@@ -25,6 +25,7 @@
 #ifndef LOCARNA_B200_H
 #define LOCARNA_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -143,6 +144,11 @@ int lb200_pair_arcmatches(const lb200_ctx *ctx, int pair, int *al, int *ar, int 
 /* Alignment edges in order (position or -1 for a gap), and per-position structure strings
  * (lenA+1 / lenB+1 bytes incl. NUL) as in Alignment (alignment.cc:81-118). edges arrays hold n_edges items. */
 int lb200_pair_alignment(const lb200_ctx *ctx, int pair, int *edges_a, int *edges_b, char *str_a, char *str_b);
+
+/* Guide tree of the all-vs-all stage (host): UPGMA over the symmetric score matrix (n x n, row major, diagonal 0) with the tie
+ * rules of lib/perl/MLocarna/Tree.pm:181-262; writes the newick string (without the trailing ';') that mlocarna stores in
+ * results/result.tree (src/Utils/mlocarna:2381-2386). */
+int lb200_upgma_newick(int n, const char *const *names, const int64_t *scores, char *out, size_t out_cap);
 
 #ifdef __cplusplus
 }

@@ -39,7 +39,7 @@ EXPORTS = [
     "lb200_default_params", "lb200_ctx_create", "lb200_ctx_destroy", "lb200_last_error", "lb200_set_params",
     "lb200_seq_add_pp", "lb200_seq_add", "lb200_seq_length", "lb200_seq_get", "lb200_pair_add", "lb200_num_pairs", "lb200_clear_pairs",
     "lb200_prepare", "lb200_upload", "lb200_run", "lb200_last_kernel_ms", "lb200_last_h2d_bytes", "lb200_last_d2h_bytes", "lb200_last_dfill_ms", "lb200_last_dfill_launches", "lb200_last_launches", "lb200_envelope_stats", "lb200_pair_score", "lb200_get_scores",
-    "lb200_pair_get_info", "lb200_pair_band", "lb200_pair_arcmatches", "lb200_pair_alignment",
+    "lb200_pair_get_info", "lb200_pair_band", "lb200_pair_arcmatches", "lb200_pair_alignment", "lb200_upgma_newick",
 ]
 
 _lib = None
@@ -89,6 +89,7 @@ def load():
     lib.lb200_pair_band.argtypes = [vp, C.c_int, ip, ip]
     lib.lb200_pair_arcmatches.argtypes = [vp, C.c_int, ip, ip, ip, ip, ip, i64p]
     lib.lb200_pair_alignment.argtypes = [vp, C.c_int, ip, ip, C.c_char_p, C.c_char_p]
+    lib.lb200_upgma_newick.argtypes = [C.c_int, C.POINTER(C.c_char_p), i64p, C.c_char_p, C.c_size_t]
     _lib = lib
     return lib
 
@@ -249,3 +250,15 @@ class Context:
         sa, sb = C.create_string_buffer(inf.lenA + 2), C.create_string_buffer(inf.lenB + 2)
         self._chk(self.lib.lb200_pair_alignment(self.h, pair, ea, eb, sa, sb))
         return [(ea[k], eb[k]) for k in range(n)], sa.value.decode(), sb.value.decode()
+
+
+def upgma_newick(names, matrix) -> str:
+    """UPGMA guide tree (newick, without ';') of a symmetric score matrix, as mlocarna builds it (host code, no GPU needed)."""
+    n = len(names)
+    arr = (C.c_char_p * n)(*[x.encode() for x in names])
+    flat = (C.c_int64 * (n * n))(*[int(matrix[i][j]) for i in range(n) for j in range(n)])
+    out = C.create_string_buffer(64 * n + 1024)
+    rc = load().lb200_upgma_newick(n, arr, flat, out, len(out))
+    if rc != OK:
+        raise Error("lb200_upgma_newick failed with code %d" % rc)
+    return out.value.decode()

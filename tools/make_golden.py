@@ -85,6 +85,28 @@ def main():
         res = O.ref_batch([(paths[a], paths[b]) for a, b in pl], flags, dump="aln", timing=False)
         out["archaea"] = {"flags": flags, "names": [n for n, _ in names], "pairs": [list(p) for p in pl],
                           "scores": [r["score"] for r in res], "rowA": [r["rowA"] for r in res], "rowB": [r["rowB"] for r in res]}
+    # guide trees by the reference's own Perl module (lib/perl/MLocarna/Tree.pm), for the archaea scores and a matrix with ties
+    import random, subprocess as sp
+    def perl_upgma(names, m):
+        script = 'use lib "/root/reference/lib/perl"; use MLocarna::Tree; my @n=(%s); my $m=[%s]; my $t=new MLocarna::Tree("UPGMA",\\@n,$m); print $t->to_newick();' % (
+            ",".join('"%s"' % x for x in names), ",".join("[" + ",".join(str(v) for v in row) + "]" for row in m))
+        return sp.run(["perl", "-e", script], capture_output=True, text=True, check=True).stdout
+    trees = []
+    if "archaea" in out:
+        from locarna_b200 import allpairs
+        g = out["archaea"]
+        m = allpairs.assemble_matrix(len(g["names"]), [tuple(p) for p in g["pairs"]], g["scores"])
+        trees.append({"names": g["names"], "matrix": m, "newick": perl_upgma(g["names"], m)})
+    rnd = random.Random(7)
+    for n in (2, 5, 12):
+        names = ["seq%d" % k for k in range(n)]
+        m = [[0] * n for _ in range(n)]
+        for i in range(n):
+            for j in range(i):
+                m[i][j] = m[j][i] = rnd.choice([-500, -120, 0, 300, 300, 750, 1200])
+        trees.append({"names": names, "matrix": m, "newick": perl_upgma(names, m)})
+    trees.append({"names": ["a:b", "it's", "plain"], "matrix": [[0, 5, 1], [5, 0, 2], [1, 2, 0]], "newick": perl_upgma(["a:b", "it's", "plain"], [[0, 5, 1], [5, 0, 2], [1, 2, 0]])})
+    out["trees"] = trees
     # stdout and --clustal file of the reference's own `locarna` binary (oracle/_ref/locarna) for the CLI parity test
     import subprocess
     cli = []
