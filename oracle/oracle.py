@@ -201,6 +201,8 @@ def parse_harness(text: str) -> list:
             cur["am_score"] = [int(r[4]) for r in rows]
             if rows and len(rows[0]) > 6:
                 cur["D"] = [sc(r[6]) for r in rows]
+            elif not rows:
+                cur["D"] = []
         elif k == "SCORE":
             cur["score"] = sc(t[1])
         elif k == "EDGES":
