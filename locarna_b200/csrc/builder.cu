@@ -180,8 +180,10 @@ __global__ void scatter_kernel(BuildCtx b, long long total) {
         const long long g = p.am_base + b.svals_sorted[t];
         const DevArcMatch x = b.am[g];
         DevEntry e;
-        e.x = ((x.ends_a & 0xfff) - 1) | (((x.ends_b & 0xfff) - 1) << 12);
-        e.y = (x.ends_a >> 12) | ((x.ends_b >> 12) << 12);
+        e.x = ((x.ends_a & 0xfff) - 1) | (((x.ends_b & 0xfff) - 1) << 16);
+        e.y = (x.ends_a >> 12) | ((x.ends_b >> 12) << 16);
+        e.d = LB_NEG;
+        e.s = (int)(x.ends_a >> 12) + (int)(x.ends_b >> 12);
         b.ent[t] = e;
         b.am[g].spos = (int)(t - p.am_base);
     }

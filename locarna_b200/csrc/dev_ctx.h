@@ -11,8 +11,7 @@ struct DevCtx {
     const uint8_t *codes;
     const int *band_lo, *band_hi;
     const int *sptr;
-    const DevEntry *ent;     // S-order
-    int *dval;               // D(arcA,arcB) in S-order
+    DevEntry *ent;           // S-order; ent[k].d = D(arcA,arcB)
     const DevArcMatch *am;   // L-order
     const DevTask *tasks;
     const int *qstart;       // task range of level group q = 4095 - ((al+bl)>>1): tasks[qstart[q] .. qstart[q+1])
@@ -24,6 +23,10 @@ struct DevCtx {
     int rowcode_bytes;       // >= max_rows + 2, multiple of 4
     int colcode_bytes;       // >= largest lenB + 2, multiple of 4
     int arcbuf_words;        // RING * 32 * NCmax
+    // padded row / column tables of the single-state sweep (kernels.cu setup_box2): no index clamps in the cell loop
+    int row_words, row_pad;  // roww[row_pad + 1 + ip], ip = -1..Rn+1; everything else holds the invalid-row sentinel
+    int col_bytes, col_pad;  // colc[col_pad + jp]
+    int region_bytes;        // max of the two layouts (they share the same shared-memory region)
     // traceback
     const unsigned *lpos;    // S-order position -> L-order index (relative to the pair)
     int *trace_edges;        // per pair n+m+3 slots (same offsets as sptr): edge at slot i+j = i << 2 | kind

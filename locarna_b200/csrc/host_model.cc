@@ -412,8 +412,10 @@ void build_pair_problem(const Sequence &A, const Sequence &B, const Band &band, 
         DevArcMatch &x = out.am[perm[s]];
         x.spos = s;
         const int al = x.ends_a & 0xfff, ar = x.ends_a >> 12, bl = x.ends_b & 0xfff, br = x.ends_b >> 12;
-        out.ent[s].x = (uint32_t)(al - 1) | ((uint32_t)(bl - 1) << 12);
-        out.ent[s].y = (uint32_t)ar | ((uint32_t)br << 12);
+        out.ent[s].x = (uint32_t)(al - 1) | ((uint32_t)(bl - 1) << 16);
+        out.ent[s].y = (uint32_t)ar | ((uint32_t)br << 16);
+        out.ent[s].d = LB_NEG;
+        out.ent[s].s = ar + br;
         out.sptr[ar + br + 1]++;
     }
     for (int s = 0; s + 1 < (int)out.sptr.size(); s++) out.sptr[s + 1] += out.sptr[s];

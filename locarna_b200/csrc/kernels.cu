@@ -51,7 +51,9 @@ struct WarpSmem {
     uint32_t *rowrange;  // [ip+1], ip = -1..Rn+1: first valid diagonal (c index) | number of further valid diagonals << 16
     uint8_t *rowcode;    // [ip+1]: 8 * symbol code of A[al+ip]
     uint8_t *colcode;    // [jp],  jp = 0..Cn+1: symbol code of B[bl+jp]
-    int *arcbuf;         // RING * 32*NC accumulators
+    int *arcbuf;         // RING * 32*NC accumulators (16-byte aligned)
+    uint32_t *roww;      // padded row words of the single-state sweep (setup_box2); shares the region with rowrange/rowcode/colcode
+    uint8_t *colc;       // padded column codes (x4)
 };
 
 __device__ __forceinline__ int warp_min(int v) {
@@ -106,175 +108,301 @@ __device__ void setup_box(const DevCtx &c, const DevPair &pr, int al, int bl, in
     __syncwarp();
 }
 
-// One anti-diagonal step of the cell recurrence for the NC diagonal pairs of this lane.
-// PAR = parity of (u - vmin): the active diagonal of pair g is c = 2g + PAR.
-//   PAR == 0: up neighbour (i-1,j) is the odd diagonal of the same pair, left neighbour (i,j-1) the odd diagonal
-//             of the previous pair (previous lane for k == 0);
-//   PAR == 1: left neighbour is the even diagonal of the same pair, up neighbour the even diagonal of the next pair.
-// GB (generic borders): row 0 / column 0 get explicit values; otherwise they fall out of the recurrence, which is
-//   exact for the all-global box init with indel_opening <= 0: M(al, bl+j') = open + j'*gap is what F yields on a
-//   row whose only finite predecessor is the origin (and E likewise for column 0).
-// CLAMP: sequence-local top level, M = max(M, 0) (aligner.cc:866-868).
+// ------------------------------------------------------------------------------------------------
+// Single-state sweep (global / sequence-local / free end gaps / noLP boxes).
+//
+// Row / column tables in shared memory, padded so that the cell loop needs no index clamps:
+//   roww[row_pad + 1 + ip]   one word per row ip = -1..Rn+1 (everything else = ROWW_INVALID):
+//        bits  0..10  first valid diagonal index c (c = j' - i' - vmin), bit 11 guard
+//        bits 12..22  2047 - last valid diagonal index, bit 23 guard
+//        bits 24..31  32 * symbol code of A[al+ip]  (byte offset of the sigma row)
+//   colc[col_pad + jp]       4 * symbol code of B[bl+jp]
+// Band test of a cell on diagonal c in row word w:  z = K(c) - w  with  K(c) = (c | 0x800) | ((2047 - c) | 0x800) << 12;
+// the guard bits of z survive iff first <= c and c <= last (no borrow crosses a field), i.e. one IADD3 + one LOP3.
+constexpr uint32_t ROWW_INVALID = 0x007ff7ffu;   // first = 2047, last = 0
+constexpr uint32_t ROWW_GUARDS = 0x00800800u;
+
+template <int NC> struct RingStride { static constexpr int v = NC <= 1 ? 32 : NC <= 2 ? 64 : NC <= 4 ? 128 : NC <= 8 ? 256 : 512; };
+
+__device__ void setup_box2(const DevCtx &c, const DevPair &pr, int al, int bl, int R, int C, BoxGeom &g, const WarpSmem &ws) {
+    const int lane = threadIdx.x & 31;
+    g.al = al; g.bl = bl; g.Rn = R - al; g.Cn = C - bl;
+    for (int k = lane; k < c.row_words; k += 32) ws.roww[k] = ROWW_INVALID;
+    for (int k = lane; k < (c.col_bytes >> 2); k += 32) ((uint32_t *)ws.colc)[k] = 0;
+    __syncwarp();
+    int vmin = 1 << 20, vmax = -(1 << 20), umax = 0;
+    const int *lo = c.band_lo + pr.band, *hi = c.band_hi + pr.band;
+    const uint8_t *ca = c.codes + pr.codesA, *cb = c.codes + pr.codesB;
+    uint32_t *rw = ws.roww + c.row_pad + 1;
+    for (int ip = lane; ip <= g.Rn; ip += 32) {
+        const int i = al + ip;
+        const int l = lo[i], h = hi[i];
+        int jl = (ip == 0 || l <= bl) ? 0 : (l - bl);
+        int jh = min(g.Cn, h - bl);
+        if (jh < jl) { jl = 0xffff; jh = 0xffff; }
+        else { vmin = min(vmin, jl - ip); vmax = max(vmax, jh - ip); umax = max(umax, ip + jh); }
+        rw[ip] = (uint32_t)jl | ((uint32_t)jh << 16);
+    }
+    for (int jp = lane; jp <= g.Cn; jp += 32) ws.colc[c.col_pad + jp] = (uint8_t)(((bl + jp >= 1) ? cb[bl + jp] : 0) * 4);
+    g.vmin = warp_min(vmin);
+    vmax = warp_max(vmax);
+    g.umax = warp_max(umax);
+    const int wd = vmax - g.vmin + 1;
+    g.nslots = (((wd + 1) >> 1) + 3) & ~3;   // row stride of the box: diagonal pairs, rounded up for vector stores
+    __syncwarp();
+    for (int ip = lane; ip <= g.Rn; ip += 32) {
+        const uint32_t r = rw[ip];
+        const int jl = r & 0xffff, jh = r >> 16;
+        const int i = al + ip;
+        const uint32_t code = (uint32_t)((i >= 1) ? ca[i] : 0) << 29;   // 32 * code in bits 24..31
+        rw[ip] = (jl == 0xffff) ? ROWW_INVALID : ((uint32_t)(jl - ip - g.vmin) | ((uint32_t)(2047 - (jh - ip - g.vmin)) << 12) | code);
+    }
+    __syncwarp();
+}
+
+// Register state of the sweep: per diagonal pair the cell last computed on the even / odd diagonal, the current row word and
+// column code, and the per-lane table pointers.
+template <int NC>
+struct Sweep {
+    int mE[NC], eE[NC], fE[NC], mO[NC], eO[NC], fO[NC];
+    uint32_t w[NC];          // row words of the current rows (slot k: row U2 - gidx_k)
+    int cc[NC];              // 4 * column code of the current columns
+    uint32_t K0[NC];         // band-test constant of the even diagonal of slot k (odd: K0 - 4095)
+    const uint32_t *rp;      // &roww[row_pad + 1 + U2 - lane*NC]      (slot k at rp[-k])
+    const uint8_t *cp;       // &colc[col_pad + J2 + lane*NC]          (slot k at cp[k])
+    int *ap;                 // &arcbuf[lane*NC]
+    int *bp;                 // &box[u * stride + lane*NC]
+    int ip0, jp0;            // row / column of slot 0 (generic borders only)
+    bool st_ok;              // lane*NC < stride: this lane's slots lie inside the box row
+};
+
+// One anti-diagonal step. PAR = parity of (u - vmin): the active diagonal of pair g is c = 2g + PAR.
+//   PAR == 0: new row (U2 advances): up neighbour = odd diagonal of the same pair, left = odd diagonal of the previous pair
+//   PAR == 1: new column (J2 advances): left neighbour = even diagonal of the same pair, up = even diagonal of the next pair
+// GB (generic borders): row 0 / column 0 get explicit values; otherwise they fall out of the recurrence, which is exact for
+//   the all-global box init with indel_opening <= 0.   CLAMP: sequence-local top level (aligner.cc:866-868).
 template <int NC, int PAR, bool GB, bool CLAMP>
-__device__ __forceinline__ void dp_step(const BoxGeom &g, const BoxInit &init, const WarpSmem &ws, int *box, const DevParams &P, int u,
-                                        int lane, int (&mE)[NC], int (&eE)[NC], int (&fE)[NC], int (&mO)[NC], int (&eO)[NC],
-                                        int (&fO)[NC]) {
-    constexpr int NW = 32 * NC;
+__device__ __forceinline__ void dp_step2(Sweep<NC> &S, const BoxInit &init, const int *sig, int ringoff, int stride, int gap, int gap_open, int lane) {
     int xm, xo;
     if (PAR == 0) {
-        xm = __shfl_up_sync(0xffffffffu, mO[NC - 1], 1);
-        xo = __shfl_up_sync(0xffffffffu, fO[NC - 1], 1);
+        xm = __shfl_up_sync(0xffffffffu, S.mO[NC - 1], 1);
+        xo = __shfl_up_sync(0xffffffffu, S.fO[NC - 1], 1);
         if (lane == 0) { xm = LB_NEG; xo = LB_NEG; }
+        S.rp += 1;
+        if (GB) S.ip0 += 1;
     } else {
-        xm = __shfl_down_sync(0xffffffffu, mE[0], 1);
-        xo = __shfl_down_sync(0xffffffffu, eE[0], 1);
+        xm = __shfl_down_sync(0xffffffffu, S.mE[0], 1);
+        xo = __shfl_down_sync(0xffffffffu, S.eE[0], 1);
         if (lane == 31) { xm = LB_NEG; xo = LB_NEG; }
+        S.cp += 1;
+        if (GB) S.jp0 += 1;
     }
-    // warp-uniform per step: row / column of diagonal pair 0
-    const int U2 = (u - g.vmin - PAR) >> 1;  // ip = U2 - gidx
-    const int J2 = (u + g.vmin + PAR) >> 1;  // jp = J2 + gidx
-    const int ring = (u & (RING - 1)) * NW;
-    int *boxrow = box + u * g.nslots;
-    const int gap = P.gap, gap_open = P.gap_open;
+    int *arc = S.ap + ringoff;
     int nm[NC], ne[NC], nf[NC];
 #pragma unroll
     for (int k = 0; k < NC; k++) {
-        const int gidx = lane * NC + k;
         int m_up, e_up, m_left, f_left, m_diag;
         if (PAR == 0) {
-            m_up = mO[k]; e_up = eO[k]; m_diag = mE[k];
-            if (k == 0) { m_left = xm; f_left = xo; } else { m_left = mO[k > 0 ? k - 1 : 0]; f_left = fO[k > 0 ? k - 1 : 0]; }
+            S.w[k] = S.rp[-k];
+            m_up = S.mO[k]; e_up = S.eO[k]; m_diag = S.mE[k];
+            if (k == 0) { m_left = xm; f_left = xo; } else { m_left = S.mO[k > 0 ? k - 1 : 0]; f_left = S.fO[k > 0 ? k - 1 : 0]; }
         } else {
-            m_left = mE[k]; f_left = fE[k]; m_diag = mO[k];
-            if (k == NC - 1) { m_up = xm; e_up = xo; } else { m_up = mE[k < NC - 1 ? k + 1 : k]; e_up = eE[k < NC - 1 ? k + 1 : k]; }
+            S.cc[k] = S.cp[k];
+            m_left = S.mE[k]; f_left = S.fE[k]; m_diag = S.mO[k];
+            if (k == NC - 1) { m_up = xm; e_up = xo; } else { m_up = S.mE[k < NC - 1 ? k + 1 : k]; e_up = S.eE[k < NC - 1 ? k + 1 : k]; }
         }
-        const int ip = U2 - gidx, jp = J2 + gidx;
-        const uint32_t ridx = min((uint32_t)(ip + 1), (uint32_t)(g.Rn + 2));  // rows outside 0..Rn hit an invalid sentinel
-        const uint32_t cidx = min((uint32_t)jp, (uint32_t)(g.Cn + 1));
-        const uint32_t rr = ws.rowrange[ridx];
-        const int sg = ws.sig[ws.rowcode[ridx] + ws.colcode[cidx]];
-        const bool ok = (uint32_t)(2 * gidx + PAR - (int)(rr & 0xffff)) <= (rr >> 16);
+        const uint32_t w = S.w[k];
+        const uint32_t z = S.K0[k] - w - (PAR ? 4095u : 0u);
+        const bool ok = (~z & ROWW_GUARDS) == 0;
+        const int sg = *(const int *)((const char *)sig + (w >> 24) + S.cc[k]);
         int e = addmax(e_up, gap, m_up + gap_open);
         int f = addmax(f_left, gap, m_left + gap_open);
-        const int arc = ws.arcbuf[ring + gidx];
-        ws.arcbuf[ring + gidx] = LB_NEG;
-        int m = max3(addmax(m_diag, sg, e), f, arc);
+        const int a = arc[k];
+        int m = max3(addmax(m_diag, sg, e), f, a);
         if (CLAMP) m = max(m, 0);
         if (GB) {
+            const int ip = S.ip0 - k, jp = S.jp0 + k;
             if (ip == 0) { m = (jp == 0) ? 0 : init.row_base + jp * init.row_step; e = LB_NEG; f = LB_NEG; }
             else if (jp == 0) { m = init.col_base + ip * init.col_step; e = LB_NEG; f = LB_NEG; }
         }
-        if (ok) boxrow[gidx] = m;
         nm[k] = ok ? m : LB_NEG; ne[k] = ok ? e : LB_NEG; nf[k] = ok ? f : LB_NEG;
     }
+    // reset the consumed accumulators, store the row of the box (vector stores: lane*NC and the stride are multiples of the width)
+    if (NC % 4 == 0) {
 #pragma unroll
-    for (int k = 0; k < NC; k++) {
-        if (PAR == 0) { mE[k] = nm[k]; eE[k] = ne[k]; fE[k] = nf[k]; }
-        else { mO[k] = nm[k]; eO[k] = ne[k]; fO[k] = nf[k]; }
-    }
-}
-
-// The arc-match entry stream of one box: entries of the pair in S-order restricted to the anti-diagonals of the
-// box, consumed in chunks of 32 with the global loads (entry, D) prefetched one chunk ahead and the M(source)
-// load of a chunk left in flight across the next cell step.
-struct EntryStream {
-    const DevEntry *ent;
-    const int *dval;
-    int pos, end;        // next entry / end of the stream (relative to the pair's S-order)
-    DevEntry pre_en;     // prefetched ent[pos + lane]
-    int pre_dv;          // prefetched dval[pos + lane]
-    int pend_m, pend_d, pend_slot;  // chunk in flight: M(source) (load pending), D, accumulator slot (-1: none)
-};
-
-__device__ __forceinline__ void stream_prefetch(EntryStream &es, int lane) {
-    const int e = es.pos + lane;
-    if (e < es.end) { es.pre_en = es.ent[e]; es.pre_dv = es.dval[e]; }
-}
-
-__device__ __forceinline__ void stream_finish(EntryStream &es, const WarpSmem &ws) {
-    if (es.pend_slot >= 0) atomicMax(&ws.arcbuf[es.pend_slot], es.pend_m + es.pend_d);
-    es.pend_slot = -1;
-}
-
-// issue one chunk [pos, pos+count): filter, compute the accumulator slot, start the M(source) load
-template <int NC>
-__device__ __forceinline__ void stream_issue(EntryStream &es, const BoxGeom &g, const int *box, int count, int lane) {
-    constexpr int NW = 32 * NC;
-    es.pend_slot = -1;
-    if (lane < count) {
-        const DevEntry en = es.pre_en;
-        const int p = (int)(en.x & 0xfff) - g.al, q = (int)(en.x >> 12) - g.bl;
-        const int ar = (int)(en.y & 0xfff) - g.al, br = (int)(en.y >> 12) - g.bl;
-        // inside the box: left ends right of the origin (al' > al, bl' > bl, aligner.cc:214-215), right ends within
-        if ((p | q | (g.Rn - ar) | (g.Cn - br)) >= 0) {
-            es.pend_m = box[(p + q) * g.nslots + ((q - p - g.vmin) >> 1)];
-            es.pend_d = es.pre_dv;
-            es.pend_slot = ((ar + br) & (RING - 1)) * NW + ((br - ar - g.vmin) >> 1);
+        for (int k = 0; k < NC; k += 4) {
+            *(int4 *)(arc + k) = make_int4(LB_NEG, LB_NEG, LB_NEG, LB_NEG);
+            if (NC == 4 ? S.st_ok : (lane * NC + k < stride)) *(int4 *)(S.bp + k) = make_int4(nm[k], nm[k + 1], nm[k + 2], nm[k + 3]);
+        }
+    } else if (NC % 2 == 0) {
+#pragma unroll
+        for (int k = 0; k < NC; k += 2) {
+            *(int2 *)(arc + k) = make_int2(LB_NEG, LB_NEG);
+            if (S.st_ok) *(int2 *)(S.bp + k) = make_int2(nm[k], nm[k + 1]);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < NC; k++) {
+            arc[k] = LB_NEG;
+            if (S.st_ok && (NC == 1 || lane * NC + k < stride)) S.bp[k] = nm[k];
         }
     }
-    es.pos += count;
-    stream_prefetch(es, lane);
+    S.bp += stride;
+#pragma unroll
+    for (int k = 0; k < NC; k++) {
+        if (PAR == 0) { S.mE[k] = nm[k]; S.eE[k] = ne[k]; S.fE[k] = nf[k]; }
+        else { S.mO[k] = nm[k]; S.eO[k] = ne[k]; S.fO[k] = nf[k]; }
+    }
+}
+
+// The arc-match entry stream of one box: the pair's S-order entries (sorted by the anti-diagonal of their right ends) are
+// consumed in aligned blocks of 32 (one 16-byte entry per lane, LDG.128, prefetched one block ahead). A block is processed
+// when its first unconsumed entry is needed within two steps; lanes whose sources are not final yet (target anti-diagonal
+// > u + 8; sources lie >= 8 anti-diagonals before the target because both arcs span >= 3 positions) stay for a later pass.
+// The M(source) gather of a processed block stays in flight across the next cell step and is folded into the ring of
+// per-anti-diagonal accumulators with a shared-memory atomicMax afterwards.
+struct Stream2 {
+    const uint4 *base;       // the pair's entries
+    int blk;                 // block held in cur
+    int e_begin, e_end;      // entry range of the box (targets on local anti-diagonals 8..umax)
+    uint32_t cx, cy; int cd; // current block: entry of this lane
+    int cs;                  // its target anti-diagonal (absolute), INT_MAX once consumed / out of range
+    uint4 nx;                // prefetched block blk + 1
+    int first;               // min cs over the warp
+    int pm0, pd0, ps0, pm1, pd1, ps1;   // two gathers in flight: M(source), D, accumulator index (-1: none)
+};
+
+__device__ __forceinline__ uint4 stream_load(const Stream2 &st, int b, int lane) {
+    const int e = b * 32 + lane;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (e < st.e_end) v = __ldg(st.base + e);
+    return v;
+}
+
+__device__ __forceinline__ void stream_take(Stream2 &st, uint4 v, int lane) {
+    st.cx = v.x; st.cy = v.y; st.cd = (int)v.z;
+    const int e = st.blk * 32 + lane;
+    st.cs = (e >= st.e_begin && e < st.e_end) ? (int)v.w : 0x7fffffff;
+    st.first = __reduce_min_sync(0xffffffffu, st.cs);
+}
+
+// process the current block at step u: returns the gather of this lane (slot < 0: none)
+template <int NC>
+__device__ __forceinline__ void stream_process(Stream2 &st, const BoxGeom &g, const int *box, int s_allow, uint32_t org, uint32_t lim, int d0,
+                                               int lane, int &pm, int &pd, int &ps) {
+    constexpr int NWP = RingStride<NC>::v;
+    const bool allowed = st.cs <= s_allow;
+    const uint32_t t1 = st.cx - org, t2 = lim - st.cy;
+    ps = -1;
+    if (allowed && ((t1 | t2) & 0x80008000u) == 0) {
+        const int p = LB_ENT_LO(t1), q = LB_ENT_HI(t1);
+        pm = box[(p + q) * g.nslots + ((q - p - g.vmin) >> 1)];
+        pd = st.cd;
+        ps = (st.cs & (RING - 1)) * NWP + ((LB_ENT_HI(st.cy) - LB_ENT_LO(st.cy) - d0) >> 1);
+    }
+    if (allowed) st.cs = 0x7fffffff;
+    st.first = __reduce_min_sync(0xffffffffu, st.cs);
+    if (st.first == 0x7fffffff && st.blk * 32 + 32 < st.e_end) {   // block exhausted: rotate
+        st.blk += 1;
+        stream_take(st, st.nx, lane);
+        st.nx = stream_load(st, st.blk + 1, lane);
+    }
 }
 
 // Fill one M box. NC = diagonal pairs per lane (the warp covers 64*NC diagonals).
 template <int NC, bool GB, bool CLAMP>
 __device__ void fill_box(const DevCtx &c, const DevPair &pr, const BoxGeom &g, const BoxInit &init, const WarpSmem &ws, int *box) {
     const int lane = threadIdx.x & 31;
-    constexpr int NW = 32 * NC;
-    const DevParams &P = c.params;
+    constexpr int NWP = RingStride<NC>::v;
+    const int gap = c.params.gap, gap_open = c.params.gap_open;
+    const int stride = g.nslots;
 
-    for (int k = lane; k < RING * NW; k += 32) ws.arcbuf[k] = LB_NEG;
+    for (int k = lane; k < RING * NWP; k += 32) ws.arcbuf[k] = LB_NEG;
 
-    // S-order offset of the first entry whose right ends lie on local anti-diagonal >= t
-    const int *sptr = c.sptr + pr.sptr;
-    const int s_base = g.al + g.bl, s_last = pr.lenA + pr.lenB + 1;
-    auto sp = [&](int t) { return __ldg(sptr + min(s_base + min(t, g.umax + 1), s_last)); };
+    const int s0 = g.al + g.bl;
+    Stream2 st;
+    {
+        const int *sptr = c.sptr + pr.sptr;
+        const int s_last = pr.lenA + pr.lenB + 1;
+        // right ends of arc matches inside the box lie on local anti-diagonals 8..umax
+        st.e_begin = __ldg(sptr + min(s0 + min(8, g.umax + 1), s_last));
+        st.e_end = __ldg(sptr + min(s0 + g.umax + 1, s_last));
+        st.base = (const uint4 *)(c.ent + pr.am_base);
+        st.blk = st.e_begin >> 5;
+        st.ps0 = -1; st.ps1 = -1; st.pm0 = st.pm1 = st.pd0 = st.pd1 = 0;
+        stream_take(st, stream_load(st, st.blk, lane), lane);
+        st.nx = stream_load(st, st.blk + 1, lane);
+    }
+    const uint32_t org = (uint32_t)g.al | ((uint32_t)g.bl << 16);
+    const uint32_t lim = (uint32_t)(g.al + g.Rn) | ((uint32_t)(g.bl + g.Cn) << 16);
+    const int d0 = g.bl - g.al + g.vmin;
 
-    EntryStream es;
-    es.ent = c.ent + pr.am_base; es.dval = c.dval + pr.am_base;
-    // right ends of arc matches inside the box lie on local anti-diagonals >= 8 (both arcs span >= 3 positions)
-    es.pos = sp(8); es.end = sp(g.umax + 1);
-    es.pend_slot = -1; es.pend_m = 0; es.pend_d = 0;
-    stream_prefetch(es, lane);
-
-    // register state per diagonal pair: the cell last computed on the even / odd diagonal of the pair
-    int mE[NC], eE[NC], fE[NC], mO[NC], eO[NC], fO[NC];
+    Sweep<NC> S;
 #pragma unroll
-    for (int k = 0; k < NC; k++) { mE[k] = eE[k] = fE[k] = mO[k] = eO[k] = fO[k] = LB_NEG; }
-
+    for (int k = 0; k < NC; k++) { S.mE[k] = S.eE[k] = S.fE[k] = S.mO[k] = S.eO[k] = S.fO[k] = LB_NEG; }
+    const int par0 = (0 - g.vmin) & 1;   // parity class of anti-diagonal 0
+    const int U2 = (-g.vmin - par0) >> 1, J2 = (g.vmin + par0) >> 1;   // row / column of diagonal pair 0 "at u = 0"
+    S.rp = ws.roww + c.row_pad + 1 + U2 - lane * NC;
+    S.cp = ws.colc + c.col_pad + J2 + lane * NC;
+    S.ap = ws.arcbuf + lane * NC;
+    S.bp = box + stride + lane * NC;     // row u = 1
+    S.ip0 = U2 - lane * NC; S.jp0 = J2 + lane * NC;
+    S.st_ok = lane * NC < stride;
+#pragma unroll
+    for (int k = 0; k < NC; k++) {
+        const uint32_t cdiag = 2 * (lane * NC + k);
+        S.K0[k] = (cdiag | 0x800u) | (((2047u - cdiag) | 0x800u) << 12);
+        S.w[k] = S.rp[-k];
+        S.cc[k] = S.cp[k];
+    }
     // seed the origin M(al, bl) = 0 (aligner.cc:289): diagonal v = 0, i.e. c = -vmin
-    const int par0 = (0 - g.vmin) & 1;
     {
         const int c0 = -g.vmin;
 #pragma unroll
         for (int k = 0; k < NC; k++) {
-            if (2 * (lane * NC + k) + par0 == c0) { if (par0 == 0) mE[k] = 0; else mO[k] = 0; box[c0 >> 1] = 0; }
+            if (2 * (lane * NC + k) + par0 == c0) { if (par0 == 0) S.mE[k] = 0; else S.mO[k] = 0; box[c0 >> 1] = 0; }
         }
     }
-    int need_end = sp(3), allow_end = sp(9);  // for step u = 1
     __syncwarp();
 
-    for (int u = 1; u <= g.umax; u++) {
-        // (1) land the chunk that was in flight across the previous step
-        stream_finish(es, ws);
-        const int next_need = sp(u + 3), next_allow = sp(u + 9);
+    int ringoff = ((s0 + 1) & (RING - 1)) * NWP;
+    auto land = [&]() {
+        if (st.ps0 >= 0) atomicMax(&ws.arcbuf[st.ps0], st.pm0 + st.pd0);
+        if (st.ps1 >= 0) atomicMax(&ws.arcbuf[st.ps1], st.pm1 + st.pd1);
+        st.ps0 = -1; st.ps1 = -1;
+    };
+    auto stream = [&](int u) {
         __syncwarp();
-        // (2) cells of anti-diagonal u
-        if (((u + par0) & 1) == 0) dp_step<NC, 0, GB, CLAMP>(g, init, ws, box, P, u, lane, mE, eE, fE, mO, eO, fO);
-        else dp_step<NC, 1, GB, CLAMP>(g, init, ws, box, P, u, lane, mE, eE, fE, mO, eO, fO);
-        __syncwarp();
-        // (3) stream arc-match entries: everything with right ends on anti-diagonal <= u+1 must be issued now (it lands
-        //     before step u+1); entries up to anti-diagonal u+7 may be issued (their sources M(al'-1,bl'-1) lie >= 8
-        //     anti-diagonals back, i.e. are final after step u-1). Prefer full chunks.
-        int quota = 2;
-        while (es.pos < need_end || (quota > 0 && allow_end - es.pos >= 32)) {
-            stream_finish(es, ws);
-            stream_issue<NC>(es, g, box, min(32, allow_end - es.pos), lane);
-            quota--;
+        land();   // gathers issued during the previous step
+        const int s_need = s0 + u + 2, s_allow = s0 + u + 8;
+        while (st.first <= s_need) {
+            if (st.ps0 >= 0) { atomicMax(&ws.arcbuf[st.ps0], st.pm0 + st.pd0); }
+            stream_process<NC>(st, g, box, s_allow, org, lim, d0, lane, st.pm0, st.pd0, st.ps0);
+            if (st.first > s_need) break;
+            if (st.ps1 >= 0) { atomicMax(&ws.arcbuf[st.ps1], st.pm1 + st.pd1); }
+            stream_process<NC>(st, g, box, s_allow, org, lim, d0, lane, st.pm1, st.pd1, st.ps1);
         }
-        need_end = next_need; allow_end = next_allow;
+        __syncwarp();
+    };
+    int u = 1;
+    if (par0 == 0) {   // anti-diagonal 1 is of the odd class
+        dp_step2<NC, 1, GB, CLAMP>(S, init, ws.sig, ringoff, stride, gap, gap_open, lane);
+        ringoff = (ringoff + NWP) & (RING * NWP - 1);
+        stream(u);
+        u = 2;
     }
-    stream_finish(es, ws);
+    for (; u + 1 <= g.umax; u += 2) {
+        dp_step2<NC, 0, GB, CLAMP>(S, init, ws.sig, ringoff, stride, gap, gap_open, lane);
+        ringoff = (ringoff + NWP) & (RING * NWP - 1);
+        stream(u);
+        dp_step2<NC, 1, GB, CLAMP>(S, init, ws.sig, ringoff, stride, gap, gap_open, lane);
+        ringoff = (ringoff + NWP) & (RING * NWP - 1);
+        stream(u + 1);
+    }
+    if (u <= g.umax) {
+        dp_step2<NC, 0, GB, CLAMP>(S, init, ws.sig, ringoff, stride, gap, gap_open, lane);
+        __syncwarp();
+    }
     __syncwarp();
 }
 
@@ -418,7 +546,6 @@ __device__ void fill_box_sl(const DevCtx &c, const DevPair &pr, const BoxGeom &g
     const int s_base = g.al + g.bl, s_last = pr.lenA + pr.lenB + 1;
     auto sp = [&](int t) { return __ldg(sptr + min(s_base + min(t, g.umax + 1), s_last)); };
     const DevEntry *ent = c.ent + pr.am_base;
-    const int *dval = c.dval + pr.am_base;
     int mE[4][NC], eE[4][NC], fE[4][NC], mO[4][NC], eO[4][NC], fO[4][NC], oE[4][NC], oO[4][NC];
 #pragma unroll
     for (int st = 0; st < 4; st++)
@@ -447,10 +574,10 @@ __device__ void fill_box_sl(const DevCtx &c, const DevPair &pr, const BoxGeom &g
             const int tring = (u & (RING - 1)) * NW;
             for (int e = e0 + lane; e < e1; e += 32) {
                 const DevEntry en = ent[e];
-                const int p = (int)(en.x & 0xfff) - g.al, q = (int)(en.x >> 12) - g.bl;
-                const int ar = (int)(en.y & 0xfff) - g.al, br = (int)(en.y >> 12) - g.bl;
+                const int p = LB_ENT_LO(en.x) - g.al, q = LB_ENT_HI(en.x) - g.bl;
+                const int ar = LB_ENT_LO(en.y) - g.al, br = LB_ENT_HI(en.y) - g.bl;
                 if ((p | q | (g.Rn - ar) | (g.Cn - br)) >= 0) {
-                    const int d = dval[e];
+                    const int d = en.d;
                     const int src = (p + q) * g.nslots + ((q - p - g.vmin) >> 1);
                     const int slot = tring + ((br - ar - g.vmin) >> 1);
 #pragma unroll
@@ -502,7 +629,9 @@ __device__ __forceinline__ void carve(const DevCtx &c, int *smem, WarpSmem &ws) 
     ws.rowrange = (uint32_t *)(smem + 64);
     ws.rowcode = (uint8_t *)(ws.rowrange + c.max_rows + 2);
     ws.colcode = ws.rowcode + c.rowcode_bytes;
-    ws.arcbuf = (int *)(ws.colcode + c.colcode_bytes);
+    ws.roww = (uint32_t *)(smem + 64);
+    ws.colc = (uint8_t *)(ws.roww + c.row_words);
+    ws.arcbuf = (int *)((char *)(smem + 64) + c.region_bytes);
     const int lane = threadIdx.x & 31;
     sig[lane] = c.params.sigma8[lane]; sig[lane + 32] = c.params.sigma8[lane + 32];
     __syncwarp();
@@ -514,7 +643,7 @@ __device__ __forceinline__ void carve(const DevCtx &c, int *smem, WarpSmem &ws) 
 // box, whose left ends have a larger al+bl (aligner.cc:675-728; levels = al+bl descending, two at a time).
 template <int NCMAX, bool GB>
 __global__ void __launch_bounds__(32) dfill_kernel(DevCtx c, int q) {
-    extern __shared__ int smem[];
+    extern __shared__ __align__(16) int smem[];
     const int lane = threadIdx.x;
     const int task_begin = c.qstart[q], task_end = c.qstart[q + 1];
     if ((int)blockIdx.x >= task_end - task_begin) return;
@@ -534,12 +663,12 @@ __global__ void __launch_bounds__(32) dfill_kernel(DevCtx c, int q) {
         const DevTask task = c.tasks[t];
         const DevPair pr = c.pairs[task.pair];
         BoxGeom g;
-        setup_box(c, pr, task.al, task.bl, task.R, task.C, g, ws);
+        setup_box2(c, pr, task.al, task.bl, task.R, task.C, g, ws);
         if ((g.umax + 1) * g.nslots > c.scratch_words) { if (lane == 0) atomicExch(c.error_flag, 2); continue; }
         if (!run_box<NCMAX, GB, false>(c, pr, g, init, ws, box)) { if (lane == 0) atomicExch(c.error_flag, 1); continue; }
         // ---- D entries of all arc matches with these left ends (aligner.cc:574-657)
         const DevArcMatch *am = c.am + pr.am_base;
-        int *dval = c.dval + pr.am_base;
+        DevEntry *ent = c.ent + pr.am_base;
         const int sh = nolp ? 2 : 1;
         for (int k = task.run_start + lane; k < task.run_start + task.run_count; k += 32) {
             const DevArcMatch x = am[k];
@@ -550,10 +679,10 @@ __global__ void __launch_bounds__(32) dfill_kernel(DevCtx c, int q) {
             if (nolp) {
                 const DevArcMatch in = am[x.inner];
                 const int a = (mv < LB_NEG_LIMIT) ? LB_NEG : mv + in.score;
-                const int y = max(a, dval[in.spos]);
+                const int y = max(a, ent[in.spos].d);
                 d = (y < LB_NEG_LIMIT) ? LB_NEG : y + x.score;
             } else d = (mv < LB_NEG_LIMIT) ? LB_NEG : mv + x.score;
-            dval[x.spos] = d;
+            ent[x.spos].d = d;
         }
         __syncwarp();
     }
@@ -561,7 +690,7 @@ __global__ void __launch_bounds__(32) dfill_kernel(DevCtx c, int q) {
 
 // D-fill for --struct-local: D = max over the four closed states (aligner.cc:586-595, :632-640)
 __global__ void __launch_bounds__(32) dfill_sl_kernel(DevCtx c, int q) {
-    extern __shared__ int smem[];
+    extern __shared__ __align__(16) int smem[];
     const int lane = threadIdx.x;
     const int task_begin = c.qstart[q], task_end = c.qstart[q + 1];
     if ((int)blockIdx.x >= task_end - task_begin) return;
@@ -583,7 +712,7 @@ __global__ void __launch_bounds__(32) dfill_sl_kernel(DevCtx c, int q) {
         if ((g.umax + 1) * g.nslots > box_words) { if (lane == 0) atomicExch(c.error_flag, 2); continue; }
         if (!run_box_sl<false>(c, pr, g, ws, boxes, box_words)) { if (lane == 0) atomicExch(c.error_flag, 1); continue; }
         const DevArcMatch *am = c.am + pr.am_base;
-        int *dval = c.dval + pr.am_base;
+        DevEntry *ent = c.ent + pr.am_base;
         const int sh = nolp ? 2 : 1;
         for (int k = task.run_start + lane; k < task.run_start + task.run_count; k += 32) {
             const DevArcMatch x = am[k];
@@ -596,10 +725,10 @@ __global__ void __launch_bounds__(32) dfill_sl_kernel(DevCtx c, int q) {
             if (nolp) {
                 const DevArcMatch in = am[x.inner];
                 const int a = (mv < LB_NEG_LIMIT) ? LB_NEG : mv + in.score;
-                const int y = max(a, dval[in.spos]);
+                const int y = max(a, ent[in.spos].d);
                 d = (y < LB_NEG_LIMIT) ? LB_NEG : y + x.score;
             } else d = (mv < LB_NEG_LIMIT) ? LB_NEG : mv + x.score;
-            dval[x.spos] = d;
+            ent[x.spos].d = d;
         }
         __syncwarp();
     }
@@ -609,7 +738,7 @@ __global__ void __launch_bounds__(32) dfill_sl_kernel(DevCtx c, int q) {
 // Top level (aligner.cc:736-880): one box over the whole band with al = bl = 0, then the score.
 template <int NCMAX, bool CLAMP>
 __global__ void __launch_bounds__(32) toplevel_kernel(DevCtx c, int pair_begin, int pair_end, int *cursor) {
-    extern __shared__ int smem[];
+    extern __shared__ __align__(16) int smem[];
     const int lane = threadIdx.x;
     WarpSmem ws;
     carve(c, smem, ws);
@@ -627,7 +756,7 @@ __global__ void __launch_bounds__(32) toplevel_kernel(DevCtx c, int pair_begin, 
         if (t >= pair_end) break;
         const DevPair pr = c.pairs[t];
         BoxGeom g;
-        setup_box(c, pr, 0, 0, pr.lenA, pr.lenB, g, ws);
+        setup_box2(c, pr, 0, 0, pr.lenA, pr.lenB, g, ws);
         if ((g.umax + 1) * g.nslots > c.scratch_words) { if (lane == 0) atomicExch(c.error_flag, 2); continue; }
         if (!run_box<NCMAX, true, CLAMP>(c, pr, g, init, ws, box)) { if (lane == 0) atomicExch(c.error_flag, 1); continue; }
         const int n = pr.lenA, m = pr.lenB;
@@ -695,7 +824,7 @@ __global__ void __launch_bounds__(32) toplevel_kernel(DevCtx c, int pair_begin, 
 
 template <int NCMAX, bool GBD, bool CLAMP>
 __global__ void __launch_bounds__(32) trace_kernel(DevCtx c, int pair_begin, int pair_end, int *cursor) {
-    extern __shared__ int smem[];
+    extern __shared__ __align__(16) int smem[];
     const int lane = threadIdx.x;
     WarpSmem ws;
     carve(c, smem, ws);
@@ -717,7 +846,6 @@ __global__ void __launch_bounds__(32) trace_kernel(DevCtx c, int pair_begin, int
         const int *lo = c.band_lo + pr.band, *hi = c.band_hi + pr.band;
         const uint8_t *ca = c.codes + pr.codesA, *cb = c.codes + pr.codesB;
         const DevEntry *ent = c.ent + pr.am_base;
-        const int *dval = c.dval + pr.am_base;
         const DevArcMatch *am = c.am + pr.am_base;
         const unsigned *lpos = c.lpos + pr.am_base;
         const int *sptr = c.sptr + pr.sptr;
@@ -738,7 +866,7 @@ __global__ void __launch_bounds__(32) trace_kernel(DevCtx c, int pair_begin, int
         bool have = true;
         while (have) {
             BoxGeom g;
-            setup_box(c, pr, job.al, job.bl, job.R, job.C, g, ws);
+            setup_box2(c, pr, job.al, job.bl, job.R, job.C, g, ws);
             bool ok;
             if ((g.umax + 1) * g.nslots > c.scratch_words) ok = false;
             else if (tl) ok = run_box<NCMAX, true, CLAMP>(c, pr, g, top_init, ws, box);
@@ -802,15 +930,15 @@ __global__ void __launch_bounds__(32) trace_kernel(DevCtx c, int pair_begin, int
                     bool hit = false;
                     if (e < e1) {
                         const DevEntry en = ent[e];
-                        const int p = (int)(en.x & 0xfff), q = (int)(en.x >> 12);
-                        if ((int)(en.y & 0xfff) == i && p >= al && q >= bl) hit = (mij == box_get(box, g, p - al, q - bl) + dval[e]);
+                        const int p = LB_ENT_LO(en.x), q = LB_ENT_HI(en.x);
+                        if (LB_ENT_LO(en.y) == i && p >= al && q >= bl) hit = (mij == box_get(box, g, p - al, q - bl) + en.d);
                     }
                     const unsigned b = __ballot_sync(0xffffffffu, hit);
                     if (b) found = base + __ffs(b) - 1;
                 }
                 if (found < 0) { if (lane == 0) atomicExch(c.error_flag, 4); break; }
                 const DevEntry en = ent[found];
-                const int xl = (int)(en.x & 0xfff) + 1, yl = (int)(en.x >> 12) + 1;  // left ends of the arc match
+                const int xl = LB_ENT_LO(en.x) + 1, yl = LB_ENT_HI(en.x) + 1;  // left ends of the arc match
                 if (lane == 0) { strA[xl] = '('; strA[i] = ')'; strB[yl] = '('; strB[j] = ')'; }
                 emit(xl, yl, LB_EDGE_MATCH);
                 emit(i, j, LB_EDGE_MATCH);
@@ -826,7 +954,7 @@ __global__ void __launch_bounds__(32) trace_kernel(DevCtx c, int pair_begin, int
                         if (lane == 0) { strA[ial] = '('; strA[iar] = ')'; strB[ibl] = '('; strB[ibr] = ')'; }
                         emit(ial, ibl, LB_EDGE_MATCH);
                         emit(iar, ibr, LB_EDGE_MATCH);
-                        if (dval[x.spos] == dval[in.spos] + x.score) { cur = x.inner; continue; }
+                        if (ent[x.spos].d == ent[in.spos].d + x.score) { cur = x.inner; continue; }
                         if (lane == 0) { TraceJob nj; nj.al = (short)ial; nj.bl = (short)ibl; nj.R = (short)(iar - 1); nj.C = (short)(ibr - 1); nj.am = -1; stack[sp] = nj; }
                         sp++;
                         break;
@@ -848,7 +976,7 @@ __global__ void __launch_bounds__(32) trace_kernel(DevCtx c, int pair_begin, int
 // E_NO_NO; every arc-match box is refilled with all eight matrices and walked with the reference's state machine.
 template <bool CLAMP>
 __global__ void __launch_bounds__(32) trace_sl_kernel(DevCtx c, int pair_begin, int pair_end, int *cursor) {
-    extern __shared__ int smem[];
+    extern __shared__ __align__(16) int smem[];
     const int lane = threadIdx.x;
     WarpSmem ws;
     carve(c, smem, ws);
@@ -871,7 +999,6 @@ __global__ void __launch_bounds__(32) trace_sl_kernel(DevCtx c, int pair_begin, 
         const int *lo = c.band_lo + pr.band, *hi = c.band_hi + pr.band;
         const uint8_t *ca = c.codes + pr.codesA, *cb = c.codes + pr.codesB;
         const DevEntry *ent = c.ent + pr.am_base;
-        const int *dval = c.dval + pr.am_base;
         const DevArcMatch *am = c.am + pr.am_base;
         const unsigned *lpos = c.lpos + pr.am_base;
         const int *sptr = c.sptr + pr.sptr;
@@ -892,7 +1019,8 @@ __global__ void __launch_bounds__(32) trace_sl_kernel(DevCtx c, int pair_begin, 
         bool have = true;
         while (have) {
             BoxGeom g;
-            setup_box(c, pr, job.al, job.bl, job.R, job.C, g, ws);
+            if (tl) setup_box2(c, pr, job.al, job.bl, job.R, job.C, g, ws);
+            else setup_box(c, pr, job.al, job.bl, job.R, job.C, g, ws);
             bool ok = (g.umax + 1) * g.nslots <= box_words;
             if (ok) ok = tl ? run_box<4, true, CLAMP>(c, pr, g, top_init, ws, boxes) : run_box_sl<true>(c, pr, g, ws, boxes, box_words);
             if (!ok) { if (lane == 0) atomicExch(c.error_flag, 3); break; }
@@ -907,7 +1035,7 @@ __global__ void __launch_bounds__(32) trace_sl_kernel(DevCtx c, int pair_begin, 
                 const DevArcMatch x = am[job.am];
                 const int add = nolp ? x.score + am[x.inner].score : x.score;
                 st = -1;
-                for (int k = 0; k < 4; k++) if (dval[x.spos] == B(k, i, j) + add) { st = k; break; }
+                for (int k = 0; k < 4; k++) if (ent[x.spos].d == B(k, i, j) + add) { st = k; break; }
                 if (st < 0) { tl = false; have = sp > 0; if (have) { sp--; job = stack[sp]; } continue; }
             }
             for (;;) {
@@ -977,15 +1105,15 @@ __global__ void __launch_bounds__(32) trace_sl_kernel(DevCtx c, int pair_begin, 
                     bool hit = false;
                     if (e < e1) {
                         const DevEntry en = ent[e];
-                        const int p = (int)(en.x & 0xfff), q = (int)(en.x >> 12);
-                        if ((int)(en.y & 0xfff) == i && p >= al && q >= bl) hit = (mij == B(st, p, q) + dval[e]);
+                        const int p = LB_ENT_LO(en.x), q = LB_ENT_HI(en.x);
+                        if (LB_ENT_LO(en.y) == i && p >= al && q >= bl) hit = (mij == B(st, p, q) + en.d);
                     }
                     const unsigned bm = __ballot_sync(0xffffffffu, hit);
                     if (bm) found = base + __ffs(bm) - 1;
                 }
                 if (found < 0) { if (lane == 0) atomicExch(c.error_flag, 4); break; }
                 const DevEntry en = ent[found];
-                const int xl = (int)(en.x & 0xfff) + 1, yl = (int)(en.x >> 12) + 1;
+                const int xl = LB_ENT_LO(en.x) + 1, yl = LB_ENT_HI(en.x) + 1;
                 if (lane == 0) { strA[xl] = '('; strA[i] = ')'; strB[yl] = '('; strB[j] = ')'; }
                 emit(xl, yl, LB_EDGE_MATCH);
                 emit(i, j, LB_EDGE_MATCH);
@@ -1001,7 +1129,7 @@ __global__ void __launch_bounds__(32) trace_sl_kernel(DevCtx c, int pair_begin, 
                         if (lane == 0) { strA[ial] = '('; strA[iar] = ')'; strB[ibl] = '('; strB[ibr] = ')'; }
                         emit(ial, ibl, LB_EDGE_MATCH);
                         emit(iar, ibr, LB_EDGE_MATCH);
-                        if (dval[x.spos] == dval[in.spos] + x.score) { cur = x.inner; continue; }
+                        if (ent[x.spos].d == ent[in.spos].d + x.score) { cur = x.inner; continue; }
                         if (lane == 0) { TraceJob nj; nj.al = (short)ial; nj.bl = (short)ibl; nj.R = (short)(iar - 1); nj.C = (short)(ibr - 1); nj.am = cur; stack[sp] = nj; }
                         sp++;
                         break;

@@ -30,7 +30,7 @@ void launch_trace_sl(const DevCtx &c, int grid, int smem_bytes, int pair_begin, 
 
 using namespace lb200;
 
-cudaError_t lb200_fill_i32(int *p, size_t n, int v, cudaStream_t st);
+cudaError_t lb200_reset_d(DevEntry *ent, size_t n, cudaStream_t st);
 
 namespace {
 
@@ -101,9 +101,9 @@ struct lb200_ctx {
     std::vector<int> seq_prob_off;
     int64_t env_device_pairs = 0, env_host_pairs = 0;  // statistics of the last band derivation
     int env_mode = 1;  // 1: device screening + host re-check, 0: host only (LB200_ENVELOPE=host)
-    DevBuf d_pairs, d_codes, d_band_lo, d_band_hi, d_sptr, d_ent, d_dval, d_am, d_tasks, d_top, d_scratch, d_cursor, d_flag;
+    DevBuf d_pairs, d_codes, d_band_lo, d_band_hi, d_sptr, d_ent, d_am, d_tasks, d_top, d_scratch, d_cursor, d_flag;
     ~lb200_ctx() {
-        DevBuf *all[] = {&d_pairs, &d_codes, &d_band_lo, &d_band_hi, &d_sptr, &d_ent, &d_dval, &d_am, &d_tasks, &d_top, &d_scratch, &d_cursor, &d_flag,
+        DevBuf *all[] = {&d_pairs, &d_codes, &d_band_lo, &d_band_hi, &d_sptr, &d_ent, &d_am, &d_tasks, &d_top, &d_scratch, &d_cursor, &d_flag,
                          &d_arc_left, &d_arc_right, &d_arc_weight, &d_lptr, &d_lcount, &d_am_seq, &d_cell_rev, &d_cell_start, &d_skeys, &d_skeys2,
                          &d_svals, &d_svals2, &d_tasks_unsorted, &d_tkeys, &d_tkeys2, &d_tvals, &d_tvals2, &d_ntasks, &d_qstart, &d_stats, &d_tmp, &d_tr_edges, &d_tr_str, &d_tr_stack,
                          &d_pup, &d_pdown, &d_env_pairs, &d_env_lo, &d_env_hi, &d_env_olo, &d_env_ohi, &d_env_flag, &d_env_scratch};
@@ -461,7 +461,7 @@ static int upload_chunk(lb200_ctx *c, int p0, int p1) {
         d.sptr = (int)sptr_total; sptr_total += n + m + 3;
         const int wd = dmax - dmin + 1;
         wd_bound = std::max(wd_bound, wd);
-        max_box_words = std::max(max_box_words, (n + m + 1) * ((wd + 1) / 2));  // anti-diagonal major box
+        max_box_words = std::max(max_box_words, (n + m + 1) * ((((wd + 1) / 2) + 3) & ~3));  // row stride: diagonal pairs rounded up to 4  // anti-diagonal major box
         max_rows = std::max(max_rows, n + 1); max_cols = std::max(max_cols, m + 1);
     }
     if (total_cells >= (1LL << 31) - 2) return fail(c, LB200_ERR_UNSUPPORTED, "batch too large (%lld band cells); split it", total_cells);
@@ -480,7 +480,15 @@ static int upload_chunk(lb200_ctx *c, int p0, int p1) {
     const bool sl = c->params.struct_local;
     if (sl && ncmax > 4) return fail(c, LB200_ERR_UNSUPPORTED, "--struct-local supports bands of up to 256 diagonals (this batch: %d)", wd_bound);
     dc.arcbuf_words = 8 * 32 * nc_inst * (sl ? 4 : 1);  // structure local: one accumulator ring per closed state
-    const int smem_bytes = (64 + dc.max_rows + 2 + dc.arcbuf_words) * 4 + dc.rowcode_bytes + dc.colcode_bytes;
+    // padded tables of the single-state sweep: row index U2 + 1 - gidx spans [-(32 nc - 2), Rn + Cn/2 + 1], column index
+    // J2 + gidx spans [-(Rn/2), Rn/2 + Cn + 32 nc]
+    dc.row_pad = 32 * nc_inst;
+    dc.row_words = dc.row_pad + max_rows + max_cols / 2 + 8;
+    dc.col_pad = max_rows / 2 + 4;
+    dc.col_bytes = (dc.col_pad + max_rows / 2 + max_cols + 32 * nc_inst + 8 + 3) & ~3;
+    const int old_region = (dc.max_rows + 2) * 4 + dc.rowcode_bytes + dc.colcode_bytes;
+    dc.region_bytes = (std::max(old_region, dc.row_words * 4 + dc.col_bytes) + 15) & ~15;  // arcbuf stays 16-byte aligned
+    const int smem_bytes = (64 + dc.arcbuf_words) * 4 + dc.region_bytes;
     if (smem_bytes > (int)c->prop.sharedMemPerBlockOptin) return fail(c, LB200_ERR_UNSUPPORTED, "problem needs %d bytes of shared memory per warp", smem_bytes);
     int ctas_per_sm = 1;
     CUDA_TRY(c, configure_kernels(nc_inst, smem_bytes, &ctas_per_sm));
@@ -520,7 +528,6 @@ static int upload_chunk(lb200_ctx *c, int p0, int p1) {
     const size_t task_cap = std::min<size_t>(total_am, (size_t)total_cells) + 1;
     CUDA_TRY(c, c->d_am.ensure(std::max<size_t>(total_am, 1) * sizeof(DevArcMatch)));
     CUDA_TRY(c, c->d_ent.ensure(std::max<size_t>(total_am, 1) * sizeof(DevEntry)));
-    CUDA_TRY(c, c->d_dval.ensure(std::max<size_t>(total_am, 1) * 4));
     CUDA_TRY(c, c->d_skeys.ensure(std::max<size_t>(total_am, 1) * 8));
     CUDA_TRY(c, c->d_skeys2.ensure(std::max<size_t>(total_am, 1) * 8));
     CUDA_TRY(c, c->d_svals.ensure(std::max<size_t>(total_am, 1) * 4));
@@ -553,7 +560,7 @@ static int upload_chunk(lb200_ctx *c, int p0, int p1) {
     CUDA_TRY(c, c->d_flag.ensure(16));
     dc.pairs = (const DevPair *)c->d_pairs.p; dc.codes = (const uint8_t *)c->d_codes.p;
     dc.band_lo = (const int *)c->d_band_lo.p; dc.band_hi = (const int *)c->d_band_hi.p; dc.sptr = (const int *)c->d_sptr.p;
-    dc.ent = (const DevEntry *)c->d_ent.p; dc.dval = (int *)c->d_dval.p; dc.am = (const DevArcMatch *)c->d_am.p;
+    dc.ent = (DevEntry *)c->d_ent.p; dc.am = (const DevArcMatch *)c->d_am.p;
     dc.tasks = (const DevTask *)c->d_tasks.p; dc.top = (DevTopResult *)c->d_top.p; dc.scratch = (int *)c->d_scratch.p;
     dc.qstart = (const int *)c->d_qstart.p; dc.cursor = (int *)c->d_cursor.p;
     dc.error_flag = (int *)c->d_flag.p;
@@ -650,7 +657,7 @@ static int run_chunk(lb200_ctx *c, int flags) {
     CUDA_TRY(c, cudaEventRecord(c->ev0, st));
     CUDA_TRY(c, cudaMemsetAsync(c->d_cursor.p, 0, 4100 * 4, st));
     CUDA_TRY(c, cudaMemsetAsync(c->d_flag.p, 0, 16, st));
-    CUDA_TRY(c, lb200_fill_i32((int *)c->d_dval.p, R.total_am, LB_NEG, st));
+    CUDA_TRY(c, lb200_reset_d((DevEntry *)c->d_ent.p, R.total_am, st));
     int64_t launches = 1;
     for (int q = R.q_lo; q <= R.q_hi; q++) {
         if (c->params.struct_local) launch_dfill_sl(dc, R.grid_cap, R.smem_bytes, q, st);
@@ -763,7 +770,7 @@ int lb200_pair_arcmatches(const lb200_ctx *cc, int pair, int *al, int *ar, int *
     if (!c || pair < 0 || pair >= (int)c->pairs.size()) return LB200_ERR_ARG;
     const PairRec &r = c->pairs[pair];
     std::vector<DevArcMatch> am;
-    std::vector<int> dvals;
+    std::vector<DevEntry> dvals;
     if (c->device == LB200_DEVICE_NONE) {
         if (!r.built) return LB200_ERR_STATE;
         if (D) return fail(c, LB200_ERR_STATE, "no D table on a host-only context");
@@ -774,7 +781,7 @@ int lb200_pair_arcmatches(const lb200_ctx *cc, int pair, int *al, int *ar, int *
         am.resize(r.K); dvals.resize(r.K);
         if (r.K) {
             CUDA_TRY(c, cudaMemcpy(am.data(), (const DevArcMatch *)c->d_am.p + r.am_base, (size_t)r.K * sizeof(DevArcMatch), cudaMemcpyDeviceToHost));
-            CUDA_TRY(c, cudaMemcpy(dvals.data(), (const int *)c->d_dval.p + r.am_base, (size_t)r.K * 4, cudaMemcpyDeviceToHost));
+            if (D) CUDA_TRY(c, cudaMemcpy(dvals.data(), (const DevEntry *)c->d_ent.p + r.am_base, (size_t)r.K * sizeof(DevEntry), cudaMemcpyDeviceToHost));
         }
     }
     const size_t K = am.size();
@@ -797,7 +804,7 @@ int lb200_pair_arcmatches(const lb200_ctx *cc, int pair, int *al, int *ar, int *
         if (bl) bl[k] = x.ends_b & 0xfff;
         if (br) br[k] = x.ends_b >> 12;
         if (score) score[k] = x.score;
-        if (D) { const int d = dvals[x.spos]; D[k] = d < LB_NEG_LIMIT ? LB200_SCORE_NEG_INF : d; }
+        if (D) { const int d = dvals[x.spos].d; D[k] = d < LB_NEG_LIMIT ? LB200_SCORE_NEG_INF : d; }
     }
     return LB200_OK;
 }
@@ -816,12 +823,12 @@ int lb200_pair_alignment(const lb200_ctx *c, int pair, int *ea, int *eb, char *s
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------------
-__global__ void fill_i32_kernel(int *p, size_t n, int v) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+__global__ void reset_d_kernel(DevEntry *ent, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) ent[i].d = LB_NEG;
 }
-cudaError_t lb200_fill_i32(int *p, size_t n, int v, cudaStream_t st) {
+cudaError_t lb200_reset_d(DevEntry *ent, size_t n, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     const int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
-    fill_i32_kernel<<<grid, 256, 0, st>>>(p, n, v);
+    reset_d_kernel<<<grid, 256, 0, st>>>(ent, n);
     return cudaGetLastError();
 }
