@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(128) enumerate_kernel(BuildCtx b) {
                         x.score = arcmatch_score(b, v, a, bb, al, ar, bl, br);
                         x.spos = -1; x.inner = -1;
                         b.am[g + k] = x;
-                        b.skeys[g + k] = ((unsigned long long)blockIdx.x << 25) | ((unsigned long long)(ar + br) << 12) | (unsigned long long)ar;
+                        // S-order: target anti-diagonal ascending, source anti-diagonal (al-1)+(bl-1) descending (see kernels.cu Stream3)
+                        b.skeys[g + k] = ((unsigned long long)blockIdx.x << 26) | ((unsigned long long)(ar + br) << 13) | (unsigned long long)(8191 - (al + bl - 2));
                         b.svals[g + k] = (unsigned)(g + k - p.am_base);
                         atomicAdd(&b.sptr[p.sptr + ar + br + 1], 1);
                     }
@@ -175,7 +176,7 @@ __global__ void sptr_scan_kernel(BuildCtx b, int n_pairs) {
 // S-order entries and back pointers from the sorted (key, L-order index) pairs
 __global__ void scatter_kernel(BuildCtx b, long long total) {
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int pk = (int)(b.skeys_sorted[t] >> 25);
+        const int pk = (int)(b.skeys_sorted[t] >> 26);
         const DevPair &p = b.pairs[pk];
         const long long g = p.am_base + b.svals_sorted[t];
         const DevArcMatch x = b.am[g];
@@ -183,7 +184,7 @@ __global__ void scatter_kernel(BuildCtx b, long long total) {
         e.x = ((x.ends_a & 0xfff) - 1) | (((x.ends_b & 0xfff) - 1) << 16);
         e.y = (x.ends_a >> 12) | ((x.ends_b >> 12) << 16);
         e.d = LB_NEG;
-        e.s = (int)(x.ends_a >> 12) + (int)(x.ends_b >> 12);
+        e.s = (int)(x.ends_a & 0xfff) + (int)(x.ends_b & 0xfff) - 2;
         b.ent[t] = e;
         b.am[g].spos = (int)(t - p.am_base);
     }
@@ -287,7 +288,7 @@ size_t builder_sort_tmp_bytes(long long total_am, int n_pairs) {
     int pair_bits = 1;
     while ((1 << pair_bits) < n_pairs) pair_bits++;
     cub::DeviceRadixSort::SortPairs(nullptr, a, (const unsigned long long *)nullptr, (unsigned long long *)nullptr, (const unsigned *)nullptr,
-                                    (unsigned *)nullptr, total_am, 0, 25 + pair_bits);
+                                    (unsigned *)nullptr, total_am, 0, 26 + pair_bits);
     cub::DeviceRadixSort::SortPairs(nullptr, c, (const unsigned *)nullptr, (unsigned *)nullptr, (const unsigned *)nullptr, (unsigned *)nullptr,
                                     total_am, 0, 32);
     return a > c ? a : c;
@@ -304,7 +305,7 @@ cudaError_t builder_fill(const BuildCtx &b, int n_pairs, long long total_am, lon
         int pair_bits = 1;
         while ((1 << pair_bits) < n_pairs) pair_bits++;
         size_t need = tmp_bytes;
-        TRY(cub::DeviceRadixSort::SortPairs(tmp, need, b.skeys, b.skeys_sorted, b.svals, b.svals_sorted, total_am, 0, 25 + pair_bits, st));
+        TRY(cub::DeviceRadixSort::SortPairs(tmp, need, b.skeys, b.skeys_sorted, b.svals, b.svals_sorted, total_am, 0, 26 + pair_bits, st));
         const int grid = (int)((total_am + 255) / 256 < 148 * 16 ? (total_am + 255) / 256 : 148 * 16);
         scatter_kernel<<<grid, 256, 0, st>>>(b, total_am);
     }

@@ -48,11 +48,11 @@ struct DevPairStats {
     long long pad;
 };
 
-// S-order entry (16 bytes, one LDG.128): one valid arc match, sorted by (ar+br, ar, al desc, bl desc)
+// S-order entry (16 bytes, one LDG.128): one valid arc match, sorted by (ar+br ascending, (al-1)+(bl-1) descending)
 //   x = (al-1) | (bl-1) << 16         source cell of the recurrence M(al-1, bl-1) + D
 //   y = ar | br << 16                 target cell
 //   d = D(arcA, arcB)                 written by the D-fill task of the left ends (al, bl); -inf until then
-//   s = ar + br                       anti-diagonal of the target cell
+//   s = (al-1) + (bl-1)               anti-diagonal of the source cell
 struct DevEntry { uint32_t x, y; int d; int s; };
 #define LB_ENT_LO(v) ((int)((v) & 0xffffu))
 #define LB_ENT_HI(v) ((int)((v) >> 16))

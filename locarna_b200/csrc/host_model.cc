@@ -404,7 +404,8 @@ void build_pair_problem(const Sequence &A, const Sequence &B, const Band &band, 
         const int ax = out.am[x].ends_a >> 12, ay = out.am[y].ends_a >> 12;
         const int sx = ax + (int)(out.am[x].ends_b >> 12), sy = ay + (int)(out.am[y].ends_b >> 12);
         if (sx != sy) return sx < sy;
-        return ax < ay;
+        const int px = (int)(out.am[x].ends_a & 0xfff) + (int)(out.am[x].ends_b & 0xfff), py = (int)(out.am[y].ends_a & 0xfff) + (int)(out.am[y].ends_b & 0xfff);
+        return px > py;   // source anti-diagonal descending (kernels.cu Stream3)
     });
     out.ent.resize(K);
     out.sptr.assign(n + m + 3, 0);
@@ -415,7 +416,7 @@ void build_pair_problem(const Sequence &A, const Sequence &B, const Band &band, 
         out.ent[s].x = (uint32_t)(al - 1) | ((uint32_t)(bl - 1) << 16);
         out.ent[s].y = (uint32_t)ar | ((uint32_t)br << 16);
         out.ent[s].d = LB_NEG;
-        out.ent[s].s = ar + br;
+        out.ent[s].s = al + bl - 2;
         out.sptr[ar + br + 1]++;
     }
     for (int s = 0; s + 1 < (int)out.sptr.size(); s++) out.sptr[s + 1] += out.sptr[s];

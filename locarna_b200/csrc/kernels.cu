@@ -255,58 +255,36 @@ __device__ __forceinline__ void dp_step2(Sweep<NC> &S, const BoxInit &init, cons
     }
 }
 
-// The arc-match entry stream of one box: the pair's S-order entries (sorted by the anti-diagonal of their right ends) are
-// consumed in aligned blocks of 32 (one 16-byte entry per lane, LDG.128, prefetched one block ahead). A block is processed
-// when its first unconsumed entry is needed within two steps; lanes whose sources are not final yet (target anti-diagonal
-// > u + 8; sources lie >= 8 anti-diagonals before the target because both arcs span >= 3 positions) stay for a later pass.
-// The M(source) gather of a processed block stays in flight across the next cell step and is folded into the ring of
-// per-anti-diagonal accumulators with a shared-memory atomicMax afterwards.
-struct Stream2 {
+// The arc-match entry stream of one box. The pair's S-order entries are sorted by the anti-diagonal t of their right ends and,
+// inside one anti-diagonal, by the anti-diagonal of their source cell M(al'-1, bl'-1) DESCENDING. A box with origin anti-diagonal
+// s0 can only use entries whose source lies at or after s0, i.e. a prefix of every anti-diagonal's list - entries of long arcs that
+// start before the box are never touched. Per cell step u the warp handles the list of target anti-diagonal u + 2: one 16-byte
+// entry per lane (LDG.128, prefetched during the previous step), box filter, M(source) gather left in flight across the next
+// cell step, then folded into the ring of per-anti-diagonal accumulators with a shared-memory atomicMax (sources lie >= 8
+// anti-diagonals before their target because both arcs span >= 3 positions, so they are final). Lists whose prefix is longer
+// than 32 entries continue with further (unprefetched) blocks.
+struct Stream3 {
     const uint4 *base;       // the pair's entries
-    int blk;                 // block held in cur
-    int e_begin, e_end;      // entry range of the box (targets on local anti-diagonals 8..umax)
-    uint32_t cx, cy; int cd; // current block: entry of this lane
-    int cs;                  // its target anti-diagonal (absolute), INT_MAX once consumed / out of range
-    uint4 nx;                // prefetched block blk + 1
-    int first;               // min cs over the warp
+    const int *q;            // q[k] = S-order start of local anti-diagonal k (sptr + s0)
+    int q_cap;               // largest valid index into q
+    int qa, qb, qc;          // q[t], q[t+1], q[t+2] for the list handled next
+    uint4 nx;                // prefetched: entry qa + lane
     int pm0, pd0, ps0, pm1, pd1, ps1;   // two gathers in flight: M(source), D, accumulator index (-1: none)
 };
 
-__device__ __forceinline__ uint4 stream_load(const Stream2 &st, int b, int lane) {
-    const int e = b * 32 + lane;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (e < st.e_end) v = __ldg(st.base + e);
-    return v;
-}
-
-__device__ __forceinline__ void stream_take(Stream2 &st, uint4 v, int lane) {
-    st.cx = v.x; st.cy = v.y; st.cd = (int)v.z;
-    const int e = st.blk * 32 + lane;
-    st.cs = (e >= st.e_begin && e < st.e_end) ? (int)v.w : 0x7fffffff;
-    st.first = __reduce_min_sync(0xffffffffu, st.cs);
-}
-
-// process the current block at step u: returns the gather of this lane (slot < 0: none)
+// filter one block of the list of target anti-diagonal t and start the gathers; returns whether lane 31 still belongs to the prefix
 template <int NC>
-__device__ __forceinline__ void stream_process(Stream2 &st, const BoxGeom &g, const int *box, int s_allow, uint32_t org, uint32_t lim, int d0,
-                                               int lane, int &pm, int &pd, int &ps) {
-    constexpr int NWP = RingStride<NC>::v;
-    const bool allowed = st.cs <= s_allow;
-    const uint32_t t1 = st.cx - org, t2 = lim - st.cy;
+__device__ __forceinline__ bool stream_block(const uint4 v, bool valid, const BoxGeom &g, const int *box, int ring_t, int s0, uint32_t org,
+                                             uint32_t lim, int d0, int &pm, int &pd, int &ps) {
+    const uint32_t t1 = v.x - org, t2 = lim - v.y;
     ps = -1;
-    if (allowed && ((t1 | t2) & 0x80008000u) == 0) {
+    if (valid && ((t1 | t2) & 0x80008000u) == 0) {
         const int p = LB_ENT_LO(t1), q = LB_ENT_HI(t1);
-        pm = box[(p + q) * g.nslots + ((q - p - g.vmin) >> 1)];
-        pd = st.cd;
-        ps = (st.cs & (RING - 1)) * NWP + ((LB_ENT_HI(st.cy) - LB_ENT_LO(st.cy) - d0) >> 1);
+        pm = __ldcg(box + (p + q) * g.nslots + ((q - p - g.vmin) >> 1));
+        pd = (int)v.z;
+        ps = ring_t + ((LB_ENT_HI(v.y) - LB_ENT_LO(v.y) - d0) >> 1);
     }
-    if (allowed) st.cs = 0x7fffffff;
-    st.first = __reduce_min_sync(0xffffffffu, st.cs);
-    if (st.first == 0x7fffffff && st.blk * 32 + 32 < st.e_end) {   // block exhausted: rotate
-        st.blk += 1;
-        stream_take(st, st.nx, lane);
-        st.nx = stream_load(st, st.blk + 1, lane);
-    }
+    return (__ballot_sync(0xffffffffu, valid && (int)v.w >= s0) >> 31) != 0;
 }
 
 // Fill one M box. NC = diagonal pairs per lane (the warp covers 64*NC diagonals).
@@ -320,19 +298,16 @@ __device__ void fill_box(const DevCtx &c, const DevPair &pr, const BoxGeom &g, c
     for (int k = lane; k < RING * NWP; k += 32) ws.arcbuf[k] = LB_NEG;
 
     const int s0 = g.al + g.bl;
-    Stream2 st;
-    {
-        const int *sptr = c.sptr + pr.sptr;
-        const int s_last = pr.lenA + pr.lenB + 1;
-        // right ends of arc matches inside the box lie on local anti-diagonals 8..umax
-        st.e_begin = __ldg(sptr + min(s0 + min(8, g.umax + 1), s_last));
-        st.e_end = __ldg(sptr + min(s0 + g.umax + 1, s_last));
-        st.base = (const uint4 *)(c.ent + pr.am_base);
-        st.blk = st.e_begin >> 5;
-        st.ps0 = -1; st.ps1 = -1; st.pm0 = st.pm1 = st.pd0 = st.pd1 = 0;
-        stream_take(st, stream_load(st, st.blk, lane), lane);
-        st.nx = stream_load(st, st.blk + 1, lane);
-    }
+    Stream3 st;
+    st.base = (const uint4 *)(c.ent + pr.am_base);
+    st.q = c.sptr + pr.sptr + s0;
+    st.q_cap = pr.lenA + pr.lenB + 2 - s0;
+    auto qld = [&](int k) { return __ldg(st.q + min(k, st.q_cap)); };
+    auto eld = [&](int e, int e_end) { uint4 v = make_uint4(0, 0, 0, 0); if (e < e_end) v = __ldg(st.base + e); return v; };
+    // the first list handled (after cell step 1) is the one of local anti-diagonal 3
+    st.qa = qld(3); st.qb = qld(4); st.qc = qld(5);
+    st.nx = eld(st.qa + lane, st.qb);
+    st.ps0 = -1; st.ps1 = -1; st.pm0 = st.pm1 = st.pd0 = st.pd1 = 0;
     const uint32_t org = (uint32_t)g.al | ((uint32_t)g.bl << 16);
     const uint32_t lim = (uint32_t)(g.al + g.Rn) | ((uint32_t)(g.bl + g.Cn) << 16);
     const int d0 = g.bl - g.al + g.vmin;
@@ -366,22 +341,22 @@ __device__ void fill_box(const DevCtx &c, const DevPair &pr, const BoxGeom &g, c
     __syncwarp();
 
     int ringoff = ((s0 + 1) & (RING - 1)) * NWP;
-    auto land = [&]() {
-        if (st.ps0 >= 0) atomicMax(&ws.arcbuf[st.ps0], st.pm0 + st.pd0);
-        if (st.ps1 >= 0) atomicMax(&ws.arcbuf[st.ps1], st.pm1 + st.pd1);
-        st.ps0 = -1; st.ps1 = -1;
-    };
+    // after cell step u: land the gathers of the previous step, handle the list of anti-diagonal u + 2, prefetch the next one
     auto stream = [&](int u) {
         __syncwarp();
-        land();   // gathers issued during the previous step
-        const int s_need = s0 + u + 2, s_allow = s0 + u + 8;
-        while (st.first <= s_need) {
-            if (st.ps0 >= 0) { atomicMax(&ws.arcbuf[st.ps0], st.pm0 + st.pd0); }
-            stream_process<NC>(st, g, box, s_allow, org, lim, d0, lane, st.pm0, st.pd0, st.ps0);
-            if (st.first > s_need) break;
-            if (st.ps1 >= 0) { atomicMax(&ws.arcbuf[st.ps1], st.pm1 + st.pd1); }
-            stream_process<NC>(st, g, box, s_allow, org, lim, d0, lane, st.pm1, st.pd1, st.ps1);
+        if (st.ps0 >= 0) atomicMax(&ws.arcbuf[st.ps0], st.pm0 + st.pd0);
+        if (st.ps1 >= 0) atomicMax(&ws.arcbuf[st.ps1], st.pm1 + st.pd1);
+        st.ps1 = -1;
+        const int ring_t = ((s0 + u + 2) & (RING - 1)) * NWP;
+        bool more = stream_block<NC>(st.nx, st.qa + lane < st.qb, g, box, ring_t, s0, org, lim, d0, st.pm0, st.pd0, st.ps0);
+        for (int e = st.qa + 32; more && e < st.qb; e += 32) {   // prefix longer than one block (unprefetched)
+            const uint4 v = eld(e + lane, st.qb);
+            if (st.ps1 >= 0) atomicMax(&ws.arcbuf[st.ps1], st.pm1 + st.pd1);
+            more = stream_block<NC>(v, e + lane < st.qb, g, box, ring_t, s0, org, lim, d0, st.pm1, st.pd1, st.ps1);
         }
+        st.qa = st.qb; st.qb = st.qc;
+        st.nx = eld(st.qa + lane, st.qb);
+        st.qc = qld(u + 5);
         __syncwarp();
     };
     int u = 1;
@@ -924,17 +899,19 @@ __global__ void __launch_bounds__(32) trace_kernel(DevCtx c, int pair_begin, int
                 if (!vdiag) break;                                                           // :1176-1178
                 // arc matches with right ends (i, j), in common_right_end_list order (:1186-1228)
                 const int e0 = sptr[i + j], e1 = sptr[i + j + 1];
-                int found = -1;
-                for (int base = e0; base < e1 && found < 0; base += 32) {
+                // the first hit in common_right_end_list order = the hit with the largest (al, bl) (arc_matches.hh:188-220);
+                // the S-order inside an anti-diagonal is by source anti-diagonal, so all candidates are inspected
+                int found = -1, fkey = -1;
+                for (int base = e0; base < e1; base += 32) {
                     const int e = base + lane;
-                    bool hit = false;
+                    int key = -1;
                     if (e < e1) {
                         const DevEntry en = ent[e];
                         const int p = LB_ENT_LO(en.x), q = LB_ENT_HI(en.x);
-                        if (LB_ENT_LO(en.y) == i && p >= al && q >= bl) hit = (mij == box_get(box, g, p - al, q - bl) + en.d);
+                        if (LB_ENT_LO(en.y) == i && p >= al && q >= bl && mij == box_get(box, g, p - al, q - bl) + en.d) key = (p << 16) | q;
                     }
-                    const unsigned b = __ballot_sync(0xffffffffu, hit);
-                    if (b) found = base + __ffs(b) - 1;
+                    const int best = __reduce_max_sync(0xffffffffu, key);
+                    if (best > fkey) { fkey = best; found = base + __ffs(__ballot_sync(0xffffffffu, key == best)) - 1; }
                 }
                 if (found < 0) { if (lane == 0) atomicExch(c.error_flag, 4); break; }
                 const DevEntry en = ent[found];
@@ -1099,17 +1076,17 @@ __global__ void __launch_bounds__(32) trace_sl_kernel(DevCtx c, int pair_begin, 
                 if (moved) continue;
                 if (!vdiag) break;
                 const int e0 = sptr[i + j], e1 = sptr[i + j + 1];
-                int found = -1;
-                for (int base = e0; base < e1 && found < 0; base += 32) {
+                int found = -1, fkey = -1;   // hit with the largest (al, bl), see trace_kernel
+                for (int base = e0; base < e1; base += 32) {
                     const int e = base + lane;
-                    bool hit = false;
+                    int key = -1;
                     if (e < e1) {
                         const DevEntry en = ent[e];
                         const int p = LB_ENT_LO(en.x), q = LB_ENT_HI(en.x);
-                        if (LB_ENT_LO(en.y) == i && p >= al && q >= bl) hit = (mij == B(st, p, q) + en.d);
+                        if (LB_ENT_LO(en.y) == i && p >= al && q >= bl && mij == B(st, p, q) + en.d) key = (p << 16) | q;
                     }
-                    const unsigned bm = __ballot_sync(0xffffffffu, hit);
-                    if (bm) found = base + __ffs(bm) - 1;
+                    const int best = __reduce_max_sync(0xffffffffu, key);
+                    if (best > fkey) { fkey = best; found = base + __ffs(__ballot_sync(0xffffffffu, key == best)) - 1; }
                 }
                 if (found < 0) { if (lane == 0) atomicExch(c.error_flag, 4); break; }
                 const DevEntry en = ent[found];
