@@ -267,7 +267,7 @@ struct Stream3 {
     const uint4 *base;       // the pair's entries
     const int *q;            // q[k] = S-order start of local anti-diagonal k (sptr + s0)
     int q_cap;               // largest valid index into q
-    int qa, qb, qc;          // q[t], q[t+1], q[t+2] for the list handled next
+    int qa, qb, qc, qd;      // q[t], q[t+1], q[t+2], q[t+3] for the list handled next (loaded two steps ahead of their use)
     uint4 nx;                // prefetched: entry qa + lane
     int pm0, pd0, ps0, pm1, pd1, ps1;   // two gathers in flight: M(source), D, accumulator index (-1: none)
 };
@@ -305,7 +305,7 @@ __device__ void fill_box(const DevCtx &c, const DevPair &pr, const BoxGeom &g, c
     auto qld = [&](int k) { return __ldg(st.q + min(k, st.q_cap)); };
     auto eld = [&](int e, int e_end) { uint4 v = make_uint4(0, 0, 0, 0); if (e < e_end) v = __ldg(st.base + e); return v; };
     // the first list handled (after cell step 1) is the one of local anti-diagonal 3
-    st.qa = qld(3); st.qb = qld(4); st.qc = qld(5);
+    st.qa = qld(3); st.qb = qld(4); st.qc = qld(5); st.qd = qld(6);
     st.nx = eld(st.qa + lane, st.qb);
     st.ps0 = -1; st.ps1 = -1; st.pm0 = st.pm1 = st.pd0 = st.pd1 = 0;
     const uint32_t org = (uint32_t)g.al | ((uint32_t)g.bl << 16);
@@ -356,7 +356,8 @@ __device__ void fill_box(const DevCtx &c, const DevPair &pr, const BoxGeom &g, c
         }
         st.qa = st.qb; st.qb = st.qc;
         st.nx = eld(st.qa + lane, st.qb);
-        st.qc = qld(u + 5);
+        st.qc = st.qd;
+        st.qd = qld(u + 6);
         __syncwarp();
     };
     int u = 1;

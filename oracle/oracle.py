@@ -65,6 +65,9 @@ def lib():
         _lib.locarna_port_align.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(Params), C.POINTER(Result), C.c_char_p, C.c_int]
         _lib.locarna_port_align.restype = C.c_int
         _lib.locarna_port_free.argtypes = [C.POINTER(Result)]
+        _lib.locarna_port_inside_p.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(Params), C.c_double, C.POINTER(C.c_double),
+                                               C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.c_long), C.c_char_p, C.c_int]
+        _lib.locarna_port_inside_p.restype = C.c_int
     return _lib
 
 
@@ -134,6 +137,24 @@ def port_align(ppA: str, ppB: str, flags: dict | None = None, do_trace: bool = T
         return _res_to_dict(r, setup_only, do_trace)
     finally:
         lib().locarna_port_free(C.byref(r))
+
+
+def port_inside_p(ppA: str, ppB: str, flags: dict | None = None, pf_scale: float = 1.0) -> dict:
+    """LocARNA-P inside by the CPU restatement (T = double): partition function Z and the inside value of every arc match
+    (reference index order). ``flags`` as for port_align; locarna_p's own defaults differ from locarna's in
+    min-trace-probability (1e-5) and the envelope precision (pf-double) - pass them explicitly."""
+    p = make_params(flags, False, False)
+    Z = C.c_double()
+    D = C.POINTER(C.c_double)()
+    n = C.c_long()
+    err = C.create_string_buffer(512)
+    rc = lib().locarna_port_inside_p(ppA.encode(), ppB.encode(), C.byref(p), pf_scale, C.byref(Z), C.byref(D), C.byref(n), err, 512)
+    if rc != 0:
+        raise RuntimeError("oracle port: " + err.value.decode())
+    try:
+        return {"Z": Z.value, "D": [D[k] for k in range(n.value)]}
+    finally:
+        C.CDLL(None).free(D)
 
 
 def flags_to_argv(flags: dict | None) -> list:
@@ -213,6 +234,22 @@ def parse_harness(text: str) -> list:
             cur["struct" + k[-1]] = t[1] if len(t) > 1 else ""
         elif k in ("ROWA", "ROWB"):
             cur["row" + k[-1]] = t[1] if len(t) > 1 else ""
+        elif k == "PF":
+            cur["Z"] = float(t[1])
+        elif k == "PFD":
+            n = int(t[1])
+            cur["pfD"] = [float(lines[i + r]) for r in range(n)]
+            i += n
+        elif k == "AMPROBS":
+            n = int(t[1])
+            cur["am_probs"] = [tuple(int(x) for x in lines[i + r].split()[:4]) + (float(lines[i + r].split()[4]),) for r in range(n)]
+            i += n
+        elif k == "BMPROBS":
+            n = int(t[1])
+            cur["bm_probs"] = [(int(lines[i + r].split()[0]), int(lines[i + r].split()[1]), float(lines[i + r].split()[2])) for r in range(n)]
+            i += n
+        elif k in ("TIMEPF_INSIDE", "TIMEPF_OUTSIDE"):
+            cur.setdefault("time_pf_ms", {})[k[7:].lower()] = float(t[1])
         elif k == "TIME":
             cur["time_ms"] = {t[j]: float(t[j + 1]) for j in range(1, len(t), 2)}
         elif k == "END":
@@ -226,6 +263,19 @@ def ref_align(ppA: str, ppB: str, flags: dict | None = None, dump: str = "arcs,b
     argv = [REF_HARNESS] + flags_to_argv(flags) + ["--dump", dump]
     if not do_trace:
         argv.append("--no-trace")
+    if timing:
+        argv.append("--time")
+    argv += [ppA, ppB]
+    r = subprocess.run(argv, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("ref_harness failed: " + r.stderr)
+    return parse_harness(r.stdout)[0]
+
+
+def ref_inside_p(ppA: str, ppB: str, flags: dict | None = None, pf_scale: float = 1.0, probs: bool = False, timing: bool = False) -> dict:
+    """LocARNA-P by the compiled reference (AlignerP<double> through ref_harness --pf): Z, inside table, optionally the
+    arc-match / base-match probabilities (outside + probability passes)."""
+    argv = [REF_HARNESS] + flags_to_argv(flags) + ["--dump", "am,D", "--no-trace", "--pf-probs" if probs else "--pf", "--pf-scale", repr(pf_scale)]
     if timing:
         argv.append("--time")
     argv += [ppA, ppB]

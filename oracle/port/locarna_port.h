@@ -45,6 +45,9 @@ typedef struct LocarnaPortResult {
 void locarna_port_default_params(LocarnaPortParams *p);
 int locarna_port_align(const char *ppA, const char *ppB, const LocarnaPortParams *p, LocarnaPortResult *res, char *err, int errlen);
 void locarna_port_free(LocarnaPortResult *r);
+/* LocARNA-P inside (aligner_p.icc:148-438, T = double): Z and one inside value per arc match (malloc'ed, free()) */
+int locarna_port_inside_p(const char *ppA, const char *ppB, const LocarnaPortParams *p, double pf_scale, double *Z, double **D, long *n_am,
+                          char *err, int errlen);
 
 #ifdef __cplusplus
 }

@@ -27,6 +27,7 @@
 #include "LocARNA/alignment.hh"
 #include "LocARNA/aligner.hh"
 #include "LocARNA/aligner_impl.hh"
+#include "LocARNA/aligner_p.hh"
 #include "LocARNA/rna_data.hh"
 #include "LocARNA/arc_matches.hh"
 #include "LocARNA/edge_probs.hh"
@@ -49,6 +50,12 @@ struct ScoringPeek : public Scoring {
     score_t wB(size_t k) const { return weightsB[k]; }
 };
 
+// read access to AlignerP's protected inside table (aligner_p.hh:68ff)
+struct AlignerPPeek : public AlignerP<double> {
+    using AlignerP<double>::AlignerP;
+    double Dval(const ArcMatch &x) const { return Dmat(x.arcA().idx(), x.arcB().idx()); }
+};
+
 struct Opts {
     double min_prob = 0.001;
     int max_diff_am = -1, max_diff_at_am = -1, max_diff = -1;
@@ -58,6 +65,8 @@ struct Opts {
     int struct_weight = 200, indel = -150, indel_opening = -750, tau = 50, exclusion = 0;
     int match = 50, mismatch = 0, temperature_alipf = 300, unpaired_penalty = 0;
     bool do_trace = true, timing = false, pf_double = false;
+    bool pf = false, pf_probs = false;  // LocARNA-P: inside partition function (+ D), outside + probabilities
+    double pf_scale = 1.0, min_am_prob = 0.001, min_bm_prob = 0.001;
     std::string dump;  // comma list: arcs,band,am,D,aln,tables
     std::string pairs_file;
     std::vector<std::string> files;
@@ -204,6 +213,40 @@ static int run_pair(const Opts &o, const std::string &fA, const std::string &fB,
         }
     }
     out << "SCORE "; print_score(out, score); out << "\n";
+    if (o.pf) {
+        // same object pipeline as locarna_p.cc:441-526 (PFScoring<double>, AlignerP<double>)
+        double tp0 = now_ms();
+        PFScoring<double> pfs(seqA, seqB, *rA, *rB, am, nullptr, sp);
+        using app_t = AlignerPParams<double>;
+        AlignerPPeek ap2(app_t(AlignerParams::seqA(&seqA), AlignerParams::seqB(&seqB), AlignerParams::scoring(&pfs),
+                               AlignerParams::max_diff_am(o.max_diff_am), AlignerParams::max_diff_at_am(o.max_diff_at_am),
+                               AlignerParams::trace_controller(&tc), AlignerParams::constraints(&constraints),
+                               app_t::min_am_prob(o.min_am_prob), app_t::min_bm_prob(o.min_bm_prob), app_t::pf_scale(o.pf_scale)));
+        const double Z = ap2.align_inside();
+        double tp1 = now_ms();
+        char buf[64];
+        snprintf(buf, sizeof buf, "%.17g", Z);
+        out << "PF " << buf << "\n";
+        if (o.want("D")) {
+            out << "PFD " << am.num_arc_matches() << "\n";
+            for (size_t k = 0; k < am.num_arc_matches(); ++k) { snprintf(buf, sizeof buf, "%.17g", ap2.Dval(am.arcmatch(k))); out << buf << "\n"; }
+        }
+        if (o.pf_probs) {
+            ap2.align_outside();
+            ap2.compute_arcmatch_probabilities();
+            ap2.compute_basematch_probabilities(false);
+            double tp2 = now_ms();
+            std::ostringstream sa, sb;
+            sa.precision(17); sb.precision(17);
+            ap2.write_arcmatch_probabilities(sa);
+            ap2.write_basematch_probabilities(sb);
+            auto count = [](const std::string &t) { size_t n = 0; for (char ch : t) n += ch == '\n'; return n; };
+            out << "AMPROBS " << count(sa.str()) << "\n" << sa.str();
+            out << "BMPROBS " << count(sb.str()) << "\n" << sb.str();
+            if (o.timing) { snprintf(buf, sizeof buf, "%.3f", tp2 - tp1); out << "TIMEPF_OUTSIDE " << buf << "\n"; }
+        }
+        if (o.timing) { snprintf(buf, sizeof buf, "%.3f", tp1 - tp0); out << "TIMEPF_INSIDE " << buf << "\n"; }
+    }
     if (o.do_trace && o.want("aln")) {
         const Alignment &al = impl.alignment_;
         auto edges = al.alignment_edges(false);
@@ -256,6 +299,11 @@ int main(int argc, char **argv) {
         else if (a == "--no-ribosum") o.use_ribosum = false;
         else if (a == "--pf-double") o.pf_double = true;
         else if (a == "--no-trace") o.do_trace = false;
+        else if (a == "--pf") o.pf = true;
+        else if (a == "--pf-probs") { o.pf = true; o.pf_probs = true; }
+        else if (a == "--pf-scale") o.pf_scale = atof(nxt());
+        else if (a == "--min-am-prob") o.min_am_prob = atof(nxt());
+        else if (a == "--min-bm-prob") o.min_bm_prob = atof(nxt());
         else if (a == "--time") o.timing = true;
         else if (a == "--dump") o.dump = nxt();
         else if (a == "--pairs") o.pairs_file = nxt();
