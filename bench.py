@@ -250,7 +250,8 @@ def main():
     for sp in my_steps:
         ctx = new_ctx(sp)
         ctx.upload()
-        resident_bytes = max(resident_bytes, ctx.h2d_bytes)
+        # S-order entry 16 B + L-order record 20 B per arc match, 20 B per D-fill task (built on the device, dev_types.h)
+        resident_bytes = max(resident_bytes, sum(36 * ctx.info(k).n_arcmatches + 20 * ctx.info(k).n_tasks for k in range(len(sp))))
         ctxs.append(ctx)
     prep_s = time.time() - t0
     for s in range(W):
@@ -342,7 +343,9 @@ def main():
         peak_src = "measured" if "hbm_gbs" in peaks else "fallback"
         # dominant kernel = dfill_kernel; figures per launch (rank 0), DESIGN.md "roofline"
         alg_bytes = 8 * arcs + 8 * rows + 12 * am + 16 * K * B
-        ops = 9 * cells + 2 * terms
+        # SURVEY 8d R1 counts 9 int ops per cell update + 2 per arc-match term. The kernel folds only the entries whose source lies in
+        # the box (a prefix of each anti-diagonal's list) and does not tally them, so the term part is left out: a conservative count.
+        ops = 9 * cells
         dfill_s = dfill_ms / 1e3
         sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
         alu_peak = 148 * 128 * sm_mhz * 1e6
@@ -356,7 +359,7 @@ def main():
                     "launch_ms": dfill_ms / max(1, dfill_launches), "peak_source": peak_src,
                     "note": "max-plus DP: the binding roof is integer ALU issue, see roofline_alu"}
         roofline_alu = {"bound": "int_alu", "achieved": ops / dfill_s / 1e12, "peak": alu_peak / 1e12, "unit": "Tintop/s",
-                        "frac": ops / dfill_s / alu_peak, "ops": "9*cells + 2*streamed arc-match entries (SURVEY 8d R1)",
+                        "frac": ops / dfill_s / alu_peak, "ops": "9*cells (SURVEY 8d R1; the 2 ops per folded arc-match term are not counted)",
                         "gcups": cells / dfill_s / 1e9, "sm_mhz": sm_mhz}
         # bounded CPU sample of the same workload, all host cores
         n_cpu = args.cpu_sample or 2 * cores

@@ -145,6 +145,17 @@ int lb200_pair_arcmatches(const lb200_ctx *ctx, int pair, int *al, int *ar, int 
  * (lenA+1 / lenB+1 bytes incl. NUL) as in Alignment (alignment.cc:81-118). edges arrays hold n_edges items. */
 int lb200_pair_alignment(const lb200_ctx *ctx, int pair, int *edges_a, int *edges_b, char *str_a, char *str_b);
 
+/* LocARNA-P inside pass (src/locarna_p.cc:441-486; AlignerP<double>::align_inside, src/LocARNA/aligner_p.icc:148-438) for all pairs
+ * of the resident batch, in FP64 on the GPU: the partition function Z = M(lenA, lenB) and the inside value D(a,b) of every arc
+ * match. Uses the scoring parameters of the context, temperature_alipf as the Boltzmann temperature (scoring.hh:853-856) and
+ * pf_scale as in locarna_p --pf-scale. locarna_p derives its band with min_trace_probability 1e-5 and the envelope in double
+ * (pf_double = 1); set those in lb200_params for drop-in results. Not available with no_lonely_pairs / struct_local / sequ_local
+ * (AlignerP has no such modes). The outside pass and the match probabilities are not built yet. */
+int lb200_run_pf(lb200_ctx *ctx, double pf_scale);
+int lb200_pair_partition_function(const lb200_ctx *ctx, int pair, double *Z);
+/* inside values in the reference's arc-match index order (as lb200_pair_arcmatches); D holds n_arcmatches doubles */
+int lb200_pair_arcmatch_pf(const lb200_ctx *ctx, int pair, double *D);
+
 /* Guide tree of the all-vs-all stage (host): UPGMA over the symmetric score matrix (n x n, row major, diagonal 0) with the tie
  * rules of lib/perl/MLocarna/Tree.pm:181-262; writes the newick string (without the trailing ';') that mlocarna stores in
  * results/result.tree (src/Utils/mlocarna:2381-2386). */

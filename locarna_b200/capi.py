@@ -40,6 +40,7 @@ EXPORTS = [
     "lb200_seq_add_pp", "lb200_seq_add", "lb200_seq_length", "lb200_seq_get", "lb200_pair_add", "lb200_num_pairs", "lb200_clear_pairs",
     "lb200_prepare", "lb200_upload", "lb200_run", "lb200_last_kernel_ms", "lb200_last_h2d_bytes", "lb200_last_d2h_bytes", "lb200_last_dfill_ms", "lb200_last_dfill_launches", "lb200_last_launches", "lb200_envelope_stats", "lb200_pair_score", "lb200_get_scores",
     "lb200_pair_get_info", "lb200_pair_band", "lb200_pair_arcmatches", "lb200_pair_alignment", "lb200_upgma_newick",
+    "lb200_run_pf", "lb200_pair_partition_function", "lb200_pair_arcmatch_pf",
 ]
 
 _lib = None
@@ -89,6 +90,9 @@ def load():
     lib.lb200_pair_band.argtypes = [vp, C.c_int, ip, ip]
     lib.lb200_pair_arcmatches.argtypes = [vp, C.c_int, ip, ip, ip, ip, ip, i64p]
     lib.lb200_pair_alignment.argtypes = [vp, C.c_int, ip, ip, C.c_char_p, C.c_char_p]
+    lib.lb200_run_pf.argtypes = [vp, C.c_double]
+    lib.lb200_pair_partition_function.argtypes = [vp, C.c_int, dp]
+    lib.lb200_pair_arcmatch_pf.argtypes = [vp, C.c_int, dp]
     lib.lb200_upgma_newick.argtypes = [C.c_int, C.POINTER(C.c_char_p), i64p, C.c_char_p, C.c_size_t]
     _lib = lib
     return lib
@@ -242,6 +246,22 @@ class Context:
         if with_D:
             return am, score, [None if D[k] == SCORE_NEG_INF else D[k] for k in range(K)]
         return am, score
+
+    def run_pf(self, pf_scale: float = 1.0):
+        """LocARNA-P inside pass (FP64 on the GPU) for all pairs."""
+        self._chk(self.lib.lb200_run_pf(self.h, pf_scale))
+
+    def partition_function(self, pair: int) -> float:
+        z = C.c_double()
+        self._chk(self.lib.lb200_pair_partition_function(self.h, pair, C.byref(z)))
+        return z.value
+
+    def arcmatch_pf(self, pair: int):
+        """Inside values D(a,b) in the reference's arc-match index order."""
+        K = self.info(pair).n_arcmatches
+        D = (C.c_double * max(K, 1))()
+        self._chk(self.lib.lb200_pair_arcmatch_pf(self.h, pair, D))
+        return [D[k] for k in range(K)]
 
     def alignment(self, pair: int):
         inf = self.info(pair)

@@ -25,6 +25,16 @@ void launch_trace(const DevCtx &c, int ncmax, bool generic_borders, int grid, in
 cudaError_t configure_kernels(int ncmax, int smem_bytes, int *dfill_ctas_per_sm);
 void launch_dfill_sl(const DevCtx &c, int grid, int smem_bytes, int q, cudaStream_t st);
 cudaError_t configure_sl(int smem_bytes, int *ctas_per_sm);
+struct PfCtx {   // must match pf_inside.cuh
+    const double *esig; const double *bpow;
+    double g, open, inv_scale, pf_scale, temp;
+    double *dpf; double *ztop; double *scratch;
+    long long scratch_dwords;
+    int acc_doubles;
+};
+void launch_pfill(const DevCtx &c, const PfCtx &pc, int ncmax, int grid, int smem_bytes, int q, cudaStream_t st);
+void launch_ptop(const DevCtx &c, const PfCtx &pc, int ncmax, int grid, int smem_bytes, int pair_begin, int pair_end, int *cursor, cudaStream_t st);
+cudaError_t configure_pf(int ncmax, int smem_bytes, int *ctas_per_sm);
 void launch_trace_sl(const DevCtx &c, int grid, int smem_bytes, int pair_begin, int pair_end, int *cursor, cudaStream_t st);
 }  // namespace lb200
 
@@ -61,6 +71,7 @@ struct PairRec {
     // results
     int64_t score = 0; bool neg_inf = true; int max_i = 0, max_j = 0;
     std::vector<int> edges_a, edges_b; std::string str_a, str_b; bool traced = false;
+    double pf_Z = 0; bool pf_done = false;   // LocARNA-P inside
 };
 
 }  // namespace
@@ -101,11 +112,14 @@ struct lb200_ctx {
     std::vector<int> seq_prob_off;
     int64_t env_device_pairs = 0, env_host_pairs = 0;  // statistics of the last band derivation
     int env_mode = 1;  // 1: device screening + host re-check, 0: host only (LB200_ENVELOPE=host)
+    DevBuf d_pf_esig, d_pf_bpow, d_pf_d, d_pf_z, d_pf_scratch;
+    int max_box_words = 1, max_len = 1;
     DevBuf d_pairs, d_codes, d_band_lo, d_band_hi, d_sptr, d_ent, d_am, d_tasks, d_top, d_scratch, d_cursor, d_flag;
     ~lb200_ctx() {
         DevBuf *all[] = {&d_pairs, &d_codes, &d_band_lo, &d_band_hi, &d_sptr, &d_ent, &d_am, &d_tasks, &d_top, &d_scratch, &d_cursor, &d_flag,
                          &d_arc_left, &d_arc_right, &d_arc_weight, &d_lptr, &d_lcount, &d_am_seq, &d_cell_rev, &d_cell_start, &d_skeys, &d_skeys2,
                          &d_svals, &d_svals2, &d_tasks_unsorted, &d_tkeys, &d_tkeys2, &d_tvals, &d_tvals2, &d_ntasks, &d_qstart, &d_stats, &d_tmp, &d_tr_edges, &d_tr_str, &d_tr_stack,
+                         &d_pf_esig, &d_pf_bpow, &d_pf_d, &d_pf_z, &d_pf_scratch,
                          &d_pup, &d_pdown, &d_env_pairs, &d_env_lo, &d_env_hi, &d_env_olo, &d_env_ohi, &d_env_flag, &d_env_scratch};
         for (auto *b : all) b->release();
         if (ev0) cudaEventDestroy(ev0);
@@ -495,6 +509,7 @@ static int upload_chunk(lb200_ctx *c, int p0, int p1) {
     if (sl) CUDA_TRY(c, configure_sl(smem_bytes, &ctas_per_sm));
     const int grid_cap = std::max(1, ctas_per_sm) * c->prop.multiProcessorCount;
     dc.scratch_words = max_box_words * (sl ? 8 : 1);  // structure local: eight matrices per box
+    c->max_box_words = max_box_words; c->max_len = std::max(max_rows, max_cols);
 
     // ---- device builder
     CUDA_TRY(c, upload(c->d_pairs, h_pairs, st));
@@ -765,6 +780,97 @@ int lb200_pair_band(const lb200_ctx *c, int pair, int *min_col, int *max_col) {
     return LB200_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ LocARNA-P inside
+int lb200_run_pf(lb200_ctx *c, double pf_scale) {
+    if (!c) return LB200_ERR_ARG;
+    if (c->device == LB200_DEVICE_NONE) return fail(c, LB200_ERR_CUDA, "host-only context: lb200_run_pf needs a CUDA device (no CPU fallback)");
+    if (c->params.no_lonely_pairs || c->params.struct_local || c->params.sequ_local)
+        return fail(c, LB200_ERR_UNSUPPORTED, "LocARNA-P (AlignerP) has no noLP / struct-local / sequ-local mode");
+    if (!(pf_scale > 0)) return fail(c, LB200_ERR_ARG, "pf_scale must be positive");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const int P = (int)c->pairs.size();
+    if (P == 0) return LB200_OK;
+    if (!(c->res.valid && c->res.p0 == 0 && c->res.p1 == P)) {
+        const int rc = lb200_upload(c);
+        if (rc != LB200_OK) return rc;
+        if (!(c->res.valid && c->res.p0 == 0 && c->res.p1 == P))
+            return fail(c, LB200_ERR_UNSUPPORTED, "LocARNA-P needs the whole batch resident; split the pair list (LB200_CHUNK_PAIRS)");
+    }
+    lb200_ctx::Resident &R = c->res;
+    cudaStream_t st = c->stream;
+    if (R.nc_inst > 8) return fail(c, LB200_ERR_UNSUPPORTED, "LocARNA-P supports bands of up to 512 diagonals");
+    // Boltzmann weights (scoring.hh:853-931), computed with the host's libm like the reference
+    const double temp = (double)c->params.temperature_alipf;
+    std::vector<double> esig(64), bpow((size_t)c->max_len + 2);
+    for (int k = 0; k < 64; k++) esig[k] = std::exp((long)c->tables.dev.sigma8[k] / temp);
+    const double g = std::exp((long)c->tables.dev.gap / temp), open = std::exp((long)c->tables.dev.open / temp);
+    double v = open / pf_scale;                       // aligner_p.icc:156, :170
+    bpow[0] = v;
+    for (size_t k = 1; k < bpow.size(); k++) { v *= g; bpow[k] = v; }
+    CUDA_TRY(c, upload(c->d_pf_esig, esig, st));
+    CUDA_TRY(c, upload(c->d_pf_bpow, bpow, st));
+    const int smem_bytes = ((512 + (R.dc.max_rows + 2) * 4 + R.dc.rowcode_bytes + R.dc.colcode_bytes + 7) & ~7) + 32 * R.nc_inst * 8;
+    if (smem_bytes > (int)c->prop.sharedMemPerBlockOptin) return fail(c, LB200_ERR_UNSUPPORTED, "problem needs %d bytes of shared memory per warp", smem_bytes);
+    int ctas_per_sm = 1;
+    CUDA_TRY(c, configure_pf(R.nc_inst, smem_bytes, &ctas_per_sm));
+    const int grid_cap = std::max(1, ctas_per_sm) * c->prop.multiProcessorCount;
+    CUDA_TRY(c, c->d_pf_d.ensure(std::max<size_t>(R.total_am, 1) * 8));
+    CUDA_TRY(c, c->d_pf_z.ensure((size_t)P * 8));
+    CUDA_TRY(c, c->d_pf_scratch.ensure((size_t)grid_cap * c->max_box_words * 8 + 16));
+    PfCtx pc;
+    pc.esig = (const double *)c->d_pf_esig.p; pc.bpow = (const double *)c->d_pf_bpow.p;
+    pc.g = g; pc.open = open; pc.inv_scale = 1.0 / pf_scale; pc.pf_scale = pf_scale; pc.temp = temp;
+    pc.dpf = (double *)c->d_pf_d.p; pc.ztop = (double *)c->d_pf_z.p; pc.scratch = (double *)c->d_pf_scratch.p;
+    pc.scratch_dwords = c->max_box_words; pc.acc_doubles = 32 * R.nc_inst;
+    CUDA_TRY(c, cudaEventRecord(c->ev0, st));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_cursor.p, 0, 4100 * 4, st));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_flag.p, 0, 16, st));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_pf_d.p, 0, std::max<size_t>(R.total_am, 1) * 8, st));   // Dmat.fill(0), aligner_p.icc:24-26
+    int64_t launches = 0;
+    for (int q = R.q_lo; q <= R.q_hi; q++) { launch_pfill(R.dc, pc, R.nc_inst, grid_cap, smem_bytes, q, st); launches++; }
+    launch_ptop(R.dc, pc, R.nc_inst, std::min(grid_cap, P), smem_bytes, 0, P, (int *)c->d_cursor.p + 4098, st);
+    launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaEventRecord(c->ev1, st));
+    std::vector<double> z(P);
+    int h_flag[4] = {0, 0, 0, 0};
+    CUDA_TRY(c, cudaMemcpyAsync(z.data(), c->d_pf_z.p, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaMemcpyAsync(h_flag, c->d_flag.p, 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    float ms = 0;
+    CUDA_TRY(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->last_kernel_ms = ms; c->last_launches = launches; c->last_d2h_bytes = (int64_t)P * 8 + 16;
+    if (h_flag[0] != 0) return fail(c, LB200_ERR_UNSUPPORTED, "LocARNA-P kernel reported error %d (1: band too wide, 2: box exceeds scratch)", h_flag[0]);
+    for (int k = 0; k < P; k++) { c->pairs[k].pf_Z = z[k]; c->pairs[k].pf_done = true; }
+    return LB200_OK;
+}
+
+int lb200_pair_partition_function(const lb200_ctx *c, int pair, double *Z) {
+    if (!c || pair < 0 || pair >= (int)c->pairs.size() || !Z) return LB200_ERR_ARG;
+    if (!c->pairs[pair].pf_done) return LB200_ERR_STATE;
+    *Z = c->pairs[pair].pf_Z;
+    return LB200_OK;
+}
+
+static void reference_am_order(const std::vector<DevArcMatch> &am, std::vector<int> &order);
+
+int lb200_pair_arcmatch_pf(const lb200_ctx *cc, int pair, double *D) {
+    lb200_ctx *c = const_cast<lb200_ctx *>(cc);
+    if (!c || pair < 0 || pair >= (int)c->pairs.size() || !D) return LB200_ERR_ARG;
+    const PairRec &r = c->pairs[pair];
+    if (!r.pf_done || !c->res.valid || pair < c->res.p0 || pair >= c->res.p1) return fail(c, LB200_ERR_STATE, "no LocARNA-P inside table for this pair (call lb200_run_pf)");
+    std::vector<DevArcMatch> am(r.K);
+    std::vector<double> dv(r.K);
+    if (r.K) {
+        CUDA_TRY(c, cudaMemcpy(am.data(), (const DevArcMatch *)c->d_am.p + r.am_base, (size_t)r.K * sizeof(DevArcMatch), cudaMemcpyDeviceToHost));
+        CUDA_TRY(c, cudaMemcpy(dv.data(), (const double *)c->d_pf_d.p + r.am_base, (size_t)r.K * 8, cudaMemcpyDeviceToHost));
+    }
+    std::vector<int> order;
+    reference_am_order(am, order);
+    for (size_t k = 0; k < am.size(); k++) D[k] = dv[am[order[k]].spos];
+    return LB200_OK;
+}
+
 int lb200_pair_arcmatches(const lb200_ctx *cc, int pair, int *al, int *ar, int *bl, int *br, int *score, int64_t *D) {
     lb200_ctx *c = const_cast<lb200_ctx *>(cc);
     if (!c || pair < 0 || pair >= (int)c->pairs.size()) return LB200_ERR_ARG;
@@ -787,16 +893,8 @@ int lb200_pair_arcmatches(const lb200_ctx *cc, int pair, int *al, int *ar, int *
     const size_t K = am.size();
     // reference index order = (arc A index, arc B index) ascending (arc_matches.cc:161-183); arcs are indexed by
     // left end descending, right end ascending (basepairs.cc:162-163)
-    std::vector<int> order(K);
-    for (size_t k = 0; k < K; k++) order[k] = (int)k;
-    std::sort(order.begin(), order.end(), [&](int x, int y) {
-        const int xal = am[x].ends_a & 0xfff, yal = am[y].ends_a & 0xfff, xar = am[x].ends_a >> 12, yar = am[y].ends_a >> 12;
-        if (xal != yal) return xal > yal;
-        if (xar != yar) return xar < yar;
-        const int xbl = am[x].ends_b & 0xfff, ybl = am[y].ends_b & 0xfff, xbr = am[x].ends_b >> 12, ybr = am[y].ends_b >> 12;
-        if (xbl != ybl) return xbl > ybl;
-        return xbr < ybr;
-    });
+    std::vector<int> order;
+    reference_am_order(am, order);
     for (size_t k = 0; k < K; k++) {
         const DevArcMatch &x = am[order[k]];
         if (al) al[k] = x.ends_a & 0xfff;
@@ -807,6 +905,22 @@ int lb200_pair_arcmatches(const lb200_ctx *cc, int pair, int *al, int *ar, int *
         if (D) { const int d = dvals[x.spos].d; D[k] = d < LB_NEG_LIMIT ? LB200_SCORE_NEG_INF : d; }
     }
     return LB200_OK;
+}
+
+// reference index order = (arc A index, arc B index) ascending (arc_matches.cc:161-183); arcs are indexed by left end
+// descending, right end ascending (basepairs.cc:162-163)
+static void reference_am_order(const std::vector<DevArcMatch> &am, std::vector<int> &order) {
+    const size_t K = am.size();
+    order.resize(K);
+    for (size_t k = 0; k < K; k++) order[k] = (int)k;
+    std::sort(order.begin(), order.end(), [&](int x, int y) {
+        const int xal = am[x].ends_a & 0xfff, yal = am[y].ends_a & 0xfff, xar = am[x].ends_a >> 12, yar = am[y].ends_a >> 12;
+        if (xal != yal) return xal > yal;
+        if (xar != yar) return xar < yar;
+        const int xbl = am[x].ends_b & 0xfff, ybl = am[y].ends_b & 0xfff, xbr = am[x].ends_b >> 12, ybr = am[y].ends_b >> 12;
+        if (xbl != ybl) return xbl > ybl;
+        return xbr < ybr;
+    });
 }
 
 int lb200_pair_alignment(const lb200_ctx *c, int pair, int *ea, int *eb, char *sa, char *sb) {

@@ -43,3 +43,23 @@ def test_archaea_all_vs_all_scores():
         r = O.port_align(paths[a], paths[b], g["flags"])
         assert r["score"] == score
         assert r["rowA"] == rowA and r["rowB"] == rowB
+
+
+def test_port_inside_p_matches_reference_fixture():
+    """LocARNA-P inside: the port's Z and inside table against the compiled reference's AlignerP<double>
+    (tests/golden/locarna_p_outputs.json, tools/make_golden_p.py). The port follows the reference's expression order, so the
+    values agree to the last bit here; the test allows 1e-12 relative for other libm builds."""
+    import json
+    for case in json.load(open(os.path.join(GOLD, "locarna_p_outputs.json"))):
+        r = O.port_inside_p(os.path.join(GOLD, case["A"]), os.path.join(GOLD, case["B"]), case["flags"], case["pf_scale"])
+        assert abs(r["Z"] - case["Z"]) <= 1e-12 * abs(case["Z"]), case["A"]
+        assert len(r["D"]) == len(case["D"])
+        assert all(abs(x - y) <= 1e-12 * abs(y) for x, y in zip(r["D"], case["D"]))
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="compiled reference (oracle/_ref) not present")
+def test_port_inside_p_matches_live_reference(synth_dir):
+    a, b = synth_dir["cfg3"][:2]
+    for flags in ({"pf-double": True, "min-trace-probability": 1e-5}, {"pf-double": True, "min-trace-probability": 1e-5, "max-diff-am": 20}):
+        p, r = O.port_inside_p(a, b, flags), O.ref_inside_p(a, b, flags)
+        assert p["Z"] == r["Z"] and p["D"] == r["pfD"], flags
