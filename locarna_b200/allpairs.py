@@ -58,10 +58,9 @@ def gather_scores(dist, local_idx, local_scores, n_pairs: int, device=None):
     world, rank = dist.get_world_size(), dist.get_rank()
     cap = (n_pairs + world - 1) // world + 1
     NEG = -(2 ** 62)
-    buf = torch.full((cap, 2), -1, dtype=torch.int64, device=device)
-    for k, (i, s) in enumerate(zip(local_idx, local_scores)):
-        buf[k, 0] = i
-        buf[k, 1] = NEG if s is None else int(s)
+    rows = [[int(i), NEG if s is None else int(s)] for i, s in zip(local_idx, local_scores)]
+    rows += [[-1, -1]] * (cap - len(rows))
+    buf = torch.tensor(rows, dtype=torch.int64).to(device) if device is not None else torch.tensor(rows, dtype=torch.int64)   # one H2D copy
     out = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
     dist.gather(buf, out, dst=0)
     if rank != 0:

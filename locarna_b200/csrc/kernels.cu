@@ -267,24 +267,25 @@ struct Stream3 {
     const uint4 *base;       // the pair's entries
     const int *q;            // q[k] = S-order start of local anti-diagonal k (sptr + s0)
     int q_cap;               // largest valid index into q
-    int qa, qb, qc, qd;      // q[t], q[t+1], q[t+2], q[t+3] for the list handled next (loaded two steps ahead of their use)
-    uint4 nx;                // prefetched: entry qa + lane
-    int pm0, pd0, ps0, pm1, pd1, ps1;   // two gathers in flight: M(source), D, accumulator index (-1: none)
+    int qx, qy, qz, qw;      // bounds q[t], q[t+1] of the list prefetched next, and the two values after them (loaded two steps ahead)
+    uint4 nA, nB;            // prefetched lists of the next two cell steps (lanes beyond the list hold the poison entry)
+    int pm, pd, ps;          // gather in flight: M(source), D, accumulator index (-1: none)
 };
 
-// filter one block of the list of target anti-diagonal t and start the gathers; returns whether lane 31 still belongs to the prefix
+// filter one block of the list of target anti-diagonal t and start the gathers; returns whether lane 31 still belongs to the prefix.
+// Lanes beyond the list hold x = 0xffffffff (fails the box filter) and s = -1 (outside every prefix).
 template <int NC>
-__device__ __forceinline__ bool stream_block(const uint4 v, bool valid, const BoxGeom &g, const int *box, int ring_t, int s0, uint32_t org,
-                                             uint32_t lim, int d0, int &pm, int &pd, int &ps) {
+__device__ __forceinline__ bool stream_block(const uint4 v, const BoxGeom &g, const int *box, int ring_t, int s0, uint32_t org, uint32_t lim, int d0,
+                                             int &pm, int &pd, int &ps) {
     const uint32_t t1 = v.x - org, t2 = lim - v.y;
     ps = -1;
-    if (valid && ((t1 | t2) & 0x80008000u) == 0) {
+    if (((t1 | t2) & 0x80008000u) == 0) {
         const int p = LB_ENT_LO(t1), q = LB_ENT_HI(t1);
         pm = __ldcg(box + (p + q) * g.nslots + ((q - p - g.vmin) >> 1));
         pd = (int)v.z;
         ps = ring_t + ((LB_ENT_HI(v.y) - LB_ENT_LO(v.y) - d0) >> 1);
     }
-    return (__ballot_sync(0xffffffffu, valid && (int)v.w >= s0) >> 31) != 0;
+    return (__ballot_sync(0xffffffffu, (int)v.w >= s0) >> 31) != 0;
 }
 
 // Fill one M box. NC = diagonal pairs per lane (the warp covers 64*NC diagonals).
@@ -303,11 +304,15 @@ __device__ void fill_box(const DevCtx &c, const DevPair &pr, const BoxGeom &g, c
     st.q = c.sptr + pr.sptr + s0;
     st.q_cap = pr.lenA + pr.lenB + 2 - s0;
     auto qld = [&](int k) { return __ldg(st.q + min(k, st.q_cap)); };
-    auto eld = [&](int e, int e_end) { uint4 v = make_uint4(0, 0, 0, 0); if (e < e_end) v = __ldg(st.base + e); return v; };
+    auto eld = [&](int e, int e_end) { uint4 v = make_uint4(0xffffffffu, 0u, 0u, 0xffffffffu); if (e < e_end) v = __ldg(st.base + e); return v; };
     // the first list handled (after cell step 1) is the one of local anti-diagonal 3
-    st.qa = qld(3); st.qb = qld(4); st.qc = qld(5); st.qd = qld(6);
-    st.nx = eld(st.qa + lane, st.qb);
-    st.ps0 = -1; st.ps1 = -1; st.pm0 = st.pm1 = st.pd0 = st.pd1 = 0;
+    {
+        const int q3 = qld(3), q4 = qld(4);
+        st.qx = qld(5); st.qy = qld(6); st.qz = qld(7); st.qw = qld(8);
+        st.nA = eld(q3 + lane, q4);
+        st.nB = eld(q4 + lane, st.qx);
+    }
+    st.ps = -1; st.pm = st.pd = 0;
     const uint32_t org = (uint32_t)g.al | ((uint32_t)g.bl << 16);
     const uint32_t lim = (uint32_t)(g.al + g.Rn) | ((uint32_t)(g.bl + g.Cn) << 16);
     const int d0 = g.bl - g.al + g.vmin;
@@ -341,39 +346,42 @@ __device__ void fill_box(const DevCtx &c, const DevPair &pr, const BoxGeom &g, c
     __syncwarp();
 
     int ringoff = ((s0 + 1) & (RING - 1)) * NWP;
-    // after cell step u: land the gathers of the previous step, handle the list of anti-diagonal u + 2, prefetch the next one
-    auto stream = [&](int u) {
+    // after cell step u: land the gather of the previous step, handle the list of anti-diagonal u + 2 (buffer nx, loaded two steps
+    // ago), refill nx with the list of anti-diagonal u + 4
+    auto stream = [&](int u, uint4 &nx) {
         __syncwarp();
-        if (st.ps0 >= 0) atomicMax(&ws.arcbuf[st.ps0], st.pm0 + st.pd0);
-        if (st.ps1 >= 0) atomicMax(&ws.arcbuf[st.ps1], st.pm1 + st.pd1);
-        st.ps1 = -1;
+        if (st.ps >= 0) atomicMax(&ws.arcbuf[st.ps], st.pm + st.pd);
         const int ring_t = ((s0 + u + 2) & (RING - 1)) * NWP;
-        bool more = stream_block<NC>(st.nx, st.qa + lane < st.qb, g, box, ring_t, s0, org, lim, d0, st.pm0, st.pd0, st.ps0);
-        for (int e = st.qa + 32; more && e < st.qb; e += 32) {   // prefix longer than one block (unprefetched)
-            const uint4 v = eld(e + lane, st.qb);
-            if (st.ps1 >= 0) atomicMax(&ws.arcbuf[st.ps1], st.pm1 + st.pd1);
-            more = stream_block<NC>(v, e + lane < st.qb, g, box, ring_t, s0, org, lim, d0, st.pm1, st.pd1, st.ps1);
+        bool more = stream_block<NC>(nx, g, box, ring_t, s0, org, lim, d0, st.pm, st.pd, st.ps);
+        if (more) {   // prefix longer than one block: further, unprefetched blocks (rare outside the top level box)
+            const int qa = qld(u + 2), qb = qld(u + 3);
+            for (int e = qa + 32; more && e < qb; e += 32) {
+                const uint4 v = eld(e + lane, qb);
+                if (st.ps >= 0) atomicMax(&ws.arcbuf[st.ps], st.pm + st.pd);
+                more = stream_block<NC>(v, g, box, ring_t, s0, org, lim, d0, st.pm, st.pd, st.ps);
+            }
         }
-        st.qa = st.qb; st.qb = st.qc;
-        st.nx = eld(st.qa + lane, st.qb);
-        st.qc = st.qd;
-        st.qd = qld(u + 6);
+        nx = eld(st.qx + lane, st.qy);        // list of anti-diagonal u + 4: [q[u+4], q[u+5])
+        st.qx = st.qy; st.qy = st.qz; st.qz = st.qw;
+        st.qw = qld(u + 8);
         __syncwarp();
     };
     int u = 1;
     if (par0 == 0) {   // anti-diagonal 1 is of the odd class
         dp_step2<NC, 1, GB, CLAMP>(S, init, ws.sig, ringoff, stride, gap, gap_open, lane);
         ringoff = (ringoff + NWP) & (RING * NWP - 1);
-        stream(u);
+        stream(u, st.nA);
         u = 2;
+        // keep the buffer roles aligned with the unrolled loop below (nA first)
+        const uint4 t = st.nA; st.nA = st.nB; st.nB = t;
     }
     for (; u + 1 <= g.umax; u += 2) {
         dp_step2<NC, 0, GB, CLAMP>(S, init, ws.sig, ringoff, stride, gap, gap_open, lane);
         ringoff = (ringoff + NWP) & (RING * NWP - 1);
-        stream(u);
+        stream(u, st.nA);
         dp_step2<NC, 1, GB, CLAMP>(S, init, ws.sig, ringoff, stride, gap, gap_open, lane);
         ringoff = (ringoff + NWP) & (RING * NWP - 1);
-        stream(u + 1);
+        stream(u + 1, st.nB);
     }
     if (u <= g.umax) {
         dp_step2<NC, 0, GB, CLAMP>(S, init, ws.sig, ringoff, stride, gap, gap_open, lane);
@@ -618,7 +626,7 @@ __device__ __forceinline__ void carve(const DevCtx &c, int *smem, WarpSmem &ws) 
 // Tasks of a level are mutually independent: a task reads D only for arc matches strictly inside its
 // box, whose left ends have a larger al+bl (aligner.cc:675-728; levels = al+bl descending, two at a time).
 template <int NCMAX, bool GB>
-__global__ void __launch_bounds__(32) dfill_kernel(DevCtx c, int q) {
+__global__ void __launch_bounds__(32, 32) dfill_kernel(DevCtx c, int q) {
     extern __shared__ __align__(16) int smem[];
     const int lane = threadIdx.x;
     const int task_begin = c.qstart[q], task_end = c.qstart[q + 1];
