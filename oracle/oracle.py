@@ -68,6 +68,10 @@ def lib():
         _lib.locarna_port_inside_p.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(Params), C.c_double, C.POINTER(C.c_double),
                                                C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.c_long), C.c_char_p, C.c_int]
         _lib.locarna_port_inside_p.restype = C.c_int
+        dpp = C.POINTER(C.POINTER(C.c_double))
+        _lib.locarna_port_probs_p.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(Params), C.c_double, C.c_double, C.POINTER(C.c_double), dpp, dpp, dpp,
+                                              C.POINTER(C.c_long), dpp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_int]
+        _lib.locarna_port_probs_p.restype = C.c_int
     return _lib
 
 
@@ -155,6 +159,28 @@ def port_inside_p(ppA: str, ppB: str, flags: dict | None = None, pf_scale: float
         return {"Z": Z.value, "D": [D[k] for k in range(n.value)]}
     finally:
         C.CDLL(None).free(D)
+
+
+def port_probs_p(ppA: str, ppB: str, flags: dict | None = None, pf_scale: float = 1.0, min_am_prob: float = 0.001) -> dict:
+    """LocARNA-P complete by the CPU restatement (T = double): Z, inside table D, outside table Dprime and the arc-match
+    probabilities (all per arc match, reference index order), and the base-match probability matrix ``bm[i][j]`` (1-based)."""
+    p = make_params(flags, False, False)
+    Z = C.c_double()
+    D, Dp, amp, bmp = (C.POINTER(C.c_double)() for _ in range(4))
+    n, la, lb = C.c_long(), C.c_int(), C.c_int()
+    err = C.create_string_buffer(512)
+    rc = lib().locarna_port_probs_p(ppA.encode(), ppB.encode(), C.byref(p), pf_scale, min_am_prob, C.byref(Z), C.byref(D), C.byref(Dp), C.byref(amp),
+                                    C.byref(n), C.byref(bmp), C.byref(la), C.byref(lb), err, 512)
+    if rc != 0:
+        raise RuntimeError("oracle port: " + err.value.decode())
+    try:
+        K, W = n.value, lb.value + 1
+        return {"Z": Z.value, "D": [D[k] for k in range(K)], "Dprime": [Dp[k] for k in range(K)], "am_prob": [amp[k] for k in range(K)],
+                "bm": [[bmp[i * W + j] for j in range(W)] for i in range(la.value + 1)], "lenA": la.value, "lenB": lb.value}
+    finally:
+        libc = C.CDLL(None)
+        for ptr in (D, Dp, amp, bmp):
+            libc.free(ptr)
 
 
 def flags_to_argv(flags: dict | None) -> list:

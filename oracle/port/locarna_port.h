@@ -49,6 +49,10 @@ void locarna_port_free(LocarnaPortResult *r);
 int locarna_port_inside_p(const char *ppA, const char *ppB, const LocarnaPortParams *p, double pf_scale, double *Z, double **D, long *n_am,
                           char *err, int errlen);
 
+/* LocARNA-P complete (aligner_p.icc:440-1399, T = double): outside table, arc-match and base-match probabilities */
+int locarna_port_probs_p(const char *ppA, const char *ppB, const LocarnaPortParams *p, double pf_scale, double min_am_prob, double *Z,
+                         double **D, double **Dprime, double **am_prob, long *n_am, double **bm_prob, int *lenA, int *lenB, char *err, int errlen);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,3 +63,19 @@ def test_port_inside_p_matches_live_reference(synth_dir):
     for flags in ({"pf-double": True, "min-trace-probability": 1e-5}, {"pf-double": True, "min-trace-probability": 1e-5, "max-diff-am": 20}):
         p, r = O.port_inside_p(a, b, flags), O.ref_inside_p(a, b, flags)
         assert p["Z"] == r["Z"] and p["D"] == r["pfD"], flags
+
+
+def test_port_probs_p_matches_reference_fixture():
+    """LocARNA-P outside + probabilities: the port's arc-match and base-match probabilities against the compiled reference's
+    (the lists locarna_p writes with --write-arcmatch-probs / --write-basematch-probs, thresholds 0.001)."""
+    import json
+    for case in json.load(open(os.path.join(GOLD, "locarna_p_outputs.json"))):
+        r = O.port_probs_p(os.path.join(GOLD, case["A"]), os.path.join(GOLD, case["B"]), case["flags"], case["pf_scale"])
+        am = {tuple(case["am"][k]): r["am_prob"][k] for k in range(len(case["am"])) if r["am_prob"][k] >= 0.001}
+        ref_am = {tuple(x[:4]): x[4] for x in case["am_probs"]}
+        assert set(am) == set(ref_am), case["A"]
+        assert all(abs(am[k] - ref_am[k]) <= 1e-12 * ref_am[k] for k in ref_am)
+        bm = {(i, j): r["bm"][i][j] for i in range(1, r["lenA"] + 1) for j in range(1, r["lenB"] + 1) if r["bm"][i][j] >= 0.001}
+        ref_bm = {(x[0], x[1]): x[2] for x in case["bm_probs"]}
+        assert set(bm) == set(ref_bm), case["A"]
+        assert all(abs(bm[k] - ref_bm[k]) <= 1e-12 * ref_bm[k] for k in ref_bm)
