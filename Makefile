@@ -15,7 +15,7 @@ all: $(LIB) $(CLI)
 $(OBJ):
 	mkdir -p $(OBJ)
 
-$(OBJ)/%.o: $(SRC)/%.cu $(wildcard $(SRC)/*.h) include/locarna_b200.h | $(OBJ)
+$(OBJ)/%.o: $(SRC)/%.cu $(wildcard $(SRC)/*.h) $(wildcard $(SRC)/*.cuh) include/locarna_b200.h | $(OBJ)
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 
 # host-only code: plain x86-64 code generation (no -march, no fast-math) so that the 80-bit envelope

@@ -150,11 +150,21 @@ int lb200_pair_alignment(const lb200_ctx *ctx, int pair, int *edges_a, int *edge
  * match. Uses the scoring parameters of the context, temperature_alipf as the Boltzmann temperature (scoring.hh:853-856) and
  * pf_scale as in locarna_p --pf-scale. locarna_p derives its band with min_trace_probability 1e-5 and the envelope in double
  * (pf_double = 1); set those in lb200_params for drop-in results. Not available with no_lonely_pairs / struct_local / sequ_local
- * (AlignerP has no such modes). The outside pass and the match probabilities are not built yet. */
+ * (AlignerP has no such modes). */
 int lb200_run_pf(lb200_ctx *ctx, double pf_scale);
 int lb200_pair_partition_function(const lb200_ctx *ctx, int pair, double *Z);
 /* inside values in the reference's arc-match index order (as lb200_pair_arcmatches); D holds n_arcmatches doubles */
 int lb200_pair_arcmatch_pf(const lb200_ctx *ctx, int pair, double *D);
+/* LocARNA-P complete (src/locarna_p.cc:483-526): inside pass as lb200_run_pf, then the reverse / outside passes
+ * (AlignerP::align_outside, aligner_p.icc:440-1139), the arc-match probabilities (compute_arcmatch_probabilities, :1150-1195) and the
+ * base-match probabilities (compute_basematch_probabilities(false), :1201-1399; arc matches with probability > sqrt(min_am_prob)
+ * contribute the enclosed cases, as in the reference). */
+int lb200_run_pf_probs(lb200_ctx *ctx, double pf_scale, double min_am_prob);
+/* probability of every arc match, reference arc-match index order (locarna_p --write-arcmatch-probs lists those >= min_am_prob) */
+int lb200_pair_arcmatch_probs(const lb200_ctx *ctx, int pair, double *prob);
+/* base-match probabilities, dense (lenA+1) x (lenB+1) row major, entry [i][j] for positions i of A and j of B (1-based; 0 outside the
+ * band). locarna_p --write-basematch-probs lists those >= min_bm_prob */
+int lb200_pair_basematch_probs(const lb200_ctx *ctx, int pair, double *bm);
 
 /* Guide tree of the all-vs-all stage (host): UPGMA over the symmetric score matrix (n x n, row major, diagonal 0) with the tie
  * rules of lib/perl/MLocarna/Tree.pm:181-262; writes the newick string (without the trailing ';') that mlocarna stores in

@@ -40,7 +40,8 @@ EXPORTS = [
     "lb200_seq_add_pp", "lb200_seq_add", "lb200_seq_length", "lb200_seq_get", "lb200_pair_add", "lb200_num_pairs", "lb200_clear_pairs",
     "lb200_prepare", "lb200_upload", "lb200_run", "lb200_last_kernel_ms", "lb200_last_h2d_bytes", "lb200_last_d2h_bytes", "lb200_last_dfill_ms", "lb200_last_dfill_launches", "lb200_last_launches", "lb200_envelope_stats", "lb200_pair_score", "lb200_get_scores",
     "lb200_pair_get_info", "lb200_pair_band", "lb200_pair_arcmatches", "lb200_pair_alignment", "lb200_upgma_newick",
-    "lb200_run_pf", "lb200_pair_partition_function", "lb200_pair_arcmatch_pf",
+    "lb200_run_pf", "lb200_pair_partition_function", "lb200_pair_arcmatch_pf", "lb200_run_pf_probs", "lb200_pair_arcmatch_probs",
+    "lb200_pair_basematch_probs",
 ]
 
 _lib = None
@@ -93,6 +94,9 @@ def load():
     lib.lb200_run_pf.argtypes = [vp, C.c_double]
     lib.lb200_pair_partition_function.argtypes = [vp, C.c_int, dp]
     lib.lb200_pair_arcmatch_pf.argtypes = [vp, C.c_int, dp]
+    lib.lb200_run_pf_probs.argtypes = [vp, C.c_double, C.c_double]
+    lib.lb200_pair_arcmatch_probs.argtypes = [vp, C.c_int, dp]
+    lib.lb200_pair_basematch_probs.argtypes = [vp, C.c_int, dp]
     lib.lb200_upgma_newick.argtypes = [C.c_int, C.POINTER(C.c_char_p), i64p, C.c_char_p, C.c_size_t]
     _lib = lib
     return lib
@@ -262,6 +266,23 @@ class Context:
         D = (C.c_double * max(K, 1))()
         self._chk(self.lib.lb200_pair_arcmatch_pf(self.h, pair, D))
         return [D[k] for k in range(K)]
+
+    def run_pf_probs(self, pf_scale: float = 1.0, min_am_prob: float = 0.001):
+        """LocARNA-P complete: inside, outside, arc-match and base-match probabilities (FP64 on the GPU)."""
+        self._chk(self.lib.lb200_run_pf_probs(self.h, pf_scale, min_am_prob))
+
+    def arcmatch_probs(self, pair: int):
+        K = self.info(pair).n_arcmatches
+        D = (C.c_double * max(K, 1))()
+        self._chk(self.lib.lb200_pair_arcmatch_probs(self.h, pair, D))
+        return [D[k] for k in range(K)]
+
+    def basematch_probs(self, pair: int):
+        inf = self.info(pair)
+        W = inf.lenB + 1
+        buf = (C.c_double * ((inf.lenA + 1) * W))()
+        self._chk(self.lib.lb200_pair_basematch_probs(self.h, pair, buf))
+        return [[buf[i * W + j] for j in range(W)] for i in range(inf.lenA + 1)]
 
     def alignment(self, pair: int):
         inf = self.info(pair)

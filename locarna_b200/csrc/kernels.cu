@@ -1195,3 +1195,4 @@ cudaError_t configure_kernels(int ncmax, int smem_bytes, int *dfill_ctas_per_sm)
 }  // namespace lb200
 
 #include "pf_inside.cuh"
+#include "pf_outside.cuh"

@@ -35,6 +35,19 @@ struct PfCtx {   // must match pf_inside.cuh
 void launch_pfill(const DevCtx &c, const PfCtx &pc, int ncmax, int grid, int smem_bytes, int q, cudaStream_t st);
 void launch_ptop(const DevCtx &c, const PfCtx &pc, int ncmax, int grid, int smem_bytes, int pair_begin, int pair_end, int *cursor, cudaStream_t st);
 cudaError_t configure_pf(int ncmax, int smem_bytes, int *ctas_per_sm);
+struct PfoCtx {   // must match pf_outside.cuh
+    PfCtx pc;
+    const int *cell_start; const int *cell_rev;
+    const int *arc_left, *arc_right;
+    const int *lptr, *lcount;
+    double *dpp; double *amp; double *mats; double *cta;
+    long long mat_doubles;
+    double am_threshold;
+};
+void launch_pfo_prepare(const DevCtx &c, const PfoCtx &o, int n_pairs, int grid, cudaStream_t st);
+void launch_pfo_outside(const DevCtx &c, const PfoCtx &o, int q, int grid, int *cursor, cudaStream_t st);
+void launch_pfo_amprob(const DevCtx &c, const PfoCtx &o, int n_pairs, cudaStream_t st);
+void launch_pfo_bm(const DevCtx &c, const PfoCtx &o, int n_tasks, int n_pairs, int grid, int *cursor, cudaStream_t st);
 void launch_trace_sl(const DevCtx &c, int grid, int smem_bytes, int pair_begin, int pair_end, int *cursor, cudaStream_t st);
 }  // namespace lb200
 
@@ -112,14 +125,15 @@ struct lb200_ctx {
     std::vector<int> seq_prob_off;
     int64_t env_device_pairs = 0, env_host_pairs = 0;  // statistics of the last band derivation
     int env_mode = 1;  // 1: device screening + host re-check, 0: host only (LB200_ENVELOPE=host)
-    DevBuf d_pf_esig, d_pf_bpow, d_pf_d, d_pf_z, d_pf_scratch;
+    DevBuf d_pf_esig, d_pf_bpow, d_pf_d, d_pf_z, d_pf_scratch, d_pf_dp, d_pf_amp, d_pf_mats, d_pf_cta;
+    PfCtx pf_last; bool pf_have = false; bool pf_probs_done = false; long long pf_mat_doubles = 0;
     int max_box_words = 1, max_len = 1;
     DevBuf d_pairs, d_codes, d_band_lo, d_band_hi, d_sptr, d_ent, d_am, d_tasks, d_top, d_scratch, d_cursor, d_flag;
     ~lb200_ctx() {
         DevBuf *all[] = {&d_pairs, &d_codes, &d_band_lo, &d_band_hi, &d_sptr, &d_ent, &d_am, &d_tasks, &d_top, &d_scratch, &d_cursor, &d_flag,
                          &d_arc_left, &d_arc_right, &d_arc_weight, &d_lptr, &d_lcount, &d_am_seq, &d_cell_rev, &d_cell_start, &d_skeys, &d_skeys2,
                          &d_svals, &d_svals2, &d_tasks_unsorted, &d_tkeys, &d_tkeys2, &d_tvals, &d_tvals2, &d_ntasks, &d_qstart, &d_stats, &d_tmp, &d_tr_edges, &d_tr_str, &d_tr_stack,
-                         &d_pf_esig, &d_pf_bpow, &d_pf_d, &d_pf_z, &d_pf_scratch,
+                         &d_pf_esig, &d_pf_bpow, &d_pf_d, &d_pf_z, &d_pf_scratch, &d_pf_dp, &d_pf_amp, &d_pf_mats, &d_pf_cta,
                          &d_pup, &d_pdown, &d_env_pairs, &d_env_lo, &d_env_hi, &d_env_olo, &d_env_ohi, &d_env_flag, &d_env_scratch};
         for (auto *b : all) b->release();
         if (ev0) cudaEventDestroy(ev0);
@@ -842,6 +856,81 @@ int lb200_run_pf(lb200_ctx *c, double pf_scale) {
     c->last_kernel_ms = ms; c->last_launches = launches; c->last_d2h_bytes = (int64_t)P * 8 + 16;
     if (h_flag[0] != 0) return fail(c, LB200_ERR_UNSUPPORTED, "LocARNA-P kernel reported error %d (1: band too wide, 2: box exceeds scratch)", h_flag[0]);
     for (int k = 0; k < P; k++) { c->pairs[k].pf_Z = z[k]; c->pairs[k].pf_done = true; }
+    c->pf_last = pc; c->pf_have = true; c->pf_probs_done = false;
+    return LB200_OK;
+}
+
+static void reference_am_order(const std::vector<DevArcMatch> &am, std::vector<int> &order);
+
+// LocARNA-P outside pass and probabilities (aligner_p.icc:440-1399) after the inside pass
+int lb200_run_pf_probs(lb200_ctx *c, double pf_scale, double min_am_prob) {
+    { const int rc = lb200_run_pf(c, pf_scale); if (rc != LB200_OK) return rc; }
+    const int P = (int)c->pairs.size();
+    if (P == 0) return LB200_OK;
+    if (!(min_am_prob >= 0)) return fail(c, LB200_ERR_ARG, "min_am_prob must not be negative");
+    lb200_ctx::Resident &R = c->res;
+    cudaStream_t st = c->stream;
+    const double kernel_ms_inside = c->last_kernel_ms;
+    int64_t launches = c->last_launches;
+    long long mat = 1;
+    for (int k = 0; k < P; k++) mat = std::max(mat, (long long)(c->seqs[c->pairs[k].seqA].len + 1) * (c->seqs[c->pairs[k].seqB].len + 1));
+    mat = (mat + 1) & ~1LL;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(4LL * c->prop.multiProcessorCount, (8LL << 30) / (4 * mat * 8)));   // <= 8 GB of CTA scratch
+    CUDA_TRY(c, c->d_pf_dp.ensure(std::max<size_t>(R.total_am, 1) * 8));
+    CUDA_TRY(c, c->d_pf_amp.ensure(std::max<size_t>(R.total_am, 1) * 8));
+    CUDA_TRY(c, c->d_pf_mats.ensure((size_t)P * 5 * mat * 8));
+    CUDA_TRY(c, c->d_pf_cta.ensure((size_t)grid * 4 * mat * 8));
+    PfoCtx o;
+    o.pc = c->pf_last;
+    o.cell_start = (const int *)c->d_cell_start.p; o.cell_rev = (const int *)c->d_cell_rev.p;
+    o.arc_left = (const int *)c->d_arc_left.p; o.arc_right = (const int *)c->d_arc_right.p;
+    o.lptr = (const int *)c->d_lptr.p; o.lcount = (const int *)c->d_lcount.p;
+    o.dpp = (double *)c->d_pf_dp.p; o.amp = (double *)c->d_pf_amp.p; o.mats = (double *)c->d_pf_mats.p; o.cta = (double *)c->d_pf_cta.p;
+    o.mat_doubles = mat; o.am_threshold = std::sqrt(min_am_prob);
+    CUDA_TRY(c, cudaEventRecord(c->ev0, st));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_cursor.p, 0, 4100 * 4, st));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_pf_dp.p, 0, std::max<size_t>(R.total_am, 1) * 8, st));   // Dmatprime.fill(0), aligner_p.icc:46-47
+    launch_pfo_prepare(R.dc, o, P, std::min(grid, P), st); launches++;
+    for (int q = R.q_hi; q >= R.q_lo; q--) { launch_pfo_outside(R.dc, o, q, grid, (int *)c->d_cursor.p, st); launches++; }   // left ends ascending
+    launch_pfo_amprob(R.dc, o, P, st); launches++;
+    int n_tasks = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&n_tasks, (const int *)c->d_qstart.p + 4096, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    launch_pfo_bm(R.dc, o, n_tasks, P, grid, (int *)c->d_cursor.p + 4098, st); launches += 2;
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaEventRecord(c->ev1, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    float ms = 0;
+    CUDA_TRY(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->last_kernel_ms = kernel_ms_inside + ms; c->last_launches = launches;
+    c->pf_mat_doubles = mat; c->pf_probs_done = true;
+    return LB200_OK;
+}
+
+int lb200_pair_arcmatch_probs(const lb200_ctx *cc, int pair, double *prob) {
+    lb200_ctx *c = const_cast<lb200_ctx *>(cc);
+    if (!c || pair < 0 || pair >= (int)c->pairs.size() || !prob) return LB200_ERR_ARG;
+    const PairRec &r = c->pairs[pair];
+    if (!c->pf_probs_done || !c->res.valid || pair < c->res.p0 || pair >= c->res.p1) return fail(c, LB200_ERR_STATE, "no LocARNA-P probabilities for this pair (call lb200_run_pf_probs)");
+    std::vector<DevArcMatch> am(r.K);
+    std::vector<double> dv(r.K);
+    if (r.K) {
+        CUDA_TRY(c, cudaMemcpy(am.data(), (const DevArcMatch *)c->d_am.p + r.am_base, (size_t)r.K * sizeof(DevArcMatch), cudaMemcpyDeviceToHost));
+        CUDA_TRY(c, cudaMemcpy(dv.data(), (const double *)c->d_pf_amp.p + r.am_base, (size_t)r.K * 8, cudaMemcpyDeviceToHost));
+    }
+    std::vector<int> order;
+    reference_am_order(am, order);
+    for (size_t k = 0; k < am.size(); k++) prob[k] = dv[am[order[k]].spos];
+    return LB200_OK;
+}
+
+int lb200_pair_basematch_probs(const lb200_ctx *cc, int pair, double *bm) {
+    lb200_ctx *c = const_cast<lb200_ctx *>(cc);
+    if (!c || pair < 0 || pair >= (int)c->pairs.size() || !bm) return LB200_ERR_ARG;
+    if (!c->pf_probs_done || !c->res.valid || pair < c->res.p0 || pair >= c->res.p1) return fail(c, LB200_ERR_STATE, "no LocARNA-P probabilities for this pair (call lb200_run_pf_probs)");
+    const PairRec &r = c->pairs[pair];
+    const size_t cells = (size_t)(c->seqs[r.seqA].len + 1) * (c->seqs[r.seqB].len + 1);
+    CUDA_TRY(c, cudaMemcpy(bm, (const double *)c->d_pf_mats.p + ((size_t)(pair - c->res.p0) * 5 + 4) * c->pf_mat_doubles, cells * 8, cudaMemcpyDeviceToHost));
     return LB200_OK;
 }
 
@@ -851,8 +940,6 @@ int lb200_pair_partition_function(const lb200_ctx *c, int pair, double *Z) {
     *Z = c->pairs[pair].pf_Z;
     return LB200_OK;
 }
-
-static void reference_am_order(const std::vector<DevArcMatch> &am, std::vector<int> &order);
 
 int lb200_pair_arcmatch_pf(const lb200_ctx *cc, int pair, double *D) {
     lb200_ctx *c = const_cast<lb200_ctx *>(cc);

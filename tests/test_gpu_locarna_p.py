@@ -87,3 +87,61 @@ def test_rejects_unsupported_modes():
     with pytest.raises(capi.Error):
         ctx.run_pf(1.0)
     ctx.close()
+
+
+def _check_probs(files, pairs, flags, pf_scale=1.0, min_am=0.001):
+    ctx = capi.Context(0, flags)
+    ids = [ctx.add_pp(f) for f in files]
+    for a, b in pairs:
+        ctx.add_pair(ids[a], ids[b])
+    ctx.run_pf_probs(pf_scale, min_am)
+    worst = 0.0
+    for k, (a, b) in enumerate(pairs):
+        ref = O.port_probs_p(files[a], files[b], flags, pf_scale, min_am)
+        amp = ctx.arcmatch_probs(k)
+        assert len(amp) == len(ref["am_prob"])
+        for x, y in zip(amp, ref["am_prob"]):
+            # probabilities are compared where they matter (>= 1e-9); below that the absolute deviation is bounded instead
+            assert (rel(x, y) <= TOL) if max(x, y) >= 1e-9 else abs(x - y) <= 1e-12, (flags, a, b, x, y)
+        bm = ctx.basematch_probs(k)
+        for i in range(1, ref["lenA"] + 1):
+            for j in range(1, ref["lenB"] + 1):
+                x, y = bm[i][j], ref["bm"][i][j]
+                assert (rel(x, y) <= TOL) if max(x, y) >= 1e-9 else abs(x - y) <= 1e-12, (flags, a, b, i, j, x, y)
+    ctx.close()
+    return worst
+
+
+@pytest.mark.parametrize("flags", FLAGSETS)
+def test_probs_golden_inputs(flags):
+    files = sorted(glob.glob(os.path.join(GOLD, "g*.pp")))
+    pairs = [(0, 1), (2, 3), (4, 5), (3, 0), (1, 2), (5, 1), (2, 2)]
+    _check_probs(files, pairs, flags)
+
+
+def test_probs_against_reference_fixture():
+    """The lists locarna_p writes (--write-arcmatch-probs / --write-basematch-probs, thresholds 0.001) from the compiled reference."""
+    cases = json.load(open(os.path.join(GOLD, "locarna_p_outputs.json")))
+    for case in cases:
+        ctx = capi.Context(0, case["flags"])
+        a, b = ctx.add_pp(os.path.join(GOLD, case["A"])), ctx.add_pp(os.path.join(GOLD, case["B"]))
+        ctx.add_pair(a, b)
+        ctx.run_pf_probs(case["pf_scale"], 0.001)
+        amp = ctx.arcmatch_probs(0)
+        am, _ = ctx.arcmatches(0)
+        got = {tuple(am[k]): amp[k] for k in range(len(am)) if amp[k] >= 0.001}
+        want = {tuple(x[:4]): x[4] for x in case["am_probs"]}
+        edge = lambda d: {k for k, v in d.items() if abs(v - 0.001) > 1e-9}   # entries exactly at the output threshold may flip
+        assert edge(got) == edge(want), case["A"]
+        assert all(rel(got[k], want[k]) <= TOL for k in want if k in got)
+        bm = ctx.basematch_probs(0)
+        wantb = {(x[0], x[1]): x[2] for x in case["bm_probs"]}
+        gotb = {(i, j): bm[i][j] for i in range(1, len(bm)) for j in range(1, len(bm[0])) if bm[i][j] >= 0.001}
+        assert edge(gotb) == edge(wantb), case["A"]
+        assert all(rel(gotb[k], wantb[k]) <= TOL for k in wantb if k in gotb)
+        ctx.close()
+
+
+def test_probs_longer_pair(tmp_path):
+    paths = synth.make_family(str(tmp_path / "fam"), 78, 2, 100)
+    _check_probs(paths, [(1, 0)], dict(PFLAGS, **{"max-diff-am": 30}))
