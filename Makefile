@@ -9,8 +9,9 @@ LIB       := locarna_b200/liblocarna_b200.so
 OBJS := $(OBJ)/kernels.o $(OBJ)/builder.o $(OBJ)/envelope.o $(OBJ)/runtime.o $(OBJ)/host_model.o $(OBJ)/guide_tree.o
 
 CLI       := locarna_b200/bin/locarna_b200
+CLI_P     := locarna_b200/bin/locarna_p_b200
 
-all: $(LIB) $(CLI)
+all: $(LIB) $(CLI) $(CLI_P)
 
 $(OBJ):
 	mkdir -p $(OBJ)
@@ -28,6 +29,11 @@ $(LIB): $(OBJS)
 
 # `locarna`-compatible command line front end (host C++ over the C ABI)
 $(CLI): $(SRC)/cli/locarna_main.cc include/locarna_b200.hh include/locarna_b200.h $(LIB)
+	mkdir -p locarna_b200/bin
+	/usr/bin/g++ -std=c++17 -O2 -Wall -Iinclude $< -o $@ -Llocarna_b200 -llocarna_b200 -Wl,-rpath,'$$ORIGIN/..'
+
+# `locarna_p`-compatible front end (LocARNA-P: partition function, arc-match / base-match probabilities)
+$(CLI_P): $(SRC)/cli/locarna_p_main.cc include/locarna_b200.hh include/locarna_b200.h $(LIB)
 	mkdir -p locarna_b200/bin
 	/usr/bin/g++ -std=c++17 -O2 -Wall -Iinclude $< -o $@ -Llocarna_b200 -llocarna_b200 -Wl,-rpath,'$$ORIGIN/..'
 

@@ -242,5 +242,102 @@ public:
     }
 };
 
+class AlignerPParams {  // aligner_params.hh:122-156 on top of AlignerParams; defaults of the locarna_p CLI (locarna_p.cc:95-175)
+    friend class AlignerP;
+    const RnaData *rnaA_ = nullptr, *rnaB_ = nullptr;
+    ScoringParams scoring_;
+    int max_diff_am_ = -1, max_diff_at_am_ = -1, max_diff_ = -1;
+    double min_prob_ = 0.001, min_trace_probability_ = 1e-5, min_am_prob_ = 0.001, min_bm_prob_ = 0.001, pf_scale_ = 1.0;
+    std::vector<int> min_col_, max_col_;
+public:
+    AlignerPParams &seqA(const RnaData *r) { rnaA_ = r; return *this; }
+    AlignerPParams &seqB(const RnaData *r) { rnaB_ = r; return *this; }
+    AlignerPParams &scoring(const ScoringParams &s) { scoring_ = s; return *this; }
+    AlignerPParams &max_diff_am(int d) { max_diff_am_ = d; return *this; }
+    AlignerPParams &max_diff_at_am(int d) { max_diff_at_am_ = d; return *this; }
+    AlignerPParams &trace_controller(const std::vector<int> &min_col, const std::vector<int> &max_col) { min_col_ = min_col; max_col_ = max_col; return *this; }
+    AlignerPParams &max_diff(int d) { max_diff_ = d; return *this; }
+    AlignerPParams &min_trace_probability(double p) { min_trace_probability_ = p; return *this; }
+    AlignerPParams &min_prob(double p) { min_prob_ = p; return *this; }
+    AlignerPParams &min_am_prob(double p) { min_am_prob_ = p; return *this; }
+    AlignerPParams &min_bm_prob(double p) { min_bm_prob_ = p; return *this; }
+    AlignerPParams &pf_scale(double s) { pf_scale_ = s; return *this; }
+};
+
+class AlignerP {  // aligner_p.hh:55-629, T = double
+    std::shared_ptr<Context> ctx_;
+    int pair_ = -1;
+    AlignerPParams params_;
+    bool probs_ = false;
+    std::vector<int> al_, ar_, bl_, br_;
+    std::vector<double> am_prob_, bm_prob_;
+    int lenA_ = 0, lenB_ = 0;
+    void fetch() {
+        if (probs_) return;
+        ctx_->check(lb200_run_pf_probs(ctx_->get(), params_.pf_scale_, params_.min_am_prob_));
+        lb200_pair_info inf;
+        ctx_->check(lb200_pair_get_info(ctx_->get(), pair_, &inf));
+        const size_t K = (size_t)inf.n_arcmatches;
+        al_.resize(K + 1); ar_.resize(K + 1); bl_.resize(K + 1); br_.resize(K + 1); am_prob_.resize(K + 1);
+        ctx_->check(lb200_pair_arcmatches(ctx_->get(), pair_, al_.data(), ar_.data(), bl_.data(), br_.data(), nullptr, nullptr));
+        ctx_->check(lb200_pair_arcmatch_probs(ctx_->get(), pair_, am_prob_.data()));
+        al_.resize(K); am_prob_.resize(K);
+        lenA_ = inf.lenA; lenB_ = inf.lenB;
+        bm_prob_.resize((size_t)(lenA_ + 1) * (lenB_ + 1));
+        ctx_->check(lb200_pair_basematch_probs(ctx_->get(), pair_, bm_prob_.data()));
+        probs_ = true;
+    }
+public:
+    explicit AlignerP(const AlignerPParams &ap, int device = 0) : ctx_(std::make_shared<Context>(device)), params_(ap) {
+        if (!ap.rnaA_ || !ap.rnaB_) throw failure("AlignerPParams: seqA and seqB are mandatory");
+        lb200_params p;
+        lb200_default_params(&p);
+        const ScoringParams &s = ap.scoring_;
+        p.min_prob = ap.min_prob_; p.max_diff_am = ap.max_diff_am_; p.max_diff_at_am = ap.max_diff_at_am_; p.max_diff = ap.max_diff_;
+        p.min_trace_probability = ap.min_trace_probability_;
+        p.pf_double = 1;                                      // locarna_p.cc:285-294: the envelope is computed in double as well
+        p.struct_weight = s.struct_weight; p.indel = s.indel; p.indel_opening = s.indel_opening; p.tau = s.tau_factor;
+        p.match = s.match; p.mismatch = s.mismatch; p.use_ribosum = s.use_ribosum; p.temperature_alipf = s.temperature_alipf;
+        ctx_->check(lb200_set_params(ctx_->get(), &p));
+        const int a = lb200_seq_add_pp(ctx_->get(), ap.rnaA_->filename().c_str());
+        ctx_->check(a);
+        const int b = lb200_seq_add_pp(ctx_->get(), ap.rnaB_->filename().c_str());
+        ctx_->check(b);
+        pair_ = lb200_pair_add(ctx_->get(), a, b, ap.min_col_.empty() ? nullptr : ap.min_col_.data(), ap.max_col_.empty() ? nullptr : ap.max_col_.data());
+        ctx_->check(pair_);
+    }
+    //! inside algorithm; returns the partition function (aligner_p.icc:413-438)
+    double align_inside() {
+        ctx_->check(lb200_run_pf(ctx_->get(), params_.pf_scale_));
+        double z = 0;
+        ctx_->check(lb200_pair_partition_function(ctx_->get(), pair_, &z));
+        return z;
+    }
+    //! outside algorithm (aligner_p.icc:1113-1139); the device computes outside and probabilities in one call
+    void align_outside() { fetch(); }
+    void compute_arcmatch_probabilities() { fetch(); }
+    void compute_basematch_probabilities(bool basematch_probs_include_arcmatch) {
+        fetch();
+        if (basematch_probs_include_arcmatch)                 // aligner_p.icc:1382-1398
+            for (size_t k = 0; k < am_prob_.size(); k++) {
+                bm_prob_[(size_t)al_[k] * (lenB_ + 1) + bl_[k]] += am_prob_[k];
+                bm_prob_[(size_t)ar_[k] * (lenB_ + 1) + br_[k]] += am_prob_[k];
+            }
+    }
+    //! aligner_p.icc:1404-1415
+    void write_basematch_probabilities(std::ostream &out) {
+        fetch();
+        for (int i = 1; i <= lenA_; i++)
+            for (int j = 1; j <= lenB_; j++)
+                if (bm_prob_[(size_t)i * (lenB_ + 1) + j] >= params_.min_bm_prob_) out << i << " " << j << " " << bm_prob_[(size_t)i * (lenB_ + 1) + j] << std::endl;
+    }
+    //! aligner_p.icc:1420-1435
+    void write_arcmatch_probabilities(std::ostream &out) {
+        fetch();
+        for (size_t k = 0; k < am_prob_.size(); k++)
+            if (am_prob_[k] >= params_.min_am_prob_) out << al_[k] << " " << ar_[k] << " " << bl_[k] << " " << br_[k] << " " << am_prob_[k] << std::endl;
+    }
+};
+
 }  // namespace LocARNA_B200
 #endif

@@ -26,3 +26,31 @@ def test_cli_output_matches_reference(case, tmp_path):
 def test_cli_rejects_unimplemented_modes():
     r = subprocess.run([CLI, os.path.join(GOLD, "g0.pp"), os.path.join(GOLD, "g1.pp"), "--stacking"], capture_output=True, text=True)
     assert r.returncode == 255 and "does not implement" in r.stderr
+
+
+CLI_P = os.path.join(ROOT, "locarna_b200", "bin", "locarna_p_b200")
+CASES_P = json.load(open(os.path.join(GOLD, "locarna_p_cli.json")))
+
+
+def _close_lines(a: str, b: str, n_int: int) -> bool:
+    """Same lines; the leading n_int integer fields identical, the probability equal to the 6 printed digits (+- one unit)."""
+    la, lb = a.splitlines(), b.splitlines()
+    if len(la) != len(lb):
+        return False
+    for x, y in zip(la, lb):
+        fx, fy = x.split(), y.split()
+        if fx[:n_int] != fy[:n_int] or abs(float(fx[n_int]) - float(fy[n_int])) > 2e-6 * abs(float(fy[n_int])):
+            return False
+    return True
+
+
+@pytest.mark.parametrize("case", CASES_P, ids=lambda c: "%s-%s" % ("_".join(c["args"]) or "default", c["A"]))
+def test_locarna_p_cli_matches_reference(case, tmp_path):
+    """stdout and the probability files of the reference's own locarna_p binary (tests/golden/locarna_p_cli.json)."""
+    am, bm = str(tmp_path / "am"), str(tmp_path / "bm")
+    r = subprocess.run([CLI_P, os.path.join(GOLD, case["A"]), os.path.join(GOLD, case["B"]), "--write-arcmatch-probs", am, "--write-basematch-probs", bm]
+                       + case["args"], capture_output=True, text=True)
+    assert r.returncode == case["rc"], r.stderr
+    assert r.stdout == case["stdout"]
+    assert _close_lines(open(am).read(), case["am"], 4)
+    assert _close_lines(open(bm).read(), case["bm"], 2)

@@ -18,6 +18,22 @@ for it in range(2):
     inf = ctx.info(0)
     print("GPU inside: wall %.3fs kernel %.1f ms launches %d K=%d tasks=%d cells=%.3g (%.1f G cell updates/s) Z=%r" % (
         w, ctx.kernel_ms, ctx.launches, inf.n_arcmatches, inf.n_tasks, inf.cells, inf.cells / ctx.kernel_ms / 1e6, ctx.partition_function(0)), flush=True)
+if len(sys.argv) > 3 and sys.argv[3] == "probs":
+    for it in range(2):
+        t = time.time(); ctx.run_pf_probs(1.0, 0.001); w = time.time() - t
+        print("GPU inside + outside + probabilities: wall %.3fs kernel %.1f ms launches %d" % (w, ctx.kernel_ms, ctx.launches), flush=True)
+    if check == "ref":
+        t = time.time(); r = O.ref_inside_p(paths[0], paths[1], flags, probs=True, timing=True); w = time.time() - t
+        amp = ctx.arcmatch_probs(0); am, _ = ctx.arcmatches(0)
+        got = {tuple(am[k]): amp[k] for k in range(len(am)) if amp[k] >= 0.001}
+        want = {tuple(x[:4]): x[4] for x in r["am_probs"]}
+        bm = ctx.basematch_probs(0)
+        wantb = {(x[0], x[1]): x[2] for x in r["bm_probs"]}
+        rel = lambda x, y: abs(x - y) / max(abs(x), abs(y), 1e-300)
+        print("reference: %.1fs (inside %s ms, outside+probs %s ms); am probs >= 0.001: %d (GPU %d), max rel dev %.2e; bm probs >= 0.001: %d, max rel dev %.2e" % (
+            w, r["time_pf_ms"].get("inside"), r["time_pf_ms"].get("outside"), len(want), len(got), max([rel(got.get(k, 0), want[k]) for k in want] or [0]),
+            len(wantb), max([rel(bm[i][j], p) for (i, j), p in wantb.items()] or [0])), flush=True)
+    sys.exit(0)
 if check != "none":
     t = time.time()
     r = O.ref_inside_p(paths[0], paths[1], flags, timing=True) if check == "ref" else O.port_inside_p(paths[0], paths[1], flags)
