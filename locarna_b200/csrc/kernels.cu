@@ -264,27 +264,30 @@ __device__ __forceinline__ void dp_step2(Sweep<NC> &S, const BoxInit &init, cons
 // anti-diagonals before their target because both arcs span >= 3 positions, so they are final). Lists whose prefix is longer
 // than 32 entries continue with further (unprefetched) blocks.
 struct Stream3 {
-    const uint4 *base;       // the pair's entries
+    const uint4 *entl;       // the pair's entries + lane
     const int *q;            // q[k] = S-order start of local anti-diagonal k (sptr + s0)
     int q_cap;               // largest valid index into q
-    int qx, qy, qz, qw;      // bounds q[t], q[t+1] of the list prefetched next, and the two values after them (loaded two steps ahead)
+    int qreg, qbase;         // lane l holds q[qbase + l]: the list bounds are read with one SHFL instead of a load per step
+    int qx, qy;              // bounds q[t], q[t+1] of the list prefetched next
     uint4 nA, nB;            // prefetched lists of the next two cell steps (lanes beyond the list hold the poison entry)
-    int pm, pd, ps;          // gather in flight: M(source), D, accumulator index (-1: none)
+    int pm, pd, ps;          // gather in flight: M(source), D, accumulator index (lanes without a hit: -inf into their own slot)
 };
 
 // filter one block of the list of target anti-diagonal t and start the gathers; returns whether lane 31 still belongs to the prefix.
 // Lanes beyond the list hold x = 0xffffffff (fails the box filter) and s = -1 (outside every prefix).
 template <int NC>
 __device__ __forceinline__ bool stream_block(const uint4 v, const BoxGeom &g, const int *box, int ring_t, int s0, uint32_t org, uint32_t lim, int d0,
-                                             int &pm, int &pd, int &ps) {
+                                             int lane, int &pm, int &pd, int &ps) {
     const uint32_t t1 = v.x - org, t2 = lim - v.y;
-    ps = -1;
-    if (((t1 | t2) & 0x80008000u) == 0) {
-        const int p = LB_ENT_LO(t1), q = LB_ENT_HI(t1);
-        pm = __ldcg(box + (p + q) * g.nslots + ((q - p - g.vmin) >> 1));
-        pd = (int)v.z;
-        ps = ring_t + ((LB_ENT_HI(v.y) - LB_ENT_LO(v.y) - d0) >> 1);
-    }
+    const bool in = ((t1 | t2) & 0x80008000u) == 0;
+    const uint32_t p = t1 & 0xffffu, q = t1 >> 16;
+    // branch-free: lanes without a hit fold a dummy value into their own junk slot behind the ring
+    // (unconditional load from a safe address: a select after a predicated load would wait for the data inside this step)
+    uint32_t idx = (p + q) * (uint32_t)g.nslots + ((q - p - (uint32_t)g.vmin) >> 1);
+    idx = in ? idx : 0u;
+    pm = __ldcg(box + idx);
+    pd = in ? (int)v.z : LB_NEG;
+    ps = in ? ring_t + ((LB_ENT_HI(v.y) - LB_ENT_LO(v.y) - d0) >> 1) : RING * RingStride<NC>::v + lane;
     return (__ballot_sync(0xffffffffu, (int)v.w >= s0) >> 31) != 0;
 }
 
@@ -300,19 +303,30 @@ __device__ void fill_box(const DevCtx &c, const DevPair &pr, const BoxGeom &g, c
 
     const int s0 = g.al + g.bl;
     Stream3 st;
-    st.base = (const uint4 *)(c.ent + pr.am_base);
+    st.entl = (const uint4 *)(c.ent + pr.am_base) + lane;
+    asm("" : "+l"(st.entl));   // keep the lane's entry pointer in a register pair: one IMAD.WIDE per prefetch
+    const int *boxr = box;
+    asm("" : "+l"(boxr));      // likewise for the gathers (the CTA-uniform box address would be rebuilt with 64-bit adds)
     st.q = c.sptr + pr.sptr + s0;
     st.q_cap = pr.lenA + pr.lenB + 2 - s0;
-    auto qld = [&](int k) { return __ldg(st.q + min(k, st.q_cap)); };
-    auto eld = [&](int e, int e_end) { uint4 v = make_uint4(0xffffffffu, 0u, 0u, 0xffffffffu); if (e < e_end) v = __ldg(st.base + e); return v; };
+    // list bounds: lane l keeps q[qbase + l]; stream(u) needs q[u+2 .. u+5], the window is moved when u+5 leaves it
+    st.qbase = 3;
+    st.qreg = __ldg(st.q + min(st.qbase + lane, st.q_cap));
+    auto qget = [&](int k) { return __shfl_sync(0xffffffffu, st.qreg, k - st.qbase); };
+    // entries e+lane of [e, e_end); lanes beyond the list get the poison fields x (fails the box filter) and w (outside every prefix)
+    auto eld = [&](uint4 &v, int e, int e_end) {
+        if (e + lane < e_end) v = __ldg(st.entl + e);
+        else { v.x = 0xffffffffu; v.w = 0xffffffffu; }
+    };
     // the first list handled (after cell step 1) is the one of local anti-diagonal 3
     {
-        const int q3 = qld(3), q4 = qld(4);
-        st.qx = qld(5); st.qy = qld(6); st.qz = qld(7); st.qw = qld(8);
-        st.nA = eld(q3 + lane, q4);
-        st.nB = eld(q4 + lane, st.qx);
+        const int q3 = qget(3), q4 = qget(4);
+        st.qx = qget(5); st.qy = qget(6);
+        st.nA = make_uint4(0xffffffffu, 0u, 0u, 0xffffffffu); st.nB = st.nA;
+        eld(st.nA, q3, q4);
+        eld(st.nB, q4, st.qx);
     }
-    st.ps = -1; st.pm = st.pd = 0;
+    st.ps = RING * NWP + lane; st.pm = 0; st.pd = 0;
     const uint32_t org = (uint32_t)g.al | ((uint32_t)g.bl << 16);
     const uint32_t lim = (uint32_t)(g.al + g.Rn) | ((uint32_t)(g.bl + g.Cn) << 16);
     const int d0 = g.bl - g.al + g.vmin;
@@ -350,20 +364,22 @@ __device__ void fill_box(const DevCtx &c, const DevPair &pr, const BoxGeom &g, c
     // ago), refill nx with the list of anti-diagonal u + 4
     auto stream = [&](int u, uint4 &nx) {
         __syncwarp();
-        if (st.ps >= 0) atomicMax(&ws.arcbuf[st.ps], st.pm + st.pd);
+        atomicMax(&ws.arcbuf[st.ps], st.pm + st.pd);
         const int ring_t = ((s0 + u + 2) & (RING - 1)) * NWP;
-        bool more = stream_block<NC>(nx, g, box, ring_t, s0, org, lim, d0, st.pm, st.pd, st.ps);
-        if (more) {   // prefix longer than one block: further, unprefetched blocks (rare outside the top level box)
-            const int qa = qld(u + 2), qb = qld(u + 3);
+        bool more = stream_block<NC>(nx, g, boxr, ring_t, s0, org, lim, d0, lane, st.pm, st.pd, st.ps);
+        if (more) {   // prefix longer than one block: further, unprefetched blocks
+            const int qa = qget(u + 2), qb = qget(u + 3);
             for (int e = qa + 32; more && e < qb; e += 32) {
-                const uint4 v = eld(e + lane, qb);
-                if (st.ps >= 0) atomicMax(&ws.arcbuf[st.ps], st.pm + st.pd);
-                more = stream_block<NC>(v, g, box, ring_t, s0, org, lim, d0, st.pm, st.pd, st.ps);
+                uint4 v = make_uint4(0xffffffffu, 0u, 0u, 0xffffffffu);
+                eld(v, e, qb);
+                atomicMax(&ws.arcbuf[st.ps], st.pm + st.pd);
+                more = stream_block<NC>(v, g, boxr, ring_t, s0, org, lim, d0, lane, st.pm, st.pd, st.ps);
             }
         }
-        nx = eld(st.qx + lane, st.qy);        // list of anti-diagonal u + 4: [q[u+4], q[u+5])
-        st.qx = st.qy; st.qy = st.qz; st.qz = st.qw;
-        st.qw = qld(u + 8);
+        eld(nx, st.qx, st.qy);                // list of anti-diagonal u + 4: [q[u+4], q[u+5])
+        // bounds for the next call: q[u+5], q[u+6]; move the window (to start at u+3) when u+6 leaves it
+        if (u + 6 - st.qbase >= 32) { st.qbase = u + 3; st.qreg = __ldg(st.q + min(st.qbase + lane, st.q_cap)); }
+        st.qx = st.qy; st.qy = qget(u + 6);
         __syncwarp();
     };
     int u = 1;

@@ -516,7 +516,7 @@ static int upload_chunk(lb200_ctx *c, int p0, int p1) {
     dc.col_bytes = (dc.col_pad + max_rows / 2 + max_cols + 32 * nc_inst + 8 + 3) & ~3;
     const int old_region = (dc.max_rows + 2) * 4 + dc.rowcode_bytes + dc.colcode_bytes;
     dc.region_bytes = (std::max(old_region, dc.row_words * 4 + dc.col_bytes) + 15) & ~15;  // arcbuf stays 16-byte aligned
-    const int smem_bytes = (64 + dc.arcbuf_words) * 4 + dc.region_bytes;
+    const int smem_bytes = (64 + dc.arcbuf_words + 32) * 4 + dc.region_bytes;   // + 32 junk slots behind the ring (lanes without an arc-match hit)
     if (smem_bytes > (int)c->prop.sharedMemPerBlockOptin) return fail(c, LB200_ERR_UNSUPPORTED, "problem needs %d bytes of shared memory per warp", smem_bytes);
     int ctas_per_sm = 1;
     CUDA_TRY(c, configure_kernels(nc_inst, smem_bytes, &ctas_per_sm));
