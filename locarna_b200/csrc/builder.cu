@@ -268,6 +268,26 @@ __global__ void group_bounds_kernel(BuildCtx b, unsigned n) {
     b.qstart[q] = (int)lo;
 }
 
+// Dependency-driven schedule of the D fill (kernels.cu dfill_dep_kernel): the level-sorted tasks are regrouped by blocks of
+// sb_pairs pairs (stable, so every block keeps the order level descending, area descending) and every (pair, level group) learns how
+// many tasks of its pair lie in higher level groups - the number of completions a task has to wait for.
+__global__ void dep_prepare_kernel(BuildCtx b, unsigned n) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const DevTask tk = b.tasks[t];
+    b.tkeys[t] = (unsigned)tk.pair / (unsigned)b.sb_pairs;
+    b.tvals[t] = t;
+    atomicAdd(b.levcnt + (size_t)tk.pair * b.n_groups + (((int)tk.al + (int)tk.bl) >> 1), 1);
+}
+// levcnt[pair][g] := number of tasks of the pair in level groups > g
+__global__ void dep_need_kernel(BuildCtx b, int n_pairs) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    int *row = b.levcnt + (size_t)p * b.n_groups;
+    int run = 0;
+    for (int g = b.n_groups - 1; g >= 0; g--) { const int c = row[g]; row[g] = run; run += c; }
+}
+
 // ------------------------------------------------------------------------------------------------ host entry points
 #define TRY(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return e__; } while (0)
 
@@ -313,13 +333,28 @@ cudaError_t builder_fill(const BuildCtx &b, int n_pairs, long long total_am, lon
     return cudaGetLastError();
 }
 
-cudaError_t builder_sort_tasks(const BuildCtx &b, unsigned n_tasks, void *tmp, size_t tmp_bytes, cudaStream_t st) {
+cudaError_t builder_sort_tasks(const BuildCtx &b, int n_pairs, unsigned n_tasks, void *tmp, size_t tmp_bytes, cudaStream_t st) {
     if (n_tasks > 0) {
         size_t need = tmp_bytes;
         TRY(cub::DeviceRadixSort::SortPairs(tmp, need, b.tkeys, b.tkeys_sorted, b.tvals, b.tvals_sorted, (long long)n_tasks, 0, 32, st));
         gather_tasks_kernel<<<(n_tasks + 255) / 256, 256, 0, st>>>(b, n_tasks);
     }
     group_bounds_kernel<<<(4097 + 255) / 256, 256, 0, st>>>(b, n_tasks);
+    if (b.levcnt != nullptr) {
+        TRY(cudaMemsetAsync(b.levcnt, 0, (size_t)n_pairs * b.n_groups * sizeof(int), st));
+        if (n_tasks > 0) {
+            dep_prepare_kernel<<<(n_tasks + 255) / 256, 256, 0, st>>>(b, n_tasks);
+            if (b.sb_pairs >= n_pairs) {   // one block: the level order is the claim order
+                TRY(cudaMemcpyAsync(b.tvals_sorted, b.tvals, (size_t)n_tasks * sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
+            } else {
+                int sb_bits = 1;
+                while ((1 << sb_bits) < (n_pairs + b.sb_pairs - 1) / b.sb_pairs) sb_bits++;
+                size_t need = tmp_bytes;
+                TRY(cub::DeviceRadixSort::SortPairs(tmp, need, b.tkeys, b.tkeys_sorted, b.tvals, b.tvals_sorted, (long long)n_tasks, 0, sb_bits, st));
+            }
+            dep_need_kernel<<<(n_pairs + 127) / 128, 128, 0, st>>>(b, n_pairs);
+        }
+    }
     return cudaGetLastError();
 }
 

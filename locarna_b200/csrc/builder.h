@@ -28,12 +28,16 @@ struct BuildCtx {
     unsigned *n_tasks;
     int *qstart;                                // 4098 entries
     DevPairStats *stats;
+    // dependency-driven D-fill schedule (nullptr: not built). After builder_sort_tasks: tvals_sorted = task order grouped by blocks of
+    // sb_pairs pairs, levcnt[pair * n_groups + g] = number of tasks of the pair in level groups > g
+    int *levcnt;
+    int n_groups, sb_pairs;
 };
 
 cudaError_t builder_count(const BuildCtx &b, int n_pairs, long long total_cells, void *tmp, size_t tmp_bytes, size_t *tmp_need, cudaStream_t st);
 size_t builder_sort_tmp_bytes(long long total_am, int n_pairs);
 cudaError_t builder_fill(const BuildCtx &b, int n_pairs, long long total_am, long long sptr_total, void *tmp, size_t tmp_bytes, cudaStream_t st);
-cudaError_t builder_sort_tasks(const BuildCtx &b, unsigned n_tasks, void *tmp, size_t tmp_bytes, cudaStream_t st);
+cudaError_t builder_sort_tasks(const BuildCtx &b, int n_pairs, unsigned n_tasks, void *tmp, size_t tmp_bytes, cudaStream_t st);
 
 }  // namespace lb200
 #endif

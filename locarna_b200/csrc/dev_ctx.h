@@ -34,6 +34,11 @@ struct DevCtx {
     TraceJob *trace_stack;   // per pair trace_stack_cap pending boxes
     int trace_stack_cap;
     int *error_flag;
+    // dependency-driven D fill (dfill_dep_kernel): one persistent launch per batch instead of one launch per level group
+    const unsigned *dep_order;   // task indices grouped by pair blocks, inside a block level descending (builder.cu dep_prepare_kernel)
+    const int *dep_need;         // [pair * n_groups + level group]: completed tasks of the pair a task of that group waits for
+    int *dep_done;               // per pair: completed tasks
+    int n_groups, n_tasks;
 };
 
 #endif

@@ -315,7 +315,7 @@ __device__ void fill_box(const DevCtx &c, const DevPair &pr, const BoxGeom &g, c
     auto qget = [&](int k) { return __shfl_sync(0xffffffffu, st.qreg, k - st.qbase); };
     // entries e+lane of [e, e_end); lanes beyond the list get the poison fields x (fails the box filter) and w (outside every prefix)
     auto eld = [&](uint4 &v, int e, int e_end) {
-        if (e + lane < e_end) v = __ldg(st.entl + e);
+        if (e + lane < e_end) v = __ldcg(st.entl + e);   // L2: the D field may have been written by another CTA of this launch
         else { v.x = 0xffffffffu; v.w = 0xffffffffu; }
     };
     // the first list handled (after cell step 1) is the one of local anti-diagonal 3
@@ -641,6 +641,33 @@ __device__ __forceinline__ void carve(const DevCtx &c, int *smem, WarpSmem &ws) 
 // D-fill kernel: persistent one-warp CTAs pull the tasks of one scheduling level from an atomic cursor.
 // Tasks of a level are mutually independent: a task reads D only for arc matches strictly inside its
 // box, whose left ends have a larger al+bl (aligner.cc:675-728; levels = al+bl descending, two at a time).
+// One D-fill task: the M box of the left ends (al, bl), then the D entries of all arc matches with these left ends
+// (aligner.cc:574-657). D values are read and written through L2 (ld.cg / plain stores): with the dependency-driven
+// schedule they are produced by other CTAs of the same launch.
+template <int NCMAX, bool GB>
+__device__ __forceinline__ void dfill_task(const DevCtx &c, const DevTask &task, const DevPair &pr, const BoxGeom &g, const BoxInit &init,
+                                           const WarpSmem &ws, int *box, bool nolp, int lane) {
+    if ((g.umax + 1) * g.nslots > c.scratch_words) { if (lane == 0) atomicExch(c.error_flag, 2); return; }
+    if (!run_box<NCMAX, GB, false>(c, pr, g, init, ws, box)) { if (lane == 0) atomicExch(c.error_flag, 1); return; }
+    const DevArcMatch *am = c.am + pr.am_base;
+    DevEntry *ent = c.ent + pr.am_base;
+    const int sh = nolp ? 2 : 1;
+    for (int k = task.run_start + lane; k < task.run_start + task.run_count; k += 32) {
+        const DevArcMatch x = am[k];
+        if (nolp && x.inner < 0) continue;
+        const int ar = (x.ends_a >> 12) & 0xfff, br = (x.ends_b >> 12) & 0xfff;
+        const int mv = box_get(box, g, ar - sh - g.al, br - sh - g.bl);
+        int d;
+        if (nolp) {
+            const DevArcMatch in = am[x.inner];
+            const int a = (mv < LB_NEG_LIMIT) ? LB_NEG : mv + in.score;
+            const int y = max(a, __ldcg(&ent[in.spos].d));
+            d = (y < LB_NEG_LIMIT) ? LB_NEG : y + x.score;
+        } else d = (mv < LB_NEG_LIMIT) ? LB_NEG : mv + x.score;
+        ent[x.spos].d = d;
+    }
+}
+
 template <int NCMAX, bool GB>
 __global__ void __launch_bounds__(32, 32) dfill_kernel(DevCtx c, int q) {
     extern __shared__ __align__(16) int smem[];
@@ -664,27 +691,52 @@ __global__ void __launch_bounds__(32, 32) dfill_kernel(DevCtx c, int q) {
         const DevPair pr = c.pairs[task.pair];
         BoxGeom g;
         setup_box2(c, pr, task.al, task.bl, task.R, task.C, g, ws);
-        if ((g.umax + 1) * g.nslots > c.scratch_words) { if (lane == 0) atomicExch(c.error_flag, 2); continue; }
-        if (!run_box<NCMAX, GB, false>(c, pr, g, init, ws, box)) { if (lane == 0) atomicExch(c.error_flag, 1); continue; }
-        // ---- D entries of all arc matches with these left ends (aligner.cc:574-657)
-        const DevArcMatch *am = c.am + pr.am_base;
-        DevEntry *ent = c.ent + pr.am_base;
-        const int sh = nolp ? 2 : 1;
-        for (int k = task.run_start + lane; k < task.run_start + task.run_count; k += 32) {
-            const DevArcMatch x = am[k];
-            if (nolp && x.inner < 0) continue;
-            const int ar = (x.ends_a >> 12) & 0xfff, br = (x.ends_b >> 12) & 0xfff;
-            const int mv = box_get(box, g, ar - sh - g.al, br - sh - g.bl);
-            int d;
-            if (nolp) {
-                const DevArcMatch in = am[x.inner];
-                const int a = (mv < LB_NEG_LIMIT) ? LB_NEG : mv + in.score;
-                const int y = max(a, ent[in.spos].d);
-                d = (y < LB_NEG_LIMIT) ? LB_NEG : y + x.score;
-            } else d = (mv < LB_NEG_LIMIT) ? LB_NEG : mv + x.score;
-            ent[x.spos].d = d;
+        dfill_task<NCMAX, GB>(c, task, pr, g, init, ws, box, nolp, lane);
+        __syncwarp();
+    }
+}
+
+// Dependency-driven D fill: ONE persistent launch per batch. Tasks are claimed in the order dep_order[] (blocks of pairs; inside a
+// block level group descending, box area descending). A task of level group L reads D entries only of arc matches of ITS OWN PAIR
+// in level groups > L, so instead of a grid-wide barrier per level it waits until dep_done[pair] reaches dep_need[pair][L]
+// (all tasks of the pair in higher groups). Every task it waits for precedes it in the claim order and is therefore already held
+// by a resident warp: no deadlock, no co-residency requirement. Grouping by pair blocks keeps the entry tables of the pairs in
+// flight (a few hundred pairs x 0.4 MB) inside the 126 MB L2 instead of cycling through the whole batch once per level.
+template <int NCMAX, bool GB>
+__global__ void __launch_bounds__(32, 32) dfill_dep_kernel(DevCtx c, int *cursor) {
+    extern __shared__ __align__(16) int smem[];
+    const int lane = threadIdx.x;
+    WarpSmem ws;
+    carve(c, smem, ws);
+    int *box = c.scratch + (size_t)blockIdx.x * c.scratch_words;
+    const bool nolp = c.params.no_lonely_pairs != 0;
+    BoxInit init;
+    init.col_base = c.params.open; init.col_step = c.params.gap; init.row_base = c.params.open; init.row_step = c.params.gap;
+
+    for (;;) {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(cursor, 1);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= c.n_tasks) break;
+        const DevTask task = c.tasks[c.dep_order[k]];
+        const DevPair pr = c.pairs[task.pair];
+        BoxGeom g;
+        setup_box2(c, pr, task.al, task.bl, task.R, task.C, g, ws);   // reads only the band and the sequences: overlaps the wait
+        if (lane == 0) {
+            const int need = c.dep_need[(size_t)task.pair * c.n_groups + (((int)task.al + (int)task.bl) >> 1)];
+            const int *done = c.dep_done + task.pair;
+            int have;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(have) : "l"(done) : "memory");
+                if (have >= need) break;
+                __nanosleep(200);
+            }
         }
         __syncwarp();
+        dfill_task<NCMAX, GB>(c, task, pr, g, init, ws, box, nolp, lane);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(c.dep_done + task.pair, 1);
     }
 }
 
@@ -1165,6 +1217,13 @@ void launch_dfill(const DevCtx &c, int ncmax, bool generic_borders, int grid, in
     LB_DISPATCH(ncmax, CALL);
 #undef CALL
 }
+void launch_dfill_dep(const DevCtx &c, int ncmax, bool generic_borders, int grid, int smem_bytes, int *cursor, cudaStream_t st) {
+#define CALL(N)                                                                                      \
+    if (generic_borders) dfill_dep_kernel<N, true><<<grid, 32, smem_bytes, st>>>(c, cursor); \
+    else dfill_dep_kernel<N, false><<<grid, 32, smem_bytes, st>>>(c, cursor)
+    LB_DISPATCH(ncmax, CALL);
+#undef CALL
+}
 void launch_dfill_sl(const DevCtx &c, int grid, int smem_bytes, int q, cudaStream_t st) { dfill_sl_kernel<<<grid, 32, smem_bytes, st>>>(c, q); }
 void launch_trace_sl(const DevCtx &c, int grid, int smem_bytes, int pair_begin, int pair_end, int *cursor, cudaStream_t st) {
     if (c.params.sequ_local) trace_sl_kernel<true><<<grid, 32, smem_bytes, st>>>(c, pair_begin, pair_end, cursor);
@@ -1199,7 +1258,7 @@ cudaError_t configure_kernels(int ncmax, int smem_bytes, int *dfill_ctas_per_sm)
     cudaError_t e = cudaSuccess;
 #define SET(K) if (e == cudaSuccess) e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)
 #define CALL(N)                                                                                                         \
-    SET((dfill_kernel<N, true>)); SET((dfill_kernel<N, false>)); SET((toplevel_kernel<N, true>)); SET((toplevel_kernel<N, false>)); \
+    SET((dfill_kernel<N, true>)); SET((dfill_kernel<N, false>)); SET((dfill_dep_kernel<N, true>)); SET((dfill_dep_kernel<N, false>)); SET((toplevel_kernel<N, true>)); SET((toplevel_kernel<N, false>)); \
     SET((trace_kernel<N, true, true>)); SET((trace_kernel<N, false, true>)); SET((trace_kernel<N, true, false>)); SET((trace_kernel<N, false, false>)); \
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(dfill_ctas_per_sm, dfill_kernel<N, false>, 32, smem_bytes)
     LB_DISPATCH(ncmax, CALL);
