@@ -355,7 +355,7 @@ def main():
         except (OSError, ValueError):
             pass
         roofline = {"bound": "hbm", "achieved": alg_bytes / dfill_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": alg_bytes / dfill_s / 1e9 / hbm_peak, "traffic": traffic, "kernel": "dfill_kernel",
+                    "frac": alg_bytes / dfill_s / 1e9 / hbm_peak, "traffic": traffic, "kernel": "dfill_dep_kernel" if dfill_launches <= K else "dfill_kernel",
                     "launch_ms": dfill_ms / max(1, dfill_launches), "peak_source": peak_src,
                     "note": "max-plus DP: the binding roof is integer ALU issue, see roofline_alu"}
         roofline_alu = {"bound": "int_alu", "achieved": ops / dfill_s / 1e12, "peak": alu_peak / 1e12, "unit": "Tintop/s",

@@ -186,6 +186,10 @@ __global__ void scatter_kernel(BuildCtx b, long long total) {
         e.d = LB_NEG;
         e.s = (int)(x.ends_a & 0xfff) + (int)(x.ends_b & 0xfff) - 2;
         b.ent[t] = e;
+        if (b.ent8 != nullptr) {
+            const uint32_t al1 = (x.ends_a & 0xfff) - 1, bl1 = (x.ends_b & 0xfff) - 1, ar = x.ends_a >> 12, br = x.ends_b >> 12;
+            b.ent8[t] = make_uint2(al1 | (bl1 << 9) | (ar << 18) | ((br & 31u) << 27), LB_PACK_W1(br, LB_NEG));
+        }
         b.am[g].spos = (int)(t - p.am_base);
     }
 }

@@ -20,6 +20,7 @@ struct BuildCtx {
     int *cell_start;                            // total_cells + 1: counts, then exclusive offsets (global L-order index)
     DevArcMatch *am;
     DevEntry *ent;
+    uint2 *ent8;                                // packed copy of the S-order (dev_types.h LB_PACK_*), nullptr for long sequences
     int *sptr;
     unsigned long long *skeys, *skeys_sorted;
     unsigned *svals, *svals_sorted;

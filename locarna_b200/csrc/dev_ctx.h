@@ -12,6 +12,7 @@ struct DevCtx {
     const int *band_lo, *band_hi;
     const int *sptr;
     DevEntry *ent;           // S-order; ent[k].d = D(arcA,arcB)
+    uint2 *ent8;             // packed copy streamed by the single-state sweep (nullptr: stream ent); D is kept in both
     const DevArcMatch *am;   // L-order
     const DevTask *tasks;
     const int *qstart;       // task range of level group q = 4095 - ((al+bl)>>1): tasks[qstart[q] .. qstart[q+1])

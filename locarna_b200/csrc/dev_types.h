@@ -54,6 +54,13 @@ struct DevPairStats {
 //   d = D(arcA, arcB)                 written by the D-fill task of the left ends (al, bl); -inf until then
 //   s = (al-1) + (bl-1)               anti-diagonal of the source cell
 struct DevEntry { uint32_t x, y; int d; int s; };
+// Packed S-order entry (8 bytes, one LDG.64) for batches whose sequences are at most LB_PACK_MAXLEN long: the copy of the S-order
+// the single-state sweep streams (half the bytes per anti-diagonal list). 9-bit positions, 28-bit D:
+//   w0 = (al-1) | (bl-1) << 9 | ar << 18 | (br & 31) << 27        w1 = br >> 5 | D28 << 4
+//   D28 = D for finite D (|D| < 2^27), LB_PACK_NEG for -inf.  s = (al-1) + (bl-1) is recomputed.
+#define LB_PACK_MAXLEN 510
+#define LB_PACK_NEG (-(1 << 27))
+#define LB_PACK_W1(br, d) ((uint32_t)((br) >> 5) | ((uint32_t)(((d) < LB_NEG_LIMIT) ? LB_PACK_NEG : (d)) << 4))
 #define LB_ENT_LO(v) ((int)((v) & 0xffffu))
 #define LB_ENT_HI(v) ((int)((v) >> 16))
 

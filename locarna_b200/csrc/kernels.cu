@@ -265,12 +265,14 @@ __device__ __forceinline__ void dp_step2(Sweep<NC> &S, const BoxInit &init, cons
 // than 32 entries continue with further (unprefetched) blocks.
 struct Stream3 {
     const uint4 *entl;       // the pair's entries + lane
+    const uint2 *entp;       // packed entries + lane (nullptr: the batch is not packed)
     const int *q;            // q[k] = S-order start of local anti-diagonal k (sptr + s0)
     int q_cap;               // largest valid index into q
     int qreg, qbase;         // lane l holds q[qbase + l]: the list bounds are read with one SHFL instead of a load per step
     int qx, qy;              // bounds q[t], q[t+1] of the list prefetched next
     uint4 nA, nB;            // prefetched lists of the next two cell steps (lanes beyond the list hold the poison entry)
     int pm, pd, ps;          // gather in flight: M(source), D, accumulator index (lanes without a hit: -inf into their own slot)
+    int pm2, pd2, ps2;       // second gather in flight (packed batches: entries 32..63 of the list)
 };
 
 // filter one block of the list of target anti-diagonal t and start the gathers; returns whether lane 31 still belongs to the prefix.
@@ -303,8 +305,10 @@ __device__ void fill_box(const DevCtx &c, const DevPair &pr, const BoxGeom &g, c
 
     const int s0 = g.al + g.bl;
     Stream3 st;
+    const bool packed = c.ent8 != nullptr;
     st.entl = (const uint4 *)(c.ent + pr.am_base) + lane;
-    asm("" : "+l"(st.entl));   // keep the lane's entry pointer in a register pair: one IMAD.WIDE per prefetch
+    st.entp = packed ? (const uint2 *)(c.ent8 + pr.am_base) + lane : nullptr;
+    if (packed) asm("" : "+l"(st.entp)); else asm("" : "+l"(st.entl));   // keep the lane's entry pointer in a register pair: one IMAD.WIDE per prefetch
     const int *boxr = box;
     asm("" : "+l"(boxr));      // likewise for the gathers (the CTA-uniform box address would be rebuilt with 64-bit adds)
     st.q = c.sptr + pr.sptr + s0;
@@ -314,9 +318,31 @@ __device__ void fill_box(const DevCtx &c, const DevPair &pr, const BoxGeom &g, c
     st.qreg = __ldg(st.q + min(st.qbase + lane, st.q_cap));
     auto qget = [&](int k) { return __shfl_sync(0xffffffffu, st.qreg, k - st.qbase); };
     // entries e+lane of [e, e_end); lanes beyond the list get the poison fields x (fails the box filter) and w (outside every prefix)
+    // (loads go to L2: the D field may have been written by another CTA of this launch). Packed batches prefetch TWO blocks per
+    // list into the same four registers (entries e+lane -> v.x/v.y, e+32+lane -> v.z/v.w), so that only prefixes longer than 64
+    // entries fall back to synchronous blocks; their poison entry has source (0, 0) and target (511, 511): it fails the box filter
+    // and lies in a prefix only for s0 = 0.
+    constexpr uint32_t POISON0 = (511u << 18) | (31u << 27), POISON1 = 15u;
     auto eld = [&](uint4 &v, int e, int e_end) {
-        if (e + lane < e_end) v = __ldcg(st.entl + e);   // L2: the D field may have been written by another CTA of this launch
-        else { v.x = 0xffffffffu; v.w = 0xffffffffu; }
+        if (packed) {
+            if (e + lane < e_end) { const uint2 t = __ldcg(st.entp + e); v.x = t.x; v.y = t.y; }
+            else { v.x = POISON0; v.y = POISON1; }
+            if (e + 32 + lane < e_end) { const uint2 t = __ldcg(st.entp + e + 32); v.z = t.x; v.w = t.y; }
+            else { v.z = POISON0; v.w = POISON1; }
+        } else {
+            if (e + lane < e_end) v = __ldcg(st.entl + e);
+            else { v.x = 0xffffffffu; v.w = 0xffffffffu; }
+        }
+    };
+    // packed (w0, w1) -> the 16-byte entry fields
+    auto unpack = [&](uint32_t w0, uint32_t w1) {
+        uint4 r;
+        r.x = (w0 & 0x1ffu) | ((w0 << 7) & 0x01ff0000u);
+        r.y = ((w0 >> 18) & 0x1ffu) | ((w0 >> 27) << 16) | ((w1 & 15u) << 21);
+        const int d = (int)w1 >> 4;
+        r.z = (uint32_t)(d == LB_PACK_NEG ? LB_NEG : d);
+        r.w = (r.x & 0xffffu) + (r.x >> 16);
+        return r;
     };
     // the first list handled (after cell step 1) is the one of local anti-diagonal 3
     {
@@ -327,6 +353,7 @@ __device__ void fill_box(const DevCtx &c, const DevPair &pr, const BoxGeom &g, c
         eld(st.nB, q4, st.qx);
     }
     st.ps = RING * NWP + lane; st.pm = 0; st.pd = 0;
+    st.ps2 = RING * NWP + lane; st.pm2 = 0; st.pd2 = 0;
     const uint32_t org = (uint32_t)g.al | ((uint32_t)g.bl << 16);
     const uint32_t lim = (uint32_t)(g.al + g.Rn) | ((uint32_t)(g.bl + g.Cn) << 16);
     const int d0 = g.bl - g.al + g.vmin;
@@ -366,12 +393,22 @@ __device__ void fill_box(const DevCtx &c, const DevPair &pr, const BoxGeom &g, c
         __syncwarp();
         atomicMax(&ws.arcbuf[st.ps], st.pm + st.pd);
         const int ring_t = ((s0 + u + 2) & (RING - 1)) * NWP;
-        bool more = stream_block<NC>(nx, g, boxr, ring_t, s0, org, lim, d0, lane, st.pm, st.pd, st.ps);
-        if (more) {   // prefix longer than one block: further, unprefetched blocks
+        bool more;
+        if (packed) {
+            atomicMax(&ws.arcbuf[st.ps2], st.pm2 + st.pd2);
+            more = stream_block<NC>(unpack(nx.x, nx.y), g, boxr, ring_t, s0, org, lim, d0, lane, st.pm, st.pd, st.ps);
+            if (more) more = stream_block<NC>(unpack(nx.z, nx.w), g, boxr, ring_t, s0, org, lim, d0, lane, st.pm2, st.pd2, st.ps2);
+            else st.ps2 = RING * NWP + lane;   // nothing in flight: the landing of the next stage goes to the junk slot
+        } else more = stream_block<NC>(nx, g, boxr, ring_t, s0, org, lim, d0, lane, st.pm, st.pd, st.ps);
+        if (more) {   // prefix longer than the prefetched blocks: further, synchronous blocks
             const int qa = qget(u + 2), qb = qget(u + 3);
-            for (int e = qa + 32; more && e < qb; e += 32) {
+            for (int e = qa + (packed ? 64 : 32); more && e < qb; e += 32) {
                 uint4 v = make_uint4(0xffffffffu, 0u, 0u, 0xffffffffu);
-                eld(v, e, qb);
+                if (packed) {
+                    uint2 t = make_uint2(POISON0, POISON1);
+                    if (e + lane < qb) t = __ldcg(st.entp + e);
+                    v = unpack(t.x, t.y);
+                } else if (e + lane < qb) v = __ldcg(st.entl + e);
                 atomicMax(&ws.arcbuf[st.ps], st.pm + st.pd);
                 more = stream_block<NC>(v, g, boxr, ring_t, s0, org, lim, d0, lane, st.pm, st.pd, st.ps);
             }
@@ -665,6 +702,7 @@ __device__ __forceinline__ void dfill_task(const DevCtx &c, const DevTask &task,
             d = (y < LB_NEG_LIMIT) ? LB_NEG : y + x.score;
         } else d = (mv < LB_NEG_LIMIT) ? LB_NEG : mv + x.score;
         ent[x.spos].d = d;
+        if (c.ent8 != nullptr) c.ent8[pr.am_base + x.spos].y = LB_PACK_W1(br, d);
     }
 }
 

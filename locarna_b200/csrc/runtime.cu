@@ -54,7 +54,7 @@ void launch_trace_sl(const DevCtx &c, int grid, int smem_bytes, int pair_begin, 
 
 using namespace lb200;
 
-cudaError_t lb200_reset_d(DevEntry *ent, size_t n, cudaStream_t st);
+cudaError_t lb200_reset_d(DevEntry *ent, uint2 *ent8, size_t n, cudaStream_t st);
 
 namespace {
 
@@ -129,11 +129,12 @@ struct lb200_ctx {
     DevBuf d_pf_esig, d_pf_bpow, d_pf_d, d_pf_z, d_pf_scratch, d_pf_dp, d_pf_amp, d_pf_mats, d_pf_cta;
     PfCtx pf_last; bool pf_have = false; bool pf_probs_done = false; long long pf_mat_doubles = 0;
     int max_box_words = 1, max_len = 1;
-    DevBuf d_pairs, d_codes, d_band_lo, d_band_hi, d_sptr, d_ent, d_am, d_tasks, d_top, d_scratch, d_cursor, d_flag, d_levcnt, d_done;
+    DevBuf d_pairs, d_codes, d_band_lo, d_band_hi, d_sptr, d_ent, d_am, d_tasks, d_top, d_scratch, d_cursor, d_flag, d_levcnt, d_done, d_ent8;
+    int pack_entries = 1;  // 8-byte packed S-order copy for the single-state sweep when every sequence is <= LB_PACK_MAXLEN (LB200_PACK=0 disables)
     int dfill_mode = 2;   // 2: automatic, 1: dependency-driven persistent launch (LB200_DFILL=dep), 0: one launch per level group (LB200_DFILL=levels)
     int sb_pairs = 1 << 30;   // pair block of the dependency-driven order (LB200_SB_PAIRS; default: one block)
     ~lb200_ctx() {
-        DevBuf *all[] = {&d_pairs, &d_codes, &d_band_lo, &d_band_hi, &d_sptr, &d_ent, &d_am, &d_tasks, &d_top, &d_scratch, &d_cursor, &d_flag, &d_levcnt, &d_done,
+        DevBuf *all[] = {&d_pairs, &d_codes, &d_band_lo, &d_band_hi, &d_sptr, &d_ent, &d_am, &d_tasks, &d_top, &d_scratch, &d_cursor, &d_flag, &d_levcnt, &d_done, &d_ent8,
                          &d_arc_left, &d_arc_right, &d_arc_weight, &d_lptr, &d_lcount, &d_am_seq, &d_cell_rev, &d_cell_start, &d_skeys, &d_skeys2,
                          &d_svals, &d_svals2, &d_tasks_unsorted, &d_tkeys, &d_tkeys2, &d_tvals, &d_tvals2, &d_ntasks, &d_qstart, &d_stats, &d_tmp, &d_tr_edges, &d_tr_str, &d_tr_stack,
                          &d_pf_esig, &d_pf_bpow, &d_pf_d, &d_pf_z, &d_pf_scratch, &d_pf_dp, &d_pf_amp, &d_pf_mats, &d_pf_cta,
@@ -226,6 +227,7 @@ int lb200_ctx_create(int device, lb200_ctx **out) {
     if (const char *s = getenv("LB200_ENVELOPE")) c->env_mode = strcmp(s, "host") == 0 ? 0 : 1;
     if (const char *s = getenv("LB200_DFILL")) c->dfill_mode = strcmp(s, "levels") == 0 ? 0 : strcmp(s, "dep") == 0 ? 1 : 2;
     if (const char *s = getenv("LB200_SB_PAIRS")) c->sb_pairs = std::max(1, atoi(s));
+    if (const char *s = getenv("LB200_PACK")) c->pack_entries = atoi(s) != 0;
     *out = c;
     return LB200_OK;
 }
@@ -574,6 +576,9 @@ static int upload_chunk(lb200_ctx *c, int p0, int p1) {
     CUDA_TRY(c, c->d_tvals2.ensure(task_cap * 4));
     CUDA_TRY(c, c->d_tmp.ensure(builder_sort_tmp_bytes((long long)std::max<size_t>(total_am, 1), P)));
     b.am = (DevArcMatch *)c->d_am.p; b.ent = (DevEntry *)c->d_ent.p;
+    const bool pack = c->pack_entries && !sl && max_rows - 1 <= LB_PACK_MAXLEN && max_cols - 1 <= LB_PACK_MAXLEN;
+    if (pack) CUDA_TRY(c, c->d_ent8.ensure(std::max<size_t>(total_am, 1) * sizeof(uint2)));
+    b.ent8 = pack ? (uint2 *)c->d_ent8.p : nullptr;
     b.skeys = (unsigned long long *)c->d_skeys.p; b.skeys_sorted = (unsigned long long *)c->d_skeys2.p;
     b.svals = (unsigned *)c->d_svals.p; b.svals_sorted = (unsigned *)c->d_svals2.p;
     b.tasks_unsorted = (DevTask *)c->d_tasks_unsorted.p; b.tasks = (DevTask *)c->d_tasks.p;
@@ -606,7 +611,7 @@ static int upload_chunk(lb200_ctx *c, int p0, int p1) {
     CUDA_TRY(c, c->d_flag.ensure(16));
     dc.pairs = (const DevPair *)c->d_pairs.p; dc.codes = (const uint8_t *)c->d_codes.p;
     dc.band_lo = (const int *)c->d_band_lo.p; dc.band_hi = (const int *)c->d_band_hi.p; dc.sptr = (const int *)c->d_sptr.p;
-    dc.ent = (DevEntry *)c->d_ent.p; dc.am = (const DevArcMatch *)c->d_am.p;
+    dc.ent = (DevEntry *)c->d_ent.p; dc.ent8 = b.ent8; dc.am = (const DevArcMatch *)c->d_am.p;
     dc.tasks = (const DevTask *)c->d_tasks.p; dc.top = (DevTopResult *)c->d_top.p; dc.scratch = (int *)c->d_scratch.p;
     dc.qstart = (const int *)c->d_qstart.p; dc.cursor = (int *)c->d_cursor.p;
     dc.error_flag = (int *)c->d_flag.p;
@@ -703,7 +708,7 @@ static int run_chunk(lb200_ctx *c, int flags) {
     CUDA_TRY(c, cudaEventRecord(c->ev0, st));
     CUDA_TRY(c, cudaMemsetAsync(c->d_cursor.p, 0, 4100 * 4, st));
     CUDA_TRY(c, cudaMemsetAsync(c->d_flag.p, 0, 16, st));
-    CUDA_TRY(c, lb200_reset_d((DevEntry *)c->d_ent.p, R.total_am, st));
+    CUDA_TRY(c, lb200_reset_d((DevEntry *)c->d_ent.p, dc.ent8, R.total_am, st));
     int64_t launches = 1;
     int dfill_launches = 0;
     if (dc.dep_order != nullptr) {   // one persistent launch, tasks ordered by their own dependencies
@@ -1051,12 +1056,15 @@ int lb200_pair_alignment(const lb200_ctx *c, int pair, int *ea, int *eb, char *s
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------------
-__global__ void reset_d_kernel(DevEntry *ent, size_t n) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) ent[i].d = LB_NEG;
+__global__ void reset_d_kernel(DevEntry *ent, uint2 *ent8, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        ent[i].d = LB_NEG;
+        if (ent8 != nullptr) ent8[i].y = (ent8[i].y & 15u) | ((uint32_t)LB_PACK_NEG << 4);
+    }
 }
-cudaError_t lb200_reset_d(DevEntry *ent, size_t n, cudaStream_t st) {
+cudaError_t lb200_reset_d(DevEntry *ent, uint2 *ent8, size_t n, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     const int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
-    reset_d_kernel<<<grid, 256, 0, st>>>(ent, n);
+    reset_d_kernel<<<grid, 256, 0, st>>>(ent, ent8, n);
     return cudaGetLastError();
 }

@@ -87,3 +87,37 @@ def test_chunked_batches_equal_single_batch(synth_dir, monkeypatch):
     for k in range(len(pairs)):
         assert c1.alignment(k) == c2.alignment(k)
         assert c1.info(k).cells == c2.info(k).cells
+
+
+NON_SL_FLAGSETS = [f for f in FLAGSETS if not f.get("struct-local")]
+
+
+@pytest.mark.parametrize("mode,pack", [("dep", "1"), ("dep", "0"), ("levels", "1"), ("levels", "0")])
+@pytest.mark.parametrize("flags", NON_SL_FLAGSETS)
+def test_schedules_and_entry_formats(synth_dir, monkeypatch, flags, mode, pack):
+    """The dependency-driven persistent D fill (LB200_DFILL=dep; chosen automatically only for large batches) and the level schedule,
+    each with the packed 8-byte and the 16-byte entry stream: D table, score and cell count bit-exact against the oracle."""
+    monkeypatch.setenv("LB200_DFILL", mode)
+    monkeypatch.setenv("LB200_PACK", pack)
+    pairs = [tuple(synth_dir["cfg2"][:2]), tuple(synth_dir["cfg3"][:2]), tuple(synth_dir["short"][:2]),
+             (synth_dir["short"][0], synth_dir["cfg3"][5])]
+    check_pairs(pairs, flags)
+
+
+@pytest.mark.parametrize("sb", ["1", "3"])
+def test_dependency_schedule_pair_blocks_and_traceback(synth_dir, monkeypatch, sb):
+    """Dependency-driven schedule with the claim order regrouped by pair blocks (LB200_SB_PAIRS), all-vs-all family batch with
+    traceback: same scores and alignments as the level schedule, scores equal to the oracle's."""
+    fam = synth_dir["cfg3"]
+    pairs = [(fam[i], fam[j]) for i in range(6) for j in range(i)]
+    flags = {"noLP": True, "max-diff-am": 30}
+    monkeypatch.setenv("LB200_DFILL", "levels")
+    c1 = gpu_align(pairs, flags, capi.RUN_TRACE)
+    monkeypatch.setenv("LB200_DFILL", "dep")
+    monkeypatch.setenv("LB200_SB_PAIRS", sb)
+    c2 = gpu_align(pairs, flags, capi.RUN_TRACE)
+    assert c1.scores() == c2.scores()
+    for k, (a, b) in enumerate(pairs):
+        assert c1.alignment(k) == c2.alignment(k)
+        if k % 4 == 0:
+            assert c2.scores()[k] == O.port_align(a, b, flags, do_trace=False)["score"]
