@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cstring>
 #include <exception>
+#include <fstream>
 #include <memory>
 #include <ostream>
 #include <string>
@@ -68,15 +69,21 @@ struct ScoringParams {  // scoring.hh:59-166 (defaults of the locarna CLI)
     int match = 50, mismatch = 0, indel = -150, indel_opening = -750, unpaired_penalty = 0;
     int struct_weight = 200, tau_factor = 50, exclusion = 0, temperature_alipf = 300;
     bool use_ribosum = true, stacking = false, new_stacking = false, mea_scoring = false;
+    //! background probability of a base pair (ScoringParams::exp_probA / exp_probB, scoring.hh:123-127); < 0: the CLI's default
+    //! 1/(2 len) per sequence (locarna.cc:662-663). One value serves both sequences, as with `locarna --exp-prob`.
+    double exp_prob = -1.0;
 };
 
 class RnaData {  // PP 2.0 input (rna_data.cc:984-1103); p_bpcut as in RnaData(file, p_bpcut, ...)
     std::string file_;
     double p_bpcut_;
+    int max_bp_span_;
 public:
-    RnaData(const std::string &file, double p_bpcut) : file_(file), p_bpcut_(p_bpcut) {}
+    //! max_bp_span: PFoldParams::max_bp_span of the reference's constructor (rna_data.hh:102-106); -1 = unrestricted
+    RnaData(const std::string &file, double p_bpcut, int max_bp_span = -1) : file_(file), p_bpcut_(p_bpcut), max_bp_span_(max_bp_span) {}
     const std::string &filename() const { return file_; }
     double arc_cutoff_prob() const { return p_bpcut_; }
+    int max_bp_span() const { return max_bp_span_; }
 };
 
 class Alignment {  // alignment.hh:84-281
@@ -152,6 +159,50 @@ private:
     std::vector<SeqEntry> rows_;
 };
 
+//! One arc (basepairs.hh:33-89): positions only; the reference's arc index is internal to the device tables.
+class Arc {
+    int left_, right_;
+public:
+    Arc(int l, int r) : left_(l), right_(r) {}
+    int left() const { return left_; }
+    int right() const { return right_; }
+};
+
+//! arc_matches.hh:37-102
+class ArcMatch {
+    Arc a_, b_;
+    size_t idx_;
+public:
+    ArcMatch(const Arc &a, const Arc &b, size_t idx) : a_(a), b_(b), idx_(idx) {}
+    const Arc &arcA() const { return a_; }
+    const Arc &arcB() const { return b_; }
+    size_t idx() const { return idx_; }
+};
+
+//! Read-only view of the arc matches the device builder enumerated for one pair, in the reference's index order
+//! (ArcMatches, arc_matches.hh:114-504; construction arc_matches.cc:130-188), with Scoring::arcmatch of each (scoring.cc:540-554).
+//! Obtained from Aligner::arc_matches(); the reference builds it on the host and hands it to Scoring / Aligner instead.
+class ArcMatches {
+    friend class Aligner;
+    std::vector<ArcMatch> ams_;
+    std::vector<int> scores_;
+public:
+    size_t num_arc_matches() const { return ams_.size(); }
+    const ArcMatch &arcmatch(size_t idx) const { return ams_.at(idx); }
+    //! Scoring::arcmatch(am) (non-stacked)
+    long get_score(const ArcMatch &am) const { return scores_.at(am.idx()); }
+    bool explicit_scores() const { return false; }
+    std::vector<ArcMatch>::const_iterator begin() const { return ams_.begin(); }
+    std::vector<ArcMatch>::const_iterator end() const { return ams_.end(); }
+    //! arc_matches.cc:285-311: lines "al ar bl br score"
+    void write_arcmatch_scores(const std::string &arcmatch_scores_file) const {
+        std::ofstream out(arcmatch_scores_file.c_str());
+        if (!out.is_open()) throw failure("Cannot open file " + arcmatch_scores_file + " for writing arcmatch-scores.");
+        for (const ArcMatch &am : ams_)
+            out << am.arcA().left() << " " << am.arcA().right() << " " << am.arcB().left() << " " << am.arcB().right() << " " << scores_[am.idx()] << "\n";
+    }
+};
+
 class AlignerParams {  // aligner_params.hh:51-115: same argument names, chained setters instead of named-argument objects
     friend class Aligner;
     const RnaData *rnaA_ = nullptr, *rnaB_ = nullptr;
@@ -182,8 +233,9 @@ public:
 class Aligner {  // aligner.hh:67-189
     std::shared_ptr<Context> ctx_;
     int pair_ = -1;
-    bool traced_ = false;
+    bool traced_ = false, have_ams_ = false;
     Alignment alignment_;
+    ArcMatches ams_;
 public:
     explicit Aligner(const AlignerParams &ap, int device = 0) : ctx_(std::make_shared<Context>(device)) {
         if (!ap.rnaA_ || !ap.rnaB_) throw failure("AlignerParams: seqA and seqB are mandatory");
@@ -197,6 +249,8 @@ public:
         p.struct_weight = s.struct_weight; p.indel = s.indel; p.indel_opening = s.indel_opening; p.tau = s.tau_factor;
         p.exclusion = s.exclusion; p.match = s.match; p.mismatch = s.mismatch; p.use_ribosum = s.use_ribosum;
         p.unpaired_penalty = s.unpaired_penalty; p.temperature_alipf = s.temperature_alipf;
+        if (ap.rnaA_->max_bp_span() != ap.rnaB_->max_bp_span()) throw failure("locarna_b200: both RnaData objects must use the same max_bp_span");
+        p.exp_prob = s.exp_prob; p.max_bp_span = ap.rnaA_->max_bp_span();
         p.no_lonely_pairs = ap.no_lonely_pairs_; p.struct_local = ap.struct_local_; p.sequ_local = ap.sequ_local_;
         strncpy(p.free_endgaps, ap.free_endgaps_.c_str(), sizeof(p.free_endgaps) - 1);
         ctx_->check(lb200_set_params(ctx_->get(), &p));
@@ -234,6 +288,21 @@ public:
         alignment_.strA_ = sa.substr(0, inf.lenA); alignment_.strB_ = sb.substr(0, inf.lenB);
     }
     const Alignment &get_alignment() const { return alignment_; }
+    //! arc matches and their scores as built on the device (no alignment is computed: lb200_upload only)
+    const ArcMatches &arc_matches() {
+        if (!have_ams_) {
+            ctx_->check(lb200_upload(ctx_->get()));
+            lb200_pair_info inf;
+            ctx_->check(lb200_pair_get_info(ctx_->get(), pair_, &inf));
+            const size_t K = (size_t)inf.n_arcmatches;
+            std::vector<int> al(K + 1), ar(K + 1), bl(K + 1), br(K + 1), sc(K + 1);
+            ctx_->check(lb200_pair_arcmatches(ctx_->get(), pair_, al.data(), ar.data(), bl.data(), br.data(), sc.data(), nullptr));
+            ams_.ams_.clear(); ams_.scores_.assign(sc.begin(), sc.begin() + K);
+            for (size_t k = 0; k < K; k++) ams_.ams_.emplace_back(Arc(al[k], ar[k]), Arc(bl[k], br[k]), k);
+            have_ams_ = true;
+        }
+        return ams_;
+    }
     void band(std::vector<int> &min_col, std::vector<int> &max_col) const {
         lb200_pair_info inf;
         ctx_->check(lb200_pair_get_info(ctx_->get(), pair_, &inf));
@@ -298,6 +367,8 @@ public:
         p.pf_double = 1;                                      // locarna_p.cc:285-294: the envelope is computed in double as well
         p.struct_weight = s.struct_weight; p.indel = s.indel; p.indel_opening = s.indel_opening; p.tau = s.tau_factor;
         p.match = s.match; p.mismatch = s.mismatch; p.use_ribosum = s.use_ribosum; p.temperature_alipf = s.temperature_alipf;
+        if (ap.rnaA_->max_bp_span() != ap.rnaB_->max_bp_span()) throw failure("locarna_b200: both RnaData objects must use the same max_bp_span");
+        p.exp_prob = s.exp_prob; p.max_bp_span = ap.rnaA_->max_bp_span();
         ctx_->check(lb200_set_params(ctx_->get(), &p));
         const int a = lb200_seq_add_pp(ctx_->get(), ap.rnaA_->filename().c_str());
         ctx_->check(a);

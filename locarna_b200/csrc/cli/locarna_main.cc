@@ -24,7 +24,7 @@ enum {
     O_TAU, O_EXCLUSION, O_STACKING, O_NEW_STACKING, O_STRUCT_LOCAL, O_SEQU_LOCAL, O_FREE_ENDGAPS, O_NORMALIZED, O_PENALIZED, O_WIDTH,
     O_CLUSTAL, O_STOCKHOLM, O_PP, O_LOCAL_OUTPUT, O_LOCAL_FILE_OUTPUT, O_POS_OUTPUT, O_WRITE_STRUCTURE, O_MIN_PROB, O_MAX_BPS_LENGTH_RATIO,
     O_MAX_DIFF_AM, O_MAX_DIFF, O_MAX_DIFF_AT_AM, O_MIN_TRACE_PROB, O_NOLP, O_MAXBPSPAN, O_TEMPERATURE_ALIPF, O_CONSENSUS_STRUCTURE,
-    O_UNSUPPORTED, O_DEVICE, O_VERSION, O_QUIET, O_VERBOSE, O_HELP
+    O_WRITE_ARCMATCH_SCORES, O_UNSUPPORTED, O_DEVICE, O_VERSION, O_QUIET, O_VERBOSE, O_HELP
 };
 bool parse_bool(const char *s) {
     const std::string v = s ? s : "";  // options.cc:867-880
@@ -53,14 +53,14 @@ int main(int argc, char **argv) {
         {"max-diff", required_argument, 0, O_MAX_DIFF}, {"max-diff-at-am", required_argument, 0, O_MAX_DIFF_AT_AM},
         {"min-trace-probability", required_argument, 0, O_MIN_TRACE_PROB}, {"noLP", no_argument, 0, O_NOLP},
         {"maxBPspan", required_argument, 0, O_MAXBPSPAN}, {"temperature-alipf", required_argument, 0, O_TEMPERATURE_ALIPF},
-        {"consensus-structure", required_argument, 0, O_CONSENSUS_STRUCTURE},
+        {"consensus-structure", required_argument, 0, O_CONSENSUS_STRUCTURE}, {"write-arcmatch-scores", required_argument, 0, O_WRITE_ARCMATCH_SCORES},
         // recognised, not implemented on the B200 path
         {"max-diff-aln", required_argument, 0, O_UNSUPPORTED}, {"max-diff-pw-aln", required_argument, 0, O_UNSUPPORTED},
         {"max-diff-relax", no_argument, 0, O_UNSUPPORTED}, {"kbest", required_argument, 0, O_UNSUPPORTED}, {"better", required_argument, 0, O_UNSUPPORTED},
         {"mea-alignment", no_argument, 0, O_UNSUPPORTED}, {"match-prob-method", required_argument, 0, O_UNSUPPORTED},
         {"read-match-probs", required_argument, 0, O_UNSUPPORTED}, {"write-match-probs", required_argument, 0, O_UNSUPPORTED},
         {"read-arcmatch-scores", required_argument, 0, O_UNSUPPORTED}, {"read-arcmatch-probs", required_argument, 0, O_UNSUPPORTED},
-        {"write-arcmatch-scores", required_argument, 0, O_UNSUPPORTED}, {"write-trace-probs", required_argument, 0, O_UNSUPPORTED},
+        {"write-trace-probs", required_argument, 0, O_UNSUPPORTED},
         {"alifold-consensus-dp", no_argument, 0, O_UNSUPPORTED}, {"ribofit", required_argument, 0, O_UNSUPPORTED},
         {"relaxed-anchors", no_argument, 0, O_UNSUPPORTED}, {"score-components", no_argument, 0, O_UNSUPPORTED},
         {"extended-pf", no_argument, 0, O_UNSUPPORTED}, {"quad-pf", no_argument, 0, O_UNSUPPORTED},
@@ -72,7 +72,9 @@ int main(int argc, char **argv) {
     int width = 120, device = 0;
     double min_prob = 0.001;
     bool quiet = false, local_output = false, local_file_output = false, write_structure = false, pos_output = false;
-    std::string clustal;
+    std::string clustal, arcmatch_scores_file;
+    int max_bp_span = -1;
+    bool verbose = false;
     int c, idx = 0;
     while ((c = getopt_long(argc, argv, "i:m:M:s:e:t:E:w:Lp:D:d:P:qvVh", longopts, &idx)) != -1) {
         switch (c) {
@@ -108,15 +110,17 @@ int main(int argc, char **argv) {
                 if (std::string(optarg) != "none") { std::cerr << "ERROR: --consensus-structure " << optarg << " needs ViennaRNA; only \"none\" is supported." << std::endl; return 255; }
                 break;
             case O_MAX_BPS_LENGTH_RATIO: if (atof(optarg) != 0.0) { std::cerr << "ERROR: --max-bps-length-ratio is not supported by locarna_b200." << std::endl; return 255; } break;
-            case O_MAXBPSPAN: if (atoi(optarg) != -1) { std::cerr << "ERROR: --maxBPspan is not supported by locarna_b200." << std::endl; return 255; } break;
-            case 'e': case O_EXP_PROB: case O_STACKING: case O_NEW_STACKING: case O_NORMALIZED: case O_PENALIZED: case O_STOCKHOLM: case O_PP:
+            case O_MAXBPSPAN: max_bp_span = atoi(optarg); break;
+            case 'e': case O_EXP_PROB: sp.exp_prob = atof(optarg); break;
+            case O_WRITE_ARCMATCH_SCORES: arcmatch_scores_file = optarg; break;
+            case O_STACKING: case O_NEW_STACKING: case O_NORMALIZED: case O_PENALIZED: case O_STOCKHOLM: case O_PP:
             case O_UNSUPPORTED:
                 std::cerr << "ERROR: option --" << (idx >= 0 && longopts[idx].name ? longopts[idx].name : "?")
                           << " selects a mode that locarna_b200 does not implement." << std::endl;
                 return 255;
             case O_DEVICE: device = atoi(optarg); break;
             case 'q': case O_QUIET: quiet = true; break;
-            case 'v': case O_VERBOSE: break;
+            case 'v': case O_VERBOSE: verbose = true; break;
             case 'V': case O_VERSION: std::cout << "locarna_b200 (LocARNA 2.0.1 pairwise path, B200)" << std::endl; return 0;
             case 'h': case O_HELP: std::cout << "usage: locarna_b200 [options as locarna] <fileA.pp> <fileB.pp>" << std::endl; return 0;
             default: return 255;
@@ -124,9 +128,14 @@ int main(int argc, char **argv) {
     }
     if (argc - optind != 2) { std::cerr << "ERROR: expected two input files (PP 2.0)." << std::endl; return 255; }
     try {
-        RnaData rnaA(argv[optind], min_prob), rnaB(argv[optind + 1], min_prob);
+        RnaData rnaA(argv[optind], min_prob, max_bp_span), rnaB(argv[optind + 1], min_prob, max_bp_span);
         ap.seqA(&rnaA).seqB(&rnaB).scoring(sp).min_prob(min_prob);
         Aligner aligner(ap, device);
+        if (!arcmatch_scores_file.empty()) {                                        // locarna.cc:705-720: write and return without aligning
+            if (verbose) std::cout << "Write arcmatch scores to file " << arcmatch_scores_file << " and exit." << std::endl;
+            aligner.arc_matches().write_arcmatch_scores(arcmatch_scores_file);
+            return 0;
+        }
         const infty_score_t score = aligner.align();
         if (!quiet) std::cout << "Score: " << score << std::endl << std::endl;     // locarna.cc:769-771
         aligner.trace();

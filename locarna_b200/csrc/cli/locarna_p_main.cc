@@ -15,7 +15,7 @@ using namespace LocARNA_B200;
 
 namespace {
 enum { O_INDEL_OPENING = 1000, O_RIBOSUM_FILE, O_USE_RIBOSUM, O_TEMPERATURE, O_PF_SCALE, O_WRITE_AM, O_WRITE_BM, O_MAX_DIFF_AT_AM, O_MIN_TRACE_PROB,
-       O_INCLUDE_AM_IN_BM, O_UNSUPPORTED, O_DEVICE };
+       O_INCLUDE_AM_IN_BM, O_MAXBPSPAN, O_UNSUPPORTED, O_DEVICE };
 bool parse_bool(const char *s) {
     const std::string v = s ? s : "";
     if (v == "t" || v == "true" || v == "on" || v == "1") return true;
@@ -37,10 +37,10 @@ int main(int argc, char **argv) {
         {"min-prob", required_argument, 0, 'p'}, {"max-diff-am", required_argument, 0, 'D'}, {"max-diff", required_argument, 0, 'd'},
         {"max-diff-at-am", required_argument, 0, O_MAX_DIFF_AT_AM}, {"min-trace-probability", required_argument, 0, O_MIN_TRACE_PROB},
         // recognised, not implemented on the B200 path
-        {"extended-pf", no_argument, 0, O_UNSUPPORTED}, {"quad-pf", no_argument, 0, O_UNSUPPORTED}, {"exp-prob", required_argument, 0, O_UNSUPPORTED},
+        {"extended-pf", no_argument, 0, O_UNSUPPORTED}, {"quad-pf", no_argument, 0, O_UNSUPPORTED}, {"exp-prob", required_argument, 0, 'e'},
         {"max-diff-aln", required_argument, 0, O_UNSUPPORTED}, {"max-diff-pw-aln", required_argument, 0, O_UNSUPPORTED},
         {"max-diff-relax", no_argument, 0, O_UNSUPPORTED}, {"fragment-match-probs", required_argument, 0, O_UNSUPPORTED},
-        {"relaxed-anchors", no_argument, 0, O_UNSUPPORTED}, {"maxBPspan", required_argument, 0, O_UNSUPPORTED}, {"ribofit", required_argument, 0, O_UNSUPPORTED},
+        {"relaxed-anchors", no_argument, 0, O_UNSUPPORTED}, {"maxBPspan", required_argument, 0, O_MAXBPSPAN}, {"ribofit", required_argument, 0, O_UNSUPPORTED},
         {"max-bps-length-ratio", required_argument, 0, O_UNSUPPORTED},
         {"device", required_argument, 0, O_DEVICE}, {"quiet", no_argument, 0, 'q'}, {"verbose", no_argument, 0, 'v'}, {"stopwatch", no_argument, 0, 'v'},
         {"version", no_argument, 0, 'V'}, {"help", no_argument, 0, 'h'}, {0, 0, 0, 0}};
@@ -48,10 +48,11 @@ int main(int argc, char **argv) {
     AlignerPParams ap;
     int device = 0;
     double min_prob = 0.001;
+    int max_bp_span = -1;
     bool quiet = false, verbose = false, include_am_in_bm = false;
     std::string am_file, bm_file;
     int c, idx = 0;
-    while ((c = getopt_long(argc, argv, "i:m:M:s:t:a:b:p:D:d:qvVh", longopts, &idx)) != -1) {
+    while ((c = getopt_long(argc, argv, "i:m:M:s:e:t:a:b:p:D:d:qvVh", longopts, &idx)) != -1) {
         switch (c) {
             case 'i': sp.indel = atoi(optarg); break;
             case O_INDEL_OPENING: sp.indel_opening = atoi(optarg); break;
@@ -63,6 +64,8 @@ int main(int argc, char **argv) {
             case 'M': sp.mismatch = atoi(optarg); break;
             case 's': sp.struct_weight = atoi(optarg); break;
             case 't': sp.tau_factor = atoi(optarg); break;
+            case 'e': sp.exp_prob = atof(optarg); break;
+            case O_MAXBPSPAN: max_bp_span = atoi(optarg); break;
             case O_TEMPERATURE: sp.temperature_alipf = atoi(optarg); break;
             case O_PF_SCALE: ap.pf_scale(atof(optarg)); break;
             case 'a': ap.min_am_prob(atof(optarg)); break;
@@ -89,7 +92,7 @@ int main(int argc, char **argv) {
     }
     if (argc - optind != 2) { std::cerr << "ERROR: expected two input files (PP 2.0)." << std::endl; return 255; }
     try {
-        RnaData rnaA(argv[optind], min_prob), rnaB(argv[optind + 1], min_prob);
+        RnaData rnaA(argv[optind], min_prob, max_bp_span), rnaB(argv[optind + 1], min_prob, max_bp_span);
         ap.seqA(&rnaA).seqB(&rnaB).scoring(sp).min_prob(min_prob);
         AlignerP aligner(ap, device);
         if (verbose) std::cout << "Run inside algorithm." << std::endl;

@@ -55,7 +55,7 @@ static bool next_line(std::istream &in, std::string &line) {
 static bool begins(const std::string &s, const char *p) { return s.compare(0, strlen(p), p) == 0; }
 
 // rna_data.cc:984-1103 (PP 2.0), multiple_alignment.cc:279-401 (sequence block), aux.cc:65-70
-bool read_pp(const std::string &path, double p_bpcut, Sequence &out, std::string &err) {
+bool read_pp(const std::string &path, double p_bpcut, Sequence &out, std::string &err, int max_bp_span) {
     std::ifstream in(path.c_str());
     if (!in) { err = "cannot open " + path; return false; }
     std::string line;
@@ -103,11 +103,11 @@ bool read_pp(const std::string &path, double p_bpcut, Sequence &out, std::string
         pi.push_back((int)i); pj.push_back((int)j); pp.push_back(p);
     }
     // the pairs were already filtered line by line; pass a cutoff that keeps them all
-    return make_sequence(name, seq, pi.data(), pj.data(), pp.data(), (int)pi.size(), -1.0, out, err);
+    return make_sequence(name, seq, pi.data(), pj.data(), pp.data(), (int)pi.size(), -1.0, out, err, max_bp_span);
 }
 
 bool make_sequence(const std::string &name, const std::string &seq, const int *pi, const int *pj, const double *pp, int npairs,
-                   double p_bpcut, Sequence &out, std::string &err) {
+                   double p_bpcut, Sequence &out, std::string &err, int max_bp_span) {
     out = Sequence();
     out.name = name;
     out.seq = seq;
@@ -125,6 +125,7 @@ bool make_sequence(const std::string &name, const std::string &seq, const int *p
     for (int k = 0; k < npairs; k++) {
         if (!(1 <= pi[k] && pi[k] < pj[k] && pj[k] <= out.len)) { err = "invalid base pair indices"; return false; }
         if (pp[k] <= p_bpcut) continue;
+        if (max_bp_span >= 0 && pj[k] - pi[k] + 1 > max_bp_span) continue;  // rna_data.cc:1078, bp_span = j-i+1 (aux.hh:333)
         uniq[std::make_pair(pi[k], pj[k])] = pp[k];
     }
     for (auto &kv : uniq) { out.pp_i.push_back(kv.first.first); out.pp_j.push_back(kv.first.second); out.pp_p.push_back(kv.second); }
@@ -168,7 +169,7 @@ void finish_sequence(Sequence &s, double min_prob) {
 // scoring.cc:201-265 (probToWeight with p_exp = 1/(2 len), aux.hh:216-220)
 std::vector<int> arc_weights(const Sequence &s, const Params &p) {
     std::vector<int> w(s.arcs.size());
-    const double pe = 1.0 / (2.0 * s.len);
+    const double pe = p.exp_prob >= 0 ? p.exp_prob : 1.0 / (2.0 * s.len);  // locarna.cc:662-663
     for (size_t k = 0; k < w.size(); k++) w[k] = (int)round2score(round(p.struct_weight * (1 - log(s.arc_prob[k]) / log(pe))));
     return w;
 }

@@ -175,6 +175,7 @@ static Params to_params(const lb200_params &p) {
     q.struct_weight = p.struct_weight; q.indel = p.indel; q.indel_opening = p.indel_opening; q.tau = p.tau; q.exclusion = p.exclusion;
     q.match = p.match; q.mismatch = p.mismatch; q.unpaired_penalty = p.unpaired_penalty; q.temperature_alipf = p.temperature_alipf;
     q.use_ribosum = p.use_ribosum != 0; q.pf_double = p.pf_double != 0;
+    q.exp_prob = p.exp_prob; q.max_bp_span = p.max_bp_span;
     return q;
 }
 
@@ -186,6 +187,7 @@ void lb200_default_params(lb200_params *p) {
     p->struct_weight = 200; p->indel = -150; p->indel_opening = -750; p->tau = 50; p->exclusion = 0;
     p->match = 50; p->mismatch = 0; p->use_ribosum = 1; p->unpaired_penalty = 0; p->temperature_alipf = 300;
     strcpy(p->free_endgaps, "----");
+    p->exp_prob = -1.0; p->max_bp_span = -1;
 }
 
 int lb200_ctx_create(int device, lb200_ctx **out) {
@@ -247,7 +249,7 @@ int lb200_seq_add_pp(lb200_ctx *c, const char *path) {
     if (!c || !path) return LB200_ERR_ARG;
     Sequence s;
     std::string err;
-    if (!read_pp(path, c->params.min_prob, s, err)) return fail(c, LB200_ERR_IO, "%s", err.c_str());
+    if (!read_pp(path, c->params.min_prob, s, err, c->params.max_bp_span)) return fail(c, LB200_ERR_IO, "%s", err.c_str());
     finish_sequence(s, c->params.min_prob);
     c->seqs.push_back(std::move(s));
     return (int)c->seqs.size() - 1;
@@ -257,7 +259,7 @@ int lb200_seq_add(lb200_ctx *c, const char *name, const char *seq, const int *pi
     if (!c || !seq || n < 0 || (n > 0 && (!pi || !pj || !pp))) return LB200_ERR_ARG;
     Sequence s;
     std::string err;
-    if (!make_sequence(name ? name : "seq", seq, pi, pj, pp, n, c->params.min_prob, s, err)) return fail(c, LB200_ERR_ARG, "%s", err.c_str());
+    if (!make_sequence(name ? name : "seq", seq, pi, pj, pp, n, c->params.min_prob, s, err, c->params.max_bp_span)) return fail(c, LB200_ERR_ARG, "%s", err.c_str());
     finish_sequence(s, c->params.min_prob);
     c->seqs.push_back(std::move(s));
     return (int)c->seqs.size() - 1;
@@ -528,6 +530,7 @@ static int upload_chunk(lb200_ctx *c, int p0, int p1) {
     int ctas_per_sm = 1;
     CUDA_TRY(c, configure_kernels(nc_inst, smem_bytes, &ctas_per_sm));
     if (sl) CUDA_TRY(c, configure_sl(smem_bytes, &ctas_per_sm));
+    if (const char *s = getenv("LB200_CTAS_PER_SM")) ctas_per_sm = std::max(1, std::min(ctas_per_sm, atoi(s)));   // experiment knob: fewer boxes in flight
     const int grid_cap = std::max(1, ctas_per_sm) * c->prop.multiProcessorCount;
     dc.scratch_words = max_box_words * (sl ? 8 : 1);  // structure local: eight matrices per box
     c->max_box_words = max_box_words; c->max_len = std::max(max_rows, max_cols);

@@ -23,6 +23,24 @@ def test_cli_output_matches_reference(case, tmp_path):
     assert open(clu).read() == case["clustal"]
 
 
+CASES_OPT = json.load(open(os.path.join(GOLD, "locarna_cli_options.json")))
+
+
+@pytest.mark.parametrize("case", CASES_OPT, ids=lambda c: "%s-%s" % ("_".join(c["args"]) or "default", c["A"]))
+def test_cli_exp_prob_maxbpspan_arcmatch_scores(case, tmp_path):
+    """--exp-prob, --maxBPspan and --write-arcmatch-scores against the reference binary (tools/make_golden_cli_options.py)."""
+    clu, ams = str(tmp_path / "out.aln"), str(tmp_path / "out.ams")
+    a, b = os.path.join(GOLD, case["A"]), os.path.join(GOLD, case["B"])
+    r = subprocess.run([CLI, a, b, "--clustal", clu] + case["args"], capture_output=True, text=True)
+    assert r.returncode == case["rc"], r.stderr
+    assert r.stdout == case["stdout"]
+    assert open(clu).read() == case["clustal"]
+    w = subprocess.run([CLI, a, b, "--write-arcmatch-scores", ams] + case["args"], capture_output=True, text=True)
+    assert w.returncode == case["ams_rc"], w.stderr
+    assert w.stdout == case["ams_stdout"]                      # writes the file and exits without aligning (locarna.cc:705-720)
+    assert open(ams).read() == case["arcmatch_scores"]
+
+
 def test_cli_rejects_unimplemented_modes():
     r = subprocess.run([CLI, os.path.join(GOLD, "g0.pp"), os.path.join(GOLD, "g1.pp"), "--stacking"], capture_output=True, text=True)
     assert r.returncode == 255 and "does not implement" in r.stderr

@@ -46,3 +46,29 @@ def test_run_without_device_fails_loudly(synth_dir):
     ctx = host_setup(a, b, {})
     with pytest.raises(capi.Error):
         ctx.run()
+
+
+def _cli_flags(args):
+    """reference CLI arguments of tests/golden/locarna_cli_options.json -> capi flag dict"""
+    names = {"-e": "exp-prob", "--exp-prob": "exp-prob", "--maxBPspan": "maxBPspan", "--max-diff-am": "max-diff-am"}
+    flags, k = {}, 0
+    while k < len(args):
+        if args[k] == "--noLP":
+            flags["noLP"] = True; k += 1
+        else:
+            v = args[k + 1]
+            flags[names[args[k]]] = float(v) if "." in v else int(v); k += 2
+    return flags
+
+
+def test_exp_prob_maxbpspan_arcmatch_scores_vs_reference_binary():
+    """--exp-prob (arc weights, scoring.cc:201-265 with locarna.cc:662-663) and --maxBPspan (rna_data.cc:1078): arc matches and
+    Scoring::arcmatch against the `--write-arcmatch-scores` output of the reference's own binary (fixture)."""
+    import json, os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    for case in json.load(open(os.path.join(gold, "locarna_cli_options.json"))):
+        ctx = host_setup(os.path.join(gold, case["A"]), os.path.join(gold, case["B"]), _cli_flags(case["args"]))
+        am, score = ctx.arcmatches(0)
+        mine = "".join("%d %d %d %d %d\n" % (x[0], x[1], x[2], x[3], s) for x, s in zip(am, score))
+        assert mine == case["arcmatch_scores"], case["args"]
+        ctx.close()

@@ -1,0 +1,32 @@
+"""Golden outputs of the reference's own `locarna` binary (oracle/_ref/locarna, run in the build container) for the options
+--exp-prob, --maxBPspan and --write-arcmatch-scores -> tests/golden/locarna_cli_options.json (inputs: tests/golden/g*.pp)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def main():
+    out = []
+    for args in (["--exp-prob", "0.01"], ["--maxBPspan", "30"], ["-e", "0.0005", "--maxBPspan", "45", "--noLP", "--max-diff-am", "20"], []):
+        for a, b in (("g0.pp", "g1.pp"), ("g2.pp", "g3.pp")):
+            clu, ams = os.path.join(GOLD, "tmp.aln"), os.path.join(GOLD, "tmp.ams")
+            pa, pb = os.path.join(GOLD, a), os.path.join(GOLD, b)
+            r = subprocess.run([O.REF_LOCARNA, pa, pb, "--clustal", clu] + args, capture_output=True, text=True)
+            w = subprocess.run([O.REF_LOCARNA, pa, pb, "--write-arcmatch-scores", ams] + args, capture_output=True, text=True)
+            out.append({"args": args, "A": a, "B": b, "rc": r.returncode, "stdout": r.stdout, "clustal": open(clu).read(),
+                        "ams_rc": w.returncode, "ams_stdout": w.stdout, "arcmatch_scores": open(ams).read()})
+            os.unlink(clu); os.unlink(ams)
+    with open(os.path.join(GOLD, "locarna_cli_options.json"), "w") as f:
+        json.dump(out, f, indent=0)
+    print("wrote", len(out), "cases")
+
+
+if __name__ == "__main__":
+    main()
