@@ -10,8 +10,9 @@ OBJS := $(OBJ)/kernels.o $(OBJ)/builder.o $(OBJ)/envelope.o $(OBJ)/runtime.o $(O
 
 CLI       := locarna_b200/bin/locarna_b200
 CLI_P     := locarna_b200/bin/locarna_p_b200
+CLI_TREE  := locarna_b200/bin/mlocarna_tree_b200
 
-all: $(LIB) $(CLI) $(CLI_P)
+all: $(LIB) $(CLI) $(CLI_P) $(CLI_TREE)
 
 $(OBJ):
 	mkdir -p $(OBJ)
@@ -34,6 +35,11 @@ $(CLI): $(SRC)/cli/locarna_main.cc include/locarna_b200.hh include/locarna_b200.
 
 # `locarna_p`-compatible front end (LocARNA-P: partition function, arc-match / base-match probabilities)
 $(CLI_P): $(SRC)/cli/locarna_p_main.cc include/locarna_b200.hh include/locarna_b200.h $(LIB)
+	mkdir -p locarna_b200/bin
+	/usr/bin/g++ -std=c++17 -O2 -Wall -Iinclude $< -o $@ -Llocarna_b200 -llocarna_b200 -Wl,-rpath,'$$ORIGIN/..'
+
+# all-vs-all guide-tree stage of mlocarna in one process (score matrix, score list, UPGMA tree), plain C ABI
+$(CLI_TREE): $(SRC)/cli/mlocarna_tree_main.cc include/locarna_b200.h $(LIB)
 	mkdir -p locarna_b200/bin
 	/usr/bin/g++ -std=c++17 -O2 -Wall -Iinclude $< -o $@ -Llocarna_b200 -llocarna_b200 -Wl,-rpath,'$$ORIGIN/..'
 

@@ -73,6 +73,7 @@ typedef struct lb200_params {
     char free_endgaps[8];         /* --free-endgaps "----": left1 right1 left2 right2 */
     int pf_double;                /* 1: envelope in double precision (locarna_p default) instead of long double */
     double exp_prob;              /* --exp-prob / -e            < 0 = not given: background probability 1/(2 len) per sequence (src/locarna.cc:662-663) */
+    double max_bps_length_ratio;  /* --max-bps-length-ratio     0 = off; keep only the ratio*length most probable base pairs per sequence (rna_data.cc:64-67) */
     int max_bp_span;              /* --maxBPspan                -1 = unrestricted; base pairs with j-i+1 > span are dropped on input (rna_data.cc:1078) */
 } lb200_params;
 

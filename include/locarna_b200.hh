@@ -77,10 +77,14 @@ struct ScoringParams {  // scoring.hh:59-166 (defaults of the locarna CLI)
 class RnaData {  // PP 2.0 input (rna_data.cc:984-1103); p_bpcut as in RnaData(file, p_bpcut, ...)
     std::string file_;
     double p_bpcut_;
+    double max_bps_length_ratio_;
     int max_bp_span_;
 public:
-    //! max_bp_span: PFoldParams::max_bp_span of the reference's constructor (rna_data.hh:102-106); -1 = unrestricted
-    RnaData(const std::string &file, double p_bpcut, int max_bp_span = -1) : file_(file), p_bpcut_(p_bpcut), max_bp_span_(max_bp_span) {}
+    //! as RnaData(filename, p_bpcut, max_bps_length_ratio, pfoldparams) (rna_data.hh:102-106); max_bp_span stands for
+    //! PFoldParams::max_bp_span, -1 = unrestricted
+    RnaData(const std::string &file, double p_bpcut, double max_bps_length_ratio = 0.0, int max_bp_span = -1)
+        : file_(file), p_bpcut_(p_bpcut), max_bps_length_ratio_(max_bps_length_ratio), max_bp_span_(max_bp_span) {}
+    double max_bps_length_ratio() const { return max_bps_length_ratio_; }
     const std::string &filename() const { return file_; }
     double arc_cutoff_prob() const { return p_bpcut_; }
     int max_bp_span() const { return max_bp_span_; }
@@ -249,8 +253,9 @@ public:
         p.struct_weight = s.struct_weight; p.indel = s.indel; p.indel_opening = s.indel_opening; p.tau = s.tau_factor;
         p.exclusion = s.exclusion; p.match = s.match; p.mismatch = s.mismatch; p.use_ribosum = s.use_ribosum;
         p.unpaired_penalty = s.unpaired_penalty; p.temperature_alipf = s.temperature_alipf;
-        if (ap.rnaA_->max_bp_span() != ap.rnaB_->max_bp_span()) throw failure("locarna_b200: both RnaData objects must use the same max_bp_span");
-        p.exp_prob = s.exp_prob; p.max_bp_span = ap.rnaA_->max_bp_span();
+        if (ap.rnaA_->max_bp_span() != ap.rnaB_->max_bp_span() || ap.rnaA_->max_bps_length_ratio() != ap.rnaB_->max_bps_length_ratio())
+            throw failure("locarna_b200: both RnaData objects must use the same max_bp_span and max_bps_length_ratio");
+        p.exp_prob = s.exp_prob; p.max_bp_span = ap.rnaA_->max_bp_span(); p.max_bps_length_ratio = ap.rnaA_->max_bps_length_ratio();
         p.no_lonely_pairs = ap.no_lonely_pairs_; p.struct_local = ap.struct_local_; p.sequ_local = ap.sequ_local_;
         strncpy(p.free_endgaps, ap.free_endgaps_.c_str(), sizeof(p.free_endgaps) - 1);
         ctx_->check(lb200_set_params(ctx_->get(), &p));
@@ -367,8 +372,9 @@ public:
         p.pf_double = 1;                                      // locarna_p.cc:285-294: the envelope is computed in double as well
         p.struct_weight = s.struct_weight; p.indel = s.indel; p.indel_opening = s.indel_opening; p.tau = s.tau_factor;
         p.match = s.match; p.mismatch = s.mismatch; p.use_ribosum = s.use_ribosum; p.temperature_alipf = s.temperature_alipf;
-        if (ap.rnaA_->max_bp_span() != ap.rnaB_->max_bp_span()) throw failure("locarna_b200: both RnaData objects must use the same max_bp_span");
-        p.exp_prob = s.exp_prob; p.max_bp_span = ap.rnaA_->max_bp_span();
+        if (ap.rnaA_->max_bp_span() != ap.rnaB_->max_bp_span() || ap.rnaA_->max_bps_length_ratio() != ap.rnaB_->max_bps_length_ratio())
+            throw failure("locarna_b200: both RnaData objects must use the same max_bp_span and max_bps_length_ratio");
+        p.exp_prob = s.exp_prob; p.max_bp_span = ap.rnaA_->max_bp_span(); p.max_bps_length_ratio = ap.rnaA_->max_bps_length_ratio();
         ctx_->check(lb200_set_params(ctx_->get(), &p));
         const int a = lb200_seq_add_pp(ctx_->get(), ap.rnaA_->filename().c_str());
         ctx_->check(a);

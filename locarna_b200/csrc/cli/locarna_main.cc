@@ -74,6 +74,7 @@ int main(int argc, char **argv) {
     bool quiet = false, local_output = false, local_file_output = false, write_structure = false, pos_output = false;
     std::string clustal, arcmatch_scores_file;
     int max_bp_span = -1;
+    double max_bps_length_ratio = 0.0;
     bool verbose = false;
     int c, idx = 0;
     while ((c = getopt_long(argc, argv, "i:m:M:s:e:t:E:w:Lp:D:d:P:qvVh", longopts, &idx)) != -1) {
@@ -109,7 +110,7 @@ int main(int argc, char **argv) {
             case O_CONSENSUS_STRUCTURE:
                 if (std::string(optarg) != "none") { std::cerr << "ERROR: --consensus-structure " << optarg << " needs ViennaRNA; only \"none\" is supported." << std::endl; return 255; }
                 break;
-            case O_MAX_BPS_LENGTH_RATIO: if (atof(optarg) != 0.0) { std::cerr << "ERROR: --max-bps-length-ratio is not supported by locarna_b200." << std::endl; return 255; } break;
+            case O_MAX_BPS_LENGTH_RATIO: max_bps_length_ratio = atof(optarg); break;
             case O_MAXBPSPAN: max_bp_span = atoi(optarg); break;
             case 'e': case O_EXP_PROB: sp.exp_prob = atof(optarg); break;
             case O_WRITE_ARCMATCH_SCORES: arcmatch_scores_file = optarg; break;
@@ -128,7 +129,7 @@ int main(int argc, char **argv) {
     }
     if (argc - optind != 2) { std::cerr << "ERROR: expected two input files (PP 2.0)." << std::endl; return 255; }
     try {
-        RnaData rnaA(argv[optind], min_prob, max_bp_span), rnaB(argv[optind + 1], min_prob, max_bp_span);
+        RnaData rnaA(argv[optind], min_prob, max_bps_length_ratio, max_bp_span), rnaB(argv[optind + 1], min_prob, max_bps_length_ratio, max_bp_span);
         ap.seqA(&rnaA).seqB(&rnaB).scoring(sp).min_prob(min_prob);
         Aligner aligner(ap, device);
         if (!arcmatch_scores_file.empty()) {                                        // locarna.cc:705-720: write and return without aligning

@@ -15,7 +15,7 @@ using namespace LocARNA_B200;
 
 namespace {
 enum { O_INDEL_OPENING = 1000, O_RIBOSUM_FILE, O_USE_RIBOSUM, O_TEMPERATURE, O_PF_SCALE, O_WRITE_AM, O_WRITE_BM, O_MAX_DIFF_AT_AM, O_MIN_TRACE_PROB,
-       O_INCLUDE_AM_IN_BM, O_MAXBPSPAN, O_UNSUPPORTED, O_DEVICE };
+       O_INCLUDE_AM_IN_BM, O_MAXBPSPAN, O_MAX_BPS_LENGTH_RATIO, O_UNSUPPORTED, O_DEVICE };
 bool parse_bool(const char *s) {
     const std::string v = s ? s : "";
     if (v == "t" || v == "true" || v == "on" || v == "1") return true;
@@ -41,7 +41,7 @@ int main(int argc, char **argv) {
         {"max-diff-aln", required_argument, 0, O_UNSUPPORTED}, {"max-diff-pw-aln", required_argument, 0, O_UNSUPPORTED},
         {"max-diff-relax", no_argument, 0, O_UNSUPPORTED}, {"fragment-match-probs", required_argument, 0, O_UNSUPPORTED},
         {"relaxed-anchors", no_argument, 0, O_UNSUPPORTED}, {"maxBPspan", required_argument, 0, O_MAXBPSPAN}, {"ribofit", required_argument, 0, O_UNSUPPORTED},
-        {"max-bps-length-ratio", required_argument, 0, O_UNSUPPORTED},
+        {"max-bps-length-ratio", required_argument, 0, O_MAX_BPS_LENGTH_RATIO},
         {"device", required_argument, 0, O_DEVICE}, {"quiet", no_argument, 0, 'q'}, {"verbose", no_argument, 0, 'v'}, {"stopwatch", no_argument, 0, 'v'},
         {"version", no_argument, 0, 'V'}, {"help", no_argument, 0, 'h'}, {0, 0, 0, 0}};
     ScoringParams sp;
@@ -49,6 +49,7 @@ int main(int argc, char **argv) {
     int device = 0;
     double min_prob = 0.001;
     int max_bp_span = -1;
+    double max_bps_length_ratio = 0.0;
     bool quiet = false, verbose = false, include_am_in_bm = false;
     std::string am_file, bm_file;
     int c, idx = 0;
@@ -66,6 +67,7 @@ int main(int argc, char **argv) {
             case 't': sp.tau_factor = atoi(optarg); break;
             case 'e': sp.exp_prob = atof(optarg); break;
             case O_MAXBPSPAN: max_bp_span = atoi(optarg); break;
+            case O_MAX_BPS_LENGTH_RATIO: max_bps_length_ratio = atof(optarg); break;
             case O_TEMPERATURE: sp.temperature_alipf = atoi(optarg); break;
             case O_PF_SCALE: ap.pf_scale(atof(optarg)); break;
             case 'a': ap.min_am_prob(atof(optarg)); break;
@@ -92,7 +94,7 @@ int main(int argc, char **argv) {
     }
     if (argc - optind != 2) { std::cerr << "ERROR: expected two input files (PP 2.0)." << std::endl; return 255; }
     try {
-        RnaData rnaA(argv[optind], min_prob, max_bp_span), rnaB(argv[optind + 1], min_prob, max_bp_span);
+        RnaData rnaA(argv[optind], min_prob, max_bps_length_ratio, max_bp_span), rnaB(argv[optind + 1], min_prob, max_bps_length_ratio, max_bp_span);
         ap.seqA(&rnaA).seqB(&rnaB).scoring(sp).min_prob(min_prob);
         AlignerP aligner(ap, device);
         if (verbose) std::cout << "Run inside algorithm." << std::endl;

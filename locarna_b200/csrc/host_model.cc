@@ -55,7 +55,7 @@ static bool next_line(std::istream &in, std::string &line) {
 static bool begins(const std::string &s, const char *p) { return s.compare(0, strlen(p), p) == 0; }
 
 // rna_data.cc:984-1103 (PP 2.0), multiple_alignment.cc:279-401 (sequence block), aux.cc:65-70
-bool read_pp(const std::string &path, double p_bpcut, Sequence &out, std::string &err, int max_bp_span) {
+bool read_pp(const std::string &path, double p_bpcut, Sequence &out, std::string &err, int max_bp_span, double max_bps_length_ratio) {
     std::ifstream in(path.c_str());
     if (!in) { err = "cannot open " + path; return false; }
     std::string line;
@@ -103,11 +103,11 @@ bool read_pp(const std::string &path, double p_bpcut, Sequence &out, std::string
         pi.push_back((int)i); pj.push_back((int)j); pp.push_back(p);
     }
     // the pairs were already filtered line by line; pass a cutoff that keeps them all
-    return make_sequence(name, seq, pi.data(), pj.data(), pp.data(), (int)pi.size(), -1.0, out, err, max_bp_span);
+    return make_sequence(name, seq, pi.data(), pj.data(), pp.data(), (int)pi.size(), -1.0, out, err, max_bp_span, max_bps_length_ratio);
 }
 
 bool make_sequence(const std::string &name, const std::string &seq, const int *pi, const int *pj, const double *pp, int npairs,
-                   double p_bpcut, Sequence &out, std::string &err, int max_bp_span) {
+                   double p_bpcut, Sequence &out, std::string &err, int max_bp_span, double max_bps_length_ratio) {
     out = Sequence();
     out.name = name;
     out.seq = seq;
@@ -127,6 +127,20 @@ bool make_sequence(const std::string &name, const std::string &seq, const int *p
         if (pp[k] <= p_bpcut) continue;
         if (max_bp_span >= 0 && pj[k] - pi[k] + 1 > max_bp_span) continue;  // rna_data.cc:1078, bp_span = j-i+1 (aux.hh:333)
         uniq[std::make_pair(pi[k], pj[k])] = pp[k];
+    }
+    if (max_bps_length_ratio > 0.0) {
+        // rna_data.cc:64-67, :1580-1601 (drop_worst_bps): only the `keep` most probable base pairs survive. The reference pops a
+        // min-heap filled in hash-table order, so WHICH of several equally probable pairs at the cut goes is not defined by its
+        // source; such an input is refused instead of guessed.
+        const size_t keep = (size_t)(max_bps_length_ratio * out.len);
+        if (uniq.size() > keep) {
+            std::vector<double> ps;
+            for (auto &kv : uniq) ps.push_back(kv.second);
+            std::sort(ps.begin(), ps.end(), [](double x, double y) { return x > y; });
+            if (keep > 0 && ps[keep - 1] == ps[keep]) { err = "--max-bps-length-ratio: equally probable base pairs at the cut (the reference's choice among them is unspecified)"; return false; }
+            const double thr = keep > 0 ? ps[keep - 1] : 2.0;
+            for (auto it = uniq.begin(); it != uniq.end();) { if (it->second < thr) it = uniq.erase(it); else ++it; }
+        }
     }
     for (auto &kv : uniq) { out.pp_i.push_back(kv.first.first); out.pp_j.push_back(kv.first.second); out.pp_p.push_back(kv.second); }
     return true;

@@ -20,6 +20,7 @@ struct Params {  // mirrors the `locarna` CLI options that reach the path (locar
     int match = 50, mismatch = 0, unpaired_penalty = 0, temperature_alipf = 300;
     bool use_ribosum = true;
     double exp_prob = -1.0;  // --exp-prob (locarna.cc:115, :662-663); < 0: not given, background probability 1/(2 len)
+    double max_bps_length_ratio = 0.0;  // --max-bps-length-ratio (locarna.cc:185, rna_data.cc:64-67); 0: keep all base pairs
     int max_bp_span = -1;    // --maxBPspan (locarna.cc:253, rna_data.cc:1078); -1: unrestricted
     bool pf_double = false;  // envelope in double (locarna_p default) instead of long double (locarna)
 };
@@ -54,10 +55,10 @@ struct ScoreTables {
 };
 
 // PP 2.0 reader
-bool read_pp(const std::string &path, double p_bpcut, Sequence &out, std::string &err, int max_bp_span = -1);
+bool read_pp(const std::string &path, double p_bpcut, Sequence &out, std::string &err, int max_bp_span = -1, double max_bps_length_ratio = 0.0);
 // sequence + explicit pair list (i, j, p): same filtering as the PP reader with #BPCUT = cutoff
 bool make_sequence(const std::string &name, const std::string &seq, const int *pi, const int *pj, const double *pp, int npairs,
-                   double p_bpcut, Sequence &out, std::string &err, int max_bp_span = -1);
+                   double p_bpcut, Sequence &out, std::string &err, int max_bp_span = -1, double max_bps_length_ratio = 0.0);
 void finish_sequence(Sequence &s, double min_prob);
 
 std::vector<int> arc_weights(const Sequence &s, const Params &p);

@@ -175,7 +175,7 @@ static Params to_params(const lb200_params &p) {
     q.struct_weight = p.struct_weight; q.indel = p.indel; q.indel_opening = p.indel_opening; q.tau = p.tau; q.exclusion = p.exclusion;
     q.match = p.match; q.mismatch = p.mismatch; q.unpaired_penalty = p.unpaired_penalty; q.temperature_alipf = p.temperature_alipf;
     q.use_ribosum = p.use_ribosum != 0; q.pf_double = p.pf_double != 0;
-    q.exp_prob = p.exp_prob; q.max_bp_span = p.max_bp_span;
+    q.exp_prob = p.exp_prob; q.max_bp_span = p.max_bp_span; q.max_bps_length_ratio = p.max_bps_length_ratio;
     return q;
 }
 
@@ -249,7 +249,7 @@ int lb200_seq_add_pp(lb200_ctx *c, const char *path) {
     if (!c || !path) return LB200_ERR_ARG;
     Sequence s;
     std::string err;
-    if (!read_pp(path, c->params.min_prob, s, err, c->params.max_bp_span)) return fail(c, LB200_ERR_IO, "%s", err.c_str());
+    if (!read_pp(path, c->params.min_prob, s, err, c->params.max_bp_span, c->params.max_bps_length_ratio)) return fail(c, LB200_ERR_IO, "%s", err.c_str());
     finish_sequence(s, c->params.min_prob);
     c->seqs.push_back(std::move(s));
     return (int)c->seqs.size() - 1;
@@ -259,7 +259,7 @@ int lb200_seq_add(lb200_ctx *c, const char *name, const char *seq, const int *pi
     if (!c || !seq || n < 0 || (n > 0 && (!pi || !pj || !pp))) return LB200_ERR_ARG;
     Sequence s;
     std::string err;
-    if (!make_sequence(name ? name : "seq", seq, pi, pj, pp, n, c->params.min_prob, s, err, c->params.max_bp_span)) return fail(c, LB200_ERR_ARG, "%s", err.c_str());
+    if (!make_sequence(name ? name : "seq", seq, pi, pj, pp, n, c->params.min_prob, s, err, c->params.max_bp_span, c->params.max_bps_length_ratio)) return fail(c, LB200_ERR_ARG, "%s", err.c_str());
     finish_sequence(s, c->params.min_prob);
     c->seqs.push_back(std::move(s));
     return (int)c->seqs.size() - 1;

@@ -72,3 +72,27 @@ def test_locarna_p_cli_matches_reference(case, tmp_path):
     assert r.stdout == case["stdout"]
     assert _close_lines(open(am).read(), case["am"], 4)
     assert _close_lines(open(bm).read(), case["bm"], 2)
+
+
+CLI_TREE = os.path.join(ROOT, "locarna_b200", "bin", "mlocarna_tree_b200")
+
+
+def test_mlocarna_tree_stage_archaea(tmp_path):
+    """BASELINE config 1 through the one-process guide-tree front end: the 21 pairwise scores of the reference's `locarna` binary
+    (mlocarna's tree-stage flags), mlocarna's result.matrix format and the UPGMA tree of the reference's Perl module."""
+    from locarna_b200 import allpairs
+    gold = json.load(open(os.path.join(GOLD, "reference_outputs.json")))
+    arch, tree = gold["archaea"], gold["trees"][0]
+    assert tree["names"] == arch["names"]
+    (tmp_path / "results").mkdir(); (tmp_path / "scores").mkdir()
+    files = [os.path.join(GOLD, "archaea", n + ".pp") for n in arch["names"]]
+    r = subprocess.run([CLI_TREE, "--tgtdir", str(tmp_path)] + files, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(tmp_path / "results" / "result.matrix").read() == allpairs.format_matrix(tree["matrix"])
+    assert open(tmp_path / "results" / "result.tree").read() == tree["newick"] + ";\n"
+    pairs = [tuple(p) for p in arch["pairs"]]
+    assert pairs == allpairs.all_vs_all(len(files))
+    assert open(tmp_path / "scores" / "scores-0").read() == allpairs.format_score_list(pairs, arch["scores"])
+    # explicit flags equal to the defaults, results on stdout
+    r2 = subprocess.run([CLI_TREE, "--struct-weight", "200", "-D", "30", "--noLP", "-p", "0.001"] + files, capture_output=True, text=True)
+    assert r2.returncode == 0 and r2.stdout == allpairs.format_matrix(tree["matrix"]) + tree["newick"] + ";\n"

@@ -50,7 +50,8 @@ def test_run_without_device_fails_loudly(synth_dir):
 
 def _cli_flags(args):
     """reference CLI arguments of tests/golden/locarna_cli_options.json -> capi flag dict"""
-    names = {"-e": "exp-prob", "--exp-prob": "exp-prob", "--maxBPspan": "maxBPspan", "--max-diff-am": "max-diff-am"}
+    names = {"-e": "exp-prob", "--exp-prob": "exp-prob", "--maxBPspan": "maxBPspan", "--max-diff-am": "max-diff-am",
+             "--max-bps-length-ratio": "max-bps-length-ratio"}
     flags, k = {}, 0
     while k < len(args):
         if args[k] == "--noLP":
@@ -72,3 +73,14 @@ def test_exp_prob_maxbpspan_arcmatch_scores_vs_reference_binary():
         mine = "".join("%d %d %d %d %d\n" % (x[0], x[1], x[2], x[3], s) for x, s in zip(am, score))
         assert mine == case["arcmatch_scores"], case["args"]
         ctx.close()
+
+
+def test_max_bps_length_ratio_refuses_ties_at_the_cut():
+    """drop_worst_bps (rna_data.cc:1580-1601) pops a heap filled in hash order: among equally probable pairs at the cut the
+    reference's choice is unspecified, so such an input is refused instead of guessed; a clear cut is accepted."""
+    seq = "GGGGAAAACCCC"
+    ctx = capi.Context(device=capi.DEVICE_NONE, flags={"max-bps-length-ratio": 0.2})    # keep = int(0.2 * 12) = 2
+    ctx.add_seq("ok", seq, [(1, 12, 0.9), (2, 11, 0.8), (3, 10, 0.7), (4, 9, 0.7)])
+    with pytest.raises(capi.Error):
+        ctx.add_seq("tie", seq, [(1, 12, 0.9), (2, 11, 0.7), (3, 10, 0.7), (4, 9, 0.6)])
+    ctx.close()
