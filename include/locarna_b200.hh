@@ -121,6 +121,19 @@ public:
     const std::string &nameA() const { return nameA_; }
     const std::string &nameB() const { return nameB_; }
     bool empty() const { return edges_.empty(); }
+    //! first / last aligned position of each sequence (alignment.cc:169-195); (lenA, lenB) resp. (0, 0) if there is none
+    std::pair<size_t, size_t> start_positions() const {
+        size_t a = seqA_.size(), b = seqB_.size();
+        for (const auto &e : edges_) if (e.first > 0) { a = (size_t)e.first; break; }
+        for (const auto &e : edges_) if (e.second > 0) { b = (size_t)e.second; break; }
+        return std::make_pair(a, b);
+    }
+    std::pair<size_t, size_t> end_positions() const {
+        size_t a = 0, b = 0;
+        for (auto it = edges_.rbegin(); it != edges_.rend(); ++it) if (it->first > 0) { a = (size_t)it->first; break; }
+        for (auto it = edges_.rbegin(); it != edges_.rend(); ++it) if (it->second > 0) { b = (size_t)it->second; break; }
+        return std::make_pair(a, b);
+    }
 private:
     std::string project(const std::string &s, bool first, bool only_local) const {  // alignment.cc:215-230, aux.cc:23-39
         std::string out;

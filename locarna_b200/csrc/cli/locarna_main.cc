@@ -154,13 +154,24 @@ int main(int argc, char **argv) {
                 ma.write(out, width);
             } else { std::cerr << "ERROR: Cannot write to " << clustal << "." << std::endl; rc = 255; }
         }
-        if ((!pos_output && !quiet) || local_output) {                              // locarna.cc:891-935
+        if (pos_output) {                                                           // locarna.cc:879-888
+            const auto start = alignment.start_positions(), end = alignment.end_positions();
+            std::cout << "HIT " << score << " " << start.first << " " << start.second << " " << end.first << " " << end.second << " " << std::endl;
+            std::cout << std::endl;
+        }
+        if ((!pos_output && !quiet) || local_output) {                              // locarna.cc:890-944
             MultipleAlignment ma(alignment, local_output);
             if (write_structure) {
                 ma.prepend(MultipleAlignment::SeqEntry("", alignment.dot_bracket_structureA(local_output)));
                 ma.append(MultipleAlignment::SeqEntry("", alignment.dot_bracket_structureB(local_output)));
             }
+            if (pos_output)
+                std::cout << "\t+" << alignment.start_positions().first << std::endl << "\t+" << alignment.start_positions().second << std::endl
+                          << std::endl << std::endl;
             ma.write(std::cout, width);
+            if (pos_output)
+                std::cout << std::endl << "\t+" << alignment.end_positions().first << std::endl << "\t+" << alignment.end_positions().second << std::endl
+                          << std::endl;
         }
         if (!quiet) std::cout << std::endl;
         return rc;

@@ -1,5 +1,5 @@
 """Golden outputs of the reference's own `locarna` binary (oracle/_ref/locarna, run in the build container) for the options
---exp-prob, --maxBPspan, --max-bps-length-ratio and --write-arcmatch-scores -> tests/golden/locarna_cli_options.json (inputs: tests/golden/g*.pp)."""
+--exp-prob, --maxBPspan, --max-bps-length-ratio, --pos-output and --write-arcmatch-scores -> tests/golden/locarna_cli_options.json (inputs: tests/golden/g*.pp)."""
 import json
 import os
 import subprocess
@@ -15,7 +15,7 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 def main():
     out = []
     for args in (["--exp-prob", "0.01"], ["--maxBPspan", "30"], ["-e", "0.0005", "--maxBPspan", "45", "--noLP", "--max-diff-am", "20"], [],
-                 ["--max-bps-length-ratio", "1.0"]):
+                 ["--max-bps-length-ratio", "1.0"], ["-P"], ["--pos-output", "-L", "--sequ-local", "true"], ["-P", "-q", "--struct-local", "true"]):
         for a, b in (("g0.pp", "g1.pp"), ("g2.pp", "g3.pp")):
             clu, ams = os.path.join(GOLD, "tmp.aln"), os.path.join(GOLD, "tmp.ams")
             pa, pb = os.path.join(GOLD, a), os.path.join(GOLD, b)
