@@ -56,6 +56,10 @@ def _cli_flags(args):
     while k < len(args):
         if args[k] == "--noLP":
             flags["noLP"] = True; k += 1
+        elif args[k] in ("-P", "--pos-output", "-L", "-q"):      # output only
+            k += 1
+        elif args[k] in ("--sequ-local", "--struct-local"):
+            flags[args[k][2:]] = args[k + 1] == "true"; k += 2
         else:
             v = args[k + 1]
             flags[names[args[k]]] = float(v) if "." in v else int(v); k += 2
