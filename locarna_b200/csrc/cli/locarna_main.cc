@@ -77,7 +77,7 @@ int main(int argc, char **argv) {
     double max_bps_length_ratio = 0.0;
     bool verbose = false;
     int c, idx = 0;
-    while ((c = getopt_long(argc, argv, "i:m:M:s:e:t:E:w:Lp:D:d:P:qvVh", longopts, &idx)) != -1) {
+    while ((c = getopt_long(argc, argv, "i:m:M:s:e:t:E:w:Lp:D:d:PqvVh", longopts, &idx)) != -1) {
         switch (c) {
             case 'i': case O_INDEL: sp.indel = atoi(optarg); break;
             case O_INDEL_OPENING: sp.indel_opening = atoi(optarg); break;

@@ -23,17 +23,19 @@ struct EnvSeq {
     __device__ double d(int i) const { return rev ? up[len + 1 - i] : down[i]; }
 };
 
-// one pass of pf_gotoh (edge_probs.icc:76-162) over the band [lo, hi] by anti-diagonals; matrices are (n+1) x (m+1) row major
+// one pass of pf_gotoh (edge_probs.icc:76-162) over the band [lo, hi] by anti-diagonals; matrices are (n+1) x (m+1) row major.
+// The forward and the reversed pass are independent and have the same anti-diagonal count, so each half of the CTA (nt threads,
+// thread index tid) runs one of them through this one call site; the block-wide barriers are shared.
 __device__ void gotoh_pass(double *zM, double *zA, double *zB, const int *lo, const int *hi, bool band_rev, int n, int m, const EnvSeq &A,
-                           const EnvSeq &B, const EnvCtx &e, bool free_left1, bool free_left2) {
+                           const EnvSeq &B, const EnvCtx &e, bool free_left1, bool free_left2, int tid, int nt) {
     const int W = m + 1;
     const double g_open = exp(e.open / e.temp), g_ext = exp(e.ext / e.temp);
     auto LO = [&](int i) { return band_rev ? m - hi[n - i] : lo[i]; };   // trace_controller.cc:319-338
     auto HI = [&](int i) { return band_rev ? m - lo[n - i] : hi[i]; };
     auto valid = [&](int i, int j) { return LO(i) <= j && j <= HI(i); };
-    for (int k = threadIdx.x; k < (n + 1) * W; k += blockDim.x) { zM[k] = 0; zA[k] = 0; zB[k] = 0; }
+    for (int k = tid; k < (n + 1) * W; k += nt) { zM[k] = 0; zA[k] = 0; zB[k] = 0; }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         if (valid(0, 0)) zM[0] = e.local ? 0 : 1;
         if (n > 0 && valid(1, 0)) zA[1 * W] = g_open * g_ext;
         if (m > 0 && valid(0, 1)) zB[1] = g_open * g_ext;
@@ -44,7 +46,7 @@ __device__ void gotoh_pass(double *zM, double *zA, double *zB, const int *lo, co
     }
     __syncthreads();
     for (int d = 2; d <= n + m; d++) {
-        for (int i = max(1, d - m) + threadIdx.x; i <= min(n, d - 1); i += blockDim.x) {
+        for (int i = max(1, d - m) + tid; i <= min(n, d - 1); i += nt) {
             const int j = d - i;
             if (j >= max(LO(i), 1) && j <= min(HI(i), m)) {
                 // StralScore::sigma
@@ -63,7 +65,7 @@ __device__ void gotoh_pass(double *zM, double *zA, double *zB, const int *lo, co
     }
 }
 
-__global__ void __launch_bounds__(256) envelope_kernel(EnvCtx e, int n_pairs, int *cursor) {
+__global__ void __launch_bounds__(256, 4) envelope_kernel(EnvCtx e, int n_pairs, int *cursor) {
     __shared__ int s_pair;
     __shared__ double s_red[256];
     __shared__ int s_flag;
@@ -82,9 +84,10 @@ __global__ void __launch_bounds__(256) envelope_kernel(EnvCtx e, int n_pairs, in
         EnvSeq A, B;
         A.code = e.codes + pr.codesA; A.up = e.p_up + pr.probA; A.down = e.p_down + pr.probA; A.len = n; A.rev = false;
         B.code = e.codes + pr.codesB; B.up = e.p_up + pr.probB; B.down = e.p_down + pr.probB; B.len = m; B.rev = false;
-        gotoh_pass(zM, zA, zB, lo, hi, false, n, m, A, B, e, e.fe_left1, e.fe_left2);
-        A.rev = true; B.rev = true;
-        gotoh_pass(zMr, zAr, zBr, lo, hi, true, n, m, A, B, e, e.fe_right1, e.fe_right2);   // FreeEndgaps::reverse (free_endgaps.hh:74-79)
+        const bool rev = threadIdx.x >= 128;   // threads 0..127: forward pass, 128..255: pass over the reversed sequences
+        A.rev = rev; B.rev = rev;
+        gotoh_pass(rev ? zMr : zM, rev ? zAr : zA, rev ? zBr : zB, lo, hi, rev, n, m, A, B, e, rev ? e.fe_right1 : e.fe_left1,
+                   rev ? e.fe_right2 : e.fe_left2, (int)(threadIdx.x & 127), 128);   // FreeEndgaps::reverse (free_endgaps.hh:74-79)
         // partition function z (edge_probs.icc:34-59)
         double z;
         if (e.local) {
