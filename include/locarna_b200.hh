@@ -148,7 +148,7 @@ private:
 class MultipleAlignment {  // rows of a pairwise Alignment + CLUSTAL writer (multiple_alignment.cc:153-249, :1007-1086)
 public:
     struct SeqEntry { std::string name, seq; SeqEntry(const std::string &n, const std::string &s) : name(n), seq(s) {} };
-    enum class FormatType { CLUSTAL };
+    enum class FormatType { CLUSTAL, STOCKHOLM };
     MultipleAlignment(const Alignment &a, bool only_local = false) {
         const bool clash = a.nameA() == a.nameB();
         rows_.emplace_back(clash ? "A." + a.nameA() : a.nameA(), a.rowA(only_local));
@@ -157,7 +157,8 @@ public:
     void prepend(const SeqEntry &e) { rows_.insert(rows_.begin(), e); }
     void append(const SeqEntry &e) { rows_.push_back(e); }
     size_t length() const { return rows_.empty() ? 0 : rows_[0].seq.size(); }
-    std::ostream &write(std::ostream &out, size_t width, FormatType = FormatType::CLUSTAL) const {
+    size_t num_of_rows() const { return rows_.size(); }
+    std::ostream &write(std::ostream &out, size_t width, FormatType format = FormatType::CLUSTAL) const {
         size_t namewidth = 18;
         for (const auto &r : rows_) namewidth = std::max(namewidth, r.name.size());
         size_t start = 0;
@@ -170,6 +171,7 @@ public:
             }
             start = end;
         } while (start < length() && out << std::endl);
+        if (format == FormatType::STOCKHOLM) out << "//" << std::endl;   // end marker (multiple_alignment.cc:1079-1082)
         return out;
     }
 private:

@@ -72,7 +72,7 @@ int main(int argc, char **argv) {
     int width = 120, device = 0;
     double min_prob = 0.001;
     bool quiet = false, local_output = false, local_file_output = false, write_structure = false, pos_output = false;
-    std::string clustal, arcmatch_scores_file;
+    std::string clustal, stockholm, arcmatch_scores_file;
     int max_bp_span = -1;
     double max_bps_length_ratio = 0.0;
     bool verbose = false;
@@ -96,6 +96,7 @@ int main(int argc, char **argv) {
             case O_FREE_ENDGAPS: ap.free_endgaps(optarg); break;
             case 'w': case O_WIDTH: width = atoi(optarg); break;
             case O_CLUSTAL: clustal = optarg; break;
+            case O_STOCKHOLM: stockholm = optarg; break;
             case 'L': case O_LOCAL_OUTPUT: local_output = true; break;
             case O_LOCAL_FILE_OUTPUT: local_file_output = true; break;
             case 'P': case O_POS_OUTPUT: pos_output = true; break;
@@ -114,7 +115,7 @@ int main(int argc, char **argv) {
             case O_MAXBPSPAN: max_bp_span = atoi(optarg); break;
             case 'e': case O_EXP_PROB: sp.exp_prob = atof(optarg); break;
             case O_WRITE_ARCMATCH_SCORES: arcmatch_scores_file = optarg; break;
-            case O_STACKING: case O_NEW_STACKING: case O_NORMALIZED: case O_PENALIZED: case O_STOCKHOLM: case O_PP:
+            case O_STACKING: case O_NEW_STACKING: case O_NORMALIZED: case O_PENALIZED: case O_PP:
             case O_UNSUPPORTED:
                 std::cerr << "ERROR: option --" << (idx >= 0 && longopts[idx].name ? longopts[idx].name : "?")
                           << " selects a mode that locarna_b200 does not implement." << std::endl;
@@ -153,6 +154,14 @@ int main(int argc, char **argv) {
                 }
                 ma.write(out, width);
             } else { std::cerr << "ERROR: Cannot write to " << clustal << "." << std::endl; rc = 255; }
+        }
+        if (!stockholm.empty()) {                                                   // main_helper.icc:590-615 (no consensus structure: --consensus-structure none)
+            std::ofstream out(stockholm.c_str());
+            if (out.good()) {
+                MultipleAlignment ma(alignment, local_file_output);
+                out << "# STOCKHOLM 1.0" << std::endl << "#=GF CC Generated by LocARNA 2.0.1" << std::endl << "#=GF SQ " << ma.num_of_rows() << std::endl << std::endl;
+                ma.write(out, width, MultipleAlignment::FormatType::STOCKHOLM);
+            } else { std::cerr << "ERROR: Cannot write to " << stockholm << "." << std::endl; rc = 255; }
         }
         if (pos_output) {                                                           // locarna.cc:879-888
             const auto start = alignment.start_positions(), end = alignment.end_positions();

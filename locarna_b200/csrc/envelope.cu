@@ -23,29 +23,48 @@ struct EnvSeq {
     __device__ double d(int i) const { return rev ? up[len + 1 - i] : down[i]; }
 };
 
+// Layout of the (n+1) x (m+1) partition-function matrices: anti-diagonal major. Cell (i, j) lives at off(i+j) + i - max(0, i+j-m),
+// off(d) = number of cells on the anti-diagonals before d. The sweep handles one anti-diagonal per step and reads the two before
+// it, so every access of a step is to consecutive doubles (row-major storage put each cell of a step into its own 32-byte sector).
+struct DiagIdx {
+    int n, m, a, b;
+    size_t total;
+    __device__ DiagIdx(int n_, int m_) : n(n_), m(m_), a(min(n_, m_)), b(max(n_, m_)), total((size_t)(n_ + 1) * (m_ + 1)) {}
+    __device__ size_t off(int d) const {
+        if (d <= a) return (size_t)d * (d + 1) / 2;
+        if (d <= b) return (size_t)a * (a + 1) / 2 + (size_t)(d - a) * (a + 1);
+        const size_t r = (size_t)(n + m - d + 1);
+        return total - r * (r + 1) / 2;
+    }
+    __device__ size_t operator()(int i, int j) const { const int d = i + j; return off(d) + (size_t)(i - max(0, d - m)); }
+};
+
 // one pass of pf_gotoh (edge_probs.icc:76-162) over the band [lo, hi] by anti-diagonals; matrices are (n+1) x (m+1) row major.
 // The forward and the reversed pass are independent and have the same anti-diagonal count, so each half of the CTA (nt threads,
 // thread index tid) runs one of them through this one call site; the block-wide barriers are shared.
 __device__ void gotoh_pass(double *zM, double *zA, double *zB, const int *lo, const int *hi, bool band_rev, int n, int m, const EnvSeq &A,
                            const EnvSeq &B, const EnvCtx &e, bool free_left1, bool free_left2, int tid, int nt) {
-    const int W = m + 1;
+    const DiagIdx at(n, m);
+    const int total = (n + 1) * (m + 1);
     const double g_open = exp(e.open / e.temp), g_ext = exp(e.ext / e.temp);
     auto LO = [&](int i) { return band_rev ? m - hi[n - i] : lo[i]; };   // trace_controller.cc:319-338
     auto HI = [&](int i) { return band_rev ? m - lo[n - i] : hi[i]; };
     auto valid = [&](int i, int j) { return LO(i) <= j && j <= HI(i); };
-    for (int k = tid; k < (n + 1) * W; k += nt) { zM[k] = 0; zA[k] = 0; zB[k] = 0; }
+    for (int k = tid; k < total; k += nt) { zM[k] = 0; zA[k] = 0; zB[k] = 0; }
     __syncthreads();
     if (tid == 0) {
         if (valid(0, 0)) zM[0] = e.local ? 0 : 1;
-        if (n > 0 && valid(1, 0)) zA[1 * W] = g_open * g_ext;
-        if (m > 0 && valid(0, 1)) zB[1] = g_open * g_ext;
-        for (int i = 2; i <= n; i++) { if (LO(i) > 0) break; zA[i * W] = zA[(i - 1) * W] * g_ext; }
-        for (int j = max(LO(0), 2); j <= min(HI(0), m); j++) zB[j] = zB[j - 1] * g_ext;
-        if (free_left2) for (int i = 1; i <= n; i++) zA[i * W] += 1;
-        if (free_left1) for (int j = 1; j <= m; j++) zB[j] += 1;
+        if (n > 0 && valid(1, 0)) zA[at(1, 0)] = g_open * g_ext;
+        if (m > 0 && valid(0, 1)) zB[at(0, 1)] = g_open * g_ext;
+        for (int i = 2; i <= n; i++) { if (LO(i) > 0) break; zA[at(i, 0)] = zA[at(i - 1, 0)] * g_ext; }
+        for (int j = max(LO(0), 2); j <= min(HI(0), m); j++) zB[at(0, j)] = zB[at(0, j - 1)] * g_ext;
+        if (free_left2) for (int i = 1; i <= n; i++) zA[at(i, 0)] += 1;
+        if (free_left1) for (int j = 1; j <= m; j++) zB[at(0, j)] += 1;
     }
     __syncthreads();
     for (int d = 2; d <= n + m; d++) {
+        // diagonal d, d-1, d-2: cell (i, j) / (i-1, j) and (i, j-1) / (i-1, j-1)
+        const size_t o0 = at.off(d) - max(0, d - m), o1 = at.off(d - 1) - max(0, d - 1 - m), o2 = at.off(d - 2) - max(0, d - 2 - m);
         for (int i = max(1, d - m) + tid; i <= min(n, d - 1); i += nt) {
             const int j = d - i;
             if (j >= max(LO(i), 1) && j <= min(HI(i), m)) {
@@ -55,7 +74,7 @@ __device__ void gotoh_pass(double *zM, double *zA, double *zB, const int *lo, co
                 if (a < 4 && b < 4) seq_score = e.bm[a * 4 + b];
                 const double s = e.sw * (sqrt(A.d(i) * B.d(j)) + sqrt(A.u(i) * B.u(j))) + seq_score;
                 const double mt = exp(s / e.temp);
-                const int p = i * W + j, pd = p - W - 1, pu = p - W, pl = p - 1;
+                const size_t p = o0 + i, pd = o2 + (i - 1), pu = o1 + (i - 1), pl = o1 + i;
                 zM[p] = zM[pd] * mt + zA[pd] * mt + zB[pd] * mt + (e.local ? mt : 0);
                 zA[p] = zA[pu] * g_ext + zM[pu] * g_open * g_ext + zB[pu] * g_open * g_ext;
                 zB[p] = zB[pl] * g_ext + zM[pl] * g_open * g_ext + zA[pl] * g_open * g_ext;
@@ -77,8 +96,9 @@ __global__ void __launch_bounds__(256, 4) envelope_kernel(EnvCtx e, int n_pairs,
         __syncthreads();
         if (pk >= n_pairs) break;
         const EnvPair pr = e.pairs[pk];
-        const int n = pr.lenA, m = pr.lenB, W = m + 1;
-        const size_t sz = (size_t)(n + 1) * W;
+        const int n = pr.lenA, m = pr.lenB;
+        const size_t sz = (size_t)(n + 1) * (m + 1);
+        const DiagIdx at(n, m);
         double *zM = base, *zA = base + sz, *zB = base + 2 * sz, *zMr = base + 3 * sz, *zAr = base + 4 * sz, *zBr = base + 5 * sz;
         int *lo = e.band_lo + pr.band, *hi = e.band_hi + pr.band;
         EnvSeq A, B;
@@ -99,8 +119,8 @@ __global__ void __launch_bounds__(256, 4) envelope_kernel(EnvCtx e, int n_pairs,
             z = 1 + s_red[0];
         } else {
             z = zM[sz - 1] + zA[sz - 1] + zB[sz - 1];
-            if (e.fe_left2) for (int i = 0; i <= n; i++) z += zA[i * W + m];
-            if (e.fe_left1) for (int j = 0; j <= m; j++) z += zB[n * W + j];
+            if (e.fe_left2) for (int i = 0; i <= n; i++) z += zA[at(i, m)];
+            if (e.fe_left1) for (int j = 0; j <= m; j++) z += zB[at(n, j)];
         }
         if (threadIdx.x == 0) s_flag = (!isfinite(z) || z <= 0) ? 1 : 0;
         __syncthreads();
@@ -112,7 +132,7 @@ __global__ void __launch_bounds__(256, 4) envelope_kernel(EnvCtx e, int n_pairs,
             int new_min = hi[i], new_max = lo[i];
             bool unsure = false;
             for (int j = max(lo[i], 0); j <= min(hi[i], m); j++) {
-                const size_t p = (size_t)i * W + j, r = (size_t)(n - i) * W + (m - j);
+                const size_t p = at(i, j), r = at(n - i, m - j);
                 const double zij = zM[p] * (zMr[r] + zAr[r] + zBr[r] + locality_add) + zA[p] * (zMr[r] + zAr[r] / g_open + zBr[r]) +
                                    zB[p] * (zMr[r] + zAr[r] + zBr[r] / g_open);
                 const double prob = zij / z;

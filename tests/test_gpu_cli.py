@@ -31,10 +31,12 @@ def test_cli_exp_prob_maxbpspan_arcmatch_scores(case, tmp_path):
     """--exp-prob, --maxBPspan and --write-arcmatch-scores against the reference binary (tools/make_golden_cli_options.py)."""
     clu, ams = str(tmp_path / "out.aln"), str(tmp_path / "out.ams")
     a, b = os.path.join(GOLD, case["A"]), os.path.join(GOLD, case["B"])
-    r = subprocess.run([CLI, a, b, "--clustal", clu] + case["args"], capture_output=True, text=True)
+    sto = str(tmp_path / "out.sto")
+    r = subprocess.run([CLI, a, b, "--clustal", clu, "--stockholm", sto] + case["args"], capture_output=True, text=True)
     assert r.returncode == case["rc"], r.stderr
     assert r.stdout == case["stdout"]
     assert open(clu).read() == case["clustal"]
+    assert open(sto).read() == case["stockholm"]
     w = subprocess.run([CLI, a, b, "--write-arcmatch-scores", ams] + case["args"], capture_output=True, text=True)
     assert w.returncode == case["ams_rc"], w.stderr
     assert w.stdout == case["ams_stdout"]                      # writes the file and exits without aligning (locarna.cc:705-720)

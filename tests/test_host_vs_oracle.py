@@ -56,8 +56,10 @@ def _cli_flags(args):
     while k < len(args):
         if args[k] == "--noLP":
             flags["noLP"] = True; k += 1
-        elif args[k] in ("-P", "--pos-output", "-L", "-q"):      # output only
+        elif args[k] in ("-P", "--pos-output", "-L", "-q", "--local-file-output"):      # output only
             k += 1
+        elif args[k] == "--width":
+            k += 2
         elif args[k] in ("--sequ-local", "--struct-local"):
             flags[args[k][2:]] = args[k + 1] == "true"; k += 2
         else:
