@@ -16,6 +16,9 @@
 
 namespace lb200 {
 
+// a band is ~55 diagonals wide at 300 nt, i.e. <= 55 cells per anti-diagonal and pass: two warps per pass, eight CTAs per SM
+#define ENV_THREADS 128
+
 struct EnvSeq {
     const uint8_t *code; const double *up, *down; int len; bool rev;
     __device__ int c(int i) const { return code[rev ? len + 1 - i : i]; }
@@ -62,10 +65,15 @@ __device__ void gotoh_pass(double *zM, double *zA, double *zB, const int *lo, co
         if (free_left1) for (int j = 1; j <= m; j++) zB[at(0, j)] += 1;
     }
     __syncthreads();
+    // rows of the band on anti-diagonal d: i + LO(i) and i + HI(i) grow strictly with i (make_band's rows are monotone,
+    // trace_controller.cc:522-531), so they form one range [imin, imax] whose ends only move forward with d
+    int imin = 0, imax = 0;
     for (int d = 2; d <= n + m; d++) {
+        while (imin <= n && imin + HI(imin) < d) imin++;
+        while (imax < n && imax + 1 + LO(imax + 1) <= d) imax++;
         // diagonal d, d-1, d-2: cell (i, j) / (i-1, j) and (i, j-1) / (i-1, j-1)
         const size_t o0 = at.off(d) - max(0, d - m), o1 = at.off(d - 1) - max(0, d - 1 - m), o2 = at.off(d - 2) - max(0, d - 2 - m);
-        for (int i = max(1, d - m) + tid; i <= min(n, d - 1); i += nt) {
+        for (int i = max(max(1, d - m), imin) + tid; i <= min(min(n, d - 1), imax); i += nt) {
             const int j = d - i;
             if (j >= max(LO(i), 1) && j <= min(HI(i), m)) {
                 // StralScore::sigma
@@ -84,9 +92,9 @@ __device__ void gotoh_pass(double *zM, double *zA, double *zB, const int *lo, co
     }
 }
 
-__global__ void __launch_bounds__(256, 4) envelope_kernel(EnvCtx e, int n_pairs, int *cursor) {
+__global__ void __launch_bounds__(ENV_THREADS, 8) envelope_kernel(EnvCtx e, int n_pairs, int *cursor) {
     __shared__ int s_pair;
-    __shared__ double s_red[256];
+    __shared__ double s_red[ENV_THREADS];
     __shared__ int s_flag;
     double *base = e.scratch + (size_t)blockIdx.x * e.scratch_doubles;
     for (;;) {
@@ -104,10 +112,10 @@ __global__ void __launch_bounds__(256, 4) envelope_kernel(EnvCtx e, int n_pairs,
         EnvSeq A, B;
         A.code = e.codes + pr.codesA; A.up = e.p_up + pr.probA; A.down = e.p_down + pr.probA; A.len = n; A.rev = false;
         B.code = e.codes + pr.codesB; B.up = e.p_up + pr.probB; B.down = e.p_down + pr.probB; B.len = m; B.rev = false;
-        const bool rev = threadIdx.x >= 128;   // threads 0..127: forward pass, 128..255: pass over the reversed sequences
+        const bool rev = threadIdx.x >= ENV_THREADS / 2;   // first half: forward pass, second half: pass over the reversed sequences
         A.rev = rev; B.rev = rev;
         gotoh_pass(rev ? zMr : zM, rev ? zAr : zA, rev ? zBr : zB, lo, hi, rev, n, m, A, B, e, rev ? e.fe_right1 : e.fe_left1,
-                   rev ? e.fe_right2 : e.fe_left2, (int)(threadIdx.x & 127), 128);   // FreeEndgaps::reverse (free_endgaps.hh:74-79)
+                   rev ? e.fe_right2 : e.fe_left2, (int)(threadIdx.x & (ENV_THREADS / 2 - 1)), ENV_THREADS / 2);   // FreeEndgaps::reverse (free_endgaps.hh:74-79)
         // partition function z (edge_probs.icc:34-59)
         double z;
         if (e.local) {
@@ -115,7 +123,7 @@ __global__ void __launch_bounds__(256, 4) envelope_kernel(EnvCtx e, int n_pairs,
             for (size_t k = threadIdx.x; k < sz; k += blockDim.x) acc += zM[k];
             s_red[threadIdx.x] = acc;
             __syncthreads();
-            for (int o = 128; o; o >>= 1) { if ((int)threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o]; __syncthreads(); }
+            for (int o = ENV_THREADS / 2; o; o >>= 1) { if ((int)threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o]; __syncthreads(); }
             z = 1 + s_red[0];
         } else {
             z = zM[sz - 1] + zA[sz - 1] + zB[sz - 1];
@@ -159,7 +167,7 @@ __global__ void __launch_bounds__(256, 4) envelope_kernel(EnvCtx e, int n_pairs,
 cudaError_t launch_envelope(const EnvCtx &e, int n_pairs, int grid, int *cursor, cudaStream_t st) {
     cudaError_t err = cudaMemsetAsync(cursor, 0, sizeof(int), st);
     if (err != cudaSuccess) return err;
-    envelope_kernel<<<grid, 256, 0, st>>>(e, n_pairs, cursor);
+    envelope_kernel<<<grid, ENV_THREADS, 0, st>>>(e, n_pairs, cursor);
     return cudaGetLastError();
 }
 

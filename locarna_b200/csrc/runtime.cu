@@ -396,7 +396,9 @@ static int derive_bands(lb200_ctx *c) {
             hi.insert(hi.end(), r.band.hi.begin(), r.band.hi.end());
             max_cells = std::max(max_cells, (size_t)(A.len + 1) * (B.len + 1));
         }
-        const int grid = (int)std::min<size_t>(todo.size(), (size_t)c->prop.multiProcessorCount * 4);
+        // eight resident CTAs per SM (envelope.cu), at most 8 GB of partition-function scratch
+        const int grid = (int)std::min<size_t>(std::min<size_t>(todo.size(), (size_t)c->prop.multiProcessorCount * 8),
+                                                 std::max<size_t>(1, ((size_t)8 << 30) / (6 * max_cells * sizeof(double))));
         EnvCtx e;
         memset(&e, 0, sizeof e);
         CUDA_TRY(c, upload(c->d_env_pairs, ep, st));
