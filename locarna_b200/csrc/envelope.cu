@@ -16,7 +16,8 @@
 
 namespace lb200 {
 
-// a band is ~55 diagonals wide at 300 nt, i.e. <= 55 cells per anti-diagonal and pass: two warps per pass, eight CTAs per SM
+// two warps per pass, eight CTAs per SM: the sweep is bound by the latency of its global loads (profiles/r1d_envelope_ncu_summary.txt),
+// so pairs in flight matter more than threads per pair
 #define ENV_THREADS 128
 
 struct EnvSeq {
