@@ -54,3 +54,25 @@ def test_config5_step_is_schedule_format_and_chunk_independent(family, monkeypat
         ref = O.port_align(family[a], family[b], FLAGS, do_trace=False)
         assert base[k] == ref["score"], k
         assert cells[k] == ref["cells"], k
+
+
+def test_locarna_p_probabilities_are_probabilities_at_300nt(family):
+    """LocARNA-P (inside, outside, probabilities) on one 300-nt pair of the config-5 family: size-independent sanity of the result -
+    finite positive partition function, every arc-match / base-match probability inside [0, 1], and every position matched with total
+    probability <= 1 (row and column sums of the base-match matrix). Slack 1e-3: the reference's read of its -1 debugging fill
+     perturbs a few probabilities in the 4th digit, and the device reproduces that."""
+    import math
+    ctx = capi.Context(0, {"pf-double": True, "min-trace-probability": 1e-5})
+    a, b = ctx.add_pp(family[0]), ctx.add_pp(family[1])
+    ctx.add_pair(a, b)
+    ctx.run_pf_probs(1.0, 0.001)
+    z = ctx.partition_function(0)
+    assert math.isfinite(z) and z > 0
+    am = ctx.arcmatch_probs(0)
+    assert am and all(math.isfinite(p) and -1e-3 <= p <= 1 + 1e-3 for p in am)
+    bm = ctx.basematch_probs(0)
+    assert all(math.isfinite(p) and -1e-3 <= p <= 1 + 1e-3 for row in bm for p in row)
+    assert max(sum(row) for row in bm) <= 1 + 1e-3
+    assert max(sum(row[j] for row in bm) for j in range(len(bm[0]))) <= 1 + 1e-3
+    assert max(sum(row) for row in bm) > 0.5                          # the alignment is not empty
+    ctx.close()
