@@ -2,15 +2,20 @@
 """Benchmark of the B200 pairwise sequence-structure alignment path.
 
 Workload (BASELINE.json configs[4], the configuration the metric is quoted on): the all-vs-all guide-tree stage of
-mlocarna for 512 synthetic RNAs x 300 nt (130,816 pairs), flags as mlocarna passes them
-(--noLP --max-diff-am 30 --struct-weight 200 --min-prob 0.001), score-only mode (the caller consumes
-only the score, mlocarna:3516-3527).  One "step" aligns one slice of --batch pairs of that pair list; ranks take
-disjoint slices (weak scaling: the slice per GPU is fixed), there is no data-path collective, and rank 0 gathers the
-score slices with a single NCCL gather at the end of the timed region.
+mlocarna for 512 synthetic RNAs x 300 nt, flags as mlocarna passes them (--noLP --max-diff-am 30 --struct-weight 200
+--min-prob 0.001), score-only mode (the caller consumes only the score, mlocarna:3516-3527).
 
-  value  pairs/s over K steps with the step batches already resident in HBM (arc matches, tasks, bands uploaded)
-  e2e    pairs/s through the C ABI from host buffers: sequences + base pairs + bands -> lb200_run (host build,
-         H2D, kernels, D2H of the scores), everything inside the timed region
+One "step" is one JOB: a fixed list of --job-pairs (default 16,384) pairs taken evenly from the 130,816-pair all-vs-all
+list (every pair list index k * 130816 // 16384; all 512 sequences take part), identical for every N. The job's pairs
+are split over the N ranks by estimated arc-match cost (lb200_shard_pairs, longest-processing-time-first), so N GPUs
+share a fixed amount of work: STRONG scaling. There is no data-path collective; the ranks' score slices go to rank 0
+with one NCCL gather per job, rank 0 assembles the score vector and prints its checksum (identical for every N).
+
+  value  pairs/s over K jobs with the job's tables (arc matches, tasks, bands) already resident in HBM
+  e2e    pairs/s for the whole job through the C ABI, inside the timed region of every step: context creation, parse of the
+         512 PP 2.0 files (host), cost estimate + sharding, sequences and pair list H2D, band derivation (GPU envelope
+         screening + exact host re-check of uncertain pairs), device build, D fill, top level, scores D2H, NCCL gather,
+         score vector on rank 0
   --impl reference   the reference's own CPU aligner (oracle/_ref/ref_harness, compiled from the unmodified
          reference sources; the oracle port if that binary is absent), one process per host core
 
@@ -20,9 +25,11 @@ from __future__ import annotations
 
 import argparse
 import concurrent.futures as cf
+import hashlib
 import json
 import os
 import statistics
+import struct
 import subprocess
 import sys
 import threading
@@ -32,6 +39,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLAGS = {"noLP": True, "max-diff-am": 30, "struct-weight": 200, "min-prob": 0.001}
+FLAGS_STR = "--noLP --max-diff-am 30 --struct-weight 200 --min-prob 0.001"
 METRIC = "all-vs-all pairwise alignments/s (300 nt)"
 UNIT = "alignments/s"
 
@@ -55,31 +63,25 @@ def make_inputs(n_seq, length, workers):
     d = "/tmp/lb200_bench_cfg5_%d_%d" % (n_seq, length)
     os.makedirs(d, exist_ok=True)
     jobs = [(os.path.join(d, "s%d.pp" % k), "s%d" % k, length, 1000 * 5 + k) for k in range(n_seq)]
+    if all(os.path.exists(j[0]) for j in jobs):
+        return [j[0] for j in jobs]
     with cf.ProcessPoolExecutor(max_workers=workers) as ex:
         return list(ex.map(_gen_one, jobs, chunksize=4))
 
 
-def read_pp(path):
-    """Minimal PP 2.0 reader for the benchmark's own synthetic files -> (name, seq, [(i, j, p)])."""
-    name, seq, pairs, sect = None, "", [], 0
-    for line in open(path):
-        if not line.strip() or line[0].isspace():
-            continue
-        if line.startswith("#"):
-            if line.startswith("#SECTION BASEPAIRS"):
-                sect = 1
-            continue
-        t = line.split()
-        if sect == 0:
-            name, seq = t[0], seq + t[1]
-        else:
-            pairs.append((int(t[0]), int(t[1]), float(t[2])))
-    return name, seq, pairs
-
-
-def all_vs_all(n):
+def job_pairs(n_seq, n_job):
+    """The job's pair list: n_job pairs taken evenly from mlocarna's all-vs-all order (mlocarna:3577-3604)."""
     from locarna_b200 import allpairs
-    return allpairs.all_vs_all(n)  # mlocarna pair order (mlocarna:3577-3604)
+    full = allpairs.all_vs_all(n_seq)
+    n_job = min(n_job, len(full))
+    return [full[(k * len(full)) // n_job] for k in range(n_job)], len(full)
+
+
+def score_checksum(scores):
+    h = hashlib.sha256()
+    for s in scores:
+        h.update(struct.pack("<q", -(2 ** 63) if s is None else int(s)))
+    return h.hexdigest()[:16]
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -131,69 +133,101 @@ def _ref_worker(args):
     return scores, time.time() - t
 
 
-def cpu_reference(paths, pairs, cores, per_core):
-    """Align len(pairs) pairs with the reference's CPU aligner, one process per core. Returns (pairs/s, kind, scores)."""
-    from oracle import oracle as O
-    kind = "reference" if O.have_ref() else "port"
-    if kind == "port":
-        O.lib()
-    file_pairs = [(paths[a], paths[b]) for a, b in pairs]
-    chunks = [file_pairs[k::cores] for k in range(cores)]
-    chunks = [c for c in chunks if c]
-    t = time.time()
-    with cf.ProcessPoolExecutor(max_workers=cores) as ex:
-        out = list(ex.map(_ref_worker, [(kind == "reference", FLAGS, c) for c in chunks]))
-    wall = time.time() - t
-    scores = {}
-    for k, (sc, _) in enumerate(out):
-        for idx, s in enumerate(sc):
-            scores[pairs[k + idx * cores]] = s
-    return len(file_pairs) / wall, kind, scores, wall
+class CpuReference:
+    """The reference's CPU aligner on the host cores: one worker process per core, kept alive across steps (mlocarna keeps its
+    worker threads too, mlocarna:3607-3643); every worker runs the reference path per pair: PP parse, envelope, arc matches,
+    DP, traceback."""
+
+    def __init__(self, cores):
+        from oracle import oracle as O
+        self.cores = cores
+        self.kind = "reference" if O.have_ref() else "port"
+        if self.kind == "port":
+            O.lib()
+        self.pool = cf.ProcessPoolExecutor(max_workers=cores)
+        list(self.pool.map(abs, range(cores * 4)))   # start the workers before anything is timed
+
+    def align(self, paths, pairs):
+        """-> (scores by pair, wall seconds)"""
+        file_pairs = [(paths[a], paths[b]) for a, b in pairs]
+        chunks = [c for c in (file_pairs[k::self.cores] for k in range(self.cores)) if c]
+        t = time.time()
+        out = list(self.pool.map(_ref_worker, [(self.kind == "reference", FLAGS, c) for c in chunks]))
+        wall = time.time() - t
+        scores = {}
+        for k, (sc, _) in enumerate(out):
+            for idx, s in enumerate(sc):
+                scores[pairs[k + idx * self.cores]] = s
+        return scores, wall
+
+    def close(self):
+        self.pool.shutdown()
 
 
-# ----------------------------------------------------------------------------------------------- main
-def main():
+def plan(args, world):
+    """Argument / sharding logic shared by both arms (covered by tests/test_bench_plan.py on CPU)."""
+    pairs, n_full = job_pairs(args.seqs, args.job_pairs)
+    return {"pairs": pairs, "n_full": n_full, "steps": args.steps, "warmup": max(args.warmup, 0), "world": world,
+            "sub_batch": max(1, args.sub_batch)}
+
+
+def shard_job(pairs, n_arcs, lengths, world):
+    """Cost-balanced split of the job's pair list (indices into `pairs`, per rank, descending cost)."""
+    from locarna_b200 import allpairs
+    costs = [allpairs.pair_cost(n_arcs[a], n_arcs[b], lengths[a], lengths[b]) for a, b in pairs]
+    return allpairs.shard_pairs(pairs, costs, world)
+
+
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=1024, help="pairs per step and GPU")
+    ap.add_argument("--job-pairs", type=int, default=16384, help="pairs of one job (= one step), split over the GPUs")
+    ap.add_argument("--sub-batch", type=int, default=2048, help="pairs per resident device batch")
     ap.add_argument("--seqs", type=int, default=512)
     ap.add_argument("--len", type=int, default=300)
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs of the CPU baseline sample (default: 2 per core)")
-    args = ap.parse_args()
+    ap.add_argument("--traced-steps", type=int, default=1, help="extra e2e jobs with traceback (reported as e2e_traced)")
+    return ap.parse_args(argv)
 
+
+# ----------------------------------------------------------------------------------------------- main
+def main():
+    args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
-    K, W, B = args.steps, max(args.warmup, 0), args.batch
+    pl = plan(args, world)
+    K, W, pairs = pl["steps"], pl["warmup"], pl["pairs"]
+    workload = "cfg5 mlocarna guide-tree stage, all-vs-all %d x %d nt: one step = one job of %d pairs taken evenly from the %d-pair list" % (
+        args.seqs, args.len, len(pairs), pl["n_full"])
 
     if args.impl == "reference":
         if rank != 0:
             return 0
         paths = make_inputs(args.seqs, args.len, cores)
-        pairs = all_vs_all(args.seqs)
-        per_step = args.cpu_sample or cores
-        need = (W + K) * per_step
-        sample = pairs[:need]
+        per_step = args.cpu_sample or 2 * cores
+        ref = CpuReference(cores)
         times = []
         for s in range(W + K):
-            chunk = sample[s * per_step:(s + 1) * per_step]
-            v, kind, _, wall = cpu_reference(paths, chunk, cores, 1)
+            lo = (s * per_step) % max(1, len(pairs) - per_step)
+            _, wall = ref.align(paths, pairs[lo:lo + per_step])
             if s >= W:
                 times.append(wall)
+        ref.close()
         total = sum(times)
         value = K * per_step / total
         line = {
             "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
-            "ms_per_step": 1e3 * total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+            "ms_per_step": 1e3 * total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64",
             "data": "synthetic",
-            "config": {"workload": "cfg5 mlocarna guide-tree stage, all-vs-all %d x %d nt, step = %d pairs on %d host cores" % (args.seqs, args.len, per_step, cores),
-                       "flags": "--noLP --max-diff-am 30 --struct-weight 200 --min-prob 0.001", "pairs_per_step": per_step},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                             "sample": "%d pairs per step, one process per core, reference path incl. PP parse, envelope, arc matches, DP, traceback" % per_step},
+            "config": {"workload": workload + "; reference arm: each step a sample of %d of these pairs on %d host cores" % (per_step, cores),
+                       "flags": FLAGS_STR, "pairs_per_step": per_step},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": ref.kind,
+                             "sample": "%d pairs per step, one persistent worker process per core, reference path per pair incl. PP parse, envelope, arc matches, DP, traceback" % per_step},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
         print(json.dumps(line), flush=True)
@@ -210,7 +244,7 @@ def main():
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from locarna_b200 import capi
+    from locarna_b200 import allpairs, capi
 
     def barrier():
         if dist is not None:
@@ -221,117 +255,134 @@ def main():
         paths = make_inputs(args.seqs, args.len, cores)
     if dist is not None:
         dist.barrier()
-    paths = make_inputs(args.seqs, args.len, 1) if rank != 0 else paths
-    seqs = [read_pp(p) for p in paths]
-    pairs = all_vs_all(args.seqs)
+    if rank != 0:
+        paths = make_inputs(args.seqs, args.len, 1)
     n_steps = W + K
-    # rank r takes the global step slices r, r + world, ... ; a second, disjoint set of slices feeds the e2e leg
-    def slice_of(g):
-        lo = (g * B) % max(1, len(pairs) - B)
-        return pairs[lo:lo + B]
-    my_steps = [slice_of(s * world + rank) for s in range(n_steps)]
-    e2e_steps = [slice_of((n_steps + s) * world + rank) for s in range(n_steps)]
 
-    def new_ctx(step_pairs, bands=None):
-        ctx = capi.Context(local_rank, FLAGS)
-        used = sorted({x for p in step_pairs for x in p})
-        ids = {}
-        for s in used:
-            name, seq, bp = seqs[s]
-            ids[s] = ctx.add_seq(name, seq, bp)
-        for k, (a, b) in enumerate(step_pairs):
-            ctx.add_pair(ids[a], ids[b], None if bands is None else bands[k])
-        return ctx
+    def load_job(ctx):
+        """Sequences from the PP files, cost estimate, this rank's share of the job's pair list."""
+        first = ctx.add_pps(paths)
+        n_arcs = [ctx.seq_num_arcs(first + s) for s in range(len(paths))]
+        lengths = [ctx.seq_length(first + s) for s in range(len(paths))]
+        mine = shard_job(pairs, n_arcs, lengths, world)[rank]
+        return first, mine
 
-    # ---- resident leg: build + upload every step batch before the timed region
+    # ---- resident leg: build + upload this rank's share before the timed region, in device batches of --sub-batch pairs
     t0 = time.time()
-    ctxs = []
-    resident_bytes = 0
-    for sp in my_steps:
-        ctx = new_ctx(sp)
+    ctxs, resident_bytes = [], 0
+    probe = capi.Context(local_rank, FLAGS)
+    _, mine = load_job(probe)
+    probe.close()
+    for lo in range(0, len(mine), pl["sub_batch"]):
+        part = mine[lo:lo + pl["sub_batch"]]
+        ctx = capi.Context(local_rank, FLAGS)
+        first = ctx.add_pps(paths)
+        ctx.add_pairs([(first + pairs[k][0], first + pairs[k][1]) for k in part])
         ctx.upload()
-        # S-order entry 16 B + L-order record 20 B per arc match, 20 B per D-fill task (built on the device, dev_types.h)
-        resident_bytes = max(resident_bytes, sum(36 * ctx.info(k).n_arcmatches + 20 * ctx.info(k).n_tasks for k in range(len(sp))))
-        ctxs.append(ctx)
+        # S-order entry 16 B (+ 8 B packed copy) + L-order record 20 B per arc match, 20 B per D-fill task (dev_types.h)
+        resident_bytes += sum(44 * ctx.info(k).n_arcmatches + 20 * ctx.info(k).n_tasks for k in range(len(part)))
+        ctxs.append((ctx, part))
     prep_s = time.time() - t0
+
+    def resident_step():
+        for ctx, _ in ctxs:
+            ctx.run()
+
     for s in range(W):
-        ctxs[s].run()
+        resident_step()
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
     t0 = time.time()
-    for s in range(W, n_steps):
-        ctxs[s].run()
+    kernel_ms = dfill_ms = 0.0
+    dfill_launches = launches = 0
+    for s in range(K):
+        resident_step()
+        for ctx, _ in ctxs:
+            kernel_ms += ctx.kernel_ms; dfill_ms += ctx.dfill_ms; dfill_launches += ctx.dfill_launches; launches += ctx.launches
     barrier()
     elapsed = time.time() - t0
     clocks = sampler.stop()
-    kernel_ms = sum(ctxs[s].kernel_ms for s in range(W, n_steps))
-    dfill_ms = sum(ctxs[s].dfill_ms for s in range(W, n_steps))
-    dfill_launches = sum(ctxs[s].dfill_launches for s in range(W, n_steps))
-    launches = sum(ctxs[s].launches for s in range(W, n_steps))
     cells = terms = am = arcs = rows = 0
-    for s in range(W, n_steps):
-        for k in range(len(my_steps[s])):
-            inf = ctxs[s].info(k)
+    resident_scores = {}
+    for ctx, part in ctxs:
+        sc = ctx.scores()
+        for k, idx in enumerate(part):
+            inf = ctx.info(k)
             cells += inf.cells; terms += inf.terms; am += inf.n_arcmatches; arcs += inf.n_arcsA + inf.n_arcsB; rows += inf.lenA + 1
-    my_scores = [ctxs[s].scores() for s in range(n_steps)]
-    for c in ctxs:
-        c.close()
+            resident_scores[idx] = sc[k]
+        ctx.close()
+    ctxs = []
 
-    # ---- e2e leg: host buffers -> scores on the host, everything timed.
-    # The job's sequences (512 RNAs: sequence + base pairs) are uploaded once per job before the steps, as a caller
-    # of the all-vs-all stage would do; every step passes its pair list as host buffers through the C ABI
-    # (lb200_clear_pairs, lb200_pair_add with no band, lb200_run = band derivation (GPU envelope screening + exact host
-    # re-check of uncertain pairs) + device build + D fill + top level + D2H of the scores).
+    # ---- e2e leg: the whole job from the PP files on disk to the score vector on rank 0, everything timed
     env_stats = [0, 0]
-    e2e_ctx = capi.Context(local_rank, FLAGS)
-    e2e_ids = [e2e_ctx.add_seq(*seqs[s]) for s in range(len(seqs))]
 
-    def e2e_step(s):
-        e2e_ctx.clear_pairs()
-        for k, (a, b) in enumerate(e2e_steps[s]):
-            e2e_ctx.add_pair(e2e_ids[a], e2e_ids[b], None)
-        e2e_ctx.run()
-        dev, host = e2e_ctx.envelope_stats()
+    def e2e_step(run_flags=capi.RUN_SCORE_ONLY):
+        ctx = capi.Context(local_rank, FLAGS)
+        first, mine = load_job(ctx)
+        ctx.add_pairs([(first + pairs[k][0], first + pairs[k][1]) for k in mine])
+        ctx.run(run_flags)
+        sc = ctx.scores()
+        dev, host = ctx.envelope_stats()
         env_stats[0] += dev; env_stats[1] += host
-        return e2e_ctx.scores(), e2e_ctx.h2d_bytes, e2e_ctx.d2h_bytes
+        h2d, d2h = ctx.h2d_bytes, ctx.d2h_bytes
+        nl = ctx.launches
+        ctx.close()
+        if dist is not None:  # the one collective of the path: score slices to rank 0 (NCCL gather)
+            full = allpairs.gather_scores(dist, mine, sc, len(pairs), device="cuda")
+        else:
+            full = [None] * len(pairs)
+            for k, idx in enumerate(mine):
+                full[idx] = sc[k]
+        return full, h2d, d2h, nl
 
     for s in range(W):
-        e2e_step(s)
+        e2e_step()
     barrier()
     t0 = time.time()
-    h2d = d2h = 0
-    gathered = None
-    for s in range(W, n_steps):
-        sc, a, b = e2e_step(s)
-        h2d += a; d2h += b
-    if dist is not None:  # the one collective of the path: score slices of the last step to rank 0 (NCCL gather)
-        from locarna_b200 import allpairs
-        gathered = allpairs.gather_scores(dist, list(range(rank * B, rank * B + len(sc))), sc, world * B, device="cuda")
+    h2d = d2h = e2e_launches = 0
+    full = None
+    for s in range(K):
+        full, a, b, nl = e2e_step()
+        h2d += a; d2h += b; e2e_launches += nl
     barrier()
     e2e_elapsed = time.time() - t0
-    e2e_ctx.close()
+    traced_elapsed = None
+    if args.traced_steps > 0:
+        barrier()
+        t0 = time.time()
+        for s in range(args.traced_steps):
+            e2e_step(capi.RUN_TRACE)
+        barrier()
+        traced_elapsed = time.time() - t0
 
-    def max_over_ranks(x):
+    def reduce_ranks(x, op):
         if dist is None:
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def sum_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    elapsed = max_over_ranks(elapsed)
-    e2e_elapsed = max_over_ranks(e2e_elapsed)
-    total_pairs = K * B * world
+    MAX = dist.ReduceOp.MAX if dist is not None else None
+    SUM = dist.ReduceOp.SUM if dist is not None else None
+    elapsed = reduce_ranks(elapsed, MAX)
+    e2e_elapsed = reduce_ranks(e2e_elapsed, MAX)
+    if traced_elapsed is not None:
+        traced_elapsed = reduce_ranks(traced_elapsed, MAX)
+    my_dfill_ms, my_cells = dfill_ms, cells
+    dfill_ms_max = reduce_ranks(dfill_ms, MAX)
+    kernel_ms_max = reduce_ranks(kernel_ms, MAX)
+    cells_total = reduce_ranks(cells, SUM)
+    launches_total = int(reduce_ranks(launches, SUM))
+    h2d_total = int(reduce_ranks(h2d, SUM)); d2h_total = int(reduce_ranks(d2h, SUM))
+    resident_total = reduce_ranks(resident_bytes, SUM)
+    # the resident leg's scores must equal the e2e leg's (rank 0 holds the e2e score vector)
+    mismatch = 0
+    if rank == 0:
+        mismatch = sum(1 for idx, s in resident_scores.items() if full[idx] != s)
+    total_pairs = K * len(pairs)
     value = total_pairs / elapsed
     e2e_value = total_pairs / e2e_elapsed
-    launches_total = int(sum_over_ranks(launches))
 
     if rank == 0:
         peaks = {}
@@ -341,49 +392,63 @@ def main():
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "measured" if "hbm_gbs" in peaks else "fallback"
-        # dominant kernel = dfill_kernel; figures per launch (rank 0), DESIGN.md "roofline"
-        alg_bytes = 8 * arcs + 8 * rows + 12 * am + 16 * K * B
-        # SURVEY 8d R1 counts 9 int ops per cell update + 2 per arc-match term. The kernel folds only the entries whose source lies in
-        # the box (a prefix of each anti-diagonal's list) and does not tally them, so the term part is left out: a conservative count.
-        ops = 9 * cells
-        dfill_s = dfill_ms / 1e3
+        # dominant kernel = the D fill; figures of rank 0 per launch (DESIGN.md "roofline"). SURVEY 8d R1 counts 9 int ops per cell
+        # update + 2 per arc-match term; the kernel does not tally the entries it folds, so the term part is left out (conservative).
+        dfill_s = my_dfill_ms / 1e3
+        ops = 9 * my_cells * K
         sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
         alu_peak = 148 * 128 * sm_mhz * 1e6
+        alg_bytes = (8 * arcs + 8 * rows + 12 * am + 16 * len(resident_scores)) * K
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dfill_dram_bytes_per_launch")
         except (OSError, ValueError):
             pass
-        roofline = {"bound": "hbm", "achieved": alg_bytes / dfill_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": alg_bytes / dfill_s / 1e9 / hbm_peak, "traffic": traffic, "kernel": "dfill_dep_kernel" if dfill_launches <= K else "dfill_kernel",
-                    "launch_ms": dfill_ms / max(1, dfill_launches), "peak_source": peak_src,
-                    "note": "max-plus DP: the binding roof is integer ALU issue, see roofline_alu"}
-        roofline_alu = {"bound": "int_alu", "achieved": ops / dfill_s / 1e12, "peak": alu_peak / 1e12, "unit": "Tintop/s",
-                        "frac": ops / dfill_s / alu_peak, "ops": "9*cells (SURVEY 8d R1; the 2 ops per folded arc-match term are not counted)",
-                        "gcups": cells / dfill_s / 1e9, "sm_mhz": sm_mhz}
-        # bounded CPU sample of the same workload, all host cores
-        n_cpu = args.cpu_sample or 2 * cores
-        sample = my_steps[W][:n_cpu]
-        cpu_v, kind, cpu_scores, cpu_wall = cpu_reference(paths, sample, cores, 2)
-        parity = all(cpu_scores[p] == my_scores[W][k] for k, p in enumerate(sample))
+        n_dfill = max(1, dfill_launches)
+        roofline = {"bound": "int_alu", "achieved": ops / dfill_s / 1e12, "peak": alu_peak / 1e12, "unit": "Tintop/s",
+                    "frac": ops / dfill_s / alu_peak, "traffic": traffic,
+                    "kernel": "dfill kernel (dependency-driven persistent launch)" if dfill_launches <= K * max(1, (len(resident_scores) + pl["sub_batch"] - 1) // pl["sub_batch"]) else "dfill_kernel (one launch per level group)",
+                    "launch_ms": my_dfill_ms / n_dfill, "launches": dfill_launches,
+                    "ops": "9 int ops per cell update (SURVEY 8d R1; the 2 ops per folded arc-match term are not counted)",
+                    "gcups": my_cells * K / dfill_s / 1e9, "sm_mhz": sm_mhz,
+                    "peak_source": "148 SMs x 128 INT32 lanes x SM clock sampled under load",
+                    "note": "max-plus DP with data-dependent gathers: not tensor-core work; the binding roof is integer-ALU issue, the HBM figure is in roofline_hbm"}
+        roofline_hbm = {"bound": "hbm", "achieved": alg_bytes / dfill_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": alg_bytes / dfill_s / 1e9 / hbm_peak, "peak_source": peak_src,
+                        "bytes": "8 B/arc + 8 B/band row + 12 B/arc match + 16 B/pair (SURVEY 8d R2)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": 1e3 * elapsed / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "ms_per_step": 1e3 * elapsed / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic",
-            "config": {"workload": "cfg5 mlocarna guide-tree stage, all-vs-all %d x %d nt (%d pairs), step = %d-pair slice per GPU, score only" % (args.seqs, args.len, len(pairs), B),
-                       "flags": "--noLP --max-diff-am 30 --struct-weight 200 --min-prob 0.001", "pairs_per_step": B,
-                       "l2": "inputs larger than L2: one step batch holds %.0f MB of arc-match / task tables in HBM (L2: 126 MB)" % (resident_bytes / 1e6),
-                       "bands": "derived inside every run (value: before the timed region, e2e: inside it): GPU FP64 envelope screening decided %d pairs, %d re-checked on the host in long double" % (env_stats[0], env_stats[1]),
+            "config": {"workload": workload + ", split over the GPUs by estimated arc-match cost; score only", "flags": FLAGS_STR,
+                       "pairs_per_step": len(pairs), "sub_batch": pl["sub_batch"],
+                       "l2": "inputs larger than L2: the job's arc-match / task tables hold %.0f MB in HBM (L2: 126 MB)" % (resident_total / 1e6),
+                       "bands": "derived inside every job (value: before the timed region, e2e: inside it): GPU FP64 envelope screening decided %d pairs, %d re-checked on the host in long double" % (env_stats[0], env_stats[1]),
+                       "timing": "host clock between device-wide synchronisations (+ barrier), max over ranks; device_ms_per_step = CUDA-event time of the kernels",
                        "resident_prep_s": prep_s},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_total // K, "d2h_bytes_per_step": d2h_total // K,
+                    "ms_per_step": 1e3 * e2e_elapsed / K,
+                    "scope": "per job: context, parse of %d PP files, sharding, H2D, envelope bands, device build, D fill, top level, D2H, gather" % len(paths)},
             "gpu_launches": launches_total,
-            "roofline": roofline, "roofline_alu": roofline_alu,
-            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": kind,
-                             "sample": "%d pairs of the timed slice, one process per core, %.1f s wall" % (len(sample), cpu_wall),
-                             "scores_match_gpu": parity},
-            "kernel_ms_per_step": kernel_ms / K,
+            "roofline": roofline, "roofline_hbm": roofline_hbm,
+            "device_ms_per_step": kernel_ms_max / K, "dfill_ms_per_step": dfill_ms_max / K,
+            "gcups_all_gpus": cells_total * K / (dfill_ms_max / 1e3) / 1e9,
+            "score_checksum": score_checksum(full), "resident_vs_e2e_score_mismatches": mismatch,
         }
+        if traced_elapsed is not None:
+            line["e2e_traced"] = {"value": args.traced_steps * len(pairs) / traced_elapsed, "unit": UNIT, "steps": args.traced_steps,
+                                  "scope": "as e2e, plus the device traceback of every pair and the alignment edges D2H"}
+        if world == 1:
+            # bounded CPU sample of the same workload on all host cores
+            n_cpu = args.cpu_sample or 2 * cores
+            sample = pairs[:n_cpu]
+            ref = CpuReference(cores)
+            cpu_scores, cpu_wall = ref.align(paths, sample)
+            ref.close()
+            line["cpu_baseline"] = {"value": len(sample) / cpu_wall, "unit": UNIT, "cores": cores, "kind": ref.kind,
+                                    "sample": "the first %d pairs of the job, one process per core, %.1f s wall, reference path incl. PP parse, envelope, arc matches, DP, traceback" % (len(sample), cpu_wall),
+                                    "scores_match_gpu": all(cpu_scores[p] == full[k] for k, p in enumerate(sample))}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -101,17 +101,24 @@ int lb200_set_params(lb200_ctx *ctx, const lb200_params *p);
 
 /* Add one RNA from a PP 2.0 file; returns the sequence id (>= 0) or an error code. */
 int lb200_seq_add_pp(lb200_ctx *ctx, const char *path);
+/* Add n RNAs from PP 2.0 files (parsed on the host's cores in parallel; each file once, where mlocarna's N(N-1)/2 locarna
+ * processes parse every file N-1 times); returns the id of the first one, the others follow consecutively. */
+int lb200_seqs_add_pp(lb200_ctx *ctx, int n, const char *const *paths);
 /* Add one RNA from memory: sequence (ACGU..., T is read as U) and base pairs (1-based i<j, probability). */
 int lb200_seq_add(lb200_ctx *ctx, const char *name, const char *seq, const int *pair_i, const int *pair_j, const double *pair_p,
                   int n_pairs);
 int lb200_seq_length(const lb200_ctx *ctx, int seq);
-/* name (at most name_cap-1 characters) and normalised sequence (length+1 bytes incl. NUL) of a sequence; either may be NULL */
-int lb200_seq_get(const lb200_ctx *ctx, int seq, char *name, int name_cap, char *sequence);
+/* name (at most name_cap-1 characters) and normalised sequence (length+1 bytes incl. NUL; LB200_ERR_ARG if sequence_cap is
+ * smaller) of a sequence; either buffer may be NULL */
+int lb200_seq_get(const lb200_ctx *ctx, int seq, char *name, int name_cap, char *sequence, int sequence_cap);
 
 /* Add one alignment problem (A = seqA, B = seqB). min_col/max_col (lenA+1 entries each) give the band
  * [min_col(i), max_col(i)] per row; pass NULL for both to have it derived like the reference does
  * (--max-diff, then the probability envelope). Returns the pair id (>= 0). */
 int lb200_pair_add(lb200_ctx *ctx, int seqA, int seqB, const int *min_col, const int *max_col);
+/* Add n alignment problems at once (bands derived like the reference does); returns the id of the first one. This is what the
+ * all-vs-all stage of mlocarna hands over (src/Utils/mlocarna:3577-3604: the list of (a, b) index pairs). */
+int lb200_pairs_add(lb200_ctx *ctx, int n, const int *seqA, const int *seqB);
 int lb200_num_pairs(const lb200_ctx *ctx);
 int lb200_clear_pairs(lb200_ctx *ctx);
 
@@ -168,6 +175,17 @@ int lb200_pair_arcmatch_probs(const lb200_ctx *ctx, int pair, double *prob);
 /* base-match probabilities, dense (lenA+1) x (lenB+1) row major, entry [i][j] for positions i of A and j of B (1-based; 0 outside the
  * band). locarna_p --write-basematch-probs lists those >= min_bm_prob */
 int lb200_pair_basematch_probs(const lb200_ctx *ctx, int pair, double *bm);
+
+/* All-vs-all stage (host): mlocarna's pair order (src/Utils/mlocarna:3577-3604; returns n(n-1)/2, arrays may be NULL), the cost
+ * estimate of a pair and the cost-balanced split of a pair list over `world` GPUs / processes - the counterpart of mlocarna's
+ * --compute-pairwise-scores k/N (src/Utils/mlocarna:2321-2344). Longest-processing-time-first, deterministic. rank_of[k] = share of
+ * pair k; order (optional, n_pairs entries) lists the pair indices share by share, each by descending cost, with rank_begin
+ * (optional, world + 1 entries) delimiting the shares. */
+int64_t lb200_all_vs_all(int n_seqs, int *seqA, int *seqB);
+double lb200_pair_cost(int n_arcsA, int n_arcsB, int lenA, int lenB);
+int lb200_shard_pairs(int64_t n_pairs, const double *cost, int world, int *rank_of, int64_t *order, int64_t *rank_begin);
+/* number of base pairs (arcs with probability >= min_prob) of a sequence: the input of lb200_pair_cost */
+int lb200_seq_num_arcs(const lb200_ctx *ctx, int seq);
 
 /* Guide tree of the all-vs-all stage (host): UPGMA over the symmetric score matrix (n x n, row major, diagonal 0) with the tie
  * rules of lib/perl/MLocarna/Tree.pm:181-262; writes the newick string (without the trailing ';') that mlocarna stores in

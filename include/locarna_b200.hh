@@ -282,9 +282,10 @@ public:
         ctx_->check(pair_);
         char name[256], *seq;
         const int la = lb200_seq_length(ctx_->get(), a), lb = lb200_seq_length(ctx_->get(), b);
-        seq = new char[std::max(la, lb) + 1];
-        lb200_seq_get(ctx_->get(), a, name, sizeof name, seq); alignment_.nameA_ = name; alignment_.seqA_ = seq;
-        lb200_seq_get(ctx_->get(), b, name, sizeof name, seq); alignment_.nameB_ = name; alignment_.seqB_ = seq;
+        const int seq_cap = std::max(la, lb) + 1;
+        seq = new char[seq_cap];
+        ctx_->check(lb200_seq_get(ctx_->get(), a, name, sizeof name, seq, seq_cap)); alignment_.nameA_ = name; alignment_.seqA_ = seq;
+        ctx_->check(lb200_seq_get(ctx_->get(), b, name, sizeof name, seq, seq_cap)); alignment_.nameB_ = name; alignment_.seqB_ = seq;
         delete[] seq;
     }
     //! compute the alignment score (aligner.cc:924-962)

@@ -10,26 +10,30 @@ from __future__ import annotations
 
 
 def all_vs_all(n: int):
-    """Pair list in mlocarna's order."""
+    """Pair list in mlocarna's order (lb200_all_vs_all)."""
     return [(a, b) for a in range(n) for b in range(a)]
 
 
 def pair_cost(n_arcs_a: int, n_arcs_b: int, len_a: int, len_b: int) -> float:
-    """Cheap proxy of the D-fill work of a pair: candidate arc matches x band length."""
-    return float(n_arcs_a) * float(n_arcs_b) * (len_a + len_b)
+    """Cheap proxy of the D-fill work of a pair: candidate arc matches x band length (lb200_pair_cost)."""
+    from . import capi
+    return capi.load().lb200_pair_cost(n_arcs_a, n_arcs_b, len_a, len_b)
 
 
 def shard_pairs(pairs, costs, world: int):
-    """Longest-processing-time-first assignment of pairs to ranks. Returns a list (per rank) of pair indices, each
-    sorted by descending cost. Deterministic (ties by pair index)."""
-    order = sorted(range(len(pairs)), key=lambda k: (-costs[k], k))
-    load = [0.0] * world
-    shards = [[] for _ in range(world)]
-    for k in order:
-        r = min(range(world), key=lambda x: (load[x], x))
-        shards[r].append(k)
-        load[r] += costs[k]
-    return shards
+    """Longest-processing-time-first assignment of pairs to ranks (host C++: lb200_shard_pairs, the same split the C++ front
+    end uses). Returns a list (per rank) of pair indices, each sorted by descending cost. Deterministic (ties by pair index)."""
+    import ctypes as C
+    from . import capi
+    n = len(pairs)
+    cost = (C.c_double * max(n, 1))(*[float(c) for c in costs])
+    rank_of = (C.c_int * max(n, 1))()
+    order = (C.c_int64 * max(n, 1))()
+    begin = (C.c_int64 * (world + 1))()
+    rc = capi.load().lb200_shard_pairs(n, cost, world, rank_of, order, begin)
+    if rc != capi.OK:
+        raise capi.Error("lb200_shard_pairs failed with code %d" % rc)
+    return [[order[k] for k in range(begin[r], begin[r + 1])] for r in range(world)]
 
 
 def assemble_matrix(n: int, pairs, scores, neg_inf_value: int = -100000000):
@@ -56,7 +60,11 @@ def gather_scores(dist, local_idx, local_scores, n_pairs: int, device=None):
     GPU box, gloo in the CPU tests). Returns the full score list on rank 0, None elsewhere."""
     import torch
     world, rank = dist.get_world_size(), dist.get_rank()
-    cap = (n_pairs + world - 1) // world + 1
+    # shares are balanced by cost, not by count: pad every rank's rows to the largest share (one small all-reduce)
+    cnt = torch.tensor([len(local_idx)], dtype=torch.int64)
+    cnt = cnt.to(device) if device is not None else cnt
+    dist.all_reduce(cnt, op=dist.ReduceOp.MAX)
+    cap = max(1, int(cnt.item()))
     NEG = -(2 ** 62)
     rows = [[int(i), NEG if s is None else int(s)] for i, s in zip(local_idx, local_scores)]
     rows += [[-1, -1]] * (cap - len(rows))

@@ -41,7 +41,7 @@ EXPORTS = [
     "lb200_prepare", "lb200_upload", "lb200_run", "lb200_last_kernel_ms", "lb200_last_h2d_bytes", "lb200_last_d2h_bytes", "lb200_last_dfill_ms", "lb200_last_dfill_launches", "lb200_last_launches", "lb200_envelope_stats", "lb200_pair_score", "lb200_get_scores",
     "lb200_pair_get_info", "lb200_pair_band", "lb200_pair_arcmatches", "lb200_pair_alignment", "lb200_upgma_newick",
     "lb200_run_pf", "lb200_pair_partition_function", "lb200_pair_arcmatch_pf", "lb200_run_pf_probs", "lb200_pair_arcmatch_probs",
-    "lb200_pair_basematch_probs",
+    "lb200_pair_basematch_probs", "lb200_pairs_add", "lb200_all_vs_all", "lb200_pair_cost", "lb200_shard_pairs", "lb200_seq_num_arcs", "lb200_seqs_add_pp",
 ]
 
 _lib = None
@@ -63,9 +63,17 @@ def load():
     lib.lb200_last_error.restype = C.c_char_p
     lib.lb200_set_params.argtypes = [vp, C.POINTER(Params)]
     lib.lb200_seq_add_pp.argtypes = [vp, C.c_char_p]
+    lib.lb200_seqs_add_pp.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p)]
     lib.lb200_seq_add.argtypes = [vp, C.c_char_p, C.c_char_p, ip, ip, dp, C.c_int]
     lib.lb200_seq_length.argtypes = [vp, C.c_int]
-    lib.lb200_seq_get.argtypes = [vp, C.c_int, C.c_char_p, C.c_int, C.c_char_p]
+    lib.lb200_seq_get.argtypes = [vp, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    lib.lb200_seq_num_arcs.argtypes = [vp, C.c_int]
+    lib.lb200_pairs_add.argtypes = [vp, C.c_int, ip, ip]
+    lib.lb200_all_vs_all.argtypes = [C.c_int, ip, ip]
+    lib.lb200_all_vs_all.restype = C.c_int64
+    lib.lb200_pair_cost.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.lb200_pair_cost.restype = C.c_double
+    lib.lb200_shard_pairs.argtypes = [C.c_int64, dp, C.c_int, ip, i64p, i64p]
     lib.lb200_pair_add.argtypes = [vp, C.c_int, C.c_int, ip, ip]
     lib.lb200_num_pairs.argtypes = [vp]
     lib.lb200_clear_pairs.argtypes = [vp]
@@ -165,6 +173,11 @@ class Context:
     def add_pp(self, path: str) -> int:
         return self._chk(self.lib.lb200_seq_add_pp(self.h, path.encode()))
 
+    def add_pps(self, paths) -> int:
+        """Add PP 2.0 files with one call (parsed in parallel on the host); returns the id of the first, ids are consecutive."""
+        arr = (C.c_char_p * max(len(paths), 1))(*[p.encode() for p in paths])
+        return self._chk(self.lib.lb200_seqs_add_pp(self.h, len(paths), arr))
+
     def add_seq(self, name: str, seq: str, pairs) -> int:
         n = len(pairs)
         ai = (C.c_int * max(n, 1))(*[p[0] for p in pairs])
@@ -172,10 +185,26 @@ class Context:
         ap = (C.c_double * max(n, 1))(*[p[2] for p in pairs])
         return self._chk(self.lib.lb200_seq_add(self.h, name.encode(), seq.encode(), ai, aj, ap, n))
 
+    def seq_length(self, seq: int) -> int:
+        return self._chk(self.lib.lb200_seq_length(self.h, seq))
+
+    def seq_num_arcs(self, seq: int) -> int:
+        return self._chk(self.lib.lb200_seq_num_arcs(self.h, seq))
+
+    def add_pairs(self, pairs) -> int:
+        """Add a list of (seqA, seqB) pairs with one call (bands derived like the reference does)."""
+        n = len(pairs)
+        a = (C.c_int * max(n, 1))(*[p[0] for p in pairs])
+        b = (C.c_int * max(n, 1))(*[p[1] for p in pairs])
+        return self._chk(self.lib.lb200_pairs_add(self.h, n, a, b))
+
     def add_pair(self, a: int, b: int, band=None) -> int:
         if band is None:
             return self._chk(self.lib.lb200_pair_add(self.h, a, b, None, None))
         lo, hi = band
+        n = self.seq_length(a) + 1
+        if len(lo) != n or len(hi) != n:
+            raise Error("band arrays must hold lenA + 1 = %d entries (got %d / %d)" % (n, len(lo), len(hi)))
         return self._chk(self.lib.lb200_pair_add(self.h, a, b, (C.c_int * len(lo))(*lo), (C.c_int * len(hi))(*hi)))
 
     def clear_pairs(self):

@@ -121,7 +121,7 @@ int main(int argc, char **argv) {
         ids[k] = lb200_seq_add_pp(ctx, argv[optind + k]);
         if (ids[k] < 0) return die(ctx, argv[optind + k]);
         char name[256];
-        lb200_seq_get(ctx, ids[k], name, sizeof name, nullptr);
+        lb200_seq_get(ctx, ids[k], name, sizeof name, nullptr, 0);
         names[k] = name;
     }
     std::vector<std::pair<int, int>> pairs;

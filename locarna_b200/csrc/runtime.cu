@@ -65,7 +65,8 @@ struct DevBuf {
         if (bytes <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 4 + 256;
+        // growth slack only for small buffers: a quarter more of a multi-GB scratch is what once exhausted the HBM
+        size_t want = bytes + (bytes < ((size_t)64 << 20) ? bytes / 4 : 0) + 256;
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -255,6 +256,26 @@ int lb200_seq_add_pp(lb200_ctx *c, const char *path) {
     return (int)c->seqs.size() - 1;
 }
 
+// parallel_for is defined below
+static void parallel_for(int n, int threads, const std::function<void(int)> &fn);
+
+int lb200_seqs_add_pp(lb200_ctx *c, int n, const char *const *paths) {
+    if (!c || n < 0 || (n > 0 && !paths)) return LB200_ERR_ARG;
+    for (int k = 0; k < n; k++) if (!paths[k]) return LB200_ERR_ARG;
+    std::vector<Sequence> seqs((size_t)n);
+    std::vector<std::string> errs((size_t)n);
+    std::vector<char> ok((size_t)n, 0);
+    parallel_for(n, c->host_threads, [&](int k) {
+        if (!read_pp(paths[k], c->params.min_prob, seqs[k], errs[k], c->params.max_bp_span, c->params.max_bps_length_ratio)) return;
+        finish_sequence(seqs[k], c->params.min_prob);
+        ok[k] = 1;
+    });
+    for (int k = 0; k < n; k++) if (!ok[k]) return fail(c, LB200_ERR_IO, "%s", errs[k].c_str());
+    const int first = (int)c->seqs.size();
+    for (int k = 0; k < n; k++) c->seqs.push_back(std::move(seqs[k]));
+    return first;
+}
+
 int lb200_seq_add(lb200_ctx *c, const char *name, const char *seq, const int *pi, const int *pj, const double *pp, int n) {
     if (!c || !seq || n < 0 || (n > 0 && (!pi || !pj || !pp))) return LB200_ERR_ARG;
     Sequence s;
@@ -270,10 +291,18 @@ int lb200_seq_length(const lb200_ctx *c, int seq) {
     return c->seqs[seq].len;
 }
 
-int lb200_seq_get(const lb200_ctx *c, int seq, char *name, int name_cap, char *sequence) {
+int lb200_seq_num_arcs(const lb200_ctx *c, int seq) {
+    if (!c || seq < 0 || seq >= (int)c->seqs.size()) return LB200_ERR_ARG;
+    return (int)c->seqs[seq].arcs.size();
+}
+
+int lb200_seq_get(const lb200_ctx *c, int seq, char *name, int name_cap, char *sequence, int sequence_cap) {
     if (!c || seq < 0 || seq >= (int)c->seqs.size()) return LB200_ERR_ARG;
     if (name && name_cap > 0) { strncpy(name, c->seqs[seq].name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
-    if (sequence) strcpy(sequence, c->seqs[seq].seq.c_str());
+    if (sequence) {
+        if (sequence_cap < (int)c->seqs[seq].seq.size() + 1) return LB200_ERR_ARG;
+        memcpy(sequence, c->seqs[seq].seq.c_str(), c->seqs[seq].seq.size() + 1);
+    }
     return LB200_OK;
 }
 
@@ -287,12 +316,30 @@ int lb200_pair_add(lb200_ctx *c, int seqA, int seqB, const int *min_col, const i
     if (min_col) {
         r.band.lenA = n; r.band.lenB = m;
         r.band.lo.assign(min_col, min_col + n + 1); r.band.hi.assign(max_col, max_col + n + 1);
-        for (int i = 0; i <= n; i++)
+        // a band as TraceController leaves it (trace_controller.cc:522-531, :585-596): rows inside [0, m], non-empty, both
+        // borders non-decreasing - the kernels rely on it
+        for (int i = 0; i <= n; i++) {
             if (r.band.lo[i] < 0 || r.band.hi[i] > m) return fail(c, LB200_ERR_ARG, "band out of range in row %d", i);
+            if (r.band.lo[i] > r.band.hi[i]) return fail(c, LB200_ERR_ARG, "empty band row %d", i);
+            if (i > 0 && (r.band.lo[i] < r.band.lo[i - 1] || r.band.hi[i] < r.band.hi[i - 1])) return fail(c, LB200_ERR_ARG, "band is not monotone in row %d", i);
+        }
     }
     c->pairs.push_back(std::move(r));
     c->res.valid = false;
     return (int)c->pairs.size() - 1;
+}
+
+int lb200_pairs_add(lb200_ctx *c, int n, const int *seqA, const int *seqB) {
+    if (!c || n < 0 || (n > 0 && (!seqA || !seqB))) return LB200_ERR_ARG;
+    for (int k = 0; k < n; k++) {
+        if (seqA[k] < 0 || seqB[k] < 0 || seqA[k] >= (int)c->seqs.size() || seqB[k] >= (int)c->seqs.size()) return LB200_ERR_ARG;
+        if (c->seqs[seqA[k]].len < 1 || c->seqs[seqB[k]].len < 1) return fail(c, LB200_ERR_UNSUPPORTED, "empty sequences are not supported");
+    }
+    const int first = (int)c->pairs.size();
+    c->pairs.resize(c->pairs.size() + (size_t)n);
+    for (int k = 0; k < n; k++) { c->pairs[first + k].seqA = seqA[k]; c->pairs[first + k].seqB = seqB[k]; }
+    c->res.valid = false;
+    return first;
 }
 
 int lb200_num_pairs(const lb200_ctx *c) { return c ? (int)c->pairs.size() : LB200_ERR_ARG; }
@@ -396,9 +443,13 @@ static int derive_bands(lb200_ctx *c) {
             hi.insert(hi.end(), r.band.hi.begin(), r.band.hi.end());
             max_cells = std::max(max_cells, (size_t)(A.len + 1) * (B.len + 1));
         }
-        // eight resident CTAs per SM (envelope.cu), at most 8 GB of partition-function scratch
+        // eight resident CTAs per SM (envelope.cu); the partition-function scratch takes at most 4 GB and at most a quarter of
+        // the memory that is free right now
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(c, cudaMemGetInfo(&free_b, &total_b));
+        const size_t scratch_cap = std::min<size_t>((size_t)4 << 30, (free_b + c->d_env_scratch.cap) / 4);
         const int grid = (int)std::min<size_t>(std::min<size_t>(todo.size(), (size_t)c->prop.multiProcessorCount * 8),
-                                                 std::max<size_t>(1, ((size_t)8 << 30) / (6 * max_cells * sizeof(double))));
+                                                 std::max<size_t>(1, scratch_cap / (6 * max_cells * sizeof(double))));
         EnvCtx e;
         memset(&e, 0, sizeof e);
         CUDA_TRY(c, upload(c->d_env_pairs, ep, st));
@@ -669,7 +720,13 @@ int lb200_upload(lb200_ctx *c) {
     { const int rc = derive_bands(c); if (rc != LB200_OK) return rc; }
     const std::vector<int> cuts = chunk_plan(c);
     if (cuts.size() > 2) return LB200_OK;  // several chunks: lb200_run streams them, nothing stays resident
-    return upload_chunk(c, 0, (int)c->pairs.size());
+    const int rc = upload_chunk(c, 0, (int)c->pairs.size());
+    // the batch is resident now: the band-derivation scratch and the builder's sort temporaries are not needed to run it
+    // (lb200_run without a prior lb200_upload keeps them for the next batch of a streaming caller)
+    DevBuf *transient[] = {&c->d_env_scratch, &c->d_env_pairs, &c->d_env_lo, &c->d_env_hi, &c->d_env_olo, &c->d_env_ohi, &c->d_env_flag,
+                           &c->d_skeys, &c->d_skeys2, &c->d_svals, &c->d_tasks_unsorted, &c->d_tkeys, &c->d_tkeys2, &c->d_tvals, &c->d_tmp};
+    for (DevBuf *b : transient) b->release();
+    return rc;
 }
 
 static int run_chunk(lb200_ctx *c, int flags);

@@ -19,6 +19,8 @@ def test_shard_pairs_partition_and_balance():
         assert flat == list(range(len(pairs)))
         loads = [sum(costs[k] for k in s) for s in shards]
         assert max(loads) - min(loads) <= max(costs)
+    uneven = allpairs.shard_pairs([(1, 0)] * 7, [100, 1, 1, 1, 1, 1, 1], 2)
+    assert uneven == [[0], [1, 2, 3, 4, 5, 6]]
     m = allpairs.assemble_matrix(3, [(1, 0), (2, 0), (2, 1)], [5, None, -7])
     assert m == [[0, 5, -100000000], [5, 0, -7], [-100000000, -7, 0]]
     assert allpairs.format_score_list([(1, 0), (2, 0)], [5, None]) == "1 0 5\n2 0 -inf\n"
@@ -34,7 +36,8 @@ WORKER = textwrap.dedent("""
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     pairs = allpairs.all_vs_all(len(paths))
-    costs = [allpairs.pair_cost(10 + a, 10 + b, 40, 40) for a, b in pairs]
+    # very uneven costs: the shares differ in size (one rank holds a single expensive pair), the gather must cope
+    costs = [1000.0 if k == 0 else allpairs.pair_cost(10 + a, 10 + b, 40, 40) / 1e6 for k, (a, b) in enumerate(pairs)]
     mine = allpairs.shard_pairs(pairs, costs, world)[rank]
     flags = {"noLP": True, "max-diff-am": 30}
     sc = [O.port_align(paths[pairs[k][0]], paths[pairs[k][1]], flags, do_trace=False)["score"] for k in mine]
