@@ -974,6 +974,10 @@ int lb200_run_pf_probs(lb200_ctx *c, double pf_scale, double min_am_prob) {
     CUDA_TRY(c, c->d_pf_amp.ensure(std::max<size_t>(R.total_am, 1) * 8));
     CUDA_TRY(c, c->d_pf_mats.ensure((size_t)P * 5 * mat * 8));
     CUDA_TRY(c, c->d_pf_cta.ensure((size_t)grid * 4 * mat * 8));
+    if (!getenv("LB200_PF_NOCLEAR")) {   // the dense tables start zeroed like the reference's freshly constructed matrices (aligner_p.icc:24-47)
+        CUDA_TRY(c, cudaMemsetAsync(c->d_pf_mats.p, 0, (size_t)P * 5 * mat * 8, st));
+        CUDA_TRY(c, cudaMemsetAsync(c->d_pf_cta.p, 0, (size_t)grid * 4 * mat * 8, st));
+    }
     PfoCtx o;
     o.pc = c->pf_last;
     o.cell_start = (const int *)c->d_cell_start.p; o.cell_rev = (const int *)c->d_cell_rev.p;
