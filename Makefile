@@ -6,7 +6,7 @@ SRC       := locarna_b200/csrc
 OBJ       := build/obj
 LIB       := locarna_b200/liblocarna_b200.so
 
-OBJS := $(OBJ)/kernels.o $(OBJ)/builder.o $(OBJ)/envelope.o $(OBJ)/runtime.o $(OBJ)/host_model.o $(OBJ)/guide_tree.o $(OBJ)/allpairs.o
+OBJS := $(OBJ)/kernels.o $(OBJ)/dfill_rows.o $(OBJ)/builder.o $(OBJ)/envelope.o $(OBJ)/runtime.o $(OBJ)/host_model.o $(OBJ)/guide_tree.o $(OBJ)/allpairs.o
 
 CLI       := locarna_b200/bin/locarna_b200
 CLI_P     := locarna_b200/bin/locarna_p_b200

@@ -136,6 +136,11 @@ int64_t lb200_last_d2h_bytes(const lb200_ctx *ctx);
 /* device time and launch count of the D-fill kernel (the dominant kernel) within the last lb200_run */
 double lb200_last_dfill_ms(const lb200_ctx *ctx);
 int64_t lb200_last_dfill_launches(const lb200_ctx *ctx);
+/* which D-fill kernel the last lb200_run used: 0 = one launch per level group, 1 = dependency-driven persistent launch of single
+ * boxes, 2 = row-grouped persistent launch (dfill_rows.cu); and how many chunks so far were re-run box by box because the row-grouped
+ * kernel met a box it does not support */
+int lb200_last_dfill_kind(const lb200_ctx *ctx);
+int64_t lb200_rows_fallbacks(const lb200_ctx *ctx);
 /* number of kernel launches of the last lb200_run */
 int64_t lb200_last_launches(const lb200_ctx *ctx);
 

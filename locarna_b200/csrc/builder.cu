@@ -22,6 +22,8 @@
 #include <cub/device/device_scan.cuh>
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "builder.h"
 
 namespace lb200 {
@@ -292,6 +294,68 @@ __global__ void dep_need_kernel(BuildCtx b, int n_pairs) {
     for (int g = b.n_groups - 1; g >= 0; g--) { const int c = row[g]; row[g] = run; run += c; }
 }
 
+// ------------------------------------------------------------------------------------------------ row groups (dfill_rows.cu)
+__global__ void group_keys_kernel(GroupBuild g) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= g.n_tasks) return;
+    const DevTask tk = g.tasks[t];
+    g.keys[t] = ((unsigned long long)tk.pair << 24) | ((unsigned long long)(4095 - tk.al) << 12) | (unsigned long long)(4095 - tk.bl);
+    g.vals[t] = t;
+}
+// a task leads a group if its rank inside its row (pair, al) is a multiple of LB_GV
+__global__ void group_leader_kernel(GroupBuild g) {
+    const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > g.n_tasks) return;
+    if (s == g.n_tasks) { g.gid[s] = 0; return; }
+    const unsigned long long row = g.keys_sorted[s] >> 12;
+    unsigned lo = 0, hi = s;   // first task of the row: lower bound of row << 12
+    while (lo < hi) {
+        const unsigned mid = (lo + hi) >> 1;
+        if ((g.keys_sorted[mid] >> 12) < row) lo = mid + 1; else hi = mid;
+    }
+    g.gid[s] = ((s - lo) % LB_GV) == 0 ? 1 : 0;
+}
+__global__ void group_count_kernel(GroupBuild g) { *g.n_groups = g.gid[g.n_tasks]; }
+__global__ void group_fill_kernel(GroupBuild g) {
+    const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= g.n_tasks || g.gid[s + 1] == g.gid[s]) return;
+    const unsigned long long row = g.keys_sorted[s] >> 12;
+    // the row: tasks [r0, r1) of the sorted order
+    unsigned lo = 0, hi = s;
+    while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if ((g.keys_sorted[mid] >> 12) < row) lo = mid + 1; else hi = mid; }
+    const unsigned r0 = lo;
+    lo = s; hi = g.n_tasks;
+    while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if ((g.keys_sorted[mid] >> 12) <= row) lo = mid + 1; else hi = mid; }
+    const unsigned r1 = lo;
+    DevGroup grp;
+    int min_bl = 1 << 20, max_r = 0, max_c = 0;
+    for (unsigned k = r0; k < r1; k++) {   // union box of the row (all its groups sweep this geometry)
+        const DevTask tk = g.tasks[g.vals_sorted[k]];
+        if (k == r0) { grp.pair = tk.pair; grp.al = tk.al; }
+        min_bl = min(min_bl, (int)tk.bl); max_r = max(max_r, (int)tk.R); max_c = max(max_c, (int)tk.C);
+    }
+    int n = 0;
+    for (; n < LB_GV && s + n < r1; n++) grp.task[n] = (int)g.vals_sorted[s + n];
+    for (int k = n; k < LB_GV; k++) grp.task[k] = -1;
+    grp.nmem = (short)n;
+    grp.gi = (short)((s - r0) / LB_GV); grp.G = (short)((r1 - r0 + LB_GV - 1) / LB_GV);
+    grp.bl0r = (short)min_bl; grp.Rr = (short)max_r; grp.Cr = (short)max_c; grp.pad = 0;
+    const int gi = g.gid[s];
+    g.groups[gi] = grp;
+    // claim order: row descending, the groups of a row consecutively
+    g.gkeys[gi] = ((unsigned)(4095 - grp.al) << 20) | (((unsigned)grp.pair & 0xfffu) << 8) | ((unsigned)grp.gi & 0xffu);
+    g.gvals[gi] = (unsigned)gi;
+    atomicAdd(g.levcnt + (size_t)grp.pair * g.n_levels + grp.al, 1);
+}
+// levcnt[pair][al] := number of groups of the pair in rows > al
+__global__ void group_need_kernel(GroupBuild g) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= g.n_pairs) return;
+    int *row = g.levcnt + (size_t)p * g.n_levels;
+    int run = 0;
+    for (int a = g.n_levels - 1; a >= 0; a--) { const int c = row[a]; row[a] = run; run += c; }
+}
+
 // ------------------------------------------------------------------------------------------------ host entry points
 #define TRY(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return e__; } while (0)
 
@@ -359,6 +423,43 @@ cudaError_t builder_sort_tasks(const BuildCtx &b, int n_pairs, unsigned n_tasks,
             dep_need_kernel<<<(n_pairs + 127) / 128, 128, 0, st>>>(b, n_pairs);
         }
     }
+    return cudaGetLastError();
+}
+
+size_t builder_groups_tmp_bytes(unsigned n_tasks, int n_pairs) {
+    size_t a = 0, b = 0, c = 0;
+    int pair_bits = 1;
+    while ((1 << pair_bits) < n_pairs) pair_bits++;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (const unsigned long long *)nullptr, (unsigned long long *)nullptr, (const unsigned *)nullptr,
+                                    (unsigned *)nullptr, (long long)n_tasks, 0, 24 + pair_bits);
+    cub::DeviceScan::ExclusiveSum(nullptr, b, (int *)nullptr, (int *)nullptr, (long long)n_tasks + 1);
+    cub::DeviceRadixSort::SortPairs(nullptr, c, (const unsigned *)nullptr, (unsigned *)nullptr, (const unsigned *)nullptr, (unsigned *)nullptr,
+                                    (long long)n_tasks, 0, 32);
+    return std::max(a, std::max(b, c));
+}
+
+cudaError_t builder_groups_scan(const GroupBuild &g, void *tmp, size_t tmp_bytes, cudaStream_t st) {
+    if (g.n_tasks == 0) return cudaMemsetAsync(g.n_groups, 0, sizeof(int), st);
+    int pair_bits = 1;
+    while ((1 << pair_bits) < g.n_pairs) pair_bits++;
+    const unsigned blocks = (g.n_tasks + 1 + 255) / 256;
+    group_keys_kernel<<<blocks, 256, 0, st>>>(g);
+    size_t need = tmp_bytes;
+    TRY(cub::DeviceRadixSort::SortPairs(tmp, need, g.keys, g.keys_sorted, g.vals, g.vals_sorted, (long long)g.n_tasks, 0, 24 + pair_bits, st));
+    group_leader_kernel<<<blocks, 256, 0, st>>>(g);
+    need = tmp_bytes;
+    TRY(cub::DeviceScan::ExclusiveSum(tmp, need, g.gid, g.gid, (long long)g.n_tasks + 1, st));
+    group_count_kernel<<<1, 1, 0, st>>>(g);
+    return cudaGetLastError();
+}
+
+cudaError_t builder_groups_fill(const GroupBuild &g, unsigned n_groups, void *tmp, size_t tmp_bytes, cudaStream_t st) {
+    TRY(cudaMemsetAsync(g.levcnt, 0, (size_t)g.n_pairs * g.n_levels * sizeof(int), st));
+    if (g.n_tasks == 0 || n_groups == 0) return cudaSuccess;
+    group_fill_kernel<<<(g.n_tasks + 255) / 256, 256, 0, st>>>(g);
+    size_t need = tmp_bytes;
+    TRY(cub::DeviceRadixSort::SortPairs(tmp, need, g.gkeys, g.gkeys_sorted, g.gvals, g.order, (long long)n_groups, 0, 32, st));
+    group_need_kernel<<<(g.n_pairs + 127) / 128, 128, 0, st>>>(g);
     return cudaGetLastError();
 }
 

@@ -35,6 +35,28 @@ struct BuildCtx {
     int n_groups, sb_pairs;
 };
 
+// Row groups of the D fill (dfill_rows.cu): the level-sorted tasks are ordered by (pair, al descending, bl descending), every run of
+// up to LB_GV tasks of one row becomes a group; claim order = row descending, larger boxes first; levcnt[pair * n_levels + al] =
+// number of groups of the pair in rows > al.
+struct GroupBuild {
+    const DevTask *tasks;
+    unsigned n_tasks;
+    int n_pairs;
+    unsigned long long *keys, *keys_sorted;   // n_tasks
+    unsigned *vals, *vals_sorted;             // n_tasks
+    int *gid;                                 // n_tasks + 1: leader flags, then their exclusive scan
+    DevGroup *groups;                         // n_groups (set for the fill stage)
+    unsigned *gkeys, *gkeys_sorted, *gvals, *order;   // n_groups
+    int *levcnt;
+    int n_levels;
+    int *n_groups;                            // device counter
+};
+size_t builder_groups_tmp_bytes(unsigned n_tasks, int n_pairs);
+// stage 1: sort + leader scan; *n_groups (device) holds the group count afterwards
+cudaError_t builder_groups_scan(const GroupBuild &g, void *tmp, size_t tmp_bytes, cudaStream_t st);
+// stage 2 (groups allocated for the count read back): group records, claim order, per-row dependency counts
+cudaError_t builder_groups_fill(const GroupBuild &g, unsigned n_groups, void *tmp, size_t tmp_bytes, cudaStream_t st);
+
 cudaError_t builder_count(const BuildCtx &b, int n_pairs, long long total_cells, void *tmp, size_t tmp_bytes, size_t *tmp_need, cudaStream_t st);
 size_t builder_sort_tmp_bytes(long long total_am, int n_pairs);
 cudaError_t builder_fill(const BuildCtx &b, int n_pairs, long long total_am, long long sptr_total, void *tmp, size_t tmp_bytes, cudaStream_t st);

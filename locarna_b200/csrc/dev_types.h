@@ -82,6 +82,19 @@ struct DevTask {
     int run_count;
 };
 
+// Row-grouped D fill (dfill_rows.cu): the D-fill tasks of one origin row al of a pair form a ROW; up to LB_GV of them (bl descending)
+// are swept together as the layers of one box (one GROUP = one warp's work item). All groups of a row use the geometry of the row's
+// union box (bl0r, Rr, Cr), which lets them share one filtered arc-match entry list. task[] indexes DevCtx::tasks.
+#define LB_GV 4
+struct DevGroup {
+    int pair;
+    short al, nmem;      // origin row, number of member tasks
+    short gi, G;         // index of the group inside its row, number of groups of the row
+    short bl0r, Rr, Cr;  // row union box: smallest origin column, last row, last column
+    short pad;
+    int task[LB_GV];
+};
+
 // a box whose optimal path still has to be traced (traceback kernel)
 struct TraceJob { short al, bl, R, C; int am; };  // am: L-order index of the arc match the box belongs to (struct-local)
 

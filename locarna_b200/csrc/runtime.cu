@@ -17,6 +17,7 @@
 #include "envelope.h"
 #include "dev_ctx.h"
 #include "host_model.h"
+#include "rows.h"
 
 namespace lb200 {
 void launch_dfill(const DevCtx &c, int ncmax, bool generic_borders, int grid, int smem_bytes, int q, cudaStream_t st);
@@ -117,6 +118,10 @@ struct lb200_ctx {
         long long sptr_total = 0;
         int stack_cap = 0;
         std::vector<int> sptr_off;
+        bool rows = false;       // D fill by the row-grouped kernel (dfill_rows.cu)
+        RowsCtx rc;
+        int rows_grid = 1, rows_smem = 0;
+        unsigned n_groups = 0;
     } res;
     int host_threads = 0;
     size_t seqs_uploaded = 0;  // sequences whose arrays are on the device
@@ -131,11 +136,15 @@ struct lb200_ctx {
     PfCtx pf_last; bool pf_have = false; bool pf_probs_done = false; long long pf_mat_doubles = 0;
     int max_box_words = 1, max_len = 1;
     DevBuf d_pairs, d_codes, d_band_lo, d_band_hi, d_sptr, d_ent, d_am, d_tasks, d_top, d_scratch, d_cursor, d_flag, d_levcnt, d_done, d_ent8;
+    DevBuf d_col_first, d_col_last, d_groups, d_gorder, d_ngroups, d_rows_scratch, d_row_built, d_clist, d_cnblk;   // row-grouped D fill
     int pack_entries = 1;  // 8-byte packed S-order copy for the single-state sweep when every sequence is <= LB_PACK_MAXLEN (LB200_PACK=0 disables)
-    int dfill_mode = 2;   // 2: automatic, 1: dependency-driven persistent launch (LB200_DFILL=dep), 0: one launch per level group (LB200_DFILL=levels)
+    int dfill_mode = 2;   // 2: automatic (row-grouped kernel where it applies), 3: row-grouped or fail (LB200_DFILL=rows), 1: dependency-driven persistent launch of single boxes (LB200_DFILL=dep), 0: one launch per level group (LB200_DFILL=levels)
+    int last_dfill_kind = 0;      // D-fill kernel of the last run: 0 one launch per level group, 1 dependency-driven boxes, 2 row-grouped
+    int64_t rows_fallbacks = 0;   // chunks that were re-run box by box because the row-grouped kernel met an unsupported box
     int sb_pairs = 1 << 30;   // pair block of the dependency-driven order (LB200_SB_PAIRS; default: one block)
     ~lb200_ctx() {
         DevBuf *all[] = {&d_pairs, &d_codes, &d_band_lo, &d_band_hi, &d_sptr, &d_ent, &d_am, &d_tasks, &d_top, &d_scratch, &d_cursor, &d_flag, &d_levcnt, &d_done, &d_ent8,
+                         &d_col_first, &d_col_last, &d_groups, &d_gorder, &d_ngroups, &d_rows_scratch, &d_row_built, &d_clist, &d_cnblk,
                          &d_arc_left, &d_arc_right, &d_arc_weight, &d_lptr, &d_lcount, &d_am_seq, &d_cell_rev, &d_cell_start, &d_skeys, &d_skeys2,
                          &d_svals, &d_svals2, &d_tasks_unsorted, &d_tkeys, &d_tkeys2, &d_tvals, &d_tvals2, &d_ntasks, &d_qstart, &d_stats, &d_tmp, &d_tr_edges, &d_tr_str, &d_tr_stack,
                          &d_pf_esig, &d_pf_bpow, &d_pf_d, &d_pf_z, &d_pf_scratch, &d_pf_dp, &d_pf_amp, &d_pf_mats, &d_pf_cta,
@@ -228,7 +237,7 @@ int lb200_ctx_create(int device, lb200_ctx **out) {
     make_score_tables(c->params, c->tables);
     if (const char *s = getenv("LB200_HOST_THREADS")) c->host_threads = atoi(s);
     if (const char *s = getenv("LB200_ENVELOPE")) c->env_mode = strcmp(s, "host") == 0 ? 0 : 1;
-    if (const char *s = getenv("LB200_DFILL")) c->dfill_mode = strcmp(s, "levels") == 0 ? 0 : strcmp(s, "dep") == 0 ? 1 : 2;
+    if (const char *s = getenv("LB200_DFILL")) c->dfill_mode = strcmp(s, "levels") == 0 ? 0 : strcmp(s, "dep") == 0 ? 1 : strcmp(s, "rows") == 0 ? 3 : 2;
     if (const char *s = getenv("LB200_SB_PAIRS")) c->sb_pairs = std::max(1, atoi(s));
     if (const char *s = getenv("LB200_PACK")) c->pack_entries = atoi(s) != 0;
     *out = c;
@@ -523,9 +532,9 @@ static int upload_chunk(lb200_ctx *c, int p0, int p1) {
 
     // ---- per-pair inputs: band, cell ranks, offsets
     std::vector<DevPair> h_pairs(P);
-    std::vector<int> h_lo, h_hi, h_rev;
+    std::vector<int> h_lo, h_hi, h_rev, h_cfirst, h_clast;
     long long total_cells = 0, sptr_total = 0;
-    int wd_bound = 1, max_rows = 1, max_cols = 1, max_box_words = 1;
+    int wd_bound = 1, max_rows = 1, max_cols = 1, max_box_words = 1, max_active = 0;
     for (int k = 0; k < P; k++) {
         PairRec &r = c->pairs[p0 + k];
         DevPair &d = h_pairs[k];
@@ -549,6 +558,31 @@ static int upload_chunk(lb200_ctx *c, int p0, int p1) {
         d.n_cells = cells;
         d.cell_base = total_cells; total_cells += cells;
         d.sptr = (int)sptr_total; sptr_total += n + m + 3;
+        // column view of the band for the row-grouped sweep: rows [first, last] of every column (empty: first > last), and the largest
+        // number of columns an anti-diagonal of the band crosses
+        h_cfirst.resize((size_t)sptr_total, 1 << 20); h_clast.resize((size_t)sptr_total, -1);
+        {
+            int *cf = h_cfirst.data() + d.sptr, *cl = h_clast.data() + d.sptr;
+            // the band is monotone: row i is the first row of the columns beyond hi[i-1] and the last row of the columns before lo[i+1]
+            int prev_hi = -1, next_lo = m + 1;
+            for (int i = 0; i <= n; i++) {
+                const int h = std::min(r.band.hi[i], m);
+                for (int j = std::max(std::max(r.band.lo[i], 0), prev_hi + 1); j <= h; j++) cf[j] = i;
+                prev_hi = std::max(prev_hi, h);
+            }
+            for (int i = n; i >= 0; i--) {
+                const int l = std::max(r.band.lo[i], 0);
+                for (int j = l; j <= std::min(std::min(r.band.hi[i], m), next_lo - 1); j++) cl[j] = i;
+                next_lo = std::min(next_lo, l);
+            }
+            int j2 = 0;
+            for (int j = 0; j <= m; j++) {
+                if (cl[j] < cf[j]) continue;
+                if (j2 < j) j2 = j;
+                while (j2 + 1 <= m && cl[j2 + 1] >= cf[j2 + 1] && cf[j2 + 1] + j2 + 1 <= cl[j] + j) j2++;
+                max_active = std::max(max_active, j2 - j + 1);
+            }
+        }
         const int wd = dmax - dmin + 1;
         wd_bound = std::max(wd_bound, wd);
         max_box_words = std::max(max_box_words, (n + m + 1) * ((((wd + 1) / 2) + 3) & ~3));  // row stride: diagonal pairs rounded up to 4  // anti-diagonal major box
@@ -647,7 +681,11 @@ static int upload_chunk(lb200_ctx *c, int p0, int p1) {
     // automatic: the persistent launch pays off once an average level group holds at least half a wave of tasks (measured on B200:
     // +9..14 % at 256-512 pairs of 300 nt, equal at 1024, slower below ~100 pairs where most claimed tasks would only wait)
     const int n_levels = std::max(1, (max_rows + max_cols) >> 1);
-    const bool dep = !sl && (c->dfill_mode == 1 || (c->dfill_mode == 2 && (long long)n_tasks * 2 >= (long long)grid_cap * n_levels));
+    // row-grouped kernel (dfill_rows.cu): single-state boxes of packed batches whose borders fall out of the recurrence and whose
+    // anti-diagonals cross at most ~60 band columns; everything else runs box by box (kernels.cu)
+    const bool rows = !sl && pack && c->params.indel_opening <= 0 && n_tasks > 0 && max_active <= 58 && (c->dfill_mode == 2 || c->dfill_mode == 3);
+    if (c->dfill_mode == 3 && !rows) return fail(c, LB200_ERR_UNSUPPORTED, "LB200_DFILL=rows: this batch is not eligible for the row-grouped kernel (max active columns %d)", max_active);
+    const bool dep = !sl && !rows && (c->dfill_mode == 1 || (c->dfill_mode >= 2 && (long long)n_tasks * 2 >= (long long)grid_cap * n_levels));
     b.levcnt = nullptr; b.n_groups = ((max_rows + max_cols) >> 1) + 2; b.sb_pairs = c->sb_pairs;
     if (dep) {
         CUDA_TRY(c, c->d_levcnt.ensure((size_t)P * b.n_groups * sizeof(int)));
@@ -657,6 +695,70 @@ static int upload_chunk(lb200_ctx *c, int p0, int p1) {
     CUDA_TRY(c, builder_sort_tasks(b, P, n_tasks, c->d_tmp.p, c->d_tmp.cap, st));
     dc.dep_order = dep ? (const unsigned *)c->d_tvals2.p : nullptr; dc.dep_need = (const int *)c->d_levcnt.p; dc.dep_done = (int *)c->d_done.p;
     dc.n_groups = b.n_groups; dc.n_tasks = (int)n_tasks;
+    lb200_ctx::Resident &RR = c->res;
+    RR.rows = false;
+    if (rows) {
+        GroupBuild gb;
+        memset(&gb, 0, sizeof gb);
+        gb.tasks = (const DevTask *)c->d_tasks.p; gb.n_tasks = n_tasks; gb.n_pairs = P;
+        gb.keys = (unsigned long long *)c->d_skeys.p; gb.keys_sorted = (unsigned long long *)c->d_skeys2.p;
+        gb.vals = (unsigned *)c->d_tvals.p; gb.vals_sorted = (unsigned *)c->d_tvals2.p;
+        gb.gid = (int *)c->d_tkeys.p;
+        gb.n_levels = max_rows + 2;
+        CUDA_TRY(c, c->d_levcnt.ensure((size_t)P * gb.n_levels * sizeof(int)));
+        CUDA_TRY(c, c->d_done.ensure((size_t)P * sizeof(int)));
+        CUDA_TRY(c, c->d_ngroups.ensure(16));
+        CUDA_TRY(c, c->d_tmp.ensure(builder_groups_tmp_bytes(n_tasks, P)));
+        gb.levcnt = (int *)c->d_levcnt.p; gb.n_groups = (int *)c->d_ngroups.p;
+        CUDA_TRY(c, builder_groups_scan(gb, c->d_tmp.p, c->d_tmp.cap, st));
+        int n_groups = 0;
+        CUDA_TRY(c, cudaMemcpyAsync(&n_groups, c->d_ngroups.p, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));
+        CUDA_TRY(c, c->d_groups.ensure(std::max<size_t>(n_groups, 1) * sizeof(DevGroup)));
+        CUDA_TRY(c, c->d_gorder.ensure(std::max<size_t>(n_groups, 1) * 4));
+        gb.groups = (DevGroup *)c->d_groups.p; gb.gkeys = (unsigned *)c->d_tkeys2.p; gb.gkeys_sorted = (unsigned *)c->d_tkeys.p;
+        gb.gvals = (unsigned *)c->d_svals.p; gb.order = (unsigned *)c->d_gorder.p;
+        CUDA_TRY(c, builder_groups_fill(gb, (unsigned)n_groups, c->d_tmp.p, c->d_tmp.cap, st));
+        CUDA_TRY(c, upload(c->d_col_first, h_cfirst, st));
+        CUDA_TRY(c, upload(c->d_col_last, h_clast, st));
+        RowsCtx &rc = RR.rc;
+        memset(&rc, 0, sizeof rc);
+        rc.groups = gb.groups; rc.order = gb.order; rc.n_groups = gb.n_groups;
+        rc.col_first = (const int *)c->d_col_first.p; rc.col_last = (const int *)c->d_col_last.p;
+        rc.dep_need = gb.levcnt; rc.dep_done = (int *)c->d_done.p; rc.n_levels = gb.n_levels;
+        rc.nc_max = max_active <= 26 ? 1 : 2;
+        if (const char *s = getenv("LB200_ROWS_NC")) rc.nc_max = std::max(1, std::min(2, atoi(s)));
+        if (const char *s = getenv("LB200_ROWS_FORCE_NC")) { rc.force_nc = atoi(s); if (rc.force_nc == 2) rc.nc_max = 2; }
+        rc.acc_words = 8 * 32 * rc.nc_max * LB_GV;
+        // the row in flight of every pair keeps its filtered entry list here: at most the pair's arc matches + a block of padding per
+        // group of four target anti-diagonals
+        int max_K = 1;
+        {
+            std::vector<DevPair> hp(P);
+            CUDA_TRY(c, cudaMemcpyAsync(hp.data(), c->d_pairs.p, (size_t)P * sizeof(DevPair), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(c, cudaStreamSynchronize(st));
+            for (int k = 0; k < P; k++) max_K = std::max(max_K, hp[k].K);
+        }
+        rc.clist_cap = ((long long)max_K + 32LL * LB_ROWS_TG + 31) & ~31LL;
+        CUDA_TRY(c, c->d_clist.ensure((size_t)P * rc.clist_cap * sizeof(uint2)));
+        CUDA_TRY(c, c->d_cnblk.ensure((size_t)P * LB_ROWS_TG * sizeof(int)));
+        CUDA_TRY(c, c->d_row_built.ensure((size_t)P * sizeof(int)));
+        rc.clist = (uint2 *)c->d_clist.p; rc.cnblk = (int *)c->d_cnblk.p; rc.row_built = (int *)c->d_row_built.p;
+        rc.colw_words = (max_cols + 1 + 80 + 3) & ~3;
+        rc.row_pad = 32 * rc.nc_max + 8;
+        rc.rowcode_bytes = (rc.row_pad + max_rows + max_cols + 8 + 3) & ~3;
+        rc.scratch_words = (long long)(max_rows + max_cols) * 32 * rc.nc_max * LB_GV;
+        RR.rows_smem = rows_smem_bytes(rc);
+        int per_sm = 1;
+        CUDA_TRY(c, rows_configure(RR.rows_smem, &per_sm));
+        if (const char *s = getenv("LB200_ROWS_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(s)));
+        RR.rows_grid = std::max(1, per_sm) * c->prop.multiProcessorCount;
+        CUDA_TRY(c, c->d_rows_scratch.ensure((size_t)RR.rows_grid * rc.scratch_words * 4 + 16));
+        rc.scratch = (int *)c->d_rows_scratch.p;
+        RR.n_groups = (unsigned)n_groups;
+        RR.rows = true;
+        c->last_h2d_bytes += (int64_t)(h_cfirst.size() + h_clast.size()) * 4;
+    }
     std::vector<DevPairStats> h_stats(P);
     CUDA_TRY(c, cudaMemcpyAsync(h_stats.data(), c->d_stats.p, (size_t)P * sizeof(DevPairStats), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(c, cudaMemcpyAsync(h_pairs.data(), c->d_pairs.p, (size_t)P * sizeof(DevPair), cudaMemcpyDeviceToHost, st));
@@ -773,7 +875,15 @@ static int run_chunk(lb200_ctx *c, int flags) {
     CUDA_TRY(c, lb200_reset_d((DevEntry *)c->d_ent.p, dc.ent8, R.total_am, st));
     int64_t launches = 1;
     int dfill_launches = 0;
-    if (dc.dep_order != nullptr) {   // one persistent launch, tasks ordered by their own dependencies
+    c->last_dfill_kind = R.rows ? 2 : (dc.dep_order != nullptr ? 1 : 0);
+    if (R.rows) {   // row-grouped sweep: one persistent launch, groups ordered by origin row
+        CUDA_TRY(c, cudaMemsetAsync(c->d_done.p, 0, (size_t)P * sizeof(int), st));
+        CUDA_TRY(c, cudaMemsetAsync(c->d_row_built.p, 0, (size_t)P * sizeof(int), st));
+        if (R.n_groups > 0) {
+            launch_dfill_rows(dc, R.rc, (int)std::min<unsigned>((unsigned)R.rows_grid, R.n_groups), R.rows_smem, (int *)c->d_cursor.p + 4097, st);
+            dfill_launches = 1;
+        }
+    } else if (dc.dep_order != nullptr) {   // one persistent launch, tasks ordered by their own dependencies
         CUDA_TRY(c, cudaMemsetAsync(c->d_done.p, 0, (size_t)P * sizeof(int), st));
         if (dc.n_tasks > 0) {
             launch_dfill_dep(dc, R.nc_inst, c->params.indel_opening > 0, std::min(R.grid_cap, dc.n_tasks), R.smem_bytes, (int *)c->d_cursor.p + 4097, st);
@@ -816,6 +926,11 @@ static int run_chunk(lb200_ctx *c, int flags) {
     CUDA_TRY(c, cudaEventElapsedTime(&ms_dfill, c->ev0, c->ev_mid));
     c->last_kernel_ms += ms; c->last_launches += launches; c->last_dfill_ms += ms_dfill; c->last_dfill_launches += dfill_launches;
     c->last_d2h_bytes += (int64_t)((size_t)P * sizeof(DevTopResult) + 16 + h_edges.size() * 4 + h_str.size());
+    if (h_flag[0] == 5 && R.rows) {   // a box the row-grouped kernel does not handle: the whole chunk again, box by box
+        R.rows = false;
+        c->rows_fallbacks++;
+        return run_chunk(c, flags);
+    }
     if (h_flag[0] != 0)
         return fail(c, LB200_ERR_UNSUPPORTED, "kernel reported error %d (1: band too wide, 2: box exceeds scratch, 3: trace box failed, 4: traceback dead end)", h_flag[0]);
     for (int k = 0; k < P; k++) {
@@ -848,6 +963,8 @@ int64_t lb200_last_dfill_launches(const lb200_ctx *c) { return c ? c->last_dfill
 int64_t lb200_last_h2d_bytes(const lb200_ctx *c) { return c ? c->last_h2d_bytes : 0; }
 int64_t lb200_last_d2h_bytes(const lb200_ctx *c) { return c ? c->last_d2h_bytes : 0; }
 int64_t lb200_last_launches(const lb200_ctx *c) { return c ? c->last_launches : 0; }
+int lb200_last_dfill_kind(const lb200_ctx *c) { return c ? c->last_dfill_kind : LB200_ERR_ARG; }
+int64_t lb200_rows_fallbacks(const lb200_ctx *c) { return c ? c->rows_fallbacks : 0; }
 int lb200_envelope_stats(const lb200_ctx *c, int64_t *device_pairs, int64_t *host_pairs) {
     if (!c) return LB200_ERR_ARG;
     if (device_pairs) *device_pairs = c->env_device_pairs;

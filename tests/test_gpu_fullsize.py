@@ -27,7 +27,9 @@ def run(family, run_flags=capi.RUN_SCORE_ONLY):
     ctx.run(run_flags)
     scores = ctx.scores()
     cells = [ctx.info(k).cells for k in range(len(pairs))]
+    kind = (ctx.dfill_kind, ctx.rows_fallbacks)
     ctx.close()
+    run.kind = kind
     return pairs, scores, cells
 
 
@@ -38,14 +40,17 @@ def digest(xs):
 def test_config5_step_is_schedule_format_and_chunk_independent(family, monkeypatch):
     pairs, base, cells = run(family)
     assert len(pairs) == 1035 and all(s is not None for s in base)
+    assert run.kind == (2, 0)                                    # the row-grouped kernel ran, no chunk fell back
     want = digest(base)
     for env in ({"LB200_DFILL": "levels"}, {"LB200_DFILL": "dep", "LB200_PACK": "0"}, {"LB200_CHUNK_PAIRS": "300"},
-                {"LB200_DFILL": "dep", "LB200_CTAS_PER_SM": "7"}):
+                {"LB200_DFILL": "dep", "LB200_CTAS_PER_SM": "7"}, {"LB200_DFILL": "rows", "LB200_ROWS_FORCE_NC": "2"},
+                {"LB200_DFILL": "rows", "LB200_ROWS_CTAS_PER_SM": "5"}):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         _, scores, cells2 = run(family)
         assert digest(scores) == want, env
         assert cells2 == cells, env
+        assert run.kind == ({"levels": 0, "dep": 1, "rows": 2}.get(env.get("LB200_DFILL"), 2), 0), env
         for k in env:
             monkeypatch.delenv(k)
     # oracle spot check (the oracle needs about a second per 300-nt pair) incl. the reference's count of align_noex calls

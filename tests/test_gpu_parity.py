@@ -39,8 +39,10 @@ def gpu_align(pairs, flags, run_flags=capi.RUN_KEEP_D):
     return ctx
 
 
-def check_pairs(pairs, flags):
+def check_pairs(pairs, flags, want_kind=None):
     ctx = gpu_align(pairs, flags)
+    if want_kind is not None:
+        assert ctx.dfill_kind == want_kind and ctx.rows_fallbacks == 0, (ctx.dfill_kind, ctx.rows_fallbacks)
     scores = ctx.scores()
     for k, (a, b) in enumerate(pairs):
         ref = O.port_align(a, b, flags, do_trace=False)
@@ -92,16 +94,21 @@ def test_chunked_batches_equal_single_batch(synth_dir, monkeypatch):
 NON_SL_FLAGSETS = [f for f in FLAGSETS if not f.get("struct-local")]
 
 
-@pytest.mark.parametrize("mode,pack", [("dep", "1"), ("dep", "0"), ("levels", "1"), ("levels", "0")])
+@pytest.mark.parametrize("mode,pack", [("dep", "1"), ("dep", "0"), ("levels", "1"), ("levels", "0"), ("auto", "1"), ("auto2", "1")])
 @pytest.mark.parametrize("flags", NON_SL_FLAGSETS)
 def test_schedules_and_entry_formats(synth_dir, monkeypatch, flags, mode, pack):
-    """The dependency-driven persistent D fill (LB200_DFILL=dep; chosen automatically only for large batches) and the level schedule,
-    each with the packed 8-byte and the 16-byte entry stream: D table, score and cell count bit-exact against the oracle."""
-    monkeypatch.setenv("LB200_DFILL", mode)
+    """The box-by-box D fill (LB200_DFILL=dep: dependency-driven persistent launch, levels: one launch per level group), each with the
+    packed 8-byte and the 16-byte entry stream, and the row-grouped kernel (auto: wherever it applies; auto2: two columns per lane
+    forced): D table, score and cell count bit-exact against the oracle."""
+    if mode == "auto2":
+        monkeypatch.setenv("LB200_ROWS_FORCE_NC", "2")
+    monkeypatch.setenv("LB200_DFILL", "auto" if mode == "auto2" else mode)
     monkeypatch.setenv("LB200_PACK", pack)
     pairs = [tuple(synth_dir["cfg2"][:2]), tuple(synth_dir["cfg3"][:2]), tuple(synth_dir["short"][:2]),
              (synth_dir["short"][0], synth_dir["cfg3"][5])]
-    check_pairs(pairs, flags)
+    # the row-grouped kernel applies to bands of at most ~60 columns per anti-diagonal and non-positive opening (explicit borders)
+    rows_ok = flags.get("indel-opening", -750) <= 0 and (flags.get("min-trace-probability", 1) > 0 or "max-diff" in flags)
+    check_pairs(pairs, flags, {"dep": 1, "levels": 0}.get(mode, 2 if rows_ok else None))
 
 
 @pytest.mark.parametrize("sb", ["1", "3"])
