@@ -54,7 +54,7 @@ __device__ __forceinline__ uint32_t band_key(int ib) { return ((uint32_t)ib | 0x
 
 struct Smem {
     const int *sig;       // 8 x 8 base match scores
-    int *acc;             // RING x (32 NC) x V accumulators
+    int *acc;             // V x RING x (32 NC) accumulators, layer-major: the lanes of a fold hit different banks
     int *gstart;          // first block of every target group in the row's entry list (LB_ROWS_TG entries)
     uint32_t *colw;       // column words of the row's box
     uint8_t *rowcode;     // rowcode[row_pad + ip] = 32 * symbol code of A[al + ip]
@@ -169,23 +169,30 @@ __device__ void build_list(const DevCtx &c, const RowsCtx &r, const DevGroup &gr
         const int qa = __ldg(q + min(4 * t, q_cap)), qb = __ldg(q + min(4 * t + 4, q_cap));
         uint2 *out = list + (size_t)sm.gstart[t] * 32;
         int n = 0;
-        for (int e0 = qa; e0 < qb; e0 += 32) {
-            const int e = e0 + lane;
-            bool in = false;
-            uint2 o = make_uint2(0u, 0u);
-            if (e < qb) {
-                const uint4 v = __ldcg(ent + e);   // x = (al'-1) | (bl'-1) << 16, y = ar' | br' << 16, z = D
-                const uint32_t t1 = v.x - org, t2 = lim - v.y;
-                in = ((t1 | t2) & 0x80008000u) == 0 && (int)v.z >= LB_NEG_LIMIT;
-                const uint32_t p = t1 & 0xffffu, qq = t1 >> 16;
-                const uint32_t ta = (v.y & 0xffffu) + (v.y >> 16);            // absolute target anti-diagonal
-                const uint32_t tcol = (v.y >> 16) - (uint32_t)g.bl0;
-                o.x = ((p + qq) << LOGW) | (qq & (W - 1)) | ((((ta & (RING - 1)) << LOGW) | (tcol & (W - 1))) << 16);
-                o.y = v.z;
+        for (int e0 = qa; e0 < qb; e0 += 128) {   // four independent 16-byte loads per lane in flight
+            uint4 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int e = e0 + 32 * k + lane;
+                v[k] = make_uint4(0u, 0u, 0u, 0u);
+                if (e < qb) v[k] = __ldcg(ent + e);   // x = (al'-1) | (bl'-1) << 16, y = ar' | br' << 16, z = D
             }
-            const unsigned mask = __ballot_sync(0xffffffffu, in);
-            if (in) out[n + __popc(mask & ((1u << lane) - 1u))] = o;
-            n += __popc(mask);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (e0 + 32 * k >= qb) break;
+                const int e = e0 + 32 * k + lane;
+                const uint32_t t1 = v[k].x - org, t2 = lim - v[k].y;
+                const bool in = e < qb && ((t1 | t2) & 0x80008000u) == 0 && (int)v[k].z >= LB_NEG_LIMIT;
+                const uint32_t p = t1 & 0xffffu, qq = t1 >> 16;
+                const uint32_t ta = (v[k].y & 0xffffu) + (v[k].y >> 16);            // absolute target anti-diagonal
+                const uint32_t tcol = (v[k].y >> 16) - (uint32_t)g.bl0;
+                uint2 o;
+                o.x = ((p + qq) << LOGW) | (qq & (W - 1)) | ((((ta & (RING - 1)) << LOGW) | (tcol & (W - 1))) << 16);
+                o.y = v[k].z;
+                const unsigned mask = __ballot_sync(0xffffffffu, in);
+                if (in) out[n + __popc(mask & ((1u << lane) - 1u))] = o;
+                n += __popc(mask);
+            }
         }
         const int blocks = (n + 31) >> 5;
         if (n + lane < blocks * 32) out[n + lane] = make_uint2(0u, (uint32_t)LB_NEG);   // padding: folds -inf
@@ -221,10 +228,9 @@ __device__ __forceinline__ void dp_step(State<NC> &S, const Geom &g, const int *
         const bool ok = (~z & GUARDS) == 0;
         if (k == NC - 1) below = (z & G_HI) == 0;
         const int sg = *(const int *)((const char *)sig + S.rcp[-k] + (S.w[k] >> 24));
-        int *a = arcp + k * V;
-        const int4 av = *(const int4 *)a;
-        *(int4 *)a = make_int4(LB_NEG, LB_NEG, LB_NEG, LB_NEG);
-        const int arc[V] = {av.x, av.y, av.z, av.w};
+        int arc[V];
+#pragma unroll
+        for (int v = 0; v < V; v++) { arc[v] = arcp[v * (RING * 32 * NC) + k]; arcp[v * (RING * 32 * NC) + k] = LB_NEG; }
         int nm[V];
 #pragma unroll
         for (int v = 0; v < V; v++) {
@@ -276,7 +282,7 @@ __device__ void sweep(const DevCtx &c, const RowsCtx &r, const DevGroup &grp, co
     S.K = band_key(BIAS + g.u0 - S.jc);
     S.rcp = sm.rowcode + r.row_pad + g.u0 - S.jc;
     S.bp = box + (size_t)g.u0 * AW + lane * NC * V;
-    int *ap = sm.acc + lane * NC * V;
+    int *ap = sm.acc + lane * NC;
     const int left = (lane + 31) & 31;
 
     // entry list of the row: blocks of target group t become due after cell step 4t - 5
@@ -288,9 +294,9 @@ __device__ void sweep(const DevCtx &c, const RowsCtx &r, const DevGroup &grp, co
     bool pending = false;
     auto land = [&]() {
         atomicMax(sm.acc + ps, pm.x + pd);
-        atomicMax(sm.acc + ps + 1, pm.y + pd);
-        atomicMax(sm.acc + ps + 2, pm.z + pd);
-        atomicMax(sm.acc + ps + 3, pm.w + pd);
+        atomicMax(sm.acc + ps + RING * W, pm.y + pd);
+        atomicMax(sm.acc + ps + 2 * RING * W, pm.z + pd);
+        atomicMax(sm.acc + ps + 3 * RING * W, pm.w + pd);
     };
     auto fold = [&](int u) {   // after cell step u
         __syncwarp();
@@ -307,7 +313,7 @@ __device__ void sweep(const DevCtx &c, const RowsCtx &r, const DevGroup &grp, co
                     const bool live = (int)((en.x & 0xffffu) >> LOGW) >= g.u0;
                     pm = __ldcg(boxv + (live ? (en.x & 0xffffu) : 0u));   // cell 0 holds a finite or -inf value (see below)
                     pd = live ? (int)en.y : LB_NEG;
-                    ps = (int)(en.x >> 16) * V;
+                    ps = (int)(en.x >> 16);
                     pending = true;
                 }
             }
@@ -318,16 +324,16 @@ __device__ void sweep(const DevCtx &c, const RowsCtx &r, const DevGroup &grp, co
     // as the cell holds a score or -inf, so it must not be left uninitialised when the sweep starts later
     if (g.u0 > 0 && lane == 0) *(int4 *)box = make_int4(LB_NEG, LB_NEG, LB_NEG, LB_NEG);
     __syncwarp();
-    int ringoff = ((s0 + g.u0) & (RING - 1)) * AW;
+    int ringoff = ((s0 + g.u0) & (RING - 1)) * W;
     int u = g.u0;
     for (; u <= g.useed && u <= g.u1; u++) {
         dp_step<NC, true>(S, g, sm.sig, ap + ringoff, gap, gap_open, left, u);
-        ringoff = (ringoff + AW) & (RING * AW - 1);
+        ringoff = (ringoff + W) & (RING * W - 1);
         fold(u);
     }
     for (; u <= g.u1; u++) {
         dp_step<NC, false>(S, g, sm.sig, ap + ringoff, gap, gap_open, left, u);
-        ringoff = (ringoff + AW) & (RING * AW - 1);
+        ringoff = (ringoff + W) & (RING * W - 1);
         fold(u);
     }
     __syncwarp();
