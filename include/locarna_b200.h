@@ -95,6 +95,9 @@ void lb200_default_params(lb200_params *p);
 int lb200_ctx_create(int device, lb200_ctx **ctx);
 void lb200_ctx_destroy(lb200_ctx *ctx);
 const char *lb200_last_error(const lb200_ctx *ctx);
+/* Device memory of destroyed contexts is kept in a process-wide cache and reused by later contexts (allocation and release of the
+ * multi-GB tables otherwise dominate a job); this returns it to the driver. */
+void lb200_release_device_cache(void);
 
 /* Parameters must be set before sequences are added (min_prob filters the base pairs). */
 int lb200_set_params(lb200_ctx *ctx, const lb200_params *p);

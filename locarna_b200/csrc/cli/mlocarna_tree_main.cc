@@ -11,6 +11,12 @@
 // `mlocarna --treefile <tree file>` (:2223-2231), or the score list (`--score-list`, lines "<a> <b> <score>",
 // lib/perl/MLocarna/SparseMatrix.pm:264-276) dropped into <tgtdir>/scores/ for `mlocarna --score-lists`.
 //
+// Several GPUs: `--gpus N` splits the pair list over the devices 0..N-1 of this box by estimated arc-match cost (lb200_shard_pairs,
+// one host thread and one context per device, every PP file parsed once per device) and merges the scores on the host.
+// `--compute-pairwise-scores k/N` is mlocarna's own way to distribute the stage over processes (src/Utils/mlocarna:2321-2344): this
+// process computes share k of N (1-based) of the pair list, by the same cost-balanced split, and writes only the partial score list
+// (`--score-list FILE`, or <tgtdir>/scores/scores-k); `mlocarna --score-lists` merges the lists.
+//
 // Defaults are the flags mlocarna passes in this stage (@locarna_params_tree: --struct-weight 200 --max-diff-am 30 --noLP
 // --min-prob 0.001, mlocarna:1239-1242, :1433-1439, :1519-1594); every `locarna` scoring / heuristic flag of the path can be given
 // to override them (--LP switches --noLP off, as mlocarna's --LP does).
@@ -22,6 +28,7 @@
 #include <fstream>
 #include <iostream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "locarna_b200.h"
@@ -29,7 +36,7 @@
 namespace {
 enum {
     O_INDEL_OPENING = 1000, O_USE_RIBOSUM, O_UNPAIRED_PENALTY, O_STRUCT_LOCAL, O_SEQU_LOCAL, O_FREE_ENDGAPS, O_MAX_DIFF_AT_AM,
-    O_MIN_TRACE_PROB, O_NOLP, O_LP, O_MAXBPSPAN, O_MAX_BPS_LENGTH_RATIO, O_TEMPERATURE_ALIPF, O_MATRIX, O_SCORE_LIST, O_TREE, O_TGTDIR, O_DEVICE
+    O_MIN_TRACE_PROB, O_NOLP, O_LP, O_MAXBPSPAN, O_MAX_BPS_LENGTH_RATIO, O_TEMPERATURE_ALIPF, O_MATRIX, O_SCORE_LIST, O_TREE, O_TGTDIR, O_DEVICE, O_GPUS, O_SHARE
 };
 bool parse_bool(const char *s) {
     const std::string v = s ? s : "";  // options.cc:867-880
@@ -37,11 +44,6 @@ bool parse_bool(const char *s) {
     if (v == "f" || v == "false" || v == "off" || v == "0") return false;
     std::cerr << "ERROR: cannot parse boolean value \"" << v << "\"" << std::endl;
     exit(255);
-}
-int die(lb200_ctx *c, const char *what) {
-    std::cerr << "ERROR: " << what << ": " << (c ? lb200_last_error(c) : "no context") << std::endl;
-    if (c) lb200_ctx_destroy(c);
-    return 255;
 }
 }  // namespace
 
@@ -56,13 +58,14 @@ int main(int argc, char **argv) {
         {"min-trace-probability", required_argument, 0, O_MIN_TRACE_PROB}, {"noLP", no_argument, 0, O_NOLP}, {"LP", no_argument, 0, O_LP},
         {"maxBPspan", required_argument, 0, O_MAXBPSPAN}, {"max-bps-length-ratio", required_argument, 0, O_MAX_BPS_LENGTH_RATIO}, {"temperature-alipf", required_argument, 0, O_TEMPERATURE_ALIPF},
         {"matrix", required_argument, 0, O_MATRIX}, {"score-list", required_argument, 0, O_SCORE_LIST}, {"tree", required_argument, 0, O_TREE},
-        {"tgtdir", required_argument, 0, O_TGTDIR}, {"device", required_argument, 0, O_DEVICE}, {"quiet", no_argument, 0, 'q'},
+        {"tgtdir", required_argument, 0, O_TGTDIR}, {"device", required_argument, 0, O_DEVICE}, {"gpus", required_argument, 0, O_GPUS},
+        {"compute-pairwise-scores", required_argument, 0, O_SHARE}, {"quiet", no_argument, 0, 'q'},
         {"verbose", no_argument, 0, 'v'}, {"help", no_argument, 0, 'h'}, {0, 0, 0, 0}};
     lb200_params p;
     lb200_default_params(&p);
     p.struct_weight = 200; p.max_diff_am = 30; p.no_lonely_pairs = 1; p.min_prob = 0.001;   // @locarna_params_tree
     std::string matrix_file, list_file, tree_file, tgtdir;
-    int device = 0;
+    int device = 0, gpus = 1, share_k = 0, share_n = 0;
     bool quiet = false, verbose = false;
     int c, idx = 0;
     while ((c = getopt_long(argc, argv, "i:m:M:s:e:t:E:p:D:d:qvh", longopts, &idx)) != -1) {
@@ -95,10 +98,17 @@ int main(int argc, char **argv) {
             case O_TREE: tree_file = optarg; break;
             case O_TGTDIR: tgtdir = optarg; break;
             case O_DEVICE: device = atoi(optarg); break;
+            case O_GPUS: gpus = atoi(optarg); break;
+            case O_SHARE:
+                if (sscanf(optarg, "%d/%d", &share_k, &share_n) != 2 || share_n < 1 || share_k < 1 || share_k > share_n) {
+                    std::cerr << "ERROR: --compute-pairwise-scores expects k/N with 1 <= k <= N" << std::endl;
+                    return 255;
+                }
+                break;
             case 'q': quiet = true; break;
             case 'v': verbose = true; break;
             case 'h':
-                std::cout << "usage: mlocarna_tree_b200 [locarna scoring/heuristic options] [--tgtdir DIR | --matrix FILE --tree FILE --score-list FILE]"
+                std::cout << "usage: mlocarna_tree_b200 [locarna scoring/heuristic options] [--gpus N] [--compute-pairwise-scores k/N] [--tgtdir DIR | --matrix FILE --tree FILE --score-list FILE]"
                              " <seq0.pp> <seq1.pp> ...   (PP 2.0 files in input-sequence order)" << std::endl;
                 return 0;
             default: return 255;
@@ -112,29 +122,93 @@ int main(int argc, char **argv) {
         if (list_file.empty()) list_file = tgtdir + "/scores/scores-0";
     }
 
-    lb200_ctx *ctx = nullptr;
-    if (lb200_ctx_create(device, &ctx) < 0) return die(ctx, "cannot create the device context");
-    if (lb200_set_params(ctx, &p) < 0) return die(ctx, "parameters");
-    std::vector<int> ids(n);
+    if (gpus < 1) { std::cerr << "ERROR: --gpus expects a positive number" << std::endl; return 255; }
+    if (!tgtdir.empty() && share_n > 0 && list_file == tgtdir + "/scores/scores-0") list_file = tgtdir + "/scores/scores-" + std::to_string(share_k);
+
+    // pair list in mlocarna's order (mlocarna:3577-3604: A = the later sequence)
+    const int64_t n_pairs = lb200_all_vs_all(n, nullptr, nullptr);
+    std::vector<int> pa((size_t)n_pairs), pb((size_t)n_pairs);
+    lb200_all_vs_all(n, pa.data(), pb.data());
+    std::vector<std::pair<int, int>> pairs((size_t)n_pairs);
+    for (int64_t k = 0; k < n_pairs; k++) pairs[k] = std::make_pair(pa[k], pb[k]);
+    std::vector<const char *> files(n);
+    for (int k = 0; k < n; k++) files[k] = argv[optind + k];
+
+    // one context per device; the first one also yields the names and the cost estimate of every pair
+    const int n_ctx = gpus;
+    std::vector<lb200_ctx *> ctxs(n_ctx, nullptr);
     std::vector<std::string> names(n);
+    std::vector<std::string> errors(n_ctx);
+    auto open_ctx = [&](int g) -> bool {
+        if (lb200_ctx_create(device + g, &ctxs[g]) < 0) { errors[g] = "cannot create the device context"; return false; }
+        if (lb200_set_params(ctxs[g], &p) < 0 || lb200_seqs_add_pp(ctxs[g], n, files.data()) < 0) { errors[g] = lb200_last_error(ctxs[g]); return false; }
+        return true;
+    };
+    if (!open_ctx(0)) { std::cerr << "ERROR: " << errors[0] << std::endl; return 255; }
+    std::vector<double> cost((size_t)n_pairs);
     for (int k = 0; k < n; k++) {
-        ids[k] = lb200_seq_add_pp(ctx, argv[optind + k]);
-        if (ids[k] < 0) return die(ctx, argv[optind + k]);
         char name[256];
-        lb200_seq_get(ctx, ids[k], name, sizeof name, nullptr, 0);
+        lb200_seq_get(ctxs[0], k, name, sizeof name, nullptr, 0);
         names[k] = name;
     }
-    std::vector<std::pair<int, int>> pairs;
-    for (int a = 0; a < n; a++)
-        for (int b = 0; b < a; b++) {  // mlocarna:3577-3604: A = the later sequence
-            if (lb200_pair_add(ctx, ids[a], ids[b], nullptr, nullptr) < 0) return die(ctx, "pair");
-            pairs.emplace_back(a, b);
+    for (int64_t k = 0; k < n_pairs; k++)
+        cost[k] = lb200_pair_cost(lb200_seq_num_arcs(ctxs[0], pa[k]), lb200_seq_num_arcs(ctxs[0], pb[k]), lb200_seq_length(ctxs[0], pa[k]), lb200_seq_length(ctxs[0], pb[k]));
+
+    // this process's share of the pair list (--compute-pairwise-scores k/N), then its split over the devices
+    std::vector<int64_t> mine;
+    if (share_n > 0) {
+        std::vector<int> rank_of((size_t)n_pairs);
+        if (lb200_shard_pairs(n_pairs, cost.data(), share_n, rank_of.data(), nullptr, nullptr) < 0) { std::cerr << "ERROR: sharding failed" << std::endl; return 255; }
+        for (int64_t k = 0; k < n_pairs; k++) if (rank_of[k] == share_k - 1) mine.push_back(k);
+    } else {
+        mine.resize((size_t)n_pairs);
+        for (int64_t k = 0; k < n_pairs; k++) mine[k] = k;
+    }
+    std::vector<double> my_cost(mine.size());
+    for (size_t k = 0; k < mine.size(); k++) my_cost[k] = cost[mine[k]];
+    std::vector<int> dev_of(mine.size());
+    std::vector<int64_t> order(mine.size()), begin((size_t)n_ctx + 1);
+    if (lb200_shard_pairs((int64_t)mine.size(), my_cost.data(), n_ctx, dev_of.data(), order.data(), begin.data()) < 0) { std::cerr << "ERROR: sharding failed" << std::endl; return 255; }
+    if (verbose) std::cerr << "aligning " << mine.size() << " of " << n_pairs << " pairs of " << n << " sequences on " << n_ctx << " GPU(s)" << std::endl;
+
+    std::vector<int64_t> scores((size_t)n_pairs, 0);
+    std::vector<char> have((size_t)n_pairs, 0);
+    auto work = [&](int g) {
+        if (g > 0 && !open_ctx(g)) return;
+        lb200_ctx *ctx = ctxs[g];
+        const int64_t cnt = begin[g + 1] - begin[g];
+        std::vector<int> a((size_t)cnt), b((size_t)cnt);
+        for (int64_t k = 0; k < cnt; k++) { const int64_t gp = mine[order[begin[g] + k]]; a[k] = pa[gp]; b[k] = pb[gp]; }
+        std::vector<int64_t> sc((size_t)cnt);
+        if (lb200_pairs_add(ctx, (int)cnt, a.data(), b.data()) < 0 || lb200_run(ctx, LB200_RUN_SCORE_ONLY) < 0 ||
+            (cnt > 0 && lb200_get_scores(ctx, sc.data(), (int)cnt) < 0)) { errors[g] = lb200_last_error(ctx); return; }
+        for (int64_t k = 0; k < cnt; k++) { const int64_t gp = mine[order[begin[g] + k]]; scores[gp] = sc[k]; have[gp] = 1; }
+        if (verbose) std::cerr << "device " << device + g << ": " << cnt << " pairs, device time " << lb200_last_kernel_ms(ctx) << " ms, " << lb200_last_launches(ctx) << " kernel launches" << std::endl;
+    };
+    {
+        std::vector<std::thread> pool;
+        for (int g = 1; g < n_ctx; g++) pool.emplace_back(work, g);
+        work(0);
+        for (auto &t : pool) t.join();
+    }
+    bool failed = false;
+    for (int g = 0; g < n_ctx; g++) {
+        if (!errors[g].empty()) { std::cerr << "ERROR: device " << device + g << ": " << errors[g] << std::endl; failed = true; }
+        if (ctxs[g]) lb200_ctx_destroy(ctxs[g]);
+    }
+    if (failed) return 255;
+
+    if (share_n > 0) {   // partial score list only (merged by `mlocarna --score-lists`)
+        std::ostream *out = &std::cout;
+        std::ofstream f;
+        if (!list_file.empty()) { f.open(list_file.c_str()); if (!f.good()) { std::cerr << "ERROR: Cannot write to " << list_file << "." << std::endl; return 255; } out = &f; }
+        for (int64_t k : mine) {
+            *out << pairs[k].first << " " << pairs[k].second << " ";
+            if (scores[k] == LB200_SCORE_NEG_INF) *out << "-inf"; else *out << (long long)scores[k];
+            *out << "\n";
         }
-    if (verbose) std::cerr << "aligning " << pairs.size() << " pairs of " << n << " sequences" << std::endl;
-    if (lb200_run(ctx, LB200_RUN_SCORE_ONLY) < 0) return die(ctx, "alignment");
-    std::vector<int64_t> scores(pairs.size());
-    if (lb200_get_scores(ctx, scores.data(), (int)scores.size()) < 0) return die(ctx, "scores");
-    if (verbose) std::cerr << "device time " << lb200_last_kernel_ms(ctx) << " ms, " << lb200_last_launches(ctx) << " kernel launches" << std::endl;
+        return 0;
+    }
 
     std::vector<int64_t> matrix((size_t)n * n, 0);
     for (size_t k = 0; k < pairs.size(); k++) {
@@ -147,10 +221,8 @@ int main(int argc, char **argv) {
     std::vector<char> newick((size_t)n * 320 + 64);
     if (lb200_upgma_newick(n, cnames.data(), matrix.data(), newick.data(), newick.size()) < 0) {
         std::cerr << "ERROR: guide tree construction failed" << std::endl;
-        lb200_ctx_destroy(ctx);
         return 255;
     }
-    lb200_ctx_destroy(ctx);
 
     int rc = 0;
     auto write_matrix = [&](std::ostream &out) {

@@ -128,14 +128,24 @@ def make_pp(path: str, name: str, seq: str, seed: int = 0, density: float = 2.2)
     write_pp(path, name, seq, dotplot(seq, seed=seed, density=density))
 
 
-def make_family(outdir: str, config: int, count: int, length, related: bool = False):
+def _make_one(job):
+    path, name, seq, seed = job
+    if not os.path.exists(path):
+        tmp = "%s.tmp%d" % (path, os.getpid())
+        make_pp(tmp, name, seq, seed=seed)
+        os.replace(tmp, path)
+    return path
+
+
+def make_family(outdir: str, config: int, count: int, length, related: bool = False, workers: int = 1):
     """Write ``count`` PP files named s<k>.pp; returns the list of paths.
 
     seed = 1000*config + index.  ``length`` is an int or a callable(rng)->int.
     With ``related`` the odd members are 70 %-identity relatives of their even predecessor.
+    ``workers`` > 1 writes the files with a process pool (every file depends only on its own seed); existing files are kept.
     """
     os.makedirs(outdir, exist_ok=True)
-    paths = []
+    jobs = []
     prev = None
     for k in range(count):
         seed = 1000 * config + k
@@ -145,7 +155,9 @@ def make_family(outdir: str, config: int, count: int, length, related: bool = Fa
         else:
             seq = random_sequence(n, seed)
         prev = seq
-        p = os.path.join(outdir, "s%d.pp" % k)
-        make_pp(p, "s%d" % k, seq, seed=seed)
-        paths.append(p)
-    return paths
+        jobs.append((os.path.join(outdir, "s%d.pp" % k), "s%d" % k, seq, seed))
+    if workers > 1 and count > 1:
+        import concurrent.futures as cf
+        with cf.ProcessPoolExecutor(max_workers=workers) as ex:
+            return list(ex.map(_make_one, jobs, chunksize=16))
+    return [_make_one(j) for j in jobs]

@@ -98,3 +98,25 @@ def test_mlocarna_tree_stage_archaea(tmp_path):
     # explicit flags equal to the defaults, results on stdout
     r2 = subprocess.run([CLI_TREE, "--struct-weight", "200", "-D", "30", "--noLP", "-p", "0.001"] + files, capture_output=True, text=True)
     assert r2.returncode == 0 and r2.stdout == allpairs.format_matrix(tree["matrix"]) + tree["newick"] + ";\n"
+
+
+def test_mlocarna_tree_stage_shares_and_gpus(tmp_path):
+    """The pair list split mlocarna's way over processes (--compute-pairwise-scores k/N, src/Utils/mlocarna:2321-2344; cost-balanced
+    shares) and over devices (--gpus): the partial score lists together are exactly the full list, and --gpus 1 equals the default."""
+    gold = json.load(open(os.path.join(GOLD, "reference_outputs.json")))
+    arch = gold["archaea"]
+    files = [os.path.join(GOLD, "archaea", n + ".pp") for n in arch["names"]]
+    want = {(a, b): s for (a, b), s in zip([tuple(p) for p in arch["pairs"]], arch["scores"])}
+    got = {}
+    for k in (1, 2, 3):
+        out = tmp_path / ("scores-%d" % k)
+        r = subprocess.run([CLI_TREE, "--compute-pairwise-scores", "%d/3" % k, "--score-list", str(out)] + files, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        for line in open(out):
+            a, b, s = line.split()
+            assert (int(a), int(b)) not in got
+            got[(int(a), int(b))] = int(s)
+    assert got == want
+    r1 = subprocess.run([CLI_TREE, "--gpus", "1"] + files, capture_output=True, text=True)
+    r0 = subprocess.run([CLI_TREE] + files, capture_output=True, text=True)
+    assert r1.returncode == 0 and r1.stdout == r0.stdout and r0.stdout
