@@ -293,10 +293,14 @@ __device__ void sweep(const DevCtx &c, const RowsCtx &r, const DevGroup &grp, co
     int pd = LB_NEG, ps = 0;
     bool pending = false;
     auto land = [&]() {
-        atomicMax(sm.acc + ps, pm.x + pd);
-        atomicMax(sm.acc + ps + RING * W, pm.y + pd);
-        atomicMax(sm.acc + ps + 2 * RING * W, pm.z + pd);
-        atomicMax(sm.acc + ps + 3 * RING * W, pm.w + pd);
+        // padding entries and entries with a source before u0 carry D = -inf: they fold nothing, and left in they would all hit the
+        // same accumulator (one serialised wavefront per lane)
+        if (pd >= LB_NEG_LIMIT) {
+            atomicMax(sm.acc + ps, pm.x + pd);
+            atomicMax(sm.acc + ps + RING * W, pm.y + pd);
+            atomicMax(sm.acc + ps + 2 * RING * W, pm.z + pd);
+            atomicMax(sm.acc + ps + 3 * RING * W, pm.w + pd);
+        }
     };
     auto fold = [&](int u) {   // after cell step u
         __syncwarp();
