@@ -34,6 +34,7 @@ struct PfoCtx {
     double *mats;            // per pair: 5 dense matrices (Mtop, Mrev00, Erev00, Frev00, bm), each mat_doubles
     double *cta;             // per CTA: 4 dense scratch matrices
     long long mat_doubles;   // >= (max lenA + 1) * (max lenB + 1)
+    int acc_cols;            // >= max lenB + 2: columns of the two shared-memory arc-term accumulators
     double am_threshold;     // sqrt(min_am_prob) (aligner_p.icc:1213-1216)
 };
 
@@ -80,27 +81,47 @@ __device__ PV make_pv(const DevCtx &c, const PfoCtx &o, const DevPair &pr) {
 
 #define PFO_AT(Mx, i, j) (Mx)[(size_t)(i) * v.W + (j)]
 
+// Arc-match terms of a dense sweep: the entries of the S-order list of one anti-diagonal are handled one per thread and summed per
+// target column into a shared-memory accumulator (the cells of an anti-diagonal have distinct columns); the cell pass of that
+// anti-diagonal adds and clears it. Two accumulators alternate, so the entries of the next anti-diagonal are folded in the same
+// barrier interval in which the cells of the current one are computed (their sources lie >= 8 anti-diagonals away and are final).
+struct PfoAcc { double *a[2]; };
+
 // align_inside_arcmatch on a dense matrix (aligner_p.icc:148-312); arc terms from the S-order list of the cell's anti-diagonal
-__device__ void dense_inside(const PV &v, int al, int ar, int bl, int br, double *M, double *Ed, double *Fd) {
+__device__ void dense_inside(const PV &v, int al, int ar, int bl, int br, double *M, double *Ed, double *Fd, const PfoAcc &acc, const double *bpow) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    if (tid == 0) {   // init_M :148-190
-        PFO_AT(M, al, bl) = v.inv_scale;
-        double s = v.open * v.inv_scale;
-        int i;
-        for (i = al + 1; i < ar; i++) { if (v.lo[i] > bl) break; s *= v.g; PFO_AT(M, i, bl) = s; }
-        for (; i < ar; i++) PFO_AT(M, i, v.lo[i] - 1) = 0;
-        const int max_col = min(br - 1, v.hi[al]);
-        s = v.open * v.inv_scale;
-        int j;
-        for (j = bl + 1; j <= max_col; j++) { s *= v.g; PFO_AT(M, al, j) = s; }
+    // init_M :148-190 (border values from the table of sequential products, zero guards around the band)
+    for (int i = al + tid; i < ar; i += nt) {
+        if (i == al) PFO_AT(M, al, bl) = v.inv_scale;
+        else if (v.lo[i] <= bl) PFO_AT(M, i, bl) = bpow[i - al];
+        else PFO_AT(M, i, v.lo[i] - 1) = 0;
+    }
+    const int max_col = min(br - 1, v.hi[al]);
+    for (int j = bl + 1 + tid; j <= max_col; j += nt) PFO_AT(M, al, j) = bpow[j - bl];
+    if (tid == 0) {
+        int j = max(max_col, bl) + 1;
         for (int i2 = al + 1; i2 < ar; i2++)
             for (; j < min(br, v.hi[i2] + 1); ++j) PFO_AT(M, i2 - 1, j) = 0;
     }
-    __syncthreads();
     auto cmin = [&](int i) { return max(bl + 1, v.lo[i]); };
     auto cmax = [&](int i) { return min(br - 1, v.hi[i]); };
     auto computed = [&](int i, int j) { return i > al && i < ar && j >= cmin(i) && j <= cmax(i); };
+    // entries of anti-diagonal d -> accumulator d & 1
+    auto fold = [&](int d) {
+        if (d < al + bl + 2 || d > ar + br - 2) return;
+        double *a = acc.a[d & 1];
+        for (int t = v.sptr[d] + tid; t < v.sptr[d + 1]; t += nt) {
+            const DevEntry en = v.ent[t];
+            const int i = LB_ENT_LO(en.y), j = LB_ENT_HI(en.y);
+            const int p = LB_ENT_LO(en.x), q = LB_ENT_HI(en.x);   // al'-1, bl'-1
+            if (computed(i, j) && p >= al && q >= bl) atomicAdd(a + j, PFO_AT(M, p, q) * v.dpf[t] * v.scale);
+        }
+    };
+    __syncthreads();
+    fold(al + bl + 2);
     for (int d = al + bl + 2; d <= ar + br - 2; d++) {
+        __syncthreads();
+        double *a = acc.a[d & 1];
         for (int i = max(al + 1, d - (br - 1)) + tid; i <= min(ar - 1, d - (bl + 1)); i += nt) {
             const int j = d - i;
             if (j < cmin(i) || j > cmax(i)) continue;
@@ -108,22 +129,17 @@ __device__ void dense_inside(const PV &v, int al, int ar, int bl, int br, double
             const double e = eu * v.g + (PFO_AT(M, i - 1, j) - eu) * v.g * v.open;
             const double fl = computed(i, j - 1) ? PFO_AT(Fd, i, j - 1) : 0.0;
             const double f = fl * v.g + (PFO_AT(M, i, j - 1) - fl) * v.g * v.open;
-            double pf = PFO_AT(M, i - 1, j - 1) * v.sig(i, j) + e + f;
-            const uint32_t y = (uint32_t)i | ((uint32_t)j << 16);
-            for (int t = v.sptr[d]; t < v.sptr[d + 1]; t++) {
-                const DevEntry en = v.ent[t];
-                if (en.y != y) continue;
-                const int p = LB_ENT_LO(en.x), q = LB_ENT_HI(en.x);   // al'-1, bl'-1
-                if (p >= al && q >= bl) pf += PFO_AT(M, p, q) * v.dpf[t] * v.scale;
-            }
+            const double pf = PFO_AT(M, i - 1, j - 1) * v.sig(i, j) + e + f + a[j];
+            a[j] = 0.0;
             PFO_AT(M, i, j) = pf; PFO_AT(Ed, i, j) = e; PFO_AT(Fd, i, j) = f;
         }
-        __syncthreads();
+        fold(d + 1);
     }
+    __syncthreads();
 }
 
 // align_reverse on a dense matrix (aligner_p.icc:451-627); arc terms from the L-order run of cell (i+1, j+1)
-__device__ void dense_reverse(const PV &v, int al, int ar, int bl, int br, double *Mr, double *Ed, double *Fd) {
+__device__ void dense_reverse(const PV &v, int al, int ar, int bl, int br, double *Mr, double *Ed, double *Fd, const double *bpow) {
     const int tid = threadIdx.x, nt = blockDim.x;
     // the reference refills the region with -1 "for debugging" (:586-590); kept because such a cell can be read (see dense_outside)
     if (ar >= al && br >= bl) {
@@ -131,21 +147,17 @@ __device__ void dense_reverse(const PV &v, int al, int ar, int bl, int br, doubl
         for (int k = tid; k < (ar - al + 1) * cols; k += nt) PFO_AT(Mr, al + k / cols, bl + k % cols) = -1.0;
     }
     __syncthreads();
-    if (tid == 0) {   // init_Mrev :451-510
+    // init_Mrev :451-510 (border values from the table of sequential products; the band is monotone, so "until the band ends" is a
+    // per-row / per-column test)
+    for (int i = al - 1 + tid; i < ar; i += nt) {
+        if (v.hi[i] >= br) PFO_AT(Mr, i, br) = bpow[ar - i];
+        else PFO_AT(Mr, i, v.hi[i] + 1) = 0;
+    }
+    const int min_col = max(bl - 1, v.lo[ar]);
+    for (int j = min_col + tid; j < br; j += nt) PFO_AT(Mr, ar, j) = bpow[br - j];
+    if (tid == 0) {
         PFO_AT(Mr, ar, br) = v.inv_scale;
-        double s = v.open * v.inv_scale;
-        int i;
-        for (i = ar; i >= al;) {
-            i--;
-            if (v.hi[i] < br) { ++i; break; }
-            s *= v.g;
-            PFO_AT(Mr, i, br) = s;
-        }
-        for (; i >= al;) { i--; PFO_AT(Mr, i, v.hi[i] + 1) = 0; }
-        s = v.open * v.inv_scale;
-        const int min_col = max(bl - 1, v.lo[ar]);
-        int j;
-        for (j = br; j > min_col;) { j--; s *= v.g; PFO_AT(Mr, ar, j) = s; }
+        int j = min(min_col, br);
         for (int i2 = ar; i2 >= al;) {
             i2--;
             for (; j > max(bl - 1, v.lo[i2]);) { --j; PFO_AT(Mr, i2 + 1, j) = 0; }
@@ -180,7 +192,7 @@ __device__ void dense_reverse(const PV &v, int al, int ar, int bl, int br, doubl
 
 // align_outside_arcmatch (aligner_p.icc:894-998) for the hole with left ends (al, bl): Mprime over rows ar..max_ar, columns br..max_br
 __device__ void dense_outside(const PV &v, int al, int ar, int max_ar, int bl, int br, int max_br, double m0, double *Mp, double *Ed, double *Fd,
-                              const double *Mrl, const double *Mr00, const double *Er00, const double *Fr00) {
+                              const double *Mrl, const double *Mr00, const double *Er00, const double *Fr00, const PfoAcc &acc) {
     const int tid = threadIdx.x, nt = blockDim.x;
     // The reference refills Mprime with -1 before every hole, "only for debugging" (:918) - but the value is read: the cell diagonally
     // behind a band corner of the region (e.g. Mprime(i+1, max_br) with (i+1, max_br) outside the band) is neither initialised nor
@@ -190,18 +202,15 @@ __device__ void dense_outside(const PV &v, int al, int ar, int max_ar, int bl, i
         for (int k = tid; k < (max_ar - ar + 1) * cols; k += nt) PFO_AT(Mp, ar + k / cols, br + k % cols) = -1.0;
     }
     __syncthreads();
-    if (tid == 0) {   // :920-965
-        if (v.valid(max_ar, max_br)) PFO_AT(Mp, max_ar, max_br) = m0 * PFO_AT(Mr00, max_ar, max_br) * v.scale;
-        int i;
-        for (i = max_ar; i > ar;) {
-            i--;
-            if (v.hi[i] < max_br) { i++; break; }
-            if (v.valid(i, max_br)) PFO_AT(Mp, i, max_br) = m0 * PFO_AT(Mr00, i, max_br) * v.scale;
-        }
-        for (; i > ar;) { i--; if (v.hi[i] + 1 <= max_br) PFO_AT(Mp, i, v.hi[i] + 1) = 0; }
-        int j;
-        const int min_col = max(br, v.lo[max_ar]), max_col = min(max_br - 1, v.hi[max_ar]);
-        for (j = max_col + 1; j > min_col;) { j--; PFO_AT(Mp, max_ar, j) = m0 * PFO_AT(Mr00, max_ar, j) * v.scale; }
+    // :920-965
+    for (int i = ar + tid; i <= max_ar; i += nt) {
+        if (i == max_ar || v.hi[i] >= max_br) { if (v.valid(i, max_br)) PFO_AT(Mp, i, max_br) = m0 * PFO_AT(Mr00, i, max_br) * v.scale; }
+        else if (v.hi[i] + 1 <= max_br) PFO_AT(Mp, i, v.hi[i] + 1) = 0;
+    }
+    const int min_col = max(br, v.lo[max_ar]), max_col = min(max_br - 1, v.hi[max_ar]);
+    for (int j = min_col + tid; j <= max_col; j += nt) PFO_AT(Mp, max_ar, j) = m0 * PFO_AT(Mr00, max_ar, j) * v.scale;
+    if (tid == 0) {
+        int j = max_col + 1 > min_col ? min_col : max_col + 1;
         for (int i2 = max_ar; i2 > ar;) {
             i2--;
             for (; j > max(bl, v.lo[i2]);) { --j; PFO_AT(Mp, i2 + 1, j) = 0; }
@@ -213,7 +222,21 @@ __device__ void dense_outside(const PV &v, int al, int ar, int max_ar, int bl, i
     auto computed = [&](int i, int j) { return i >= ar && i <= max_ar - 1 && j >= cmin(i) && j <= cmax(i); };
     const int e_lo = max(br, v.lo[max_ar]), e_hi = min(max_br - 1, v.hi[max_ar]);   // Eprime of the border row max_ar (:948-953)
     auto vmp = [&](int i, int j) { return (i >= max_ar || j >= max_br) ? m0 * PFO_AT(Mr00, i, j) * v.scale : PFO_AT(Mp, i, j); };   // virtual_Mprime :784-796
+    // case 4 (:836-858): arc matches with right ends (i+1, j+1) and left ends before (al, bl), from the list of anti-diagonal d + 2
+    auto fold = [&](int d) {
+        if (d < ar + br || d > max_ar + max_br - 2) return;
+        double *a = acc.a[d & 1];
+        for (int t = v.sptr[d + 2] + tid; t < v.sptr[d + 3]; t += nt) {
+            const DevEntry en = v.ent[t];
+            const int i = LB_ENT_LO(en.y) - 1, j = LB_ENT_HI(en.y) - 1;
+            const int p = LB_ENT_LO(en.x) + 1, q = LB_ENT_HI(en.x) + 1;   // al', bl'
+            if (computed(i, j) && p < al && q < bl) atomicAdd(a + j, v.dpp[t] * PFO_AT(Mrl, p, q) * v.scale);
+        }
+    };
+    fold(max_ar + max_br - 2);
     for (int d = max_ar + max_br - 2; d >= ar + br; d--) {
+        __syncthreads();
+        double *a = acc.a[d & 1];
         for (int i = max(ar, d - (max_br - 1)) + tid; i <= min(max_ar - 1, d - br); i += nt) {
             const int j = d - i;
             if (j < cmin(i) || j > cmax(i)) continue;
@@ -225,16 +248,8 @@ __device__ void dense_outside(const PV &v, int al, int ar, int max_ar, int bl, i
             if (i + 1 == max_ar) eu = (j >= e_lo && j <= e_hi) ? m0 * PFO_AT(Er00, max_ar, j) * v.scale : 0.0;
             else eu = computed(i + 1, j) ? PFO_AT(Ed, i + 1, j) : 0.0;
             const double e = eu * v.g + (PFO_AT(Mp, i + 1, j) - eu) * v.g * v.open;
-            double pf = PFO_AT(Mp, i + 1, j + 1) * v.sig(i + 1, j + 1) + e + f;
-            {   // case 4 (:836-858): arc matches with right ends (i+1, j+1) and left ends before (al, bl)
-                const uint32_t y = (uint32_t)(i + 1) | ((uint32_t)(j + 1) << 16);
-                for (int t = v.sptr[d + 2]; t < v.sptr[d + 3]; t++) {
-                    const DevEntry en = v.ent[t];
-                    if (en.y != y) continue;
-                    const int p = LB_ENT_LO(en.x) + 1, q = LB_ENT_HI(en.x) + 1;   // al', bl'
-                    if (p < al && q < bl) pf += v.dpp[t] * PFO_AT(Mrl, p, q) * v.scale;
-                }
-            }
+            double pf = PFO_AT(Mp, i + 1, j + 1) * v.sig(i + 1, j + 1) + e + f + a[j];
+            a[j] = 0.0;
             {   // case 5 (:861-881): arc matches with left ends (i+1, j+1)
                 int r0, r1;
                 v.run(i + 1, j + 1, r0, r1);
@@ -245,19 +260,30 @@ __device__ void dense_outside(const PV &v, int al, int ar, int max_ar, int bl, i
             }
             PFO_AT(Mp, i, j) = pf; PFO_AT(Ed, i, j) = e; PFO_AT(Fd, i, j) = f;
         }
-        __syncthreads();
+        fold(d - 1);
     }
+    __syncthreads();
+}
+
+__device__ PfoAcc make_acc(const PfoCtx &o, double *smem) {
+    PfoAcc acc;
+    acc.a[0] = smem; acc.a[1] = smem + o.acc_cols;
+    for (int k = threadIdx.x; k < 2 * o.acc_cols; k += blockDim.x) smem[k] = 0.0;
+    __syncthreads();
+    return acc;
 }
 
 // per pair: prefix table of the whole sequences (aligner_p.icc:428-433) and suffix tables with the E / F copies (:1133)
 __global__ void __launch_bounds__(128) pfo_prepare_kernel(DevCtx c, PfoCtx o, int n_pairs) {
+    extern __shared__ double pfo_smem[];
+    const PfoAcc acc = make_acc(o, pfo_smem);
     for (int pk = blockIdx.x; pk < n_pairs; pk += gridDim.x) {
         const DevPair pr = c.pairs[pk];
         const PV v = make_pv(c, o, pr);
         double *mats = o.mats + (size_t)pk * 5 * o.mat_doubles;
         double *cta = o.cta + (size_t)blockIdx.x * 4 * o.mat_doubles;
-        dense_inside(v, 0, v.n + 1, 0, v.m + 1, mats, cta, cta + o.mat_doubles);
-        dense_reverse(v, 1, v.n, 1, v.m, mats + o.mat_doubles, mats + 2 * o.mat_doubles, mats + 3 * o.mat_doubles);
+        dense_inside(v, 0, v.n + 1, 0, v.m + 1, mats, cta, cta + o.mat_doubles, acc, o.pc.bpow);
+        dense_reverse(v, 1, v.n, 1, v.m, mats + o.mat_doubles, mats + 2 * o.mat_doubles, mats + 3 * o.mat_doubles, o.pc.bpow);
         for (size_t k = threadIdx.x; k < (size_t)(v.n + 1) * v.W; k += blockDim.x) mats[4 * o.mat_doubles + k] = 0.0;
         __syncthreads();
     }
@@ -265,10 +291,12 @@ __global__ void __launch_bounds__(128) pfo_prepare_kernel(DevCtx c, PfoCtx o, in
 
 // one level group of holes: align_outside_arcmatch + fill_Dprime (aligner_p.icc:1048-1108)
 __global__ void __launch_bounds__(128) pfo_outside_kernel(DevCtx c, PfoCtx o, int q, int *cursor) {
+    extern __shared__ double pfo_smem[];
     __shared__ int s_task;
     __shared__ int s_red[4];
     const int task_begin = c.qstart[q], task_end = c.qstart[q + 1];
     if ((int)blockIdx.x >= task_end - task_begin) return;
+    const PfoAcc acc = make_acc(o, pfo_smem);
     double *cta = o.cta + (size_t)blockIdx.x * 4 * o.mat_doubles;
     double *Mrl = cta, *Mp = cta + o.mat_doubles, *Ed = cta + 2 * o.mat_doubles, *Fd = cta + 3 * o.mat_doubles;
     for (;;) {
@@ -312,8 +340,8 @@ __global__ void __launch_bounds__(128) pfo_outside_kernel(DevCtx c, PfoCtx o, in
             sA = s_red[0]; sB = s_red[1]; max_ar = s_red[2]; max_br = s_red[3];
         }
         const double m0 = PFO_AT(Mtop, al - 1, bl - 1);
-        dense_reverse(v, sA + 1, al - 1, sB + 1, bl - 1, Mrl, Ed, Fd);
-        dense_outside(v, al, min_ar, max_ar, bl, min_br, max_br, m0, Mp, Ed, Fd, Mrl, Mr00, Er00, Fr00);
+        dense_reverse(v, sA + 1, al - 1, sB + 1, bl - 1, Mrl, Ed, Fd, o.pc.bpow);
+        dense_outside(v, al, min_ar, max_ar, bl, min_br, max_br, m0, Mp, Ed, Fd, Mrl, Mr00, Er00, Fr00, acc);
         // fill_Dprime (:1011-1043)
         for (int k = task.run_start + threadIdx.x; k < task.run_start + task.run_count; k += blockDim.x) {
             const DevArcMatch x = v.am[k];
@@ -340,8 +368,10 @@ __global__ void pfo_amprob_kernel(DevCtx c, PfoCtx o, int n_pairs) {
 
 // compute_basematch_probabilities, enclosed case (aligner_p.icc:1220-1330): one CTA per left-end pair
 __global__ void __launch_bounds__(128) pfo_bm_enclosed_kernel(DevCtx c, PfoCtx o, int n_tasks, int *cursor) {
+    extern __shared__ double pfo_smem[];
     __shared__ int s_task;
     __shared__ int s_red[2];
+    const PfoAcc acc = make_acc(o, pfo_smem);
     double *cta = o.cta + (size_t)blockIdx.x * 4 * o.mat_doubles;
     double *M = cta, *Mr = cta + o.mat_doubles, *Ed = cta + 2 * o.mat_doubles, *Fd = cta + 3 * o.mat_doubles;
     for (;;) {
@@ -364,12 +394,12 @@ __global__ void __launch_bounds__(128) pfo_bm_enclosed_kernel(DevCtx c, PfoCtx o
         max_ar = s_red[0]; max_br = s_red[1];
         __syncthreads();
         if (max_ar == al) continue;   // no arc match of this cell above the threshold
-        dense_inside(v, al, max_ar, bl, max_br, M, Ed, Fd);
+        dense_inside(v, al, max_ar, bl, max_br, M, Ed, Fd, acc, o.pc.bpow);
         for (int k = task.run_start; k < task.run_start + task.run_count; k++) {
             const DevArcMatch x = v.am[k];
             if (!(v.amp[x.spos] > o.am_threshold)) continue;
             const int ar = x.ends_a >> 12, br = x.ends_b >> 12;
-            dense_reverse(v, al + 1, ar - 1, bl + 1, br - 1, Mr, Ed, Fd);
+            dense_reverse(v, al + 1, ar - 1, bl + 1, br - 1, Mr, Ed, Fd, o.pc.bpow);
             const double outside_pf = v.dpp[x.spos];
             const int rows = ar - al - 1, cols = br - bl - 1;
             for (int idx = threadIdx.x; idx < rows * cols; idx += blockDim.x) {
@@ -401,11 +431,11 @@ __global__ void pfo_bm_final_kernel(DevCtx c, PfoCtx o, int n_pairs) {
 
 #undef PFO_AT
 
-void launch_pfo_prepare(const DevCtx &c, const PfoCtx &o, int n_pairs, int grid, cudaStream_t st) { pfo_prepare_kernel<<<grid, 128, 0, st>>>(c, o, n_pairs); }
-void launch_pfo_outside(const DevCtx &c, const PfoCtx &o, int q, int grid, int *cursor, cudaStream_t st) { pfo_outside_kernel<<<grid, 128, 0, st>>>(c, o, q, cursor); }
+void launch_pfo_prepare(const DevCtx &c, const PfoCtx &o, int n_pairs, int grid, cudaStream_t st) { pfo_prepare_kernel<<<grid, 128, 2 * o.acc_cols * sizeof(double), st>>>(c, o, n_pairs); }
+void launch_pfo_outside(const DevCtx &c, const PfoCtx &o, int q, int grid, int *cursor, cudaStream_t st) { pfo_outside_kernel<<<grid, 128, 2 * o.acc_cols * sizeof(double), st>>>(c, o, q, cursor); }
 void launch_pfo_amprob(const DevCtx &c, const PfoCtx &o, int n_pairs, cudaStream_t st) { pfo_amprob_kernel<<<min(n_pairs, 1184), 256, 0, st>>>(c, o, n_pairs); }
 void launch_pfo_bm(const DevCtx &c, const PfoCtx &o, int n_tasks, int n_pairs, int grid, int *cursor, cudaStream_t st) {
-    pfo_bm_enclosed_kernel<<<grid, 128, 0, st>>>(c, o, n_tasks, cursor);
+    pfo_bm_enclosed_kernel<<<grid, 128, 2 * o.acc_cols * sizeof(double), st>>>(c, o, n_tasks, cursor);
     pfo_bm_final_kernel<<<min(n_pairs, 1184), 256, 0, st>>>(c, o, n_pairs);
 }
 

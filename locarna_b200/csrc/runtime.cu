@@ -46,6 +46,7 @@ struct PfoCtx {   // must match pf_outside.cuh
     const int *lptr, *lcount;
     double *dpp; double *amp; double *mats; double *cta;
     long long mat_doubles;
+    int acc_cols;
     double am_threshold;
 };
 void launch_pfo_prepare(const DevCtx &c, const PfoCtx &o, int n_pairs, int grid, cudaStream_t st);
@@ -1171,6 +1172,8 @@ int lb200_run_pf_probs(lb200_ctx *c, double pf_scale, double min_am_prob) {
     o.lptr = (const int *)c->d_lptr.p; o.lcount = (const int *)c->d_lcount.p;
     o.dpp = (double *)c->d_pf_dp.p; o.amp = (double *)c->d_pf_amp.p; o.mats = (double *)c->d_pf_mats.p; o.cta = (double *)c->d_pf_cta.p;
     o.mat_doubles = mat; o.am_threshold = std::sqrt(min_am_prob);
+    o.acc_cols = (c->max_len + 4) & ~1;
+    if (2 * (size_t)o.acc_cols * 8 > 40000) return fail(c, LB200_ERR_UNSUPPORTED, "LocARNA-P probabilities: sequence B is too long (%d) for the shared-memory accumulators", c->max_len);
     CUDA_TRY(c, cudaEventRecord(c->ev0, st));
     CUDA_TRY(c, cudaMemsetAsync(c->d_cursor.p, 0, 4100 * 4, st));
     CUDA_TRY(c, cudaMemsetAsync(c->d_pf_dp.p, 0, std::max<size_t>(R.total_am, 1) * 8, st));   // Dmatprime.fill(0), aligner_p.icc:46-47

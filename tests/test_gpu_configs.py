@@ -91,3 +91,33 @@ def test_locarna_p_300nt_against_oracle(tmp_path_factory):
     bm = ctx.basematch_probs(0)
     assert all(close(x, y) for rx, ry in zip(bm, ref["bm"]) for x, y in zip(rx, ry))
     ctx.close()
+
+
+def test_config4_locarna_p_1500nt(tmp_path_factory):
+    """BASELINE config 4, second half: LocARNA-P match probabilities of the two 1,500-nt RNAs against the COMPILED REFERENCE
+    (tests/golden/cfg4_locarna_p.json, made by tools/make_golden_p1500.py: AlignerP<double>, about ten minutes on the CPU): the
+    partition function, and every arc-match / base-match probability >= 0.001, within 1e-6 relative."""
+    path = os.path.join(ROOT, "tests", "golden", "cfg4_locarna_p.json")
+    if not os.path.exists(path):
+        pytest.skip("fixture not generated")
+    g = json.load(open(path))
+    from locarna_b200 import synth
+    paths = synth.make_family(str(tmp_path_factory.mktemp("cfg4p")), 4, 2, g["n"])
+    ctx = capi.Context(0, g["flags"])
+    a, b = ctx.add_pp(paths[0]), ctx.add_pp(paths[1])
+    ctx.add_pair(a, b)
+    ctx.run_pf_probs(1.0, 0.001)
+    z = ctx.partition_function(0)
+    assert abs(z - g["Z"]) <= 1e-6 * abs(g["Z"])
+    am, _ = ctx.arcmatches(0)
+    assert len(am) == g["n_arcmatches"]
+    amp = ctx.arcmatch_probs(0)
+    got = {tuple(am[k]): amp[k] for k in range(len(am))}
+    rel = lambda x, y: abs(x - y) / max(abs(x), abs(y), 1e-300)
+    assert g["am_probs"] and max(rel(got[tuple(x[:4])], x[4]) for x in g["am_probs"]) <= 1e-6
+    # nothing above the reference's output threshold that the reference does not list (its list is >= 0.001)
+    listed = {tuple(x[:4]) for x in g["am_probs"]}
+    assert all(p < 0.001 * (1 + 1e-6) for k, p in got.items() if k not in listed)
+    bm = ctx.basematch_probs(0)
+    assert g["bm_probs"] and max(rel(bm[i][j], p) for i, j, p in g["bm_probs"]) <= 1e-6
+    ctx.close()
