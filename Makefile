@@ -12,7 +12,10 @@ CLI       := locarna_b200/bin/locarna_b200
 CLI_P     := locarna_b200/bin/locarna_p_b200
 CLI_TREE  := locarna_b200/bin/mlocarna_tree_b200
 
-all: $(LIB) $(CLI) $(CLI_P) $(CLI_TREE)
+REFSRC    := /root/reference/src/locarna.cc
+CLI_REF   := locarna_b200/bin/locarna_refmain_b200
+
+all: $(LIB) $(CLI) $(CLI_P) $(CLI_TREE) $(if $(wildcard $(REFSRC)),$(CLI_REF))
 
 $(OBJ):
 	mkdir -p $(OBJ)
@@ -42,6 +45,16 @@ $(CLI_P): $(SRC)/cli/locarna_p_main.cc include/locarna_b200.hh include/locarna_b
 $(CLI_TREE): $(SRC)/cli/mlocarna_tree_main.cc include/locarna_b200.h $(LIB)
 	mkdir -p locarna_b200/bin
 	/usr/bin/g++ -std=c++17 -O2 -Wall -Iinclude $< -o $@ -Llocarna_b200 -llocarna_b200 -Wl,-rpath,'$$ORIGIN/..'
+
+# The reference's own pipeline code on the B200 library: the body of run_and_report() is cut from the reference tree (never committed)
+# and compiled unmodified against include/locarna_b200_compat.hh. Built only where the reference tree is present.
+refmain: $(CLI_REF)
+build/refmain/refmain_block.inc: $(REFSRC) tools/extract_ref_block.py
+	mkdir -p build/refmain
+	python tools/extract_ref_block.py $(REFSRC) $@
+$(CLI_REF): $(SRC)/cli/refmain_driver.cc build/refmain/refmain_block.inc include/locarna_b200_compat.hh include/locarna_b200.hh include/locarna_b200.h $(LIB)
+	mkdir -p locarna_b200/bin
+	/usr/bin/g++ -std=c++17 -O2 -Wall -Wno-unused-variable -Wno-unused-local-typedefs -Iinclude -Ibuild/refmain $< -o $@ -Llocarna_b200 -llocarna_b200 -Wl,-rpath,'$$ORIGIN/..'
 
 clean:
 	rm -rf build $(LIB) locarna_b200/bin
