@@ -75,6 +75,9 @@ typedef struct lb200_params {
     double exp_prob;              /* --exp-prob / -e            < 0 = not given: background probability 1/(2 len) per sequence (src/locarna.cc:662-663) */
     double max_bps_length_ratio;  /* --max-bps-length-ratio     0 = off; keep only the ratio*length most probable base pairs per sequence (rna_data.cc:64-67) */
     int max_bp_span;              /* --maxBPspan                -1 = unrestricted; base pairs with j-i+1 > span are dropped on input (rna_data.cc:1078) */
+    int stacking;                 /* --stacking                 stacked arc matches scored by P(pair | inner pair) (scoring.cc:201-248, aligner.cc:600-607);
+                                                                needs the joint probabilities of the PP input (fourth column, #STACK) */
+    int new_stacking;             /* --new-stacking             stack weight = weight + weight of the joint probability */
 } lb200_params;
 
 typedef struct lb200_pair_info {

@@ -258,7 +258,6 @@ class Aligner {  // aligner.hh:67-189
 public:
     explicit Aligner(const AlignerParams &ap, int device = 0) : ctx_(std::make_shared<Context>(device)) {
         if (!ap.rnaA_ || !ap.rnaB_) throw failure("AlignerParams: seqA and seqB are mandatory");
-        if (ap.stacking_ || ap.scoring_.stacking || ap.scoring_.new_stacking) throw failure("locarna_b200: stacking is not supported");
         if (ap.scoring_.mea_scoring) throw failure("locarna_b200: MEA scoring is not supported");
         lb200_params p;
         lb200_default_params(&p);
@@ -268,6 +267,7 @@ public:
         p.struct_weight = s.struct_weight; p.indel = s.indel; p.indel_opening = s.indel_opening; p.tau = s.tau_factor;
         p.exclusion = s.exclusion; p.match = s.match; p.mismatch = s.mismatch; p.use_ribosum = s.use_ribosum;
         p.unpaired_penalty = s.unpaired_penalty; p.temperature_alipf = s.temperature_alipf;
+        p.stacking = s.stacking; p.new_stacking = s.new_stacking;   // Scoring::stacking() decides (scoring.hh:652-655); AlignerParams::stacking is unused by the reference's aligner
         if (ap.rnaA_->max_bp_span() != ap.rnaB_->max_bp_span() || ap.rnaA_->max_bps_length_ratio() != ap.rnaB_->max_bps_length_ratio())
             throw failure("locarna_b200: both RnaData objects must use the same max_bp_span and max_bps_length_ratio");
         p.exp_prob = s.exp_prob; p.max_bp_span = ap.rnaA_->max_bp_span(); p.max_bps_length_ratio = ap.rnaA_->max_bps_length_ratio();

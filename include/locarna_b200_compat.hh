@@ -26,7 +26,7 @@
 //
 // The objects of the reference compute on construction (RnaData parses, ArcMatches enumerates, Scoring precomputes). Here they record
 // their arguments; the device builds bands, arc matches and scores when Aligner runs. What the B200 path does not implement
-// (reference alignments for --max-diff-aln, anchors, MEA, explicit arc-match scores, k-best) throws LocARNA::failure from the object
+// (reference alignments for --max-diff-aln, anchors, MEA, explicit arc-match scores, k-best, normalized / penalized) throws LocARNA::failure from the object
 // that would need it, so the caller's existing error handling applies.
 #ifndef LOCARNA_B200_COMPAT_HH
 #define LOCARNA_B200_COMPAT_HH
@@ -294,11 +294,11 @@ public:
 inline LocARNA_B200::AlignerParams to_b200_params(const Scoring &s, const TraceController &tc, bool noLP, bool struct_local, bool sequ_local,
                                                   const std::string &free_endgaps, int max_diff_am, int max_diff_at_am) {
     const ScoringParams &p = s.params();
-    if (p.stacking_ || p.new_stacking_) throw failure("locarna_b200: stacking is not supported");
     LocARNA_B200::ScoringParams sp;
     sp.match = p.match_; sp.mismatch = p.mismatch_; sp.indel = p.indel_; sp.indel_opening = p.indel_opening_; sp.unpaired_penalty = p.unpaired_penalty_;
     sp.struct_weight = p.struct_weight_; sp.tau_factor = p.tau_factor_; sp.exclusion = p.exclusion_; sp.temperature_alipf = p.temperature_alipf_;
     sp.use_ribosum = p.ribosum_ != nullptr;
+    sp.stacking = p.stacking_; sp.new_stacking = p.new_stacking_;
     // background probabilities: the library takes one value for both sequences, or derives 1 / (2 len) per sequence (locarna.cc:662-663)
     const double defA = prob_exp_f((int)s.rnaA().length()), defB = prob_exp_f((int)s.rnaB().length());
     if (p.exp_probA_ == defA && p.exp_probB_ == defB) sp.exp_prob = -1.0;
@@ -316,7 +316,6 @@ class Aligner {   // aligner.hh:67-189
 public:
     explicit Aligner(const AlignerParams &ap) {
         if (!ap.seqA_ || !ap.seqB_ || !ap.scoring_ || !ap.trace_controller_) throw failure("AlignerParams: seqA, seqB, scoring and trace_controller are mandatory");
-        if (ap.stacking_) throw failure("locarna_b200: stacking is not supported");
         if (ap.constraints_ && !ap.constraints_->empty()) throw failure("locarna_b200: anchor constraints are not supported");
         impl_.reset(new LocARNA_B200::Aligner(to_b200_params(*ap.scoring_, *ap.trace_controller_, ap.no_lonely_pairs_, ap.struct_local_, ap.sequ_local_,
                                                                ap.free_endgaps_.str(), ap.max_diff_am_, ap.max_diff_at_am_)));

@@ -27,6 +27,7 @@ class Params(C.Structure):
         ("temperature_alipf", C.c_int),
         ("no_lonely_pairs", C.c_int), ("struct_local", C.c_int), ("sequ_local", C.c_int),
         ("free_endgaps", C.c_char * 8), ("pf_double", C.c_int), ("exp_prob", C.c_double), ("max_bps_length_ratio", C.c_double), ("max_bp_span", C.c_int),
+        ("stacking", C.c_int), ("new_stacking", C.c_int),
     ]
 
 
@@ -119,7 +120,7 @@ FLAG_FIELDS = {
     "min-trace-probability": "min_trace_probability", "noLP": "no_lonely_pairs", "struct-local": "struct_local",
     "sequ-local": "sequ_local", "struct-weight": "struct_weight", "indel": "indel", "indel-opening": "indel_opening",
     "tau": "tau", "exclusion": "exclusion", "match": "match", "mismatch": "mismatch",
-    "temperature-alipf": "temperature_alipf", "unpaired-penalty": "unpaired_penalty", "pf-double": "pf_double", "exp-prob": "exp_prob", "maxBPspan": "max_bp_span", "max-bps-length-ratio": "max_bps_length_ratio",
+    "temperature-alipf": "temperature_alipf", "unpaired-penalty": "unpaired_penalty", "pf-double": "pf_double", "exp-prob": "exp_prob", "maxBPspan": "max_bp_span", "max-bps-length-ratio": "max_bps_length_ratio", "stacking": "stacking", "new-stacking": "new_stacking",
 }
 
 

@@ -36,8 +36,8 @@ __device__ __forceinline__ bool valid_match(const int *lo, const int *hi, int i,
 
 struct PairView {
     const int *lo, *hi, *rev;
-    const int *alA, *arA, *wA, *lpA, *lcA;
-    const int *alB, *arB, *wB, *lpB, *lcB;
+    const int *alA, *arA, *wA, *lpA, *lcA, *sdA;
+    const int *alB, *arB, *wB, *lpB, *lcB, *sdB;
     const uint8_t *cA, *cB;
     int n, m;
     long mdam, mdat;
@@ -48,6 +48,7 @@ __device__ __forceinline__ PairView view(const BuildCtx &b, const DevPair &p) {
     v.lo = b.band_lo + p.band; v.hi = b.band_hi + p.band; v.rev = b.cell_rev + p.band;
     v.alA = b.arc_left + p.arcsA; v.arA = b.arc_right + p.arcsA; v.wA = b.arc_weight + p.arcsA;
     v.alB = b.arc_left + p.arcsB; v.arB = b.arc_right + p.arcsB; v.wB = b.arc_weight + p.arcsB;
+    v.sdA = b.arc_sdelta + p.arcsA; v.sdB = b.arc_sdelta + p.arcsB;
     v.lpA = b.lptr + p.lptrA; v.lcA = b.lcount + p.lptrA; v.lpB = b.lptr + p.lptrB; v.lcB = b.lcount + p.lptrB;
     v.cA = b.codes + p.codesA; v.cB = b.codes + p.codesB;
     v.n = p.lenA; v.m = p.lenB;
@@ -110,6 +111,9 @@ __global__ void __launch_bounds__(128) enumerate_kernel(BuildCtx b) {
                         x.ends_b = (uint32_t)bl | ((uint32_t)br << 12);
                         x.score = arcmatch_score(b, v, a, bb, al, ar, bl, br);
                         x.spos = -1; x.inner = -1;
+                        // Scoring::arcmatch(am, true): the same sequence term with the stack weights (scoring.cc:478-483)
+                        const int da = v.sdA[a], db = v.sdB[bb];
+                        x.score_st = (da == LB_NOSTACK || db == LB_NOSTACK) ? LB_NOSTACK : x.score + da + db;
                         b.am[g + k] = x;
                         // S-order: target anti-diagonal ascending, source anti-diagonal (al-1)+(bl-1) descending (see kernels.cu Stream3)
                         b.skeys[g + k] = ((unsigned long long)blockIdx.x << 26) | ((unsigned long long)(ar + br) << 13) | (unsigned long long)(8191 - (al + bl - 2));

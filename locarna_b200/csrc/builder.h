@@ -13,6 +13,7 @@ struct BuildCtx {
     const uint8_t *codes;
     const int *band_lo, *band_hi, *cell_rev;   // cell_rev[al] = number of band cells in rows > al
     const int *arc_left, *arc_right, *arc_weight, *lptr, *lcount;
+    const int *arc_sdelta;                      // per arc: stack weight - weight, LB_NOSTACK if the arc is not stackable
     const int *am_seq;                          // 256: (tau * ribosum arc-match score) / 100
     int sigma8[64];
     int tau, use_ribosum, no_lonely_pairs, struct_local, max_diff_am, max_diff_at_am;

@@ -115,7 +115,9 @@ int main(int argc, char **argv) {
             case O_MAXBPSPAN: max_bp_span = atoi(optarg); break;
             case 'e': case O_EXP_PROB: sp.exp_prob = atof(optarg); break;
             case O_WRITE_ARCMATCH_SCORES: arcmatch_scores_file = optarg; break;
-            case O_STACKING: case O_NEW_STACKING: case O_NORMALIZED: case O_PENALIZED: case O_PP:
+            case O_STACKING: sp.stacking = true; break;
+            case O_NEW_STACKING: sp.new_stacking = true; break;
+            case O_NORMALIZED: case O_PENALIZED: case O_PP:
             case O_UNSUPPORTED:
                 std::cerr << "ERROR: option --" << (idx >= 0 && longopts[idx].name ? longopts[idx].name : "?")
                           << " selects a mode that locarna_b200 does not implement." << std::endl;
@@ -129,6 +131,12 @@ int main(int argc, char **argv) {
         }
     }
     if (argc - optind != 2) { std::cerr << "ERROR: expected two input files (PP 2.0)." << std::endl; return 255; }
+    if (sp.stacking && sp.exp_prob < 0) {   // locarna.cc:406-414
+        std::cerr << "WARNING: stacking turned off. "
+                  << "Stacking requires setting a background probability "
+                  << "explicitely (option --exp-prob)." << std::endl;
+        sp.stacking = false;
+    }
     try {
         RnaData rnaA(argv[optind], min_prob, max_bps_length_ratio, max_bp_span), rnaB(argv[optind + 1], min_prob, max_bps_length_ratio, max_bp_span);
         ap.seqA(&rnaA).seqB(&rnaB).scoring(sp).min_prob(min_prob);

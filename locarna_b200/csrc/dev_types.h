@@ -22,6 +22,7 @@ struct DevParams {
     int open;         // indel_opening
     int exclusion;
     int no_lonely_pairs, struct_local, sequ_local;
+    int stacking;     // Scoring::stacking(): stacked arc matches (scoring.hh:652-655)
     int fe_left1, fe_right1, fe_left2, fe_right2;  // free_endgaps.hh:42-70
     int sigma8[64];   // base match score by symbol codes (8x8), unpaired penalty applied (scoring.cc:141-198)
 };
@@ -71,7 +72,9 @@ struct DevArcMatch {
     int score;         // Scoring::arcmatch(am) (scoring.cc:441-485)
     int spos;          // position in S-order (relative to am_base)
     int inner;         // L-order index of the inner arc match (al+1,ar-1,bl+1,br-1) or -1
+    int score_st;      // Scoring::arcmatch(am, true) if both arcs are stackable (scoring.cc:556-569), else LB_NOSTACK
 };
+#define LB_NOSTACK (-0x7fffffff - 1)
 
 // one D-fill task: all arc matches with common left ends (arc_matches.cc:313-355, aligner.cc:660-732)
 struct DevTask {

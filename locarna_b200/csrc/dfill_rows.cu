@@ -354,6 +354,7 @@ __device__ void write_d(const DevCtx &c, const DevPair &pr, const DevGroup &grp,
     const DevArcMatch *am = c.am + pr.am_base;
     DevEntry *ent = c.ent + pr.am_base;
     const int sh = nolp ? 2 : 1;
+    const bool stacking = c.params.stacking != 0;
     int end[V], total = 0;
 #pragma unroll
     for (int v = 0; v < V; v++) { total += v < grp.nmem ? tk[v].run_count : 0; end[v] = total; }
@@ -366,7 +367,7 @@ __device__ void write_d(const DevCtx &c, const DevPair &pr, const DevGroup &grp,
         for (int k = 1; k < V; k++) if (v == k) run_start = tk[k].run_start;
         const int k = run_start + (t - base);
         const DevArcMatch x = am[k];
-        if (nolp && x.inner < 0) continue;
+        if (nolp && (x.inner < 0 || (stacking && x.score_st == LB_NOSTACK))) continue;   // aligner.cc:628-629
         const int ar = (x.ends_a >> 12) & 0xfff, br = (x.ends_b >> 12) & 0xfff;
         const int ip = ar - sh - g.al, jp = br - sh - g.bl0;
         const int mv = __ldcg(box + ((ip + jp) * W + (jp & (W - 1))) * V + v);
@@ -375,8 +376,14 @@ __device__ void write_d(const DevCtx &c, const DevPair &pr, const DevGroup &grp,
             const DevArcMatch in = am[x.inner];
             const int a = (mv < LB_NEG_LIMIT) ? LB_NEG : mv + in.score;
             const int y = max(a, __ldcg(&ent[in.spos].d));
-            d = (y < LB_NEG_LIMIT) ? LB_NEG : y + x.score;
-        } else d = (mv < LB_NEG_LIMIT) ? LB_NEG : mv + x.score;
+            d = (y < LB_NEG_LIMIT) ? LB_NEG : y + (stacking ? x.score_st : x.score);
+        } else {
+            d = (mv < LB_NEG_LIMIT) ? LB_NEG : mv + x.score;
+            if (stacking && x.inner >= 0 && x.score_st != LB_NOSTACK) {   // aligner.cc:600-607
+                const int di = __ldcg(&ent[am[x.inner].spos].d);
+                if (di >= LB_NEG_LIMIT) d = max(d, di + x.score_st);
+            }
+        }
         ent[x.spos].d = d;
         if (c.ent8 != nullptr) c.ent8[pr.am_base + x.spos].y = LB_PACK_W1(br, d);
     }

@@ -55,7 +55,7 @@ static bool next_line(std::istream &in, std::string &line) {
 static bool begins(const std::string &s, const char *p) { return s.compare(0, strlen(p), p) == 0; }
 
 // rna_data.cc:984-1103 (PP 2.0), multiple_alignment.cc:279-401 (sequence block), aux.cc:65-70
-bool read_pp(const std::string &path, double p_bpcut, Sequence &out, std::string &err, int max_bp_span, double max_bps_length_ratio) {
+bool read_pp(const std::string &path, double p_bpcut, Sequence &out, std::string &err, int max_bp_span, double max_bps_length_ratio, bool stacking) {
     std::ifstream in(path.c_str());
     if (!in) { err = "cannot open " + path; return false; }
     std::string line;
@@ -78,7 +78,8 @@ bool read_pp(const std::string &path, double p_bpcut, Sequence &out, std::string
     }
     if (!next_line(in, line) || line != "#SECTION BASEPAIRS") { err = path + ": Expected base pair section header."; return false; }
     std::vector<int> pi, pj;
-    std::vector<double> pp;
+    std::vector<double> pp, pp2;
+    bool stack_keyword = false, any_p2 = false;
     double cut = p_bpcut;
     // #BPCUT may raise the cutoff at any point of the section; it applies to the lines after it (rna_data.cc:1047-1078)
     std::vector<double> cut_at;
@@ -91,7 +92,7 @@ bool read_pp(const std::string &path, double p_bpcut, Sequence &out, std::string
                 ls >> d >> p;
                 if (ls.fail()) { err = "Cannot parse line \"" + line + "\" in base pairs section."; return false; }
                 cut = std::max(p, cut);
-            }
+            } else if (begins(line, "#STACK")) stack_keyword = true;
             continue;
         }
         std::istringstream ls(line);
@@ -100,14 +101,21 @@ bool read_pp(const std::string &path, double p_bpcut, Sequence &out, std::string
         if (ls.fail()) { err = "Cannot parse line \"" + line + "\" in base pairs section."; return false; }
         if (!(1 <= i && i < j && j <= (long)seq.size())) { err = "Invalid indices in PP input line \"" + line + "\"."; return false; }
         if (p <= cut) continue;
-        pi.push_back((int)i); pj.push_back((int)j); pp.push_back(p);
+        if (max_bp_span >= 0 && j - i + 1 > max_bp_span) continue;
+        double p2 = 0.0;
+        if (stacking) {   // joint probability of (i, j) and (i+1, j-1), kept above the cutoff (rna_data.cc:1083-1093)
+            double v;
+            if (ls >> v) { if (v > cut) { p2 = v; any_p2 = true; } }
+        }
+        pi.push_back((int)i); pj.push_back((int)j); pp.push_back(p); pp2.push_back(p2);
     }
+    if (!stack_keyword && any_p2) { err = "Stacking probabilties found but stack keyword is missing."; return false; }   // rna_data.cc:1097-1100
     // the pairs were already filtered line by line; pass a cutoff that keeps them all
-    return make_sequence(name, seq, pi.data(), pj.data(), pp.data(), (int)pi.size(), -1.0, out, err, max_bp_span, max_bps_length_ratio);
+    return make_sequence(name, seq, pi.data(), pj.data(), pp.data(), (int)pi.size(), -1.0, out, err, max_bp_span, max_bps_length_ratio, pp2.data());
 }
 
 bool make_sequence(const std::string &name, const std::string &seq, const int *pi, const int *pj, const double *pp, int npairs,
-                   double p_bpcut, Sequence &out, std::string &err, int max_bp_span, double max_bps_length_ratio) {
+                   double p_bpcut, Sequence &out, std::string &err, int max_bp_span, double max_bps_length_ratio, const double *pp2) {
     out = Sequence();
     out.name = name;
     out.seq = seq;
@@ -122,11 +130,13 @@ bool make_sequence(const std::string &name, const std::string &seq, const int *p
     }
     out.cutoff = p_bpcut;
     std::map<std::pair<int, int>, double> uniq;  // a repeated pair overwrites the earlier value (sparse matrix assignment)
+    std::map<std::pair<int, int>, double> joint;
     for (int k = 0; k < npairs; k++) {
         if (!(1 <= pi[k] && pi[k] < pj[k] && pj[k] <= out.len)) { err = "invalid base pair indices"; return false; }
         if (pp[k] <= p_bpcut) continue;
         if (max_bp_span >= 0 && pj[k] - pi[k] + 1 > max_bp_span) continue;  // rna_data.cc:1078, bp_span = j-i+1 (aux.hh:333)
         uniq[std::make_pair(pi[k], pj[k])] = pp[k];
+        if (pp2 != nullptr && pp2[k] > 0) joint[std::make_pair(pi[k], pj[k])] = pp2[k];
     }
     if (max_bps_length_ratio > 0.0) {
         // rna_data.cc:64-67, :1580-1601 (drop_worst_bps): only the `keep` most probable base pairs survive. The reference pops a
@@ -142,7 +152,11 @@ bool make_sequence(const std::string &name, const std::string &seq, const int *p
             for (auto it = uniq.begin(); it != uniq.end();) { if (it->second < thr) it = uniq.erase(it); else ++it; }
         }
     }
-    for (auto &kv : uniq) { out.pp_i.push_back(kv.first.first); out.pp_j.push_back(kv.first.second); out.pp_p.push_back(kv.second); }
+    for (auto &kv : uniq) {
+        out.pp_i.push_back(kv.first.first); out.pp_j.push_back(kv.first.second); out.pp_p.push_back(kv.second);
+        auto it = joint.find(kv.first);
+        out.pp_p2.push_back(it == joint.end() ? 0.0 : it->second);
+    }
     return true;
 }
 
@@ -157,14 +171,19 @@ void finish_sequence(Sequence &s, double min_prob) {
         if (s.pp_i[x] != s.pp_i[y]) return s.pp_i[x] > s.pp_i[y];
         return s.pp_j[x] < s.pp_j[y];
     });
-    s.arcs.clear(); s.arc_prob.clear();
+    s.arcs.clear(); s.arc_prob.clear(); s.arc_joint.clear(); s.arc_inner.clear();
     s.lptr.assign(n + 2, 0); s.lcount.assign(n + 2, 0);
+    std::map<std::pair<int, int>, double> prob;   // RnaData::arc_prob of every pair the reader kept
+    for (size_t k = 0; k < s.pp_i.size(); k++) prob[std::make_pair(s.pp_i[k], s.pp_j[k])] = s.pp_p[k];
     for (int k : order) {
         int l = s.pp_i[k];
         if (s.lcount[l] == 0) s.lptr[l] = (int)s.arcs.size();
         s.lcount[l]++;
         s.arcs.push_back(Arc{s.pp_i[k], s.pp_j[k]});
         s.arc_prob.push_back(s.pp_p[k]);
+        s.arc_joint.push_back(k < (int)s.pp_p2.size() ? s.pp_p2[k] : 0.0);
+        auto it = prob.find(std::make_pair(s.pp_i[k] + 1, s.pp_j[k] - 1));
+        s.arc_inner.push_back(it == prob.end() ? 0.0 : it->second);
     }
     // pp_* is sorted by (i, j) ascending (std::map order)
     s.p_up.assign(n + 1, 0.0); s.p_down.assign(n + 1, 0.0);
@@ -188,6 +207,25 @@ std::vector<int> arc_weights(const Sequence &s, const Params &p) {
     return w;
 }
 
+// scoring.cc:201-248 (stack_weights) relative to the weight, scoring.cc:556-564 (is_stackable_arc: joint probability > 0)
+std::vector<int> arc_stack_deltas(const Sequence &s, const Params &p) {
+    std::vector<int> d(s.arcs.size(), LB_NOSTACK);
+    const double pe = p.exp_prob >= 0 ? p.exp_prob : 1.0 / (2.0 * s.len);
+    auto weight = [&](double prob) { return round2score(round(p.struct_weight * (1 - log(prob) / log(pe)))); };
+    for (size_t k = 0; k < d.size(); k++) {
+        if (!(s.arc_joint[k] > 0)) continue;   // not stackable: the stacked score is never used
+        const long w = weight(s.arc_prob[k]);
+        long sw = 0;
+        if (p.stacking && s.arc_inner[k] > 0) sw = weight(s.arc_joint[k] / s.arc_inner[k]);   // RnaData::stacked_arc_prob (rna_data.cc:705-710)
+        if (p.new_stacking) {
+            if (!p.stacking) sw = w;
+            if (s.arc_inner[k] > 0) sw += weight(s.arc_joint[k]);
+        }
+        d[k] = (int)(sw - w);
+    }
+    return d;
+}
+
 // scoring.cc:141-198 (sigma_ for single sequences), :64-74 (unpaired penalty), :369-485 (arc match sequence term)
 void make_score_tables(const Params &p, ScoreTables &t) {
     memset(&t, 0, sizeof t);
@@ -207,6 +245,7 @@ void make_score_tables(const Params &p, ScoreTables &t) {
     d.gap_open = d.gap + d.open;
     d.exclusion = p.exclusion;
     d.no_lonely_pairs = p.no_lonely_pairs; d.struct_local = p.struct_local; d.sequ_local = p.sequ_local;
+    d.stacking = p.stacking || p.new_stacking;
     d.fe_left1 = p.fe_left1; d.fe_right1 = p.fe_right1; d.fe_left2 = p.fe_left2; d.fe_right2 = p.fe_right2;
 }
 
@@ -394,7 +433,7 @@ void build_pair_problem(const Sequence &A, const Sequence &B, const Band &band, 
                     x.ends_a = (uint32_t)al | ((uint32_t)ar << 12);
                     x.ends_b = (uint32_t)bl | ((uint32_t)br << 12);
                     x.score = arcmatch_score(t, p, A, B, a, b, wA, wB);
-                    x.spos = -1; x.inner = -1;
+                    x.spos = -1; x.inner = -1; x.score_st = LB_NOSTACK;   // host-only inspection: no stacked scores
                     out.am.push_back(x); out.am_a.push_back(a); out.am_b.push_back(b);
                 }
             }

@@ -23,6 +23,7 @@ struct Params {  // mirrors the `locarna` CLI options that reach the path (locar
     double max_bps_length_ratio = 0.0;  // --max-bps-length-ratio (locarna.cc:185, rna_data.cc:64-67); 0: keep all base pairs
     int max_bp_span = -1;    // --maxBPspan (locarna.cc:253, rna_data.cc:1078); -1: unrestricted
     bool pf_double = false;  // envelope in double (locarna_p default) instead of long double (locarna)
+    bool stacking = false, new_stacking = false;  // --stacking / --new-stacking (locarna.cc:120-123, scoring.cc:201-248)
 };
 
 struct Arc { int left, right; };
@@ -35,10 +36,13 @@ struct Sequence {
     // all pairs kept by the PP reader (p > cutoff), for the envelope's paired-up/down sums
     std::vector<int> pp_i, pp_j;
     std::vector<double> pp_p;
+    std::vector<double> pp_p2;         // joint probability of (i, j) and (i+1, j-1) (PP fourth column, rna_data.cc:1085-1093); 0: none
     double cutoff = 0;
     // arcs with p >= min_prob in the reference's index order (left descending, right ascending)
     std::vector<Arc> arcs;
     std::vector<double> arc_prob;
+    std::vector<double> arc_joint;     // RnaData::joint_arc_prob of the arc
+    std::vector<double> arc_inner;     // RnaData::arc_prob(left + 1, right - 1)
     std::vector<int> lptr;             // arcs with left end l are arcs[lptr[l] .. lptr[l]+lcount[l])
     std::vector<int> lcount;
     std::vector<double> p_up, p_down;  // rna_data.cc:713-732
@@ -55,13 +59,16 @@ struct ScoreTables {
 };
 
 // PP 2.0 reader
-bool read_pp(const std::string &path, double p_bpcut, Sequence &out, std::string &err, int max_bp_span = -1, double max_bps_length_ratio = 0.0);
+bool read_pp(const std::string &path, double p_bpcut, Sequence &out, std::string &err, int max_bp_span = -1, double max_bps_length_ratio = 0.0,
+             bool stacking = false);
 // sequence + explicit pair list (i, j, p): same filtering as the PP reader with #BPCUT = cutoff
 bool make_sequence(const std::string &name, const std::string &seq, const int *pi, const int *pj, const double *pp, int npairs,
-                   double p_bpcut, Sequence &out, std::string &err, int max_bp_span = -1, double max_bps_length_ratio = 0.0);
+                   double p_bpcut, Sequence &out, std::string &err, int max_bp_span = -1, double max_bps_length_ratio = 0.0, const double *pp2 = nullptr);
 void finish_sequence(Sequence &s, double min_prob);
 
 std::vector<int> arc_weights(const Sequence &s, const Params &p);
+// per arc: stack weight minus weight (scoring.cc:201-248), LB_NOSTACK for arcs that are not stackable (scoring.cc:556-564)
+std::vector<int> arc_stack_deltas(const Sequence &s, const Params &p);
 void make_score_tables(const Params &p, ScoreTables &t);
 int base_match_score(const ScoreTables &t, uint8_t a, uint8_t b);
 int arcmatch_score(const ScoreTables &t, const Params &p, const Sequence &A, const Sequence &B, int a, int b, const std::vector<int> &wA,

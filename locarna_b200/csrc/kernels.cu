@@ -689,9 +689,10 @@ __device__ __forceinline__ void dfill_task(const DevCtx &c, const DevTask &task,
     const DevArcMatch *am = c.am + pr.am_base;
     DevEntry *ent = c.ent + pr.am_base;
     const int sh = nolp ? 2 : 1;
+    const bool stacking = c.params.stacking != 0;
     for (int k = task.run_start + lane; k < task.run_start + task.run_count; k += 32) {
         const DevArcMatch x = am[k];
-        if (nolp && x.inner < 0) continue;
+        if (nolp && (x.inner < 0 || (stacking && x.score_st == LB_NOSTACK))) continue;   // aligner.cc:628-629
         const int ar = (x.ends_a >> 12) & 0xfff, br = (x.ends_b >> 12) & 0xfff;
         const int mv = box_get(box, g, ar - sh - g.al, br - sh - g.bl);
         int d;
@@ -699,8 +700,14 @@ __device__ __forceinline__ void dfill_task(const DevCtx &c, const DevTask &task,
             const DevArcMatch in = am[x.inner];
             const int a = (mv < LB_NEG_LIMIT) ? LB_NEG : mv + in.score;
             const int y = max(a, __ldcg(&ent[in.spos].d));
-            d = (y < LB_NEG_LIMIT) ? LB_NEG : y + x.score;
-        } else d = (mv < LB_NEG_LIMIT) ? LB_NEG : mv + x.score;
+            d = (y < LB_NEG_LIMIT) ? LB_NEG : y + (stacking ? x.score_st : x.score);
+        } else {
+            d = (mv < LB_NEG_LIMIT) ? LB_NEG : mv + x.score;
+            if (stacking && x.inner >= 0 && x.score_st != LB_NOSTACK) {   // aligner.cc:600-607
+                const int di = __ldcg(&ent[am[x.inner].spos].d);
+                if (di >= LB_NEG_LIMIT) d = max(d, di + x.score_st);
+            }
+        }
         ent[x.spos].d = d;
         if (c.ent8 != nullptr) c.ent8[pr.am_base + x.spos].y = LB_PACK_W1(br, d);
     }
@@ -804,9 +811,10 @@ __global__ void __launch_bounds__(32) dfill_sl_kernel(DevCtx c, int q) {
         const DevArcMatch *am = c.am + pr.am_base;
         DevEntry *ent = c.ent + pr.am_base;
         const int sh = nolp ? 2 : 1;
+        const bool stacking = c.params.stacking != 0;
         for (int k = task.run_start + lane; k < task.run_start + task.run_count; k += 32) {
             const DevArcMatch x = am[k];
-            if (nolp && x.inner < 0) continue;
+            if (nolp && (x.inner < 0 || (stacking && x.score_st == LB_NOSTACK))) continue;
             const int ar = (x.ends_a >> 12) & 0xfff, br = (x.ends_b >> 12) & 0xfff;
             int mv = LB_NEG;
 #pragma unroll
@@ -816,8 +824,14 @@ __global__ void __launch_bounds__(32) dfill_sl_kernel(DevCtx c, int q) {
                 const DevArcMatch in = am[x.inner];
                 const int a = (mv < LB_NEG_LIMIT) ? LB_NEG : mv + in.score;
                 const int y = max(a, ent[in.spos].d);
-                d = (y < LB_NEG_LIMIT) ? LB_NEG : y + x.score;
-            } else d = (mv < LB_NEG_LIMIT) ? LB_NEG : mv + x.score;
+                d = (y < LB_NEG_LIMIT) ? LB_NEG : y + (stacking ? x.score_st : x.score);
+            } else {
+                d = (mv < LB_NEG_LIMIT) ? LB_NEG : mv + x.score;
+                if (stacking && x.inner >= 0 && x.score_st != LB_NOSTACK) {
+                    const int di = ent[am[x.inner].spos].d;
+                    if (di >= LB_NEG_LIMIT) d = max(d, di + x.score_st);
+                }
+            }
             ent[x.spos].d = d;
         }
         __syncwarp();
@@ -1035,7 +1049,19 @@ __global__ void __launch_bounds__(32) trace_kernel(DevCtx c, int pair_begin, int
                 emit(xl, yl, LB_EDGE_MATCH);
                 emit(i, j, LB_EDGE_MATCH);
                 if (!nolp) {                                                                 // trace_arcmatch :967-1028
-                    if (lane == 0) { TraceJob nj; nj.al = (short)xl; nj.bl = (short)yl; nj.R = (short)(i - 1); nj.C = (short)(j - 1); nj.am = -1; stack[sp] = nj; }
+                    int cur = (int)lpos[found];
+                    DevArcMatch x = am[cur];
+                    // stacked arc matches (:984-1003): while D is explained by the inner arc match, descend without opening a box
+                    while (P.stacking && x.inner >= 0 && x.score_st != LB_NOSTACK && ent[x.spos].d == ent[am[x.inner].spos].d + x.score_st &&
+                           ent[am[x.inner].spos].d >= LB_NEG_LIMIT) {
+                        cur = x.inner; x = am[cur];
+                        const int ial = x.ends_a & 0xfff, iar = x.ends_a >> 12, ibl = x.ends_b & 0xfff, ibr = x.ends_b >> 12;
+                        if (lane == 0) { strA[ial] = '('; strA[iar] = ')'; strB[ibl] = '('; strB[ibr] = ')'; }
+                        emit(ial, ibl, LB_EDGE_MATCH);
+                        emit(iar, ibr, LB_EDGE_MATCH);
+                    }
+                    const int bal = x.ends_a & 0xfff, bar = x.ends_a >> 12, bbl = x.ends_b & 0xfff, bbr = x.ends_b >> 12;
+                    if (lane == 0) { TraceJob nj; nj.al = (short)bal; nj.bl = (short)bbl; nj.R = (short)(bar - 1); nj.C = (short)(bbr - 1); nj.am = -1; stack[sp] = nj; }
                     sp++;
                 } else {                                                                     // trace_arcmatch_noLP :1030-1079
                     int cur = (int)lpos[found];
@@ -1046,7 +1072,7 @@ __global__ void __launch_bounds__(32) trace_kernel(DevCtx c, int pair_begin, int
                         if (lane == 0) { strA[ial] = '('; strA[iar] = ')'; strB[ibl] = '('; strB[ibr] = ')'; }
                         emit(ial, ibl, LB_EDGE_MATCH);
                         emit(iar, ibr, LB_EDGE_MATCH);
-                        if (ent[x.spos].d == ent[in.spos].d + x.score) { cur = x.inner; continue; }
+                        if (ent[x.spos].d == ent[in.spos].d + (P.stacking ? x.score_st : x.score)) { cur = x.inner; continue; }
                         if (lane == 0) { TraceJob nj; nj.al = (short)ial; nj.bl = (short)ibl; nj.R = (short)(iar - 1); nj.C = (short)(ibr - 1); nj.am = -1; stack[sp] = nj; }
                         sp++;
                         break;
@@ -1125,7 +1151,7 @@ __global__ void __launch_bounds__(32) trace_sl_kernel(DevCtx c, int pair_begin, 
             if (!tl) {
                 // state in which the arc match closes: first closed state that explains D (aligner.cc:1019-1025, :1065-1075)
                 const DevArcMatch x = am[job.am];
-                const int add = nolp ? x.score + am[x.inner].score : x.score;
+                const int add = nolp ? (P.stacking ? x.score_st : x.score) + am[x.inner].score : x.score;
                 st = -1;
                 for (int k = 0; k < 4; k++) if (ent[x.spos].d == B(k, i, j) + add) { st = k; break; }
                 if (st < 0) { tl = false; have = sp > 0; if (have) { sp--; job = stack[sp]; } continue; }
@@ -1211,7 +1237,17 @@ __global__ void __launch_bounds__(32) trace_sl_kernel(DevCtx c, int pair_begin, 
                 emit(i, j, LB_EDGE_MATCH);
                 int cur = (int)lpos[found];
                 if (!nolp) {
-                    if (lane == 0) { TraceJob nj; nj.al = (short)xl; nj.bl = (short)yl; nj.R = (short)(i - 1); nj.C = (short)(j - 1); nj.am = cur; stack[sp] = nj; }
+                    DevArcMatch x = am[cur];
+                    while (P.stacking && x.inner >= 0 && x.score_st != LB_NOSTACK && ent[x.spos].d == ent[am[x.inner].spos].d + x.score_st &&
+                           ent[am[x.inner].spos].d >= LB_NEG_LIMIT) {
+                        cur = x.inner; x = am[cur];
+                        const int ial = x.ends_a & 0xfff, iar = x.ends_a >> 12, ibl = x.ends_b & 0xfff, ibr = x.ends_b >> 12;
+                        if (lane == 0) { strA[ial] = '('; strA[iar] = ')'; strB[ibl] = '('; strB[ibr] = ')'; }
+                        emit(ial, ibl, LB_EDGE_MATCH);
+                        emit(iar, ibr, LB_EDGE_MATCH);
+                    }
+                    const int bal = x.ends_a & 0xfff, bar = x.ends_a >> 12, bbl = x.ends_b & 0xfff, bbr = x.ends_b >> 12;
+                    if (lane == 0) { TraceJob nj; nj.al = (short)bal; nj.bl = (short)bbl; nj.R = (short)(bar - 1); nj.C = (short)(bbr - 1); nj.am = cur; stack[sp] = nj; }
                     sp++;
                 } else {
                     for (;;) {
@@ -1221,7 +1257,7 @@ __global__ void __launch_bounds__(32) trace_sl_kernel(DevCtx c, int pair_begin, 
                         if (lane == 0) { strA[ial] = '('; strA[iar] = ')'; strB[ibl] = '('; strB[ibr] = ')'; }
                         emit(ial, ibl, LB_EDGE_MATCH);
                         emit(iar, ibr, LB_EDGE_MATCH);
-                        if (ent[x.spos].d == ent[in.spos].d + x.score) { cur = x.inner; continue; }
+                        if (ent[x.spos].d == ent[in.spos].d + (P.stacking ? x.score_st : x.score)) { cur = x.inner; continue; }
                         if (lane == 0) { TraceJob nj; nj.al = (short)ial; nj.bl = (short)ibl; nj.R = (short)(iar - 1); nj.C = (short)(ibr - 1); nj.am = cur; stack[sp] = nj; }
                         sp++;
                         break;

@@ -183,7 +183,7 @@ struct lb200_ctx {
     int host_threads = 0;
     size_t seqs_uploaded = 0;  // sequences whose arrays are on the device
     std::vector<int> seq_codes_off, seq_arcs_off, seq_lptr_off;
-    DevBuf d_arc_left, d_arc_right, d_arc_weight, d_lptr, d_lcount, d_am_seq, d_cell_rev, d_cell_start, d_skeys, d_skeys2, d_svals, d_svals2,
+    DevBuf d_arc_left, d_arc_right, d_arc_weight, d_arc_sdelta, d_lptr, d_lcount, d_am_seq, d_cell_rev, d_cell_start, d_skeys, d_skeys2, d_svals, d_svals2,
         d_tasks_unsorted, d_tkeys, d_tkeys2, d_tvals, d_tvals2, d_ntasks, d_qstart, d_stats, d_tmp, d_tr_edges, d_tr_str, d_tr_stack,
         d_pup, d_pdown, d_env_pairs, d_env_lo, d_env_hi, d_env_olo, d_env_ohi, d_env_flag, d_env_scratch;
     std::vector<int> seq_prob_off;
@@ -202,7 +202,7 @@ struct lb200_ctx {
     ~lb200_ctx() {
         DevBuf *all[] = {&d_pairs, &d_codes, &d_band_lo, &d_band_hi, &d_sptr, &d_ent, &d_am, &d_tasks, &d_top, &d_scratch, &d_cursor, &d_flag, &d_levcnt, &d_done, &d_ent8,
                          &d_col_first, &d_col_last, &d_groups, &d_gorder, &d_ngroups, &d_rows_scratch, &d_row_built, &d_clist, &d_cnblk,
-                         &d_arc_left, &d_arc_right, &d_arc_weight, &d_lptr, &d_lcount, &d_am_seq, &d_cell_rev, &d_cell_start, &d_skeys, &d_skeys2,
+                         &d_arc_left, &d_arc_right, &d_arc_weight, &d_arc_sdelta, &d_lptr, &d_lcount, &d_am_seq, &d_cell_rev, &d_cell_start, &d_skeys, &d_skeys2,
                          &d_svals, &d_svals2, &d_tasks_unsorted, &d_tkeys, &d_tkeys2, &d_tvals, &d_tvals2, &d_ntasks, &d_qstart, &d_stats, &d_tmp, &d_tr_edges, &d_tr_str, &d_tr_stack,
                          &d_pf_esig, &d_pf_bpow, &d_pf_d, &d_pf_z, &d_pf_scratch, &d_pf_dp, &d_pf_amp, &d_pf_mats, &d_pf_cta,
                          &d_pup, &d_pdown, &d_env_pairs, &d_env_lo, &d_env_hi, &d_env_olo, &d_env_ohi, &d_env_flag, &d_env_scratch};
@@ -243,6 +243,7 @@ static Params to_params(const lb200_params &p) {
     q.match = p.match; q.mismatch = p.mismatch; q.unpaired_penalty = p.unpaired_penalty; q.temperature_alipf = p.temperature_alipf;
     q.use_ribosum = p.use_ribosum != 0; q.pf_double = p.pf_double != 0;
     q.exp_prob = p.exp_prob; q.max_bp_span = p.max_bp_span; q.max_bps_length_ratio = p.max_bps_length_ratio;
+    q.stacking = p.stacking != 0; q.new_stacking = p.new_stacking != 0;
     return q;
 }
 
@@ -320,7 +321,7 @@ int lb200_seq_add_pp(lb200_ctx *c, const char *path) {
     if (!c || !path) return LB200_ERR_ARG;
     Sequence s;
     std::string err;
-    if (!read_pp(path, c->params.min_prob, s, err, c->params.max_bp_span, c->params.max_bps_length_ratio)) return fail(c, LB200_ERR_IO, "%s", err.c_str());
+    if (!read_pp(path, c->params.min_prob, s, err, c->params.max_bp_span, c->params.max_bps_length_ratio, c->params.stacking || c->params.new_stacking)) return fail(c, LB200_ERR_IO, "%s", err.c_str());
     finish_sequence(s, c->params.min_prob);
     c->seqs.push_back(std::move(s));
     return (int)c->seqs.size() - 1;
@@ -336,7 +337,7 @@ int lb200_seqs_add_pp(lb200_ctx *c, int n, const char *const *paths) {
     std::vector<std::string> errs((size_t)n);
     std::vector<char> ok((size_t)n, 0);
     parallel_for(n, c->host_threads, [&](int k) {
-        if (!read_pp(paths[k], c->params.min_prob, seqs[k], errs[k], c->params.max_bp_span, c->params.max_bps_length_ratio)) return;
+        if (!read_pp(paths[k], c->params.min_prob, seqs[k], errs[k], c->params.max_bp_span, c->params.max_bps_length_ratio, c->params.stacking || c->params.new_stacking)) return;
         finish_sequence(seqs[k], c->params.min_prob);
         ok[k] = 1;
     });
@@ -447,7 +448,7 @@ extern "C" {
 static int upload_sequences(lb200_ctx *c) {
     if (c->seqs_uploaded == c->seqs.size()) return LB200_OK;
     std::vector<uint8_t> codes;
-    std::vector<int> al, ar, aw, lptr, lcount;
+    std::vector<int> al, ar, aw, asd, lptr, lcount;
     std::vector<double> pup, pdown;
     c->seq_codes_off.clear(); c->seq_arcs_off.clear(); c->seq_lptr_off.clear(); c->seq_prob_off.clear();
     for (const Sequence &s : c->seqs) {
@@ -455,7 +456,8 @@ static int upload_sequences(lb200_ctx *c) {
         codes.insert(codes.end(), s.codes.begin(), s.codes.end());
         c->seq_arcs_off.push_back((int)al.size());
         const std::vector<int> w = arc_weights(s, c->params);
-        for (size_t k = 0; k < s.arcs.size(); k++) { al.push_back(s.arcs[k].left); ar.push_back(s.arcs[k].right); aw.push_back(w[k]); }
+        const std::vector<int> sd = (c->params.stacking || c->params.new_stacking) ? arc_stack_deltas(s, c->params) : std::vector<int>(s.arcs.size(), LB_NOSTACK);
+        for (size_t k = 0; k < s.arcs.size(); k++) { al.push_back(s.arcs[k].left); ar.push_back(s.arcs[k].right); aw.push_back(w[k]); asd.push_back(sd[k]); }
         c->seq_lptr_off.push_back((int)lptr.size());
         lptr.insert(lptr.end(), s.lptr.begin(), s.lptr.end());
         lcount.insert(lcount.end(), s.lcount.begin(), s.lcount.end());
@@ -469,6 +471,7 @@ static int upload_sequences(lb200_ctx *c) {
     CUDA_TRY(c, upload(c->d_arc_left, al, st));
     CUDA_TRY(c, upload(c->d_arc_right, ar, st));
     CUDA_TRY(c, upload(c->d_arc_weight, aw, st));
+    CUDA_TRY(c, upload(c->d_arc_sdelta, asd, st));
     CUDA_TRY(c, upload(c->d_lptr, lptr, st));
     CUDA_TRY(c, upload(c->d_lcount, lcount, st));
     CUDA_TRY(c, upload(c->d_am_seq, amseq, st));
@@ -697,7 +700,7 @@ static int upload_chunk(lb200_ctx *c, int p0, int p1) {
     memset(&b, 0, sizeof b);
     b.pairs = (DevPair *)c->d_pairs.p; b.codes = (const uint8_t *)c->d_codes.p;
     b.band_lo = (const int *)c->d_band_lo.p; b.band_hi = (const int *)c->d_band_hi.p; b.cell_rev = (const int *)c->d_cell_rev.p;
-    b.arc_left = (const int *)c->d_arc_left.p; b.arc_right = (const int *)c->d_arc_right.p; b.arc_weight = (const int *)c->d_arc_weight.p;
+    b.arc_left = (const int *)c->d_arc_left.p; b.arc_right = (const int *)c->d_arc_right.p; b.arc_weight = (const int *)c->d_arc_weight.p; b.arc_sdelta = (const int *)c->d_arc_sdelta.p;
     b.lptr = (const int *)c->d_lptr.p; b.lcount = (const int *)c->d_lcount.p; b.am_seq = (const int *)c->d_am_seq.p;
     memcpy(b.sigma8, c->tables.dev.sigma8, sizeof b.sigma8);
     b.tau = c->params.tau; b.use_ribosum = c->params.use_ribosum; b.no_lonely_pairs = c->params.no_lonely_pairs; b.struct_local = c->params.struct_local;

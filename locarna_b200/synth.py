@@ -114,18 +114,28 @@ def dotplot(seq: str, seed: int = 0, density: float = 2.2, cutoff: float = 0.000
     return res
 
 
-def write_pp(path: str, name: str, seq: str, pairs, cutoff: float = 0.0005) -> None:
+def write_pp(path: str, name: str, seq: str, pairs, cutoff: float = 0.0005, stacking: bool = False) -> None:
+    """PP 2.0 file. With ``stacking`` the base pair lines carry the joint probability of (i, j) and (i+1, j-1) as a fourth column
+    (rna_data.cc:1058-1095, keyword #STACK): here 0.85 x the smaller of the two pair probabilities where the inner pair is listed."""
+    prob = {(i, j): p for (i, j, p) in pairs}
     with open(path, "w") as f:
         f.write("#PP 2.0\n\n")
         f.write("%s %s\n" % (name, seq))
-        f.write("\n#END\n\n#SECTION BASEPAIRS\n\n#BPCUT %g\n\n" % cutoff)
+        f.write("\n#END\n\n#SECTION BASEPAIRS\n\n#BPCUT %g\n" % cutoff)
+        if stacking:
+            f.write("#STACK\n")
+        f.write("\n")
         for (i, j, p) in pairs:
-            f.write("%d %d %.6g\n" % (i, j, p))
+            q = prob.get((i + 1, j - 1))
+            if stacking and q is not None and 0.85 * min(p, q) > cutoff:
+                f.write("%d %d %.6g %.6g\n" % (i, j, p, 0.85 * min(p, q)))
+            else:
+                f.write("%d %d %.6g\n" % (i, j, p))
         f.write("\n#END\n")
 
 
-def make_pp(path: str, name: str, seq: str, seed: int = 0, density: float = 2.2) -> None:
-    write_pp(path, name, seq, dotplot(seq, seed=seed, density=density))
+def make_pp(path: str, name: str, seq: str, seed: int = 0, density: float = 2.2, stacking: bool = False) -> None:
+    write_pp(path, name, seq, dotplot(seq, seed=seed, density=density), stacking=stacking)
 
 
 def _make_one(job):

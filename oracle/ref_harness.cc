@@ -65,6 +65,8 @@ struct Opts {
     int struct_weight = 200, indel = -150, indel_opening = -750, tau = 50, exclusion = 0;
     int match = 50, mismatch = 0, temperature_alipf = 300, unpaired_penalty = 0;
     bool do_trace = true, timing = false, pf_double = false;
+    bool stacking = false, new_stacking = false;   // locarna --stacking / --new-stacking (locarna.cc:120-123)
+    double exp_prob = -1.0;                        // --exp-prob; < 0: prob_exp_f(len) per sequence (locarna.cc:662-663)
     bool pf = false, pf_probs = false;  // LocARNA-P: inside partition function (+ D), outside + probabilities
     double pf_scale = 1.0, min_am_prob = 0.001, min_bm_prob = 0.001;
     std::string dump;  // comma list: arcs,band,am,D,aln,tables
@@ -111,7 +113,7 @@ static std::shared_ptr<RnaData> load(const Opts &o, const std::string &f, const 
 }
 
 static int run_pair(const Opts &o, const std::string &fA, const std::string &fB, const RibosumFreq *ribosum, long idx) {
-    PFoldParams pfoldparams(PFoldParams::args::noLP(o.noLP), PFoldParams::args::stacking(false),
+    PFoldParams pfoldparams(PFoldParams::args::noLP(o.noLP), PFoldParams::args::stacking(o.stacking || o.new_stacking),
                             PFoldParams::args::max_bp_span(-1));
     double t0 = now_ms();
     std::shared_ptr<RnaData> rA, rB;
@@ -139,9 +141,10 @@ static int run_pair(const Opts &o, const std::string &fA, const std::string &fB,
                             ScoringParams::ribosum(ribosum), ScoringParams::ribofit(nullptr),
                             ScoringParams::unpaired_penalty(o.unpaired_penalty),
                             ScoringParams::struct_weight(o.struct_weight), ScoringParams::tau_factor(o.tau),
-                            ScoringParams::exclusion(o.exclusion), ScoringParams::exp_probA(prob_exp_f(lenA)),
-                            ScoringParams::exp_probB(prob_exp_f(lenB)),
-                            ScoringParams::temperature_alipf(o.temperature_alipf));
+                            ScoringParams::exclusion(o.exclusion), ScoringParams::exp_probA(o.exp_prob >= 0 ? o.exp_prob : prob_exp_f(lenA)),
+                            ScoringParams::exp_probB(o.exp_prob >= 0 ? o.exp_prob : prob_exp_f(lenB)),
+                            ScoringParams::temperature_alipf(o.temperature_alipf), ScoringParams::stacking(o.stacking),
+                            ScoringParams::new_stacking(o.new_stacking));
     ScoringPeek scoring(seqA, seqB, *rA, *rB, am, nullptr, sp);
     double t4 = now_ms();
 
@@ -149,7 +152,7 @@ static int run_pair(const Opts &o, const std::string &fA, const std::string &fB,
                      AlignerParams::no_lonely_pairs(o.noLP), AlignerParams::struct_local(o.struct_local),
                      AlignerParams::sequ_local(o.sequ_local), AlignerParams::free_endgaps(FreeEndgaps(o.free_endgaps)),
                      AlignerParams::max_diff_am(o.max_diff_am), AlignerParams::max_diff_at_am(o.max_diff_at_am),
-                     AlignerParams::trace_controller(&tc), AlignerParams::stacking(false),
+                     AlignerParams::trace_controller(&tc), AlignerParams::stacking(o.stacking || o.new_stacking),
                      AlignerParams::constraints(&constraints));
     Aligner aligner(ap);
     // Aligner's only data member is its (private) pimpl pointer (aligner.hh:68); the harness reads D
@@ -297,6 +300,9 @@ int main(int argc, char **argv) {
         else if (a == "--unpaired-penalty") o.unpaired_penalty = atoi(nxt());
         else if (a == "--temperature-alipf") o.temperature_alipf = atoi(nxt());
         else if (a == "--no-ribosum") o.use_ribosum = false;
+        else if (a == "--stacking") o.stacking = true;
+        else if (a == "--new-stacking") o.new_stacking = true;
+        else if (a == "--exp-prob") o.exp_prob = atof(nxt());
         else if (a == "--pf-double") o.pf_double = true;
         else if (a == "--no-trace") o.do_trace = false;
         else if (a == "--pf") o.pf = true;

@@ -44,7 +44,7 @@ def test_cli_exp_prob_maxbpspan_arcmatch_scores(case, tmp_path):
 
 
 def test_cli_rejects_unimplemented_modes():
-    r = subprocess.run([CLI, os.path.join(GOLD, "g0.pp"), os.path.join(GOLD, "g1.pp"), "--stacking"], capture_output=True, text=True)
+    r = subprocess.run([CLI, os.path.join(GOLD, "g0.pp"), os.path.join(GOLD, "g1.pp"), "--normalized", "100"], capture_output=True, text=True)
     assert r.returncode == 255 and "does not implement" in r.stderr
 
 
