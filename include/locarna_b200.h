@@ -134,6 +134,12 @@ int lb200_prepare(lb200_ctx *ctx);
 int lb200_upload(lb200_ctx *ctx);
 /* Align all pairs added so far on the GPU. */
 int lb200_run(lb200_ctx *ctx, int flags);
+/* Normalized local alignment (Aligner::normalized_align(L), src/LocARNA/aligner.cc:1522-1597; `locarna --normalized L`, needs sequ_local) and
+ * penalized alignment (Aligner::penalized_align(position_penalty), aligner.cc:1599-1622; `locarna --penalized PP`) of all pairs, with
+ * traceback. Afterwards lb200_pair_score gives the normalized score (the final lambda) resp. the penalized score, lb200_pair_alignment
+ * the alignment. Not available with struct_local. */
+int lb200_run_normalized(lb200_ctx *ctx, int64_t L);
+int lb200_run_penalized(lb200_ctx *ctx, int64_t position_penalty);
 /* device time of the last lb200_run's kernels (CUDA events on the launching stream), milliseconds */
 double lb200_last_kernel_ms(const lb200_ctx *ctx);
 /* host->device bytes of the last lb200_upload (0 if lb200_run found the batch resident) and device->host bytes of the last lb200_run */

@@ -296,6 +296,16 @@ public:
         ctx_->check(lb200_pair_score(ctx_->get(), pair_, &sc));
         return sc == LB200_SCORE_NEG_INF ? infty_score_t::neg_infty_value() : infty_score_t((long)sc);
     }
+    //! normalized local alignment by Dinkelbach's algorithm (aligner.cc:1522-1597); returns the normalized score, the alignment is traced
+    infty_score_t normalized_align(long L, bool /*verbose*/ = false) {
+        ctx_->check(lb200_run_normalized(ctx_->get(), (int64_t)L));
+        return modified_result();
+    }
+    //! alignment with every aligned position penalized (aligner.cc:1599-1622); returns the penalized score, the alignment is traced
+    infty_score_t penalized_align(long position_penalty) {
+        ctx_->check(lb200_run_penalized(ctx_->get(), (int64_t)position_penalty));
+        return modified_result();
+    }
     //! trace back (aligner.cc:1345-1363); the device already traced during align()
     void trace() {
         if (!traced_) align();
@@ -309,6 +319,15 @@ public:
         alignment_.strA_ = sa.substr(0, inf.lenA); alignment_.strB_ = sb.substr(0, inf.lenB);
     }
     const Alignment &get_alignment() const { return alignment_; }
+private:
+    infty_score_t modified_result() {
+        traced_ = true;
+        trace();
+        int64_t sc = 0;
+        ctx_->check(lb200_pair_score(ctx_->get(), pair_, &sc));
+        return sc == LB200_SCORE_NEG_INF ? infty_score_t::neg_infty_value() : infty_score_t((long)sc);
+    }
+public:
     //! arc matches and their scores as built on the device (no alignment is computed: lb200_upload only)
     const ArcMatches &arc_matches() {
         if (!have_ams_) {

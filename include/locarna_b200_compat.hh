@@ -26,7 +26,7 @@
 //
 // The objects of the reference compute on construction (RnaData parses, ArcMatches enumerates, Scoring precomputes). Here they record
 // their arguments; the device builds bands, arc matches and scores when Aligner runs. What the B200 path does not implement
-// (reference alignments for --max-diff-aln, anchors, MEA, explicit arc-match scores, k-best, normalized / penalized) throws LocARNA::failure from the object
+// (reference alignments for --max-diff-aln, anchors, MEA, explicit arc-match scores, k-best) throws LocARNA::failure from the object
 // that would need it, so the caller's existing error handling applies.
 #ifndef LOCARNA_B200_COMPAT_HH
 #define LOCARNA_B200_COMPAT_HH
@@ -323,8 +323,8 @@ public:
     infty_score_t align() { return impl_->align(); }
     void trace() { impl_->trace(); }
     const Alignment &get_alignment() const { return impl_->get_alignment(); }
-    infty_score_t normalized_align(score_t, bool) { throw failure("locarna_b200: normalized alignment is not supported"); }
-    infty_score_t penalized_align(score_t) { throw failure("locarna_b200: penalized alignment is not supported"); }
+    infty_score_t normalized_align(score_t L, bool verbose) { return impl_->normalized_align(L, verbose); }
+    infty_score_t penalized_align(score_t position_penalty) { return impl_->penalized_align(position_penalty); }
     void suboptimal(int, score_t, bool, score_t, size_t, bool, bool, bool, bool) { throw failure("locarna_b200: k-best alignment is not supported"); }
 };
 

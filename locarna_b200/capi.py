@@ -42,7 +42,7 @@ EXPORTS = [
     "lb200_prepare", "lb200_upload", "lb200_run", "lb200_last_kernel_ms", "lb200_last_h2d_bytes", "lb200_last_d2h_bytes", "lb200_last_dfill_ms", "lb200_last_dfill_launches", "lb200_last_launches", "lb200_envelope_stats", "lb200_pair_score", "lb200_get_scores",
     "lb200_pair_get_info", "lb200_pair_band", "lb200_pair_arcmatches", "lb200_pair_alignment", "lb200_upgma_newick",
     "lb200_run_pf", "lb200_pair_partition_function", "lb200_pair_arcmatch_pf", "lb200_run_pf_probs", "lb200_pair_arcmatch_probs",
-    "lb200_pair_basematch_probs", "lb200_pairs_add", "lb200_all_vs_all", "lb200_pair_cost", "lb200_shard_pairs", "lb200_seq_num_arcs", "lb200_seqs_add_pp", "lb200_last_dfill_kind", "lb200_rows_fallbacks", "lb200_release_device_cache",
+    "lb200_pair_basematch_probs", "lb200_pairs_add", "lb200_all_vs_all", "lb200_pair_cost", "lb200_shard_pairs", "lb200_seq_num_arcs", "lb200_seqs_add_pp", "lb200_last_dfill_kind", "lb200_rows_fallbacks", "lb200_release_device_cache", "lb200_run_normalized", "lb200_run_penalized",
 ]
 
 _lib = None
@@ -91,6 +91,8 @@ def load():
     lib.lb200_run.argtypes = [vp, C.c_int]
     lib.lb200_last_kernel_ms.argtypes = [vp]
     lib.lb200_last_kernel_ms.restype = C.c_double
+    lib.lb200_run_normalized.argtypes = [vp, C.c_int64]
+    lib.lb200_run_penalized.argtypes = [vp, C.c_int64]
     lib.lb200_last_dfill_kind.argtypes = [vp]
     lib.lb200_rows_fallbacks.argtypes = [vp]
     lib.lb200_rows_fallbacks.restype = C.c_int64
@@ -230,6 +232,13 @@ class Context:
 
     def run(self, flags: int = RUN_SCORE_ONLY):
         self._chk(self.lib.lb200_run(self.h, flags))
+
+    def run_normalized(self, L: int):
+        """Normalized local alignment (locarna --normalized L); scores() gives the normalized scores, alignment(k) the alignments."""
+        self._chk(self.lib.lb200_run_normalized(self.h, L))
+
+    def run_penalized(self, position_penalty: int):
+        self._chk(self.lib.lb200_run_penalized(self.h, position_penalty))
 
     @property
     def kernel_ms(self) -> float:

@@ -76,6 +76,8 @@ int main(int argc, char **argv) {
     int max_bp_span = -1;
     double max_bps_length_ratio = 0.0;
     bool verbose = false;
+    bool struct_local = false, struct_local_given = false, sequ_local = false, sequ_local_given = false, normalized = false, penalized = false;
+    long normalized_L = 0, position_penalty = 0;
     int c, idx = 0;
     while ((c = getopt_long(argc, argv, "i:m:M:s:e:t:E:w:Lp:D:d:PqvVh", longopts, &idx)) != -1) {
         switch (c) {
@@ -91,8 +93,10 @@ int main(int argc, char **argv) {
             case 's': case O_STRUCT_WEIGHT: sp.struct_weight = atoi(optarg); break;
             case 't': case O_TAU: sp.tau_factor = atoi(optarg); break;
             case 'E': case O_EXCLUSION: sp.exclusion = atoi(optarg); break;
-            case O_STRUCT_LOCAL: ap.struct_local(parse_bool(optarg)); break;
-            case O_SEQU_LOCAL: ap.sequ_local(parse_bool(optarg)); break;
+            case O_STRUCT_LOCAL: struct_local = parse_bool(optarg); struct_local_given = true; break;
+            case O_SEQU_LOCAL: sequ_local = parse_bool(optarg); sequ_local_given = true; break;
+            case O_NORMALIZED: normalized = true; normalized_L = atol(optarg); break;
+            case O_PENALIZED: penalized = true; position_penalty = atol(optarg); break;
             case O_FREE_ENDGAPS: ap.free_endgaps(optarg); break;
             case 'w': case O_WIDTH: width = atoi(optarg); break;
             case O_CLUSTAL: clustal = optarg; break;
@@ -117,7 +121,7 @@ int main(int argc, char **argv) {
             case O_WRITE_ARCMATCH_SCORES: arcmatch_scores_file = optarg; break;
             case O_STACKING: sp.stacking = true; break;
             case O_NEW_STACKING: sp.new_stacking = true; break;
-            case O_NORMALIZED: case O_PENALIZED: case O_PP:
+            case O_PP:
             case O_UNSUPPORTED:
                 std::cerr << "ERROR: option --" << (idx >= 0 && longopts[idx].name ? longopts[idx].name : "?")
                           << " selects a mode that locarna_b200 does not implement." << std::endl;
@@ -131,6 +135,18 @@ int main(int argc, char **argv) {
         }
     }
     if (argc - optind != 2) { std::cerr << "ERROR: expected two input files (PP 2.0)." << std::endl; return 255; }
+    if (normalized && penalized) {   // locarna.cc:369-373
+        std::cerr << "One cannot specify penalized and normalized " << "simultaneously." << std::endl;
+        return 255;
+    }
+    if (penalized && !sequ_local_given) sequ_local = true;   // locarna.cc:417-424
+    if (normalized) {                                        // locarna.cc:426-447
+        if (!sequ_local_given) sequ_local = true;
+        else if (!sequ_local) { std::cerr << "ERROR: Cannot run normalized alignment " << "without --sequ_local on." << std::endl; return 255; }
+        if (struct_local_given && struct_local) { std::cerr << "ERROR: Normalized structure local alignment " << "not supported." << std::endl; return 255; }
+        struct_local = false;
+    }
+    ap.struct_local(struct_local).sequ_local(sequ_local);
     if (sp.stacking && sp.exp_prob < 0) {   // locarna.cc:406-414
         std::cerr << "WARNING: stacking turned off. "
                   << "Stacking requires setting a background probability "
@@ -146,7 +162,8 @@ int main(int argc, char **argv) {
             aligner.arc_matches().write_arcmatch_scores(arcmatch_scores_file);
             return 0;
         }
-        const infty_score_t score = aligner.align();
+        const infty_score_t score = normalized ? aligner.normalized_align(normalized_L, verbose)     // locarna.cc:751-763
+                                    : penalized ? aligner.penalized_align(position_penalty) : aligner.align();
         if (!quiet) std::cout << "Score: " << score << std::endl << std::endl;     // locarna.cc:769-771
         aligner.trace();
         const Alignment &alignment = aligner.get_alignment();

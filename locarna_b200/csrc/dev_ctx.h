@@ -40,6 +40,13 @@ struct DevCtx {
     const int *dep_need;         // [pair * n_groups + level group]: completed tasks of the pair a task of that group waits for
     int *dep_done;               // per pair: completed tasks
     int n_groups, n_tasks;
+    // normalized / penalized alignment (aligner.cc:1522-1622): the TOP LEVEL box is filled and traced with the scoring modified by
+    // lambda (sigma - 2 lambda, gap - lambda, D - lambda * arc lengths: aligner_impl.hh:190-275, scoring.cc:77-90); the boxes of the arc
+    // matches on the path keep the unmodified scoring
+    int use_tl;                  // 1: the traceback's top level uses params_tl / ent_tl / ent8_tl
+    DevParams params_tl;
+    const DevEntry *ent_tl;
+    const uint2 *ent8_tl;
 };
 
 #endif

@@ -104,7 +104,7 @@ struct TraceJob { short al, bl, R, C; int am; };  // am: L-order index of the ar
 struct DevTopResult {
     int score;         // LB_NEG.. if -inf
     int max_i, max_j;
-    int pad;
+    int min_ij;        // traceback of a sequence-local top level: the cell it stopped at, min_i | min_j << 16 (aligner.cc:1251-1255)
 };
 
 #endif

@@ -907,7 +907,7 @@ __global__ void __launch_bounds__(32) toplevel_kernel(DevCtx c, int pair_begin, 
         }
         if (lane == 0) {
             DevTopResult r;
-            r.score = best; r.max_i = bi; r.max_j = bj; r.pad = 0;
+            r.score = best; r.max_i = bi; r.max_j = bj; r.min_ij = 0;
             if (!P.sequ_local && (P.fe_right1 || P.fe_right2) && best <= LB_NEG_LIMIT) { r.max_i = 0; r.max_j = 0; }
             c.top[t] = r;
         }
@@ -935,10 +935,12 @@ __global__ void __launch_bounds__(32) trace_kernel(DevCtx c, int pair_begin, int
     int *box = c.scratch + (size_t)blockIdx.x * c.scratch_words;
     const DevParams &P = c.params;
     const bool nolp = P.no_lonely_pairs != 0;
+    const bool mod = c.use_tl != 0;            // normalized / penalized: the top level box uses the modified scoring
+    const DevParams &PT = mod ? c.params_tl : c.params;
     BoxInit top_init, in_init;
     const bool globalA = !(P.sequ_local || P.fe_left2), globalB = !(P.sequ_local || P.fe_left1);
-    top_init.col_base = globalA ? P.open : 0; top_init.col_step = globalA ? P.gap : 0;
-    top_init.row_base = globalB ? P.open : 0; top_init.row_step = globalB ? P.gap : 0;
+    top_init.col_base = globalA ? PT.open : 0; top_init.col_step = globalA ? PT.gap : 0;
+    top_init.row_base = globalB ? PT.open : 0; top_init.row_step = globalB ? PT.gap : 0;
     in_init.col_base = P.open; in_init.col_step = P.gap; in_init.row_base = P.open; in_init.row_step = P.gap;
     for (;;) {
         int t = 0;
@@ -973,15 +975,28 @@ __global__ void __launch_bounds__(32) trace_kernel(DevCtx c, int pair_begin, int
             setup_box2(c, pr, job.al, job.bl, job.R, job.C, g, ws);
             bool ok;
             if ((g.umax + 1) * g.nslots > c.scratch_words) ok = false;
+            else if (tl && mod) {
+                DevCtx ct = c;
+                ct.params = c.params_tl; ct.ent = const_cast<DevEntry *>(c.ent_tl); ct.ent8 = const_cast<uint2 *>(c.ent8_tl);
+                int *sg = const_cast<int *>(ws.sig);
+                sg[lane] = ct.params.sigma8[lane]; sg[lane + 32] = ct.params.sigma8[lane + 32];
+                __syncwarp();
+                ok = run_box<NCMAX, true, CLAMP>(ct, pr, g, top_init, ws, box);
+                __syncwarp();
+                sg[lane] = c.params.sigma8[lane]; sg[lane + 32] = c.params.sigma8[lane + 32];
+                __syncwarp();
+            }
             else if (tl) ok = run_box<NCMAX, true, CLAMP>(c, pr, g, top_init, ws, box);
             else ok = run_box<NCMAX, GBD, false>(c, pr, g, in_init, ws, box);
             if (!ok) { if (lane == 0) atomicExch(c.error_flag, 3); break; }
             const int al = job.al, bl = job.bl;
             int i = tl ? top.max_i : job.R, j = tl ? top.max_j : job.C;
+            const DevParams &PW = (tl && mod) ? c.params_tl : c.params;                      // scoring of this box's walk
+            const DevEntry *entw = (tl && mod) ? c.ent_tl + pr.am_base : ent;                // D view of this box's walk
             // ---- walk (trace_in_arcmatch / trace_noex, state E_NO_NO)
             for (;;) {
                 const int mij = box_get(box, g, i - al, j - bl);
-                if (tl && P.sequ_local && mij == 0) break;                                   // aligner.cc:1251-1255
+                if (tl && P.sequ_local && mij == 0) { if (lane == 0) c.top[t].min_ij = (i & 0xffff) | (j << 16); break; }   // aligner.cc:1251-1255
                 if (i <= al) {                                                               // :1257-1271
                     if (!(tl && (P.sequ_local || P.fe_left1))) for (int k = bl + 1 + lane; k <= j; k += 32) edges[al + k] = (al << 2) | LB_EDGE_INS;
                     break;
@@ -991,20 +1006,20 @@ __global__ void __launch_bounds__(32) trace_kernel(DevCtx c, int pair_begin, int
                     break;
                 }
                 const bool vdiag = valid(i - 1, j - 1);
-                if (vdiag && mij == box_get(box, g, i - 1 - al, j - 1 - bl) + P.sigma8[ca[i] * LB_NCODES + cb[j]]) {   // :1099-1105
+                if (vdiag && mij == box_get(box, g, i - 1 - al, j - 1 - bl) + PW.sigma8[ca[i] * LB_NCODES + cb[j]]) {   // :1099-1105
                     emit(i, j, LB_EDGE_MATCH);
                     i--; j--;
                     continue;
                 }
                 bool moved = false;
-                if (P.open == 0) {                                                           // :1107-1124 linear gap cost
-                    if (valid(i - 1, j) && mij == box_get(box, g, i - 1 - al, j - bl) + P.gap) { emit(i, j, LB_EDGE_DEL); i--; moved = true; }
-                    else if (valid(i, j - 1) && mij == box_get(box, g, i - al, j - 1 - bl) + P.gap) { emit(i, j, LB_EDGE_INS); j--; moved = true; }
+                if (PW.open == 0) {                                                           // :1107-1124 linear gap cost
+                    if (valid(i - 1, j) && mij == box_get(box, g, i - 1 - al, j - bl) + PW.gap) { emit(i, j, LB_EDGE_DEL); i--; moved = true; }
+                    else if (valid(i, j - 1) && mij == box_get(box, g, i - al, j - 1 - bl) + PW.gap) { emit(i, j, LB_EDGE_INS); j--; moved = true; }
                 } else {                                                                     // :1125-1172 affine: gap runs
-                    int cost = P.open;
+                    int cost = PW.open;
                     for (int k = 1; i >= al + k; k++) {
                         if (!valid(i - k, j)) break;
-                        cost += P.gap;
+                        cost += PW.gap;
                         if (mij == box_get(box, g, i - k - al, j - bl) + cost) {
                             for (int l = lane; l < k; l += 32) edges[(i - l) + j] = ((i - l) << 2) | LB_EDGE_DEL;
                             i -= k; moved = true;
@@ -1012,10 +1027,10 @@ __global__ void __launch_bounds__(32) trace_kernel(DevCtx c, int pair_begin, int
                         }
                     }
                     if (!moved) {
-                        cost = P.open;
+                        cost = PW.open;
                         for (int k = 1; j >= bl + k; k++) {
                             if (!valid(i, j - k)) break;
-                            cost += P.gap;
+                            cost += PW.gap;
                             if (mij == box_get(box, g, i - al, j - k - bl) + cost) {
                                 for (int l = lane; l < k; l += 32) edges[i + (j - l)] = (i << 2) | LB_EDGE_INS;
                                 j -= k; moved = true;
@@ -1035,7 +1050,7 @@ __global__ void __launch_bounds__(32) trace_kernel(DevCtx c, int pair_begin, int
                     const int e = base + lane;
                     int key = -1;
                     if (e < e1) {
-                        const DevEntry en = ent[e];
+                        const DevEntry en = entw[e];
                         const int p = LB_ENT_LO(en.x), q = LB_ENT_HI(en.x);
                         if (LB_ENT_LO(en.y) == i && p >= al && q >= bl && mij == box_get(box, g, p - al, q - bl) + en.d) key = (p << 16) | q;
                     }

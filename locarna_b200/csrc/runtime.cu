@@ -193,6 +193,7 @@ struct lb200_ctx {
     PfCtx pf_last; bool pf_have = false; bool pf_probs_done = false; long long pf_mat_doubles = 0;
     int max_box_words = 1, max_len = 1;
     DevBuf d_pairs, d_codes, d_band_lo, d_band_hi, d_sptr, d_ent, d_am, d_tasks, d_top, d_scratch, d_cursor, d_flag, d_levcnt, d_done, d_ent8;
+    DevBuf d_ent_mod, d_ent8_mod;   // D view of the modified scoring (normalized / penalized alignment)
     DevBuf d_col_first, d_col_last, d_groups, d_gorder, d_ngroups, d_rows_scratch, d_row_built, d_clist, d_cnblk;   // row-grouped D fill
     int pack_entries = 1;  // 8-byte packed S-order copy for the single-state sweep when every sequence is <= LB_PACK_MAXLEN (LB200_PACK=0 disables)
     int dfill_mode = 2;   // 2: automatic (row-grouped kernel where it applies), 3: row-grouped or fail (LB200_DFILL=rows), 1: dependency-driven persistent launch of single boxes (LB200_DFILL=dep), 0: one launch per level group (LB200_DFILL=levels)
@@ -201,7 +202,7 @@ struct lb200_ctx {
     int sb_pairs = 1 << 30;   // pair block of the dependency-driven order (LB200_SB_PAIRS; default: one block)
     ~lb200_ctx() {
         DevBuf *all[] = {&d_pairs, &d_codes, &d_band_lo, &d_band_hi, &d_sptr, &d_ent, &d_am, &d_tasks, &d_top, &d_scratch, &d_cursor, &d_flag, &d_levcnt, &d_done, &d_ent8,
-                         &d_col_first, &d_col_last, &d_groups, &d_gorder, &d_ngroups, &d_rows_scratch, &d_row_built, &d_clist, &d_cnblk,
+                         &d_ent_mod, &d_ent8_mod, &d_col_first, &d_col_last, &d_groups, &d_gorder, &d_ngroups, &d_rows_scratch, &d_row_built, &d_clist, &d_cnblk,
                          &d_arc_left, &d_arc_right, &d_arc_weight, &d_arc_sdelta, &d_lptr, &d_lcount, &d_am_seq, &d_cell_rev, &d_cell_start, &d_skeys, &d_skeys2,
                          &d_svals, &d_svals2, &d_tasks_unsorted, &d_tkeys, &d_tkeys2, &d_tvals, &d_tvals2, &d_ntasks, &d_qstart, &d_stats, &d_tmp, &d_tr_edges, &d_tr_str, &d_tr_stack,
                          &d_pf_esig, &d_pf_bpow, &d_pf_d, &d_pf_z, &d_pf_scratch, &d_pf_dp, &d_pf_amp, &d_pf_mats, &d_pf_cta,
@@ -1078,6 +1079,104 @@ int lb200_pair_band(const lb200_ctx *c, int pair, int *min_col, int *max_col) {
     return LB200_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ normalized / penalized alignment
+// aligner.cc:1522-1622. The D table is filled as for an ordinary alignment; then the TOP LEVEL is aligned and traced with the scoring
+// modified by lambda (ModifiedScoringView, aligner_impl.hh:190-275; Scoring::modify_by_parameter, scoring.cc:77-90): sigma - 2 lambda,
+// gap - lambda, D(a, b) - lambda * (length of arc a + length of arc b). Normalized alignment iterates lambda := score / (length + L)
+// (Dinkelbach) until it does not change; penalized alignment is one pass with lambda = the position penalty. One pair per launch:
+// lambda differs from pair to pair after the first iteration.
+cudaError_t lb200_adjust_d(const DevEntry *ent, DevEntry *ent_mod, uint2 *ent8_mod, size_t n, int lambda, cudaStream_t st);
+
+static int run_modified(lb200_ctx *c, bool normalized, int64_t arg) {
+    if (c->device == LB200_DEVICE_NONE) return fail(c, LB200_ERR_CUDA, "host-only context: needs a CUDA device (no CPU fallback)");
+    if (c->params.struct_local) return fail(c, LB200_ERR_UNSUPPORTED, normalized ? "Normalized structure local alignment not supported." : "penalized structure local alignment is not supported");
+    if (normalized && !c->params.sequ_local) return fail(c, LB200_ERR_ARG, "Cannot run normalized alignment without --sequ_local on.");   // locarna.cc:431-436
+    { const int rc = lb200_run(c, LB200_RUN_SCORE_ONLY); if (rc != LB200_OK) return rc; }       // D fill (aligner.cc:1529-1530, :1607-1608)
+    const int P = (int)c->pairs.size();
+    if (P == 0) return LB200_OK;
+    lb200_ctx::Resident &R = c->res;
+    if (!(R.valid && R.p0 == 0 && R.p1 == P)) return fail(c, LB200_ERR_UNSUPPORTED, "normalized / penalized alignment needs the whole batch resident; split the pair list");
+    cudaStream_t st = c->stream;
+    CUDA_TRY(c, c->d_ent_mod.ensure(std::max<size_t>(R.total_am, 1) * sizeof(DevEntry)));
+    const bool packed = R.dc.ent8 != nullptr;
+    if (packed) CUDA_TRY(c, c->d_ent8_mod.ensure(std::max<size_t>(R.total_am, 1) * sizeof(uint2)));
+    CUDA_TRY(c, c->d_tr_edges.ensure((size_t)R.sptr_total * 4));
+    CUDA_TRY(c, c->d_tr_str.ensure((size_t)R.sptr_total));
+    CUDA_TRY(c, c->d_tr_stack.ensure((size_t)P * R.stack_cap * sizeof(TraceJob)));
+    R.dc.trace_edges = (int *)c->d_tr_edges.p; R.dc.trace_str = (char *)c->d_tr_str.p;
+    R.dc.trace_stack = (TraceJob *)c->d_tr_stack.p; R.dc.trace_stack_cap = R.stack_cap;
+    int64_t launches = 0;
+    CUDA_TRY(c, cudaEventRecord(c->ev0, st));
+    for (int k = 0; k < P; k++) {
+        PairRec &r = c->pairs[k];
+        const int n = c->seqs[r.seqA].len, m = c->seqs[r.seqB].len, off = R.sptr_off[k];
+        long new_lambda = normalized ? 0 : (long)arg, lambda = normalized ? -1 : (long)arg - 1;
+        DevTopResult top;
+        std::vector<int> h_edges((size_t)n + m + 3);
+        std::vector<char> h_str((size_t)n + m + 3);
+        int iterations = 0;
+        while (lambda != new_lambda) {
+            lambda = new_lambda;
+            if (++iterations > 10000) return fail(c, LB200_ERR_STATE, "normalized alignment does not converge");
+            if (lambda > (1 << 20) || lambda < -(1 << 20)) return fail(c, LB200_ERR_UNSUPPORTED, "modification parameter %ld out of the supported range", lambda);
+            // modified scoring of this pair's top level
+            DevCtx ct = R.dc;
+            for (int x = 0; x < 64; x++) ct.params.sigma8[x] -= 2 * (int)lambda;
+            ct.params.gap -= (int)lambda;
+            ct.params.gap_open = ct.params.gap + ct.params.open;
+            CUDA_TRY(c, lb200_adjust_d((const DevEntry *)c->d_ent.p + r.am_base, (DevEntry *)c->d_ent_mod.p + r.am_base,
+                                       packed ? (uint2 *)c->d_ent8_mod.p + r.am_base : nullptr, (size_t)r.K, (int)lambda, st));
+            ct.ent = (DevEntry *)c->d_ent_mod.p; ct.ent8 = packed ? (uint2 *)c->d_ent8_mod.p : nullptr;
+            CUDA_TRY(c, cudaMemsetAsync(c->d_cursor.p, 0, 4100 * 4, st));
+            CUDA_TRY(c, cudaMemsetAsync(c->d_flag.p, 0, 16, st));
+            launch_toplevel(ct, R.nc_inst, 1, R.smem_bytes, k, k + 1, (int *)c->d_cursor.p + 4098, st);
+            DevCtx dt = R.dc;
+            dt.use_tl = 1; dt.params_tl = ct.params; dt.ent_tl = ct.ent; dt.ent8_tl = ct.ent8;
+            launch_trace(dt, R.nc_inst, c->params.indel_opening > 0, 1, R.smem_bytes, k, k + 1, (int *)c->d_cursor.p + 4099, st);
+            launches += 3;
+            int h_flag[4] = {0, 0, 0, 0};
+            CUDA_TRY(c, cudaMemcpyAsync(&top, (DevTopResult *)c->d_top.p + k, sizeof top, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(c, cudaMemcpyAsync(h_flag, c->d_flag.p, 16, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(c, cudaStreamSynchronize(st));
+            if (h_flag[0] != 0) return fail(c, LB200_ERR_UNSUPPORTED, "kernel reported error %d in the modified top level", h_flag[0]);
+            if (!normalized) break;
+            if (top.score < LB_NEG_LIMIT) return fail(c, LB200_ERR_STATE, "normalized alignment: the local score is -inf");
+            // aligner.cc:1566-1575: length of the aligned subsequences from the trace; the modified score plus length * lambda is the
+            // unmodified score of this alignment (every position lost lambda); the arithmetic is the reference's (size_t + long, unsigned)
+            const int min_i = top.min_ij & 0xffff, min_j = (top.min_ij >> 16) & 0xffff;
+            const unsigned long length = (unsigned long)top.max_i - (unsigned long)min_i + 1 + (unsigned long)top.max_j - (unsigned long)min_j + 1;
+            const long score = (long)top.score + (long)(length * (unsigned long)lambda);
+            new_lambda = (long)((unsigned long)score / (length + (unsigned long)arg));
+        }
+        CUDA_TRY(c, cudaMemcpyAsync(h_edges.data(), (int *)c->d_tr_edges.p + off, ((size_t)n + m + 3) * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaMemcpyAsync(h_str.data(), (char *)c->d_tr_str.p + off, (size_t)n + m + 3, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));
+        if (normalized) { r.neg_inf = false; r.score = new_lambda; }                       // aligner.cc:1596
+        else { r.neg_inf = top.score < LB_NEG_LIMIT; r.score = r.neg_inf ? 0 : top.score; }
+        r.max_i = top.max_i; r.max_j = top.max_j;
+        r.edges_a.clear(); r.edges_b.clear();
+        for (int idx = 0; idx <= n + m; idx++) {
+            const int v = h_edges[idx];
+            if (v == 0) continue;
+            const int i = v >> 2, j = idx - i, kind = v & 3;
+            r.edges_a.push_back(kind == 3 ? -1 : i);
+            r.edges_b.push_back(kind == 2 ? -1 : j);
+        }
+        r.str_a.assign(h_str.begin() + 1, h_str.begin() + n + 1);
+        r.str_b.assign(h_str.begin() + n + 2, h_str.begin() + n + 2 + m);
+        r.traced = true;
+    }
+    CUDA_TRY(c, cudaEventRecord(c->ev1, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    float ms = 0;
+    CUDA_TRY(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->last_kernel_ms += ms; c->last_launches += launches;
+    return LB200_OK;
+}
+
+int lb200_run_normalized(lb200_ctx *c, int64_t L) { return c ? run_modified(c, true, L) : LB200_ERR_ARG; }
+int lb200_run_penalized(lb200_ctx *c, int64_t position_penalty) { return c ? run_modified(c, false, position_penalty) : LB200_ERR_ARG; }
+
 // ------------------------------------------------------------------------------------------------ LocARNA-P inside
 int lb200_run_pf(lb200_ctx *c, double pf_scale) {
     if (!c) return LB200_ERR_ARG;
@@ -1319,6 +1418,23 @@ __global__ void reset_d_kernel(DevEntry *ent, uint2 *ent8, size_t n) {
         ent[i].d = LB_NEG;
         if (ent8 != nullptr) ent8[i].y = (ent8[i].y & 15u) | ((uint32_t)LB_PACK_NEG << 4);
     }
+}
+// D view of the modified scoring: D(a, b) - lambda * (arc_length(a) + arc_length(b)) (aligner_impl.hh:235-253); -inf stays -inf
+__global__ void adjust_d_kernel(const DevEntry *ent, DevEntry *ent_mod, uint2 *ent8_mod, size_t n, int lambda) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        DevEntry e = ent[i];
+        const int al1 = LB_ENT_LO(e.x), bl1 = LB_ENT_HI(e.x), ar = LB_ENT_LO(e.y), br = LB_ENT_HI(e.y);
+        if (e.d >= LB_NEG_LIMIT) e.d -= lambda * ((ar - al1) + (br - bl1));
+        else e.d = LB_NEG;
+        ent_mod[i] = e;
+        if (ent8_mod != nullptr) ent8_mod[i] = make_uint2((uint32_t)al1 | ((uint32_t)bl1 << 9) | ((uint32_t)ar << 18) | (((uint32_t)br & 31u) << 27), LB_PACK_W1(br, e.d));
+    }
+}
+cudaError_t lb200_adjust_d(const DevEntry *ent, DevEntry *ent_mod, uint2 *ent8_mod, size_t n, int lambda, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+    adjust_d_kernel<<<grid, 256, 0, st>>>(ent, ent_mod, ent8_mod, n, lambda);
+    return cudaGetLastError();
 }
 cudaError_t lb200_reset_d(DevEntry *ent, uint2 *ent8, size_t n, cudaStream_t st) {
     if (n == 0) return cudaSuccess;

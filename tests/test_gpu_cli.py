@@ -44,8 +44,25 @@ def test_cli_exp_prob_maxbpspan_arcmatch_scores(case, tmp_path):
 
 
 def test_cli_rejects_unimplemented_modes():
-    r = subprocess.run([CLI, os.path.join(GOLD, "g0.pp"), os.path.join(GOLD, "g1.pp"), "--normalized", "100"], capture_output=True, text=True)
+    r = subprocess.run([CLI, os.path.join(GOLD, "g0.pp"), os.path.join(GOLD, "g1.pp"), "--kbest", "3"], capture_output=True, text=True)
     assert r.returncode == 255 and "does not implement" in r.stderr
+
+
+CASES_NORM = json.load(open(os.path.join(GOLD, "normalized_outputs.json")))
+
+
+@pytest.mark.parametrize("case", CASES_NORM, ids=lambda c: "%s-%s" % ("_".join(c["args"]), c["A"]))
+def test_cli_normalized_penalized(case, tmp_path):
+    """--normalized L (Dinkelbach iteration, aligner.cc:1522-1597) and --penalized PP (aligner.cc:1599-1622) against the reference binary:
+    stdout (score + alignment), stderr of the rejected combinations and the clustal file (tools/make_golden_normalized.py)."""
+    clu = str(tmp_path / "out.aln")
+    r = subprocess.run([CLI, os.path.join(GOLD, case["A"]), os.path.join(GOLD, case["B"]), "--clustal", clu] + case["args"], capture_output=True, text=True)
+    assert r.returncode == case["rc"], r.stderr
+    assert r.stdout == case["stdout"]
+    if case["rc"] != 0:
+        assert r.stderr == case["stderr"]
+    else:
+        assert open(clu).read() == case["clustal"]
 
 
 CLI_P = os.path.join(ROOT, "locarna_b200", "bin", "locarna_p_b200")
