@@ -296,13 +296,16 @@ def main():
     t0 = time.time()
     kernel_ms = dfill_ms = 0.0
     dfill_launches = launches = 0
+    dfill_kinds, rows_fallbacks = set(), 0
     for s in range(K):
         resident_step()
         for ctx, _ in ctxs:
             kernel_ms += ctx.kernel_ms; dfill_ms += ctx.dfill_ms; dfill_launches += ctx.dfill_launches; launches += ctx.launches
+            dfill_kinds.add(ctx.dfill_kind)
     barrier()
     elapsed = time.time() - t0
     clocks = sampler.stop()
+    rows_fallbacks = sum(ctx.rows_fallbacks for ctx, _ in ctxs)
     cells = terms = am = arcs = rows = 0
     resident_scores = {}
     for ctx, part in ctxs:
@@ -407,7 +410,10 @@ def main():
         n_dfill = max(1, dfill_launches)
         roofline = {"bound": "int_alu", "achieved": ops / dfill_s / 1e12, "peak": alu_peak / 1e12, "unit": "Tintop/s",
                     "frac": ops / dfill_s / alu_peak, "traffic": traffic,
-                    "kernel": "dfill kernel (dependency-driven persistent launch)" if dfill_launches <= K * max(1, (len(resident_scores) + pl["sub_batch"] - 1) // pl["sub_batch"]) else "dfill_kernel (one launch per level group)",
+                    "kernel": " + ".join({0: "dfill_kernel (one launch per level group)", 1: "dfill_dep_kernel (one box per warp, dependency counters)",
+                                          2: "dfill_rows_kernel (row-grouped sweep, one persistent launch per sub-batch)"}.get(k, "?") for k in sorted(dfill_kinds)),
+                    "rows_fallbacks": rows_fallbacks,
+                    "traffic_source": "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch on a 2048-pair sub-batch (ncu --set full)",
                     "launch_ms": my_dfill_ms / n_dfill, "launches": dfill_launches,
                     "ops": "9 int ops per cell update (SURVEY 8d R1; the 2 ops per folded arc-match term are not counted)",
                     "gcups": my_cells * K / dfill_s / 1e9, "sm_mhz": sm_mhz,

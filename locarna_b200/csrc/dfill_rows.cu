@@ -222,15 +222,26 @@ __device__ __forceinline__ void dp_step(State<NC> &S, const Geom &g, const int *
         fL0[v] = __shfl_sync(0xffffffffu, S.f[NC - 1][v], left);
     }
     bool below = false;
+    // the accumulators of the lane's NC cells are adjacent words: one access per layer (NC = 2: 64-bit, no bank conflict between lanes)
+    int arc[NC][V];
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+        if (NC == 2) {
+            int2 *a2 = (int2 *)(arcp + v * (RING * 32 * NC));
+            const int2 a = *a2;
+            *a2 = make_int2(LB_NEG, LB_NEG);
+            arc[0][v] = a.x; arc[NC - 1][v] = a.y;
+        } else {
+#pragma unroll
+            for (int k = 0; k < NC; k++) { arc[k][v] = arcp[v * (RING * 32 * NC) + k]; arcp[v * (RING * 32 * NC) + k] = LB_NEG; }
+        }
+    }
 #pragma unroll
     for (int k = NC - 1; k >= 0; k--) {   // right to left: slot k reads slot k - 1's previous cell
         const uint32_t z = S.K + (uint32_t)k * 4095u - S.w[k];
         const bool ok = (~z & GUARDS) == 0;
         if (k == NC - 1) below = (z & G_HI) == 0;
         const int sg = *(const int *)((const char *)sig + S.rcp[-k] + (S.w[k] >> 24));
-        int arc[V];
-#pragma unroll
-        for (int v = 0; v < V; v++) { arc[v] = arcp[v * (RING * 32 * NC) + k]; arcp[v * (RING * 32 * NC) + k] = LB_NEG; }
         int nm[V];
 #pragma unroll
         for (int v = 0; v < V; v++) {
@@ -238,7 +249,7 @@ __device__ __forceinline__ void dp_step(State<NC> &S, const Geom &g, const int *
             const int fl = k == 0 ? fL0[v] : S.f[k > 0 ? k - 1 : 0][v];
             const int ee = addmax(S.e[k][v], gap, S.m[k][v] + gap_open);
             const int ff = addmax(fl, gap, ml + gap_open);
-            int mm = max3(addmax(S.md[k][v], sg, ee), ff, arc[v]);
+            int mm = max3(addmax(S.md[k][v], sg, ee), ff, arc[k][v]);
             if (SEED) mm = (u == g.jv[v] && S.jc + k == u) ? 0 : mm;
             nm[v] = ok ? mm : LB_NEG;
             S.m[k][v] = nm[v]; S.e[k][v] = ok ? ee : LB_NEG; S.f[k][v] = ok ? ff : LB_NEG;
@@ -285,13 +296,26 @@ __device__ void sweep(const DevCtx &c, const RowsCtx &r, const DevGroup &grp, co
     int *ap = sm.acc + lane * NC;
     const int left = (lane + 31) & 31;
 
-    // entry list of the row: blocks of target group t become due after cell step 4t - 5
+    // entry list of the row: blocks of target group t become due after cell step 4t - 5. The block counts move next to the block
+    // offsets (the list is complete: all groups of the row have contributed), and the first block of the next target group is
+    // requested one group ahead, so that a fold waits for one memory round trip (the gather of the sources), not for three in a row
     const uint2 *list = r.clist + (size_t)grp.pair * r.clist_cap + lane;
-    const int *nblk = r.cnblk + (size_t)grp.pair * LB_ROWS_TG;
+    {
+        const int *nblk = r.cnblk + (size_t)grp.pair * LB_ROWS_TG;
+        for (int t = lane; t < LB_ROWS_TG; t += 32) {
+            const int nb = (t >= 2 && t < g.n_tg) ? min(__ldcg(nblk + t), 2047) : 0;
+            sm.gstart[t] = (t < g.n_tg ? sm.gstart[t] & 0xfffff : 0) | (nb << 20);
+        }
+        __syncwarp();
+    }
     const int4 *boxv = (const int4 *)box;
     int4 pm = make_int4(0, 0, 0, 0);
     int pd = LB_NEG, ps = 0;
     bool pending = false;
+    {
+        const int gs = sm.gstart[min((g.u0 + 8) >> 2, LB_ROWS_TG - 1)];   // the first group that falls due
+        if ((gs >> 20) > 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(list + (size_t)(gs & 0xfffff) * 32));
+    }
     auto land = [&]() {
         // padding entries and entries with a source before u0 carry D = -inf: they fold nothing, and left in they would all hit the
         // same accumulator (one serialised wavefront per lane)
@@ -308,10 +332,18 @@ __device__ void sweep(const DevCtx &c, const RowsCtx &r, const DevGroup &grp, co
         if (((u + 5) & 3) == 0) {
             const int t = (u + 5) >> 2;
             if (t < g.n_tg) {
-                const int nb = __ldcg(nblk + t);
-                const uint2 *p = list + (size_t)sm.gstart[t] * 32;
-                for (int b = 0; b < nb; b++, p += 32) {
-                    const uint2 en = __ldcg(p);
+                const int gs = sm.gstart[t], gs1 = sm.gstart[t + 1];
+                const int nb = gs >> 20;
+                // the first block of the next group is pulled into L1 now and read from there at the next fold. (Carrying it in
+                // registers does not work: ptxas loads into a temporary and copies it at the end of this fold, i.e. waits here.)
+                // L1 is safe for the list: it is complete before any group of the row sweeps, and every group starts with an
+                // acquire, which invalidates the SM's L1.
+                if ((gs1 >> 20) > 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(list + (size_t)(gs1 & 0xfffff) * 32));
+                uint2 en = make_uint2(0u, 0u);
+                const uint2 *p = list + (size_t)(gs & 0xfffff) * 32;
+                for (int b = 0; b < nb; b++) {
+                    if (b == 0) asm volatile("ld.global.ca.v2.u32 {%0, %1}, [%2];" : "=r"(en.x), "=r"(en.y) : "l"(p) : "memory");
+                    else en = __ldcg(p + b * 32);
                     if (pending) land();
                     // sources before this group's first anti-diagonal are -inf in all its layers (and not stored in its box)
                     const bool live = (int)((en.x & 0xffffu) >> LOGW) >= g.u0;
@@ -410,7 +442,7 @@ __device__ void run_group(const DevCtx &c, const RowsCtx &r, const DevGroup &grp
     write_d<NC>(c, pr, grp, g, box, nolp);
 }
 
-__global__ void __launch_bounds__(32, 20) dfill_rows_kernel(DevCtx c, RowsCtx r, int *cursor) {
+__global__ void __launch_bounds__(32, 18) dfill_rows_kernel(DevCtx c, RowsCtx r, int *cursor) {
     extern __shared__ __align__(16) int smem[];
     const int lane = threadIdx.x;
     Smem sm;
