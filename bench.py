@@ -78,6 +78,7 @@ def job_pairs(n_seq, n_job):
 
 
 def score_checksum(scores):
+    """sha256 prefix over the int64 scores in pair order; -inf (None, or the library's LB200_SCORE_NEG_INF = -2^63) as -2^63."""
     h = hashlib.sha256()
     for s in scores:
         h.update(struct.pack("<q", -(2 ** 63) if s is None else int(s)))
@@ -189,6 +190,7 @@ def parse_args(argv=None):
     ap.add_argument("--seqs", type=int, default=512)
     ap.add_argument("--len", type=int, default=300)
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs of the CPU baseline sample (default: 2 per core)")
+    ap.add_argument("--lanes", type=int, default=2, help="contexts (host thread + CUDA stream each) that work off a rank's share in the e2e leg")
     ap.add_argument("--traced-steps", type=int, default=1, help="extra e2e jobs with traceback (reported as e2e_traced)")
     return ap.parse_args(argv)
 
@@ -259,20 +261,24 @@ def main():
         paths = make_inputs(args.seqs, args.len, 1)
     n_steps = W + K
 
+    import numpy as np
+    pair_a = np.array([p[0] for p in pairs], dtype=np.int32)
+    pair_b = np.array([p[1] for p in pairs], dtype=np.int32)
+
     def load_job(ctx):
-        """Sequences from the PP files, cost estimate, this rank's share of the job's pair list."""
+        """Sequences from the PP files, cost estimate and this rank's share of the job's pair list (lb200_shard_job: every rank
+        computes the same deterministic split). Returns the first sequence id, this rank's pair indices, the largest share."""
         first = ctx.add_pps(paths)
-        n_arcs = [ctx.seq_num_arcs(first + s) for s in range(len(paths))]
-        lengths = [ctx.seq_length(first + s) for s in range(len(paths))]
-        mine = shard_job(pairs, n_arcs, lengths, world)[rank]
-        return first, mine
+        shares = ctx.shard_job(pair_a + first, pair_b + first, world)
+        return first, shares[rank], max(len(x) for x in shares)
 
     # ---- resident leg: build + upload this rank's share before the timed region, in device batches of --sub-batch pairs
     t0 = time.time()
     ctxs, resident_bytes = [], 0
     probe = capi.Context(local_rank, FLAGS)
-    _, mine = load_job(probe)
+    _, mine, _ = load_job(probe)
     probe.close()
+    mine = [int(k) for k in mine]
     for lo in range(0, len(mine), pl["sub_batch"]):
         part = mine[lo:lo + pl["sub_batch"]]
         ctx = capi.Context(local_rank, FLAGS)
@@ -321,23 +327,15 @@ def main():
     env_stats = [0, 0]
 
     def e2e_step(run_flags=capi.RUN_SCORE_ONLY):
-        ctx = capi.Context(local_rank, FLAGS)
-        first, mine = load_job(ctx)
-        ctx.add_pairs([(first + pairs[k][0], first + pairs[k][1]) for k in mine])
-        ctx.run(run_flags)
-        sc = ctx.scores()
-        dev, host = ctx.envelope_stats()
-        env_stats[0] += dev; env_stats[1] += host
-        h2d, d2h = ctx.h2d_bytes, ctx.d2h_bytes
-        nl = ctx.launches
-        ctx.close()
+        mine, sc, cap, st = allpairs.align_share(paths, pair_a, pair_b, FLAGS, device=local_rank, world=world, rank=rank,
+                                                 lanes=args.lanes, run_flags=run_flags)
+        env_stats[0] += st["env_device"]; env_stats[1] += st["env_host"]
         if dist is not None:  # the one collective of the path: score slices to rank 0 (NCCL gather)
-            full = allpairs.gather_scores(dist, mine, sc, len(pairs), device="cuda")
+            full = allpairs.gather_scores_np(dist, mine, sc, len(pairs), cap, device="cuda", fill=capi.SCORE_NEG_INF)
         else:
-            full = [None] * len(pairs)
-            for k, idx in enumerate(mine):
-                full[idx] = sc[k]
-        return full, h2d, d2h, nl
+            full = np.full(len(pairs), capi.SCORE_NEG_INF, dtype=np.int64)
+            full[mine] = sc
+        return full, st["h2d"], st["d2h"], st["launches"]
 
     for s in range(W):
         e2e_step()
@@ -350,6 +348,8 @@ def main():
         h2d += a; d2h += b; e2e_launches += nl
     barrier()
     e2e_elapsed = time.time() - t0
+    if full is not None:   # rank 0: plain Python values for the checks below (outside the timed region)
+        full = [None if v == capi.SCORE_NEG_INF else int(v) for v in full]
     traced_elapsed = None
     if args.traced_steps > 0:
         barrier()
@@ -435,7 +435,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_total // K, "d2h_bytes_per_step": d2h_total // K,
                     "ms_per_step": 1e3 * e2e_elapsed / K,
-                    "scope": "per job: context, parse of %d PP files, sharding, H2D, envelope bands, device build, D fill, top level, D2H, gather" % len(paths)},
+                    "scope": "per job: context, parse of %d PP files, sharding, H2D, envelope bands, device build, D fill, top level, D2H, gather; the share is worked off by %d contexts (host thread + stream each)" % (len(paths), args.lanes)},
             "gpu_launches": launches_total,
             "roofline": roofline, "roofline_hbm": roofline_hbm,
             "device_ms_per_step": kernel_ms_max / K, "dfill_ms_per_step": dfill_ms_max / K,

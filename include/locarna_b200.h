@@ -203,6 +203,9 @@ double lb200_pair_cost(int n_arcsA, int n_arcsB, int lenA, int lenB);
 int lb200_shard_pairs(int64_t n_pairs, const double *cost, int world, int *rank_of, int64_t *order, int64_t *rank_begin);
 /* number of base pairs (arcs with probability >= min_prob) of a sequence: the input of lb200_pair_cost */
 int lb200_seq_num_arcs(const lb200_ctx *ctx, int seq);
+/* lb200_pair_cost + lb200_shard_pairs for pairs (seqA[k], seqB[k]) of the context's sequences in one call; rank_of may be NULL */
+int lb200_shard_job(const lb200_ctx *ctx, int64_t n_pairs, const int *seqA, const int *seqB, int world, int *rank_of, int64_t *order,
+                    int64_t *rank_begin);
 
 /* Guide tree of the all-vs-all stage (host): UPGMA over the symmetric score matrix (n x n, row major, diagonal 0) with the tie
  * rules of lib/perl/MLocarna/Tree.pm:181-262; writes the newick string (without the trailing ';') that mlocarna stores in

@@ -36,6 +36,72 @@ def shard_pairs(pairs, costs, world: int):
     return [[order[k] for k in range(begin[r], begin[r + 1])] for r in range(world)]
 
 
+def gather_scores_np(dist, local_idx, local_scores, n_pairs: int, cap: int, device=None, fill=None):
+    """gather_scores for numpy arrays: `cap` = the largest share (every rank knows all share sizes: the split is deterministic),
+    so the exchange is the ONE gather and nothing else. Returns an int64 array of n_pairs scores on rank 0 (`fill` where no rank
+    reported), None elsewhere."""
+    import numpy as np
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    rows = np.full((max(cap, 1), 2), -1, dtype=np.int64)
+    rows[:len(local_idx), 0] = local_idx
+    rows[:len(local_idx), 1] = local_scores
+    buf = torch.from_numpy(rows)
+    buf = buf.to(device) if device is not None else buf
+    out = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+    dist.gather(buf, out, dst=0)
+    if rank != 0:
+        return None
+    allrows = torch.stack(out).reshape(-1, 2).cpu().numpy()
+    keep = allrows[:, 0] >= 0
+    full = np.full(n_pairs, np.iinfo(np.int64).min if fill is None else fill, dtype=np.int64)
+    full[allrows[keep, 0]] = allrows[keep, 1]
+    return full
+
+
+def align_share(paths, pair_a, pair_b, flags, device: int = 0, world: int = 1, rank: int = 0, lanes: int = 2, run_flags: int = 0):
+    """This rank's share of an all-vs-all job, from the PP files to the scores: parse, cost-balanced split over `world` ranks
+    (lb200_shard_job, the same on every rank), alignment on `device`. The share is worked off by `lanes` contexts on their own
+    host threads and CUDA streams: while one context's D fill runs (and tails off), the other one parses, derives bands and builds
+    its tables - the same scheme mlocarna_tree_b200 uses across devices. pair_a / pair_b: int32 arrays of sequence indices.
+    Returns (pair indices of the share, int64 scores (capi.SCORE_NEG_INF = -inf), largest share of any rank, stats dict)."""
+    import threading
+    import numpy as np
+    from . import capi
+    lanes = max(1, lanes)
+    out = [None] * lanes
+    err = []
+
+    def work(lane):
+        ctx = None
+        try:
+            ctx = capi.Context(device, flags)
+            first = ctx.add_pps(paths)
+            shares = ctx.shard_job(pair_a + first, pair_b + first, world)
+            mine = shares[rank][lane::lanes]          # descending cost, dealt out in turn: equal work per lane
+            ctx.add_pairs_np(pair_a[mine] + first, pair_b[mine] + first)
+            ctx.run(run_flags)
+            dev, host = ctx.envelope_stats()
+            out[lane] = (mine, ctx.scores_np().copy(), max(len(x) for x in shares),
+                         {"h2d": ctx.h2d_bytes, "d2h": ctx.d2h_bytes, "launches": ctx.launches, "env_device": dev, "env_host": host})
+        except Exception as e:  # noqa: BLE001 - reported by the caller's thread
+            err.append(e)
+        finally:
+            if ctx is not None:
+                ctx.close()
+
+    threads = [threading.Thread(target=work, args=(l,)) for l in range(1, lanes)]
+    for t in threads:
+        t.start()
+    work(0)
+    for t in threads:
+        t.join()
+    if err:
+        raise err[0]
+    stats = {k: sum(o[3][k] for o in out) for k in out[0][3]}
+    return np.concatenate([o[0] for o in out]), np.concatenate([o[1] for o in out]), out[0][2], stats
+
+
 def assemble_matrix(n: int, pairs, scores, neg_inf_value: int = -100000000):
     """Symmetric score matrix with zero diagonal (mlocarna:2353-2373); '-inf' maps to -1e8 (mlocarna:3523)."""
     m = [[0] * n for _ in range(n)]

@@ -42,7 +42,7 @@ EXPORTS = [
     "lb200_prepare", "lb200_upload", "lb200_run", "lb200_last_kernel_ms", "lb200_last_h2d_bytes", "lb200_last_d2h_bytes", "lb200_last_dfill_ms", "lb200_last_dfill_launches", "lb200_last_launches", "lb200_envelope_stats", "lb200_pair_score", "lb200_get_scores",
     "lb200_pair_get_info", "lb200_pair_band", "lb200_pair_arcmatches", "lb200_pair_alignment", "lb200_upgma_newick",
     "lb200_run_pf", "lb200_pair_partition_function", "lb200_pair_arcmatch_pf", "lb200_run_pf_probs", "lb200_pair_arcmatch_probs",
-    "lb200_pair_basematch_probs", "lb200_pairs_add", "lb200_all_vs_all", "lb200_pair_cost", "lb200_shard_pairs", "lb200_seq_num_arcs", "lb200_seqs_add_pp", "lb200_last_dfill_kind", "lb200_rows_fallbacks", "lb200_release_device_cache", "lb200_run_normalized", "lb200_run_penalized",
+    "lb200_pair_basematch_probs", "lb200_pairs_add", "lb200_all_vs_all", "lb200_pair_cost", "lb200_shard_pairs", "lb200_seq_num_arcs", "lb200_seqs_add_pp", "lb200_last_dfill_kind", "lb200_rows_fallbacks", "lb200_release_device_cache", "lb200_run_normalized", "lb200_run_penalized", "lb200_shard_job",
 ]
 
 _lib = None
@@ -91,6 +91,7 @@ def load():
     lib.lb200_run.argtypes = [vp, C.c_int]
     lib.lb200_last_kernel_ms.argtypes = [vp]
     lib.lb200_last_kernel_ms.restype = C.c_double
+    lib.lb200_shard_job.argtypes = [vp, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.lb200_run_normalized.argtypes = [vp, C.c_int64]
     lib.lb200_run_penalized.argtypes = [vp, C.c_int64]
     lib.lb200_last_dfill_kind.argtypes = [vp]
@@ -203,6 +204,32 @@ class Context:
         a = (C.c_int * max(n, 1))(*[p[0] for p in pairs])
         b = (C.c_int * max(n, 1))(*[p[1] for p in pairs])
         return self._chk(self.lib.lb200_pairs_add(self.h, n, a, b))
+
+    def add_pairs_np(self, a, b) -> int:
+        """add_pairs for two int32 numpy arrays (no per-pair Python work)."""
+        import numpy as np
+        a = np.ascontiguousarray(a, dtype=np.int32); b = np.ascontiguousarray(b, dtype=np.int32)
+        if a.shape != b.shape or a.ndim != 1:
+            raise Error("add_pairs_np: two 1-d arrays of equal length expected")
+        return self._chk(self.lib.lb200_pairs_add(self.h, len(a), a.ctypes.data_as(C.POINTER(C.c_int)), b.ctypes.data_as(C.POINTER(C.c_int))))
+
+    def shard_job(self, a, b, world: int):
+        """Cost-balanced split (lb200_shard_job) of the pairs (a[k], b[k]) of this context's sequences over `world` shares:
+        list of int64 numpy arrays of pair indices, each by descending cost."""
+        import numpy as np
+        a = np.ascontiguousarray(a, dtype=np.int32); b = np.ascontiguousarray(b, dtype=np.int32)
+        n = len(a)
+        order = np.empty(max(n, 1), dtype=np.int64); begin = np.zeros(world + 1, dtype=np.int64)
+        self._chk(self.lib.lb200_shard_job(self.h, n, a.ctypes.data, b.ctypes.data, world, None, order.ctypes.data, begin.ctypes.data))
+        return [order[begin[r]:begin[r + 1]] for r in range(world)]
+
+    def scores_np(self):
+        """Scores as an int64 numpy array; SCORE_NEG_INF marks -inf."""
+        import numpy as np
+        n = self.num_pairs()
+        out = np.empty(max(n, 1), dtype=np.int64)
+        self._chk(self.lib.lb200_get_scores(self.h, out.ctypes.data_as(C.POINTER(C.c_int64)), n))
+        return out[:n]
 
     def add_pair(self, a: int, b: int, band=None) -> int:
         if band is None:

@@ -49,4 +49,20 @@ struct DevCtx {
     const uint2 *ent8_tl;
 };
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device, per-function MAXIMUM; contexts on several host threads configure the
+// same kernels with different sizes, so a family only ever raises its value (never below what another context is about to launch with).
+#include <map>
+#include <mutex>
+#include <utility>
+inline int lb200_sticky_smem(int family, int smem_bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, int> seen;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    int &m = seen[std::make_pair(dev, family)];
+    if (smem_bytes > m) m = smem_bytes;
+    return m;
+}
+
 #endif

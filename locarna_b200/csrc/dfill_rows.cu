@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(32, 18) dfill_rows_kernel(DevCtx c, RowsCtx r,
 int rows_smem_bytes(const RowsCtx &r) { return 64 * 4 + r.acc_words * 4 + LB_ROWS_TG * 4 + r.colw_words * 4 + r.rowcode_bytes; }
 
 cudaError_t rows_configure(int smem_bytes, int *ctas_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(dfill_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(dfill_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lb200_sticky_smem(100, smem_bytes));
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, dfill_rows_kernel, 32, smem_bytes);
     return e;
 }

@@ -1319,9 +1319,10 @@ void launch_trace_sl(const DevCtx &c, int grid, int smem_bytes, int pair_begin, 
     else trace_sl_kernel<false><<<grid, 32, smem_bytes, st>>>(c, pair_begin, pair_end, cursor);
 }
 cudaError_t configure_sl(int smem_bytes, int *ctas_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(dfill_sl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(trace_sl_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(trace_sl_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    const int cap = lb200_sticky_smem(200, smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(dfill_sl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(trace_sl_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(trace_sl_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, dfill_sl_kernel, 32, smem_bytes);
     return e;
 }
@@ -1345,7 +1346,8 @@ void launch_trace(const DevCtx &c, int ncmax, bool generic_borders, int grid, in
 }
 cudaError_t configure_kernels(int ncmax, int smem_bytes, int *dfill_ctas_per_sm) {
     cudaError_t e = cudaSuccess;
-#define SET(K) if (e == cudaSuccess) e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)
+    const int cap = lb200_sticky_smem(ncmax, smem_bytes);
+#define SET(K) if (e == cudaSuccess) e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, cap)
 #define CALL(N)                                                                                                         \
     SET((dfill_kernel<N, true>)); SET((dfill_kernel<N, false>)); SET((dfill_dep_kernel<N, true>)); SET((dfill_dep_kernel<N, false>)); SET((toplevel_kernel<N, true>)); SET((toplevel_kernel<N, false>)); \
     SET((trace_kernel<N, true, true>)); SET((trace_kernel<N, false, true>)); SET((trace_kernel<N, true, false>)); SET((trace_kernel<N, false, false>)); \

@@ -246,8 +246,9 @@ cudaError_t configure_pf(int ncmax, int smem_bytes, int *ctas_per_sm) {
     cudaError_t e = cudaSuccess;
 #define LB_PF_SET(N)                                                                                                            \
     do {                                                                                                                        \
-        e = cudaFuncSetAttribute(pfill_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);                      \
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ptop_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); \
+        const int cap = lb200_sticky_smem(300 + N, smem_bytes);                                                                 \
+        e = cudaFuncSetAttribute(pfill_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);                            \
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ptop_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);       \
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, pfill_kernel<N>, 32, smem_bytes);   \
     } while (0)
     if (ncmax <= 1) LB_PF_SET(1); else if (ncmax <= 2) LB_PF_SET(2); else if (ncmax <= 4) LB_PF_SET(4); else LB_PF_SET(8);

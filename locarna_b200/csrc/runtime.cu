@@ -12,6 +12,8 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "../../include/locarna_b200.h"
@@ -259,6 +261,22 @@ void lb200_default_params(lb200_params *p) {
     p->exp_prob = -1.0; p->max_bp_span = -1;
 }
 
+// cudaGetDeviceProperties takes milliseconds; a job creates a context per run (all-vs-all stage), so ask once per device and process
+static cudaError_t cached_device_properties(cudaDeviceProp *out, int device) {
+    static std::mutex mu;
+    static std::map<int, cudaDeviceProp> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(device);
+    if (it == cache.end()) {
+        cudaDeviceProp p;
+        const cudaError_t e = cudaGetDeviceProperties(&p, device);
+        if (e != cudaSuccess) return e;
+        it = cache.emplace(device, p).first;
+    }
+    *out = it->second;
+    return cudaSuccess;
+}
+
 int lb200_ctx_create(int device, lb200_ctx **out) {
     if (!out) return LB200_ERR_ARG;
     *out = nullptr;
@@ -283,7 +301,7 @@ int lb200_ctx_create(int device, lb200_ctx **out) {
     if (device < 0 || device >= ndev) return LB200_ERR_ARG;
     lb200_ctx *c = new lb200_ctx();
     c->device = device;
-    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&c->prop, device) != cudaSuccess ||
+    if (cudaSetDevice(device) != cudaSuccess || cached_device_properties(&c->prop, device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess ||
         cudaEventCreate(&c->ev1) != cudaSuccess || cudaEventCreate(&c->ev_mid) != cudaSuccess) {
         fprintf(stderr, "locarna_b200: cannot initialise device %d: %s\n", device, cudaGetErrorString(cudaGetLastError()));
@@ -328,8 +346,9 @@ int lb200_seq_add_pp(lb200_ctx *c, const char *path) {
     return (int)c->seqs.size() - 1;
 }
 
-// parallel_for is defined below
+// parallel_for / parallel_blocks are defined below
 static void parallel_for(int n, int threads, const std::function<void(int)> &fn);
+static void parallel_blocks(int n, int threads, const std::function<void(int, int)> &fn);
 
 int lb200_seqs_add_pp(lb200_ctx *c, int n, const char *const *paths) {
     if (!c || n < 0 || (n > 0 && !paths)) return LB200_ERR_ARG;
@@ -366,6 +385,21 @@ int lb200_seq_length(const lb200_ctx *c, int seq) {
 int lb200_seq_num_arcs(const lb200_ctx *c, int seq) {
     if (!c || seq < 0 || seq >= (int)c->seqs.size()) return LB200_ERR_ARG;
     return (int)c->seqs[seq].arcs.size();
+}
+
+// cost-balanced split of a pair list over `world` shares from the context's own sequences (lb200_pair_cost + lb200_shard_pairs in one call)
+int lb200_shard_job(const lb200_ctx *c, int64_t n_pairs, const int *seqA, const int *seqB, int world, int *rank_of, int64_t *order, int64_t *rank_begin) {
+    if (!c || n_pairs < 0 || world < 1 || (n_pairs > 0 && (!seqA || !seqB))) return LB200_ERR_ARG;
+    const int ns = (int)c->seqs.size();
+    std::vector<double> cost((size_t)n_pairs);
+    for (int64_t k = 0; k < n_pairs; k++) {
+        const int a = seqA[k], b = seqB[k];
+        if (a < 0 || a >= ns || b < 0 || b >= ns) return LB200_ERR_ARG;
+        cost[(size_t)k] = lb200_pair_cost((int)c->seqs[a].arcs.size(), (int)c->seqs[b].arcs.size(), c->seqs[a].len, c->seqs[b].len);
+    }
+    std::vector<int> tmp_rank;
+    if (!rank_of) { tmp_rank.resize((size_t)std::max<int64_t>(n_pairs, 1)); rank_of = tmp_rank.data(); }
+    return lb200_shard_pairs(n_pairs, cost.data(), world, rank_of, order, rank_begin);
 }
 
 int lb200_seq_get(const lb200_ctx *c, int seq, char *name, int name_cap, char *sequence, int sequence_cap) {
@@ -432,6 +466,19 @@ static void parallel_for(int n, int threads, const std::function<void(int)> &fn)
     std::vector<std::thread> pool;
     for (int t = 0; t < threads; t++)
         pool.emplace_back([&]() { for (int i = next++; i < n; i = next++) fn(i); });
+    for (auto &t : pool) t.join();
+}
+
+// contiguous index blocks [begin, end) on the host threads: for per-item work of a few microseconds
+static void parallel_blocks(int n, int threads, const std::function<void(int, int)> &fn) {
+    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    threads = std::max(1, std::min(threads, (n + 63) / 64));
+    if (threads == 1) { if (n > 0) fn(0, n); return; }
+    const int block = std::max(16, (n + threads * 4 - 1) / (threads * 4));
+    std::atomic<int> next(0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++)
+        pool.emplace_back([&]() { for (int b = next.fetch_add(block); b < n; b = next.fetch_add(block)) fn(b, std::min(n, b + block)); });
     for (auto &t : pool) t.join();
 }
 
@@ -506,16 +553,27 @@ static int derive_bands(lb200_ctx *c) {
         std::vector<EnvPair> ep(todo.size());
         std::vector<int> lo, hi;
         size_t max_cells = 1;
-        for (size_t t = 0; t < todo.size(); t++) {
-            PairRec &r = c->pairs[todo[t]];
-            const Sequence &A = c->seqs[r.seqA], &B = c->seqs[r.seqB];
-            r.band = make_band(A.len, B.len, c->params.max_diff);
-            EnvPair &e = ep[t];
-            e.lenA = A.len; e.lenB = B.len; e.codesA = c->seq_codes_off[r.seqA]; e.codesB = c->seq_codes_off[r.seqB];
-            e.probA = c->seq_prob_off[r.seqA]; e.probB = c->seq_prob_off[r.seqB]; e.band = (int)lo.size(); e.pad = 0;
-            lo.insert(lo.end(), r.band.lo.begin(), r.band.lo.end());
-            hi.insert(hi.end(), r.band.hi.begin(), r.band.hi.end());
-            max_cells = std::max(max_cells, (size_t)(A.len + 1) * (B.len + 1));
+        {   // band offsets first (serial, trivial), then the per-pair work on the host threads
+            size_t off = 0;
+            for (size_t t = 0; t < todo.size(); t++) {
+                const PairRec &r = c->pairs[todo[t]];
+                const Sequence &A = c->seqs[r.seqA], &B = c->seqs[r.seqB];
+                ep[t].band = (int)off; off += (size_t)A.len + 1;
+                max_cells = std::max(max_cells, (size_t)(A.len + 1) * (B.len + 1));
+            }
+            lo.resize(off); hi.resize(off);
+            parallel_blocks((int)todo.size(), c->host_threads, [&](int t0, int t1) {
+                for (int t = t0; t < t1; t++) {
+                    PairRec &r = c->pairs[todo[t]];
+                    const Sequence &A = c->seqs[r.seqA], &B = c->seqs[r.seqB];
+                    r.band = make_band(A.len, B.len, c->params.max_diff);
+                    EnvPair &e = ep[t];
+                    e.lenA = A.len; e.lenB = B.len; e.codesA = c->seq_codes_off[r.seqA]; e.codesB = c->seq_codes_off[r.seqB];
+                    e.probA = c->seq_prob_off[r.seqA]; e.probB = c->seq_prob_off[r.seqB]; e.pad = 0;
+                    std::copy(r.band.lo.begin(), r.band.lo.end(), lo.begin() + e.band);
+                    std::copy(r.band.hi.begin(), r.band.hi.end(), hi.begin() + e.band);
+                }
+            });
         }
         // eight resident CTAs per SM (envelope.cu); the partition-function scratch takes at most 4 GB and at most a quarter of
         // the memory that is free right now
@@ -547,15 +605,17 @@ static int derive_bands(lb200_ctx *c) {
         CUDA_TRY(c, cudaMemcpyAsync(ohi.data(), c->d_env_ohi.p, lo.size() * 4, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(c, cudaMemcpyAsync(flag.data(), c->d_env_flag.p, todo.size() * 4, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(c, cudaStreamSynchronize(st));
-        for (size_t t = 0; t < todo.size(); t++) {
-            if (flag[t] != 0) continue;  // uncertain: exact host computation below
-            PairRec &r = c->pairs[todo[t]];
-            std::copy(olo.begin() + ep[t].band, olo.begin() + ep[t].band + ep[t].lenA + 1, r.band.lo.begin());
-            std::copy(ohi.begin() + ep[t].band, ohi.begin() + ep[t].band + ep[t].lenA + 1, r.band.hi.begin());
-            r.banded = true;
-            on_host[t] = 0;
-            c->env_device_pairs++;
-        }
+        parallel_blocks((int)todo.size(), c->host_threads, [&](int t0, int t1) {
+            for (int t = t0; t < t1; t++) {
+                if (flag[t] != 0) continue;  // uncertain: exact host computation below
+                PairRec &r = c->pairs[todo[t]];
+                std::copy(olo.begin() + ep[t].band, olo.begin() + ep[t].band + ep[t].lenA + 1, r.band.lo.begin());
+                std::copy(ohi.begin() + ep[t].band, ohi.begin() + ep[t].band + ep[t].lenA + 1, r.band.hi.begin());
+                r.banded = true;
+                on_host[t] = 0;
+            }
+        });
+        for (size_t t = 0; t < todo.size(); t++) c->env_device_pairs += on_host[t] ? 0 : 1;
     }
     parallel_for((int)todo.size(), c->host_threads, [&](int t) {
         if (!on_host[t]) return;
@@ -600,58 +660,72 @@ static int upload_chunk(lb200_ctx *c, int p0, int p1) {
     std::vector<int> h_lo, h_hi, h_rev, h_cfirst, h_clast;
     long long total_cells = 0, sptr_total = 0;
     int wd_bound = 1, max_rows = 1, max_cols = 1, max_box_words = 1, max_active = 0;
-    for (int k = 0; k < P; k++) {
-        PairRec &r = c->pairs[p0 + k];
-        DevPair &d = h_pairs[k];
-        memset(&d, 0, sizeof d);
-        const int n = c->seqs[r.seqA].len, m = c->seqs[r.seqB].len;
-        d.lenA = n; d.lenB = m;
-        d.codesA = c->seq_codes_off[r.seqA]; d.codesB = c->seq_codes_off[r.seqB];
-        d.arcsA = c->seq_arcs_off[r.seqA]; d.arcsB = c->seq_arcs_off[r.seqB];
-        d.lptrA = c->seq_lptr_off[r.seqA]; d.lptrB = c->seq_lptr_off[r.seqB];
-        d.band = (int)h_lo.size();
-        h_lo.insert(h_lo.end(), r.band.lo.begin(), r.band.lo.end());
-        h_hi.insert(h_hi.end(), r.band.hi.begin(), r.band.hi.end());
-        // cells (al, bl), al >= 1, bl >= 1, ranked al descending / bl descending; diagonal bound of any box
-        h_rev.resize(h_lo.size());
-        int cells = 0, dmin = 0, dmax = 0;
-        for (int i = n; i >= 0; i--) {
-            h_rev[d.band + i] = cells;
-            if (i >= 1) cells += std::max(0, std::min(r.band.hi[i], m) - std::max(r.band.lo[i], 1) + 1);
-            dmin = std::min(dmin, r.band.lo[i] - i); dmax = std::max(dmax, r.band.hi[i] - i);
+    {   // offsets first (serial, trivial), the O(n + m) work per pair on the host threads, then the reductions
+        size_t band_total = 0;
+        for (int k = 0; k < P; k++) {
+            const PairRec &r = c->pairs[p0 + k];
+            const int n = c->seqs[r.seqA].len, m = c->seqs[r.seqB].len;
+            DevPair &d = h_pairs[k];
+            memset(&d, 0, sizeof d);
+            d.band = (int)band_total; band_total += (size_t)n + 1;
+            d.sptr = (int)sptr_total; sptr_total += n + m + 3;
         }
-        d.n_cells = cells;
-        d.cell_base = total_cells; total_cells += cells;
-        d.sptr = (int)sptr_total; sptr_total += n + m + 3;
-        // column view of the band for the row-grouped sweep: rows [first, last] of every column (empty: first > last), and the largest
-        // number of columns an anti-diagonal of the band crosses
-        h_cfirst.resize((size_t)sptr_total, 1 << 20); h_clast.resize((size_t)sptr_total, -1);
-        {
-            int *cf = h_cfirst.data() + d.sptr, *cl = h_clast.data() + d.sptr;
-            // the band is monotone: row i is the first row of the columns beyond hi[i-1] and the last row of the columns before lo[i+1]
-            int prev_hi = -1, next_lo = m + 1;
-            for (int i = 0; i <= n; i++) {
-                const int h = std::min(r.band.hi[i], m);
-                for (int j = std::max(std::max(r.band.lo[i], 0), prev_hi + 1); j <= h; j++) cf[j] = i;
-                prev_hi = std::max(prev_hi, h);
+        h_lo.resize(band_total); h_hi.resize(band_total); h_rev.resize(band_total);
+        h_cfirst.assign((size_t)sptr_total, 1 << 20); h_clast.assign((size_t)sptr_total, -1);
+        std::vector<int> p_wd(P), p_active(P);
+        parallel_blocks(P, c->host_threads, [&](int k0, int k1) {
+            for (int k = k0; k < k1; k++) {
+                const PairRec &r = c->pairs[p0 + k];
+                DevPair &d = h_pairs[k];
+                const int n = c->seqs[r.seqA].len, m = c->seqs[r.seqB].len;
+                d.lenA = n; d.lenB = m;
+                d.codesA = c->seq_codes_off[r.seqA]; d.codesB = c->seq_codes_off[r.seqB];
+                d.arcsA = c->seq_arcs_off[r.seqA]; d.arcsB = c->seq_arcs_off[r.seqB];
+                d.lptrA = c->seq_lptr_off[r.seqA]; d.lptrB = c->seq_lptr_off[r.seqB];
+                std::copy(r.band.lo.begin(), r.band.lo.end(), h_lo.begin() + d.band);
+                std::copy(r.band.hi.begin(), r.band.hi.end(), h_hi.begin() + d.band);
+                // cells (al, bl), al >= 1, bl >= 1, ranked al descending / bl descending; diagonal bound of any box
+                int cells = 0, dmin = 0, dmax = 0;
+                for (int i = n; i >= 0; i--) {
+                    h_rev[d.band + i] = cells;
+                    if (i >= 1) cells += std::max(0, std::min(r.band.hi[i], m) - std::max(r.band.lo[i], 1) + 1);
+                    dmin = std::min(dmin, r.band.lo[i] - i); dmax = std::max(dmax, r.band.hi[i] - i);
+                }
+                d.n_cells = cells;
+                p_wd[k] = dmax - dmin + 1;
+                // column view of the band for the row-grouped sweep: rows [first, last] of every column (empty: first > last), and
+                // the largest number of columns an anti-diagonal of the band crosses
+                int *cf = h_cfirst.data() + d.sptr, *cl = h_clast.data() + d.sptr;
+                // the band is monotone: row i is the first row of the columns beyond hi[i-1] and the last row of the columns before lo[i+1]
+                int prev_hi = -1, next_lo = m + 1;
+                for (int i = 0; i <= n; i++) {
+                    const int h = std::min(r.band.hi[i], m);
+                    for (int j = std::max(std::max(r.band.lo[i], 0), prev_hi + 1); j <= h; j++) cf[j] = i;
+                    prev_hi = std::max(prev_hi, h);
+                }
+                for (int i = n; i >= 0; i--) {
+                    const int l = std::max(r.band.lo[i], 0);
+                    for (int j = l; j <= std::min(std::min(r.band.hi[i], m), next_lo - 1); j++) cl[j] = i;
+                    next_lo = std::min(next_lo, l);
+                }
+                int j2 = 0, active = 0;
+                for (int j = 0; j <= m; j++) {
+                    if (cl[j] < cf[j]) continue;
+                    if (j2 < j) j2 = j;
+                    while (j2 + 1 <= m && cl[j2 + 1] >= cf[j2 + 1] && cf[j2 + 1] + j2 + 1 <= cl[j] + j) j2++;
+                    active = std::max(active, j2 - j + 1);
+                }
+                p_active[k] = active;
             }
-            for (int i = n; i >= 0; i--) {
-                const int l = std::max(r.band.lo[i], 0);
-                for (int j = l; j <= std::min(std::min(r.band.hi[i], m), next_lo - 1); j++) cl[j] = i;
-                next_lo = std::min(next_lo, l);
-            }
-            int j2 = 0;
-            for (int j = 0; j <= m; j++) {
-                if (cl[j] < cf[j]) continue;
-                if (j2 < j) j2 = j;
-                while (j2 + 1 <= m && cl[j2 + 1] >= cf[j2 + 1] && cf[j2 + 1] + j2 + 1 <= cl[j] + j) j2++;
-                max_active = std::max(max_active, j2 - j + 1);
-            }
+        });
+        for (int k = 0; k < P; k++) {
+            DevPair &d = h_pairs[k];
+            d.cell_base = total_cells; total_cells += d.n_cells;
+            max_active = std::max(max_active, p_active[k]);
+            wd_bound = std::max(wd_bound, p_wd[k]);
+            max_box_words = std::max(max_box_words, (d.lenA + d.lenB + 1) * ((((p_wd[k] + 1) / 2) + 3) & ~3));  // anti-diagonal major box, row stride: diagonal pairs rounded up to 4
+            max_rows = std::max(max_rows, d.lenA + 1); max_cols = std::max(max_cols, d.lenB + 1);
         }
-        const int wd = dmax - dmin + 1;
-        wd_bound = std::max(wd_bound, wd);
-        max_box_words = std::max(max_box_words, (n + m + 1) * ((((wd + 1) / 2) + 3) & ~3));  // row stride: diagonal pairs rounded up to 4  // anti-diagonal major box
-        max_rows = std::max(max_rows, n + 1); max_cols = std::max(max_cols, m + 1);
     }
     if (total_cells >= (1LL << 31) - 2) return fail(c, LB200_ERR_UNSUPPORTED, "batch too large (%lld band cells); split it", total_cells);
 

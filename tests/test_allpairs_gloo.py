@@ -42,7 +42,12 @@ WORKER = textwrap.dedent("""
     flags = {"noLP": True, "max-diff-am": 30}
     sc = [O.port_align(paths[pairs[k][0]], paths[pairs[k][1]], flags, do_trace=False)["score"] for k in mine]
     full = allpairs.gather_scores(dist, mine, sc, len(pairs))
+    # the vectorised variant bench.py uses: share sizes are known to every rank, so the gather is the only collective
+    import numpy as np
+    shares = allpairs.shard_pairs(pairs, costs, world)
+    full_np = allpairs.gather_scores_np(dist, np.array(mine, dtype=np.int64), np.array(sc, dtype=np.int64), len(pairs), max(len(x) for x in shares))
     if rank == 0:
+        assert full_np.tolist() == full
         print("SCORES " + json.dumps(full))
     dist.destroy_process_group()
 """)
@@ -64,3 +69,20 @@ def test_two_rank_gather_matches_single_process(synth_dir, tmp_path):
     flags = {"noLP": True, "max-diff-am": 30}
     want = [O.port_align(paths[a], paths[b], flags, do_trace=False)["score"] for a, b in pairs]
     assert got == want
+
+
+def test_shard_job_from_context_equals_cost_then_shard(synth_dir):
+    """lb200_shard_job (costs from the context's sequences + LPT in one C call) = pair_cost + shard_pairs."""
+    import numpy as np
+    from locarna_b200 import capi
+    paths = synth_dir["short"][:6]
+    ctx = capi.Context(capi.DEVICE_NONE, {"noLP": True})
+    first = ctx.add_pps(paths)
+    pairs = allpairs.all_vs_all(len(paths))
+    a = np.array([p[0] for p in pairs], dtype=np.int32) + first
+    b = np.array([p[1] for p in pairs], dtype=np.int32) + first
+    costs = [allpairs.pair_cost(ctx.seq_num_arcs(x), ctx.seq_num_arcs(y), ctx.seq_length(x), ctx.seq_length(y)) for x, y in zip(a, b)]
+    for world in (1, 2, 3):
+        got = [list(map(int, x)) for x in ctx.shard_job(a, b, world)]
+        assert got == allpairs.shard_pairs(pairs, costs, world)
+    ctx.close()

@@ -1,18 +1,28 @@
-import sys, time, os
-sys.path.insert(0,'/root/repo')
+"""Phase times of one end-to-end job as bench.py's e2e leg runs it (development aid, not a benchmark).
+usage: [LB200_TIMING=1] python tools/e2e_phases.py [world]   -- times rank 0's share of a `world`-way split on one GPU"""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
 import bench
 from locarna_b200 import capi
-args=bench.parse_args(["--job-pairs","16384"])
-pl=bench.plan(args,1); pairs=pl["pairs"]
-paths=bench.make_inputs(512,300,16)
-def T(): return time.time()
-for it in range(3):
-    t0=T(); ctx=capi.Context(0,bench.FLAGS); t1=T()
-    first=ctx.add_pps(paths); t2=T()
-    n_arcs=[ctx.seq_num_arcs(first+s) for s in range(512)]; lengths=[ctx.seq_length(first+s) for s in range(512)]
-    mine=bench.shard_job(pairs,n_arcs,lengths,1)[0]; t3=T()
-    ctx.add_pairs([(first+pairs[k][0],first+pairs[k][1]) for k in mine]); t4=T()
-    ctx.run(); t5=T()
-    sc=ctx.scores(); t6=T()
-    ctx.close(); t7=T()
-    print("ctx %.3f parse %.3f shard %.3f addpairs %.3f run %.3f scores %.3f close %.3f total %.3f kernel_ms %.1f"%(t1-t0,t2-t1,t3-t2,t4-t3,t5-t4,t6-t5,t7-t6,t7-t0,ctx_k if False else 0))
+
+world = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+args = bench.parse_args(["--job-pairs", "16384"])
+pairs = bench.plan(args, world)["pairs"]
+paths = bench.make_inputs(512, 300, 16)
+pa = np.array([p[0] for p in pairs], dtype=np.int32)
+pb = np.array([p[1] for p in pairs], dtype=np.int32)
+for it in range(4):
+    t0 = time.time(); ctx = capi.Context(0, bench.FLAGS); t1 = time.time()
+    first = ctx.add_pps(paths); t2 = time.time()
+    mine = ctx.shard_job(pa + first, pb + first, world)[0]; t3 = time.time()
+    ctx.add_pairs_np(pa[mine] + first, pb[mine] + first); t4 = time.time()
+    ctx.run(); t5 = time.time()
+    sc = ctx.scores_np(); t6 = time.time()
+    ctx.close(); t7 = time.time()
+    print("pairs %d: ctx %.4f parse %.4f shard %.4f addpairs %.4f run %.4f scores %.4f close %.4f total %.4f" % (
+        len(mine), t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, t6 - t5, t7 - t6, t7 - t0))
