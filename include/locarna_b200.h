@@ -140,6 +140,17 @@ int lb200_run(lb200_ctx *ctx, int flags);
  * the alignment. Not available with struct_local. */
 int lb200_run_normalized(lb200_ctx *ctx, int64_t L);
 int lb200_run_penalized(lb200_ctx *ctx, int64_t position_penalty);
+/* Restriction of a pair's top level to rows startA..endA and columns startB..endB (AlignerRestriction, aligner_restriction.hh:26-130;
+ * Aligner::set_restriction, aligner.cc:1368-1376); (1, 1, lenA, lenB) lifts it. It applies to lb200_run_pair_toplevel. */
+int lb200_pair_set_restriction(lb200_ctx *ctx, int pair, int startA, int startB, int endA, int endB);
+/* Aligner::align (+ trace with LB200_RUN_TRACE) of ONE pair on the D table that is already filled - the D fill runs only if no table is
+ * resident (AlignerImpl::D_created_, aligner.cc:924-962) - under the pair's restriction. mode: LB200_TOP_PLAIN, LB200_TOP_NORMALIZED
+ * (arg = L) or LB200_TOP_PENALIZED (arg = position penalty). This is what k-best alignment by interval splitting (Aligner::suboptimal,
+ * aligner.cc:1383-1514; include/locarna_b200.hh) calls per task. */
+#define LB200_TOP_PLAIN 0
+#define LB200_TOP_NORMALIZED 1
+#define LB200_TOP_PENALIZED 2
+int lb200_run_pair_toplevel(lb200_ctx *ctx, int pair, int mode, int64_t arg, int flags);
 /* device time of the last lb200_run's kernels (CUDA events on the launching stream), milliseconds */
 double lb200_last_kernel_ms(const lb200_ctx *ctx);
 /* host->device bytes of the last lb200_upload (0 if lb200_run found the batch resident) and device->host bytes of the last lb200_run */

@@ -22,6 +22,7 @@
 #include <ostream>
 #include <string>
 #include <utility>
+#include <queue>
 #include <vector>
 
 #include "locarna_b200.h"
@@ -45,6 +46,8 @@ public:
     bool is_neg_infty() const { return neg_inf_; }
     bool is_finite() const { return !neg_inf_; }
     long finite_value() const { return val_; }
+    //! order of the reference's InftyInt (infty_int.hh:419-447): -inf below every finite value
+    bool operator<(const infty_score_t &o) const { return neg_inf_ ? !o.neg_inf_ : (!o.neg_inf_ && val_ < o.val_); }
 };
 inline std::ostream &operator<<(std::ostream &out, const infty_score_t &s) {  // infty_int.cc:33-43
     if (s.is_neg_infty()) return out << "-inf";
@@ -222,6 +225,24 @@ public:
     }
 };
 
+//! Restriction of the top level to subsequences (aligner_restriction.hh:26-130)
+class AlignerRestriction {
+    int startA_, startB_, endA_, endB_;
+public:
+    AlignerRestriction(int startA, int startB, int endA, int endB) : startA_(startA), startB_(startB), endA_(endA), endB_(endB) {}
+    size_t startA() const { return startA_; }
+    size_t endA() const { return endA_; }
+    size_t startB() const { return startB_; }
+    size_t endB() const { return endB_; }
+    void set_startA(size_t p) { startA_ = (int)p; }
+    void set_endA(size_t p) { endA_ = (int)p; }
+    void set_startB(size_t p) { startB_ = (int)p; }
+    void set_endB(size_t p) { endB_ = (int)p; }
+};
+inline std::ostream &operator<<(std::ostream &out, const AlignerRestriction &r) {   // aligner_restriction.hh:137-141
+    return out << r.startA() << " " << r.startB() << " " << r.endA() << " " << r.endB();
+}
+
 class AlignerParams {  // aligner_params.hh:51-115: same argument names, chained setters instead of named-argument objects
     friend class Aligner;
     const RnaData *rnaA_ = nullptr, *rnaB_ = nullptr;
@@ -252,7 +273,8 @@ public:
 class Aligner {  // aligner.hh:67-189
     std::shared_ptr<Context> ctx_;
     int pair_ = -1;
-    bool traced_ = false, have_ams_ = false;
+    bool traced_ = false, have_ams_ = false, restricted_ = false;
+    AlignerRestriction r_{1, 1, 0, 0};
     Alignment alignment_;
     ArcMatches ams_;
 public:
@@ -287,24 +309,84 @@ public:
         ctx_->check(lb200_seq_get(ctx_->get(), a, name, sizeof name, seq, seq_cap)); alignment_.nameA_ = name; alignment_.seqA_ = seq;
         ctx_->check(lb200_seq_get(ctx_->get(), b, name, sizeof name, seq, seq_cap)); alignment_.nameB_ = name; alignment_.seqB_ = seq;
         delete[] seq;
+        r_ = AlignerRestriction(1, 1, la, lb);
     }
-    //! compute the alignment score (aligner.cc:924-962)
+    //! compute the alignment score (aligner.cc:924-962); under a restriction only the top level is redone on the filled D table
     infty_score_t align() {
-        ctx_->check(lb200_run(ctx_->get(), LB200_RUN_TRACE));
+        if (restricted_) ctx_->check(lb200_run_pair_toplevel(ctx_->get(), pair_, LB200_TOP_PLAIN, 0, LB200_RUN_TRACE));
+        else ctx_->check(lb200_run(ctx_->get(), LB200_RUN_TRACE));
         traced_ = true;
-        int64_t sc = 0;
-        ctx_->check(lb200_pair_score(ctx_->get(), pair_, &sc));
-        return sc == LB200_SCORE_NEG_INF ? infty_score_t::neg_infty_value() : infty_score_t((long)sc);
+        return result_score();
     }
     //! normalized local alignment by Dinkelbach's algorithm (aligner.cc:1522-1597); returns the normalized score, the alignment is traced
     infty_score_t normalized_align(long L, bool /*verbose*/ = false) {
-        ctx_->check(lb200_run_normalized(ctx_->get(), (int64_t)L));
+        if (restricted_) ctx_->check(lb200_run_pair_toplevel(ctx_->get(), pair_, LB200_TOP_NORMALIZED, (int64_t)L, LB200_RUN_TRACE));
+        else ctx_->check(lb200_run_normalized(ctx_->get(), (int64_t)L));
         return modified_result();
     }
     //! alignment with every aligned position penalized (aligner.cc:1599-1622); returns the penalized score, the alignment is traced
     infty_score_t penalized_align(long position_penalty) {
-        ctx_->check(lb200_run_penalized(ctx_->get(), (int64_t)position_penalty));
+        if (restricted_) ctx_->check(lb200_run_pair_toplevel(ctx_->get(), pair_, LB200_TOP_PENALIZED, (int64_t)position_penalty, LB200_RUN_TRACE));
+        else ctx_->check(lb200_run_penalized(ctx_->get(), (int64_t)position_penalty));
         return modified_result();
+    }
+    //! restrict the top level to subsequences (aligner.cc:1368-1376); the D table is not affected
+    void set_restriction(const AlignerRestriction &r) {
+        ctx_->check(lb200_pair_set_restriction(ctx_->get(), pair_, (int)r.startA(), (int)r.startB(), (int)r.endA(), (int)r.endB()));
+        r_ = r;
+        restricted_ = true;
+    }
+    const AlignerRestriction &get_restriction() const { return r_; }
+    //! k-best alignments by interval splitting (aligner.cc:1383-1514): same task queue, same splits, same output
+    void suboptimal(int k, long threshold, bool normalized, long normalized_L, size_t /*output_width*/, bool verbose, bool /*opt_local_output*/,
+                    bool opt_pos_output, bool /*opt_write_structure*/) {
+        typedef std::pair<AlignerRestriction, infty_score_t> task_t;
+        struct greater_second { bool operator()(const task_t &a, const task_t &b) const { return a.second < b.second; } };   // aligner.hh:34-45
+        Aligner &a = *this;
+        infty_score_t a_score = !normalized ? a.align() : a.normalized_align(normalized_L, false);
+        std::priority_queue<task_t, std::vector<task_t>, greater_second> tasks;
+        tasks.push(task_t(a.get_restriction(), a_score));
+        size_t i = 1;
+        while (k < 0 || i <= (size_t)k) {
+            task_t task = tasks.top();
+            tasks.pop();
+            AlignerRestriction &task_r = task.first;
+            const infty_score_t task_score = task.second;
+            if (task_score < infty_score_t(threshold + 1)) break;
+            a.set_restriction(task_r);
+            if (!normalized) { a.align(); a.trace(); }
+            else a.normalized_align(normalized_L, verbose);
+            Alignment alignment = a.get_alignment();
+            if (alignment.empty()) continue;
+            if (opt_pos_output) {
+                std::cout << "HIT " << task_score << " " << alignment.start_positions().first << " " << alignment.start_positions().first << " "
+                          << alignment.end_positions().second << " " << alignment.end_positions().second << " " << std::endl;
+            } else {
+                MultipleAlignment ma(alignment, true);
+                std::cout << "Score: " << task_score << std::endl;
+                ma.write(std::cout, 120, MultipleAlignment::FormatType::CLUSTAL);
+            }
+            if (!opt_pos_output) std::cout << std::endl << std::endl;
+            if (k >= 0 && i == (size_t)k) break;
+            const size_t lenA = task_r.endA() - task_r.startA(), lenB = task_r.endB() - task_r.startB();
+            AlignerRestriction r1(task_r), r2(task_r);
+            if (lenA > lenB) {
+                const int splitA = (int)((alignment.start_positions().first + alignment.end_positions().first) / 2);
+                if (verbose) std::cout << "Split A at " << splitA << std::endl;
+                r1.set_endA(splitA); r2.set_startA(splitA);
+            } else {
+                const int splitB = (int)((alignment.start_positions().second + alignment.end_positions().second) / 2);
+                if (verbose) std::cout << "Split B at " << splitB << std::endl;
+                r1.set_endB(splitB); r2.set_startB(splitB);
+            }
+            a.set_restriction(r1);
+            const infty_score_t a1_score = !normalized ? a.align() : a.normalized_align(normalized_L, false);
+            a.set_restriction(r2);
+            const infty_score_t a2_score = !normalized ? a.align() : a.normalized_align(normalized_L, false);
+            tasks.push(task_t(r1, a1_score));
+            tasks.push(task_t(r2, a2_score));
+            ++i;
+        }
     }
     //! trace back (aligner.cc:1345-1363); the device already traced during align()
     void trace() {
@@ -320,12 +402,15 @@ public:
     }
     const Alignment &get_alignment() const { return alignment_; }
 private:
-    infty_score_t modified_result() {
-        traced_ = true;
-        trace();
+    infty_score_t result_score() {
         int64_t sc = 0;
         ctx_->check(lb200_pair_score(ctx_->get(), pair_, &sc));
         return sc == LB200_SCORE_NEG_INF ? infty_score_t::neg_infty_value() : infty_score_t((long)sc);
+    }
+    infty_score_t modified_result() {
+        traced_ = true;
+        trace();
+        return result_score();
     }
 public:
     //! arc matches and their scores as built on the device (no alignment is computed: lb200_upload only)

@@ -26,7 +26,7 @@
 //
 // The objects of the reference compute on construction (RnaData parses, ArcMatches enumerates, Scoring precomputes). Here they record
 // their arguments; the device builds bands, arc matches and scores when Aligner runs. What the B200 path does not implement
-// (reference alignments for --max-diff-aln, anchors, MEA, explicit arc-match scores, k-best) throws LocARNA::failure from the object
+// (reference alignments for --max-diff-aln, anchors, MEA, explicit arc-match scores) throws LocARNA::failure from the object
 // that would need it, so the caller's existing error handling applies.
 #ifndef LOCARNA_B200_COMPAT_HH
 #define LOCARNA_B200_COMPAT_HH
@@ -325,7 +325,12 @@ public:
     const Alignment &get_alignment() const { return impl_->get_alignment(); }
     infty_score_t normalized_align(score_t L, bool verbose) { return impl_->normalized_align(L, verbose); }
     infty_score_t penalized_align(score_t position_penalty) { return impl_->penalized_align(position_penalty); }
-    void suboptimal(int, score_t, bool, score_t, size_t, bool, bool, bool, bool) { throw failure("locarna_b200: k-best alignment is not supported"); }
+    void set_restriction(const LocARNA_B200::AlignerRestriction &r) { impl_->set_restriction(r); }
+    const LocARNA_B200::AlignerRestriction &get_restriction() const { return impl_->get_restriction(); }
+    void suboptimal(int k, score_t threshold, bool normalized, score_t normalized_L, size_t output_width, bool verbose, bool opt_local_output,
+                    bool opt_pos_output, bool opt_write_structure) {
+        impl_->suboptimal(k, threshold, normalized, normalized_L, output_width, verbose, opt_local_output, opt_pos_output, opt_write_structure);
+    }
 };
 
 inline void ArcMatches::write_arcmatch_scores(const std::string &file, const Scoring &scoring) const {

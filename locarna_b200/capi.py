@@ -42,7 +42,7 @@ EXPORTS = [
     "lb200_prepare", "lb200_upload", "lb200_run", "lb200_last_kernel_ms", "lb200_last_h2d_bytes", "lb200_last_d2h_bytes", "lb200_last_dfill_ms", "lb200_last_dfill_launches", "lb200_last_launches", "lb200_envelope_stats", "lb200_pair_score", "lb200_get_scores",
     "lb200_pair_get_info", "lb200_pair_band", "lb200_pair_arcmatches", "lb200_pair_alignment", "lb200_upgma_newick",
     "lb200_run_pf", "lb200_pair_partition_function", "lb200_pair_arcmatch_pf", "lb200_run_pf_probs", "lb200_pair_arcmatch_probs",
-    "lb200_pair_basematch_probs", "lb200_pairs_add", "lb200_all_vs_all", "lb200_pair_cost", "lb200_shard_pairs", "lb200_seq_num_arcs", "lb200_seqs_add_pp", "lb200_last_dfill_kind", "lb200_rows_fallbacks", "lb200_release_device_cache", "lb200_run_normalized", "lb200_run_penalized", "lb200_shard_job",
+    "lb200_pair_basematch_probs", "lb200_pairs_add", "lb200_all_vs_all", "lb200_pair_cost", "lb200_shard_pairs", "lb200_seq_num_arcs", "lb200_seqs_add_pp", "lb200_last_dfill_kind", "lb200_rows_fallbacks", "lb200_release_device_cache", "lb200_run_normalized", "lb200_run_penalized", "lb200_shard_job", "lb200_pair_set_restriction", "lb200_run_pair_toplevel",
 ]
 
 _lib = None
@@ -92,6 +92,8 @@ def load():
     lib.lb200_last_kernel_ms.argtypes = [vp]
     lib.lb200_last_kernel_ms.restype = C.c_double
     lib.lb200_shard_job.argtypes = [vp, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.lb200_pair_set_restriction.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.lb200_run_pair_toplevel.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int]
     lib.lb200_run_normalized.argtypes = [vp, C.c_int64]
     lib.lb200_run_penalized.argtypes = [vp, C.c_int64]
     lib.lb200_last_dfill_kind.argtypes = [vp]
@@ -263,6 +265,13 @@ class Context:
     def run_normalized(self, L: int):
         """Normalized local alignment (locarna --normalized L); scores() gives the normalized scores, alignment(k) the alignments."""
         self._chk(self.lib.lb200_run_normalized(self.h, L))
+
+    def set_restriction(self, pair: int, startA: int, startB: int, endA: int, endB: int):
+        self._chk(self.lib.lb200_pair_set_restriction(self.h, pair, startA, startB, endA, endB))
+
+    def run_pair_toplevel(self, pair: int, mode: int = 0, arg: int = 0, flags: int = RUN_TRACE):
+        """Top level (+ trace) of one pair on the resident D table under its restriction (k-best building block)."""
+        self._chk(self.lib.lb200_run_pair_toplevel(self.h, pair, mode, arg, flags))
 
     def run_penalized(self, position_penalty: int):
         self._chk(self.lib.lb200_run_penalized(self.h, position_penalty))

@@ -26,7 +26,7 @@ struct command_line_parameters {   // the fields the pipeline reads (src/locarna
     std::string arcmatch_scores_infile, arcmatch_scores_outfile, matchprobs_outfile, clustal_out;
     int match = 50, mismatch = 0, indel = -150, indel_opening = -750, unpaired_penalty = 0, struct_weight = 200, tau = 50, exclusion = 0;
     int temperature_alipf = 300, max_diff_am = -1, max_diff_at_am = -1, max_diff = -1, max_bp_span = -1, width = 120;
-    int mea_alpha = 0, mea_beta = 200, mea_gamma = 100, probability_scale = 10000, kbest_k = -1, subopt_threshold = 1000000;
+    int mea_alpha = 0, mea_beta = 200, mea_gamma = 100, probability_scale = 10000, kbest_k = -1, subopt_threshold = -1000000;
     long normalized_L = 0, position_penalty = 0;
     double min_prob = 0.001, max_bps_length_ratio = 0.0, exp_prob = 0.0, min_trace_probability = 1e-4;
     bool use_ribosum = true, ribofit = false, exp_prob_given = false, stacking = false, new_stacking = false, no_lonely_pairs = false;
@@ -100,7 +100,7 @@ static int run_and_report() {
 int main(int argc, char **argv) {
     enum { O_INDEL_OPENING = 1000, O_USE_RIBOSUM, O_UNPAIRED_PENALTY, O_STRUCT_LOCAL, O_SEQU_LOCAL, O_FREE_ENDGAPS, O_MAX_DIFF_AT_AM, O_MIN_TRACE_PROB, O_NOLP,
            O_MAXBPSPAN, O_MAX_BPS_LENGTH_RATIO, O_TEMPERATURE_ALIPF, O_CLUSTAL, O_LOCAL_FILE_OUTPUT, O_WRITE_STRUCTURE, O_WRITE_AMS, O_STACKING, O_NORMALIZED,
-           O_PENALIZED, O_KBEST };
+           O_PENALIZED, O_KBEST, O_BETTER };
     static const struct option longopts[] = {
         {"indel", required_argument, 0, 'i'}, {"indel-opening", required_argument, 0, O_INDEL_OPENING}, {"use-ribosum", required_argument, 0, O_USE_RIBOSUM},
         {"match", required_argument, 0, 'm'}, {"mismatch", required_argument, 0, 'M'}, {"unpaired-penalty", required_argument, 0, O_UNPAIRED_PENALTY},
@@ -112,7 +112,7 @@ int main(int argc, char **argv) {
         {"temperature-alipf", required_argument, 0, O_TEMPERATURE_ALIPF}, {"width", required_argument, 0, 'w'}, {"clustal", required_argument, 0, O_CLUSTAL},
         {"local-output", no_argument, 0, 'L'}, {"local-file-output", no_argument, 0, O_LOCAL_FILE_OUTPUT}, {"pos-output", no_argument, 0, 'P'},
         {"write-structure", no_argument, 0, O_WRITE_STRUCTURE}, {"write-arcmatch-scores", required_argument, 0, O_WRITE_AMS}, {"stacking", no_argument, 0, O_STACKING},
-        {"normalized", required_argument, 0, O_NORMALIZED}, {"penalized", required_argument, 0, O_PENALIZED}, {"kbest", required_argument, 0, O_KBEST},
+        {"normalized", required_argument, 0, O_NORMALIZED}, {"penalized", required_argument, 0, O_PENALIZED}, {"kbest", required_argument, 0, O_KBEST}, {"better", required_argument, 0, O_BETTER},
         {"quiet", no_argument, 0, 'q'}, {"verbose", no_argument, 0, 'v'}, {0, 0, 0, 0}};
     int c, idx = 0;
     while ((c = getopt_long(argc, argv, "i:m:M:s:e:t:E:w:Lp:D:d:Pqv", longopts, &idx)) != -1) {
@@ -150,6 +150,7 @@ int main(int argc, char **argv) {
             case O_NORMALIZED: clp.normalized = true; clp.normalized_L = atol(optarg); break;
             case O_PENALIZED: clp.penalized = true; clp.position_penalty = atol(optarg); break;
             case O_KBEST: clp.subopt = true; clp.kbest_k = atoi(optarg); break;
+            case O_BETTER: clp.subopt = true; clp.subopt_threshold = atoi(optarg); break;
             case 'q': clp.quiet = true; break;
             case 'v': clp.verbose = true; break;
             default: return 255;

@@ -43,6 +43,9 @@ struct DevCtx {
     // normalized / penalized alignment (aligner.cc:1522-1622): the TOP LEVEL box is filled and traced with the scoring modified by
     // lambda (sigma - 2 lambda, gap - lambda, D - lambda * arc lengths: aligner_impl.hh:190-275, scoring.cc:77-90); the boxes of the arc
     // matches on the path keep the unmodified scoring
+    // AlignerRestriction (aligner_restriction.hh:26-130; k-best alignment, aligner.cc:1383-1514): the top level covers only
+    // rows r_sa..r_ea and columns r_sb..r_eb (box origin (r_sa - 1, r_sb - 1)); set for single-pair launches only
+    int r_on, r_sa, r_sb, r_ea, r_eb;
     int use_tl;                  // 1: the traceback's top level uses params_tl / ent_tl / ent8_tl
     DevParams params_tl;
     const DevEntry *ent_tl;

@@ -860,39 +860,41 @@ __global__ void __launch_bounds__(32) toplevel_kernel(DevCtx c, int pair_begin, 
         if (t >= pair_end) break;
         const DevPair pr = c.pairs[t];
         BoxGeom g;
-        setup_box2(c, pr, 0, 0, pr.lenA, pr.lenB, g, ws);
+        // the box of the (restricted) top level: origin (sa - 1, sb - 1), last row / column (ea, eb) (aligner.cc:743-745, :832-833)
+        const int n = c.r_on ? c.r_ea : pr.lenA, m = c.r_on ? c.r_eb : pr.lenB;
+        const int sa = c.r_on ? c.r_sa : 1, sb = c.r_on ? c.r_sb : 1, al0 = sa - 1, bl0 = sb - 1;
+        setup_box2(c, pr, al0, bl0, n, m, g, ws);
         if ((g.umax + 1) * g.nslots > c.scratch_words) { if (lane == 0) atomicExch(c.error_flag, 2); continue; }
         if (!run_box<NCMAX, true, CLAMP>(c, pr, g, init, ws, box)) { if (lane == 0) atomicExch(c.error_flag, 1); continue; }
-        const int n = pr.lenA, m = pr.lenB;
         const int *lo = c.band_lo + pr.band, *hi = c.band_hi + pr.band;
         // band cell of the top level box, normalised -inf
         auto cell = [&](int i, int j) -> int {
-            if (j < ((i == 0) ? 0 : lo[i]) || j > min(m, hi[i])) return LB_NEG;
-            const int v = box_get(box, g, i, j);
+            if (j < ((i == al0) ? bl0 : max(lo[i], bl0)) || j > min(m, hi[i])) return LB_NEG;
+            const int v = box_get(box, g, i - al0, j - bl0);
             return v < LB_NEG_LIMIT ? LB_NEG : v;
         };
         // candidates are ranked by (score, earlier position in the reference's scan order)
-        int best = LB_NEG, bi = 0, bj = 0;
+        int best = LB_NEG, bi = al0, bj = bl0;
         long long bkey = 0x7fffffffffffffffLL;  // smaller = earlier in scan order
         auto consider = [&](int v, int i, int j, long long key) {
             if (v > best || (v == best && v > LB_NEG && key < bkey)) { best = v; bi = i; bj = j; bkey = key; }
         };
         if (P.sequ_local) {
-            // first strict maximum in row-major order, initial best 0 at (0,0) (aligner.cc:829-876)
+            // first strict maximum in row-major order, initial best 0 at (sa - 1, sb - 1) (aligner.cc:829-876)
             best = 0; bkey = -1;
-            for (int i = 1; i <= n; i++) {
-                const int jl = max(1, lo[i]), jh = min(m, hi[i]);
-                for (int j = jl + lane; j <= jh; j += 32) consider(cell(i, j), i, j, (long long)i * (m + 1) + j);
+            for (int i = sa; i <= n; i++) {
+                const int jl = max(sb, lo[i]), jh = min(m, hi[i]);
+                for (int j = jl + lane; j <= jh; j += 32) consider(cell(i, j), i, j, (long long)i * (pr.lenB + 1) + j);
             }
         } else if (P.fe_right1 || P.fe_right2) {
             // aligner.cc:775-816: last column scanned by rows first, then the last row by columns; strict >
             if (P.fe_right2) {
-                for (int i = 1 + lane; i <= n; i += 32)
+                for (int i = sa + lane; i <= n; i += 32)
                     if (hi[i] >= m) consider(cell(i, m), i, m, (long long)i);
             }
             if (P.fe_right1) {
-                const int jl = max(1, lo[n]), jh = min(m, hi[n]);
-                for (int j = jl + lane; j <= jh; j += 32) consider(cell(n, j), n, j, (long long)n + 1 + j);
+                const int jl = max(sb, lo[n]), jh = min(m, hi[n]);
+                for (int j = jl + lane; j <= jh; j += 32) consider(cell(n, j), n, j, (long long)pr.lenA + 1 + j);
             }
         } else {
             if (lane == 0) { best = cell(n, m); bi = n; bj = m; bkey = 0; }
@@ -908,7 +910,7 @@ __global__ void __launch_bounds__(32) toplevel_kernel(DevCtx c, int pair_begin, 
         if (lane == 0) {
             DevTopResult r;
             r.score = best; r.max_i = bi; r.max_j = bj; r.min_ij = 0;
-            if (!P.sequ_local && (P.fe_right1 || P.fe_right2) && best <= LB_NEG_LIMIT) { r.max_i = 0; r.max_j = 0; }
+            if (!P.sequ_local && (P.fe_right1 || P.fe_right2) && best <= LB_NEG_LIMIT) { r.max_i = al0; r.max_j = bl0; }
             c.top[t] = r;
         }
         __syncwarp();
@@ -968,7 +970,8 @@ __global__ void __launch_bounds__(32) trace_kernel(DevCtx c, int pair_begin, int
         const DevTopResult top = c.top[t];
         bool tl = true;
         TraceJob job;
-        job.al = 0; job.bl = 0; job.R = (short)n; job.C = (short)m; job.am = -1;
+        job.al = (short)(c.r_on ? c.r_sa - 1 : 0); job.bl = (short)(c.r_on ? c.r_sb - 1 : 0);
+        job.R = (short)(c.r_on ? c.r_ea : n); job.C = (short)(c.r_on ? c.r_eb : m); job.am = -1;
         bool have = true;
         while (have) {
             BoxGeom g;
@@ -1148,7 +1151,8 @@ __global__ void __launch_bounds__(32) trace_sl_kernel(DevCtx c, int pair_begin, 
         const DevTopResult top = c.top[t];
         bool tl = true;
         TraceJob job;
-        job.al = 0; job.bl = 0; job.R = (short)n; job.C = (short)m; job.am = -1;
+        job.al = (short)(c.r_on ? c.r_sa - 1 : 0); job.bl = (short)(c.r_on ? c.r_sb - 1 : 0);
+        job.R = (short)(c.r_on ? c.r_ea : n); job.C = (short)(c.r_on ? c.r_eb : m); job.am = -1;
         bool have = true;
         while (have) {
             BoxGeom g;

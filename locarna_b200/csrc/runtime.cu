@@ -147,6 +147,7 @@ struct PairRec {
     int64_t score = 0; bool neg_inf = true; int max_i = 0, max_j = 0;
     std::vector<int> edges_a, edges_b; std::string str_a, str_b; bool traced = false;
     double pf_Z = 0; bool pf_done = false;   // LocARNA-P inside
+    bool restricted = false; int r_sa = 1, r_sb = 1, r_ea = 0, r_eb = 0;   // AlignerRestriction of the top level (k-best)
 };
 
 }  // namespace
@@ -183,6 +184,7 @@ struct lb200_ctx {
         unsigned n_groups = 0;
     } res;
     int host_threads = 0;
+    bool d_filled = false;   // the resident chunk's D table is complete (Aligner's D_created_)
     size_t seqs_uploaded = 0;  // sequences whose arrays are on the device
     std::vector<int> seq_codes_off, seq_arcs_off, seq_lptr_off;
     DevBuf d_arc_left, d_arc_right, d_arc_weight, d_arc_sdelta, d_lptr, d_lcount, d_am_seq, d_cell_rev, d_cell_start, d_skeys, d_skeys2, d_svals, d_svals2,
@@ -651,6 +653,7 @@ int lb200_prepare(lb200_ctx *c) {
 static int upload_chunk(lb200_ctx *c, int p0, int p1) {
     const int P = p1 - p0;
     c->res.valid = false;
+    c->d_filled = false;
     if (P <= 0) return LB200_OK;
     { const int rc = upload_sequences(c); if (rc != LB200_OK) return rc; }
     cudaStream_t st = c->stream;
@@ -1102,6 +1105,7 @@ static int run_chunk(lb200_ctx *c, int flags) {
             r.traced = true;
         }
     }
+    c->d_filled = true;
     return LB200_OK;
 }
 
@@ -1161,19 +1165,28 @@ int lb200_pair_band(const lb200_ctx *c, int pair, int *min_col, int *max_col) {
 // lambda differs from pair to pair after the first iteration.
 cudaError_t lb200_adjust_d(const DevEntry *ent, DevEntry *ent_mod, uint2 *ent8_mod, size_t n, int lambda, cudaStream_t st);
 
-static int run_modified(lb200_ctx *c, bool normalized, int64_t arg) {
+// mode 0: plain top level (Aligner::align + trace under a restriction), 1: normalized, 2: penalized; pair < 0: all pairs
+static int run_modified(lb200_ctx *c, int mode, int64_t arg, int pair, bool do_trace) {
+    const bool normalized = mode == 1;
     if (c->device == LB200_DEVICE_NONE) return fail(c, LB200_ERR_CUDA, "host-only context: needs a CUDA device (no CPU fallback)");
-    if (c->params.struct_local) return fail(c, LB200_ERR_UNSUPPORTED, normalized ? "Normalized structure local alignment not supported." : "penalized structure local alignment is not supported");
+    if (c->params.struct_local) return fail(c, LB200_ERR_UNSUPPORTED, normalized ? "Normalized structure local alignment not supported." : mode == 2 ? "penalized structure local alignment is not supported" : "restricted structure local alignment is not supported");
     if (normalized && !c->params.sequ_local) return fail(c, LB200_ERR_ARG, "Cannot run normalized alignment without --sequ_local on.");   // locarna.cc:431-436
-    { const int rc = lb200_run(c, LB200_RUN_SCORE_ONLY); if (rc != LB200_OK) return rc; }       // D fill (aligner.cc:1529-1530, :1607-1608)
     const int P = (int)c->pairs.size();
+    if (pair >= P) return fail(c, LB200_ERR_ARG, "no such pair");
     if (P == 0) return LB200_OK;
     lb200_ctx::Resident &R = c->res;
-    if (!(R.valid && R.p0 == 0 && R.p1 == P)) return fail(c, LB200_ERR_UNSUPPORTED, "normalized / penalized alignment needs the whole batch resident; split the pair list");
+    // D fill (aligner.cc:1529-1530, :1607-1608); the table of an earlier run is kept (D_created_)
+    if (!(R.valid && R.p0 == 0 && R.p1 == P && c->d_filled)) {
+        const int rc = lb200_run(c, LB200_RUN_SCORE_ONLY);
+        if (rc != LB200_OK) return rc;
+    }
+    if (!(R.valid && R.p0 == 0 && R.p1 == P)) return fail(c, LB200_ERR_UNSUPPORTED, "normalized / penalized / restricted alignment needs the whole batch resident; split the pair list");
     cudaStream_t st = c->stream;
-    CUDA_TRY(c, c->d_ent_mod.ensure(std::max<size_t>(R.total_am, 1) * sizeof(DevEntry)));
     const bool packed = R.dc.ent8 != nullptr;
-    if (packed) CUDA_TRY(c, c->d_ent8_mod.ensure(std::max<size_t>(R.total_am, 1) * sizeof(uint2)));
+    if (mode != 0) {
+        CUDA_TRY(c, c->d_ent_mod.ensure(std::max<size_t>(R.total_am, 1) * sizeof(DevEntry)));
+        if (packed) CUDA_TRY(c, c->d_ent8_mod.ensure(std::max<size_t>(R.total_am, 1) * sizeof(uint2)));
+    }
     CUDA_TRY(c, c->d_tr_edges.ensure((size_t)R.sptr_total * 4));
     CUDA_TRY(c, c->d_tr_str.ensure((size_t)R.sptr_total));
     CUDA_TRY(c, c->d_tr_stack.ensure((size_t)P * R.stack_cap * sizeof(TraceJob)));
@@ -1181,7 +1194,7 @@ static int run_modified(lb200_ctx *c, bool normalized, int64_t arg) {
     R.dc.trace_stack = (TraceJob *)c->d_tr_stack.p; R.dc.trace_stack_cap = R.stack_cap;
     int64_t launches = 0;
     CUDA_TRY(c, cudaEventRecord(c->ev0, st));
-    for (int k = 0; k < P; k++) {
+    for (int k = (pair < 0 ? 0 : pair); k < (pair < 0 ? P : pair + 1); k++) {
         PairRec &r = c->pairs[k];
         const int n = c->seqs[r.seqA].len, m = c->seqs[r.seqB].len, off = R.sptr_off[k];
         long new_lambda = normalized ? 0 : (long)arg, lambda = normalized ? -1 : (long)arg - 1;
@@ -1192,27 +1205,35 @@ static int run_modified(lb200_ctx *c, bool normalized, int64_t arg) {
         while (lambda != new_lambda) {
             lambda = new_lambda;
             if (++iterations > 10000) return fail(c, LB200_ERR_STATE, "normalized alignment does not converge");
-            if (lambda > (1 << 20) || lambda < -(1 << 20)) return fail(c, LB200_ERR_UNSUPPORTED, "modification parameter %ld out of the supported range", lambda);
-            // modified scoring of this pair's top level
+            if ((lambda < 0 ? -lambda : lambda) * (long)(n + m + 2) > 50000000L) return fail(c, LB200_ERR_UNSUPPORTED, "modification parameter %ld out of the supported range", lambda);
+            // scoring view of this pair's top level
             DevCtx ct = R.dc;
-            for (int x = 0; x < 64; x++) ct.params.sigma8[x] -= 2 * (int)lambda;
-            ct.params.gap -= (int)lambda;
-            ct.params.gap_open = ct.params.gap + ct.params.open;
-            CUDA_TRY(c, lb200_adjust_d((const DevEntry *)c->d_ent.p + r.am_base, (DevEntry *)c->d_ent_mod.p + r.am_base,
-                                       packed ? (uint2 *)c->d_ent8_mod.p + r.am_base : nullptr, (size_t)r.K, (int)lambda, st));
-            ct.ent = (DevEntry *)c->d_ent_mod.p; ct.ent8 = packed ? (uint2 *)c->d_ent8_mod.p : nullptr;
+            if (r.restricted) { ct.r_on = 1; ct.r_sa = r.r_sa; ct.r_sb = r.r_sb; ct.r_ea = r.r_ea; ct.r_eb = r.r_eb; }
+            if (mode != 0) {
+                for (int x = 0; x < 64; x++) ct.params.sigma8[x] -= 2 * (int)lambda;
+                ct.params.gap -= (int)lambda;
+                ct.params.gap_open = ct.params.gap + ct.params.open;
+                CUDA_TRY(c, lb200_adjust_d((const DevEntry *)c->d_ent.p + r.am_base, (DevEntry *)c->d_ent_mod.p + r.am_base,
+                                           packed ? (uint2 *)c->d_ent8_mod.p + r.am_base : nullptr, (size_t)r.K, (int)lambda, st));
+                ct.ent = (DevEntry *)c->d_ent_mod.p; ct.ent8 = packed ? (uint2 *)c->d_ent8_mod.p : nullptr;
+                launches++;
+            }
             CUDA_TRY(c, cudaMemsetAsync(c->d_cursor.p, 0, 4100 * 4, st));
             CUDA_TRY(c, cudaMemsetAsync(c->d_flag.p, 0, 16, st));
             launch_toplevel(ct, R.nc_inst, 1, R.smem_bytes, k, k + 1, (int *)c->d_cursor.p + 4098, st);
-            DevCtx dt = R.dc;
-            dt.use_tl = 1; dt.params_tl = ct.params; dt.ent_tl = ct.ent; dt.ent8_tl = ct.ent8;
-            launch_trace(dt, R.nc_inst, c->params.indel_opening > 0, 1, R.smem_bytes, k, k + 1, (int *)c->d_cursor.p + 4099, st);
-            launches += 3;
+            launches++;
+            if (do_trace) {
+                DevCtx dt = R.dc;
+                dt.r_on = ct.r_on; dt.r_sa = ct.r_sa; dt.r_sb = ct.r_sb; dt.r_ea = ct.r_ea; dt.r_eb = ct.r_eb;
+                if (mode != 0) { dt.use_tl = 1; dt.params_tl = ct.params; dt.ent_tl = ct.ent; dt.ent8_tl = ct.ent8; }
+                launch_trace(dt, R.nc_inst, c->params.indel_opening > 0, 1, R.smem_bytes, k, k + 1, (int *)c->d_cursor.p + 4099, st);
+                launches++;
+            }
             int h_flag[4] = {0, 0, 0, 0};
             CUDA_TRY(c, cudaMemcpyAsync(&top, (DevTopResult *)c->d_top.p + k, sizeof top, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(c, cudaMemcpyAsync(h_flag, c->d_flag.p, 16, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(c, cudaStreamSynchronize(st));
-            if (h_flag[0] != 0) return fail(c, LB200_ERR_UNSUPPORTED, "kernel reported error %d in the modified top level", h_flag[0]);
+            if (h_flag[0] != 0) return fail(c, LB200_ERR_UNSUPPORTED, "kernel reported error %d in the top level of pair %d", h_flag[0], k);
             if (!normalized) break;
             if (top.score < LB_NEG_LIMIT) return fail(c, LB200_ERR_STATE, "normalized alignment: the local score is -inf");
             // aligner.cc:1566-1575: length of the aligned subsequences from the trace; the modified score plus length * lambda is the
@@ -1222,13 +1243,14 @@ static int run_modified(lb200_ctx *c, bool normalized, int64_t arg) {
             const long score = (long)top.score + (long)(length * (unsigned long)lambda);
             new_lambda = (long)((unsigned long)score / (length + (unsigned long)arg));
         }
-        CUDA_TRY(c, cudaMemcpyAsync(h_edges.data(), (int *)c->d_tr_edges.p + off, ((size_t)n + m + 3) * 4, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(c, cudaMemcpyAsync(h_str.data(), (char *)c->d_tr_str.p + off, (size_t)n + m + 3, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(c, cudaStreamSynchronize(st));
         if (normalized) { r.neg_inf = false; r.score = new_lambda; }                       // aligner.cc:1596
         else { r.neg_inf = top.score < LB_NEG_LIMIT; r.score = r.neg_inf ? 0 : top.score; }
         r.max_i = top.max_i; r.max_j = top.max_j;
-        r.edges_a.clear(); r.edges_b.clear();
+        r.edges_a.clear(); r.edges_b.clear(); r.str_a.clear(); r.str_b.clear(); r.traced = false;
+        if (!do_trace) continue;
+        CUDA_TRY(c, cudaMemcpyAsync(h_edges.data(), (int *)c->d_tr_edges.p + off, ((size_t)n + m + 3) * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaMemcpyAsync(h_str.data(), (char *)c->d_tr_str.p + off, (size_t)n + m + 3, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));
         for (int idx = 0; idx <= n + m; idx++) {
             const int v = h_edges[idx];
             if (v == 0) continue;
@@ -1248,8 +1270,26 @@ static int run_modified(lb200_ctx *c, bool normalized, int64_t arg) {
     return LB200_OK;
 }
 
-int lb200_run_normalized(lb200_ctx *c, int64_t L) { return c ? run_modified(c, true, L) : LB200_ERR_ARG; }
-int lb200_run_penalized(lb200_ctx *c, int64_t position_penalty) { return c ? run_modified(c, false, position_penalty) : LB200_ERR_ARG; }
+int lb200_run_normalized(lb200_ctx *c, int64_t L) { return c ? run_modified(c, 1, L, -1, true) : LB200_ERR_ARG; }
+int lb200_run_penalized(lb200_ctx *c, int64_t position_penalty) { return c ? run_modified(c, 2, position_penalty, -1, true) : LB200_ERR_ARG; }
+
+// AlignerRestriction of a pair's top level (Aligner::set_restriction, aligner.cc:1368-1376); (1, 1, lenA, lenB) lifts it
+int lb200_pair_set_restriction(lb200_ctx *c, int pair, int startA, int startB, int endA, int endB) {
+    if (!c || pair < 0 || pair >= (int)c->pairs.size()) return LB200_ERR_ARG;
+    PairRec &r = c->pairs[pair];
+    const int n = c->seqs[r.seqA].len, m = c->seqs[r.seqB].len;
+    if (startA < 1 || startB < 1 || endA > n || endB > m || startA > endA + 1 || startB > endB + 1) return fail(c, LB200_ERR_ARG, "restriction (%d, %d, %d, %d) outside the sequences", startA, startB, endA, endB);
+    r.restricted = !(startA == 1 && startB == 1 && endA == n && endB == m);
+    r.r_sa = startA; r.r_sb = startB; r.r_ea = endA; r.r_eb = endB;
+    return LB200_OK;
+}
+
+// Aligner::align (+ trace) of ONE pair on the D table that is already filled (aligner.cc:924-962: "alignment needs to be recomputed
+// (this is fast)!", :1426-1431), under the pair's restriction; mode LB200_TOP_PLAIN / _NORMALIZED / _PENALIZED with its parameter
+int lb200_run_pair_toplevel(lb200_ctx *c, int pair, int mode, int64_t arg, int flags) {
+    if (!c || pair < 0 || mode < 0 || mode > 2) return LB200_ERR_ARG;
+    return run_modified(c, mode, arg, pair, (flags & LB200_RUN_TRACE) != 0 || mode == 1);
+}
 
 // ------------------------------------------------------------------------------------------------ LocARNA-P inside
 int lb200_run_pf(lb200_ctx *c, double pf_scale) {

@@ -15,7 +15,8 @@ BIN = os.path.join(ROOT, "locarna_b200", "bin", "locarna_refmain_b200")
 REF = "/root/reference/src/locarna.cc"
 CASES = json.load(open(os.path.join(GOLD, "reference_outputs.json")))["cli"] + [
     c for c in json.load(open(os.path.join(GOLD, "locarna_cli_options.json")))] + [
-    c for c in json.load(open(os.path.join(GOLD, "normalized_outputs.json"))) if c["rc"] == 0 or "simultaneously" not in c["stderr"]]
+    c for c in json.load(open(os.path.join(GOLD, "normalized_outputs.json")))[::3] if c["rc"] == 0 or "simultaneously" not in c["stderr"]] + [
+    dict(c, clustal=None) for c in json.load(open(os.path.join(GOLD, "kbest_outputs.json")))[::3]]   # every third case: the CLI tests run all of them
 
 
 @pytest.mark.skipif(not os.path.exists(REF), reason="the reference tree is only present in the build container")
@@ -56,5 +57,5 @@ def test_refmain_output_matches_reference_binary(case, tmp_path):
     r = subprocess.run([BIN, os.path.join(GOLD, case["A"]), os.path.join(GOLD, case["B"]), "--clustal", clu] + case["args"], capture_output=True, text=True)
     assert r.returncode == case["rc"], r.stderr
     assert r.stdout == case["stdout"]
-    if case["rc"] == 0:
+    if case["rc"] == 0 and case["clustal"] is not None:
         assert open(clu).read() == case["clustal"]

@@ -44,8 +44,20 @@ def test_cli_exp_prob_maxbpspan_arcmatch_scores(case, tmp_path):
 
 
 def test_cli_rejects_unimplemented_modes():
-    r = subprocess.run([CLI, os.path.join(GOLD, "g0.pp"), os.path.join(GOLD, "g1.pp"), "--kbest", "3"], capture_output=True, text=True)
+    r = subprocess.run([CLI, os.path.join(GOLD, "g0.pp"), os.path.join(GOLD, "g1.pp"), "--mea-alignment"], capture_output=True, text=True)
     assert r.returncode == 255 and "does not implement" in r.stderr
+
+
+CASES_KBEST = json.load(open(os.path.join(GOLD, "kbest_outputs.json")))
+
+
+@pytest.mark.parametrize("case", CASES_KBEST, ids=lambda c: "%s-%s" % ("_".join(c["args"]), c["A"]))
+def test_cli_kbest(case):
+    """--kbest k / --better t: k-best alignments by interval splitting (Aligner::suboptimal, aligner.cc:1383-1514; restricted top levels
+    on the resident D table) against the reference binary's stdout (tools/make_golden_kbest.py)."""
+    r = subprocess.run([CLI, os.path.join(GOLD, case["A"]), os.path.join(GOLD, case["B"])] + case["args"], capture_output=True, text=True)
+    assert r.returncode == case["rc"], r.stderr
+    assert r.stdout == case["stdout"]
 
 
 CASES_NORM = json.load(open(os.path.join(GOLD, "normalized_outputs.json")))
