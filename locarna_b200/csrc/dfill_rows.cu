@@ -211,8 +211,8 @@ struct State {
     int jc;                  // first owned column
 };
 
-// One anti-diagonal step. SEED: the origins of the layers are set in the first steps (cell (0, jv) on anti-diagonal jv).
-template <int NC, bool SEED>
+// One anti-diagonal step. The origins of the layers (cell (0, jv) on anti-diagonal jv) are seeded through the accumulators, see sweep().
+template <int NC>
 __device__ __forceinline__ void dp_step(State<NC> &S, const Geom &g, const int *sig, int *arcp, int gap, int gap_open, int left, int u) {
     constexpr int AW = 32 * NC * V;
     int mL0[V], fL0[V];
@@ -250,7 +250,6 @@ __device__ __forceinline__ void dp_step(State<NC> &S, const Geom &g, const int *
             const int ee = addmax(S.e[k][v], gap, S.m[k][v] + gap_open);
             const int ff = addmax(fl, gap, ml + gap_open);
             int mm = max3(addmax(S.md[k][v], sg, ee), ff, arc[k][v]);
-            if (SEED) mm = (u == g.jv[v] && S.jc + k == u) ? 0 : mm;
             nm[v] = ok ? mm : LB_NEG;
             S.m[k][v] = nm[v]; S.e[k][v] = ok ? ee : LB_NEG; S.f[k][v] = ok ? ff : LB_NEG;
             S.md[k][v] = ml;
@@ -341,6 +340,7 @@ __device__ void sweep(const DevCtx &c, const RowsCtx &r, const DevGroup &grp, co
                 if ((gs1 >> 20) > 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(list + (size_t)(gs1 & 0xfffff) * 32));
                 uint2 en = make_uint2(0u, 0u);
                 const uint2 *p = list + (size_t)(gs & 0xfffff) * 32;
+#pragma unroll 1
                 for (int b = 0; b < nb; b++) {
                     if (b == 0) asm volatile("ld.global.ca.v2.u32 {%0, %1}, [%2];" : "=r"(en.x), "=r"(en.y) : "l"(p) : "memory");
                     else en = __ldcg(p + b * 32);
@@ -362,13 +362,21 @@ __device__ void sweep(const DevCtx &c, const RowsCtx &r, const DevGroup &grp, co
     __syncwarp();
     int ringoff = ((s0 + g.u0) & (RING - 1)) * W;
     int u = g.u0;
+    int my_jv = -1;   // lane v seeds layer v
+#pragma unroll
+    for (int v = 0; v < V; v++) if (lane == v) my_jv = g.jv[v];
     for (; u <= g.useed && u <= g.u1; u++) {
-        dp_step<NC, true>(S, g, sm.sig, ap + ringoff, gap, gap_open, left, u);
+        // origin of layer v: M = 0 (init_state, aligner.cc:282). At the origin every other term of the recurrence is -inf for this
+        // layer (nothing of it lies above or to the left, no arc match ends there), so a 0 in its accumulator IS the cell value;
+        // an origin outside the band stays -inf like any out-of-band cell.
+        if (my_jv == u) sm.acc[lane * (RING * W) + ringoff + (u & (W - 1))] = 0;
+        __syncwarp();
+        dp_step<NC>(S, g, sm.sig, ap + ringoff, gap, gap_open, left, u);
         ringoff = (ringoff + W) & (RING * W - 1);
         fold(u);
     }
     for (; u <= g.u1; u++) {
-        dp_step<NC, false>(S, g, sm.sig, ap + ringoff, gap, gap_open, left, u);
+        dp_step<NC>(S, g, sm.sig, ap + ringoff, gap, gap_open, left, u);
         ringoff = (ringoff + W) & (RING * W - 1);
         fold(u);
     }
