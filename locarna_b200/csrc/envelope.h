@@ -21,14 +21,18 @@ struct EnvCtx {
     int *band_lo, *band_hi;       // band before the restriction (--max-diff or unrestricted)
     int *out_lo, *out_hi;         // restricted band
     int *out_flag;                // per pair: 1 = uncertain, recompute on the host in long double
-    double *scratch;              // per CTA 6 matrices of (lenA+1) x (lenB+1) doubles
+    double *scratch;              // per CTA 3 (fallback kernel: 6) matrices of (lenA+1) x (lenB+1) doubles
     size_t scratch_doubles;
     double bm[16];                // base similarity (ribosum base match scores or match/mismatch)
     double sw, open, ext, temp, min_prob;
     int local, fe_left1, fe_right1, fe_left2, fe_right2;
 };
 
-cudaError_t launch_envelope(const EnvCtx &e, int n_pairs, int grid, int *cursor, cudaStream_t st);
+// max_rows / max_cols = longest first / second sequence + 1 of the batch (sizes of the shared-memory buffers)
+cudaError_t launch_envelope(const EnvCtx &e, int n_pairs, int grid, int *cursor, int max_rows, int max_cols, cudaStream_t st);
+int envelope_smem_bytes(int max_rows, int max_cols);
+// doubles of scratch one CTA needs for matrices of max_cells cells (3 forward matrices; 6 for the global-memory fallback)
+size_t envelope_scratch_doubles(size_t max_cells, int max_rows, int max_cols);
 
 }  // namespace lb200
 #endif

@@ -555,6 +555,7 @@ static int derive_bands(lb200_ctx *c) {
         std::vector<EnvPair> ep(todo.size());
         std::vector<int> lo, hi;
         size_t max_cells = 1;
+        int env_rows = 1, env_cols = 1;
         {   // band offsets first (serial, trivial), then the per-pair work on the host threads
             size_t off = 0;
             for (size_t t = 0; t < todo.size(); t++) {
@@ -562,6 +563,7 @@ static int derive_bands(lb200_ctx *c) {
                 const Sequence &A = c->seqs[r.seqA], &B = c->seqs[r.seqB];
                 ep[t].band = (int)off; off += (size_t)A.len + 1;
                 max_cells = std::max(max_cells, (size_t)(A.len + 1) * (B.len + 1));
+                env_rows = std::max(env_rows, A.len + 1); env_cols = std::max(env_cols, B.len + 1);
             }
             lo.resize(off); hi.resize(off);
             parallel_blocks((int)todo.size(), c->host_threads, [&](int t0, int t1) {
@@ -583,7 +585,7 @@ static int derive_bands(lb200_ctx *c) {
         CUDA_TRY(c, cudaMemGetInfo(&free_b, &total_b));
         const size_t scratch_cap = std::min<size_t>((size_t)4 << 30, (free_b + c->d_env_scratch.cap) / 4);
         const int grid = (int)std::min<size_t>(std::min<size_t>(todo.size(), (size_t)c->prop.multiProcessorCount * 8),
-                                                 std::max<size_t>(1, scratch_cap / (6 * max_cells * sizeof(double))));
+                                                 std::max<size_t>(1, scratch_cap / (envelope_scratch_doubles(max_cells, env_rows, env_cols) * sizeof(double))));
         EnvCtx e;
         memset(&e, 0, sizeof e);
         CUDA_TRY(c, upload(c->d_env_pairs, ep, st));
@@ -592,16 +594,16 @@ static int derive_bands(lb200_ctx *c) {
         CUDA_TRY(c, c->d_env_olo.ensure(lo.size() * 4));
         CUDA_TRY(c, c->d_env_ohi.ensure(lo.size() * 4));
         CUDA_TRY(c, c->d_env_flag.ensure(todo.size() * 4 + 16));
-        CUDA_TRY(c, c->d_env_scratch.ensure((size_t)grid * 6 * max_cells * sizeof(double)));
+        CUDA_TRY(c, c->d_env_scratch.ensure((size_t)grid * envelope_scratch_doubles(max_cells, env_rows, env_cols) * sizeof(double)));
         CUDA_TRY(c, c->d_cursor.ensure(4100 * 4));
         e.pairs = (const EnvPair *)c->d_env_pairs.p; e.codes = (const uint8_t *)c->d_codes.p;
         e.p_up = (const double *)c->d_pup.p; e.p_down = (const double *)c->d_pdown.p;
         e.band_lo = (int *)c->d_env_lo.p; e.band_hi = (int *)c->d_env_hi.p; e.out_lo = (int *)c->d_env_olo.p; e.out_hi = (int *)c->d_env_ohi.p;
-        e.out_flag = (int *)c->d_env_flag.p; e.scratch = (double *)c->d_env_scratch.p; e.scratch_doubles = 6 * max_cells;
+        e.out_flag = (int *)c->d_env_flag.p; e.scratch = (double *)c->d_env_scratch.p; e.scratch_doubles = envelope_scratch_doubles(max_cells, env_rows, env_cols);
         envelope_score_params(c->params, e.bm, &e.sw, &e.open, &e.ext, &e.temp);
         e.min_prob = c->params.min_trace_probability; e.local = c->params.sequ_local;
         e.fe_left1 = c->params.fe_left1; e.fe_right1 = c->params.fe_right1; e.fe_left2 = c->params.fe_left2; e.fe_right2 = c->params.fe_right2;
-        CUDA_TRY(c, launch_envelope(e, (int)todo.size(), grid, (int *)c->d_cursor.p, st));
+        CUDA_TRY(c, launch_envelope(e, (int)todo.size(), grid, (int *)c->d_cursor.p, env_rows, env_cols, st));
         std::vector<int> olo(lo.size()), ohi(lo.size()), flag(todo.size());
         CUDA_TRY(c, cudaMemcpyAsync(olo.data(), c->d_env_olo.p, lo.size() * 4, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(c, cudaMemcpyAsync(ohi.data(), c->d_env_ohi.p, lo.size() * 4, cudaMemcpyDeviceToHost, st));

@@ -11,8 +11,12 @@ FLAGSETS = [{}, {"noLP": True, "max-diff-am": 30}, {"sequ-local": True}, {"free-
             {"no-ribosum": True, "struct-weight": 100}, {"pf-double": True}]
 
 
-@pytest.mark.parametrize("flags", FLAGSETS)
-def test_device_bands_equal_oracle(synth_dir, flags):
+@pytest.mark.parametrize("flags", FLAGSETS + [dict(_v1=True), dict({"sequ-local": True}, _v1=True), dict({"free-endgaps": "+--+"}, _v1=True)],
+                         ids=lambda f: "_".join("%s=%s" % kv for kv in f.items()) or "default")
+def test_device_bands_equal_oracle(synth_dir, flags, monkeypatch):
+    flags = dict(flags)
+    if flags.pop("_v1", False):   # the global-memory kernel that serves sequences too long for the shared-memory sweep
+        monkeypatch.setenv("LB200_ENVELOPE_V1", "1")
     files = synth_dir["cfg3"][:6] + synth_dir["short"][:4] + synth_dir["cfg2"][:2]
     pairs = [(files[a], files[b]) for a in range(len(files)) for b in range(a)]
     ctx = capi.Context(0, flags)
