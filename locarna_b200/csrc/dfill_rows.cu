@@ -160,35 +160,37 @@ __device__ void build_list(const DevCtx &c, const RowsCtx &r, const DevGroup &gr
     const int s0 = g.al + g.bl0;
     const int *q = c.sptr + pr.sptr + s0;
     const int q_cap = pr.lenA + pr.lenB + 2 - s0;
-    const uint4 *ent = (const uint4 *)(c.ent + pr.am_base);
+    const uint2 *ent8 = c.ent8 + pr.am_base;   // packed S-order (LB_PACK_*): 8 bytes per entry, D kept current by write_d
     uint2 *list = r.clist + (size_t)grp.pair * r.clist_cap;
     int *nblk = r.cnblk + (size_t)grp.pair * LB_ROWS_TG;
-    const uint32_t org = (uint32_t)g.al | ((uint32_t)g.bl0 << 16);
-    const uint32_t lim = (uint32_t)(g.al + g.Rn) | ((uint32_t)(g.bl0 + g.Cn) << 16);
+    const int a_lo = g.al, b_lo = g.bl0, a_hi = g.al + g.Rn, b_hi = g.bl0 + g.Cn;
     for (int t = 2 + grp.gi; t < g.n_tg; t += grp.G) {
-        const int qa = __ldg(q + min(4 * t, q_cap)), qb = __ldg(q + min(4 * t + 4, q_cap));
         uint2 *out = list + (size_t)sm.gstart[t] * 32;
         int n = 0;
-        for (int e0 = qa; e0 < qb; e0 += 128) {   // four independent 16-byte loads per lane in flight
-            uint4 v[4];
+        const int qa = __ldg(q + min(4 * t, q_cap)), qb = __ldg(q + min(4 * t + 4, q_cap));
+#pragma unroll 1
+        for (int e0 = qa; e0 < qb; e0 += 128) {   // four independent loads per lane in flight
+            uint2 v[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const int e = e0 + 32 * k + lane;
-                v[k] = make_uint4(0u, 0u, 0u, 0u);
-                if (e < qb) v[k] = __ldcg(ent + e);   // x = (al'-1) | (bl'-1) << 16, y = ar' | br' << 16, z = D
+                v[k] = make_uint2(0u, 0u);
+                if (e < qb) v[k] = __ldcg(ent8 + e);
             }
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 if (e0 + 32 * k >= qb) break;
                 const int e = e0 + 32 * k + lane;
-                const uint32_t t1 = v[k].x - org, t2 = lim - v[k].y;
-                const bool in = e < qb && ((t1 | t2) & 0x80008000u) == 0 && (int)v[k].z >= LB_NEG_LIMIT;
-                const uint32_t p = t1 & 0xffffu, qq = t1 >> 16;
-                const uint32_t ta = (v[k].y & 0xffffu) + (v[k].y >> 16);            // absolute target anti-diagonal
-                const uint32_t tcol = (v[k].y >> 16) - (uint32_t)g.bl0;
+                const int p1 = (int)(v[k].x & 511u), q1 = (int)((v[k].x >> 9) & 511u);          // al' - 1, bl' - 1
+                const int ar = (int)((v[k].x >> 18) & 511u), br = (int)((v[k].x >> 27) | ((v[k].y & 15u) << 5));
+                const int d = (int)v[k].y >> 4;
+                const bool in = e < qb && p1 >= a_lo && q1 >= b_lo && ar <= a_hi && br <= b_hi && d != LB_PACK_NEG;
+                const uint32_t p = (uint32_t)(p1 - a_lo), qq = (uint32_t)(q1 - b_lo);
+                const uint32_t ta = (uint32_t)(ar + br);                                        // absolute target anti-diagonal
+                const uint32_t tcol = (uint32_t)(br - b_lo);
                 uint2 o;
                 o.x = ((p + qq) << LOGW) | (qq & (W - 1)) | ((((ta & (RING - 1)) << LOGW) | (tcol & (W - 1))) << 16);
-                o.y = v[k].z;
+                o.y = (uint32_t)d;
                 const unsigned mask = __ballot_sync(0xffffffffu, in);
                 if (in) out[n + __popc(mask & ((1u << lane) - 1u))] = o;
                 n += __popc(mask);
