@@ -21,7 +21,7 @@
 // only moves right, so a lane whose column has left the band moves on to column j + 32 NC; the state it carries over is -inf because
 // every out-of-band cell is forced to -inf. A box needs NC = 2 when more than ~30 of its columns are active at once.
 // Arc-match terms: the entries of four target anti-diagonals 4g..4g+3 form one padded run of the list; it is folded after cell step
-// 4g - 5 (all sources lie >= 8 anti-diagonals before their target, so they are final) into a ring of eight per-anti-diagonal
+// 4g - 2 (all sources lie >= 8 anti-diagonals before their target, so they are final) into a ring of six per-anti-diagonal
 // accumulators (shared memory, atomicMax) which the cell step consumes and resets.
 //
 // Schedule: groups are claimed in the order row al descending, the groups of a row consecutively. A group of row al reads D only of
@@ -38,7 +38,7 @@ namespace lb200 {
 namespace {
 
 constexpr int V = LB_GV;
-constexpr int RING = 8;
+constexpr int RING = LB_ROWS_RING;   // accumulator rows: the anti-diagonal being consumed + the five a fold may target (see sweep)
 constexpr int BIAS = 640;   // row indices are biased so that the bit-field band test never sees a negative row
 constexpr uint32_t G_LO = 0x800u, G_HI = 0x800000u, GUARDS = G_LO | G_HI;
 // column word: bits 0..10 first valid row + BIAS, bits 12..22 2047 - (last valid row + BIAS), bits 24..31 4 * symbol code of B
@@ -189,7 +189,7 @@ __device__ void build_list(const DevCtx &c, const RowsCtx &r, const DevGroup &gr
                 const uint32_t ta = (uint32_t)(ar + br);                                        // absolute target anti-diagonal
                 const uint32_t tcol = (uint32_t)(br - b_lo);
                 uint2 o;
-                o.x = ((p + qq) << LOGW) | (qq & (W - 1)) | ((((ta & (RING - 1)) << LOGW) | (tcol & (W - 1))) << 16);
+                o.x = ((p + qq) << LOGW) | (qq & (W - 1)) | ((((ta % RING) << LOGW) | (tcol & (W - 1))) << 16);
                 o.y = (uint32_t)d;
                 const unsigned mask = __ballot_sync(0xffffffffu, in);
                 if (in) out[n + __popc(mask & ((1u << lane) - 1u))] = o;
@@ -297,7 +297,9 @@ __device__ void sweep(const DevCtx &c, const RowsCtx &r, const DevGroup &grp, co
     int *ap = sm.acc + lane * NC;
     const int left = (lane + 31) & 31;
 
-    // entry list of the row: blocks of target group t become due after cell step 4t - 5. The block counts move next to the block
+    // entry list of the row: the blocks of target group t (targets 4t .. 4t+3) are folded after cell step 4t - 2: their sources lie at
+    // least 8 anti-diagonals before the target, so they are final; the last gather lands after step 4t - 1, just before its first target
+    // is consumed. The accumulators then cover the anti-diagonals 4t-1 .. 4t+3, which is why a ring of six suffices. The block counts move next to the block
     // offsets (the list is complete: all groups of the row have contributed), and the first block of the next target group is
     // requested one group ahead, so that a fold waits for one memory round trip (the gather of the sources), not for three in a row
     const uint2 *list = r.clist + (size_t)grp.pair * r.clist_cap + lane;
@@ -314,7 +316,7 @@ __device__ void sweep(const DevCtx &c, const RowsCtx &r, const DevGroup &grp, co
     int pd = LB_NEG, ps = 0;
     bool pending = false;
     {
-        const int gs = sm.gstart[min((g.u0 + 8) >> 2, LB_ROWS_TG - 1)];   // the first group that falls due
+        const int gs = sm.gstart[min((g.u0 + 5) >> 2, LB_ROWS_TG - 1)];   // the first group that falls due
         if ((gs >> 20) > 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(list + (size_t)(gs & 0xfffff) * 32));
     }
     auto land = [&]() {
@@ -330,8 +332,8 @@ __device__ void sweep(const DevCtx &c, const RowsCtx &r, const DevGroup &grp, co
     auto fold = [&](int u) {   // after cell step u
         __syncwarp();
         if (pending) { land(); pending = false; }
-        if (((u + 5) & 3) == 0) {
-            const int t = (u + 5) >> 2;
+        if (((u + 2) & 3) == 0) {
+            const int t = (u + 2) >> 2;
             if (t < g.n_tg) {
                 const int gs = sm.gstart[t], gs1 = sm.gstart[t + 1];
                 const int nb = gs >> 20;
@@ -362,7 +364,7 @@ __device__ void sweep(const DevCtx &c, const RowsCtx &r, const DevGroup &grp, co
     // as the cell holds a score or -inf, so it must not be left uninitialised when the sweep starts later
     if (g.u0 > 0 && lane == 0) *(int4 *)box = make_int4(LB_NEG, LB_NEG, LB_NEG, LB_NEG);
     __syncwarp();
-    int ringoff = ((s0 + g.u0) & (RING - 1)) * W;
+    int ringoff = ((s0 + g.u0) % RING) * W;
     int u = g.u0;
     int my_jv = -1;   // lane v seeds layer v
 #pragma unroll
@@ -374,12 +376,12 @@ __device__ void sweep(const DevCtx &c, const RowsCtx &r, const DevGroup &grp, co
         if (my_jv == u) sm.acc[lane * (RING * W) + ringoff + (u & (W - 1))] = 0;
         __syncwarp();
         dp_step<NC>(S, g, sm.sig, ap + ringoff, gap, gap_open, left, u);
-        ringoff = (ringoff + W) & (RING * W - 1);
+        ringoff = ringoff + W == RING * W ? 0 : ringoff + W;
         fold(u);
     }
     for (; u <= g.u1; u++) {
         dp_step<NC>(S, g, sm.sig, ap + ringoff, gap, gap_open, left, u);
-        ringoff = (ringoff + W) & (RING * W - 1);
+        ringoff = ringoff + W == RING * W ? 0 : ringoff + W;
         fold(u);
     }
     __syncwarp();

@@ -7,7 +7,8 @@
 
 namespace lb200 {
 
-#define LB_ROWS_TG 264   // groups of four target anti-diagonals of a box (sequences <= 510 nt)
+#define LB_ROWS_TG 264
+#define LB_ROWS_RING 6   // anti-diagonals of arc-match accumulators per layer (dfill_rows.cu)   // groups of four target anti-diagonals of a box (sequences <= 510 nt)
 
 struct RowsCtx {
     const DevGroup *groups;

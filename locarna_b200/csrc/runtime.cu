@@ -873,7 +873,7 @@ static int upload_chunk(lb200_ctx *c, int p0, int p1) {
         rc.nc_max = max_active <= 26 ? 1 : 2;
         if (const char *s = getenv("LB200_ROWS_NC")) rc.nc_max = std::max(1, std::min(2, atoi(s)));
         if (const char *s = getenv("LB200_ROWS_FORCE_NC")) { rc.force_nc = atoi(s); if (rc.force_nc == 2) rc.nc_max = 2; }
-        rc.acc_words = 8 * 32 * rc.nc_max * LB_GV;
+        rc.acc_words = LB_ROWS_RING * 32 * rc.nc_max * LB_GV;
         // the row in flight of every pair keeps its filtered entry list here: at most the pair's arc matches + a block of padding per
         // group of four target anti-diagonals
         int max_K = 1;
