@@ -122,6 +122,14 @@ int lb200_seq_get(const lb200_ctx *ctx, int seq, char *name, int name_cap, char 
  * [min_col(i), max_col(i)] per row; pass NULL for both to have it derived like the reference does
  * (--max-diff, then the probability envelope). Returns the pair id (>= 0). */
 int lb200_pair_add(lb200_ctx *ctx, int seqA, int seqB, const int *min_col, const int *max_col);
+/* A pair whose band is given as TraceController has it BEFORE restrict_by_trace_probabilities (main_helper.icc:371-426): built from a
+ * reference alignment (trace_controller.cc:406-539) or restricted by anchors; the probability envelope (min_trace_probability > 0) is
+ * then applied inside this range, exactly as for the --max-diff band of lb200_pair_add(.., NULL, NULL). */
+int lb200_pair_add_restricted(lb200_ctx *ctx, int seqA, int seqB, const int *min_col, const int *max_col);
+/* Rows of TraceController(seqA, seqB, reference alignment, delta) for single sequences (--max-diff-aln / --max-diff-pw-aln with
+ * --max-diff delta; TraceRange, trace_controller.cc:44-215, merge_in_trace_range :606-622). aliA / aliB: the rows of the two sequences in
+ * the reference alignment (gap symbols "-_~."); min_col / max_col: lenA + 1 entries. Host only. */
+int lb200_band_from_alignment(int lenA, int lenB, const char *aliA, const char *aliB, int delta, int *min_col, int *max_col);
 /* Add n alignment problems at once (bands derived like the reference does); returns the id of the first one. This is what the
  * all-vs-all stage of mlocarna hands over (src/Utils/mlocarna:3577-3604: the list of (a, b) index pairs). */
 int lb200_pairs_add(lb200_ctx *ctx, int n, const int *seqA, const int *seqB);

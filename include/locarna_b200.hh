@@ -19,7 +19,9 @@
 #include <exception>
 #include <fstream>
 #include <memory>
+#include <iostream>
 #include <ostream>
+#include <sstream>
 #include <string>
 #include <utility>
 #include <queue>
@@ -152,6 +154,38 @@ class MultipleAlignment {  // rows of a pairwise Alignment + CLUSTAL writer (mul
 public:
     struct SeqEntry { std::string name, seq; SeqEntry(const std::string &n, const std::string &s) : name(n), seq(s) {} };
     enum class FormatType { CLUSTAL, STOCKHOLM };
+    MultipleAlignment() {}
+    //! CLUSTAL W file (multiple_alignment.cc:253-340): header line, blocks of "name row" lines; annotation ('#...'), conservation
+    //! (leading blank) and empty lines are skipped
+    explicit MultipleAlignment(const std::string &file) {
+        std::ifstream in(file.c_str());
+        if (!in) throw failure("Cannot read " + file);
+        std::string line;
+        bool header = false;
+        while (std::getline(in, line)) {
+            if (!header) { if (line.compare(0, 7, "CLUSTAL") == 0) header = true; else if (!line.empty()) throw failure("missing CLUSTAL header in " + file); continue; }
+            if (line.empty() || line[0] == ' ' || line[0] == '#' || line[0] == '/') continue;
+            std::istringstream is(line);
+            std::string name, row;
+            if (!(is >> name >> row)) continue;
+            bool found = false;
+            for (auto &r : rows_) if (r.name == name) { r.seq += row; found = true; }
+            if (!found) rows_.emplace_back(name, row);
+        }
+    }
+    //! pairwise alignment from two rows (multiple_alignment.cc:132-151)
+    MultipleAlignment(const std::string &nameA, const std::string &nameB, const std::string &aliA, const std::string &aliB) : pairwise_(true) {
+        rows_.emplace_back(nameA, aliA);
+        rows_.emplace_back(nameB, aliB);
+    }
+    //! built from two rows: row 0 belongs to the first, row 1 to the second sequence whatever their names
+    bool pairwise() const { return pairwise_; }
+    const SeqEntry &seqentry(size_t k) const { return rows_.at(k); }
+    bool contains(const std::string &name) const { for (const auto &r : rows_) if (r.name == name) return true; return false; }
+    const SeqEntry &seqentry(const std::string &name) const {
+        for (const auto &r : rows_) if (r.name == name) return r;
+        throw failure("MultipleAlignment: no sequence " + name);
+    }
     MultipleAlignment(const Alignment &a, bool only_local = false) {
         const bool clash = a.nameA() == a.nameB();
         rows_.emplace_back(clash ? "A." + a.nameA() : a.nameA(), a.rowA(only_local));
@@ -179,6 +213,7 @@ public:
     }
 private:
     std::vector<SeqEntry> rows_;
+    bool pairwise_ = false;
 };
 
 //! One arc (basepairs.hh:33-89): positions only; the reference's arc index is internal to the device tables.
@@ -252,6 +287,7 @@ class AlignerParams {  // aligner_params.hh:51-115: same argument names, chained
     int max_diff_am_ = -1, max_diff_at_am_ = -1, max_diff_ = -1;
     double min_prob_ = 0.001, min_trace_probability_ = 1e-4;
     std::vector<int> min_col_, max_col_;
+    const MultipleAlignment *ref_aln_ = nullptr;
 public:
     AlignerParams &seqA(const RnaData *r) { rnaA_ = r; return *this; }
     AlignerParams &seqB(const RnaData *r) { rnaB_ = r; return *this; }
@@ -265,6 +301,8 @@ public:
     AlignerParams &stacking(bool b) { stacking_ = b; return *this; }
     // the reference passes a TraceController; here either its rows (min_col/max_col) or the two numbers it is built from
     AlignerParams &trace_controller(const std::vector<int> &min_col, const std::vector<int> &max_col) { min_col_ = min_col; max_col_ = max_col; return *this; }
+    //! reference alignment of TraceController(seqA, seqB, ma, max_diff) (trace_controller.cc:406-539): the band lies within max_diff of it
+    AlignerParams &reference_alignment(const MultipleAlignment *ma) { ref_aln_ = ma; return *this; }
     AlignerParams &max_diff(int d) { max_diff_ = d; return *this; }
     AlignerParams &min_trace_probability(double p) { min_trace_probability_ = p; return *this; }
     AlignerParams &min_prob(double p) { min_prob_ = p; return *this; }
@@ -300,8 +338,6 @@ public:
         ctx_->check(a);
         const int b = lb200_seq_add_pp(ctx_->get(), ap.rnaB_->filename().c_str());
         ctx_->check(b);
-        pair_ = lb200_pair_add(ctx_->get(), a, b, ap.min_col_.empty() ? nullptr : ap.min_col_.data(), ap.max_col_.empty() ? nullptr : ap.max_col_.data());
-        ctx_->check(pair_);
         char name[256], *seq;
         const int la = lb200_seq_length(ctx_->get(), a), lb = lb200_seq_length(ctx_->get(), b);
         const int seq_cap = std::max(la, lb) + 1;
@@ -309,6 +345,21 @@ public:
         ctx_->check(lb200_seq_get(ctx_->get(), a, name, sizeof name, seq, seq_cap)); alignment_.nameA_ = name; alignment_.seqA_ = seq;
         ctx_->check(lb200_seq_get(ctx_->get(), b, name, sizeof name, seq, seq_cap)); alignment_.nameB_ = name; alignment_.seqB_ = seq;
         delete[] seq;
+        if (ap.ref_aln_ != nullptr && ap.max_diff_ != -1) {
+            // TraceController(seqA, seqB, ma, delta): rows within delta of the reference alignment (trace_controller.cc:431-483); the
+            // probability envelope is applied inside this range
+            std::vector<int> lo((size_t)la + 1), hi((size_t)la + 1);
+            const MultipleAlignment &ma = *ap.ref_aln_;
+            const std::string &rowA = ma.pairwise() ? ma.seqentry((size_t)0).seq : ma.seqentry(alignment_.nameA_).seq;
+            const std::string &rowB = ma.pairwise() ? ma.seqentry((size_t)1).seq : ma.seqentry(alignment_.nameB_).seq;
+            if (lb200_band_from_alignment(la, lb, rowA.c_str(), rowB.c_str(),
+                                          ap.max_diff_, lo.data(), hi.data()) != LB200_OK)
+                throw failure("Inconsistent trace range due to max-diff heuristic");
+            pair_ = lb200_pair_add_restricted(ctx_->get(), a, b, lo.data(), hi.data());
+        } else {
+            pair_ = lb200_pair_add(ctx_->get(), a, b, ap.min_col_.empty() ? nullptr : ap.min_col_.data(), ap.max_col_.empty() ? nullptr : ap.max_col_.data());
+        }
+        ctx_->check(pair_);
         r_ = AlignerRestriction(1, 1, la, lb);
     }
     //! compute the alignment score (aligner.cc:924-962); under a restriction only the top level is redone on the filled D table

@@ -26,7 +26,7 @@
 //
 // The objects of the reference compute on construction (RnaData parses, ArcMatches enumerates, Scoring precomputes). Here they record
 // their arguments; the device builds bands, arc matches and scores when Aligner runs. What the B200 path does not implement
-// (reference alignments for --max-diff-aln, anchors, MEA, explicit arc-match scores) throws LocARNA::failure from the object
+// (anchors, MEA, explicit arc-match scores, --max-diff-relax) throws LocARNA::failure from the object
 // that would need it, so the caller's existing error handling applies.
 #ifndef LOCARNA_B200_COMPAT_HH
 #define LOCARNA_B200_COMPAT_HH
@@ -98,13 +98,10 @@ class MultipleAlignment : public LocARNA_B200::MultipleAlignment {   // multiple
 public:
     enum class AnnoType { consensus_structure, structure, fixed_structure, anchors };
     MultipleAlignment(const Alignment &a, bool only_local = false, bool = false) : LocARNA_B200::MultipleAlignment(a, only_local) {}
-    //! reference alignments (--max-diff-aln / --max-diff-pw-aln) are not part of the B200 path
-    explicit MultipleAlignment(const std::string &file) : LocARNA_B200::MultipleAlignment(Alignment(), false) {
-        throw failure("locarna_b200: reference alignments (" + file + ") for --max-diff-aln are not supported");
-    }
-    MultipleAlignment(const std::string &, const std::string &, const std::string &, const std::string &) : LocARNA_B200::MultipleAlignment(Alignment(), false) {
-        throw failure("locarna_b200: --max-diff-pw-aln is not supported");
-    }
+    //! reference alignments for --max-diff-aln (CLUSTAL file) / --max-diff-pw-aln (two rows)
+    explicit MultipleAlignment(const std::string &file) : LocARNA_B200::MultipleAlignment(file) {}
+    MultipleAlignment(const std::string &nameA, const std::string &nameB, const std::string &aliA, const std::string &aliB)
+        : LocARNA_B200::MultipleAlignment(nameA, nameB, aliA, aliB) {}
 };
 
 class Sequence {   // one row: the B200 path aligns single sequences (profile inputs: SURVEY 8f N3)
@@ -164,10 +161,12 @@ public:
 class TraceController {   // trace_controller.hh:200: the band; its rows are derived on the device when the aligner runs
     int max_diff_;
     double min_trace_probability_ = 0.0;
+    const MultipleAlignment *ref_aln_ = nullptr;
 public:
-    TraceController(const Sequence &, const Sequence &, const MultipleAlignment *ma, int max_diff, bool /*relax*/ = false) : max_diff_(max_diff) {
-        if (ma != nullptr) throw failure("locarna_b200: reference-alignment bands are not supported");
+    TraceController(const Sequence &, const Sequence &, const MultipleAlignment *ma, int max_diff, bool relax = false) : max_diff_(max_diff), ref_aln_(ma) {
+        if (ma != nullptr && relax) throw failure("locarna_b200: --max-diff-relax is not supported");
     }
+    const MultipleAlignment *reference_alignment() const { return ref_aln_; }
     void restrict_by_anchors(const AnchorConstraints &c) { if (!c.empty()) throw failure("locarna_b200: anchor constraints are not supported"); }
     //! what MainHelper::restrict_trace_by_probabilities records (main_helper.icc:408-426)
     void set_min_trace_probability(double p) { min_trace_probability_ = p; }
@@ -308,6 +307,7 @@ inline LocARNA_B200::AlignerParams to_b200_params(const Scoring &s, const TraceC
     ap.seqA(&s.rnaA().data()).seqB(&s.rnaB().data()).scoring(sp).min_prob(s.arc_matches().min_prob());
     ap.no_lonely_pairs(noLP).struct_local(struct_local).sequ_local(sequ_local).free_endgaps(free_endgaps);
     ap.max_diff_am(max_diff_am).max_diff_at_am(max_diff_at_am).max_diff(tc.max_diff()).min_trace_probability(tc.min_trace_probability());
+    ap.reference_alignment(tc.reference_alignment());
     return ap;
 }
 

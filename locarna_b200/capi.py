@@ -42,7 +42,7 @@ EXPORTS = [
     "lb200_prepare", "lb200_upload", "lb200_run", "lb200_last_kernel_ms", "lb200_last_h2d_bytes", "lb200_last_d2h_bytes", "lb200_last_dfill_ms", "lb200_last_dfill_launches", "lb200_last_launches", "lb200_envelope_stats", "lb200_pair_score", "lb200_get_scores",
     "lb200_pair_get_info", "lb200_pair_band", "lb200_pair_arcmatches", "lb200_pair_alignment", "lb200_upgma_newick",
     "lb200_run_pf", "lb200_pair_partition_function", "lb200_pair_arcmatch_pf", "lb200_run_pf_probs", "lb200_pair_arcmatch_probs",
-    "lb200_pair_basematch_probs", "lb200_pairs_add", "lb200_all_vs_all", "lb200_pair_cost", "lb200_shard_pairs", "lb200_seq_num_arcs", "lb200_seqs_add_pp", "lb200_last_dfill_kind", "lb200_rows_fallbacks", "lb200_release_device_cache", "lb200_run_normalized", "lb200_run_penalized", "lb200_shard_job", "lb200_pair_set_restriction", "lb200_run_pair_toplevel",
+    "lb200_pair_basematch_probs", "lb200_pairs_add", "lb200_all_vs_all", "lb200_pair_cost", "lb200_shard_pairs", "lb200_seq_num_arcs", "lb200_seqs_add_pp", "lb200_last_dfill_kind", "lb200_rows_fallbacks", "lb200_release_device_cache", "lb200_run_normalized", "lb200_run_penalized", "lb200_shard_job", "lb200_pair_set_restriction", "lb200_run_pair_toplevel", "lb200_pair_add_restricted", "lb200_band_from_alignment",
 ]
 
 _lib = None
@@ -92,6 +92,8 @@ def load():
     lib.lb200_last_kernel_ms.argtypes = [vp]
     lib.lb200_last_kernel_ms.restype = C.c_double
     lib.lb200_shard_job.argtypes = [vp, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.lb200_pair_add_restricted.argtypes = [vp, C.c_int, C.c_int, ip, ip]
+    lib.lb200_band_from_alignment.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_int, ip, ip]
     lib.lb200_pair_set_restriction.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.lb200_run_pair_toplevel.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int]
     lib.lb200_run_normalized.argtypes = [vp, C.c_int64]
@@ -140,6 +142,15 @@ def make_params(flags: dict | None = None) -> Params:
         else:
             setattr(p, FLAG_FIELDS[k], int(v) if isinstance(v, bool) else v)
     return p
+
+
+def band_from_alignment(lenA: int, lenB: int, aliA: str, aliB: str, delta: int):
+    """min_col / max_col of TraceController(seqA, seqB, reference alignment, delta) (lb200_band_from_alignment)."""
+    lo, hi = (C.c_int * (lenA + 1))(), (C.c_int * (lenA + 1))()
+    rc = load().lb200_band_from_alignment(lenA, lenB, aliA.encode(), aliB.encode(), delta, lo, hi)
+    if rc != OK:
+        raise Error("lb200_band_from_alignment failed with code %d" % rc)
+    return list(lo), list(hi)
 
 
 class Error(RuntimeError):
@@ -241,6 +252,13 @@ class Context:
         if len(lo) != n or len(hi) != n:
             raise Error("band arrays must hold lenA + 1 = %d entries (got %d / %d)" % (n, len(lo), len(hi)))
         return self._chk(self.lib.lb200_pair_add(self.h, a, b, (C.c_int * len(lo))(*lo), (C.c_int * len(hi))(*hi)))
+
+    def add_pair_restricted(self, a: int, b: int, lo, hi) -> int:
+        """A pair whose band (before the probability envelope) is given: reference-alignment or anchor bands."""
+        n = self.seq_length(a) + 1
+        if len(lo) != n or len(hi) != n:
+            raise Error("band arrays must hold lenA + 1 = %d entries (got %d / %d)" % (n, len(lo), len(hi)))
+        return self._chk(self.lib.lb200_pair_add_restricted(self.h, a, b, (C.c_int * n)(*lo), (C.c_int * n)(*hi)))
 
     def clear_pairs(self):
         self._chk(self.lib.lb200_clear_pairs(self.h))

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -24,7 +25,7 @@ enum {
     O_TAU, O_EXCLUSION, O_STACKING, O_NEW_STACKING, O_STRUCT_LOCAL, O_SEQU_LOCAL, O_FREE_ENDGAPS, O_NORMALIZED, O_PENALIZED, O_WIDTH,
     O_CLUSTAL, O_STOCKHOLM, O_PP, O_LOCAL_OUTPUT, O_LOCAL_FILE_OUTPUT, O_POS_OUTPUT, O_WRITE_STRUCTURE, O_MIN_PROB, O_MAX_BPS_LENGTH_RATIO,
     O_MAX_DIFF_AM, O_MAX_DIFF, O_MAX_DIFF_AT_AM, O_MIN_TRACE_PROB, O_NOLP, O_MAXBPSPAN, O_TEMPERATURE_ALIPF, O_CONSENSUS_STRUCTURE,
-    O_WRITE_ARCMATCH_SCORES, O_KBEST, O_BETTER, O_UNSUPPORTED, O_DEVICE, O_VERSION, O_QUIET, O_VERBOSE, O_HELP
+    O_WRITE_ARCMATCH_SCORES, O_KBEST, O_BETTER, O_MAX_DIFF_ALN, O_MAX_DIFF_PW_ALN, O_UNSUPPORTED, O_DEVICE, O_VERSION, O_QUIET, O_VERBOSE, O_HELP
 };
 bool parse_bool(const char *s) {
     const std::string v = s ? s : "";  // options.cc:867-880
@@ -55,7 +56,7 @@ int main(int argc, char **argv) {
         {"maxBPspan", required_argument, 0, O_MAXBPSPAN}, {"temperature-alipf", required_argument, 0, O_TEMPERATURE_ALIPF},
         {"consensus-structure", required_argument, 0, O_CONSENSUS_STRUCTURE}, {"write-arcmatch-scores", required_argument, 0, O_WRITE_ARCMATCH_SCORES},
         // recognised, not implemented on the B200 path
-        {"max-diff-aln", required_argument, 0, O_UNSUPPORTED}, {"max-diff-pw-aln", required_argument, 0, O_UNSUPPORTED},
+        {"max-diff-aln", required_argument, 0, O_MAX_DIFF_ALN}, {"max-diff-pw-aln", required_argument, 0, O_MAX_DIFF_PW_ALN},
         {"max-diff-relax", no_argument, 0, O_UNSUPPORTED}, {"kbest", required_argument, 0, O_KBEST}, {"better", required_argument, 0, O_BETTER},
         {"mea-alignment", no_argument, 0, O_UNSUPPORTED}, {"match-prob-method", required_argument, 0, O_UNSUPPORTED},
         {"read-match-probs", required_argument, 0, O_UNSUPPORTED}, {"write-match-probs", required_argument, 0, O_UNSUPPORTED},
@@ -79,6 +80,7 @@ int main(int argc, char **argv) {
     bool struct_local = false, struct_local_given = false, sequ_local = false, sequ_local_given = false, normalized = false, penalized = false;
     long normalized_L = 0, position_penalty = 0, subopt_threshold = -1000000;
     bool subopt = false;
+    std::string max_diff_alignment_file, max_diff_pw_alignment;
     int kbest_k = -1;
     int c, idx = 0;
     while ((c = getopt_long(argc, argv, "i:m:M:s:e:t:E:w:Lp:D:d:PqvVh", longopts, &idx)) != -1) {
@@ -97,6 +99,8 @@ int main(int argc, char **argv) {
             case 'E': case O_EXCLUSION: sp.exclusion = atoi(optarg); break;
             case O_STRUCT_LOCAL: struct_local = parse_bool(optarg); struct_local_given = true; break;
             case O_SEQU_LOCAL: sequ_local = parse_bool(optarg); sequ_local_given = true; break;
+            case O_MAX_DIFF_ALN: max_diff_alignment_file = optarg; break;
+            case O_MAX_DIFF_PW_ALN: max_diff_pw_alignment = optarg; break;
             case O_KBEST: subopt = true; kbest_k = atoi(optarg); break;          // locarna.cc:203-207
             case O_BETTER: subopt = true; subopt_threshold = atol(optarg); break;
             case O_NORMALIZED: normalized = true; normalized_L = atol(optarg); break;
@@ -151,6 +155,10 @@ int main(int argc, char **argv) {
         struct_local = false;
     }
     ap.struct_local(struct_local).sequ_local(sequ_local);
+    if (max_diff_pw_alignment != "" && max_diff_alignment_file != "") {   // locarna.cc:504-508
+        std::cerr << "Cannot simultaneously use options --max-diff-pw-alignment" << " and --max-diff-alignment-file." << std::endl;
+        return 255;
+    }
     if (sp.stacking && sp.exp_prob < 0) {   // locarna.cc:406-414
         std::cerr << "WARNING: stacking turned off. "
                   << "Stacking requires setting a background probability "
@@ -160,6 +168,23 @@ int main(int argc, char **argv) {
     try {
         RnaData rnaA(argv[optind], min_prob, max_bps_length_ratio, max_bp_span), rnaB(argv[optind + 1], min_prob, max_bps_length_ratio, max_bp_span);
         ap.seqA(&rnaA).seqB(&rnaB).scoring(sp).min_prob(min_prob);
+        std::unique_ptr<MultipleAlignment> multiple_ref_alignment;                   // locarna.cc:514-548
+        if (max_diff_alignment_file != "") {
+            multiple_ref_alignment.reset(new MultipleAlignment(max_diff_alignment_file));
+        } else if (max_diff_pw_alignment != "") {
+            const size_t amp = max_diff_pw_alignment.find('&');
+            if (amp == std::string::npos || max_diff_pw_alignment.find('&', amp + 1) != std::string::npos) {
+                std::cerr << "Invalid argument to --max-diff-pw-alignemnt; require " << "exactly one '&' separating the alignment strings." << std::endl;
+                return 255;
+            }
+            const std::string rowA = max_diff_pw_alignment.substr(0, amp), rowB = max_diff_pw_alignment.substr(amp + 1);
+            if (rowA.length() != rowB.length()) {
+                std::cerr << "Invalid argument to --max-diff-pw-alignemnt;" << " alignment strings have unequal lengths." << std::endl;
+                return 255;
+            }
+            multiple_ref_alignment.reset(new MultipleAlignment("A", "B", rowA, rowB));
+        }
+        ap.reference_alignment(multiple_ref_alignment.get());
         Aligner aligner(ap, device);
         if (!arcmatch_scores_file.empty()) {                                        // locarna.cc:705-720: write and return without aligning
             if (verbose) std::cout << "Write arcmatch scores to file " << arcmatch_scores_file << " and exit." << std::endl;

@@ -323,14 +323,15 @@ __global__ void __launch_bounds__(ENV_THREADS) envelope_kernel_v2(EnvCtx e, int 
     }
 }
 
-size_t envelope_scratch_doubles(size_t max_cells, int max_rows, int max_cols) { return (envelope_smem_bytes(max_rows, max_cols) <= 200 * 1024 ? 3 : 6) * max_cells; }
+static bool envelope_use_v2(int max_rows, int max_cols) { return envelope_smem_bytes(max_rows, max_cols) <= 200 * 1024 && getenv("LB200_ENVELOPE_V1") == nullptr; }
+size_t envelope_scratch_doubles(size_t max_cells, int max_rows, int max_cols) { return (envelope_use_v2(max_rows, max_cols) ? 3 : 6) * max_cells; }
 int envelope_smem_bytes(int max_rows, int max_cols) { return (11 * max_rows + 2 * max_cols + ENV_THREADS) * 8 + 2 * max_rows * 4; }
 
 cudaError_t launch_envelope(const EnvCtx &e, int n_pairs, int grid, int *cursor, int max_rows, int max_cols, cudaStream_t st) {
     cudaError_t err = cudaMemsetAsync(cursor, 0, sizeof(int), st);
     if (err != cudaSuccess) return err;
     const int smem = envelope_smem_bytes(max_rows, max_cols);
-    if (smem <= 200 * 1024 && getenv("LB200_ENVELOPE_V1") == nullptr) {
+    if (envelope_use_v2(max_rows, max_cols)) {
         err = cudaFuncSetAttribute(envelope_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, lb200_sticky_smem(400, smem));
         if (err != cudaSuccess) return err;
         envelope_kernel_v2<<<grid, ENV_THREADS, smem, st>>>(e, n_pairs, cursor, max_rows, max_cols);

@@ -283,6 +283,37 @@ Band make_band(int lenA, int lenB, int max_diff) {
     return b;
 }
 
+// Band around a pairwise reference alignment (--max-diff-aln / --max-diff-pw-aln with --max-diff delta): TraceRange(pseqA, pseqB,
+// paliA, paliB, delta), trace_controller.cc:44-215 (position cut distance), for ungapped sequences A and B (their positions are their
+// columns), intersected with the unconstrained range as merge_in_trace_range does (:606-622). aliA / aliB: the two rows of the
+// reference alignment, gap symbols "-_~." (aux.cc:24). Returns false (err set) if the rows do not spell out sequences of these
+// lengths or the range is inconsistent.
+bool band_from_alignment(int lenA, int lenB, const std::string &aliA_in, const std::string &aliB_in, int delta, Band &b, std::string &err) {
+    auto gap = [](char c) { return c == '-' || c == '_' || c == '~' || c == '.'; };
+    if (aliA_in.size() != aliB_in.size()) { err = "reference alignment rows have unequal lengths"; return false; }
+    std::string aliA, aliB;   // remove_common_gaps (:25-42)
+    for (size_t k = 0; k < aliA_in.size(); k++)
+        if (!(gap(aliA_in[k]) && gap(aliB_in[k]))) { aliA += aliA_in[k]; aliB += aliB_in[k]; }
+    size_t na = 0, nb = 0;
+    for (char c : aliA) na += gap(c) ? 0 : 1;
+    for (char c : aliB) nb += gap(c) ? 0 : 1;
+    if ((int)na != lenA || (int)nb != lenB) { err = "reference alignment does not match the sequence lengths"; return false; }
+    b.lenA = lenA; b.lenB = lenB;
+    b.lo.assign(lenA + 1, lenB); b.hi.assign(lenA + 1, 0);
+    const size_t d = (size_t)std::max(delta, 0), A = (size_t)lenA, B = (size_t)lenB;
+    size_t i = 0, j = 0;
+    for (size_t c = 0; c <= aliA.size(); c++) {   // cut of the reference alignment after column c
+        if (c > 0) { i += gap(aliA[c - 1]) ? 0 : 1; j += gap(aliB[c - 1]) ? 0 : 1; }
+        const size_t i_minus = std::max(d, i) - d, i_plus = std::min(A, i + d), j_minus = std::max(d, j) - d, j_plus = std::min(B, j + d);
+        b.lo[i] = std::min(b.lo[i], (int)j_minus); b.hi[i] = std::max(b.hi[i], (int)j_plus);
+        for (size_t pi = i_minus; pi < i; pi++) b.hi[pi] = std::max(b.hi[pi], (int)j);
+        for (size_t pi = i + 1; pi <= i_plus; pi++) b.lo[pi] = std::min(b.lo[pi], (int)j);
+    }
+    for (int r = 0; r <= lenA; r++)
+        if (b.lo[r] > b.hi[r] || (r > 0 && b.hi[r - 1] + 1 < b.lo[r])) { err = "Inconsistent trace range due to max-diff heuristic"; return false; }
+    return true;
+}
+
 namespace {
 
 // STRAL-like position score of the sequence-only partition function (stral_score.cc:29-60);

@@ -75,6 +75,8 @@ int arcmatch_score(const ScoreTables &t, const Params &p, const Sequence &A, con
                    const std::vector<int> &wB);
 
 Band make_band(int lenA, int lenB, int max_diff);
+// band around a pairwise reference alignment (trace_controller.cc:44-215, :606-622)
+bool band_from_alignment(int lenA, int lenB, const std::string &aliA, const std::string &aliB, int delta, Band &b, std::string &err);
 // probability envelope (PFGotoh in 80-bit or 64-bit floating point on the host)
 void restrict_band_by_envelope(Band &band, const Sequence &A, const Sequence &B, const Params &p);
 // score parameters of the envelope partition function as the reference passes them (main_helper.icc:389-400)

@@ -147,6 +147,7 @@ struct PairRec {
     int64_t score = 0; bool neg_inf = true; int max_i = 0, max_j = 0;
     std::vector<int> edges_a, edges_b; std::string str_a, str_b; bool traced = false;
     double pf_Z = 0; bool pf_done = false;   // LocARNA-P inside
+    bool band_initial = false;   // band given by the caller is the range BEFORE the probability envelope (reference alignment, anchors)
     bool restricted = false; int r_sa = 1, r_sb = 1, r_ea = 0, r_eb = 0;   // AlignerRestriction of the top level (k-best)
 };
 
@@ -414,7 +415,21 @@ int lb200_seq_get(const lb200_ctx *c, int seq, char *name, int name_cap, char *s
     return LB200_OK;
 }
 
-int lb200_pair_add(lb200_ctx *c, int seqA, int seqB, const int *min_col, const int *max_col) {
+static int pair_add(lb200_ctx *c, int seqA, int seqB, const int *min_col, const int *max_col, bool initial);
+int lb200_pair_add(lb200_ctx *c, int seqA, int seqB, const int *min_col, const int *max_col) { return pair_add(c, seqA, seqB, min_col, max_col, false); }
+int lb200_pair_add_restricted(lb200_ctx *c, int seqA, int seqB, const int *min_col, const int *max_col) {
+    if (!min_col || !max_col) return LB200_ERR_ARG;
+    return pair_add(c, seqA, seqB, min_col, max_col, true);
+}
+int lb200_band_from_alignment(int lenA, int lenB, const char *aliA, const char *aliB, int delta, int *min_col, int *max_col) {
+    if (lenA < 0 || lenB < 0 || !aliA || !aliB || !min_col || !max_col) return LB200_ERR_ARG;
+    Band b;
+    std::string err;
+    if (!band_from_alignment(lenA, lenB, aliA, aliB, delta, b, err)) { fprintf(stderr, "locarna_b200: %s\n", err.c_str()); return LB200_ERR_ARG; }
+    std::copy(b.lo.begin(), b.lo.end(), min_col); std::copy(b.hi.begin(), b.hi.end(), max_col);
+    return LB200_OK;
+}
+static int pair_add(lb200_ctx *c, int seqA, int seqB, const int *min_col, const int *max_col, bool initial) {
     if (!c || seqA < 0 || seqB < 0 || seqA >= (int)c->seqs.size() || seqB >= (int)c->seqs.size()) return LB200_ERR_ARG;
     if ((min_col == nullptr) != (max_col == nullptr)) return LB200_ERR_ARG;
     PairRec r;
@@ -431,6 +446,7 @@ int lb200_pair_add(lb200_ctx *c, int seqA, int seqB, const int *min_col, const i
             if (r.band.lo[i] > r.band.hi[i]) return fail(c, LB200_ERR_ARG, "empty band row %d", i);
             if (i > 0 && (r.band.lo[i] < r.band.lo[i - 1] || r.band.hi[i] < r.band.hi[i - 1])) return fail(c, LB200_ERR_ARG, "band is not monotone in row %d", i);
         }
+        r.band_initial = initial;
     }
     c->pairs.push_back(std::move(r));
     c->res.valid = false;
@@ -542,7 +558,7 @@ static int derive_bands(lb200_ctx *c) {
     for (int k = 0; k < P; k++) {
         PairRec &r = c->pairs[k];
         if (r.banded) continue;
-        if (!r.band.lo.empty()) { r.banded = true; continue; }
+        if (!r.band.lo.empty() && !r.band_initial) { r.banded = true; continue; }
         todo.push_back(k);
     }
     c->env_device_pairs = 0; c->env_host_pairs = 0;
@@ -570,7 +586,7 @@ static int derive_bands(lb200_ctx *c) {
                 for (int t = t0; t < t1; t++) {
                     PairRec &r = c->pairs[todo[t]];
                     const Sequence &A = c->seqs[r.seqA], &B = c->seqs[r.seqB];
-                    r.band = make_band(A.len, B.len, c->params.max_diff);
+                    if (!r.band_initial) r.band = make_band(A.len, B.len, c->params.max_diff);
                     EnvPair &e = ep[t];
                     e.lenA = A.len; e.lenB = B.len; e.codesA = c->seq_codes_off[r.seqA]; e.codesB = c->seq_codes_off[r.seqB];
                     e.probA = c->seq_prob_off[r.seqA]; e.probB = c->seq_prob_off[r.seqB]; e.pad = 0;
@@ -625,7 +641,7 @@ static int derive_bands(lb200_ctx *c) {
         if (!on_host[t]) return;
         PairRec &r = c->pairs[todo[t]];
         const Sequence &A = c->seqs[r.seqA], &B = c->seqs[r.seqB];
-        r.band = make_band(A.len, B.len, c->params.max_diff);
+        if (!r.band_initial) r.band = make_band(A.len, B.len, c->params.max_diff);
         restrict_band_by_envelope(r.band, A, B, c->params);
         r.banded = true;
     });

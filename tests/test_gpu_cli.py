@@ -149,3 +149,18 @@ def test_mlocarna_tree_stage_shares_and_gpus(tmp_path):
     r1 = subprocess.run([CLI_TREE, "--gpus", "1"] + files, capture_output=True, text=True)
     r0 = subprocess.run([CLI_TREE] + files, capture_output=True, text=True)
     assert r1.returncode == 0 and r1.stdout == r0.stdout and r0.stdout
+
+
+CASES_REFALN = json.load(open(os.path.join(GOLD, "maxdiffaln_outputs.json")))
+
+
+@pytest.mark.parametrize("case", CASES_REFALN, ids=lambda c: "%s-%s" % ("_".join(x[:12] for x in c["args"]), c["A"]))
+def test_cli_reference_alignment_bands(case):
+    """--max-diff d with --max-diff-pw-aln / --max-diff-aln: band around a reference alignment (TraceController from a MultipleAlignment,
+    trace_controller.cc:406-539), then the probability envelope inside it; stdout / error exits of the reference binary
+    (tools/make_golden_maxdiffaln.py)."""
+    r = subprocess.run([CLI, case["A"], case["B"]] + case["args"], capture_output=True, text=True, cwd=GOLD)
+    assert r.returncode == case["rc"], r.stderr
+    assert r.stdout == case["stdout"]
+    if case["rc"] != 0:
+        assert r.stderr == case["stderr"]

@@ -1,6 +1,7 @@
 """Host-side logic of the product (PP reader, base pairs, band incl. 80-bit envelope, arc matches, arc-match
 scores) against the oracle port, on a host-only context (no GPU needed)."""
 import itertools
+import os
 
 import pytest
 
@@ -90,3 +91,32 @@ def test_max_bps_length_ratio_refuses_ties_at_the_cut():
     with pytest.raises(capi.Error):
         ctx.add_seq("tie", seq, [(1, 12, 0.9), (2, 11, 0.7), (3, 10, 0.7), (4, 9, 0.6)])
     ctx.close()
+
+
+def test_band_from_reference_alignment_equals_reference():
+    """lb200_band_from_alignment (TraceRange from a pairwise reference alignment, trace_controller.cc:44-215) against the compiled
+    reference's TraceController (ref_harness --max-diff-pw-aln, envelope off), for the reference's own alignment, a random other
+    alignment and other gap symbols."""
+    import random
+    import pytest
+    from locarna_b200 import capi
+    if not O.have_ref():
+        pytest.skip("compiled reference not available")
+    rng = random.Random(5)
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    for a, b in (("g0.pp", "g1.pp"), ("g4.pp", "g5.pp")):
+        pa, pb = os.path.join(G, a), os.path.join(G, b)
+        r = O.ref_align(pa, pb, {}, dump="aln")
+        sa, sb = r["rowA"].replace("-", ""), r["rowB"].replace("-", "")
+        L = max(len(sa), len(sb)) + 4
+
+        def regap(s):
+            pos = set(rng.sample(range(L), L - len(s)))
+            it = iter(s)
+            return "".join("-" if k in pos else next(it) for k in range(L))
+        for A, B in ((r["rowA"], r["rowB"]), (regap(sa), regap(sb)), (r["rowA"].replace("-", "~"), r["rowB"].replace("-", "."))):
+            for delta in (0, 1, 4, 15):
+                ref = O.ref_align(pa, pb, {"max-diff": delta, "max-diff-pw-aln": A + "&" + B, "min-trace-probability": 0}, dump="band", do_trace=False)
+                assert capi.band_from_alignment(len(sa), len(sb), A, B, delta) == (ref["min_col"], ref["max_col"])
+    with pytest.raises(capi.Error):
+        capi.band_from_alignment(5, 4, "ACGU-", "AC-GU", 1)       # rows do not spell out sequences of these lengths
