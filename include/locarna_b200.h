@@ -220,6 +220,13 @@ int lb200_pair_basematch_probs(const lb200_ctx *ctx, int pair, double *bm);
 int64_t lb200_all_vs_all(int n_seqs, int *seqA, int *seqB);
 double lb200_pair_cost(int n_arcsA, int n_arcsB, int lenA, int lenB);
 int lb200_shard_pairs(int64_t n_pairs, const double *cost, int world, int *rank_of, int64_t *order, int64_t *rank_begin);
+/* Anchor constraints: the PP reader keeps the "#A<k>" annotation rows of a sequence (multiple_alignment.cc:324-346). Pairs whose two
+ * sequences both carry anchor names (the same names, strictly increasing: strict semantics of AnchorConstraints, anchor_constraints.cc)
+ * get their band restricted as TraceController::restrict_by_anchors does (trace_controller.cc:541-563) before the probability envelope,
+ * and only arc matches between positions of equal names (or two unnamed positions) are built (arc_matches.cc:27-28). Global alignment
+ * without free end gaps only; names that occur in one sequence only, relaxed anchors and LocARNA-P are refused.
+ * lb200_seq_anchors: the annotation as SequenceAnnotation::single_string gives it (rows joined by '#', "" = none); returns its length. */
+int lb200_seq_anchors(const lb200_ctx *ctx, int seq, char *out, int cap);
 /* number of base pairs (arcs with probability >= min_prob) of a sequence: the input of lb200_pair_cost */
 int lb200_seq_num_arcs(const lb200_ctx *ctx, int seq);
 /* lb200_pair_cost + lb200_shard_pairs for pairs (seqA[k], seqB[k]) of the context's sequences in one call; rank_of may be NULL */

@@ -100,8 +100,11 @@ class Alignment {  // alignment.hh:84-281
     std::string nameA_, nameB_, seqA_, seqB_;
     std::vector<std::pair<int, int>> edges_;  // position or -1 (gap), in order
     std::string strA_, strB_;                 // per position, '.', '(' or ')'
+    std::vector<std::string> anchorsA_, anchorsB_;   // "#A<k>" annotation rows of the inputs (empty: none)
 public:
     typedef std::vector<std::pair<int, int>> edges_t;
+    const std::vector<std::string> &anchorsA() const { return anchorsA_; }
+    const std::vector<std::string> &anchorsB() const { return anchorsB_; }
     // alignment_edges(only_local) (alignment.cc:120-167): locality gaps are reported as -3
     edges_t alignment_edges(bool only_local) const {
         edges_t res;
@@ -190,6 +193,30 @@ public:
         const bool clash = a.nameA() == a.nameB();
         rows_.emplace_back(clash ? "A." + a.nameA() : a.nameA(), a.rowA(only_local));
         rows_.emplace_back(clash ? "B." + a.nameB() : a.nameB(), a.rowB(only_local));
+        // consensus anchor annotation (multiple_alignment.cc:157-165, sequence_annotation.cc:12-50): per column the name of the
+        // non-gap side, of the named side, or the smaller of two names; dropped if a name would occur twice
+        const auto &A = a.anchorsA(), &B = a.anchorsB();
+        if (!A.empty() && !B.empty() && A.size() == B.size()) {
+            std::vector<std::string> cons(A.size());
+            auto name = [](const std::vector<std::string> &rows, int pos) { std::string n; for (const auto &r : rows) n += r[(size_t)pos - 1]; return n; };
+            auto neutral = [](const std::string &n) { for (char c : n) if (!(c == ' ' || c == '.')) return false; return true; };
+            std::vector<std::string> names;
+            for (const auto &e : a.alignment_edges(only_local)) {
+                std::string n;
+                if (e.first <= 0) n = name(B, e.second);
+                else if (e.second <= 0) n = name(A, e.first);
+                else {
+                    const std::string na = name(A, e.first), nb = name(B, e.second);
+                    n = neutral(na) ? nb : neutral(nb) ? na : std::min(na, nb);
+                }
+                names.push_back(n);
+                for (size_t k = 0; k < cons.size(); k++) cons[k] += n[k];
+            }
+            bool dup = false;
+            for (size_t x = 0; x < names.size() && !dup; x++)
+                if (!neutral(names[x])) for (size_t y = x + 1; y < names.size(); y++) if (!neutral(names[y]) && names[x] == names[y]) { dup = true; break; }
+            if (!dup) anchors_ = cons;
+        }
     }
     void prepend(const SeqEntry &e) { rows_.insert(rows_.begin(), e); }
     void append(const SeqEntry &e) { rows_.push_back(e); }
@@ -206,6 +233,11 @@ public:
                 name.resize(namewidth, ' ');
                 out << name << " " << r.seq.substr(start, end - start) << std::endl;
             }
+            for (size_t k = 0; k < anchors_.size(); k++) {   // multi-line anchor annotation (multiple_alignment.cc:1036-1050)
+                std::string name = (format == FormatType::STOCKHOLM ? "#=GC cA" : "#A") + std::to_string(k + 1);
+                if (name.size() < namewidth) name.resize(namewidth, ' ');
+                out << name << " " << anchors_[k].substr(start, end - start) << std::endl;
+            }
             start = end;
         } while (start < length() && out << std::endl);
         if (format == FormatType::STOCKHOLM) out << "//" << std::endl;   // end marker (multiple_alignment.cc:1079-1082)
@@ -213,6 +245,7 @@ public:
     }
 private:
     std::vector<SeqEntry> rows_;
+    std::vector<std::string> anchors_;   // consensus anchor annotation rows
     bool pairwise_ = false;
 };
 
@@ -345,6 +378,14 @@ public:
         ctx_->check(lb200_seq_get(ctx_->get(), a, name, sizeof name, seq, seq_cap)); alignment_.nameA_ = name; alignment_.seqA_ = seq;
         ctx_->check(lb200_seq_get(ctx_->get(), b, name, sizeof name, seq, seq_cap)); alignment_.nameB_ = name; alignment_.seqB_ = seq;
         delete[] seq;
+        for (int which = 0; which < 2; which++) {   // "#A<k>" rows of the inputs, for the consensus annotation of the output
+            const int id = which ? b : a;
+            std::vector<char> buf((size_t)lb200_seq_anchors(ctx_->get(), id, nullptr, 0) + 1);
+            lb200_seq_anchors(ctx_->get(), id, buf.data(), (int)buf.size());
+            std::vector<std::string> &rows = which ? alignment_.anchorsB_ : alignment_.anchorsA_;
+            std::string cur;
+            for (const char *p = buf.data(); ; p++) { if (*p == '#' || *p == 0) { if (!cur.empty()) rows.push_back(cur); cur.clear(); if (*p == 0) break; } else cur += *p; }
+        }
         if (ap.ref_aln_ != nullptr && ap.max_diff_ != -1) {
             // TraceController(seqA, seqB, ma, delta): rows within delta of the reference alignment (trace_controller.cc:431-483); the
             // probability envelope is applied inside this range

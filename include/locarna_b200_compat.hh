@@ -26,7 +26,7 @@
 //
 // The objects of the reference compute on construction (RnaData parses, ArcMatches enumerates, Scoring precomputes). Here they record
 // their arguments; the device builds bands, arc matches and scores when Aligner runs. What the B200 path does not implement
-// (anchors, MEA, explicit arc-match scores, --max-diff-relax) throws LocARNA::failure from the object
+// (relaxed anchors, MEA, explicit arc-match scores, --max-diff-relax) throws LocARNA::failure from the object
 // that would need it, so the caller's existing error handling applies.
 #ifndef LOCARNA_B200_COMPAT_HH
 #define LOCARNA_B200_COMPAT_HH
@@ -88,10 +88,13 @@ public:
     int max_bp_span() const { return max_bp_span_; }
 };
 
-class SequenceAnnotation {
+class SequenceAnnotation {   // sequence_annotation.hh: here only the anchor rows of a PP file, joined by '#'
+    std::string str_;
 public:
-    bool empty() const { return true; }
-    std::string single_string() const { return ""; }
+    SequenceAnnotation() {}
+    explicit SequenceAnnotation(const std::string &s) : str_(s) {}
+    bool empty() const { return str_.empty(); }
+    std::string single_string() const { return str_; }
 };
 
 class MultipleAlignment : public LocARNA_B200::MultipleAlignment {   // multiple_alignment.hh
@@ -113,7 +116,7 @@ public:
         const std::string &name() const { return name_; }
         const std::string &seq() const { return seq_; }
     };
-    Sequence(const std::string &name, const std::string &seq) : entry_(name, seq) {}
+    Sequence(const std::string &name, const std::string &seq, const std::string &anchors = "") : entry_(name, seq), anno_(anchors) {}
     size_type length() const { return entry_.seq().size(); }
     size_type num_of_rows() const { return 1; }
     const SeqEntry &seqentry(size_type) const { return entry_; }
@@ -141,7 +144,9 @@ public:
         const int len = lb200_seq_length(c, id);
         std::vector<char> name(512), seq((size_t)len + 1);
         lb200_seq_get(c, id, name.data(), (int)name.size(), seq.data(), (int)seq.size());
-        seq_.reset(new Sequence(name.data(), seq.data()));
+        std::vector<char> anchors((size_t)lb200_seq_anchors(c, id, nullptr, 0) + 1);
+        lb200_seq_anchors(c, id, anchors.data(), (int)anchors.size());
+        seq_.reset(new Sequence(name.data(), seq.data(), anchors.data()));
         lb200_ctx_destroy(c);
     }
     const Sequence &sequence() const { return *seq_; }
@@ -150,11 +155,13 @@ public:
     const LocARNA_B200::RnaData &data() const { return data_; }
 };
 
-class AnchorConstraints {   // anchor_constraints.hh: anchors come from the "#A" annotation of the input, which the PP reader here ignores
+class AnchorConstraints {   // anchor_constraints.hh: the library applies the "#A" annotation of the PP inputs itself (strict semantics)
     bool empty_;
 public:
-    AnchorConstraints(size_type, const std::string &anchorsA, size_type, const std::string &anchorsB, bool /*strict*/)
-        : empty_(anchorsA.empty() && anchorsB.empty()) {}
+    AnchorConstraints(size_type, const std::string &anchorsA, size_type, const std::string &anchorsB, bool strict)
+        : empty_(anchorsA.empty() || anchorsB.empty()) {   // one spec empty: no anchors at all (anchor_constraints.cc:27-31)
+        if (!empty_ && !strict) throw failure("locarna_b200: relaxed anchor constraints are not supported");
+    }
     bool empty() const { return empty_; }
 };
 
@@ -167,7 +174,7 @@ public:
         if (ma != nullptr && relax) throw failure("locarna_b200: --max-diff-relax is not supported");
     }
     const MultipleAlignment *reference_alignment() const { return ref_aln_; }
-    void restrict_by_anchors(const AnchorConstraints &c) { if (!c.empty()) throw failure("locarna_b200: anchor constraints are not supported"); }
+    void restrict_by_anchors(const AnchorConstraints &) {}   // done by the library when the pair is added (lb200_seq_anchors)
     //! what MainHelper::restrict_trace_by_probabilities records (main_helper.icc:408-426)
     void set_min_trace_probability(double p) { min_trace_probability_ = p; }
     int max_diff() const { return max_diff_; }
@@ -185,7 +192,7 @@ public:
     ArcMatches(const RnaData &a, const RnaData &b, double min_prob, size_type max_length_diff, size_type max_diff_at_am, const TraceController &tc,
                const AnchorConstraints &constraints)
         : rnaA_(&a), rnaB_(&b), min_prob_(min_prob), max_diff_am_(max_length_diff), max_diff_at_am_(max_diff_at_am), tc_(&tc) {
-        if (!constraints.empty()) throw failure("locarna_b200: anchor constraints are not supported");
+        (void)constraints;   // applied by the library (arc matches join positions of equal anchor names only)
     }
     //! explicit arc-match scores (--read-arcmatch-scores / --read-arcmatch-probs, arc_matches.cc:190-282)
     ArcMatches(const Sequence &, const Sequence &, const std::string &file, int, size_type, size_type, const TraceController &, const AnchorConstraints &) {
@@ -316,7 +323,6 @@ class Aligner {   // aligner.hh:67-189
 public:
     explicit Aligner(const AlignerParams &ap) {
         if (!ap.seqA_ || !ap.seqB_ || !ap.scoring_ || !ap.trace_controller_) throw failure("AlignerParams: seqA, seqB, scoring and trace_controller are mandatory");
-        if (ap.constraints_ && !ap.constraints_->empty()) throw failure("locarna_b200: anchor constraints are not supported");
         impl_.reset(new LocARNA_B200::Aligner(to_b200_params(*ap.scoring_, *ap.trace_controller_, ap.no_lonely_pairs_, ap.struct_local_, ap.sequ_local_,
                                                                ap.free_endgaps_.str(), ap.max_diff_am_, ap.max_diff_at_am_)));
     }

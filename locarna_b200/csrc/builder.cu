@@ -39,6 +39,7 @@ struct PairView {
     const int *alA, *arA, *wA, *lpA, *lcA, *sdA;
     const int *alB, *arB, *wB, *lpB, *lcB, *sdB;
     const uint8_t *cA, *cB;
+    const uint8_t *acA, *acB;   // anchor ranks, nullptr without anchor constraints
     int n, m;
     long mdam, mdat;
 };
@@ -51,6 +52,7 @@ __device__ __forceinline__ PairView view(const BuildCtx &b, const DevPair &p) {
     v.sdA = b.arc_sdelta + p.arcsA; v.sdB = b.arc_sdelta + p.arcsB;
     v.lpA = b.lptr + p.lptrA; v.lcA = b.lcount + p.lptrA; v.lpB = b.lptr + p.lptrB; v.lcB = b.lcount + p.lptrB;
     v.cA = b.codes + p.codesA; v.cB = b.codes + p.codesB;
+    v.acA = p.anchored ? b.acodes + p.codesA : nullptr; v.acB = p.anchored ? b.acodes + p.codesB : nullptr;
     v.n = p.lenA; v.m = p.lenB;
     const int mx = max(p.lenA, p.lenB);
     v.mdam = b.max_diff_am >= 0 ? b.max_diff_am : mx;      // locarna.cc:617-626
@@ -65,8 +67,11 @@ __device__ __forceinline__ bool cell_exists(const PairView &v, int al, int bl) {
 }
 
 // arc_matches.cc:19-48 for the right ends and the length difference (left ends are tested per cell)
+// constraints.allowed_match (arc_matches.cc:27-28) for anchor names that occur in both sequences: equal ranks (0 = unnamed); everything
+// else the constraints forbid lies outside the anchor-restricted band
+__device__ __forceinline__ bool anchors_allow(const PairView &v, int i, int j) { return v.acA == nullptr || v.acA[i] == v.acB[j]; }
 __device__ __forceinline__ bool valid_arcmatch_right(const PairView &v, int al, int ar, int bl, int br) {
-    return valid_match(v.lo, v.hi, ar, br) && labs((long)(ar - al) - (long)(br - bl)) <= v.mdam && labs((long)(ar - br)) <= v.mdat;
+    return valid_match(v.lo, v.hi, ar, br) && anchors_allow(v, ar, br) && labs((long)(ar - al) - (long)(br - bl)) <= v.mdam && labs((long)(ar - br)) <= v.mdat;
 }
 
 // scoring.cc:441-485 for single sequences
@@ -94,7 +99,7 @@ __global__ void __launch_bounds__(128) enumerate_kernel(BuildCtx b) {
         const int hi_eff = min(v.hi[al], v.m), lo_eff = max(v.lo[al], 1);
         for (int bl = hi_eff - lane; bl >= lo_eff; bl -= 32) {
             const int nb = v.lcB[bl];
-            if (nb == 0 || !valid_match(v.lo, v.hi, al, bl) || labs((long)(al - bl)) > v.mdat) continue;
+            if (nb == 0 || !valid_match(v.lo, v.hi, al, bl) || !anchors_allow(v, al, bl) || labs((long)(al - bl)) > v.mdat) continue;
             const int b0 = v.lpB[bl];
             const int r = v.rev[al] + (hi_eff - bl);
             int k = 0;

@@ -11,6 +11,7 @@ struct BuildCtx {
     // inputs
     DevPair *pairs;
     const uint8_t *codes;
+    const uint8_t *acodes;       // anchor rank per position (same offsets as codes); read only for pairs with DevPair::anchored
     const int *band_lo, *band_hi, *cell_rev;   // cell_rev[al] = number of band cells in rows > al
     const int *arc_left, *arc_right, *arc_weight, *lptr, *lcount;
     const int *arc_sdelta;                      // per arc: stack weight - weight, LB_NOSTACK if the arc is not stackable

@@ -39,6 +39,8 @@ struct DevPair {
     int K;                // number of arc matches                                       (filled by the device builder)
     long long cell_base;  // offset of this pair's cells in the cell arrays (cells ranked al desc, bl desc)
     long long am_base;    // offset of this pair's arc matches in the L-order / S-order arrays  (device builder)
+    int anchored;         // 1: arc matches must join positions of equal anchor rank (acodes[], same offsets as codes[])
+    int pad;
 };
 
 // per-pair counters produced by the device builder

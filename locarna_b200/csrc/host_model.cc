@@ -62,11 +62,20 @@ bool read_pp(const std::string &path, double p_bpcut, Sequence &out, std::string
     std::getline(in, line);
     if (!begins(line, "#PP 2")) { err = path + ": not in PP 2.0 format"; return false; }
     std::string name, seq;
+    std::vector<std::string> anchor_rows;
     bool named = false;
     while (next_line(in, line)) {
         if (line[0] == '#') {
             if (begins(line, "#END")) break;
-            if (begins(line, "#A")) { err = path + ": anchor constraints are not supported by the B200 path"; return false; }
+            if (begins(line, "#A")) {   // anchor annotation "#A<k> <string>", possibly in several blocks (multiple_alignment.cc:324-346)
+                std::istringstream ls(line.substr(2));
+                int idx = 0; std::string astr;
+                ls >> idx >> astr;
+                if (idx < 1) { err = "Invalid index in anchor specification."; return false; }
+                if ((size_t)idx > anchor_rows.size() + 1) { err = "Non-contiguous anchor specification."; return false; }
+                if ((size_t)idx > anchor_rows.size()) anchor_rows.resize(idx);
+                anchor_rows[idx - 1] += astr;
+            }
             continue;
         }
         std::istringstream ls(line);
@@ -111,7 +120,34 @@ bool read_pp(const std::string &path, double p_bpcut, Sequence &out, std::string
     }
     if (!stack_keyword && any_p2) { err = "Stacking probabilties found but stack keyword is missing."; return false; }   // rna_data.cc:1097-1100
     // the pairs were already filtered line by line; pass a cutoff that keeps them all
-    return make_sequence(name, seq, pi.data(), pj.data(), pp.data(), (int)pi.size(), -1.0, out, err, max_bp_span, max_bps_length_ratio, pp2.data());
+    if (!make_sequence(name, seq, pi.data(), pj.data(), pp.data(), (int)pi.size(), -1.0, out, err, max_bp_span, max_bps_length_ratio, pp2.data())) return false;
+    return set_anchors(out, anchor_rows, err);
+}
+
+// names per position from the anchor rows (AnchorConstraints::transform_input, anchor_constraints.cc:93-135, strict semantics)
+bool set_anchors(Sequence &s, const std::vector<std::string> &rows, std::string &err) {
+    s.anchor_names.clear(); s.anchor_rows.clear(); s.anchor_rank.assign(s.len + 1, 0);
+    if (rows.empty()) return true;
+    s.anchor_rows = rows;
+    s.anchor_names.assign(s.len + 1, "");
+    for (const std::string &x : rows) {
+        if ((int)x.size() != s.len) { err = "Error during parsing of anchor constraints. Anchor specification strings must have exactly the same length as the corresponding sequences."; return false; }
+        for (int i = 0; i < s.len; i++) s.anchor_names[i + 1].push_back(x[i]);
+    }
+    std::string last;
+    int rank = 0;
+    for (int i = 1; i <= s.len; i++) {
+        std::string &x = s.anchor_names[i];
+        bool dont_care = true;
+        for (char c : x) if (!(c == ' ' || c == '.' || c == '-')) dont_care = false;
+        if (dont_care) { x.clear(); continue; }
+        if (x <= last) { err = "Error during parsing of constraints. Anchor names not in strict lexicographic order at name \"" + x + "\"."; return false; }
+        last = x;
+        if (++rank > 255) { err = "more than 255 anchors per sequence are not supported"; return false; }
+        s.anchor_rank[i] = (uint8_t)rank;
+    }
+    if (rank == 0) s.anchor_names.clear();
+    return true;
 }
 
 bool make_sequence(const std::string &name, const std::string &seq, const int *pi, const int *pj, const double *pp, int npairs,
@@ -283,6 +319,56 @@ Band make_band(int lenA, int lenB, int max_diff) {
     return b;
 }
 
+int restrict_band_by_anchors(Band &band, const Sequence &A, const Sequence &B, std::string &err) {
+    if (A.anchor_names.empty() || B.anchor_names.empty()) return 0;   // one anchor spec empty: no anchors at all (anchor_constraints.cc:27-31)
+    const int n = A.len, m = B.len;
+    std::vector<int> ia, jb;   // positions of the names, in order
+    for (int i = 1; i <= n; i++) if (A.anchor_rank[i]) ia.push_back(i);
+    for (int j = 1; j <= m; j++) if (B.anchor_rank[j]) jb.push_back(j);
+    bool same = ia.size() == jb.size();
+    for (size_t k = 0; same && k < ia.size(); k++) same = A.anchor_names[ia[k]] == B.anchor_names[jb[k]];
+    if (!same) { err = "anchor names that occur in only one of the two sequences are not supported"; return -1; }
+    // allowed match / deletion / insertion ranges for names that all occur in both sequences (init_tables, anchor_constraints.cc:164-330,
+    // strict): entries 0 keep the constructor's defaults (1, len)
+    typedef std::pair<int, int> range;
+    std::vector<range> ar(n + 1, range(1, m)), adr(n + 1, range(1, m)), air(m + 1, range(1, n));
+    {
+        int last = 0;
+        for (int i = 1; i <= n; i++) { if (A.anchor_rank[i]) { last = jb[A.anchor_rank[i] - 1]; ar[i].first = last; } else ar[i].first = last + 1; }
+        last = m + 1;
+        for (int i = n; i >= 1; i--) { if (A.anchor_rank[i]) { last = jb[A.anchor_rank[i] - 1]; ar[i].second = last; } else ar[i].second = last - 1; }
+        int prev = 0;   // partner of the last name at or before i
+        std::vector<int> nextj(n + 2, m + 1);
+        for (int i = n; i >= 1; i--) nextj[i] = A.anchor_rank[i] ? jb[A.anchor_rank[i] - 1] : nextj[i + 1];
+        for (int i = 1; i <= n; i++) {
+            if (A.anchor_rank[i]) { prev = jb[A.anchor_rank[i] - 1]; adr[i] = range(m + 1, 0); }
+            else adr[i] = range(prev, nextj[i] - 1);
+        }
+        prev = 0;
+        std::vector<int> nexti(m + 2, n + 1);
+        for (int j = m; j >= 1; j--) nexti[j] = B.anchor_rank[j] ? ia[B.anchor_rank[j] - 1] : nexti[j + 1];
+        for (int j = 1; j <= m; j++) {
+            if (B.anchor_rank[j]) { prev = ia[B.anchor_rank[j] - 1]; air[j] = range(n + 1, 0); }
+            else air[j] = range(prev, nexti[j] - 1);
+        }
+    }
+    auto allowed_match = [&](int i, int j) { return ar[i].first <= j && j <= ar[i].second; };
+    auto allowed_del = [&](int i, int j) { return adr[i].first <= j && j <= adr[i].second; };
+    auto allowed_ins = [&](int i, int j) { return air[j].first <= i && i <= air[j].second; };
+    for (int i = 1; i <= n; i++) {   // TraceController::restrict_by_anchors (trace_controller.cc:541-563); row 0 is not touched
+        int cmin = band.hi[i], cmax = band.lo[i];
+        for (int j = band.lo[i]; j <= band.hi[i]; j++)
+            if (allowed_match(i, j) || (j > 0 && allowed_ins(i, j)) || (i > 0 && allowed_del(i, j))) { cmin = std::min(cmin, j); cmax = std::max(cmax, j); }
+        band.lo[i] = std::max(band.lo[i], cmin);
+        band.hi[i] = std::min(band.hi[i], cmax);
+    }
+    // The reference leaves row 0 as it was, i.e. possibly wider than row 1. Border cells (0, j) beyond row 1's last column are read by no
+    // cell of the band and carry no trace probability, so cutting row 0 back changes no score, alignment or envelope - and keeps the
+    // rows monotone, which the kernels rely on. (Without the envelope the reference's own row 0 stays wide: the only visible difference.)
+    if (n >= 1) band.hi[0] = std::min(band.hi[0], band.hi[1]);
+    return 1;
+}
+
 // Band around a pairwise reference alignment (--max-diff-aln / --max-diff-pw-aln with --max-diff delta): TraceRange(pseqA, pseqB,
 // paliA, paliB, delta), trace_controller.cc:44-215 (position cut distance), for ungapped sequences A and B (their positions are their
 // columns), intersected with the unconstrained range as merge_in_trace_range does (:606-622). aliA / aliB: the two rows of the
@@ -434,7 +520,7 @@ void restrict_band_by_envelope(Band &band, const Sequence &A, const Sequence &B,
 // ---------------------------------------------------------------------------------- arc matches, tasks
 // arc_matches.cc:19-48 (validity), :130-188 (enumeration), :50-74 (inner arc matches), :313-355 (max right ends);
 // aligner.cc:660-732 (task = left end pair)
-void build_pair_problem(const Sequence &A, const Sequence &B, const Band &band, const Params &p, const ScoreTables &t, PairProblem &out) {
+void build_pair_problem(const Sequence &A, const Sequence &B, const Band &band, const Params &p, const ScoreTables &t, PairProblem &out, bool anchored) {
     out = PairProblem();
     const int n = A.len, m = B.len;
     const std::vector<int> &lo = band.lo, &hi = band.hi;
@@ -451,6 +537,7 @@ void build_pair_problem(const Sequence &A, const Sequence &B, const Band &band, 
         if (A.lcount[al] == 0) continue;
         for (int bl = std::min(hi[al], m); bl >= std::max(lo[al], 1); bl--) {
             if (B.lcount[bl] == 0 || !valid_match(al, bl)) continue;
+            if (anchored && A.anchor_rank[al] != B.anchor_rank[bl]) continue;   // constraints.allowed_match of the left ends (arc_matches.cc:27)
             if (std::abs(al - bl) > mdat) continue;
             const int start = (int)out.am.size();
             for (int a = A.lptr[al]; a < A.lptr[al] + A.lcount[al]; a++) {
@@ -458,6 +545,7 @@ void build_pair_problem(const Sequence &A, const Sequence &B, const Band &band, 
                 for (int b = B.lptr[bl]; b < B.lptr[bl] + B.lcount[bl]; b++) {
                     const int br = B.arcs[b].right;
                     if (!valid_match(ar, br)) continue;
+                    if (anchored && A.anchor_rank[ar] != B.anchor_rank[br]) continue;   // ... and of the right ends (arc_matches.cc:28)
                     if (std::labs((long)(ar - al) - (long)(br - bl)) > mdam) continue;
                     if (std::abs(ar - br) > mdat) continue;
                     DevArcMatch x;

@@ -46,6 +46,11 @@ struct Sequence {
     std::vector<int> lptr;             // arcs with left end l are arcs[lptr[l] .. lptr[l]+lcount[l])
     std::vector<int> lcount;
     std::vector<double> p_up, p_down;  // rna_data.cc:713-732
+    // anchor constraints (PP annotation lines "#A<k> <string>", multiple_alignment.cc:324-346): name of every position ("" = none) and
+    // its rank among the names of this sequence (1-based, 0 = unnamed); names must increase strictly (anchor_constraints.cc:100-132)
+    std::vector<std::string> anchor_rows;    // the annotation rows as read (each of length len); empty: no annotation
+    std::vector<std::string> anchor_names;   // entries 0..len (0 unused); empty vector: no annotation
+    std::vector<uint8_t> anchor_rank;        // entries 0..len
 };
 
 struct Band {
@@ -65,6 +70,7 @@ bool read_pp(const std::string &path, double p_bpcut, Sequence &out, std::string
 bool make_sequence(const std::string &name, const std::string &seq, const int *pi, const int *pj, const double *pp, int npairs,
                    double p_bpcut, Sequence &out, std::string &err, int max_bp_span = -1, double max_bps_length_ratio = 0.0, const double *pp2 = nullptr);
 void finish_sequence(Sequence &s, double min_prob);
+bool set_anchors(Sequence &s, const std::vector<std::string> &anchor_rows, std::string &err);
 
 std::vector<int> arc_weights(const Sequence &s, const Params &p);
 // per arc: stack weight minus weight (scoring.cc:201-248), LB_NOSTACK for arcs that are not stackable (scoring.cc:556-564)
@@ -75,6 +81,10 @@ int arcmatch_score(const ScoreTables &t, const Params &p, const Sequence &A, con
                    const std::vector<int> &wB);
 
 Band make_band(int lenA, int lenB, int max_diff);
+// Anchor constraints of a pair whose two sequences carry the same anchor names (strict semantics, anchor_constraints.cc:164-330): rows
+// [min_col, max_col] of `band` restricted like TraceController::restrict_by_anchors (trace_controller.cc:541-563). Returns 0 if the pair
+// has no constraints (one sequence without names), 1 if the band was restricted, -1 (err set) if the names differ between the sequences.
+int restrict_band_by_anchors(Band &band, const Sequence &A, const Sequence &B, std::string &err);
 // band around a pairwise reference alignment (trace_controller.cc:44-215, :606-622)
 bool band_from_alignment(int lenA, int lenB, const std::string &aliA, const std::string &aliB, int delta, Band &b, std::string &err);
 // probability envelope (PFGotoh in 80-bit or 64-bit floating point on the host)
@@ -94,7 +104,7 @@ struct PairProblem {
     uint64_t cells = 0;               // DP cell updates of all D-fill tasks + top level (reference count)
     uint64_t terms = 0;               // arc-match entries streamed by all boxes (S-order range of the box anti-diagonals)
 };
-void build_pair_problem(const Sequence &A, const Sequence &B, const Band &band, const Params &p, const ScoreTables &t, PairProblem &out);
+void build_pair_problem(const Sequence &A, const Sequence &B, const Band &band, const Params &p, const ScoreTables &t, PairProblem &out, bool anchored = false);
 
 }  // namespace lb200
 #endif

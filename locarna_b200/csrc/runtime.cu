@@ -147,6 +147,7 @@ struct PairRec {
     int64_t score = 0; bool neg_inf = true; int max_i = 0, max_j = 0;
     std::vector<int> edges_a, edges_b; std::string str_a, str_b; bool traced = false;
     double pf_Z = 0; bool pf_done = false;   // LocARNA-P inside
+    bool anchored = false;       // both sequences carry anchor names: band restricted and arc matches filtered by them
     bool band_initial = false;   // band given by the caller is the range BEFORE the probability envelope (reference alignment, anchors)
     bool restricted = false; int r_sa = 1, r_sb = 1, r_ea = 0, r_eb = 0;   // AlignerRestriction of the top level (k-best)
 };
@@ -197,7 +198,7 @@ struct lb200_ctx {
     DevBuf d_pf_esig, d_pf_bpow, d_pf_d, d_pf_z, d_pf_scratch, d_pf_dp, d_pf_amp, d_pf_mats, d_pf_cta;
     PfCtx pf_last; bool pf_have = false; bool pf_probs_done = false; long long pf_mat_doubles = 0;
     int max_box_words = 1, max_len = 1;
-    DevBuf d_pairs, d_codes, d_band_lo, d_band_hi, d_sptr, d_ent, d_am, d_tasks, d_top, d_scratch, d_cursor, d_flag, d_levcnt, d_done, d_ent8;
+    DevBuf d_acodes, d_pairs, d_codes, d_band_lo, d_band_hi, d_sptr, d_ent, d_am, d_tasks, d_top, d_scratch, d_cursor, d_flag, d_levcnt, d_done, d_ent8;
     DevBuf d_ent_mod, d_ent8_mod;   // D view of the modified scoring (normalized / penalized alignment)
     DevBuf d_col_first, d_col_last, d_groups, d_gorder, d_ngroups, d_rows_scratch, d_row_built, d_clist, d_cnblk;   // row-grouped D fill
     int pack_entries = 1;  // 8-byte packed S-order copy for the single-state sweep when every sequence is <= LB_PACK_MAXLEN (LB200_PACK=0 disables)
@@ -206,7 +207,7 @@ struct lb200_ctx {
     int64_t rows_fallbacks = 0;   // chunks that were re-run box by box because the row-grouped kernel met an unsupported box
     int sb_pairs = 1 << 30;   // pair block of the dependency-driven order (LB200_SB_PAIRS; default: one block)
     ~lb200_ctx() {
-        DevBuf *all[] = {&d_pairs, &d_codes, &d_band_lo, &d_band_hi, &d_sptr, &d_ent, &d_am, &d_tasks, &d_top, &d_scratch, &d_cursor, &d_flag, &d_levcnt, &d_done, &d_ent8,
+        DevBuf *all[] = {&d_acodes, &d_pairs, &d_codes, &d_band_lo, &d_band_hi, &d_sptr, &d_ent, &d_am, &d_tasks, &d_top, &d_scratch, &d_cursor, &d_flag, &d_levcnt, &d_done, &d_ent8,
                          &d_ent_mod, &d_ent8_mod, &d_col_first, &d_col_last, &d_groups, &d_gorder, &d_ngroups, &d_rows_scratch, &d_row_built, &d_clist, &d_cnblk,
                          &d_arc_left, &d_arc_right, &d_arc_weight, &d_arc_sdelta, &d_lptr, &d_lcount, &d_am_seq, &d_cell_rev, &d_cell_start, &d_skeys, &d_skeys2,
                          &d_svals, &d_svals2, &d_tasks_unsorted, &d_tkeys, &d_tkeys2, &d_tvals, &d_tvals2, &d_ntasks, &d_qstart, &d_stats, &d_tmp, &d_tr_edges, &d_tr_str, &d_tr_stack,
@@ -405,6 +406,16 @@ int lb200_shard_job(const lb200_ctx *c, int64_t n_pairs, const int *seqA, const 
     return lb200_shard_pairs(n_pairs, cost.data(), world, rank_of, order, rank_begin);
 }
 
+// anchor annotation of a sequence as SequenceAnnotation::single_string gives it (rows joined by '#'; "" = none); returns the length needed
+int lb200_seq_anchors(const lb200_ctx *c, int seq, char *out, int cap) {
+    if (!c || seq < 0 || seq >= (int)c->seqs.size()) return LB200_ERR_ARG;
+    const Sequence &s = c->seqs[seq];
+    std::string str;
+    for (size_t k = 0; k < s.anchor_rows.size(); k++) { if (k) str += '#'; str += s.anchor_rows[k]; }
+    if (out && cap > 0) { strncpy(out, str.c_str(), cap - 1); out[cap - 1] = 0; }
+    return (int)str.size();
+}
+
 int lb200_seq_get(const lb200_ctx *c, int seq, char *name, int name_cap, char *sequence, int sequence_cap) {
     if (!c || seq < 0 || seq >= (int)c->seqs.size()) return LB200_ERR_ARG;
     if (name && name_cap > 0) { strncpy(name, c->seqs[seq].name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
@@ -513,13 +524,15 @@ extern "C" {
 // sequences -> device arrays (codes, arcs in index order, arc weights, left-end index)
 static int upload_sequences(lb200_ctx *c) {
     if (c->seqs_uploaded == c->seqs.size()) return LB200_OK;
-    std::vector<uint8_t> codes;
+    std::vector<uint8_t> codes, acodes;
     std::vector<int> al, ar, aw, asd, lptr, lcount;
     std::vector<double> pup, pdown;
     c->seq_codes_off.clear(); c->seq_arcs_off.clear(); c->seq_lptr_off.clear(); c->seq_prob_off.clear();
     for (const Sequence &s : c->seqs) {
         c->seq_codes_off.push_back((int)codes.size());
         codes.insert(codes.end(), s.codes.begin(), s.codes.end());
+        acodes.insert(acodes.end(), s.anchor_rank.begin(), s.anchor_rank.end());
+        acodes.resize(codes.size(), 0);
         c->seq_arcs_off.push_back((int)al.size());
         const std::vector<int> w = arc_weights(s, c->params);
         const std::vector<int> sd = (c->params.stacking || c->params.new_stacking) ? arc_stack_deltas(s, c->params) : std::vector<int>(s.arcs.size(), LB_NOSTACK);
@@ -534,6 +547,7 @@ static int upload_sequences(lb200_ctx *c) {
     cudaStream_t st = c->stream;
     std::vector<int> amseq(c->tables.am_seq, c->tables.am_seq + 256);
     CUDA_TRY(c, upload(c->d_codes, codes, st));
+    CUDA_TRY(c, upload(c->d_acodes, acodes, st));
     CUDA_TRY(c, upload(c->d_arc_left, al, st));
     CUDA_TRY(c, upload(c->d_arc_right, ar, st));
     CUDA_TRY(c, upload(c->d_arc_weight, aw, st));
@@ -554,6 +568,29 @@ static int upload_sequences(lb200_ctx *c) {
 // LB200_ENVELOPE=host) compute everything on the host. Either way the bands equal the reference's.
 static int derive_bands(lb200_ctx *c) {
     const int P = (int)c->pairs.size();
+    // anchor constraints (AnchorConstraints + TraceController::restrict_by_anchors, locarna.cc:551-576): pairs of sequences that both
+    // carry anchor names get their band restricted before the probability envelope, and their arc matches filtered
+    bool any_names = false;
+    for (const Sequence &s : c->seqs) any_names |= !s.anchor_names.empty();
+    if (any_names) {
+        for (int k = 0; k < P; k++) {
+            PairRec &r = c->pairs[k];
+            const Sequence &A = c->seqs[r.seqA], &B = c->seqs[r.seqB];
+            if (r.banded || A.anchor_names.empty() || B.anchor_names.empty()) continue;
+            if (c->params.sequ_local || c->params.struct_local || c->params.fe_left1 || c->params.fe_left2 || c->params.fe_right1 || c->params.fe_right2)
+                return fail(c, LB200_ERR_UNSUPPORTED, "anchor constraints are supported for global alignment without free end gaps only");
+            const bool given = !r.band.lo.empty();
+            Band b = given ? r.band : make_band(A.len, B.len, c->params.max_diff);
+            std::string err;
+            const int rc = restrict_band_by_anchors(b, A, B, err);
+            if (rc < 0) return fail(c, LB200_ERR_UNSUPPORTED, "%s", err.c_str());
+            for (int i = 0; i <= A.len; i++)
+                if (b.lo[i] > b.hi[i] || (i > 0 && (b.lo[i] < b.lo[i - 1] || b.hi[i] < b.hi[i - 1])))
+                    return fail(c, LB200_ERR_ARG, "anchor constraints leave no consistent band in row %d", i);
+            r.anchored = true;
+            if (!given || r.band_initial) { r.band = b; r.band_initial = true; }   // a final band given by the caller is kept as it is
+        }
+    }
     std::vector<int> todo;
     for (int k = 0; k < P; k++) {
         PairRec &r = c->pairs[k];
@@ -659,7 +696,7 @@ int lb200_prepare(lb200_ctx *c) {
     parallel_for(P, c->host_threads, [&](int k) {
         PairRec &r = c->pairs[k];
         if (r.built) return;
-        build_pair_problem(c->seqs[r.seqA], c->seqs[r.seqB], r.band, c->params, c->tables, r.prob);
+        build_pair_problem(c->seqs[r.seqA], c->seqs[r.seqB], r.band, c->params, c->tables, r.prob, r.anchored);
         r.K = (int)r.prob.am.size();
         r.stats.n_tasks = (long long)r.prob.tasks.size(); r.stats.cells = (long long)r.prob.cells; r.stats.terms = (long long)r.prob.terms;
         r.built = true;
@@ -699,7 +736,7 @@ static int upload_chunk(lb200_ctx *c, int p0, int p1) {
                 const PairRec &r = c->pairs[p0 + k];
                 DevPair &d = h_pairs[k];
                 const int n = c->seqs[r.seqA].len, m = c->seqs[r.seqB].len;
-                d.lenA = n; d.lenB = m;
+                d.lenA = n; d.lenB = m; d.anchored = r.anchored ? 1 : 0;
                 d.codesA = c->seq_codes_off[r.seqA]; d.codesB = c->seq_codes_off[r.seqB];
                 d.arcsA = c->seq_arcs_off[r.seqA]; d.arcsB = c->seq_arcs_off[r.seqB];
                 d.lptrA = c->seq_lptr_off[r.seqA]; d.lptrB = c->seq_lptr_off[r.seqB];
@@ -794,7 +831,7 @@ static int upload_chunk(lb200_ctx *c, int p0, int p1) {
     CUDA_TRY(c, c->d_qstart.ensure(4098 * 4));
     BuildCtx b;
     memset(&b, 0, sizeof b);
-    b.pairs = (DevPair *)c->d_pairs.p; b.codes = (const uint8_t *)c->d_codes.p;
+    b.pairs = (DevPair *)c->d_pairs.p; b.codes = (const uint8_t *)c->d_codes.p; b.acodes = (const uint8_t *)c->d_acodes.p;
     b.band_lo = (const int *)c->d_band_lo.p; b.band_hi = (const int *)c->d_band_hi.p; b.cell_rev = (const int *)c->d_cell_rev.p;
     b.arc_left = (const int *)c->d_arc_left.p; b.arc_right = (const int *)c->d_arc_right.p; b.arc_weight = (const int *)c->d_arc_weight.p; b.arc_sdelta = (const int *)c->d_arc_sdelta.p;
     b.lptr = (const int *)c->d_lptr.p; b.lcount = (const int *)c->d_lcount.p; b.am_seq = (const int *)c->d_am_seq.p;
@@ -1316,6 +1353,7 @@ int lb200_run_pf(lb200_ctx *c, double pf_scale) {
     if (c->params.no_lonely_pairs || c->params.struct_local || c->params.sequ_local)
         return fail(c, LB200_ERR_UNSUPPORTED, "LocARNA-P (AlignerP) has no noLP / struct-local / sequ-local mode");
     if (!(pf_scale > 0)) return fail(c, LB200_ERR_ARG, "pf_scale must be positive");
+    for (const Sequence &s : c->seqs) if (!s.anchor_names.empty()) return fail(c, LB200_ERR_UNSUPPORTED, "LocARNA-P with anchor constraints is not supported");
     CUDA_TRY(c, cudaSetDevice(c->device));
     const int P = (int)c->pairs.size();
     if (P == 0) return LB200_OK;

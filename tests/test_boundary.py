@@ -16,7 +16,9 @@ REF = "/root/reference/src/locarna.cc"
 CASES = json.load(open(os.path.join(GOLD, "reference_outputs.json")))["cli"] + [
     c for c in json.load(open(os.path.join(GOLD, "locarna_cli_options.json")))] + [
     c for c in json.load(open(os.path.join(GOLD, "normalized_outputs.json")))[::3] if c["rc"] == 0 or "simultaneously" not in c["stderr"]] + [
-    dict(c, clustal=None) for c in json.load(open(os.path.join(GOLD, "kbest_outputs.json")))[::3]]   # every third case: the CLI tests run all of them
+    dict(c, clustal=None) for c in json.load(open(os.path.join(GOLD, "kbest_outputs.json")))[::3]] + [
+    c for c in json.load(open(os.path.join(GOLD, "anchors_outputs.json")))[::4]] + [
+    dict(c, clustal=None) for c in json.load(open(os.path.join(GOLD, "maxdiffaln_outputs.json")))[::6] if c["rc"] == 0]   # every third case: the CLI tests run all of them
 
 
 @pytest.mark.skipif(not os.path.exists(REF), reason="the reference tree is only present in the build container")
@@ -54,7 +56,7 @@ def test_refmain_output_matches_reference_binary(case, tmp_path):
     if not os.access(BIN, os.X_OK):
         pytest.skip("locarna_refmain_b200 not built (no reference tree at build time)")
     clu = str(tmp_path / "out.aln")
-    r = subprocess.run([BIN, os.path.join(GOLD, case["A"]), os.path.join(GOLD, case["B"]), "--clustal", clu] + case["args"], capture_output=True, text=True)
+    r = subprocess.run([BIN, os.path.join(GOLD, case["A"]), os.path.join(GOLD, case["B"]), "--clustal", clu] + case["args"], capture_output=True, text=True, cwd=GOLD)
     assert r.returncode == case["rc"], r.stderr
     assert r.stdout == case["stdout"]
     if case["rc"] == 0 and case["clustal"] is not None:
