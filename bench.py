@@ -247,6 +247,8 @@ def main():
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from locarna_b200 import allpairs, capi
+    if world > 1:   # the ranks share the host cores: each library instance uses its part of them for parsing and table preparation
+        os.environ.setdefault("LB200_HOST_THREADS", str(max(2, cores // world)))
 
     def barrier():
         if dist is not None:

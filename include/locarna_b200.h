@@ -227,6 +227,9 @@ int lb200_shard_pairs(int64_t n_pairs, const double *cost, int world, int *rank_
  * without free end gaps only; names that occur in one sequence only, relaxed anchors and LocARNA-P are refused.
  * lb200_seq_anchors: the annotation as SequenceAnnotation::single_string gives it (rows joined by '#', "" = none); returns its length. */
 int lb200_seq_anchors(const lb200_ctx *ctx, int seq, char *out, int cap);
+/* Append the parsed sequences of another context (same min_prob / maxBPspan / max-bps-length-ratio / stacking); returns the index of the
+ * first one. For contexts that work off one job side by side (one per stream or device): every PP file is parsed once. */
+int lb200_seqs_copy(lb200_ctx *ctx, const lb200_ctx *src);
 /* number of base pairs (arcs with probability >= min_prob) of a sequence: the input of lb200_pair_cost */
 int lb200_seq_num_arcs(const lb200_ctx *ctx, int seq);
 /* lb200_pair_cost + lb200_shard_pairs for pairs (seqA[k], seqB[k]) of the context's sequences in one call; rank_of may be NULL */

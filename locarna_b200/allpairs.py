@@ -71,12 +71,20 @@ def align_share(paths, pair_a, pair_b, flags, device: int = 0, world: int = 1, r
     lanes = max(1, lanes)
     out = [None] * lanes
     err = []
+    ctxs = [None] * lanes
+    parsed = threading.Event()
 
     def work(lane):
-        ctx = None
         try:
-            ctx = capi.Context(device, flags)
-            first = ctx.add_pps(paths)
+            ctx = ctxs[lane] = capi.Context(device, flags)
+            if lane == 0:
+                first = ctx.add_pps(paths)            # every file is parsed once per rank; the other lanes copy the result
+                parsed.set()
+            else:
+                parsed.wait()
+                if err:
+                    return
+                first = ctx.copy_seqs_from(ctxs[0])
             shares = ctx.shard_job(pair_a + first, pair_b + first, world)
             mine = shares[rank][lane::lanes]          # descending cost, dealt out in turn: equal work per lane
             ctx.add_pairs_np(pair_a[mine] + first, pair_b[mine] + first)
@@ -86,9 +94,7 @@ def align_share(paths, pair_a, pair_b, flags, device: int = 0, world: int = 1, r
                          {"h2d": ctx.h2d_bytes, "d2h": ctx.d2h_bytes, "launches": ctx.launches, "env_device": dev, "env_host": host})
         except Exception as e:  # noqa: BLE001 - reported by the caller's thread
             err.append(e)
-        finally:
-            if ctx is not None:
-                ctx.close()
+            parsed.set()
 
     threads = [threading.Thread(target=work, args=(l,)) for l in range(1, lanes)]
     for t in threads:
@@ -96,6 +102,9 @@ def align_share(paths, pair_a, pair_b, flags, device: int = 0, world: int = 1, r
     work(0)
     for t in threads:
         t.join()
+    for ctx in ctxs:
+        if ctx is not None:
+            ctx.close()
     if err:
         raise err[0]
     stats = {k: sum(o[3][k] for o in out) for k in out[0][3]}

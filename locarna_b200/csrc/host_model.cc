@@ -104,17 +104,26 @@ bool read_pp(const std::string &path, double p_bpcut, Sequence &out, std::string
             } else if (begins(line, "#STACK")) stack_keyword = true;
             continue;
         }
-        std::istringstream ls(line);
-        long i, j; double p;
-        ls >> i >> j >> p;
-        if (ls.fail()) { err = "Cannot parse line \"" + line + "\" in base pairs section."; return false; }
+        // "i j p [p2]" (the all-vs-all stage parses hundreds of files per job: no stream object per line)
+        const char *cur = line.c_str();
+        char *end = nullptr;
+        const long i = strtol(cur, &end, 10);
+        bool bad = end == cur;
+        cur = end;
+        const long j = strtol(cur, &end, 10);
+        bad |= end == cur;
+        cur = end;
+        const double p = strtod(cur, &end);
+        bad |= end == cur;
+        cur = end;
+        if (bad) { err = "Cannot parse line \"" + line + "\" in base pairs section."; return false; }
         if (!(1 <= i && i < j && j <= (long)seq.size())) { err = "Invalid indices in PP input line \"" + line + "\"."; return false; }
         if (p <= cut) continue;
         if (max_bp_span >= 0 && j - i + 1 > max_bp_span) continue;
         double p2 = 0.0;
         if (stacking) {   // joint probability of (i, j) and (i+1, j-1), kept above the cutoff (rna_data.cc:1083-1093)
-            double v;
-            if (ls >> v) { if (v > cut) { p2 = v; any_p2 = true; } }
+            const double v = strtod(cur, &end);
+            if (end != cur && v > cut) { p2 = v; any_p2 = true; }
         }
         pi.push_back((int)i); pj.push_back((int)j); pp.push_back(p); pp2.push_back(p2);
     }
@@ -165,14 +174,25 @@ bool make_sequence(const std::string &name, const std::string &seq, const int *p
         out.codes[i] = (uint8_t)code;
     }
     out.cutoff = p_bpcut;
-    std::map<std::pair<int, int>, double> uniq;  // a repeated pair overwrites the earlier value (sparse matrix assignment)
-    std::map<std::pair<int, int>, double> joint;
-    for (int k = 0; k < npairs; k++) {
-        if (!(1 <= pi[k] && pi[k] < pj[k] && pj[k] <= out.len)) { err = "invalid base pair indices"; return false; }
-        if (pp[k] <= p_bpcut) continue;
-        if (max_bp_span >= 0 && pj[k] - pi[k] + 1 > max_bp_span) continue;  // rna_data.cc:1078, bp_span = j-i+1 (aux.hh:333)
-        uniq[std::make_pair(pi[k], pj[k])] = pp[k];
-        if (pp2 != nullptr && pp2[k] > 0) joint[std::make_pair(pi[k], pj[k])] = pp2[k];
+    // a repeated pair overwrites the earlier value (sparse matrix assignment): stable sort by (i, j), keep the last of every run
+    struct Rec { int i, j; double p, p2; };
+    std::vector<Rec> uniq;
+    {
+        std::vector<Rec> all;
+        all.reserve((size_t)npairs);
+        for (int k = 0; k < npairs; k++) {
+            if (!(1 <= pi[k] && pi[k] < pj[k] && pj[k] <= out.len)) { err = "invalid base pair indices"; return false; }
+            if (pp[k] <= p_bpcut) continue;
+            if (max_bp_span >= 0 && pj[k] - pi[k] + 1 > max_bp_span) continue;  // rna_data.cc:1078, bp_span = j-i+1 (aux.hh:333)
+            all.push_back(Rec{pi[k], pj[k], pp[k], (pp2 != nullptr && pp2[k] > 0) ? pp2[k] : -1.0});
+        }
+        std::stable_sort(all.begin(), all.end(), [](const Rec &x, const Rec &y) { return x.i != y.i ? x.i < y.i : x.j < y.j; });
+        for (size_t k = 0; k < all.size(); k++) {
+            if (!uniq.empty() && uniq.back().i == all[k].i && uniq.back().j == all[k].j) {
+                uniq.back().p = all[k].p;
+                if (all[k].p2 >= 0) uniq.back().p2 = all[k].p2;     // the joint value of an earlier line stays unless this line gives one
+            } else uniq.push_back(all[k]);
+        }
     }
     if (max_bps_length_ratio > 0.0) {
         // rna_data.cc:64-67, :1580-1601 (drop_worst_bps): only the `keep` most probable base pairs survive. The reference pops a
@@ -181,17 +201,19 @@ bool make_sequence(const std::string &name, const std::string &seq, const int *p
         const size_t keep = (size_t)(max_bps_length_ratio * out.len);
         if (uniq.size() > keep) {
             std::vector<double> ps;
-            for (auto &kv : uniq) ps.push_back(kv.second);
+            for (auto &kv : uniq) ps.push_back(kv.p);
             std::sort(ps.begin(), ps.end(), [](double x, double y) { return x > y; });
             if (keep > 0 && ps[keep - 1] == ps[keep]) { err = "--max-bps-length-ratio: equally probable base pairs at the cut (the reference's choice among them is unspecified)"; return false; }
             const double thr = keep > 0 ? ps[keep - 1] : 2.0;
-            for (auto it = uniq.begin(); it != uniq.end();) { if (it->second < thr) it = uniq.erase(it); else ++it; }
+            std::vector<Rec> kept;
+            for (auto &kv : uniq) if (!(kv.p < thr)) kept.push_back(kv);
+            uniq.swap(kept);
         }
     }
+    out.pp_i.reserve(uniq.size()); out.pp_j.reserve(uniq.size()); out.pp_p.reserve(uniq.size()); out.pp_p2.reserve(uniq.size());
     for (auto &kv : uniq) {
-        out.pp_i.push_back(kv.first.first); out.pp_j.push_back(kv.first.second); out.pp_p.push_back(kv.second);
-        auto it = joint.find(kv.first);
-        out.pp_p2.push_back(it == joint.end() ? 0.0 : it->second);
+        out.pp_i.push_back(kv.i); out.pp_j.push_back(kv.j); out.pp_p.push_back(kv.p);
+        out.pp_p2.push_back(kv.p2 > 0 ? kv.p2 : 0.0);
     }
     return true;
 }
@@ -209,8 +231,15 @@ void finish_sequence(Sequence &s, double min_prob) {
     });
     s.arcs.clear(); s.arc_prob.clear(); s.arc_joint.clear(); s.arc_inner.clear();
     s.lptr.assign(n + 2, 0); s.lcount.assign(n + 2, 0);
-    std::map<std::pair<int, int>, double> prob;   // RnaData::arc_prob of every pair the reader kept
-    for (size_t k = 0; k < s.pp_i.size(); k++) prob[std::make_pair(s.pp_i[k], s.pp_j[k])] = s.pp_p[k];
+    // RnaData::arc_prob of every pair the reader kept: pp_* is sorted by (i, j) ascending, so a binary search finds a pair
+    auto arc_prob_of = [&](int i, int j) -> double {
+        size_t lo = 0, hi = s.pp_i.size();
+        while (lo < hi) {
+            const size_t mid = (lo + hi) / 2;
+            if (s.pp_i[mid] < i || (s.pp_i[mid] == i && s.pp_j[mid] < j)) lo = mid + 1; else hi = mid;
+        }
+        return (lo < s.pp_i.size() && s.pp_i[lo] == i && s.pp_j[lo] == j) ? s.pp_p[lo] : 0.0;
+    };
     for (int k : order) {
         int l = s.pp_i[k];
         if (s.lcount[l] == 0) s.lptr[l] = (int)s.arcs.size();
@@ -218,8 +247,7 @@ void finish_sequence(Sequence &s, double min_prob) {
         s.arcs.push_back(Arc{s.pp_i[k], s.pp_j[k]});
         s.arc_prob.push_back(s.pp_p[k]);
         s.arc_joint.push_back(k < (int)s.pp_p2.size() ? s.pp_p2[k] : 0.0);
-        auto it = prob.find(std::make_pair(s.pp_i[k] + 1, s.pp_j[k] - 1));
-        s.arc_inner.push_back(it == prob.end() ? 0.0 : it->second);
+        s.arc_inner.push_back(arc_prob_of(s.pp_i[k] + 1, s.pp_j[k] - 1));
     }
     // pp_* is sorted by (i, j) ascending (std::map order)
     s.p_up.assign(n + 1, 0.0); s.p_down.assign(n + 1, 0.0);

@@ -371,6 +371,17 @@ int lb200_seqs_add_pp(lb200_ctx *c, int n, const char *const *paths) {
     return first;
 }
 
+// the parsed sequences of another context (same input filters): contexts that work off one job side by side parse every file once
+int lb200_seqs_copy(lb200_ctx *c, const lb200_ctx *src) {
+    if (!c || !src || c == src) return LB200_ERR_ARG;
+    if (c->params.min_prob != src->params.min_prob || c->params.max_bp_span != src->params.max_bp_span ||
+        c->params.max_bps_length_ratio != src->params.max_bps_length_ratio || (c->params.stacking || c->params.new_stacking) != (src->params.stacking || src->params.new_stacking))
+        return fail(c, LB200_ERR_ARG, "lb200_seqs_copy: the two contexts filter their inputs differently");
+    const int first = (int)c->seqs.size();
+    c->seqs.insert(c->seqs.end(), src->seqs.begin(), src->seqs.end());
+    return first;
+}
+
 int lb200_seq_add(lb200_ctx *c, const char *name, const char *seq, const int *pi, const int *pj, const double *pp, int n) {
     if (!c || !seq || n < 0 || (n > 0 && (!pi || !pj || !pp))) return LB200_ERR_ARG;
     Sequence s;
