@@ -141,7 +141,11 @@ int main(int argc, char **argv) {
     std::vector<std::string> errors(n_ctx);
     auto open_ctx = [&](int g) -> bool {
         if (lb200_ctx_create(device + g, &ctxs[g]) < 0) { errors[g] = "cannot create the device context"; return false; }
-        if (lb200_set_params(ctxs[g], &p) < 0 || lb200_seqs_add_pp(ctxs[g], n, files.data()) < 0) { errors[g] = lb200_last_error(ctxs[g]); return false; }
+        // every .pp file is parsed once (by the first context, on all host cores); the other devices' contexts copy the result
+        if (lb200_set_params(ctxs[g], &p) < 0 || (g == 0 ? lb200_seqs_add_pp(ctxs[g], n, files.data()) : lb200_seqs_copy(ctxs[g], ctxs[0])) < 0) {
+            errors[g] = lb200_last_error(ctxs[g]);
+            return false;
+        }
         return true;
     };
     if (!open_ctx(0)) { std::cerr << "ERROR: " << errors[0] << std::endl; return 255; }
