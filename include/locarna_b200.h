@@ -227,6 +227,10 @@ int lb200_shard_pairs(int64_t n_pairs, const double *cost, int world, int *rank_
  * without free end gaps only; names that occur in one sequence only, relaxed anchors and LocARNA-P are refused.
  * lb200_seq_anchors: the annotation as SequenceAnnotation::single_string gives it (rows joined by '#', "" = none); returns its length. */
 int lb200_seq_anchors(const lb200_ctx *ctx, int seq, char *out, int cap);
+/* --ribosum-file (src/locarna.cc:86-88, main_helper.icc:311-350, RibosumFreq(filename) ribosum.cc:40-200): base-match and arc-match score
+ * tables from a matrix file in the reference's extended ribosum format; NULL or "RIBOSUM85_60" selects the built-in matrix. Call it
+ * before pairs are added (the tables of resident batches are not rebuilt). */
+int lb200_set_ribosum_file(lb200_ctx *ctx, const char *path);
 /* Append the parsed sequences of another context (same min_prob / maxBPspan / max-bps-length-ratio / stacking); returns the index of the
  * first one. For contexts that work off one job side by side (one per stream or device): every PP file is parsed once. */
 int lb200_seqs_copy(lb200_ctx *ctx, const lb200_ctx *src);

@@ -74,6 +74,7 @@ struct ScoringParams {  // scoring.hh:59-166 (defaults of the locarna CLI)
     int match = 50, mismatch = 0, indel = -150, indel_opening = -750, unpaired_penalty = 0;
     int struct_weight = 200, tau_factor = 50, exclusion = 0, temperature_alipf = 300;
     bool use_ribosum = true, stacking = false, new_stacking = false, mea_scoring = false;
+    std::string ribosum_file;   // --ribosum-file: a matrix in extended ribosum format; empty or "RIBOSUM85_60": the built-in one
     //! background probability of a base pair (ScoringParams::exp_probA / exp_probB, scoring.hh:123-127); < 0: the CLI's default
     //! 1/(2 len) per sequence (locarna.cc:662-663). One value serves both sequences, as with `locarna --exp-prob`.
     double exp_prob = -1.0;
@@ -366,6 +367,7 @@ public:
         p.exp_prob = s.exp_prob; p.max_bp_span = ap.rnaA_->max_bp_span(); p.max_bps_length_ratio = ap.rnaA_->max_bps_length_ratio();
         p.no_lonely_pairs = ap.no_lonely_pairs_; p.struct_local = ap.struct_local_; p.sequ_local = ap.sequ_local_;
         strncpy(p.free_endgaps, ap.free_endgaps_.c_str(), sizeof(p.free_endgaps) - 1);
+        ctx_->check(lb200_set_ribosum_file(ctx_->get(), s.ribosum_file.empty() ? nullptr : s.ribosum_file.c_str()));
         ctx_->check(lb200_set_params(ctx_->get(), &p));
         const int a = lb200_seq_add_pp(ctx_->get(), ap.rnaA_->filename().c_str());
         ctx_->check(a);
@@ -587,6 +589,7 @@ public:
         if (ap.rnaA_->max_bp_span() != ap.rnaB_->max_bp_span() || ap.rnaA_->max_bps_length_ratio() != ap.rnaB_->max_bps_length_ratio())
             throw failure("locarna_b200: both RnaData objects must use the same max_bp_span and max_bps_length_ratio");
         p.exp_prob = s.exp_prob; p.max_bp_span = ap.rnaA_->max_bp_span(); p.max_bps_length_ratio = ap.rnaA_->max_bps_length_ratio();
+        ctx_->check(lb200_set_ribosum_file(ctx_->get(), s.ribosum_file.empty() ? nullptr : s.ribosum_file.c_str()));
         ctx_->check(lb200_set_params(ctx_->get(), &p));
         const int a = lb200_seq_add_pp(ctx_->get(), ap.rnaA_->filename().c_str());
         ctx_->check(a);

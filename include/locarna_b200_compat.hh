@@ -66,7 +66,20 @@ inline void split_at_separator(const std::string &s, char c, std::vector<std::st
 }
 
 class Ribosum { public: virtual ~Ribosum() {} };
-class RibosumFreq : public Ribosum {};   // the built-in RIBOSUM85_60 tables live in the library
+class RibosumFreq : public Ribosum {   // ribosum.hh: the built-in RIBOSUM85_60 tables live in the library; a file is read by it, too
+    std::string file_;
+public:
+    RibosumFreq() {}
+    explicit RibosumFreq(const std::string &file) : file_(file) {   // parse now, so that a bad file is reported where the reference reports it
+        lb200_ctx *c = nullptr;
+        if (lb200_ctx_create(LB200_DEVICE_NONE, &c) != LB200_OK) throw failure("locarna_b200: cannot create a host context");
+        const int rc = lb200_set_ribosum_file(c, file.c_str());
+        const std::string msg = rc < 0 ? lb200_last_error(c) : "";
+        lb200_ctx_destroy(c);
+        if (rc < 0) throw failure(msg);
+    }
+    const std::string &file() const { return file_; }
+};
 class Ribofit {};
 class MatchProbs {};
 
@@ -304,6 +317,7 @@ inline LocARNA_B200::AlignerParams to_b200_params(const Scoring &s, const TraceC
     sp.match = p.match_; sp.mismatch = p.mismatch_; sp.indel = p.indel_; sp.indel_opening = p.indel_opening_; sp.unpaired_penalty = p.unpaired_penalty_;
     sp.struct_weight = p.struct_weight_; sp.tau_factor = p.tau_factor_; sp.exclusion = p.exclusion_; sp.temperature_alipf = p.temperature_alipf_;
     sp.use_ribosum = p.ribosum_ != nullptr;
+    if (const RibosumFreq *rf = dynamic_cast<const RibosumFreq *>(p.ribosum_)) sp.ribosum_file = rf->file();
     sp.stacking = p.stacking_; sp.new_stacking = p.new_stacking_;
     // background probabilities: the library takes one value for both sequences, or derives 1 / (2 len) per sequence (locarna.cc:662-663)
     const double defA = prob_exp_f((int)s.rnaA().length()), defB = prob_exp_f((int)s.rnaB().length());
@@ -354,8 +368,8 @@ void init_ribo_matrix(const CLP &clp, std::unique_ptr<RibosumFreq> &ribosum, std
     ribosum.reset();
     if (clp.ribofit) throw failure("locarna_b200: ribofit is not supported");
     if (clp.use_ribosum) {
-        if (clp.ribosum_file != "RIBOSUM85_60") throw failure("locarna_b200: only the built-in RIBOSUM85_60 is supported");
-        ribosum.reset(new RibosumFreq());
+        if (clp.ribosum_file == "RIBOSUM85_60") ribosum.reset(new RibosumFreq());   // main_helper.icc:326-333
+        else ribosum.reset(new RibosumFreq(clp.ribosum_file));
     }
 }
 template <class CLP, class PF>

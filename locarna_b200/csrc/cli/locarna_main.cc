@@ -87,9 +87,7 @@ int main(int argc, char **argv) {
         switch (c) {
             case 'i': case O_INDEL: sp.indel = atoi(optarg); break;
             case O_INDEL_OPENING: sp.indel_opening = atoi(optarg); break;
-            case O_RIBOSUM_FILE:
-                if (std::string(optarg) != "RIBOSUM85_60") { std::cerr << "ERROR: only the built-in RIBOSUM85_60 is supported by locarna_b200." << std::endl; return 255; }
-                break;
+            case O_RIBOSUM_FILE: sp.ribosum_file = optarg; break;   // read when the aligner is set up (main_helper.icc:311-350)
             case O_USE_RIBOSUM: sp.use_ribosum = parse_bool(optarg); break;
             case 'm': case O_MATCH: sp.match = atoi(optarg); break;
             case 'M': case O_MISMATCH: sp.mismatch = atoi(optarg); break;

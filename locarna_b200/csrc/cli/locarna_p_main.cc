@@ -57,9 +57,7 @@ int main(int argc, char **argv) {
         switch (c) {
             case 'i': sp.indel = atoi(optarg); break;
             case O_INDEL_OPENING: sp.indel_opening = atoi(optarg); break;
-            case O_RIBOSUM_FILE:
-                if (std::string(optarg) != "RIBOSUM85_60") { std::cerr << "ERROR: only the built-in RIBOSUM85_60 is supported by locarna_p_b200." << std::endl; return 255; }
-                break;
+            case O_RIBOSUM_FILE: sp.ribosum_file = optarg; break;   // read when the aligner is set up (main_helper.icc:311-350)
             case O_USE_RIBOSUM: sp.use_ribosum = parse_bool(optarg); break;
             case 'm': sp.match = atoi(optarg); break;
             case 'M': sp.mismatch = atoi(optarg); break;

@@ -98,11 +98,11 @@ static int run_and_report() {
 }
 
 int main(int argc, char **argv) {
-    enum { O_INDEL_OPENING = 1000, O_USE_RIBOSUM, O_UNPAIRED_PENALTY, O_STRUCT_LOCAL, O_SEQU_LOCAL, O_FREE_ENDGAPS, O_MAX_DIFF_AT_AM, O_MIN_TRACE_PROB, O_NOLP,
+    enum { O_INDEL_OPENING = 1000, O_RIBOSUM_FILE, O_USE_RIBOSUM, O_UNPAIRED_PENALTY, O_STRUCT_LOCAL, O_SEQU_LOCAL, O_FREE_ENDGAPS, O_MAX_DIFF_AT_AM, O_MIN_TRACE_PROB, O_NOLP,
            O_MAXBPSPAN, O_MAX_BPS_LENGTH_RATIO, O_TEMPERATURE_ALIPF, O_CLUSTAL, O_LOCAL_FILE_OUTPUT, O_WRITE_STRUCTURE, O_WRITE_AMS, O_STACKING, O_NORMALIZED,
            O_PENALIZED, O_KBEST, O_BETTER, O_MAX_DIFF_ALN, O_MAX_DIFF_PW_ALN };
     static const struct option longopts[] = {
-        {"indel", required_argument, 0, 'i'}, {"indel-opening", required_argument, 0, O_INDEL_OPENING}, {"use-ribosum", required_argument, 0, O_USE_RIBOSUM},
+        {"indel", required_argument, 0, 'i'}, {"indel-opening", required_argument, 0, O_INDEL_OPENING}, {"use-ribosum", required_argument, 0, O_USE_RIBOSUM}, {"ribosum-file", required_argument, 0, O_RIBOSUM_FILE},
         {"match", required_argument, 0, 'm'}, {"mismatch", required_argument, 0, 'M'}, {"unpaired-penalty", required_argument, 0, O_UNPAIRED_PENALTY},
         {"struct-weight", required_argument, 0, 's'}, {"exp-prob", required_argument, 0, 'e'}, {"tau", required_argument, 0, 't'},
         {"exclusion", required_argument, 0, 'E'}, {"struct-local", required_argument, 0, O_STRUCT_LOCAL}, {"sequ-local", required_argument, 0, O_SEQU_LOCAL},
@@ -120,6 +120,7 @@ int main(int argc, char **argv) {
             case 'i': clp.indel = atoi(optarg); break;
             case O_INDEL_OPENING: clp.indel_opening = atoi(optarg); break;
             case O_USE_RIBOSUM: clp.use_ribosum = parse_bool(optarg); break;
+            case O_RIBOSUM_FILE: clp.ribosum_file = optarg; break;
             case 'm': clp.match = atoi(optarg); break;
             case 'M': clp.mismatch = atoi(optarg); break;
             case O_UNPAIRED_PENALTY: clp.unpaired_penalty = atoi(optarg); break;

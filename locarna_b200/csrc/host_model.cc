@@ -296,13 +296,13 @@ void make_score_tables(const Params &p, ScoreTables &t) {
     for (int a = 0; a < LB_NCODES; a++)
         for (int b = 0; b < LB_NCODES; b++) {
             long s;
-            if (a < 4 && b < 4) s = p.use_ribosum ? RIBOSUM85_60_SIGMA4[a * 4 + b] : (a == b ? p.match : p.mismatch);
+            if (a < 4 && b < 4) s = p.use_ribosum ? p.ribosum.sigma4[a * 4 + b] : (a == b ? p.match : p.mismatch);
             else if (a == CODE_N || b == CODE_N) s = 0;
             else s = (a == b) ? p.match : p.mismatch;
             t.dev.sigma8[a * LB_NCODES + b] = (int)s - 2 * p.unpaired_penalty;
         }
     for (int x = 0; x < 16; x++)
-        for (int y = 0; y < 16; y++) t.am_seq[x * 16 + y] = (int)(((long)p.tau * RIBOSUM85_60_AM16[x * 16 + y]) / 100);
+        for (int y = 0; y < 16; y++) t.am_seq[x * 16 + y] = (int)(((long)p.tau * p.ribosum.am16[x * 16 + y]) / 100);
     DevParams &d = t.dev;
     d.gap = p.indel - p.unpaired_penalty;
     d.open = p.indel_opening;
@@ -327,6 +327,75 @@ int arcmatch_score(const ScoreTables &t, const Params &p, const Sequence &A, con
         } else seqc = (long)base_match_score(t, c1, c3) + base_match_score(t, c2, c4);
     }
     return (int)(((long)p.tau * seqc) / 100) + wA[a] + wB[b];
+}
+
+// ---------------------------------------------------------------------------------- ribosum
+RibosumTables::RibosumTables() {
+    memcpy(bm, RIBOSUM85_60_BM, sizeof bm); memcpy(sigma4, RIBOSUM85_60_SIGMA4, sizeof sigma4); memcpy(am16, RIBOSUM85_60_AM16, sizeof am16);
+}
+
+namespace {
+long round2score_d(double d) { return (long)(d < 0 ? d - 0.5 : d + 0.5); }   // aux.hh round2score
+
+// lower-triangular score matrix with a header line of names and a name in front of every row (Ribosum::read_matrix, ribosum.hh:383-424)
+bool read_tri_matrix(std::istream &in, const std::vector<std::string> &names, std::vector<double> &mat, std::string &err) {
+    const size_t n = names.size();
+    std::string line;
+    while (std::getline(in, line) && line == "") {}
+    {
+        std::istringstream ls(line);
+        for (size_t i = 0; i < n; i++) { std::string nm; ls >> nm; if (nm != names[i]) { err = "Expecting correct table header. Found: " + line; return false; } }
+    }
+    mat.assign(n * n, 0.0);
+    for (size_t i = 0; i < n; i++) {
+        if (!std::getline(in, line)) { err = "unexpected end of the matrix"; return false; }
+        std::istringstream ls(line);
+        std::string base;
+        ls >> base;
+        if (base != names[i]) { err = "Expecting base name " + names[i] + " as row header"; return false; }
+        for (size_t j = 0; j <= i; j++) { double v; if (!(ls >> v)) { err = "missing matrix entry"; return false; } mat[i * n + j] = mat[j * n + i] = v; }
+    }
+    return true;
+}
+// "HEADER" line followed by xdim * ydim numbers (RibosumFreq::read_matrix, ribosum.cc:169-197)
+bool read_freq_matrix(std::istream &in, const std::string &header, size_t count, std::vector<double> &mat, std::string &err) {
+    std::string line;
+    auto blank = [](const std::string &s) { for (char c : s) if (!isspace((unsigned char)c)) return false; return true; };
+    while (std::getline(in, line) && blank(line)) {}
+    if (line != header) { err = "Expected header " + header + ". Read instead '" + line + "'."; return false; }
+    mat.assign(count, 0.0);
+    for (size_t k = 0; k < count; k++) if (!(in >> mat[k])) { err = "missing entries under " + header; return false; }
+    return true;
+}
+}  // namespace
+
+bool read_ribosum_file(const std::string &path, RibosumTables &out, std::string &err) {
+    std::ifstream in(path.c_str());
+    if (!in) { err = "Cannot open file " + path + " for reading ribosum data."; return false; }
+    std::string line, e;
+    if (!std::getline(in, line)) { err = "Cannot parse ribosum input. Expecting name."; return false; }
+    const std::vector<std::string> bases = {"A", "C", "G", "U"};
+    std::vector<std::string> arcs;
+    for (const auto &x : bases) for (const auto &y : bases) arcs.push_back(x + y);
+    std::vector<double> bm, am, f_base, f_nonstruct, f_pair, f_match, f_arcmatch;
+    bool ok = read_tri_matrix(in, bases, bm, e);
+    if (ok) { std::getline(in, line); std::getline(in, line); ok = read_tri_matrix(in, arcs, am, e); }   // "ignore two lines" (ribosum.cc:59-62)
+    if (!ok) { err = "Cannot parse ribosum input. " + e + ": iostream error\nFile not in ribosum format."; return false; }   // text of the reference incl. ifstream::failure::what()
+    std::getline(in, line); std::getline(in, line);
+    ok = read_freq_matrix(in, "BASE FREQUENCIES", 4, f_base, e) && read_freq_matrix(in, "BASE NONSTRUCTURAL FREQUENCIES", 4, f_nonstruct, e) &&
+         read_freq_matrix(in, "BASE PAIR FREQUENCIES", 16, f_pair, e) && read_freq_matrix(in, "BASE MATCH FREQUENCIES", 16, f_match, e) &&
+         read_freq_matrix(in, "BASE PAIR MATCH FREQUENCIES", 256, f_arcmatch, e);
+    if (!ok) { err = "Cannot parse ribosum frequency input. " + e + ": iostream error\nFile not in extended ribosum format."; return false; }
+    for (int a = 0; a < 4; a++)
+        for (int b = 0; b < 4; b++) {
+            out.bm[a * 4 + b] = bm[a * 4 + b];
+            // basematch_score_corrected (ribosum.cc:324-331), scoring.cc:174-177
+            out.sigma4[a * 4 + b] = (int)round2score_d(100.0 * (log(f_match[a * 4 + b] / (f_nonstruct[a] * f_nonstruct[b])) / log(2)));
+        }
+    for (int x = 0; x < 16; x++)
+        for (int y = 0; y < 16; y++)   // scoring.cc:411-427 for one row per sequence
+            out.am16[x * 16 + y] = (int)round2score_d(100.0 * (log(f_arcmatch[x * 16 + y] / (f_pair[x] * f_pair[y])) / log(2)) / 1);
+    return true;
 }
 
 // ---------------------------------------------------------------------------------- band
@@ -437,13 +506,14 @@ struct EnvScore {
     bool rev = false;
     double sw, match, mismatch;
     bool ribo;
+    const double *ribo_bm;
     double up(const Sequence &s, int i) const { return rev ? s.p_down[s.len + 1 - i] : s.p_up[i]; }
     double down(const Sequence &s, int i) const { return rev ? s.p_up[s.len + 1 - i] : s.p_down[i]; }
     uint8_t code(const Sequence &s, int i) const { return s.codes[rev ? s.len + 1 - i : i]; }
     double sigma(int i, int j) const {
         double seq_score = 0;
         const uint8_t a = code(*A, i), b = code(*B, j);
-        if (a < 4 && b < 4) { seq_score += ribo ? RIBOSUM85_60_BM[a * 4 + b] : (a == b ? match : mismatch); seq_score /= 1; }
+        if (a < 4 && b < 4) { seq_score += ribo ? ribo_bm[a * 4 + b] : (a == b ? match : mismatch); seq_score /= 1; }
         double res = sw * (sqrt(down(*A, i) * down(*B, j)) + sqrt(up(*A, i) * up(*B, j))) + seq_score;
         return res;
     }
@@ -490,7 +560,7 @@ template <class T>
 void envelope_impl(Band &band, const Sequence &A, const Sequence &B, const Params &p) {
     const size_t lenA = A.len, lenB = B.len;
     EnvScore sc;
-    sc.A = &A; sc.B = &B; sc.sw = p.struct_weight / 100.0; sc.match = p.match; sc.mismatch = p.mismatch; sc.ribo = p.use_ribosum;
+    sc.A = &A; sc.B = &B; sc.sw = p.struct_weight / 100.0; sc.match = p.match; sc.mismatch = p.mismatch; sc.ribo = p.use_ribosum; sc.ribo_bm = p.ribosum.bm;
     const double open = p.indel_opening / 100.0, ext = p.indel / 100.0, temp = p.temperature_alipf / 100.0;
     const bool local = p.sequ_local;
     Grid<T> zM, zA, zB, zMr, zAr, zBr;
@@ -535,7 +605,7 @@ void envelope_impl(Band &band, const Sequence &A, const Sequence &B, const Param
 
 void envelope_score_params(const Params &p, double bm[16], double *sw, double *open, double *ext, double *temp) {
     for (int a = 0; a < 4; a++)
-        for (int b = 0; b < 4; b++) bm[a * 4 + b] = p.use_ribosum ? RIBOSUM85_60_BM[a * 4 + b] : (a == b ? (double)p.match : (double)p.mismatch);
+        for (int b = 0; b < 4; b++) bm[a * 4 + b] = p.use_ribosum ? p.ribosum.bm[a * 4 + b] : (a == b ? (double)p.match : (double)p.mismatch);
     *sw = p.struct_weight / 100.0; *open = p.indel_opening / 100.0; *ext = p.indel / 100.0; *temp = p.temperature_alipf / 100.0;
 }
 

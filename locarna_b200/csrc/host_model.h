@@ -10,6 +10,18 @@
 
 namespace lb200 {
 
+// Score tables derived from a RIBOSUM matrix (ribosum.hh:34-439): base similarity as stored (used by the envelope's STRAL-like score,
+// stral_score.cc:29-60), round2score(100 log2(P_basematch / (P_nonstruct P_nonstruct))) (scoring.cc:141-198, ribosum.cc:324-331) and
+// round2score(100 log2(P_arcmatch / (P_basepair P_basepair))) (scoring.cc:369-438). Nucleotide order A C G U, pair index 4 left + right.
+struct RibosumTables {
+    double bm[16];
+    int sigma4[16];
+    int am16[256];
+    RibosumTables();   // the built-in RIBOSUM85_60
+};
+// --ribosum-file: a matrix in the reference's extended ribosum format (RibosumFreq(filename), ribosum.cc:40-200)
+bool read_ribosum_file(const std::string &path, RibosumTables &out, std::string &err);
+
 struct Params {  // mirrors the `locarna` CLI options that reach the path (locarna.cc:83-272)
     double min_prob = 0.001;
     int max_diff_am = -1, max_diff_at_am = -1, max_diff = -1;
@@ -24,6 +36,7 @@ struct Params {  // mirrors the `locarna` CLI options that reach the path (locar
     int max_bp_span = -1;    // --maxBPspan (locarna.cc:253, rna_data.cc:1078); -1: unrestricted
     bool pf_double = false;  // envelope in double (locarna_p default) instead of long double (locarna)
     bool stacking = false, new_stacking = false;  // --stacking / --new-stacking (locarna.cc:120-123, scoring.cc:201-248)
+    RibosumTables ribosum;   // --ribosum-file (default: the built-in RIBOSUM85_60)
 };
 
 struct Arc { int left, right; };

@@ -187,6 +187,7 @@ struct lb200_ctx {
     } res;
     int host_threads = 0;
     bool d_filled = false;   // the resident chunk's D table is complete (Aligner's D_created_)
+    RibosumTables ribosum;   // --ribosum-file (lb200_set_ribosum_file); default: the built-in matrix
     size_t seqs_uploaded = 0;  // sequences whose arrays are on the device
     std::vector<int> seq_codes_off, seq_arcs_off, seq_lptr_off;
     DevBuf d_arc_left, d_arc_right, d_arc_weight, d_arc_sdelta, d_lptr, d_lcount, d_am_seq, d_cell_rev, d_cell_start, d_skeys, d_skeys2, d_svals, d_svals2,
@@ -336,6 +337,7 @@ int lb200_set_params(lb200_ctx *c, const lb200_params *p) {
     if (!c || !p) return LB200_ERR_ARG;
     if (!c->seqs.empty()) return fail(c, LB200_ERR_STATE, "parameters must be set before sequences are added");
     c->params = to_params(*p);
+    c->params.ribosum = c->ribosum;
     make_score_tables(c->params, c->tables);
     return LB200_OK;
 }
@@ -380,6 +382,22 @@ int lb200_seqs_copy(lb200_ctx *c, const lb200_ctx *src) {
     const int first = (int)c->seqs.size();
     c->seqs.insert(c->seqs.end(), src->seqs.begin(), src->seqs.end());
     return first;
+}
+
+// --ribosum-file (locarna.cc:86-88, main_helper.icc:311-350): score tables from a matrix file in the reference's extended ribosum format;
+// NULL or "RIBOSUM85_60" selects the built-in matrix. Takes effect for tables built afterwards (call it before adding pairs).
+int lb200_set_ribosum_file(lb200_ctx *c, const char *path) {
+    if (!c) return LB200_ERR_ARG;
+    RibosumTables t;
+    if (path != nullptr && strcmp(path, "RIBOSUM85_60") != 0) {
+        std::string err;
+        if (!read_ribosum_file(path, t, err)) return fail(c, LB200_ERR_IO, "%s", err.c_str());
+    }
+    c->ribosum = t;
+    c->params.ribosum = t;
+    make_score_tables(c->params, c->tables);
+    c->res.valid = false;
+    return LB200_OK;
 }
 
 int lb200_seq_add(lb200_ctx *c, const char *name, const char *seq, const int *pi, const int *pj, const double *pp, int n) {

@@ -18,7 +18,8 @@ CASES = json.load(open(os.path.join(GOLD, "reference_outputs.json")))["cli"] + [
     c for c in json.load(open(os.path.join(GOLD, "normalized_outputs.json")))[::3] if c["rc"] == 0 or "simultaneously" not in c["stderr"]] + [
     dict(c, clustal=None) for c in json.load(open(os.path.join(GOLD, "kbest_outputs.json")))[::3]] + [
     c for c in json.load(open(os.path.join(GOLD, "anchors_outputs.json")))[::4]] + [
-    dict(c, clustal=None) for c in json.load(open(os.path.join(GOLD, "maxdiffaln_outputs.json")))[::6] if c["rc"] == 0]   # every third case: the CLI tests run all of them
+    dict(c, clustal=None) for c in json.load(open(os.path.join(GOLD, "maxdiffaln_outputs.json")))[::6] if c["rc"] == 0] + [
+    dict(c, clustal=None) for c in json.load(open(os.path.join(GOLD, "ribosum_outputs.json")))[::4] if c["rc"] == 0]   # every third case: the CLI tests run all of them
 
 
 @pytest.mark.skipif(not os.path.exists(REF), reason="the reference tree is only present in the build container")

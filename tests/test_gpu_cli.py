@@ -164,3 +164,23 @@ def test_cli_reference_alignment_bands(case):
     assert r.stdout == case["stdout"]
     if case["rc"] != 0:
         assert r.stderr == case["stderr"]
+
+
+CASES_RIBOSUM = json.load(open(os.path.join(GOLD, "ribosum_outputs.json")))
+
+
+@pytest.mark.parametrize("case", CASES_RIBOSUM, ids=lambda c: "%s-%s" % ("_".join(c["args"][1:]), c["A"]))
+def test_cli_ribosum_file(case, tmp_path):
+    """--ribosum-file with a matrix other than the built-in one (tests/golden/synthetic.ribosum, tools/make_golden_ribosum.py): base-match
+    and arc-match score tables from the file (RibosumFreq, ribosum.cc:40-200, :324-331; scoring.cc:141-198, :369-438), stdout and the
+    arc-match scores of the reference binary; a file that is not a ribosum matrix is refused with the reference's message."""
+    r = subprocess.run([CLI, case["A"], case["B"]] + case["args"], capture_output=True, text=True, cwd=GOLD)
+    assert r.returncode == case["rc"], r.stderr
+    assert r.stdout == case["stdout"]
+    if case["rc"] != 0:
+        assert r.stderr == case["stderr"]
+        return
+    ams = str(tmp_path / "out.ams")
+    w = subprocess.run([CLI, case["A"], case["B"], "--write-arcmatch-scores", ams] + case["args"], capture_output=True, text=True, cwd=GOLD)
+    assert w.returncode == 0, w.stderr
+    assert open(ams).read() == case["arcmatch_scores"]

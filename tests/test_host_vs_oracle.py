@@ -120,3 +120,30 @@ def test_band_from_reference_alignment_equals_reference():
                 assert capi.band_from_alignment(len(sa), len(sb), A, B, delta) == (ref["min_col"], ref["max_col"])
     with pytest.raises(capi.Error):
         capi.band_from_alignment(5, 4, "ACGU-", "AC-GU", 1)       # rows do not spell out sequences of these lengths
+
+
+def test_ribosum_file_reader():
+    """lb200_set_ribosum_file: the reference's own matrix file gives the built-in tables (arc-match scores unchanged); the synthetic
+    matrix of tests/golden changes them; a file in another format is refused."""
+    import pytest
+    from locarna_b200 import capi
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+    def scores(path):
+        ctx = capi.Context(capi.DEVICE_NONE, {})
+        if path:
+            ctx.set_ribosum_file(path)
+        ctx.add_pair(ctx.add_pp(os.path.join(G, "g0.pp")), ctx.add_pp(os.path.join(G, "g1.pp")))
+        ctx.prepare()
+        out = ctx.arcmatches(0)
+        ctx.close()
+        return out
+    builtin = scores(None)
+    assert scores("RIBOSUM85_60") == builtin
+    ref_file = "/root/reference/Data/Matrices/RIBOSUM85_60"
+    if os.path.exists(ref_file):
+        assert scores(ref_file) == builtin
+    syn = scores(os.path.join(G, "synthetic.ribosum"))
+    assert syn != builtin          # other scores (and another band: the envelope uses the matrix' base similarities)
+    with pytest.raises(capi.Error, match="Cannot parse ribosum input"):
+        scores(os.path.join(G, "g0.pp"))
