@@ -35,7 +35,7 @@
 
 namespace {
 enum {
-    O_INDEL_OPENING = 1000, O_USE_RIBOSUM, O_UNPAIRED_PENALTY, O_STRUCT_LOCAL, O_SEQU_LOCAL, O_FREE_ENDGAPS, O_MAX_DIFF_AT_AM,
+    O_INDEL_OPENING = 1000, O_USE_RIBOSUM, O_RIBOSUM_FILE, O_UNPAIRED_PENALTY, O_STRUCT_LOCAL, O_SEQU_LOCAL, O_FREE_ENDGAPS, O_MAX_DIFF_AT_AM,
     O_MIN_TRACE_PROB, O_NOLP, O_LP, O_MAXBPSPAN, O_MAX_BPS_LENGTH_RATIO, O_TEMPERATURE_ALIPF, O_MATRIX, O_SCORE_LIST, O_TREE, O_TGTDIR, O_DEVICE, O_GPUS, O_SHARE
 };
 bool parse_bool(const char *s) {
@@ -49,7 +49,7 @@ bool parse_bool(const char *s) {
 
 int main(int argc, char **argv) {
     static const struct option longopts[] = {
-        {"indel", required_argument, 0, 'i'}, {"indel-opening", required_argument, 0, O_INDEL_OPENING}, {"use-ribosum", required_argument, 0, O_USE_RIBOSUM},
+        {"indel", required_argument, 0, 'i'}, {"indel-opening", required_argument, 0, O_INDEL_OPENING}, {"use-ribosum", required_argument, 0, O_USE_RIBOSUM}, {"ribosum-file", required_argument, 0, O_RIBOSUM_FILE},
         {"match", required_argument, 0, 'm'}, {"mismatch", required_argument, 0, 'M'}, {"unpaired-penalty", required_argument, 0, O_UNPAIRED_PENALTY},
         {"struct-weight", required_argument, 0, 's'}, {"exp-prob", required_argument, 0, 'e'}, {"tau", required_argument, 0, 't'},
         {"exclusion", required_argument, 0, 'E'}, {"struct-local", required_argument, 0, O_STRUCT_LOCAL}, {"sequ-local", required_argument, 0, O_SEQU_LOCAL},
@@ -64,7 +64,7 @@ int main(int argc, char **argv) {
     lb200_params p;
     lb200_default_params(&p);
     p.struct_weight = 200; p.max_diff_am = 30; p.no_lonely_pairs = 1; p.min_prob = 0.001;   // @locarna_params_tree
-    std::string matrix_file, list_file, tree_file, tgtdir;
+    std::string matrix_file, list_file, tree_file, tgtdir, ribosum_file;
     int device = 0, gpus = 1, share_k = 0, share_n = 0;
     bool quiet = false, verbose = false;
     int c, idx = 0;
@@ -73,6 +73,7 @@ int main(int argc, char **argv) {
             case 'i': p.indel = atoi(optarg); break;
             case O_INDEL_OPENING: p.indel_opening = atoi(optarg); break;
             case O_USE_RIBOSUM: p.use_ribosum = parse_bool(optarg); break;
+            case O_RIBOSUM_FILE: ribosum_file = optarg; break;
             case 'm': p.match = atoi(optarg); break;
             case 'M': p.mismatch = atoi(optarg); break;
             case O_UNPAIRED_PENALTY: p.unpaired_penalty = atoi(optarg); break;
@@ -142,7 +143,7 @@ int main(int argc, char **argv) {
     auto open_ctx = [&](int g) -> bool {
         if (lb200_ctx_create(device + g, &ctxs[g]) < 0) { errors[g] = "cannot create the device context"; return false; }
         // every .pp file is parsed once (by the first context, on all host cores); the other devices' contexts copy the result
-        if (lb200_set_params(ctxs[g], &p) < 0 || (g == 0 ? lb200_seqs_add_pp(ctxs[g], n, files.data()) : lb200_seqs_copy(ctxs[g], ctxs[0])) < 0) {
+        if ((!ribosum_file.empty() && lb200_set_ribosum_file(ctxs[g], ribosum_file.c_str()) < 0) || lb200_set_params(ctxs[g], &p) < 0 || (g == 0 ? lb200_seqs_add_pp(ctxs[g], n, files.data()) : lb200_seqs_copy(ctxs[g], ctxs[0])) < 0) {
             errors[g] = lb200_last_error(ctxs[g]);
             return false;
         }
