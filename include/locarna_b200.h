@@ -128,8 +128,9 @@ int lb200_pair_add(lb200_ctx *ctx, int seqA, int seqB, const int *min_col, const
 int lb200_pair_add_restricted(lb200_ctx *ctx, int seqA, int seqB, const int *min_col, const int *max_col);
 /* Rows of TraceController(seqA, seqB, reference alignment, delta) for single sequences (--max-diff-aln / --max-diff-pw-aln with
  * --max-diff delta; TraceRange, trace_controller.cc:44-215, merge_in_trace_range :606-622). aliA / aliB: the rows of the two sequences in
- * the reference alignment (gap symbols "-_~."); min_col / max_col: lenA + 1 entries. Host only. */
-int lb200_band_from_alignment(int lenA, int lenB, const char *aliA, const char *aliB, int delta, int *min_col, int *max_col);
+ * the reference alignment (gap symbols "-_~."); relaxed != 0: --max-diff-relax (relaxed merging, trace_controller.cc:485-511); min_col /
+ * max_col: lenA + 1 entries. Host only. */
+int lb200_band_from_alignment(int lenA, int lenB, const char *aliA, const char *aliB, int delta, int relaxed, int *min_col, int *max_col);
 /* Add n alignment problems at once (bands derived like the reference does); returns the id of the first one. This is what the
  * all-vs-all stage of mlocarna hands over (src/Utils/mlocarna:3577-3604: the list of (a, b) index pairs). */
 int lb200_pairs_add(lb200_ctx *ctx, int n, const int *seqA, const int *seqB);

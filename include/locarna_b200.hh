@@ -322,6 +322,7 @@ class AlignerParams {  // aligner_params.hh:51-115: same argument names, chained
     double min_prob_ = 0.001, min_trace_probability_ = 1e-4;
     std::vector<int> min_col_, max_col_;
     const MultipleAlignment *ref_aln_ = nullptr;
+    bool ref_relaxed_ = false;
 public:
     AlignerParams &seqA(const RnaData *r) { rnaA_ = r; return *this; }
     AlignerParams &seqB(const RnaData *r) { rnaB_ = r; return *this; }
@@ -336,7 +337,7 @@ public:
     // the reference passes a TraceController; here either its rows (min_col/max_col) or the two numbers it is built from
     AlignerParams &trace_controller(const std::vector<int> &min_col, const std::vector<int> &max_col) { min_col_ = min_col; max_col_ = max_col; return *this; }
     //! reference alignment of TraceController(seqA, seqB, ma, max_diff) (trace_controller.cc:406-539): the band lies within max_diff of it
-    AlignerParams &reference_alignment(const MultipleAlignment *ma) { ref_aln_ = ma; return *this; }
+    AlignerParams &reference_alignment(const MultipleAlignment *ma, bool relaxed_merging = false) { ref_aln_ = ma; ref_relaxed_ = relaxed_merging; return *this; }
     AlignerParams &max_diff(int d) { max_diff_ = d; return *this; }
     AlignerParams &min_trace_probability(double p) { min_trace_probability_ = p; return *this; }
     AlignerParams &min_prob(double p) { min_prob_ = p; return *this; }
@@ -396,7 +397,7 @@ public:
             const std::string &rowA = ma.pairwise() ? ma.seqentry((size_t)0).seq : ma.seqentry(alignment_.nameA_).seq;
             const std::string &rowB = ma.pairwise() ? ma.seqentry((size_t)1).seq : ma.seqentry(alignment_.nameB_).seq;
             if (lb200_band_from_alignment(la, lb, rowA.c_str(), rowB.c_str(),
-                                          ap.max_diff_, lo.data(), hi.data()) != LB200_OK)
+                                          ap.max_diff_, ap.ref_relaxed_ ? 1 : 0, lo.data(), hi.data()) != LB200_OK)
                 throw failure("Inconsistent trace range due to max-diff heuristic");
             pair_ = lb200_pair_add_restricted(ctx_->get(), a, b, lo.data(), hi.data());
         } else {

@@ -26,7 +26,7 @@
 //
 // The objects of the reference compute on construction (RnaData parses, ArcMatches enumerates, Scoring precomputes). Here they record
 // their arguments; the device builds bands, arc matches and scores when Aligner runs. What the B200 path does not implement
-// (relaxed anchors, MEA, explicit arc-match scores, --max-diff-relax) throws LocARNA::failure from the object
+// (relaxed anchors, MEA, explicit arc-match scores) throws LocARNA::failure from the object
 // that would need it, so the caller's existing error handling applies.
 #ifndef LOCARNA_B200_COMPAT_HH
 #define LOCARNA_B200_COMPAT_HH
@@ -183,10 +183,10 @@ class TraceController {   // trace_controller.hh:200: the band; its rows are der
     double min_trace_probability_ = 0.0;
     const MultipleAlignment *ref_aln_ = nullptr;
 public:
-    TraceController(const Sequence &, const Sequence &, const MultipleAlignment *ma, int max_diff, bool relax = false) : max_diff_(max_diff), ref_aln_(ma) {
-        if (ma != nullptr && relax) throw failure("locarna_b200: --max-diff-relax is not supported");
-    }
+    bool relax_ = false;
+    TraceController(const Sequence &, const Sequence &, const MultipleAlignment *ma, int max_diff, bool relax = false) : max_diff_(max_diff), ref_aln_(ma), relax_(relax) {}
     const MultipleAlignment *reference_alignment() const { return ref_aln_; }
+    bool relaxed_merging() const { return relax_; }
     void restrict_by_anchors(const AnchorConstraints &) {}   // done by the library when the pair is added (lb200_seq_anchors)
     //! what MainHelper::restrict_trace_by_probabilities records (main_helper.icc:408-426)
     void set_min_trace_probability(double p) { min_trace_probability_ = p; }
@@ -328,7 +328,7 @@ inline LocARNA_B200::AlignerParams to_b200_params(const Scoring &s, const TraceC
     ap.seqA(&s.rnaA().data()).seqB(&s.rnaB().data()).scoring(sp).min_prob(s.arc_matches().min_prob());
     ap.no_lonely_pairs(noLP).struct_local(struct_local).sequ_local(sequ_local).free_endgaps(free_endgaps);
     ap.max_diff_am(max_diff_am).max_diff_at_am(max_diff_at_am).max_diff(tc.max_diff()).min_trace_probability(tc.min_trace_probability());
-    ap.reference_alignment(tc.reference_alignment());
+    ap.reference_alignment(tc.reference_alignment(), tc.relaxed_merging());
     return ap;
 }
 

@@ -96,7 +96,7 @@ def load():
     lib.lb200_set_ribosum_file.argtypes = [vp, C.c_char_p]
     lib.lb200_seq_anchors.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]
     lib.lb200_pair_add_restricted.argtypes = [vp, C.c_int, C.c_int, ip, ip]
-    lib.lb200_band_from_alignment.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_int, ip, ip]
+    lib.lb200_band_from_alignment.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int, ip, ip]
     lib.lb200_pair_set_restriction.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.lb200_run_pair_toplevel.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int]
     lib.lb200_run_normalized.argtypes = [vp, C.c_int64]
@@ -147,10 +147,10 @@ def make_params(flags: dict | None = None) -> Params:
     return p
 
 
-def band_from_alignment(lenA: int, lenB: int, aliA: str, aliB: str, delta: int):
+def band_from_alignment(lenA: int, lenB: int, aliA: str, aliB: str, delta: int, relaxed: bool = False):
     """min_col / max_col of TraceController(seqA, seqB, reference alignment, delta) (lb200_band_from_alignment)."""
     lo, hi = (C.c_int * (lenA + 1))(), (C.c_int * (lenA + 1))()
-    rc = load().lb200_band_from_alignment(lenA, lenB, aliA.encode(), aliB.encode(), delta, lo, hi)
+    rc = load().lb200_band_from_alignment(lenA, lenB, aliA.encode(), aliB.encode(), delta, int(relaxed), lo, hi)
     if rc != OK:
         raise Error("lb200_band_from_alignment failed with code %d" % rc)
     return list(lo), list(hi)

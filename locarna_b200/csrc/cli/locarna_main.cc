@@ -25,7 +25,7 @@ enum {
     O_TAU, O_EXCLUSION, O_STACKING, O_NEW_STACKING, O_STRUCT_LOCAL, O_SEQU_LOCAL, O_FREE_ENDGAPS, O_NORMALIZED, O_PENALIZED, O_WIDTH,
     O_CLUSTAL, O_STOCKHOLM, O_PP, O_LOCAL_OUTPUT, O_LOCAL_FILE_OUTPUT, O_POS_OUTPUT, O_WRITE_STRUCTURE, O_MIN_PROB, O_MAX_BPS_LENGTH_RATIO,
     O_MAX_DIFF_AM, O_MAX_DIFF, O_MAX_DIFF_AT_AM, O_MIN_TRACE_PROB, O_NOLP, O_MAXBPSPAN, O_TEMPERATURE_ALIPF, O_CONSENSUS_STRUCTURE,
-    O_WRITE_ARCMATCH_SCORES, O_KBEST, O_BETTER, O_MAX_DIFF_ALN, O_MAX_DIFF_PW_ALN, O_UNSUPPORTED, O_DEVICE, O_VERSION, O_QUIET, O_VERBOSE, O_HELP
+    O_WRITE_ARCMATCH_SCORES, O_KBEST, O_BETTER, O_MAX_DIFF_ALN, O_MAX_DIFF_PW_ALN, O_MAX_DIFF_RELAX, O_UNSUPPORTED, O_DEVICE, O_VERSION, O_QUIET, O_VERBOSE, O_HELP
 };
 bool parse_bool(const char *s) {
     const std::string v = s ? s : "";  // options.cc:867-880
@@ -57,7 +57,7 @@ int main(int argc, char **argv) {
         {"consensus-structure", required_argument, 0, O_CONSENSUS_STRUCTURE}, {"write-arcmatch-scores", required_argument, 0, O_WRITE_ARCMATCH_SCORES},
         // recognised, not implemented on the B200 path
         {"max-diff-aln", required_argument, 0, O_MAX_DIFF_ALN}, {"max-diff-pw-aln", required_argument, 0, O_MAX_DIFF_PW_ALN},
-        {"max-diff-relax", no_argument, 0, O_UNSUPPORTED}, {"kbest", required_argument, 0, O_KBEST}, {"better", required_argument, 0, O_BETTER},
+        {"max-diff-relax", no_argument, 0, O_MAX_DIFF_RELAX}, {"kbest", required_argument, 0, O_KBEST}, {"better", required_argument, 0, O_BETTER},
         {"mea-alignment", no_argument, 0, O_UNSUPPORTED}, {"match-prob-method", required_argument, 0, O_UNSUPPORTED},
         {"read-match-probs", required_argument, 0, O_UNSUPPORTED}, {"write-match-probs", required_argument, 0, O_UNSUPPORTED},
         {"read-arcmatch-scores", required_argument, 0, O_UNSUPPORTED}, {"read-arcmatch-probs", required_argument, 0, O_UNSUPPORTED},
@@ -79,7 +79,7 @@ int main(int argc, char **argv) {
     bool verbose = false;
     bool struct_local = false, struct_local_given = false, sequ_local = false, sequ_local_given = false, normalized = false, penalized = false;
     long normalized_L = 0, position_penalty = 0, subopt_threshold = -1000000;
-    bool subopt = false;
+    bool subopt = false, max_diff_relax = false;
     std::string max_diff_alignment_file, max_diff_pw_alignment;
     int kbest_k = -1;
     int c, idx = 0;
@@ -97,6 +97,7 @@ int main(int argc, char **argv) {
             case 'E': case O_EXCLUSION: sp.exclusion = atoi(optarg); break;
             case O_STRUCT_LOCAL: struct_local = parse_bool(optarg); struct_local_given = true; break;
             case O_SEQU_LOCAL: sequ_local = parse_bool(optarg); sequ_local_given = true; break;
+            case O_MAX_DIFF_RELAX: max_diff_relax = true; break;
             case O_MAX_DIFF_ALN: max_diff_alignment_file = optarg; break;
             case O_MAX_DIFF_PW_ALN: max_diff_pw_alignment = optarg; break;
             case O_KBEST: subopt = true; kbest_k = atoi(optarg); break;          // locarna.cc:203-207
@@ -182,7 +183,7 @@ int main(int argc, char **argv) {
             }
             multiple_ref_alignment.reset(new MultipleAlignment("A", "B", rowA, rowB));
         }
-        ap.reference_alignment(multiple_ref_alignment.get());
+        ap.reference_alignment(multiple_ref_alignment.get(), max_diff_relax);
         Aligner aligner(ap, device);
         if (!arcmatch_scores_file.empty()) {                                        // locarna.cc:705-720: write and return without aligning
             if (verbose) std::cout << "Write arcmatch scores to file " << arcmatch_scores_file << " and exit." << std::endl;

@@ -100,7 +100,7 @@ static int run_and_report() {
 int main(int argc, char **argv) {
     enum { O_INDEL_OPENING = 1000, O_RIBOSUM_FILE, O_USE_RIBOSUM, O_UNPAIRED_PENALTY, O_STRUCT_LOCAL, O_SEQU_LOCAL, O_FREE_ENDGAPS, O_MAX_DIFF_AT_AM, O_MIN_TRACE_PROB, O_NOLP,
            O_MAXBPSPAN, O_MAX_BPS_LENGTH_RATIO, O_TEMPERATURE_ALIPF, O_CLUSTAL, O_LOCAL_FILE_OUTPUT, O_WRITE_STRUCTURE, O_WRITE_AMS, O_STACKING, O_NORMALIZED,
-           O_PENALIZED, O_KBEST, O_BETTER, O_MAX_DIFF_ALN, O_MAX_DIFF_PW_ALN };
+           O_PENALIZED, O_KBEST, O_BETTER, O_MAX_DIFF_ALN, O_MAX_DIFF_PW_ALN, O_MAX_DIFF_RELAX };
     static const struct option longopts[] = {
         {"indel", required_argument, 0, 'i'}, {"indel-opening", required_argument, 0, O_INDEL_OPENING}, {"use-ribosum", required_argument, 0, O_USE_RIBOSUM}, {"ribosum-file", required_argument, 0, O_RIBOSUM_FILE},
         {"match", required_argument, 0, 'm'}, {"mismatch", required_argument, 0, 'M'}, {"unpaired-penalty", required_argument, 0, O_UNPAIRED_PENALTY},
@@ -112,7 +112,7 @@ int main(int argc, char **argv) {
         {"temperature-alipf", required_argument, 0, O_TEMPERATURE_ALIPF}, {"width", required_argument, 0, 'w'}, {"clustal", required_argument, 0, O_CLUSTAL},
         {"local-output", no_argument, 0, 'L'}, {"local-file-output", no_argument, 0, O_LOCAL_FILE_OUTPUT}, {"pos-output", no_argument, 0, 'P'},
         {"write-structure", no_argument, 0, O_WRITE_STRUCTURE}, {"write-arcmatch-scores", required_argument, 0, O_WRITE_AMS}, {"stacking", no_argument, 0, O_STACKING},
-        {"normalized", required_argument, 0, O_NORMALIZED}, {"penalized", required_argument, 0, O_PENALIZED}, {"kbest", required_argument, 0, O_KBEST}, {"max-diff-aln", required_argument, 0, O_MAX_DIFF_ALN}, {"max-diff-pw-aln", required_argument, 0, O_MAX_DIFF_PW_ALN}, {"better", required_argument, 0, O_BETTER},
+        {"normalized", required_argument, 0, O_NORMALIZED}, {"penalized", required_argument, 0, O_PENALIZED}, {"kbest", required_argument, 0, O_KBEST}, {"max-diff-aln", required_argument, 0, O_MAX_DIFF_ALN}, {"max-diff-relax", no_argument, 0, O_MAX_DIFF_RELAX}, {"max-diff-pw-aln", required_argument, 0, O_MAX_DIFF_PW_ALN}, {"better", required_argument, 0, O_BETTER},
         {"quiet", no_argument, 0, 'q'}, {"verbose", no_argument, 0, 'v'}, {0, 0, 0, 0}};
     int c, idx = 0;
     while ((c = getopt_long(argc, argv, "i:m:M:s:e:t:E:w:Lp:D:d:Pqv", longopts, &idx)) != -1) {
@@ -150,6 +150,7 @@ int main(int argc, char **argv) {
             case O_STACKING: clp.stacking = true; break;
             case O_NORMALIZED: clp.normalized = true; clp.normalized_L = atol(optarg); break;
             case O_PENALIZED: clp.penalized = true; clp.position_penalty = atol(optarg); break;
+            case O_MAX_DIFF_RELAX: clp.max_diff_relax = true; break;
             case O_MAX_DIFF_ALN: clp.max_diff_alignment_file = optarg; break;
             case O_MAX_DIFF_PW_ALN: clp.max_diff_pw_alignment = optarg; break;
             case O_KBEST: clp.subopt = true; clp.kbest_k = atoi(optarg); break;

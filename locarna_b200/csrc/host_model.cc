@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstring>
 #include <fstream>
+#include <limits>
 #include <map>
 #include <mutex>
 #include <sstream>
@@ -471,7 +472,8 @@ int restrict_band_by_anchors(Band &band, const Sequence &A, const Sequence &B, s
 // columns), intersected with the unconstrained range as merge_in_trace_range does (:606-622). aliA / aliB: the two rows of the
 // reference alignment, gap symbols "-_~." (aux.cc:24). Returns false (err set) if the rows do not spell out sequences of these
 // lengths or the range is inconsistent.
-bool band_from_alignment(int lenA, int lenB, const std::string &aliA_in, const std::string &aliB_in, int delta, Band &b, std::string &err) {
+bool band_from_alignment(int lenA, int lenB, const std::string &aliA_in, const std::string &aliB_in, int delta_in, Band &b, std::string &err, bool relaxed) {
+    const int delta = relaxed ? 0 : delta_in;   // relaxed merging: the trace of the reference alignment itself, widened afterwards (trace_controller.cc:462-468)
     auto gap = [](char c) { return c == '-' || c == '_' || c == '~' || c == '.'; };
     if (aliA_in.size() != aliB_in.size()) { err = "reference alignment rows have unequal lengths"; return false; }
     std::string aliA, aliB;   // remove_common_gaps (:25-42)
@@ -491,6 +493,53 @@ bool band_from_alignment(int lenA, int lenB, const std::string &aliA_in, const s
         b.lo[i] = std::min(b.lo[i], (int)j_minus); b.hi[i] = std::max(b.hi[i], (int)j_plus);
         for (size_t pi = i_minus; pi < i; pi++) b.hi[pi] = std::max(b.hi[pi], (int)j);
         for (size_t pi = i + 1; pi <= i_plus; pi++) b.lo[pi] = std::min(b.lo[pi], (int)j);
+    }
+    if (relaxed) {
+        // --max-diff-relax (trace_controller.cc:485-511): consensus trace through the trace ranges (one range here: single sequences),
+        // TraceRange(lenA, lenB, trs, delta) :246-311 with consensus_cost :214-243 (its second branch takes the minimum with the running
+        // value, as written there), then the range is blown up by delta in both directions
+        const Band tr0 = b;
+        const int n = lenA, m = lenB;
+        auto cost = [&](long i, long j) -> size_t {
+            size_t dprime = std::numeric_limits<size_t>::max();
+            for (long i2 = 0; i2 <= n; i2++) {
+                size_t d2;
+                if (j < tr0.lo[i2]) d2 = (size_t)(labs(i - i2) + (tr0.lo[i2] - j));
+                else if (j > tr0.hi[i2]) d2 = std::min(dprime, (size_t)(labs(i - i2) + (j - tr0.hi[i2])));
+                else d2 = (size_t)labs(i - i2);
+                dprime = std::min(dprime, d2);
+            }
+            return dprime;
+        };
+        std::vector<size_t> C((size_t)(n + 1) * (m + 1));
+        std::vector<uint8_t> T((size_t)(n + 1) * (m + 1));
+        auto at = [&](int i, int j) { return (size_t)i * (m + 1) + j; };
+        T[at(0, 0)] = 3; C[at(0, 0)] = cost(0, 0);
+        for (int i = 1; i <= n; i++) { T[at(i, 0)] = 1; C[at(i, 0)] = cost(i, 0) + C[at(i - 1, 0)]; }
+        for (int j = 1; j <= m; j++) { T[at(0, j)] = 2; C[at(0, j)] = cost(0, j) + C[at(0, j - 1)]; }
+        for (int i = 1; i <= n; i++)
+            for (int j = 1; j <= m; j++) {
+                size_t c = cost(i, j);
+                if (C[at(i - 1, j - 1)] < C[at(i - 1, j)] && C[at(i - 1, j - 1)] < C[at(i, j - 1)]) { T[at(i, j)] = 0; c += C[at(i - 1, j - 1)]; }
+                else if (C[at(i - 1, j)] < C[at(i, j - 1)]) { T[at(i, j)] = 1; c += C[at(i - 1, j)]; }
+                else { T[at(i, j)] = 2; c += C[at(i, j - 1)]; }
+                C[at(i, j)] = c;
+            }
+        Band tr;
+        tr.lo.assign(n + 1, m); tr.hi.assign(n + 1, 0);
+        for (int i = n, j = m;;) {
+            tr.lo[i] = std::min(tr.lo[i], j); tr.hi[i] = std::max(tr.hi[i], j);
+            if (T[at(i, j)] == 3) break;
+            if (T[at(i, j)] == 0) { i--; j--; } else if (T[at(i, j)] == 1) i--; else j--;
+        }
+        const int dl = std::max(delta_in, 0);
+        for (int i = 0; i <= n; i++) {
+            int lo = std::min(std::max(tr.lo[i], dl) - dl, m), hi = std::max(std::min(tr.hi[i] + dl, m), 0);
+            const int i_minus = std::max(dl, i) - dl, i_plus = std::min(i + dl, n);
+            lo = std::min(tr.lo[i_minus], lo); hi = std::max(tr.hi[i_plus], hi);
+            b.lo[i] = lo; b.hi[i] = hi;
+        }
+        return true;
     }
     for (int r = 0; r <= lenA; r++)
         if (b.lo[r] > b.hi[r] || (r > 0 && b.hi[r - 1] + 1 < b.lo[r])) { err = "Inconsistent trace range due to max-diff heuristic"; return false; }

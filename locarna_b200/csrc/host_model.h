@@ -99,7 +99,7 @@ Band make_band(int lenA, int lenB, int max_diff);
 // has no constraints (one sequence without names), 1 if the band was restricted, -1 (err set) if the names differ between the sequences.
 int restrict_band_by_anchors(Band &band, const Sequence &A, const Sequence &B, std::string &err);
 // band around a pairwise reference alignment (trace_controller.cc:44-215, :606-622)
-bool band_from_alignment(int lenA, int lenB, const std::string &aliA, const std::string &aliB, int delta, Band &b, std::string &err);
+bool band_from_alignment(int lenA, int lenB, const std::string &aliA, const std::string &aliB, int delta, Band &b, std::string &err, bool relaxed = false);
 // probability envelope (PFGotoh in 80-bit or 64-bit floating point on the host)
 void restrict_band_by_envelope(Band &band, const Sequence &A, const Sequence &B, const Params &p);
 // score parameters of the envelope partition function as the reference passes them (main_helper.icc:389-400)

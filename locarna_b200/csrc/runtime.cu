@@ -461,11 +461,11 @@ int lb200_pair_add_restricted(lb200_ctx *c, int seqA, int seqB, const int *min_c
     if (!min_col || !max_col) return LB200_ERR_ARG;
     return pair_add(c, seqA, seqB, min_col, max_col, true);
 }
-int lb200_band_from_alignment(int lenA, int lenB, const char *aliA, const char *aliB, int delta, int *min_col, int *max_col) {
+int lb200_band_from_alignment(int lenA, int lenB, const char *aliA, const char *aliB, int delta, int relaxed, int *min_col, int *max_col) {
     if (lenA < 0 || lenB < 0 || !aliA || !aliB || !min_col || !max_col) return LB200_ERR_ARG;
     Band b;
     std::string err;
-    if (!band_from_alignment(lenA, lenB, aliA, aliB, delta, b, err)) { fprintf(stderr, "locarna_b200: %s\n", err.c_str()); return LB200_ERR_ARG; }
+    if (!band_from_alignment(lenA, lenB, aliA, aliB, delta, b, err, relaxed != 0)) { fprintf(stderr, "locarna_b200: %s\n", err.c_str()); return LB200_ERR_ARG; }
     std::copy(b.lo.begin(), b.lo.end(), min_col); std::copy(b.hi.begin(), b.hi.end(), max_col);
     return LB200_OK;
 }

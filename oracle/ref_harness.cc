@@ -67,6 +67,7 @@ struct Opts {
     bool do_trace = true, timing = false, pf_double = false;
     bool stacking = false, new_stacking = false;   // locarna --stacking / --new-stacking (locarna.cc:120-123)
     double exp_prob = -1.0;                        // --exp-prob; < 0: prob_exp_f(len) per sequence (locarna.cc:662-663)
+    bool max_diff_relax = false;                   // --max-diff-relax: relaxed merging of the trace ranges
     std::string max_diff_pw_aln;                   // --max-diff-pw-aln "rowA&rowB" (locarna.cc:519-548): band around a reference alignment
     bool pf = false, pf_probs = false;  // LocARNA-P: inside partition function (+ D), outside + probabilities
     double pf_scale = 1.0, min_am_prob = 0.001, min_bm_prob = 0.001;
@@ -133,7 +134,7 @@ static int run_pair(const Opts &o, const std::string &fA, const std::string &fB,
         ref_aln = std::make_unique<MultipleAlignment>(seqA.seqentry(0).name(), seqB.seqentry(0).name(), o.max_diff_pw_aln.substr(0, amp),
                                                       o.max_diff_pw_aln.substr(amp + 1));
     }
-    TraceController tc(seqA, seqB, ref_aln.get(), o.max_diff, false);
+    TraceController tc(seqA, seqB, ref_aln.get(), o.max_diff, o.max_diff_relax);
     tc.restrict_by_anchors(constraints);
     if (o.pf_double) envelope<double>(o, *rA, *rB, ribosum, tc);
     else envelope<long double>(o, *rA, *rB, ribosum, tc);  // locarna.cc:384-391 forces extended pf
@@ -293,6 +294,7 @@ int main(int argc, char **argv) {
         else if (a == "--max-diff-at-am") o.max_diff_at_am = atoi(nxt());
         else if (a == "--max-diff") o.max_diff = atoi(nxt());
         else if (a == "--max-diff-pw-aln") o.max_diff_pw_aln = nxt();
+        else if (a == "--max-diff-relax") o.max_diff_relax = true;
         else if (a == "--min-trace-probability") o.min_trace_probability = atof(nxt());
         else if (a == "--noLP") o.noLP = true;
         else if (a == "--struct-local") o.struct_local = true;

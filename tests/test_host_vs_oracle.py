@@ -118,6 +118,10 @@ def test_band_from_reference_alignment_equals_reference():
             for delta in (0, 1, 4, 15):
                 ref = O.ref_align(pa, pb, {"max-diff": delta, "max-diff-pw-aln": A + "&" + B, "min-trace-probability": 0}, dump="band", do_trace=False)
                 assert capi.band_from_alignment(len(sa), len(sb), A, B, delta) == (ref["min_col"], ref["max_col"])
+                # --max-diff-relax: relaxed merging (consensus trace of the trace ranges, widened by delta; trace_controller.cc:214-311, :485-511)
+                ref = O.ref_align(pa, pb, {"max-diff": delta, "max-diff-pw-aln": A + "&" + B, "max-diff-relax": True, "min-trace-probability": 0},
+                                  dump="band", do_trace=False)
+                assert capi.band_from_alignment(len(sa), len(sb), A, B, delta, relaxed=True) == (ref["min_col"], ref["max_col"])
     with pytest.raises(capi.Error):
         capi.band_from_alignment(5, 4, "ACGU-", "AC-GU", 1)       # rows do not spell out sequences of these lengths
 

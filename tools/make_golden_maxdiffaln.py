@@ -40,7 +40,8 @@ def main():
                 for k in range(0, len(ra), 40):
                     f.write("%-18s %s\n%-18s %s\n\n" % (names[0], ra[k:k + 40], names[1], rb[k:k + 40]))
             combos = [(0, [], "pw"), (2, [], "pw"), (2, [], "file"), (6, ["--noLP"], "file"), (6, ["--sequ-local", "true"], "pw"),
-                      (6, ["--min-trace-probability", "0"], "file"), (6, ["--struct-local", "true"], "pw"), (20, [], "file")]
+                      (6, ["--min-trace-probability", "0"], "file"), (6, ["--struct-local", "true"], "pw"), (20, [], "file"),
+                      (3, ["--max-diff-relax"], "pw"), (8, ["--max-diff-relax", "--noLP"], "file")]
             for delta, extra, mode in combos:
                 args = ["--max-diff", str(delta)] + extra + (["--max-diff-pw-aln", ra + "&" + rb] if mode == "pw" else ["--max-diff-aln", os.path.basename(aln)])
                 p = subprocess.run([O.REF_LOCARNA, a, b] + args, capture_output=True, text=True, cwd=GOLD)
