@@ -151,3 +151,27 @@ def test_ribosum_file_reader():
     assert syn != builtin          # other scores (and another band: the envelope uses the matrix' base similarities)
     with pytest.raises(capi.Error, match="Cannot parse ribosum input"):
         scores(os.path.join(G, "g0.pp"))
+
+
+def test_seqs_copy_shares_parsed_inputs(synth_dir):
+    """lb200_seqs_copy: a second context takes over the parsed sequences (bands and arc matches identical to parsing again);
+    contexts that filter their inputs differently are refused."""
+    import pytest
+    from locarna_b200 import capi
+    paths = synth_dir["short"][:3]
+    flags = {"noLP": True, "max-diff-am": 30}
+    a = capi.Context(capi.DEVICE_NONE, flags)
+    first = a.add_pps(paths)
+    b = capi.Context(capi.DEVICE_NONE, flags)
+    assert b.copy_seqs_from(a) == 0 and b.copy_seqs_from(a) == len(paths)        # appended, like add_pps
+    for ctx, off in ((a, first), (b, len(paths))):
+        ctx.add_pair(off + 1, off + 0)
+        ctx.add_pair(off + 2, off + 1)
+        ctx.prepare()
+    for k in range(2):
+        assert a.band(k) == b.band(k) and a.arcmatches(k) == b.arcmatches(k)
+    c = capi.Context(capi.DEVICE_NONE, {"min-prob": 0.01})
+    with pytest.raises(capi.Error, match="filter their inputs differently"):
+        c.copy_seqs_from(a)
+    for ctx in (a, b, c):
+        ctx.close()
