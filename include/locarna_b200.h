@@ -235,6 +235,10 @@ int lb200_set_ribosum_file(lb200_ctx *ctx, const char *path);
 /* Append the parsed sequences of another context (same min_prob / maxBPspan / max-bps-length-ratio / stacking); returns the index of the
  * first one. For contexts that work off one job side by side (one per stream or device): every PP file is parsed once. */
 int lb200_seqs_copy(lb200_ctx *ctx, const lb200_ctx *src);
+/* The base pairs the PP reader kept for a sequence (RnaData::arc_prob > 0, rna_data.cc:1057-1093), sorted by (i, j): positions,
+ * probability, joint probability with the inner pair (0 = none). Pass NULL arrays to get the count (the return value). cutoff_out:
+ * RnaData::arc_cutoff_prob(), stacking_out: RnaData::has_stacking(). The input of a consensus dot plot (locarna --pp, rna_data.cc:1474-1548). */
+int64_t lb200_seq_pairs(const lb200_ctx *ctx, int seq, int *i, int *j, double *p, double *p2, double *cutoff_out, int *stacking_out);
 /* number of base pairs (arcs with probability >= min_prob) of a sequence: the input of lb200_pair_cost */
 int lb200_seq_num_arcs(const lb200_ctx *ctx, int seq);
 /* lb200_pair_cost + lb200_shard_pairs for pairs (seqA[k], seqB[k]) of the context's sequences in one call; rank_of may be NULL */

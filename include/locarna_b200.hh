@@ -15,6 +15,7 @@
 #define LOCARNA_B200_HH
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <exception>
 #include <fstream>
@@ -23,6 +24,7 @@
 #include <ostream>
 #include <sstream>
 #include <string>
+#include <unordered_map>
 #include <utility>
 #include <queue>
 #include <vector>
@@ -347,6 +349,7 @@ class Aligner {  // aligner.hh:67-189
     std::shared_ptr<Context> ctx_;
     int pair_ = -1;
     bool traced_ = false, have_ams_ = false, restricted_ = false;
+    int seq_a_ = -1, seq_b_ = -1;
     AlignerRestriction r_{1, 1, 0, 0};
     Alignment alignment_;
     ArcMatches ams_;
@@ -374,6 +377,7 @@ public:
         ctx_->check(a);
         const int b = lb200_seq_add_pp(ctx_->get(), ap.rnaB_->filename().c_str());
         ctx_->check(b);
+        seq_a_ = a; seq_b_ = b;
         char name[256], *seq;
         const int la = lb200_seq_length(ctx_->get(), a), lb = lb200_seq_length(ctx_->get(), b);
         const int seq_cap = std::max(la, lb) + 1;
@@ -496,6 +500,73 @@ public:
         alignment_.strA_ = sa.substr(0, inf.lenA); alignment_.strB_ = sb.substr(0, inf.lenB);
     }
     const Alignment &get_alignment() const { return alignment_; }
+    //! Alignment with its consensus dot plot in PP 2.0 format (`locarna --pp`; MainHelper::consensus main_helper.icc:472-530, the consensus
+    //! constructor of RnaData rna_data.cc:104-126 / :1474-1548, RnaData::write_pp :1242-1350). exp_prob < 0: 1 / (2 len) per sequence
+    //! (locarna.cc:662-663). The base pairs are written in the iteration order of the reference's hash map (sparse_vector_base.hh:28,
+    //! aux.hh:24-34): the same container type with the same hash, filled in the same order.
+    void write_pp(std::ostream &out, bool only_local, double exp_prob) const {
+        struct PairHash { size_t operator()(const std::pair<size_t, size_t> &p) const noexcept { return std::hash<size_t>()(p.first) ^ (std::hash<size_t>()(p.second) << 1); } };
+        typedef std::unordered_map<std::pair<size_t, size_t>, double, PairHash> sparse_t;
+        struct Probs { std::vector<int> i, j; std::vector<double> p, p2; double cutoff = 0; int stacking = 0;
+            double get(const std::vector<double> &v, int a, int b) const {
+                size_t lo = 0, hi = i.size();
+                while (lo < hi) { const size_t mid = (lo + hi) / 2; if (i[mid] < a || (i[mid] == a && j[mid] < b)) lo = mid + 1; else hi = mid; }
+                return (lo < i.size() && i[lo] == a && j[lo] == b) ? v[lo] : 0.0;
+            } } P[2];
+        for (int w = 0; w < 2; w++) {
+            const int id = w ? seq_b_ : seq_a_;
+            const int64_t n = lb200_seq_pairs(ctx_->get(), id, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+            ctx_->check((int)std::min<int64_t>(n, 0));
+            P[w].i.resize((size_t)n + 1); P[w].j.resize((size_t)n + 1); P[w].p.resize((size_t)n + 1); P[w].p2.resize((size_t)n + 1);
+            lb200_seq_pairs(ctx_->get(), id, P[w].i.data(), P[w].j.data(), P[w].p.data(), P[w].p2.data(), &P[w].cutoff, &P[w].stacking);
+            P[w].i.resize((size_t)n); P[w].j.resize((size_t)n); P[w].p.resize((size_t)n); P[w].p2.resize((size_t)n);
+        }
+        const double p_expA = exp_prob < 0 ? 1.0 / (2.0 * alignment_.seqA_.size()) : exp_prob, p_expB = exp_prob < 0 ? 1.0 / (2.0 * alignment_.seqB_.size()) : exp_prob;
+        const bool stacking = P[0].stacking && P[1].stacking;
+        const double p_minMean = std::exp((std::log(P[0].cutoff) * 1 + std::log(P[1].cutoff) * 1) / (1 + 1));
+        const double p_penalty = p_minMean * 0.1;
+        auto consensus_probability = [&](double pA, double pB) {   // rna_data.cc:1550-1578: weighted geometric mean
+            pA = std::max(std::min(p_expA, p_penalty), pA);
+            pB = std::max(std::min(p_expB, p_penalty), pB);
+            return std::exp((std::log(pA) * 1 + std::log(pB) * 1) / (1 + 1));
+        };
+        const Alignment::edges_t edges = alignment_.alignment_edges(only_local);
+        sparse_t arc_probs;
+        for (size_t i = 0; i < edges.size(); i++)
+            for (size_t j = i + 1; j < edges.size(); j++) {
+                const auto &ei = edges[i], &ej = edges[j];
+                const bool gapA = ei.first <= 0 || ej.first <= 0, gapB = ei.second <= 0 || ej.second <= 0;
+                const double p = consensus_probability(gapA ? 0 : P[0].get(P[0].p, ei.first, ej.first), gapB ? 0 : P[1].get(P[1].p, ei.second, ej.second));
+                if (stacking) {
+                    const double st_p = consensus_probability(gapA ? 0 : P[0].get(P[0].p2, ei.first, ej.first), gapB ? 0 : P[1].get(P[1].p2, ei.second, ej.second));
+                    // with joint probabilities on both sides a pair is also kept for its stacked probability; the consensus object itself
+                    // never reports has_stacking (rna_data.cc:117), so neither "#STACK" nor the fourth column is written
+                    if ((p > p_minMean || st_p > p_minMean) && p != 0.0) arc_probs[std::make_pair(i + 1, j + 1)] = p;
+                } else if (p > p_minMean) arc_probs.insert(std::make_pair(std::make_pair(i + 1, j + 1), p));
+            }
+        auto format_prob = [](double prob) {   // rna_data.cc:1279-1304
+            std::ostringstream outd;
+            outd.precision(4);
+            outd << prob;
+            std::string t = outd.str();
+            if (t.length() > 4 + 4) { std::ostringstream outs; outs.setf(std::ios::scientific, std::ios::floatfield); outs.precision(3); outs << prob; t = outs.str(); }
+            const size_t pos = t.find("e-0");
+            if (pos != std::string::npos) t.replace(pos, 3, "e-");
+            return t;
+        };
+        out << "#PP 2.0" << std::endl << std::endl;
+        MultipleAlignment ma(alignment_, only_local);
+        ma.write(out, (size_t)-1, MultipleAlignment::FormatType::CLUSTAL);
+        out << std::endl << "#END" << std::endl;
+        out << std::endl << "#SECTION BASEPAIRS" << std::endl << std::endl << "#BPCUT " << format_prob(std::max(p_minMean, 0.0)) << std::endl;
+        out << std::endl;
+        for (const auto &x : arc_probs) {
+            if (!(x.second > 0.0)) continue;
+            out << x.first.first << " " << x.first.second << " " << format_prob(x.second);
+            out << std::endl;
+        }
+        out << std::endl << "#END" << std::endl;
+    }
 private:
     infty_score_t result_score() {
         int64_t sc = 0;

@@ -42,7 +42,7 @@ EXPORTS = [
     "lb200_prepare", "lb200_upload", "lb200_run", "lb200_last_kernel_ms", "lb200_last_h2d_bytes", "lb200_last_d2h_bytes", "lb200_last_dfill_ms", "lb200_last_dfill_launches", "lb200_last_launches", "lb200_envelope_stats", "lb200_pair_score", "lb200_get_scores",
     "lb200_pair_get_info", "lb200_pair_band", "lb200_pair_arcmatches", "lb200_pair_alignment", "lb200_upgma_newick",
     "lb200_run_pf", "lb200_pair_partition_function", "lb200_pair_arcmatch_pf", "lb200_run_pf_probs", "lb200_pair_arcmatch_probs",
-    "lb200_pair_basematch_probs", "lb200_pairs_add", "lb200_all_vs_all", "lb200_pair_cost", "lb200_shard_pairs", "lb200_seq_num_arcs", "lb200_seqs_add_pp", "lb200_last_dfill_kind", "lb200_rows_fallbacks", "lb200_release_device_cache", "lb200_run_normalized", "lb200_run_penalized", "lb200_shard_job", "lb200_pair_set_restriction", "lb200_run_pair_toplevel", "lb200_pair_add_restricted", "lb200_band_from_alignment", "lb200_seq_anchors", "lb200_seqs_copy", "lb200_set_ribosum_file",
+    "lb200_pair_basematch_probs", "lb200_pairs_add", "lb200_all_vs_all", "lb200_pair_cost", "lb200_shard_pairs", "lb200_seq_num_arcs", "lb200_seqs_add_pp", "lb200_last_dfill_kind", "lb200_rows_fallbacks", "lb200_release_device_cache", "lb200_run_normalized", "lb200_run_penalized", "lb200_shard_job", "lb200_pair_set_restriction", "lb200_run_pair_toplevel", "lb200_pair_add_restricted", "lb200_band_from_alignment", "lb200_seq_anchors", "lb200_seqs_copy", "lb200_set_ribosum_file", "lb200_seq_pairs",
 ]
 
 _lib = None
@@ -92,6 +92,8 @@ def load():
     lib.lb200_last_kernel_ms.argtypes = [vp]
     lib.lb200_last_kernel_ms.restype = C.c_double
     lib.lb200_shard_job.argtypes = [vp, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.lb200_seq_pairs.argtypes = [vp, C.c_int, ip, ip, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), ip]
+    lib.lb200_seq_pairs.restype = C.c_int64
     lib.lb200_seqs_copy.argtypes = [vp, vp]
     lib.lb200_set_ribosum_file.argtypes = [vp, C.c_char_p]
     lib.lb200_seq_anchors.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]

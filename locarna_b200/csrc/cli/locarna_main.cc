@@ -23,7 +23,7 @@ struct Opt { const char *name; int has_arg; int id; };
 enum {
     O_INDEL = 1000, O_INDEL_OPENING, O_RIBOSUM_FILE, O_USE_RIBOSUM, O_MATCH, O_MISMATCH, O_UNPAIRED_PENALTY, O_STRUCT_WEIGHT, O_EXP_PROB,
     O_TAU, O_EXCLUSION, O_STACKING, O_NEW_STACKING, O_STRUCT_LOCAL, O_SEQU_LOCAL, O_FREE_ENDGAPS, O_NORMALIZED, O_PENALIZED, O_WIDTH,
-    O_CLUSTAL, O_STOCKHOLM, O_PP, O_LOCAL_OUTPUT, O_LOCAL_FILE_OUTPUT, O_POS_OUTPUT, O_WRITE_STRUCTURE, O_MIN_PROB, O_MAX_BPS_LENGTH_RATIO,
+    O_CLUSTAL, O_STOCKHOLM, O_PP, O_UNUSED_PP_PLACEHOLDER, O_LOCAL_OUTPUT, O_LOCAL_FILE_OUTPUT, O_POS_OUTPUT, O_WRITE_STRUCTURE, O_MIN_PROB, O_MAX_BPS_LENGTH_RATIO,
     O_MAX_DIFF_AM, O_MAX_DIFF, O_MAX_DIFF_AT_AM, O_MIN_TRACE_PROB, O_NOLP, O_MAXBPSPAN, O_TEMPERATURE_ALIPF, O_CONSENSUS_STRUCTURE,
     O_WRITE_ARCMATCH_SCORES, O_KBEST, O_BETTER, O_MAX_DIFF_ALN, O_MAX_DIFF_PW_ALN, O_MAX_DIFF_RELAX, O_UNSUPPORTED, O_DEVICE, O_VERSION, O_QUIET, O_VERBOSE, O_HELP
 };
@@ -80,7 +80,7 @@ int main(int argc, char **argv) {
     bool struct_local = false, struct_local_given = false, sequ_local = false, sequ_local_given = false, normalized = false, penalized = false;
     long normalized_L = 0, position_penalty = 0, subopt_threshold = -1000000;
     bool subopt = false, max_diff_relax = false;
-    std::string max_diff_alignment_file, max_diff_pw_alignment;
+    std::string max_diff_alignment_file, max_diff_pw_alignment, pp_file;
     int kbest_k = -1;
     int c, idx = 0;
     while ((c = getopt_long(argc, argv, "i:m:M:s:e:t:E:w:Lp:D:d:PqvVh", longopts, &idx)) != -1) {
@@ -128,7 +128,8 @@ int main(int argc, char **argv) {
             case O_WRITE_ARCMATCH_SCORES: arcmatch_scores_file = optarg; break;
             case O_STACKING: sp.stacking = true; break;
             case O_NEW_STACKING: sp.new_stacking = true; break;
-            case O_PP:
+            case O_PP: pp_file = optarg; break;
+            case O_UNUSED_PP_PLACEHOLDER:
             case O_UNSUPPORTED:
                 std::cerr << "ERROR: option --" << (idx >= 0 && longopts[idx].name ? longopts[idx].name : "?")
                           << " selects a mode that locarna_b200 does not implement." << std::endl;
@@ -219,6 +220,11 @@ int main(int argc, char **argv) {
                 out << "# STOCKHOLM 1.0" << std::endl << "#=GF CC Generated by LocARNA 2.0.1" << std::endl << "#=GF SQ " << ma.num_of_rows() << std::endl << std::endl;
                 ma.write(out, width, MultipleAlignment::FormatType::STOCKHOLM);
             } else { std::cerr << "ERROR: Cannot write to " << stockholm << "." << std::endl; rc = 255; }
+        }
+        if (!pp_file.empty()) {                                                      // main_helper.icc:617-634: alignment + consensus dot plot
+            std::ofstream out(pp_file.c_str());
+            if (out.good()) aligner.write_pp(out, local_file_output, sp.exp_prob);
+            else { std::cerr << "ERROR: Cannot write to " << pp_file << std::endl; rc = 255; }
         }
         if (pos_output) {                                                           // locarna.cc:879-888
             const auto start = alignment.start_positions(), end = alignment.end_positions();

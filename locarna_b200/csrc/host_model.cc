@@ -131,6 +131,8 @@ bool read_pp(const std::string &path, double p_bpcut, Sequence &out, std::string
     if (!stack_keyword && any_p2) { err = "Stacking probabilties found but stack keyword is missing."; return false; }   // rna_data.cc:1097-1100
     // the pairs were already filtered line by line; pass a cutoff that keeps them all
     if (!make_sequence(name, seq, pi.data(), pj.data(), pp.data(), (int)pi.size(), -1.0, out, err, max_bp_span, max_bps_length_ratio, pp2.data())) return false;
+    out.cutoff = cut;                 // RnaData::arc_cutoff_prob(): the largest of the given cutoff and the file's #BPCUT lines
+    out.has_stacking = stack_keyword && stacking;
     return set_anchors(out, anchor_rows, err);
 }
 

@@ -51,6 +51,7 @@ struct Sequence {
     std::vector<double> pp_p;
     std::vector<double> pp_p2;         // joint probability of (i, j) and (i+1, j-1) (PP fourth column, rna_data.cc:1085-1093); 0: none
     double cutoff = 0;
+    bool has_stacking = false;         // RnaData::has_stacking(): the file carries joint probabilities and they were read
     // arcs with p >= min_prob in the reference's index order (left descending, right ascending)
     std::vector<Arc> arcs;
     std::vector<double> arc_prob;

@@ -435,6 +435,24 @@ int lb200_shard_job(const lb200_ctx *c, int64_t n_pairs, const int *seqA, const 
     return lb200_shard_pairs(n_pairs, cost.data(), world, rank_of, order, rank_begin);
 }
 
+// The base pairs the reader kept (RnaData::arc_prob > 0, rna_data.cc:1057-1093), sorted by (i, j): positions, probability, joint
+// probability with the inner pair (0 = none). Arrays of lb200_seq_pairs(ctx, seq, NULL, ..) entries; returns the count. cutoff_out:
+// RnaData::arc_cutoff_prob(); stacking_out: RnaData::has_stacking(). What a consensus dot plot (locarna --pp) is computed from.
+int64_t lb200_seq_pairs(const lb200_ctx *c, int seq, int *pi, int *pj, double *pp, double *pp2, double *cutoff_out, int *stacking_out) {
+    if (!c || seq < 0 || seq >= (int)c->seqs.size()) return LB200_ERR_ARG;
+    const Sequence &s = c->seqs[seq];
+    const size_t n = s.pp_i.size();
+    for (size_t k = 0; k < n; k++) {
+        if (pi) pi[k] = s.pp_i[k];
+        if (pj) pj[k] = s.pp_j[k];
+        if (pp) pp[k] = s.pp_p[k];
+        if (pp2) pp2[k] = k < s.pp_p2.size() ? s.pp_p2[k] : 0.0;
+    }
+    if (cutoff_out) *cutoff_out = s.cutoff;
+    if (stacking_out) *stacking_out = s.has_stacking ? 1 : 0;
+    return (int64_t)n;
+}
+
 // anchor annotation of a sequence as SequenceAnnotation::single_string gives it (rows joined by '#'; "" = none); returns the length needed
 int lb200_seq_anchors(const lb200_ctx *c, int seq, char *out, int cap) {
     if (!c || seq < 0 || seq >= (int)c->seqs.size()) return LB200_ERR_ARG;

@@ -184,3 +184,17 @@ def test_cli_ribosum_file(case, tmp_path):
     w = subprocess.run([CLI, case["A"], case["B"], "--write-arcmatch-scores", ams] + case["args"], capture_output=True, text=True, cwd=GOLD)
     assert w.returncode == 0, w.stderr
     assert open(ams).read() == case["arcmatch_scores"]
+
+
+CASES_PP = json.load(open(os.path.join(GOLD, "pp_outputs.json")))
+
+
+@pytest.mark.parametrize("case", CASES_PP, ids=lambda c: "%s-%s" % ("_".join(c["args"]) or "default", c["A"]))
+def test_cli_pp_output(case, tmp_path):
+    """--pp: the alignment with its consensus dot plot in PP 2.0 format (the hand-over to mlocarna's progressive stage; consensus
+    constructor of RnaData rna_data.cc:104-126 / :1474-1578, write_pp :1242-1350), byte-equal to the reference binary's file incl. the
+    order of the base pair lines (tools/make_golden_pp.py)."""
+    pp = str(tmp_path / "out.pp")
+    r = subprocess.run([CLI, case["A"], case["B"], "--pp", pp, "-q"] + case["args"], capture_output=True, text=True, cwd=GOLD)
+    assert r.returncode == case["rc"], r.stderr
+    assert open(pp).read() == case["pp"]
