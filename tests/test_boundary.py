@@ -8,7 +8,7 @@ import subprocess
 
 import pytest
 
-from golden_util import GOLD
+from golden_util import GOLD, out_dir, prefetch, run
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "locarna_b200", "bin", "locarna_refmain_b200")
@@ -52,14 +52,24 @@ def test_refmain_fails_loudly_without_a_device():
     assert r.returncode == 255 and "failed to read from file" in r.stderr      # the reference's own error text (locarna.cc:470-476)
 
 
+def _cmd(i, case):
+    return ([BIN, os.path.join(GOLD, case["A"]), os.path.join(GOLD, case["B"]), "--clustal", os.path.join(out_dir(), "refmain%d.aln" % i)] + case["args"], GOLD)
+
+
+@pytest.fixture(scope="module")
+def commands_started():
+    """All cases are started together, a few processes at a time (golden_util.prefetch)."""
+    if os.access(BIN, os.X_OK):
+        prefetch([_cmd(i, c) for i, c in enumerate(CASES)])
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", CASES, ids=lambda c: "%s-%s" % ("_".join(c["args"]) or "default", c["A"]))
-def test_refmain_output_matches_reference_binary(case, tmp_path):
+@pytest.mark.parametrize("i,case", list(enumerate(CASES)), ids=["%s-%s" % ("_".join(c["args"]) or "default", c["A"]) for c in CASES])
+def test_refmain_output_matches_reference_binary(i, case, commands_started):
     if not os.access(BIN, os.X_OK):
         pytest.skip("locarna_refmain_b200 not built (no reference tree at build time)")
-    clu = str(tmp_path / "out.aln")
-    r = subprocess.run([BIN, os.path.join(GOLD, case["A"]), os.path.join(GOLD, case["B"]), "--clustal", clu] + case["args"], capture_output=True, text=True, cwd=GOLD)
+    r = run(*_cmd(i, case))
     assert r.returncode == case["rc"], r.stderr
     assert r.stdout == case["stdout"]
     if case["rc"] == 0 and case["clustal"] is not None:
-        assert open(clu).read() == case["clustal"]
+        assert open(os.path.join(out_dir(), "refmain%d.aln" % i)).read() == case["clustal"]

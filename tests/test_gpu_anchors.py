@@ -7,7 +7,7 @@ import subprocess
 
 import pytest
 
-from golden_util import GOLD, digest, full_edges
+from golden_util import GOLD, digest, full_edges, out_dir, prefetch, run
 from locarna_b200 import capi
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -56,14 +56,26 @@ def test_anchors_match_reference(case, mode, monkeypatch):
     ctx.close()
 
 
+CLI_CASES = list(enumerate(CASES))[::3]
+
+
+def _cmd(i, case):
+    return ([CLI, case["A"], case["B"], "--clustal", os.path.join(out_dir(), "anchors%d.aln" % i)] + case["args"], GOLD)
+
+
+@pytest.fixture(scope="module")
+def commands_started():
+    """All CLI cases are started together, a few processes at a time (golden_util.prefetch)."""
+    prefetch([_cmd(i, c) for i, c in CLI_CASES])
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", CASES[::3], ids=IDS[::3])
-def test_cli_with_anchors(case, tmp_path):
-    clu = str(tmp_path / "out.aln")
-    r = subprocess.run([CLI, case["A"], case["B"], "--clustal", clu] + case["args"], capture_output=True, text=True, cwd=GOLD)
+@pytest.mark.parametrize("i,case", CLI_CASES, ids=IDS[::3])
+def test_cli_with_anchors(i, case, commands_started):
+    r = run(*_cmd(i, case))
     assert r.returncode == case["rc"], r.stderr
     assert r.stdout == case["stdout"]
-    assert open(clu).read() == case["clustal"]
+    assert open(os.path.join(out_dir(), "anchors%d.aln" % i)).read() == case["clustal"]
 
 
 @pytest.mark.gpu

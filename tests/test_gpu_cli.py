@@ -1,46 +1,120 @@
-"""The `locarna`-compatible command line front end against stdout / --clustal output of the reference's own binary."""
+"""The `locarna`-compatible command line front end against stdout / --clustal output of the reference's own binary.
+
+Every case is one process of the front end; the commands of the whole module are started together, a few at a time
+(golden_util.prefetch), and each test then checks the result of its own command."""
 import json
 import os
 import subprocess
 
 import pytest
 
-from golden_util import GOLD
+from golden_util import GOLD, out_dir, prefetch, run
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CLI = os.path.join(ROOT, "locarna_b200", "bin", "locarna_b200")
-CASES = json.load(open(os.path.join(GOLD, "reference_outputs.json")))["cli"]
+CLI_P = os.path.join(ROOT, "locarna_b200", "bin", "locarna_p_b200")
+CLI_TREE = os.path.join(ROOT, "locarna_b200", "bin", "mlocarna_tree_b200")
 
 
-@pytest.mark.parametrize("case", CASES, ids=lambda c: "%s-%s" % ("_".join(c["args"]) or "default", c["A"]))
-def test_cli_output_matches_reference(case, tmp_path):
-    clu = str(tmp_path / "out.aln")
-    r = subprocess.run([CLI, os.path.join(GOLD, case["A"]), os.path.join(GOLD, case["B"]), "--clustal", clu] + case["args"],
-                       capture_output=True, text=True)
+def _load(name):
+    return json.load(open(os.path.join(GOLD, name)))
+
+
+def _f(tag, i, ext):
+    """Output file of case i of the test family `tag` (fixed name: the command is started before the test runs)."""
+    return os.path.join(out_dir(), "%s%d.%s" % (tag, i, ext))
+
+
+CASES = list(enumerate(_load("reference_outputs.json")["cli"]))
+CASES_OPT = list(enumerate(_load("locarna_cli_options.json")))
+CASES_KBEST = list(enumerate(_load("kbest_outputs.json")))
+CASES_NORM = list(enumerate(_load("normalized_outputs.json")))
+CASES_P = list(enumerate(_load("locarna_p_cli.json")))
+CASES_REFALN = list(enumerate(_load("maxdiffaln_outputs.json")))
+CASES_RIBOSUM = list(enumerate(_load("ribosum_outputs.json")))
+CASES_PP = list(enumerate(_load("pp_outputs.json")))
+
+
+def _ab(case):
+    return [os.path.join(GOLD, case["A"]), os.path.join(GOLD, case["B"])]
+
+
+# the commands of each test family: (argv, cwd)
+def _cmd_plain(i, c):
+    return ([CLI] + _ab(c) + ["--clustal", _f("plain", i, "aln")] + c["args"], None)
+
+
+def _cmd_opt(i, c):
+    return ([CLI] + _ab(c) + ["--clustal", _f("opt", i, "aln"), "--stockholm", _f("opt", i, "sto")] + c["args"], None)
+
+
+def _cmd_opt_ams(i, c):
+    return ([CLI] + _ab(c) + ["--write-arcmatch-scores", _f("opt", i, "ams")] + c["args"], None)
+
+
+def _cmd_kbest(i, c):
+    return ([CLI] + _ab(c) + c["args"], None)
+
+
+def _cmd_norm(i, c):
+    return ([CLI] + _ab(c) + ["--clustal", _f("norm", i, "aln")] + c["args"], None)
+
+
+def _cmd_p(i, c):
+    return ([CLI_P] + _ab(c) + ["--write-arcmatch-probs", _f("p", i, "am"), "--write-basematch-probs", _f("p", i, "bm")] + c["args"], None)
+
+
+def _cmd_refaln(i, c):
+    return ([CLI, c["A"], c["B"]] + c["args"], GOLD)
+
+
+def _cmd_ribosum(i, c):
+    return ([CLI, c["A"], c["B"]] + c["args"], GOLD)
+
+
+def _cmd_ribosum_ams(i, c):
+    return ([CLI, c["A"], c["B"], "--write-arcmatch-scores", _f("ribosum", i, "ams")] + c["args"], GOLD)
+
+
+def _cmd_pp(i, c):
+    return ([CLI, c["A"], c["B"], "--pp", _f("pp", i, "pp"), "-q"] + c["args"], GOLD)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _all_commands_started():
+    jobs = []
+    for fn, cases in ((_cmd_plain, CASES), (_cmd_opt, CASES_OPT), (_cmd_opt_ams, CASES_OPT), (_cmd_kbest, CASES_KBEST), (_cmd_norm, CASES_NORM),
+                      (_cmd_p, CASES_P), (_cmd_refaln, CASES_REFALN), (_cmd_ribosum, CASES_RIBOSUM), (_cmd_pp, CASES_PP)):
+        jobs += [fn(i, c) for i, c in cases]
+    jobs += [_cmd_ribosum_ams(i, c) for i, c in CASES_RIBOSUM if c["rc"] == 0]
+    prefetch(jobs)
+
+
+def _ids(cases, cut=None):
+    return ["%s-%s" % ("_".join((x[:cut] if cut else x) for x in c["args"]) or "default", c["A"]) for _, c in cases]
+
+
+@pytest.mark.parametrize("i,case", CASES, ids=_ids(CASES))
+def test_cli_output_matches_reference(i, case):
+    r = run(*_cmd_plain(i, case))
     assert r.returncode == case["rc"], r.stderr
     assert r.stdout == case["stdout"]
-    assert open(clu).read() == case["clustal"]
+    assert open(_f("plain", i, "aln")).read() == case["clustal"]
 
 
-CASES_OPT = json.load(open(os.path.join(GOLD, "locarna_cli_options.json")))
-
-
-@pytest.mark.parametrize("case", CASES_OPT, ids=lambda c: "%s-%s" % ("_".join(c["args"]) or "default", c["A"]))
-def test_cli_exp_prob_maxbpspan_arcmatch_scores(case, tmp_path):
+@pytest.mark.parametrize("i,case", CASES_OPT, ids=_ids(CASES_OPT))
+def test_cli_exp_prob_maxbpspan_arcmatch_scores(i, case):
     """--exp-prob, --maxBPspan and --write-arcmatch-scores against the reference binary (tools/make_golden_cli_options.py)."""
-    clu, ams = str(tmp_path / "out.aln"), str(tmp_path / "out.ams")
-    a, b = os.path.join(GOLD, case["A"]), os.path.join(GOLD, case["B"])
-    sto = str(tmp_path / "out.sto")
-    r = subprocess.run([CLI, a, b, "--clustal", clu, "--stockholm", sto] + case["args"], capture_output=True, text=True)
+    r = run(*_cmd_opt(i, case))
     assert r.returncode == case["rc"], r.stderr
     assert r.stdout == case["stdout"]
-    assert open(clu).read() == case["clustal"]
-    assert open(sto).read() == case["stockholm"]
-    w = subprocess.run([CLI, a, b, "--write-arcmatch-scores", ams] + case["args"], capture_output=True, text=True)
+    assert open(_f("opt", i, "aln")).read() == case["clustal"]
+    assert open(_f("opt", i, "sto")).read() == case["stockholm"]
+    w = run(*_cmd_opt_ams(i, case))
     assert w.returncode == case["ams_rc"], w.stderr
     assert w.stdout == case["ams_stdout"]                      # writes the file and exits without aligning (locarna.cc:705-720)
-    assert open(ams).read() == case["arcmatch_scores"]
+    assert open(_f("opt", i, "ams")).read() == case["arcmatch_scores"]
 
 
 def test_cli_rejects_unimplemented_modes():
@@ -48,37 +122,26 @@ def test_cli_rejects_unimplemented_modes():
     assert r.returncode == 255 and "does not implement" in r.stderr
 
 
-CASES_KBEST = json.load(open(os.path.join(GOLD, "kbest_outputs.json")))
-
-
-@pytest.mark.parametrize("case", CASES_KBEST, ids=lambda c: "%s-%s" % ("_".join(c["args"]), c["A"]))
-def test_cli_kbest(case):
+@pytest.mark.parametrize("i,case", CASES_KBEST, ids=_ids(CASES_KBEST))
+def test_cli_kbest(i, case):
     """--kbest k / --better t: k-best alignments by interval splitting (Aligner::suboptimal, aligner.cc:1383-1514; restricted top levels
     on the resident D table) against the reference binary's stdout (tools/make_golden_kbest.py)."""
-    r = subprocess.run([CLI, os.path.join(GOLD, case["A"]), os.path.join(GOLD, case["B"])] + case["args"], capture_output=True, text=True)
+    r = run(*_cmd_kbest(i, case))
     assert r.returncode == case["rc"], r.stderr
     assert r.stdout == case["stdout"]
 
 
-CASES_NORM = json.load(open(os.path.join(GOLD, "normalized_outputs.json")))
-
-
-@pytest.mark.parametrize("case", CASES_NORM, ids=lambda c: "%s-%s" % ("_".join(c["args"]), c["A"]))
-def test_cli_normalized_penalized(case, tmp_path):
+@pytest.mark.parametrize("i,case", CASES_NORM, ids=_ids(CASES_NORM))
+def test_cli_normalized_penalized(i, case):
     """--normalized L (Dinkelbach iteration, aligner.cc:1522-1597) and --penalized PP (aligner.cc:1599-1622) against the reference binary:
     stdout (score + alignment), stderr of the rejected combinations and the clustal file (tools/make_golden_normalized.py)."""
-    clu = str(tmp_path / "out.aln")
-    r = subprocess.run([CLI, os.path.join(GOLD, case["A"]), os.path.join(GOLD, case["B"]), "--clustal", clu] + case["args"], capture_output=True, text=True)
+    r = run(*_cmd_norm(i, case))
     assert r.returncode == case["rc"], r.stderr
     assert r.stdout == case["stdout"]
     if case["rc"] != 0:
         assert r.stderr == case["stderr"]
     else:
-        assert open(clu).read() == case["clustal"]
-
-
-CLI_P = os.path.join(ROOT, "locarna_b200", "bin", "locarna_p_b200")
-CASES_P = json.load(open(os.path.join(GOLD, "locarna_p_cli.json")))
+        assert open(_f("norm", i, "aln")).read() == case["clustal"]
 
 
 def _close_lines(a: str, b: str, n_int: int) -> bool:
@@ -93,19 +156,14 @@ def _close_lines(a: str, b: str, n_int: int) -> bool:
     return True
 
 
-@pytest.mark.parametrize("case", CASES_P, ids=lambda c: "%s-%s" % ("_".join(c["args"]) or "default", c["A"]))
-def test_locarna_p_cli_matches_reference(case, tmp_path):
+@pytest.mark.parametrize("i,case", CASES_P, ids=_ids(CASES_P))
+def test_locarna_p_cli_matches_reference(i, case):
     """stdout and the probability files of the reference's own locarna_p binary (tests/golden/locarna_p_cli.json)."""
-    am, bm = str(tmp_path / "am"), str(tmp_path / "bm")
-    r = subprocess.run([CLI_P, os.path.join(GOLD, case["A"]), os.path.join(GOLD, case["B"]), "--write-arcmatch-probs", am, "--write-basematch-probs", bm]
-                       + case["args"], capture_output=True, text=True)
+    r = run(*_cmd_p(i, case))
     assert r.returncode == case["rc"], r.stderr
     assert r.stdout == case["stdout"]
-    assert _close_lines(open(am).read(), case["am"], 4)
-    assert _close_lines(open(bm).read(), case["bm"], 2)
-
-
-CLI_TREE = os.path.join(ROOT, "locarna_b200", "bin", "mlocarna_tree_b200")
+    assert _close_lines(open(_f("p", i, "am")).read(), case["am"], 4)
+    assert _close_lines(open(_f("p", i, "bm")).read(), case["bm"], 2)
 
 
 def test_mlocarna_tree_stage_archaea(tmp_path):
@@ -151,50 +209,39 @@ def test_mlocarna_tree_stage_shares_and_gpus(tmp_path):
     assert r1.returncode == 0 and r1.stdout == r0.stdout and r0.stdout
 
 
-CASES_REFALN = json.load(open(os.path.join(GOLD, "maxdiffaln_outputs.json")))
-
-
-@pytest.mark.parametrize("case", CASES_REFALN, ids=lambda c: "%s-%s" % ("_".join(x[:12] for x in c["args"]), c["A"]))
-def test_cli_reference_alignment_bands(case):
+@pytest.mark.parametrize("i,case", CASES_REFALN, ids=_ids(CASES_REFALN, 12))
+def test_cli_reference_alignment_bands(i, case):
     """--max-diff d with --max-diff-pw-aln / --max-diff-aln: band around a reference alignment (TraceController from a MultipleAlignment,
     trace_controller.cc:406-539), then the probability envelope inside it; stdout / error exits of the reference binary
     (tools/make_golden_maxdiffaln.py)."""
-    r = subprocess.run([CLI, case["A"], case["B"]] + case["args"], capture_output=True, text=True, cwd=GOLD)
+    r = run(*_cmd_refaln(i, case))
     assert r.returncode == case["rc"], r.stderr
     assert r.stdout == case["stdout"]
     if case["rc"] != 0:
         assert r.stderr == case["stderr"]
 
 
-CASES_RIBOSUM = json.load(open(os.path.join(GOLD, "ribosum_outputs.json")))
-
-
-@pytest.mark.parametrize("case", CASES_RIBOSUM, ids=lambda c: "%s-%s" % ("_".join(c["args"][1:]), c["A"]))
-def test_cli_ribosum_file(case, tmp_path):
+@pytest.mark.parametrize("i,case", CASES_RIBOSUM, ids=["%s-%s" % ("_".join(c["args"][1:]), c["A"]) for _, c in CASES_RIBOSUM])
+def test_cli_ribosum_file(i, case):
     """--ribosum-file with a matrix other than the built-in one (tests/golden/synthetic.ribosum, tools/make_golden_ribosum.py): base-match
     and arc-match score tables from the file (RibosumFreq, ribosum.cc:40-200, :324-331; scoring.cc:141-198, :369-438), stdout and the
     arc-match scores of the reference binary; a file that is not a ribosum matrix is refused with the reference's message."""
-    r = subprocess.run([CLI, case["A"], case["B"]] + case["args"], capture_output=True, text=True, cwd=GOLD)
+    r = run(*_cmd_ribosum(i, case))
     assert r.returncode == case["rc"], r.stderr
     assert r.stdout == case["stdout"]
     if case["rc"] != 0:
         assert r.stderr == case["stderr"]
         return
-    ams = str(tmp_path / "out.ams")
-    w = subprocess.run([CLI, case["A"], case["B"], "--write-arcmatch-scores", ams] + case["args"], capture_output=True, text=True, cwd=GOLD)
+    w = run(*_cmd_ribosum_ams(i, case))
     assert w.returncode == 0, w.stderr
-    assert open(ams).read() == case["arcmatch_scores"]
+    assert open(_f("ribosum", i, "ams")).read() == case["arcmatch_scores"]
 
 
-CASES_PP = json.load(open(os.path.join(GOLD, "pp_outputs.json")))
-
-
-@pytest.mark.parametrize("case", CASES_PP, ids=lambda c: "%s-%s" % ("_".join(c["args"]) or "default", c["A"]))
-def test_cli_pp_output(case, tmp_path):
+@pytest.mark.parametrize("i,case", CASES_PP, ids=_ids(CASES_PP))
+def test_cli_pp_output(i, case):
     """--pp: the alignment with its consensus dot plot in PP 2.0 format (the hand-over to mlocarna's progressive stage; consensus
     constructor of RnaData rna_data.cc:104-126 / :1474-1578, write_pp :1242-1350), byte-equal to the reference binary's file incl. the
     order of the base pair lines (tools/make_golden_pp.py)."""
-    pp = str(tmp_path / "out.pp")
-    r = subprocess.run([CLI, case["A"], case["B"], "--pp", pp, "-q"] + case["args"], capture_output=True, text=True, cwd=GOLD)
+    r = run(*_cmd_pp(i, case))
     assert r.returncode == case["rc"], r.stderr
-    assert open(pp).read() == case["pp"]
+    assert open(_f("pp", i, "pp")).read() == case["pp"]
