@@ -117,6 +117,16 @@ int lb200_seq_length(const lb200_ctx *ctx, int seq);
 /* name (at most name_cap-1 characters) and normalised sequence (length+1 bytes incl. NUL; LB200_ERR_ARG if sequence_cap is
  * smaller) of a sequence; either buffer may be NULL */
 int lb200_seq_get(const lb200_ctx *ctx, int seq, char *name, int name_cap, char *sequence, int sequence_cap);
+/* Profile input (the step after the guide tree, src/Utils/mlocarna:3660-3716): a PP 2.0 file whose sequence block holds an ALIGNMENT
+ * (several rows, gap symbol '-') with its consensus dot plot (MultipleAlignment / Sequence with several rows, sequence.hh:24-80).
+ * lb200_seq_add_pp reads it as one "sequence" whose length is the number of alignment columns. Pairs of a context that holds such
+ * an input are scored position by position as Scoring does for alignment columns (scoring.cc:141-198 averaged sigma, :272-311
+ * gap costs scaled by the gap frequency, :369-438 averaged ribosum arc-match score; stral_score.cc:29-44 for the envelope).
+ * Global alignment without free end gaps only; LocARNA-P, anchors, normalized / penalized / k-best are refused for such input.
+ * lb200_seq_num_rows: rows of the input (1 for a single sequence). lb200_seq_get_row: name and aligned string of one row (same buffer
+ * rules as lb200_seq_get). */
+int lb200_seq_num_rows(const lb200_ctx *ctx, int seq);
+int lb200_seq_get_row(const lb200_ctx *ctx, int seq, int row, char *name, int name_cap, char *sequence, int sequence_cap);
 
 /* Add one alignment problem (A = seqA, B = seqB). min_col/max_col (lenA+1 entries each) give the band
  * [min_col(i), max_col(i)] per row; pass NULL for both to have it derived like the reference does

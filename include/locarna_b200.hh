@@ -104,8 +104,17 @@ class Alignment {  // alignment.hh:84-281
     std::vector<std::pair<int, int>> edges_;  // position or -1 (gap), in order
     std::string strA_, strB_;                 // per position, '.', '(' or ')'
     std::vector<std::string> anchorsA_, anchorsB_;   // "#A<k>" annotation rows of the inputs (empty: none)
+    // all rows (name, aligned string) of the two inputs: one each for single sequences, several for profile input (Sequence with
+    // several rows, sequence.hh:24-80); nameA_ / seqA_ are row 0
+    std::vector<std::pair<std::string, std::string>> rowsA_, rowsB_;
 public:
     typedef std::vector<std::pair<int, int>> edges_t;
+    size_t num_rowsA() const { return rowsA_.empty() ? 1 : rowsA_.size(); }
+    size_t num_rowsB() const { return rowsB_.empty() ? 1 : rowsB_.size(); }
+    std::string row_nameA(size_t k) const { return rowsA_.empty() ? nameA_ : rowsA_[k].first; }
+    std::string row_nameB(size_t k) const { return rowsB_.empty() ? nameB_ : rowsB_[k].first; }
+    std::string rowA(size_t k, bool only_local) const { return project(rowsA_.empty() ? seqA_ : rowsA_[k].second, true, only_local); }
+    std::string rowB(size_t k, bool only_local) const { return project(rowsB_.empty() ? seqB_ : rowsB_[k].second, false, only_local); }
     const std::vector<std::string> &anchorsA() const { return anchorsA_; }
     const std::vector<std::string> &anchorsB() const { return anchorsB_; }
     // alignment_edges(only_local) (alignment.cc:120-167): locality gaps are reported as -3
@@ -193,9 +202,11 @@ public:
         throw failure("MultipleAlignment: no sequence " + name);
     }
     MultipleAlignment(const Alignment &a, bool only_local = false) {
-        const bool clash = a.nameA() == a.nameB();
-        rows_.emplace_back(clash ? "A." + a.nameA() : a.nameA(), a.rowA(only_local));
-        rows_.emplace_back(clash ? "B." + a.nameB() : a.nameB(), a.rowB(only_local));
+        // all rows of A, then all rows of B; "A." / "B." prefixes if a row name of A occurs in B (multiple_alignment.cc:184-247)
+        bool clash = false;
+        for (size_t k = 0; k < a.num_rowsA(); k++) for (size_t l = 0; l < a.num_rowsB(); l++) clash |= a.row_nameA(k) == a.row_nameB(l);
+        for (size_t k = 0; k < a.num_rowsA(); k++) rows_.emplace_back(clash ? "A." + a.row_nameA(k) : a.row_nameA(k), a.rowA(k, only_local));
+        for (size_t l = 0; l < a.num_rowsB(); l++) rows_.emplace_back(clash ? "B." + a.row_nameB(l) : a.row_nameB(l), a.rowB(l, only_local));
         // consensus anchor annotation (multiple_alignment.cc:157-165, sequence_annotation.cc:12-50): per column the name of the
         // non-gap side, of the named side, or the smaller of two names; dropped if a name would occur twice
         const auto &A = a.anchorsA(), &B = a.anchorsB();
@@ -384,6 +395,16 @@ public:
         seq = new char[seq_cap];
         ctx_->check(lb200_seq_get(ctx_->get(), a, name, sizeof name, seq, seq_cap)); alignment_.nameA_ = name; alignment_.seqA_ = seq;
         ctx_->check(lb200_seq_get(ctx_->get(), b, name, sizeof name, seq, seq_cap)); alignment_.nameB_ = name; alignment_.seqB_ = seq;
+        for (int which = 0; which < 2; which++) {   // rows of profile inputs (one row: a single sequence)
+            const int id = which ? b : a;
+            auto &rows = which ? alignment_.rowsB_ : alignment_.rowsA_;
+            const int nr = lb200_seq_num_rows(ctx_->get(), id);
+            ctx_->check(nr);
+            for (int k = 0; k < nr; k++) {
+                ctx_->check(lb200_seq_get_row(ctx_->get(), id, k, name, sizeof name, seq, seq_cap));
+                rows.emplace_back(std::string(name), std::string(seq));
+            }
+        }
         delete[] seq;
         for (int which = 0; which < 2; which++) {   // "#A<k>" rows of the inputs, for the consensus annotation of the output
             const int id = which ? b : a;
@@ -523,12 +544,13 @@ public:
         }
         const double p_expA = exp_prob < 0 ? 1.0 / (2.0 * alignment_.seqA_.size()) : exp_prob, p_expB = exp_prob < 0 ? 1.0 / (2.0 * alignment_.seqB_.size()) : exp_prob;
         const bool stacking = P[0].stacking && P[1].stacking;
-        const double p_minMean = std::exp((std::log(P[0].cutoff) * 1 + std::log(P[1].cutoff) * 1) / (1 + 1));
+        const size_t rowsA = alignment_.num_rowsA(), rowsB = alignment_.num_rowsB();   // weights of the two inputs (rna_data.cc:1482-1489)
+        const double p_minMean = std::exp((std::log(P[0].cutoff) * rowsA + std::log(P[1].cutoff) * rowsB) / (rowsA + rowsB));
         const double p_penalty = p_minMean * 0.1;
         auto consensus_probability = [&](double pA, double pB) {   // rna_data.cc:1550-1578: weighted geometric mean
             pA = std::max(std::min(p_expA, p_penalty), pA);
             pB = std::max(std::min(p_expB, p_penalty), pB);
-            return std::exp((std::log(pA) * 1 + std::log(pB) * 1) / (1 + 1));
+            return std::exp((std::log(pA) * rowsA + std::log(pB) * rowsB) / (rowsA + rowsB));
         };
         const Alignment::edges_t edges = alignment_.alignment_edges(only_local);
         sparse_t arc_probs;

@@ -43,6 +43,7 @@ EXPORTS = [
     "lb200_pair_get_info", "lb200_pair_band", "lb200_pair_arcmatches", "lb200_pair_alignment", "lb200_upgma_newick",
     "lb200_run_pf", "lb200_pair_partition_function", "lb200_pair_arcmatch_pf", "lb200_run_pf_probs", "lb200_pair_arcmatch_probs",
     "lb200_pair_basematch_probs", "lb200_pairs_add", "lb200_all_vs_all", "lb200_pair_cost", "lb200_shard_pairs", "lb200_seq_num_arcs", "lb200_seqs_add_pp", "lb200_last_dfill_kind", "lb200_rows_fallbacks", "lb200_release_device_cache", "lb200_run_normalized", "lb200_run_penalized", "lb200_shard_job", "lb200_pair_set_restriction", "lb200_run_pair_toplevel", "lb200_pair_add_restricted", "lb200_band_from_alignment", "lb200_seq_anchors", "lb200_seqs_copy", "lb200_set_ribosum_file", "lb200_seq_pairs",
+    "lb200_seq_num_rows", "lb200_seq_get_row",
 ]
 
 _lib = None
@@ -69,6 +70,8 @@ def load():
     lib.lb200_seq_length.argtypes = [vp, C.c_int]
     lib.lb200_seq_get.argtypes = [vp, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
     lib.lb200_seq_num_arcs.argtypes = [vp, C.c_int]
+    lib.lb200_seq_num_rows.argtypes = [vp, C.c_int]
+    lib.lb200_seq_get_row.argtypes = [vp, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
     lib.lb200_pairs_add.argtypes = [vp, C.c_int, ip, ip]
     lib.lb200_all_vs_all.argtypes = [C.c_int, ip, ip]
     lib.lb200_all_vs_all.restype = C.c_int64
@@ -226,6 +229,17 @@ class Context:
         buf = C.create_string_buffer(n + 1)
         self._chk(self.lib.lb200_seq_anchors(self.h, seq, buf, n + 1))
         return buf.value.decode()
+
+    def seq_rows(self, seq: int):
+        """(name, aligned string) of every row of a sequence (one row for a single sequence, several for a profile input)."""
+        n = self._chk(self.lib.lb200_seq_num_rows(self.h, seq))
+        length = self._chk(self.lib.lb200_seq_length(self.h, seq))
+        out = []
+        for k in range(n):
+            name, s = C.create_string_buffer(256), C.create_string_buffer(length + 1)
+            self._chk(self.lib.lb200_seq_get_row(self.h, seq, k, name, 256, s, length + 1))
+            out.append((name.value.decode(), s.value.decode()))
+        return out
 
     def seq_num_arcs(self, seq: int) -> int:
         return self._chk(self.lib.lb200_seq_num_arcs(self.h, seq))

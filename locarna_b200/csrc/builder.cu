@@ -40,6 +40,8 @@ struct PairView {
     const int *alB, *arB, *wB, *lpB, *lcB, *sdB;
     const uint8_t *cA, *cB;
     const uint8_t *acA, *acB;   // anchor ranks, nullptr without anchor constraints
+    const int *psam;            // profile pair: sequence term of the arc-match score per (a, b), row length nB; nullptr: by symbol codes
+    int nB;
     int n, m;
     long mdam, mdat;
 };
@@ -54,6 +56,7 @@ __device__ __forceinline__ PairView view(const BuildCtx &b, const DevPair &p) {
     v.cA = b.codes + p.codesA; v.cB = b.codes + p.codesB;
     v.acA = p.anchored ? b.acodes + p.codesA : nullptr; v.acB = p.anchored ? b.acodes + p.codesB : nullptr;
     v.n = p.lenA; v.m = p.lenB;
+    v.psam = (p.ps_am >= 0 && b.ps_am != nullptr) ? b.ps_am + p.ps_am : nullptr; v.nB = p.n_arcsB;
     const int mx = max(p.lenA, p.lenB);
     v.mdam = b.max_diff_am >= 0 ? b.max_diff_am : mx;      // locarna.cc:617-626
     v.mdat = b.max_diff_at_am >= 0 ? b.max_diff_at_am : mx;
@@ -76,6 +79,7 @@ __device__ __forceinline__ bool valid_arcmatch_right(const PairView &v, int al, 
 
 // scoring.cc:441-485 for single sequences
 __device__ __forceinline__ int arcmatch_score(const BuildCtx &b, const PairView &v, int a, int bb, int al, int ar, int bl, int br) {
+    if (v.psam != nullptr) return v.psam[(size_t)a * v.nB + bb] + v.wA[a] + v.wB[bb];   // profiles: scoring.cc:369-438, averaged on the host
     long seqc = 0;
     if (b.tau != 0) {
         const int c1 = v.cA[al], c2 = v.cA[ar], c3 = v.cB[bl], c4 = v.cB[br];

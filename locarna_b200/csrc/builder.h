@@ -16,6 +16,7 @@ struct BuildCtx {
     const int *arc_left, *arc_right, *arc_weight, *lptr, *lcount;
     const int *arc_sdelta;                      // per arc: stack weight - weight, LB_NOSTACK if the arc is not stackable
     const int *am_seq;                          // 256: (tau * ribosum arc-match score) / 100
+    const int *ps_am;                           // profile pairs (DevPair::ps_am >= 0): sequence term per (arc of A, arc of B)
     int sigma8[64];
     int tau, use_ribosum, no_lonely_pairs, struct_local, max_diff_am, max_diff_at_am;
     // outputs / work arrays

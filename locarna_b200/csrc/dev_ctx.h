@@ -9,6 +9,7 @@ struct DevCtx {
     DevParams params;
     const DevPair *pairs;
     const uint8_t *codes;
+    const int *ps_sig;       // position-specific base match scores of profile pairs (DevPair::ps_sig), nullptr: none
     const int *band_lo, *band_hi;
     const int *sptr;
     DevEntry *ent;           // S-order; ent[k].d = D(arcA,arcB)

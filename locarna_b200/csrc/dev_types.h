@@ -40,7 +40,11 @@ struct DevPair {
     long long cell_base;  // offset of this pair's cells in the cell arrays (cells ranked al desc, bl desc)
     long long am_base;    // offset of this pair's arc matches in the L-order / S-order arrays  (device builder)
     int anchored;         // 1: arc matches must join positions of equal anchor rank (acodes[], same offsets as codes[])
-    int pad;
+    int n_arcsB;          // arcs of B (row length of the profile arc-match table)
+    // profile (multi-row) inputs: position-specific scoring (scoring.cc:141-198, :272-311, :369-438) in the gap-free frame, see
+    // host_model.h ProfileTables. -1: single sequences, score tables by symbol code.
+    long long ps_sig;     // offset into DevCtx::ps_sig: (lenA+1) x (lenB+1) base match scores sigma'(i, j)
+    long long ps_am;      // offset into DevCtx::ps_am: arcs(A) x arcs(B) sequence terms of the arc-match scores
 };
 
 // per-pair counters produced by the device builder

@@ -64,7 +64,7 @@ bool read_pp(const std::string &path, double p_bpcut, Sequence &out, std::string
     if (!begins(line, "#PP 2")) { err = path + ": not in PP 2.0 format"; return false; }
     std::string name, seq;
     std::vector<std::string> anchor_rows;
-    bool named = false;
+    std::vector<std::string> row_names, rows;   // all rows of the sequence block, in order of first appearance (multiple_alignment.cc:279-401)
     while (next_line(in, line)) {
         if (line[0] == '#') {
             if (begins(line, "#END")) break;
@@ -82,10 +82,14 @@ bool read_pp(const std::string &path, double p_bpcut, Sequence &out, std::string
         std::istringstream ls(line);
         std::string n, s;
         ls >> n >> s;
-        if (!named) { name = n; named = true; }
-        else if (n != name) { err = path + ": alignments (several rows) are not supported by the B200 path yet"; return false; }
-        seq += s;
+        size_t k = 0;
+        while (k < row_names.size() && row_names[k] != n) k++;
+        if (k == row_names.size()) { row_names.push_back(n); rows.push_back(std::string()); }
+        rows[k] += s;
     }
+    if (rows.empty()) { err = path + ": no sequence in the PP input"; return false; }
+    for (const std::string &r : rows) if (r.size() != rows[0].size()) { err = "Rows of unequal length in the alignment of " + path; return false; }
+    name = row_names[0]; seq = rows[0];
     if (!next_line(in, line) || line != "#SECTION BASEPAIRS") { err = path + ": Expected base pair section header."; return false; }
     std::vector<int> pi, pj;
     std::vector<double> pp, pp2;
@@ -130,7 +134,14 @@ bool read_pp(const std::string &path, double p_bpcut, Sequence &out, std::string
     }
     if (!stack_keyword && any_p2) { err = "Stacking probabilties found but stack keyword is missing."; return false; }   // rna_data.cc:1097-1100
     // the pairs were already filtered line by line; pass a cutoff that keeps them all
-    if (!make_sequence(name, seq, pi.data(), pj.data(), pp.data(), (int)pi.size(), -1.0, out, err, max_bp_span, max_bps_length_ratio, pp2.data())) return false;
+    // (profile input: the symbol codes are not used, and gap symbols must not take one of the three free codes)
+    if (!make_sequence(name, rows.size() > 1 ? std::string(seq.size(), 'N') : seq, pi.data(), pj.data(), pp.data(), (int)pi.size(), -1.0, out, err, max_bp_span,
+                       max_bps_length_ratio, pp2.data())) return false;
+    if (rows.size() > 1) {            // profile input: keep all rows (normalised like the first one)
+        for (std::string &r : rows) for (auto &ch : r) { ch = (char)toupper((unsigned char)ch); if (ch == 'T') ch = 'U'; }
+        out.row_names = row_names; out.rows = rows; out.seq = rows[0];
+        out.codes.assign(out.len + 1, CODE_N);   // never scored by symbol code: profile pairs use position-specific tables
+    }
     out.cutoff = cut;                 // RnaData::arc_cutoff_prob(): the largest of the given cutoff and the file's #BPCUT lines
     out.has_stacking = stack_keyword && stacking;
     return set_anchors(out, anchor_rows, err);
@@ -332,9 +343,87 @@ int arcmatch_score(const ScoreTables &t, const Params &p, const Sequence &A, con
     return (int)(((long)p.tau * seqc) / 100) + wA[a] + wB[b];
 }
 
+// ---------------------------------------------------------------------------------- profile (multi-row) scoring
+static inline int acgu_index(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'U' ? 3 : -1; }   // the ribosum alphabet
+
+void make_profile_tables(const Sequence &A, const Sequence &B, const Params &p, ProfileTables &out) {
+    const int n = A.len, m = B.len, ra = A.num_rows(), rb = B.num_rows();
+    out = ProfileTables();
+    out.n = n; out.m = m; out.arcsA = (int)A.arcs.size(); out.arcsB = (int)B.arcs.size();
+    // Scoring::sigma_ (scoring.cc:141-198): sum over all row pairs of the rounded per-pair score, integer division by the number of
+    // row pairs ("-" against "-" counts as a match, N never counts); unpaired penalty as apply_unpaired_penalty (:64-74)
+    out.sigma.assign((size_t)(n + 1) * (m + 1), 0);
+    std::vector<int8_t> ia((size_t)ra * (n + 1)), ib((size_t)rb * (m + 1));
+    for (int k = 0; k < ra; k++) for (int i = 1; i <= n; i++) ia[(size_t)k * (n + 1) + i] = (int8_t)acgu_index(A.row(k)[i - 1]);
+    for (int l = 0; l < rb; l++) for (int j = 1; j <= m; j++) ib[(size_t)l * (m + 1) + j] = (int8_t)acgu_index(B.row(l)[j - 1]);
+    for (int i = 1; i <= n; i++)
+        for (int j = 1; j <= m; j++) {
+            long score = 0;
+            for (int k = 0; k < ra; k++) {
+                const char ca = A.row(k)[i - 1];
+                const int xa = ia[(size_t)k * (n + 1) + i];
+                for (int l = 0; l < rb; l++) {
+                    const char cb = B.row(l)[j - 1];
+                    const int xb = ib[(size_t)l * (m + 1) + j];
+                    if (p.use_ribosum && xa >= 0 && xb >= 0) score += p.ribosum.sigma4[xa * 4 + xb];
+                    else if (ca != 'N' && cb != 'N') score += (ca == cb) ? p.match : p.mismatch;
+                }
+            }
+            out.sigma[(size_t)i * (m + 1) + j] = (int)round2score((double)(score / (long)(ra * rb))) - 2 * p.unpaired_penalty;
+        }
+    // Scoring::precompute_gapcost (scoring.cc:272-311): gap frequencies in float, as there
+    auto gaps = [&](const Sequence &S, int len, int rows, std::vector<int> &g, std::vector<long> &P) {
+        g.assign(len + 1, 0); P.assign(len + 1, 0);
+        for (int i = 1; i <= len; i++) {
+            float f = 0;
+            for (int k = 0; k < rows; k++) f += (S.row(k)[i - 1] == '-') ? 1 : 0;
+            f /= rows;
+            g[i] = (int)round2score((1 - f) * p.indel) - p.unpaired_penalty;
+            P[i] = P[i - 1] + g[i];
+        }
+    };
+    gaps(A, n, ra, out.gapA, out.PA);
+    gaps(B, m, rb, out.gapB, out.PB);
+    // sequence contribution of Scoring::arcmatch (scoring.cc:441-485): riboX_arcmatch_score (:369-438) with a ribosum matrix,
+    // sigma of the two ends without one
+    out.am_seq.assign((size_t)out.arcsA * out.arcsB, 0);
+    if (p.tau != 0) {
+        for (int a = 0; a < out.arcsA; a++) {
+            const int al = A.arcs[a].left, ar = A.arcs[a].right;
+            for (int b = 0; b < out.arcsB; b++) {
+                const int bl = B.arcs[b].left, br = B.arcs[b].right;
+                long seqc;
+                if (p.use_ribosum) {
+                    double score = 0;
+                    int considered = 0;
+                    for (int k = 0; k < ra; k++) {
+                        const char a1 = A.row(k)[al - 1], a2 = A.row(k)[ar - 1];
+                        if (a1 == '-' || a2 == '-') continue;
+                        const int x1 = ia[(size_t)k * (n + 1) + al], x2 = ia[(size_t)k * (n + 1) + ar];
+                        for (int l = 0; l < rb; l++) {
+                            const char b1 = B.row(l)[bl - 1], b2 = B.row(l)[br - 1];
+                            if (b1 == '-' || b2 == '-') continue;
+                            const int y1 = ib[(size_t)l * (m + 1) + bl], y2 = ib[(size_t)l * (m + 1) + br];
+                            if (x1 < 0 || x2 < 0 || y1 < 0 || y2 < 0) continue;
+                            considered++;
+                            score += p.ribosum.amlog2[(x1 * 4 + x2) * 16 + y1 * 4 + y2];
+                        }
+                    }
+                    seqc = considered == 0 ? 0 : round2score(100.0 * score / considered);
+                } else {
+                    // sigma_tab of both ends; the tables carry the unpaired penalty like the reference's
+                    seqc = (long)out.sigma[(size_t)al * (m + 1) + bl] + out.sigma[(size_t)ar * (m + 1) + br];
+                }
+                out.am_seq[(size_t)a * out.arcsB + b] = (int)(((long)p.tau * seqc) / 100);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------- ribosum
 RibosumTables::RibosumTables() {
     memcpy(bm, RIBOSUM85_60_BM, sizeof bm); memcpy(sigma4, RIBOSUM85_60_SIGMA4, sizeof sigma4); memcpy(am16, RIBOSUM85_60_AM16, sizeof am16);
+    memcpy(amlog2, RIBOSUM85_60_AMLOG2, sizeof amlog2);
 }
 
 namespace {
@@ -396,8 +485,10 @@ bool read_ribosum_file(const std::string &path, RibosumTables &out, std::string 
             out.sigma4[a * 4 + b] = (int)round2score_d(100.0 * (log(f_match[a * 4 + b] / (f_nonstruct[a] * f_nonstruct[b])) / log(2)));
         }
     for (int x = 0; x < 16; x++)
-        for (int y = 0; y < 16; y++)   // scoring.cc:411-427 for one row per sequence
+        for (int y = 0; y < 16; y++) {   // scoring.cc:411-427 for one row per sequence
+            out.amlog2[x * 16 + y] = log(f_arcmatch[x * 16 + y] / (f_pair[x] * f_pair[y])) / log(2);
             out.am16[x * 16 + y] = (int)round2score_d(100.0 * (log(f_arcmatch[x * 16 + y] / (f_pair[x] * f_pair[y])) / log(2)) / 1);
+        }
     return true;
 }
 
@@ -563,6 +654,19 @@ struct EnvScore {
     uint8_t code(const Sequence &s, int i) const { return s.codes[rev ? s.len + 1 - i : i]; }
     double sigma(int i, int j) const {
         double seq_score = 0;
+        if (A->num_rows() > 1 || B->num_rows() > 1) {   // alignment columns: average over the row pairs of alphabet symbols (stral_score.cc:29-44)
+            const int pi = rev ? A->len + 1 - i : i, pj = rev ? B->len + 1 - j : j;
+            int pairs = 0;
+            for (int k = 0; k < A->num_rows(); k++) {
+                const int a = acgu_index(A->row(k)[pi - 1]);
+                for (int l = 0; l < B->num_rows(); l++) {
+                    const int b = acgu_index(B->row(l)[pj - 1]);
+                    if (a >= 0 && b >= 0) { seq_score += ribo ? ribo_bm[a * 4 + b] : (a == b ? match : mismatch); pairs++; }
+                }
+            }
+            if (pairs != 0) seq_score /= pairs;
+            return sw * (sqrt(down(*A, i) * down(*B, j)) + sqrt(up(*A, i) * up(*B, j))) + seq_score;
+        }
         const uint8_t a = code(*A, i), b = code(*B, j);
         if (a < 4 && b < 4) { seq_score += ribo ? ribo_bm[a * 4 + b] : (a == b ? match : mismatch); seq_score /= 1; }
         double res = sw * (sqrt(down(*A, i) * down(*B, j)) + sqrt(up(*A, i) * up(*B, j))) + seq_score;
@@ -669,7 +773,8 @@ void restrict_band_by_envelope(Band &band, const Sequence &A, const Sequence &B,
 // ---------------------------------------------------------------------------------- arc matches, tasks
 // arc_matches.cc:19-48 (validity), :130-188 (enumeration), :50-74 (inner arc matches), :313-355 (max right ends);
 // aligner.cc:660-732 (task = left end pair)
-void build_pair_problem(const Sequence &A, const Sequence &B, const Band &band, const Params &p, const ScoreTables &t, PairProblem &out, bool anchored) {
+void build_pair_problem(const Sequence &A, const Sequence &B, const Band &band, const Params &p, const ScoreTables &t, PairProblem &out, bool anchored,
+                        const ProfileTables *profile) {
     out = PairProblem();
     const int n = A.len, m = B.len;
     const std::vector<int> &lo = band.lo, &hi = band.hi;
@@ -700,7 +805,7 @@ void build_pair_problem(const Sequence &A, const Sequence &B, const Band &band, 
                     DevArcMatch x;
                     x.ends_a = (uint32_t)al | ((uint32_t)ar << 12);
                     x.ends_b = (uint32_t)bl | ((uint32_t)br << 12);
-                    x.score = arcmatch_score(t, p, A, B, a, b, wA, wB);
+                    x.score = profile != nullptr ? profile->am_seq[(size_t)a * profile->arcsB + b] + wA[a] + wB[b] : arcmatch_score(t, p, A, B, a, b, wA, wB);
                     x.spos = -1; x.inner = -1; x.score_st = LB_NOSTACK;   // host-only inspection: no stacked scores
                     out.am.push_back(x); out.am_a.push_back(a); out.am_b.push_back(b);
                 }

@@ -17,6 +17,7 @@ struct RibosumTables {
     double bm[16];
     int sigma4[16];
     int am16[256];
+    double amlog2[256];   // log2(P_arcmatch / (P_basepair P_basepair)) unrounded: profile inputs average it over row pairs (scoring.cc:369-438)
     RibosumTables();   // the built-in RIBOSUM85_60
 };
 // --ribosum-file: a matrix in the reference's extended ribosum format (RibosumFreq(filename), ribosum.cc:40-200)
@@ -65,7 +66,32 @@ struct Sequence {
     std::vector<std::string> anchor_rows;    // the annotation rows as read (each of length len); empty: no annotation
     std::vector<std::string> anchor_names;   // entries 0..len (0 unused); empty vector: no annotation
     std::vector<uint8_t> anchor_rank;        // entries 0..len
+    // profile input (an alignment with its consensus dot plot, as mlocarna's progressive stage passes it on): the rows of the
+    // alignment, each `len` columns long, gap symbol '-'. Single sequences have one row (rows may be empty: then it is `seq`).
+    std::vector<std::string> row_names, rows;
+    int num_rows() const { return rows.empty() ? 1 : (int)rows.size(); }
+    const std::string &row(int k) const { return rows.empty() ? seq : rows[(size_t)k]; }
 };
+
+// Position-specific score tables of a pair with profile input (Scoring::precompute_sigma / precompute_gapcost / riboX_arcmatch_score,
+// scoring.cc:141-198, :272-311, :369-438; unpaired penalty applied as scoring.cc:64-74).
+// The kernels run such a pair in the GAP-FREE FRAME: every alignment of the cells (al, bl)..(i, j) deletes or matches each row
+// al+1..i and inserts or matches each column bl+1..j exactly once, so subtracting gapA(i) and gapB(j) from every operation that
+// consumes row i / column j shifts all alignments of the same box by the same amount:
+//     sigma'(i, j) = sigma(i, j) - gapA(i) - gapB(j),   gap' = 0,   opening unchanged,
+//     arcmatch'(a, b) = arcmatch(a, b) - gapA(al) - gapA(ar) - gapB(bl) - gapB(br),
+//     M'(i, j) = M(i, j) - (PA[i] - PA[al]) - (PB[j] - PB[bl]),   D'(a, b) = D(a, b) - (PA[ar] - PA[al-1]) - (PB[br] - PB[bl-1])
+// with the prefix sums PA, PB of the gap costs. Maxima, ties and therefore scores and tracebacks are those of the original recurrences
+// (global alignment; a clamp at 0 or free end gaps would not commute with the shift and are refused for profile input).
+struct ProfileTables {
+    int n = 0, m = 0, arcsA = 0, arcsB = 0;
+    std::vector<int> sigma;          // (n+1) x (m+1), Scoring::basematch(i, j)
+    std::vector<int> gapA, gapB;     // Scoring::gapA(i), gapB(j), entries 1..len
+    std::vector<long> PA, PB;        // prefix sums of the gap costs, entries 0..len
+    std::vector<int> am_seq;         // arcsA x arcsB: (tau * sequence contribution) / 100 of Scoring::arcmatch
+    int sigma_shifted(int i, int j) const { return sigma[(size_t)i * (m + 1) + j] - (i >= 1 ? gapA[i] : 0) - (j >= 1 ? gapB[j] : 0); }
+};
+void make_profile_tables(const Sequence &A, const Sequence &B, const Params &p, ProfileTables &out);
 
 struct Band {
     int lenA = 0, lenB = 0;
@@ -118,7 +144,8 @@ struct PairProblem {
     uint64_t cells = 0;               // DP cell updates of all D-fill tasks + top level (reference count)
     uint64_t terms = 0;               // arc-match entries streamed by all boxes (S-order range of the box anti-diagonals)
 };
-void build_pair_problem(const Sequence &A, const Sequence &B, const Band &band, const Params &p, const ScoreTables &t, PairProblem &out, bool anchored = false);
+void build_pair_problem(const Sequence &A, const Sequence &B, const Band &band, const Params &p, const ScoreTables &t, PairProblem &out, bool anchored = false,
+                        const ProfileTables *profile = nullptr);
 
 }  // namespace lb200
 #endif

@@ -173,6 +173,8 @@ struct Sweep {
     int *ap;                 // &arcbuf[lane*NC]
     int *bp;                 // &box[u * stride + lane*NC]
     int ip0, jp0;            // row / column of slot 0 (generic borders only)
+    const int *psig;         // profile pairs (generic borders only): &sigma'(al, bl), row length pld; nullptr: scores by symbol code
+    int pld;
     bool st_ok;              // lane*NC < stride: this lane's slots lie inside the box row
 };
 
@@ -214,7 +216,10 @@ __device__ __forceinline__ void dp_step2(Sweep<NC> &S, const BoxInit &init, cons
         const uint32_t w = S.w[k];
         const uint32_t z = S.K0[k] - w - (PAR ? 4095u : 0u);
         const bool ok = (~z & ROWW_GUARDS) == 0;
-        const int sg = *(const int *)((const char *)sig + (w >> 24) + S.cc[k]);
+        int sg = *(const int *)((const char *)sig + (w >> 24) + S.cc[k]);
+        if (GB) {   // position-specific base match score of a profile pair (valid cells lie inside the box: 0 <= ip <= Rn, 0 <= jp <= Cn)
+            if (S.psig != nullptr) sg = ok ? __ldg(S.psig + (S.ip0 - k) * S.pld + (S.jp0 + k)) : 0;
+        }
         int e = addmax(e_up, gap, m_up + gap_open);
         int f = addmax(f_left, gap, m_left + gap_open);
         const int a = arc[k];
@@ -368,6 +373,8 @@ __device__ void fill_box(const DevCtx &c, const DevPair &pr, const BoxGeom &g, c
     S.ap = ws.arcbuf + lane * NC;
     S.bp = box + stride + lane * NC;     // row u = 1
     S.ip0 = U2 - lane * NC; S.jp0 = J2 + lane * NC;
+    S.psig = (GB && c.ps_sig != nullptr && pr.ps_sig >= 0) ? c.ps_sig + pr.ps_sig + (long long)g.al * (pr.lenB + 1) + g.bl : nullptr;
+    S.pld = pr.lenB + 1;
     S.st_ok = lane * NC < stride;
 #pragma unroll
     for (int k = 0; k < NC; k++) {
@@ -953,6 +960,7 @@ __global__ void __launch_bounds__(32) trace_kernel(DevCtx c, int pair_begin, int
         const int n = pr.lenA, m = pr.lenB;
         const int *lo = c.band_lo + pr.band, *hi = c.band_hi + pr.band;
         const uint8_t *ca = c.codes + pr.codesA, *cb = c.codes + pr.codesB;
+        const int *psig = (c.ps_sig != nullptr && pr.ps_sig >= 0) ? c.ps_sig + pr.ps_sig : nullptr;   // profile pair: sigma'(i, j) table
         const DevEntry *ent = c.ent + pr.am_base;
         const DevArcMatch *am = c.am + pr.am_base;
         const unsigned *lpos = c.lpos + pr.am_base;
@@ -1009,7 +1017,8 @@ __global__ void __launch_bounds__(32) trace_kernel(DevCtx c, int pair_begin, int
                     break;
                 }
                 const bool vdiag = valid(i - 1, j - 1);
-                if (vdiag && mij == box_get(box, g, i - 1 - al, j - 1 - bl) + PW.sigma8[ca[i] * LB_NCODES + cb[j]]) {   // :1099-1105
+                const int sg_ij = psig != nullptr ? __ldg(psig + (long long)i * (m + 1) + j) : PW.sigma8[ca[i] * LB_NCODES + cb[j]];
+                if (vdiag && mij == box_get(box, g, i - 1 - al, j - 1 - bl) + sg_ij) {   // :1099-1105
                     emit(i, j, LB_EDGE_MATCH);
                     i--; j--;
                     continue;

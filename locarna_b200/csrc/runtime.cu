@@ -13,7 +13,7 @@
 #include <string>
 #include <thread>
 #include <map>
-#include <mutex>
+#include <memory>
 #include <vector>
 
 #include "../../include/locarna_b200.h"
@@ -150,6 +150,7 @@ struct PairRec {
     bool anchored = false;       // both sequences carry anchor names: band restricted and arc matches filtered by them
     bool band_initial = false;   // band given by the caller is the range BEFORE the probability envelope (reference alignment, anchors)
     bool restricted = false; int r_sa = 1, r_sb = 1, r_ea = 0, r_eb = 0;   // AlignerRestriction of the top level (k-best)
+    std::shared_ptr<ProfileTables> prof;   // position-specific score tables (contexts with profile input)
 };
 
 }  // namespace
@@ -201,6 +202,10 @@ struct lb200_ctx {
     int max_box_words = 1, max_len = 1;
     DevBuf d_acodes, d_pairs, d_codes, d_band_lo, d_band_hi, d_sptr, d_ent, d_am, d_tasks, d_top, d_scratch, d_cursor, d_flag, d_levcnt, d_done, d_ent8;
     DevBuf d_ent_mod, d_ent8_mod;   // D view of the modified scoring (normalized / penalized alignment)
+    DevBuf d_ps_sig, d_ps_am;       // profile pairs: sigma'(i, j) tables and arc-match sequence terms (host_model.h ProfileTables)
+    // profile mode: some sequence of the context is an alignment (several rows). All pairs are then scored position by position
+    // (which for two single sequences gives the same numbers as the tables by symbol code).
+    bool profile_mode() const { for (const Sequence &s : seqs) if (s.num_rows() > 1) return true; return false; }
     DevBuf d_col_first, d_col_last, d_groups, d_gorder, d_ngroups, d_rows_scratch, d_row_built, d_clist, d_cnblk;   // row-grouped D fill
     int pack_entries = 1;  // 8-byte packed S-order copy for the single-state sweep when every sequence is <= LB_PACK_MAXLEN (LB200_PACK=0 disables)
     int dfill_mode = 2;   // 2: automatic (row-grouped kernel where it applies), 3: row-grouped or fail (LB200_DFILL=rows), 1: dependency-driven persistent launch of single boxes (LB200_DFILL=dep), 0: one launch per level group (LB200_DFILL=levels)
@@ -208,7 +213,7 @@ struct lb200_ctx {
     int64_t rows_fallbacks = 0;   // chunks that were re-run box by box because the row-grouped kernel met an unsupported box
     int sb_pairs = 1 << 30;   // pair block of the dependency-driven order (LB200_SB_PAIRS; default: one block)
     ~lb200_ctx() {
-        DevBuf *all[] = {&d_acodes, &d_pairs, &d_codes, &d_band_lo, &d_band_hi, &d_sptr, &d_ent, &d_am, &d_tasks, &d_top, &d_scratch, &d_cursor, &d_flag, &d_levcnt, &d_done, &d_ent8,
+        DevBuf *all[] = {&d_ps_sig, &d_ps_am, &d_acodes, &d_pairs, &d_codes, &d_band_lo, &d_band_hi, &d_sptr, &d_ent, &d_am, &d_tasks, &d_top, &d_scratch, &d_cursor, &d_flag, &d_levcnt, &d_done, &d_ent8,
                          &d_ent_mod, &d_ent8_mod, &d_col_first, &d_col_last, &d_groups, &d_gorder, &d_ngroups, &d_rows_scratch, &d_row_built, &d_clist, &d_cnblk,
                          &d_arc_left, &d_arc_right, &d_arc_weight, &d_arc_sdelta, &d_lptr, &d_lcount, &d_am_seq, &d_cell_rev, &d_cell_start, &d_skeys, &d_skeys2,
                          &d_svals, &d_svals2, &d_tasks_unsorted, &d_tkeys, &d_tkeys2, &d_tvals, &d_tvals2, &d_ntasks, &d_qstart, &d_stats, &d_tmp, &d_tr_edges, &d_tr_str, &d_tr_stack,
@@ -463,6 +468,25 @@ int lb200_seq_anchors(const lb200_ctx *c, int seq, char *out, int cap) {
     return (int)str.size();
 }
 
+int lb200_seq_num_rows(const lb200_ctx *c, int seq) {
+    if (!c || seq < 0 || seq >= (int)c->seqs.size()) return LB200_ERR_ARG;
+    return c->seqs[seq].num_rows();
+}
+
+int lb200_seq_get_row(const lb200_ctx *c, int seq, int row, char *name, int name_cap, char *sequence, int sequence_cap) {
+    if (!c || seq < 0 || seq >= (int)c->seqs.size()) return LB200_ERR_ARG;
+    const Sequence &s = c->seqs[seq];
+    if (row < 0 || row >= s.num_rows()) return LB200_ERR_ARG;
+    const std::string &nm = s.rows.empty() ? s.name : s.row_names[(size_t)row];
+    const std::string &str = s.row(row);
+    if (name && name_cap > 0) { strncpy(name, nm.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+    if (sequence) {
+        if (sequence_cap < (int)str.size() + 1) return LB200_ERR_ARG;
+        memcpy(sequence, str.c_str(), str.size() + 1);
+    }
+    return LB200_OK;
+}
+
 int lb200_seq_get(const lb200_ctx *c, int seq, char *name, int name_cap, char *sequence, int sequence_cap) {
     if (!c || seq < 0 || seq >= (int)c->seqs.size()) return LB200_ERR_ARG;
     if (name && name_cap > 0) { strncpy(name, c->seqs[seq].name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
@@ -638,6 +662,19 @@ static int derive_bands(lb200_ctx *c) {
             if (!given || r.band_initial) { r.band = b; r.band_initial = true; }   // a final band given by the caller is kept as it is
         }
     }
+    const bool ps = c->profile_mode();
+    if (ps) {
+        const Params &q = c->params;
+        if (q.sequ_local || q.struct_local || q.fe_left1 || q.fe_left2 || q.fe_right1 || q.fe_right2)
+            return fail(c, LB200_ERR_UNSUPPORTED, "profile (multi-row) input is supported for global alignment without free end gaps only");
+        if (any_names) return fail(c, LB200_ERR_UNSUPPORTED, "anchor constraints with profile (multi-row) input are not supported");
+        parallel_for(P, c->host_threads, [&](int k) {
+            PairRec &r = c->pairs[k];
+            if (r.prof) return;
+            r.prof = std::make_shared<ProfileTables>();
+            make_profile_tables(c->seqs[r.seqA], c->seqs[r.seqB], c->params, *r.prof);
+        });
+    }
     std::vector<int> todo;
     for (int k = 0; k < P; k++) {
         PairRec &r = c->pairs[k];
@@ -649,7 +686,7 @@ static int derive_bands(lb200_ctx *c) {
     if (todo.empty()) return LB200_OK;
     const bool envelope = c->params.min_trace_probability > 0.0;
     std::vector<char> on_host(todo.size(), 1);
-    if (envelope && c->device != LB200_DEVICE_NONE && c->env_mode == 1) {
+    if (envelope && c->device != LB200_DEVICE_NONE && c->env_mode == 1 && !ps) {   // (profile columns: host envelope, stral_score.cc:29-44)
         { const int rc = upload_sequences(c); if (rc != LB200_OK) return rc; }
         cudaStream_t st = c->stream;
         std::vector<EnvPair> ep(todo.size());
@@ -743,7 +780,7 @@ int lb200_prepare(lb200_ctx *c) {
     parallel_for(P, c->host_threads, [&](int k) {
         PairRec &r = c->pairs[k];
         if (r.built) return;
-        build_pair_problem(c->seqs[r.seqA], c->seqs[r.seqB], r.band, c->params, c->tables, r.prob, r.anchored);
+        build_pair_problem(c->seqs[r.seqA], c->seqs[r.seqB], r.band, c->params, c->tables, r.prob, r.anchored, r.prof.get());
         r.K = (int)r.prob.am.size();
         r.stats.n_tasks = (long long)r.prob.tasks.size(); r.stats.cells = (long long)r.prob.cells; r.stats.terms = (long long)r.prob.terms;
         r.built = true;
@@ -787,6 +824,7 @@ static int upload_chunk(lb200_ctx *c, int p0, int p1) {
                 d.codesA = c->seq_codes_off[r.seqA]; d.codesB = c->seq_codes_off[r.seqB];
                 d.arcsA = c->seq_arcs_off[r.seqA]; d.arcsB = c->seq_arcs_off[r.seqB];
                 d.lptrA = c->seq_lptr_off[r.seqA]; d.lptrB = c->seq_lptr_off[r.seqB];
+                d.n_arcsB = (int)c->seqs[r.seqB].arcs.size(); d.ps_sig = -1; d.ps_am = -1;
                 std::copy(r.band.lo.begin(), r.band.lo.end(), h_lo.begin() + d.band);
                 std::copy(r.band.hi.begin(), r.band.hi.end(), h_hi.begin() + d.band);
                 // cells (al, bl), al >= 1, bl >= 1, ranked al descending / bl descending; diagonal bound of any box
@@ -842,6 +880,30 @@ static int upload_chunk(lb200_ctx *c, int p0, int p1) {
     DevCtx dc;
     memset(&dc, 0, sizeof dc);
     dc.params = c->tables.dev;
+    const bool ps = c->profile_mode();
+    if (ps) {
+        // profile pairs run in the gap-free frame (host_model.h ProfileTables): sigma'(i, j) and the arc-match sequence terms from
+        // tables, gap extension 0
+        dc.params.gap = 0; dc.params.gap_open = dc.params.open;
+        std::vector<int> h_sig, h_am;
+        for (int k = 0; k < P; k++) {
+            const PairRec &r = c->pairs[p0 + k];
+            if (!r.prof) return fail(c, LB200_ERR_STATE, "profile tables missing (lb200_prepare not run for pair %d)", p0 + k);
+            const ProfileTables &T = *r.prof;
+            const Sequence &A = c->seqs[r.seqA], &B = c->seqs[r.seqB];
+            DevPair &d = h_pairs[k];
+            d.ps_sig = (long long)h_sig.size(); d.ps_am = (long long)h_am.size();
+            for (int i = 0; i <= T.n; i++) for (int j = 0; j <= T.m; j++) h_sig.push_back(T.sigma_shifted(i, j));
+            for (int a = 0; a < T.arcsA; a++)
+                for (int bb = 0; bb < T.arcsB; bb++)
+                    h_am.push_back(T.am_seq[(size_t)a * T.arcsB + bb] - T.gapA[A.arcs[a].left] - T.gapA[A.arcs[a].right] - T.gapB[B.arcs[bb].left] - T.gapB[B.arcs[bb].right]);
+        }
+        if (h_am.empty()) h_am.push_back(0);
+        CUDA_TRY(c, upload(c->d_ps_sig, h_sig, st));
+        CUDA_TRY(c, upload(c->d_ps_am, h_am, st));
+        dc.ps_sig = (const int *)c->d_ps_sig.p;
+        c->last_h2d_bytes += (int64_t)((h_sig.size() + h_am.size()) * 4);
+    }
     dc.max_rows = max_rows;
     dc.rowcode_bytes = (max_rows + 2 + 3) & ~3;
     dc.colcode_bytes = (max_cols + 1 + 3) & ~3;
@@ -882,6 +944,7 @@ static int upload_chunk(lb200_ctx *c, int p0, int p1) {
     b.band_lo = (const int *)c->d_band_lo.p; b.band_hi = (const int *)c->d_band_hi.p; b.cell_rev = (const int *)c->d_cell_rev.p;
     b.arc_left = (const int *)c->d_arc_left.p; b.arc_right = (const int *)c->d_arc_right.p; b.arc_weight = (const int *)c->d_arc_weight.p; b.arc_sdelta = (const int *)c->d_arc_sdelta.p;
     b.lptr = (const int *)c->d_lptr.p; b.lcount = (const int *)c->d_lcount.p; b.am_seq = (const int *)c->d_am_seq.p;
+    b.ps_am = ps ? (const int *)c->d_ps_am.p : nullptr;
     memcpy(b.sigma8, c->tables.dev.sigma8, sizeof b.sigma8);
     b.tau = c->params.tau; b.use_ribosum = c->params.use_ribosum; b.no_lonely_pairs = c->params.no_lonely_pairs; b.struct_local = c->params.struct_local;
     b.max_diff_am = c->params.max_diff_am; b.max_diff_at_am = c->params.max_diff_at_am;
@@ -927,7 +990,7 @@ static int upload_chunk(lb200_ctx *c, int p0, int p1) {
     const int n_levels = std::max(1, (max_rows + max_cols) >> 1);
     // row-grouped kernel (dfill_rows.cu): single-state boxes of packed batches whose borders fall out of the recurrence and whose
     // anti-diagonals cross at most ~60 band columns; everything else runs box by box (kernels.cu)
-    const bool rows = !sl && pack && c->params.indel_opening <= 0 && n_tasks > 0 && max_active <= 58 && (c->dfill_mode == 2 || c->dfill_mode == 3);
+    const bool rows = !sl && !ps && pack && c->params.indel_opening <= 0 && n_tasks > 0 && max_active <= 58 && (c->dfill_mode == 2 || c->dfill_mode == 3);
     if (c->dfill_mode == 3 && !rows) return fail(c, LB200_ERR_UNSUPPORTED, "LB200_DFILL=rows: this batch is not eligible for the row-grouped kernel (max active columns %d)", max_active);
     const bool dep = !sl && !rows && (c->dfill_mode == 1 || (c->dfill_mode >= 2 && (long long)n_tasks * 2 >= (long long)grid_cap * n_levels));
     b.levcnt = nullptr; b.n_groups = ((max_rows + max_cols) >> 1) + 2; b.sb_pairs = c->sb_pairs;
@@ -1139,13 +1202,13 @@ static int run_chunk(lb200_ctx *c, int flags) {
     } else if (dc.dep_order != nullptr) {   // one persistent launch, tasks ordered by their own dependencies
         CUDA_TRY(c, cudaMemsetAsync(c->d_done.p, 0, (size_t)P * sizeof(int), st));
         if (dc.n_tasks > 0) {
-            launch_dfill_dep(dc, R.nc_inst, c->params.indel_opening > 0, std::min(R.grid_cap, dc.n_tasks), R.smem_bytes, (int *)c->d_cursor.p + 4097, st);
+            launch_dfill_dep(dc, R.nc_inst, c->params.indel_opening > 0 || dc.ps_sig != nullptr, std::min(R.grid_cap, dc.n_tasks), R.smem_bytes, (int *)c->d_cursor.p + 4097, st);
             dfill_launches = 1;
         }
     } else {
         for (int q = R.q_lo; q <= R.q_hi; q++) {
             if (c->params.struct_local) launch_dfill_sl(dc, R.grid_cap, R.smem_bytes, q, st);
-            else launch_dfill(dc, R.nc_inst, c->params.indel_opening > 0, R.grid_cap, R.smem_bytes, q, st);
+            else launch_dfill(dc, R.nc_inst, c->params.indel_opening > 0 || dc.ps_sig != nullptr, R.grid_cap, R.smem_bytes, q, st);
             dfill_launches++;
         }
     }
@@ -1155,7 +1218,7 @@ static int run_chunk(lb200_ctx *c, int flags) {
     launches++;
     if (do_trace) {
         if (c->params.struct_local) launch_trace_sl(dc, std::min(R.grid_cap, P), R.smem_bytes, 0, P, (int *)c->d_cursor.p + 4099, st);
-        else launch_trace(dc, R.nc_inst, c->params.indel_opening > 0, std::min(R.grid_cap, P), R.smem_bytes, 0, P, (int *)c->d_cursor.p + 4099, st);
+        else launch_trace(dc, R.nc_inst, c->params.indel_opening > 0 || dc.ps_sig != nullptr, std::min(R.grid_cap, P), R.smem_bytes, 0, P, (int *)c->d_cursor.p + 4099, st);
         launches++;
     }
     CUDA_TRY(c, cudaGetLastError());
@@ -1190,6 +1253,7 @@ static int run_chunk(lb200_ctx *c, int flags) {
         PairRec &r = c->pairs[p0 + k];
         r.neg_inf = h_top[k].score < LB_NEG_LIMIT;
         r.score = r.neg_inf ? 0 : h_top[k].score;
+        if (r.prof && !r.neg_inf) r.score += r.prof->PA[r.prof->n] + r.prof->PB[r.prof->m];   // back from the gap-free frame: M(n, m) = M'(n, m) + PA[n] + PB[m]
         r.max_i = h_top[k].max_i; r.max_j = h_top[k].max_j;
         r.edges_a.clear(); r.edges_b.clear(); r.str_a.clear(); r.str_b.clear();
         if (do_trace) {
@@ -1271,6 +1335,7 @@ cudaError_t lb200_adjust_d(const DevEntry *ent, DevEntry *ent_mod, uint2 *ent8_m
 static int run_modified(lb200_ctx *c, int mode, int64_t arg, int pair, bool do_trace) {
     const bool normalized = mode == 1;
     if (c->device == LB200_DEVICE_NONE) return fail(c, LB200_ERR_CUDA, "host-only context: needs a CUDA device (no CPU fallback)");
+    if (c->profile_mode()) return fail(c, LB200_ERR_UNSUPPORTED, "normalized, penalized and restricted (k-best) alignment are not supported for profile (multi-row) input");
     if (c->params.struct_local) return fail(c, LB200_ERR_UNSUPPORTED, normalized ? "Normalized structure local alignment not supported." : mode == 2 ? "penalized structure local alignment is not supported" : "restricted structure local alignment is not supported");
     if (normalized && !c->params.sequ_local) return fail(c, LB200_ERR_ARG, "Cannot run normalized alignment without --sequ_local on.");   // locarna.cc:431-436
     const int P = (int)c->pairs.size();
@@ -1400,6 +1465,7 @@ int lb200_run_pf(lb200_ctx *c, double pf_scale) {
     if (c->params.no_lonely_pairs || c->params.struct_local || c->params.sequ_local)
         return fail(c, LB200_ERR_UNSUPPORTED, "LocARNA-P (AlignerP) has no noLP / struct-local / sequ-local mode");
     if (!(pf_scale > 0)) return fail(c, LB200_ERR_ARG, "pf_scale must be positive");
+    if (c->profile_mode()) return fail(c, LB200_ERR_UNSUPPORTED, "LocARNA-P with profile (multi-row) input is not supported");
     for (const Sequence &s : c->seqs) if (!s.anchor_names.empty()) return fail(c, LB200_ERR_UNSUPPORTED, "LocARNA-P with anchor constraints is not supported");
     CUDA_TRY(c, cudaSetDevice(c->device));
     const int P = (int)c->pairs.size();
@@ -1594,8 +1660,16 @@ int lb200_pair_arcmatches(const lb200_ctx *cc, int pair, int *al, int *ar, int *
         if (ar) ar[k] = x.ends_a >> 12;
         if (bl) bl[k] = x.ends_b & 0xfff;
         if (br) br[k] = x.ends_b >> 12;
-        if (score) score[k] = x.score;
-        if (D) { const int d = dvals[x.spos].d; D[k] = d < LB_NEG_LIMIT ? LB200_SCORE_NEG_INF : d; }
+        // profile pairs on the device hold scores in the gap-free frame (host_model.h ProfileTables): shift back
+        long shift_s = 0, shift_d = 0;
+        if (r.prof && c->device != LB200_DEVICE_NONE) {
+            const ProfileTables &T = *r.prof;
+            const int xal = x.ends_a & 0xfff, xar = x.ends_a >> 12, xbl = x.ends_b & 0xfff, xbr = x.ends_b >> 12;
+            shift_s = (long)T.gapA[xal] + T.gapA[xar] + T.gapB[xbl] + T.gapB[xbr];
+            shift_d = (T.PA[xar] - T.PA[xal - 1]) + (T.PB[xbr] - T.PB[xbl - 1]);
+        }
+        if (score) score[k] = x.score + (int)shift_s;
+        if (D) { const int d = dvals[x.spos].d; D[k] = d < LB_NEG_LIMIT ? LB200_SCORE_NEG_INF : d + shift_d; }
     }
     return LB200_OK;
 }

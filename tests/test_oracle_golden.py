@@ -79,3 +79,21 @@ def test_port_probs_p_matches_reference_fixture():
         ref_bm = {(x[0], x[1]): x[2] for x in case["bm_probs"]}
         assert set(bm) == set(ref_bm), case["A"]
         assert all(abs(bm[k] - ref_bm[k]) <= 1e-12 * ref_bm[k] for k in ref_bm)
+
+
+@pytest.mark.parametrize("pair", [("g0.pp", "g1.pp"), ("g2.pp", "g3.pp"), ("st0.pp", "st1.pp")])
+@pytest.mark.parametrize("flags", [{}, {"noLP": True}, {"indel-opening": 0}, {"max-diff": 12}, {"no-ribosum": True, "indel-opening": -300}, {"tau": 0}])
+def test_gap_free_frame_is_score_and_trace_preserving(pair, flags, monkeypatch):
+    """The product runs profile pairs in the gap-free frame (locarna_b200/csrc/host_model.h ProfileTables: gap costs moved into the base
+    match and arc-match scores, gap extension 0). The restatement, run with position-dependent gap costs once as the reference computes
+    and once in that frame (Scoring::to_gap_free_frame), must give the same score, the same D for every arc match and the same trace."""
+    import os
+    from oracle import oracle as O
+    from golden_util import GOLD
+    a, b = os.path.join(GOLD, pair[0]), os.path.join(GOLD, pair[1])
+    monkeypatch.setenv("LOCARNA_PORT_TEST_GAPS", "1")
+    plain = O.port_align(a, b, flags)
+    monkeypatch.setenv("LOCARNA_PORT_GAP_FREE_FRAME", "1")
+    framed = O.port_align(a, b, flags)
+    assert plain["am_score"] == framed["am_score"]
+    assert plain["score"] == framed["score"] and plain["D"] == framed["D"] and plain["edges"] == framed["edges"]
