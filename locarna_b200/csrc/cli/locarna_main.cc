@@ -205,7 +205,10 @@ int main(int argc, char **argv) {
             std::ofstream out(clustal.c_str());
             if (out.good()) {
                 MultipleAlignment ma(alignment, local_file_output);
-                out << "CLUSTAL W --- LocARNA 2.0.1 --- Score: " << score << std::endl << std::endl;
+                out << "CLUSTAL W --- LocARNA 2.0.1";
+                // "for legacy, clustal files of pairwise alignments contain the score" (main_helper.icc:562-568): not for profile input
+                if (alignment.num_rowsA() == 1 && alignment.num_rowsB() == 1) out << " --- Score: " << score;
+                out << std::endl << std::endl;
                 if (write_structure) {
                     ma.prepend(MultipleAlignment::SeqEntry("", alignment.dot_bracket_structureA(local_file_output)));
                     ma.append(MultipleAlignment::SeqEntry("", alignment.dot_bracket_structureB(local_file_output)));

@@ -66,7 +66,9 @@ static int run_and_report() {
         std::ofstream out(clp.clustal_out.c_str());
         if (out.good()) {
             LocARNA_B200::MultipleAlignment ma(alignment, clp.local_file_output);
-            out << "CLUSTAL W --- LocARNA 2.0.1 --- Score: " << score << std::endl << std::endl;
+            out << "CLUSTAL W --- LocARNA 2.0.1";
+            if (alignment.num_rowsA() == 1 && alignment.num_rowsB() == 1) out << " --- Score: " << score;   // main_helper.icc:562-568
+            out << std::endl << std::endl;
             if (clp.write_structure) {
                 ma.prepend(LocARNA_B200::MultipleAlignment::SeqEntry("", alignment.dot_bracket_structureA(clp.local_file_output)));
                 ma.append(LocARNA_B200::MultipleAlignment::SeqEntry("", alignment.dot_bracket_structureB(clp.local_file_output)));
