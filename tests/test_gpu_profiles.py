@@ -28,6 +28,32 @@ def test_profile_rows_are_read():
     ctx.close()
 
 
+@pytest.mark.parametrize("flags", [{}, {"noLP": True, "max-diff": 12}, {"no-ribosum": True, "indel-opening": 0}, {"tau": 0, "min-prob": 0.01}])
+def test_position_specific_tables_of_single_sequences_equal_the_tables_by_symbol(flags):
+    """A context that holds a profile scores ALL its pairs position by position. For two single sequences that must give what the
+    tables by symbol code give: same band, same arc matches, same scores."""
+    plain = capi.Context(capi.DEVICE_NONE, flags)
+    plain.add_pair(plain.add_pp(os.path.join(GOLD, "g2.pp")), plain.add_pp(os.path.join(GOLD, "g3.pp")))
+    plain.prepare()
+    mixed = capi.Context(capi.DEVICE_NONE, flags)
+    mixed.add_pp(os.path.join(GOLD, "prof_a.pp"))
+    mixed.add_pair(mixed.add_pp(os.path.join(GOLD, "g2.pp")), mixed.add_pp(os.path.join(GOLD, "g3.pp")))
+    mixed.prepare()
+    assert plain.band(0) == mixed.band(0)
+    assert plain.arcmatches(0) == mixed.arcmatches(0) and len(plain.arcmatches(0)[0]) > 0
+    plain.close(); mixed.close()
+
+
+def test_profile_input_is_refused_where_the_frame_does_not_hold():
+    """Local alignment and free end gaps do not commute with the gap-free frame of the profile path: refused when the bands are derived."""
+    for flags in ({"sequ-local": True}, {"struct-local": True}, {"free-endgaps": "+---"}):
+        ctx = capi.Context(capi.DEVICE_NONE, flags)
+        ctx.add_pair(ctx.add_pp(os.path.join(GOLD, "prof_a.pp")), ctx.add_pp(os.path.join(GOLD, "g4.pp")))
+        with pytest.raises(capi.Error, match="profile .* input is supported for global alignment"):
+            ctx.prepare()
+        ctx.close()
+
+
 @pytest.mark.parametrize("case", CASES, ids=IDS)
 def test_profile_band_and_arc_match_scores_on_the_host(case):
     """Host mirror (no GPU): band after the envelope over alignment columns and the arc-match list with the averaged scores."""
