@@ -415,6 +415,9 @@ public:
             for (const char *p = buf.data(); ; p++) { if (*p == '#' || *p == 0) { if (!cur.empty()) rows.push_back(cur); cur.clear(); if (*p == 0) break; } else cur += *p; }
         }
         if (ap.ref_aln_ != nullptr && ap.max_diff_ != -1) {
+            // (for profile input the reference merges the trace ranges of all row pairs, trace_controller.cc:426-511: not built)
+            if (alignment_.num_rowsA() > 1 || alignment_.num_rowsB() > 1)
+                throw failure("a band around a reference alignment (--max-diff-aln / --max-diff-pw-aln) is not supported for profile (multi-row) input");
             // TraceController(seqA, seqB, ma, delta): rows within delta of the reference alignment (trace_controller.cc:431-483); the
             // probability envelope is applied inside this range
             std::vector<int> lo((size_t)la + 1), hi((size_t)la + 1);
