@@ -10,7 +10,7 @@ consensus dot plot, written by `--pp`) further up - with
 exactly as mlocarna calls its pairwise aligner; the alignment of the root is copied to results/result.aln and results/result.pp.
 Intermediate files are named as mlocarna names them (lib/perl/MLocarna.pm:104-131: "intermediate", "intermediate-1", ...).
 Each step is one profile-profile / profile-sequence alignment on the GPU; consensus dot plots are the averaged ones
-(`--consensus-structure none`), the RNAalifold-based variant of stock mlocarna needs ViennaRNA and is out of scope.
+(`--consensus-structure none`, what mlocarna passes by default), the optional RNAalifold-based variant needs ViennaRNA: out of scope.
 
     python -m locarna_b200.progressive --treefile T --input-dir DIR --tgtdir OUT [--dry-run] [-- locarna flags]
 """
