@@ -25,7 +25,7 @@ enum {
     O_TAU, O_EXCLUSION, O_STACKING, O_NEW_STACKING, O_STRUCT_LOCAL, O_SEQU_LOCAL, O_FREE_ENDGAPS, O_NORMALIZED, O_PENALIZED, O_WIDTH,
     O_CLUSTAL, O_STOCKHOLM, O_PP, O_UNUSED_PP_PLACEHOLDER, O_LOCAL_OUTPUT, O_LOCAL_FILE_OUTPUT, O_POS_OUTPUT, O_WRITE_STRUCTURE, O_MIN_PROB, O_MAX_BPS_LENGTH_RATIO,
     O_MAX_DIFF_AM, O_MAX_DIFF, O_MAX_DIFF_AT_AM, O_MIN_TRACE_PROB, O_NOLP, O_MAXBPSPAN, O_TEMPERATURE_ALIPF, O_CONSENSUS_STRUCTURE,
-    O_WRITE_ARCMATCH_SCORES, O_KBEST, O_BETTER, O_MAX_DIFF_ALN, O_MAX_DIFF_PW_ALN, O_MAX_DIFF_RELAX, O_UNSUPPORTED, O_DEVICE, O_VERSION, O_QUIET, O_VERBOSE, O_HELP
+    O_WRITE_ARCMATCH_SCORES, O_KBEST, O_BETTER, O_MAX_DIFF_ALN, O_MAX_DIFF_PW_ALN, O_MAX_DIFF_RELAX, O_UNSUPPORTED, O_MATCHPROB_PARAM, O_DEVICE, O_VERSION, O_QUIET, O_VERBOSE, O_HELP
 };
 bool parse_bool(const char *s) {
     const std::string v = s ? s : "";  // options.cc:867-880
@@ -62,6 +62,11 @@ int main(int argc, char **argv) {
         {"read-match-probs", required_argument, 0, O_UNSUPPORTED}, {"write-match-probs", required_argument, 0, O_UNSUPPORTED},
         {"read-arcmatch-scores", required_argument, 0, O_UNSUPPORTED}, {"read-arcmatch-probs", required_argument, 0, O_UNSUPPORTED},
         {"write-trace-probs", required_argument, 0, O_UNSUPPORTED},
+        // parameters of the base-match probability computation (locarna.cc:236-246): they only act in MEA mode / --write-match-probs, which
+        // are refused above; mlocarna passes them on when the user sets them (mlocarna:1181-1218). Listed so that "--temperature" is not
+        // taken for an abbreviation of --temperature-alipf.
+        {"temperature", required_argument, 0, O_MATCHPROB_PARAM}, {"pf-struct-weight", required_argument, 0, O_MATCHPROB_PARAM},
+        {"probcons-file", required_argument, 0, O_MATCHPROB_PARAM},
         {"alifold-consensus-dp", no_argument, 0, O_UNSUPPORTED}, {"ribofit", required_argument, 0, O_UNSUPPORTED},
         {"relaxed-anchors", no_argument, 0, O_UNSUPPORTED}, {"score-components", no_argument, 0, O_UNSUPPORTED},
         {"extended-pf", no_argument, 0, O_UNSUPPORTED}, {"quad-pf", no_argument, 0, O_UNSUPPORTED},
@@ -129,6 +134,7 @@ int main(int argc, char **argv) {
             case O_STACKING: sp.stacking = true; break;
             case O_NEW_STACKING: sp.new_stacking = true; break;
             case O_PP: pp_file = optarg; break;
+            case O_MATCHPROB_PARAM: break;
             case O_UNUSED_PP_PLACEHOLDER:
             case O_UNSUPPORTED:
                 std::cerr << "ERROR: option --" << (idx >= 0 && longopts[idx].name ? longopts[idx].name : "?")
