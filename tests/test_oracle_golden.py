@@ -97,3 +97,20 @@ def test_gap_free_frame_is_score_and_trace_preserving(pair, flags, monkeypatch):
     framed = O.port_align(a, b, flags)
     assert plain["am_score"] == framed["am_score"]
     assert plain["score"] == framed["score"] and plain["D"] == framed["D"] and plain["edges"] == framed["edges"]
+
+
+PROFILE_CASES = __import__("json").load(open(os.path.join(GOLD, "profiles_outputs.json")))
+
+
+@pytest.mark.parametrize("case", PROFILE_CASES, ids=["%s-%s-%s" % (c["A"], c["B"], "_".join(c["args"]) or "default") for c in PROFILE_CASES])
+def test_port_profile_input_matches_reference_fixture(case):
+    """Profile (multi-row) input: the port's scoring of alignment columns (scoring.cc:141-198, :272-311, :369-438; stral_score.cc:29-44)
+    against the compiled reference (tests/golden/profiles_outputs.json, tools/make_golden_profiles.py): band, arc matches with scores,
+    every D, score and alignment edges."""
+    r = O.port_align(os.path.join(GOLD, case["A"]), os.path.join(GOLD, case["B"]), case["flags"])
+    assert r["min_col"] == case["min_col"] and r["max_col"] == case["max_col"]
+    am_rows = [list(x[:4]) + [s, d] for x, s, d in zip(r["am"], r["am_score"], r["D"])]
+    assert len(am_rows) == case["n_am"] and am_rows[:5] == case["am_head"]
+    assert digest(am_rows) == case["am_sha256"]
+    assert r["score"] == case["score"]
+    assert full_edges(r["edges"], r["lenA"], r["lenB"]) == case["edges_full"]
